@@ -1,0 +1,382 @@
+// Persistent, warp-specialised bf16 GEMM on tcgen05 tensor cores with TMEM accumulators and a fused epilogue.
+//
+//   C[M,N] = epilogue( A . B^T )      A: [M,K] (K-major) or [K,M] (MN-major),  B: [N,K] or [K,N]
+//
+// One CTA per SM, 256 threads:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, STAGES-deep mbarrier ring)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers)
+//   warp 2      TMEM allocator (2 accumulator stages x BN columns)
+//   warps 4-7   epilogue       (tcgen05.ld -> bias / activation / residual -> 16-byte global stores)
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile
+// i+1 -- at K = 256 (the ViT width) the epilogue is as long as the mainloop, so this overlap is what
+// keeps the tensor pipe busy.  Tiles are scheduled n-fastest so CTAs that share an A row-block run
+// together and re-read it from L2, not HBM.
+//
+// Replaces: every nn.Linear on the ViT path (reference vit.py:29-32, :52-57, :112), the HF q/k/v/dense
+// layers (vit_hg.py via transformers), the RND fully-connected layers and im2col'ed convolutions
+// (model.py:368-416), and all of their backward GEMMs (dX = dY W, dW = dY^T X via MN-major operands).
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace eavit {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmKernelParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int m_tiles, n_tiles, splits, kb_per_split, kb_total;
+  const float* bias;
+  const __nv_bfloat16* aux;
+  const float* residual;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  __nv_bfloat16* out_pre;
+  long long ldc;
+  int act;
+  int atomic_f32;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;    // power of two >= 32 for BN in {64,128,256}
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float a) {
+  switch (act) {
+    case EAVIT_ACT_GELU: return gelu_erf(v);
+    case EAVIT_ACT_GELU_BWD: return v * gelu_erf_grad(a);
+    case EAVIT_ACT_LRELU: return v > 0.f ? v : 0.01f * v;
+    case EAVIT_ACT_LRELU_BWD: return a > 0.f ? v : 0.01f * v;
+    case EAVIT_ACT_RELU: return fmaxf(v, 0.f);
+    case EAVIT_ACT_RELU_BWD: return a > 0.f ? v : 0.f;
+    default: return v;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmKernelParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]   TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES]   MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;         // [2]        MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;    // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles, split = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          tc::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!p.a_mn) {
+            tc::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tc::tma_load_2d(sa + i * 8192, &tmA, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+          }
+          if (!p.b_mn) {
+            tc::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tc::tma_load_2d(sb + i * 8192, &tmB, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        tc::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          // K-major:  rows of 128 B, 8-row groups 1024 B apart (SBO); K advance = 32 B inside the swizzle atom.
+          // MN-major: 64-element (128 B) MN chunks, 8 k-rows per 1024 B (SBO), MN blocks 8192 B apart (LBO);
+          //           K advance = 16 k-rows = 2048 B.
+          const uint64_t a_desc = p.a_mn ? tc::make_sdesc_sw128(sa, 8192, 1024) : tc::make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t b_desc = p.b_mn ? tc::make_sdesc_sw128(sb, 8192, 1024) : tc::make_sdesc_sw128(sb, 16, 1024);
+          const uint32_t a_step = p.a_mn ? (2048 >> 4) : (32 >> 4);
+          const uint32_t b_step = p.b_mn ? (2048 >> 4) : (32 >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            tc::mma_bf16_ss(d_tmem, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
+                            (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc::mma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit(&acc_full[acc]);               // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =====================================
+    const int q = warp & 3;                           // TMEM lane quadrant owned by this warp
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
+      tc::mbar_wait(&acc_full[acc], acc_phase);
+      tc::fence_after_sync();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const size_t row_off = (size_t)row * (size_t)p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;                        // warp-uniform
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tc::tmem_ld_wait();
+        if (row_ok) {
+          const int ncols = min(32, p.N - col0);       // multiple of 8
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (p.out_pre != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                uint4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(p.out_pre + row_off + col0 + j) = o;
+              }
+            }
+          }
+          if (p.act != EAVIT_ACT_NONE) {
+            const bool need_aux = (p.act == EAVIT_ACT_GELU_BWD || p.act == EAVIT_ACT_LRELU_BWD || p.act == EAVIT_ACT_RELU_BWD);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (need_aux) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col0 + j));
+                  float2 t;
+                  t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
+                  t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
+                  t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
+                  t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[j + i] = apply_act(v[j + i], p.act, a[i]);
+              }
+            }
+          }
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.residual + row_off + col0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            if (p.atomic_f32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) atomicAdd(p.out_f32 + row_off + col0 + j, v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (j < ncols)
+                  *reinterpret_cast<float4*>(p.out_f32 + row_off + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+          if (p.out_bf16 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                uint4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(p.out_bf16 + row_off + col0 + j) = o;
+              }
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || p == nullptr) {
+      set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map, 128-byte swizzle: dims {inner, outer}, box {64, box_outer}
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                      uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return EAVIT_ECUDA;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d (base %p inner %llu outer %llu pitch %llu box %u)", (int)r, base,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes, box_outer);
+    return EAVIT_ECUDA;
+  }
+  return EAVIT_OK;
+}
+
+template <int BN>
+static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a->a_mn) rc = make_tmap_bf16_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BM);
+  else          rc = make_tmap_bf16_2d(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64);
+  if (rc) return rc;
+  if (!a->b_mn) rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, BN);
+  else          rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64);
+  if (rc) return rc;
+
+  GemmKernelParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = a->a_mn; p.b_mn = a->b_mn;
+  p.m_tiles = cdiv(a->M, BM);
+  p.n_tiles = cdiv(a->N, BN);
+  p.kb_total = cdiv(a->K, BK);
+  int splits = a->split_k > 0 ? a->split_k : 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = cdiv(p.kb_total, splits);
+  p.splits = cdiv(p.kb_total, p.kb_per_split);
+  p.bias = a->bias;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux_bf16);
+  p.residual = a->residual;
+  p.out_f32 = a->out_f32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  p.out_pre = reinterpret_cast<__nv_bfloat16*>(a->out_pre_bf16);
+  p.ldc = a->ldc;
+  p.act = a->act;
+  p.atomic_f32 = a->atomic_f32;
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+}  // namespace eavit
+
+using namespace eavit;
+
+extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
+  EAVIT_CHECK_ARG(a != nullptr);
+  EAVIT_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0);
+  EAVIT_CHECK_ARG(a->A != nullptr && a->B != nullptr);
+  EAVIT_CHECK_ARG(a->N % 8 == 0);
+  EAVIT_CHECK_ARG((a->lda * 2) % 16 == 0 && (a->ldb * 2) % 16 == 0 && a->ldc % 8 == 0);
+  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0);
+  EAVIT_CHECK_ARG(a->out_f32 != nullptr || a->out_bf16 != nullptr || a->out_pre_bf16 != nullptr);
+  EAVIT_CHECK_ARG(a->split_k <= 1 || (a->atomic_f32 && a->out_f32 != nullptr && a->out_bf16 == nullptr &&
+                                      a->out_pre_bf16 == nullptr && a->act == EAVIT_ACT_NONE && a->residual == nullptr));
+  const bool need_aux = (a->act == EAVIT_ACT_GELU_BWD || a->act == EAVIT_ACT_LRELU_BWD || a->act == EAVIT_ACT_RELU_BWD);
+  EAVIT_CHECK_ARG(!need_aux || a->aux_bf16 != nullptr);
+  EAVIT_CHECK_ARG(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->N > 128) return launch_gemm<256>(a, st);
+  if (a->N > 64) return launch_gemm<128>(a, st);
+  return launch_gemm<64>(a, st);
+}

@@ -1,0 +1,532 @@
+// Normalisation / GAE / reward-filter kernels: HBM- or latency-bound integer/float work, parallel over
+// envs and pixels, vectorised 16-byte loads, warp-shuffle reductions.  No tensor cores here by design.
+//
+// Reference arithmetic restated (file:line relative to the reference root):
+//   utils.py:42-67   make_train_data      -> gae_f64_kernel / gae_f32_scan_kernel
+//   utils.py:83-115  RunningMeanStd       -> rms_partial_kernel + rms_merge_kernel
+//   train.py:666,855 obs normalise + clip -> obs_normalize_kernel
+//   utils.py:118-128 + train.py:736-743   -> reward_filter_kernel, scale_kernel
+//   agents.py:216    intrinsic reward MSE -> intrinsic_mse_kernel
+#include "common.cuh"
+
+namespace eavit {
+
+// ------------------------------------------------------------------------------------------------
+// GAE, float64 emulation of numpy's promotion (bit-exact contract)
+// ------------------------------------------------------------------------------------------------
+constexpr int GAE_TC = 128;      // time-chunk staged in shared memory per warp
+constexpr int GAE_WARPS = 4;
+
+template <int KIND>
+__global__ void __launch_bounds__(GAE_WARPS * 32) gae_f64_kernel(const void* __restrict__ reward_,
+                                                                const uint8_t* __restrict__ done,
+                                                                const float* __restrict__ value,
+                                                                double* __restrict__ ret, double* __restrict__ adv,
+                                                                int E, int T, double gamma, double lam) {
+  __shared__ double s_r[GAE_WARPS][GAE_TC];
+  __shared__ double s_out[GAE_WARPS][GAE_TC];
+  __shared__ float s_v[GAE_WARPS][GAE_TC + 1];
+  __shared__ float s_nd[GAE_WARPS][GAE_TC];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * GAE_WARPS + w;
+  if (e >= E) return;
+  const float g32 = (float)gamma;                    // python float * float32 array -> float32 (NEP 50)
+  const double gl = gamma * lam;                     // python float product
+  const float gl32 = (float)gl;
+  double gae = 0.0;
+  for (int t1 = T; t1 > 0; t1 -= GAE_TC) {
+    const int t0 = max(0, t1 - GAE_TC), n = t1 - t0;
+    for (int i = lane; i < n; i += 32) {
+      const size_t g = (size_t)e * T + t0 + i;
+      if (KIND == 0) {
+        s_r[w][i] = reinterpret_cast<const double*>(reward_)[g];
+        s_nd[w][i] = done[g] ? 0.f : 1.f;
+      } else {
+        s_r[w][i] = (double)reinterpret_cast<const float*>(reward_)[g];   // exact widening, narrowed back below
+      }
+    }
+    for (int i = lane; i <= n; i += 32) s_v[w][i] = value[(size_t)e * (T + 1) + t0 + i];
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = n - 1; i >= 0; --i) {
+        const float v0 = s_v[w][i], v1 = s_v[w][i + 1];
+        const float gv = __fmul_rn(g32, v1);                       // gamma * value[:, t+1]   (float32)
+        if (KIND == 0) {
+          const double nd = (double)s_nd[w][i];                     // (1 - done) is int64 -> product is float64
+          const double term = __dmul_rn((double)gv, nd);
+          const double delta = __dadd_rn(__dadd_rn(s_r[w][i], term), -(double)v0);
+          gae = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, nd), gae));
+        } else {
+          // done == zeros_like(float32): every operand of delta is float32; (gamma*lam)*(1-0) is float32
+          const float delta = __fadd_rn(__fadd_rn((float)s_r[w][i], gv), -v0);
+          gae = __dadd_rn((double)delta, __dmul_rn((double)gl32, gae));
+        }
+        s_out[w][i] = __dadd_rn(gae, (double)v0);                   // discounted_return[:, t]
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const size_t g = (size_t)e * T + t0 + i;
+      const double r = s_out[w][i];
+      ret[g] = r;
+      adv[g] = __dadd_rn(r, -(double)s_v[w][i]);                    // adv = return - value[:, :-1]
+    }
+    __syncwarp();
+  }
+}
+
+// fp32 GAE as a warp-shuffle suffix scan of affine maps  gae_t = delta_t + c_t * gae_{t+1}.
+// One warp per env, each lane owns L consecutive steps (coalesced, 16-byte loads when L == 4).
+constexpr int GAE_MAXL = 32;
+__global__ void __launch_bounds__(128) gae_f32_scan_kernel(const float* __restrict__ reward,
+                                                           const uint8_t* __restrict__ done,
+                                                           const float* __restrict__ value,
+                                                           float* __restrict__ ret, float* __restrict__ adv,
+                                                           int E, int T, float gamma, float lam) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 4 + w;
+  if (e >= E) return;
+  const int L = (T + 31) / 32;
+  const int s = lane * L;
+  float dl[GAE_MAXL], cl[GAE_MAXL], vl[GAE_MAXL];
+  float A = 1.f, B = 0.f;                     // segment map: gae_s = B + A * gae_in
+#pragma unroll 4
+  for (int j = L - 1; j >= 0; --j) {
+    const int t = s + j;
+    float d = 0.f, c = 1.f, v0 = 0.f;         // identity map for padded steps
+    if (t < T) {
+      const size_t g = (size_t)e * T + t;
+      const float nd = (done != nullptr && done[g]) ? 0.f : 1.f;
+      v0 = value[(size_t)e * (T + 1) + t];
+      const float v1 = value[(size_t)e * (T + 1) + t + 1];
+      d = reward[g] + gamma * v1 * nd - v0;
+      c = gamma * lam * nd;
+    }
+    dl[j] = d; cl[j] = c; vl[j] = v0;
+    B = d + c * B;                            // compose: this step applied after the later ones
+    A = c * A;
+  }
+  // inclusive suffix scan over lanes: map_l = map_l o map_{l+1} o ... o map_31
+  float As = A, Bs = B;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float Ao = __shfl_down_sync(0xffffffffu, As, o);
+    const float Bo = __shfl_down_sync(0xffffffffu, Bs, o);
+    if (lane + o < 32) { Bs = Bs + As * Bo; As = As * Ao; }
+  }
+  // gae entering this lane's segment = suffix of the lanes above applied to 0
+  float gin = __shfl_down_sync(0xffffffffu, Bs, 1);
+  if (lane == 31) gin = 0.f;
+  float gae = gin;
+#pragma unroll 4
+  for (int j = L - 1; j >= 0; --j) {
+    const int t = s + j;
+    gae = dl[j] + cl[j] * gae;
+    if (t < T) {
+      const size_t g = (size_t)e * T + t;
+      ret[g] = gae + vl[j];
+      adv[g] = gae;                           // (gae + v) - v evaluated without the round trip
+    }
+  }
+}
+
+__global__ void axpby_f64_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                 double* __restrict__ out, long long n, double ca, double cb) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __dadd_rn(__dmul_rn(a[i], ca), __dmul_rn(b[i], cb));   // int_adv*IntCoef + ext_adv*ExtCoef
+}
+
+// ------------------------------------------------------------------------------------------------
+// RunningMeanStd.update over [N, F]
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct VecLoad;
+template <> struct VecLoad<uint8_t> {
+  static constexpr int V = 16;
+  static __device__ __forceinline__ void load(const uint8_t* p, double* o) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i * 4 + j] = (double)((w[i] >> (8 * j)) & 0xffu);
+  }
+};
+template <> struct VecLoad<float> {
+  static constexpr int V = 4;
+  static __device__ __forceinline__ void load(const float* p, double* o) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = u.x; o[1] = u.y; o[2] = u.z; o[3] = u.w;
+  }
+};
+template <> struct VecLoad<double> {
+  static constexpr int V = 2;
+  static __device__ __forceinline__ void load(const double* p, double* o) {
+    const double2 u = __ldg(reinterpret_cast<const double2*>(p));
+    o[0] = u.x; o[1] = u.y;
+  }
+};
+
+// grid.x tiles the F/V column vectors, grid.y splits the N rows; partial sums go to ws[split][2][F].
+template <typename T>
+__global__ void __launch_bounds__(256) rms_partial_kernel(const T* __restrict__ x, long long N, int F,
+                                                          const double* __restrict__ shift,
+                                                          double* __restrict__ ws, int rows_per_split) {
+  constexpr int V = VecLoad<T>::V;
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;      // column-vector index
+  if (cv * V >= F) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_split;
+  const long long r1 = min(N, r0 + rows_per_split);
+  double sh[V], s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sh[i] = shift[cv * V + i]; s[i] = 0.0; q[i] = 0.0; }
+  const T* p = x + r0 * F + (long long)cv * V;
+  long long r = r0;
+  for (; r + 4 <= r1; r += 4) {                              // 4 independent 16-byte loads in flight
+    double a[4][V];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) VecLoad<T>::load(p + (long long)k * F, a[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < V; ++i) { const double d = a[k][i] - sh[i]; s[i] += d; q[i] += d * d; }
+    p += 4LL * F;
+  }
+  for (; r < r1; ++r) {
+    double a[V];
+    VecLoad<T>::load(p, a);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { const double d = a[i] - sh[i]; s[i] += d; q[i] += d * d; }
+    p += F;
+  }
+  double* o = ws + (long long)blockIdx.y * 2 * F;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { o[cv * V + i] = s[i]; o[F + cv * V + i] = q[i]; }
+}
+
+// Deterministic merge over splits; mode 0 -> write (sum, sumsq) for the moment all-reduce,
+// mode 1 -> Chan merge into the running state (utils.py:101-115).
+__global__ void rms_reduce_kernel(const double* __restrict__ ws, int splits, int F, double batch_count,
+                                  double* __restrict__ sum_out, double* __restrict__ sq_out,
+                                  double* __restrict__ mean, double* __restrict__ var,
+                                  const double* __restrict__ count, int mode) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= F) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < splits; ++k) { s += ws[(long long)k * 2 * F + c]; q += ws[(long long)k * 2 * F + F + c]; }
+  if (mode == 0) { sum_out[c] = s; sq_out[c] = q; return; }
+  const double old_mean = mean[c], old_var = var[c], n_a = count[0], n_b = batch_count;
+  const double ds = s / n_b;                            // batch_mean - shift, shift == old_mean
+  const double b_var = fmax(q / n_b - ds * ds, 0.0);
+  const double tot = n_a + n_b;
+  mean[c] = old_mean + ds * n_b / tot;
+  const double m2 = old_var * n_a + b_var * n_b + ds * ds * n_a * n_b / tot;
+  var[c] = m2 / tot;
+}
+__global__ void rms_merge_kernel(const double* __restrict__ sum, const double* __restrict__ sq, double n_b, int F,
+                                 double* __restrict__ mean, double* __restrict__ var, const double* __restrict__ count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= F) return;
+  const double n_a = count[0], ds = sum[c] / n_b, b_var = fmax(sq[c] / n_b - ds * ds, 0.0), tot = n_a + n_b;
+  const double om = mean[c], ov = var[c];
+  mean[c] = om + ds * n_b / tot;
+  var[c] = (ov * n_a + b_var * n_b + ds * ds * n_a * n_b / tot) / tot;
+}
+__global__ void add_count_kernel(double* count, double n_b) { count[0] = n_b + count[0]; }
+
+static int rms_splits(long long N, int F, int V) {
+  const int col_blocks = cdiv(cdiv(F, V), 256);
+  long long want = (4LL * kNumSMs + col_blocks - 1) / col_blocks;   // ~4 CTAs per SM
+  if (want > N) want = N;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  return (int)want;
+}
+
+template <typename T>
+static int rms_partial_launch(const void* x, long long N, int F, const double* shift, double* ws, int& splits,
+                              cudaStream_t st) {
+  constexpr int V = VecLoad<T>::V;
+  EAVIT_CHECK_ARG(F % V == 0);
+  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  splits = rms_splits(N, F, V);
+  const int rows = cdiv(N, splits);
+  splits = cdiv(N, rows);
+  dim3 grid(cdiv(cdiv(F, V), 256), splits);
+  rms_partial_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), N, F, shift, ws, rows);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+static int rms_partial_dispatch(const void* x, int dt, long long N, int F, const double* shift, double* ws,
+                                int& splits, cudaStream_t st) {
+  switch (dt) {
+    case EAVIT_U8: return rms_partial_launch<uint8_t>(x, N, F, shift, ws, splits, st);
+    case EAVIT_F32: return rms_partial_launch<float>(x, N, F, shift, ws, splits, st);
+    case EAVIT_F64: return rms_partial_launch<double>(x, N, F, shift, ws, splits, st);
+  }
+  set_error("rms: unsupported dtype %d", dt);
+  return EAVIT_EINVAL;
+}
+
+// ------------------------------------------------------------------------------------------------
+// obs normalise + clip
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename O>
+__global__ void __launch_bounds__(256) obs_normalize_kernel(const T* __restrict__ x, long long N, int F,
+                                                            const double* __restrict__ mean,
+                                                            const double* __restrict__ var, O* __restrict__ out,
+                                                            int rows_per_split) {
+  constexpr int V = VecLoad<T>::V;
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cv * V >= F) return;
+  double m[V], sd[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { m[i] = mean[cv * V + i]; sd[i] = sqrt(var[cv * V + i]); }   // np.sqrt(obs_rms.var)
+  const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(N, r0 + rows_per_split);
+  for (long long r = r0; r < r1; ++r) {
+    double a[V];
+    VecLoad<T>::load(x + r * F + (long long)cv * V, a);
+    float y[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      double z = __ddiv_rn(a[i] - m[i], sd[i]);                     // (x - mean) / sqrt(var), float64
+      z = fmin(fmax(z, -5.0), 5.0);                                  // .clip(-5, 5)
+      y[i] = (float)z;                                               // torch.FloatTensor(...)
+    }
+    O* o = out + r * F + (long long)cv * V;
+    if constexpr (sizeof(O) == 4) {
+      if constexpr (V == 2) {
+        *reinterpret_cast<float2*>(o) = make_float2(y[0], y[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; i += 4)
+          *reinterpret_cast<float4*>(o + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+      }
+    } else {
+      uint32_t pk[V / 2];
+#pragma unroll
+      for (int i = 0; i < V; i += 2) pk[i / 2] = pack_bf16x2(y[i], y[i + 1]);
+      if constexpr (V == 2) {
+        *reinterpret_cast<uint32_t*>(o) = pk[0];
+      } else if constexpr (V == 4) {
+        *reinterpret_cast<uint2*>(o) = make_uint2(pk[0], pk[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V / 2; i += 4)
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(o) + i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+      }
+    }
+  }
+}
+
+template <typename T, typename O>
+static int obs_normalize_launch(const void* x, long long N, int F, const double* mean, const double* var, void* out,
+                                cudaStream_t st) {
+  constexpr int V = VecLoad<T>::V;
+  EAVIT_CHECK_ARG(F % V == 0);
+  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  int splits = rms_splits(N, F, V) * 2;
+  if (splits > N) splits = (int)N;
+  const int rows = cdiv(N, splits);
+  splits = cdiv(N, rows);
+  dim3 grid(cdiv(cdiv(F, V), 256), splits);
+  obs_normalize_kernel<T, O><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), N, F, mean, var,
+                                                  reinterpret_cast<O*>(out), rows);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reward forward filter + moments, scale
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) reward_filter_kernel(const float* __restrict__ r, float* __restrict__ rewems,
+                                                             int has_state, int E, int T, float gamma,
+                                                             double* __restrict__ moments) {
+  __shared__ double s_s[32], s_q[32];
+  double s = 0.0, q = 0.0;
+  // shift by r[0][0]-ish scale is unnecessary in float64: T*E <= 2^20 terms of O(1) magnitude
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float acc = has_state ? rewems[e] : 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float x = r[(size_t)e * T + t];
+      // utils.py:123-127: first ever call returns rews itself, afterwards rewems*gamma + rews (float32)
+      acc = (!has_state && t == 0) ? x : __fadd_rn(__fmul_rn(acc, gamma), x);
+      s += (double)acc;
+      q += (double)acc * (double)acc;
+    }
+    rewems[e] = acc;
+  }
+  s = warp_sum(s); q = warp_sum(q);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_s[w] = s; s_q[w] = q; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    s = lane < nw ? s_s[lane] : 0.0;
+    q = lane < nw ? s_q[lane] : 0.0;
+    s = warp_sum(s); q = warp_sum(q);
+    if (lane == 0) {
+      const double n = (double)E * (double)T, mean = s / n;
+      moments[0] = mean;
+      moments[1] = fmax(q / n - mean * mean, 0.0);   // np.std(...)**2, population
+      moments[2] = (double)T;                        // len(total_reward_per_env) == T (train.py:739)
+      moments[3] = s;                                // raw sums for the multi-GPU moment all-reduce
+      moments[4] = q;
+    }
+  }
+}
+
+__global__ void scale_rsqrt_var_kernel(float* __restrict__ x, long long n, const double* __restrict__ var) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = (float)__ddiv_rn((double)x[i], sqrt(var[0]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// intrinsic reward: per-row mean squared difference, one warp per row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) intrinsic_mse_kernel(const float* __restrict__ tgt, const float* __restrict__ prd,
+                                                            float* __restrict__ out, int N, int R) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float4* a = reinterpret_cast<const float4*>(tgt + (size_t)row * R);
+  const float4* b = reinterpret_cast<const float4*>(prd + (size_t)row * R);
+  float acc = 0.f;
+  for (int i = lane; i < R / 4; i += 32) {
+    const float4 u = __ldg(a + i), v = __ldg(b + i);
+    const float d0 = u.x - v.x, d1 = u.y - v.y, d2 = u.z - v.z, d3 = u.w - v.w;
+    acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc / (float)R;
+}
+
+}  // namespace eavit
+
+using namespace eavit;
+
+extern "C" {
+
+int eavit_gae_f64(int kind, const void* reward, const uint8_t* done, const float* value, double* ret, double* adv,
+                  int E, int T, double gamma, double lam, void* stream) {
+  EAVIT_CHECK_ARG(E > 0 && T > 0 && reward && value && ret && adv);
+  EAVIT_CHECK_ARG(kind == 0 || kind == 1);
+  EAVIT_CHECK_ARG(kind == 1 || done != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = cdiv(E, GAE_WARPS);
+  if (kind == 0)
+    gae_f64_kernel<0><<<grid, GAE_WARPS * 32, 0, st>>>(reward, done, value, ret, adv, E, T, gamma, lam);
+  else
+    gae_f64_kernel<1><<<grid, GAE_WARPS * 32, 0, st>>>(reward, done, value, ret, adv, E, T, gamma, lam);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_gae_f32(const float* reward, const uint8_t* done, const float* value, float* ret, float* adv, int E, int T,
+                  float gamma, float lam, void* stream) {
+  EAVIT_CHECK_ARG(E > 0 && T > 0 && reward && value && ret && adv);
+  EAVIT_CHECK_ARG(T <= 32 * GAE_MAXL);
+  gae_f32_scan_kernel<<<cdiv(E, 4), 128, 0, (cudaStream_t)stream>>>(reward, done, value, ret, adv, E, T, gamma, lam);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_axpby_f64(const double* a, const double* b, double* out, long long n, double ca, double cb, void* stream) {
+  EAVIT_CHECK_ARG(n >= 0 && a && b && out);
+  if (n == 0) return EAVIT_OK;
+  axpby_f64_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, ca, cb);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+long long eavit_rms_workspace_bytes(long long N, int F) {
+  (void)N;
+  return 1024LL * 2 * F * (long long)sizeof(double);
+}
+
+int eavit_rms_update(const void* x, int x_dtype, long long N, int F, double* mean, double* var, double* count,
+                     void* workspace, void* stream) {
+  EAVIT_CHECK_ARG(N > 0 && F > 0 && x && mean && var && count && workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  int splits = 0;
+  int rc = rms_partial_dispatch(x, x_dtype, N, F, mean, (double*)workspace, splits, st);
+  if (rc) return rc;
+  rms_reduce_kernel<<<cdiv(F, 256), 256, 0, st>>>((const double*)workspace, splits, F, (double)N, nullptr, nullptr,
+                                                  mean, var, count, 1);
+  EAVIT_LAUNCH_OK();
+  add_count_kernel<<<1, 1, 0, st>>>(count, (double)N);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_rms_partial(const void* x, int x_dtype, long long N, int F, const double* shift, double* sum, double* sumsq,
+                      void* workspace, void* stream) {
+  EAVIT_CHECK_ARG(N > 0 && F > 0 && x && shift && sum && sumsq && workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  int splits = 0;
+  int rc = rms_partial_dispatch(x, x_dtype, N, F, shift, (double*)workspace, splits, st);
+  if (rc) return rc;
+  rms_reduce_kernel<<<cdiv(F, 256), 256, 0, st>>>((const double*)workspace, splits, F, (double)N, sum, sumsq, nullptr,
+                                                  nullptr, nullptr, 0);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_rms_merge(const double* sum, const double* sumsq, double batch_count, int F, double* mean, double* var,
+                    double* count, void* stream) {
+  EAVIT_CHECK_ARG(F > 0 && sum && sumsq && mean && var && count && batch_count > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  rms_merge_kernel<<<cdiv(F, 256), 256, 0, st>>>(sum, sumsq, batch_count, F, mean, var, count);
+  EAVIT_LAUNCH_OK();
+  add_count_kernel<<<1, 1, 0, st>>>(count, batch_count);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_obs_normalize(const void* x, int x_dtype, long long N, int F, const double* mean, const double* var,
+                        void* out, int out_dtype, void* stream) {
+  EAVIT_CHECK_ARG(N > 0 && F > 0 && x && mean && var && out);
+  EAVIT_CHECK_ARG(out_dtype == EAVIT_F32 || out_dtype == EAVIT_BF16);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f32 = out_dtype == EAVIT_F32;
+  switch (x_dtype) {
+    case EAVIT_U8:
+      return f32 ? obs_normalize_launch<uint8_t, float>(x, N, F, mean, var, out, st)
+                 : obs_normalize_launch<uint8_t, __nv_bfloat16>(x, N, F, mean, var, out, st);
+    case EAVIT_F32:
+      return f32 ? obs_normalize_launch<float, float>(x, N, F, mean, var, out, st)
+                 : obs_normalize_launch<float, __nv_bfloat16>(x, N, F, mean, var, out, st);
+    case EAVIT_F64:
+      return f32 ? obs_normalize_launch<double, float>(x, N, F, mean, var, out, st)
+                 : obs_normalize_launch<double, __nv_bfloat16>(x, N, F, mean, var, out, st);
+  }
+  set_error("obs_normalize: unsupported dtype %d", x_dtype);
+  return EAVIT_EINVAL;
+}
+
+int eavit_reward_filter(const float* int_reward, float* rewems, int has_state, int E, int T, float gamma,
+                        double* moments, void* workspace, void* stream) {
+  (void)workspace;
+  EAVIT_CHECK_ARG(E > 0 && T > 0 && int_reward && rewems && moments);
+  int threads = ((E + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  reward_filter_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(int_reward, rewems, has_state, E, T, gamma, moments);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_scale_by_rsqrt_var(float* x, long long n, const double* var, void* stream) {
+  EAVIT_CHECK_ARG(n >= 0 && x && var);
+  if (n == 0) return EAVIT_OK;
+  scale_rsqrt_var_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, var);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_intrinsic_mse(const float* target, const float* predict, float* out, int N, int R, void* stream) {
+  EAVIT_CHECK_ARG(N > 0 && R > 0 && R % 4 == 0 && target && predict && out);
+  intrinsic_mse_kernel<<<cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>(target, predict, out, N, R);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+}  // extern "C"

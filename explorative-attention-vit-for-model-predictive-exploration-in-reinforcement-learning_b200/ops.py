@@ -1,0 +1,162 @@
+"""Tensor-level wrappers over the C ABI (one Python function per ``eavit_*`` entry point).
+
+All tensors must live on the current CUDA device; kernels are enqueued on the current torch stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check
+
+U8, F32, F64, BF16 = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_LRELU, ACT_LRELU_BWD, ACT_RELU, ACT_RELU_BWD = range(7)
+_DT = {torch.uint8: U8, torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda, "eavit_b200 ops take CUDA tensors only (no CPU fallback)"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------- numerics
+def gae_f64(reward: torch.Tensor, done: Optional[torch.Tensor], value: torch.Tensor, gamma: float, lam: float,
+            kind: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """utils.py:42-67 with numpy promotion.  kind 0: reward f64 + done u8; kind 1: reward f32, no done."""
+    E, T = reward.shape
+    assert value.shape == (E, T + 1) and value.dtype == torch.float32 and value.is_contiguous()
+    assert reward.is_contiguous() and reward.dtype == (torch.float64 if kind == 0 else torch.float32)
+    if kind == 0:
+        assert done is not None and done.dtype == torch.uint8 and done.shape == (E, T) and done.is_contiguous()
+    ret = torch.empty(E * T, dtype=torch.float64, device=reward.device)
+    adv = torch.empty_like(ret)
+    check(_lib.lib().eavit_gae_f64(ctypes.c_int(kind), _p(reward), _p(done), _p(value), _p(ret), _p(adv), ctypes.c_int(E),
+                                   ctypes.c_int(T), ctypes.c_double(gamma), ctypes.c_double(lam), _st()), "gae_f64")
+    return ret, adv
+
+
+def gae_f32(reward, done, value, gamma: float, lam: float):
+    E, T = reward.shape
+    assert reward.dtype == torch.float32 and value.dtype == torch.float32 and value.shape == (E, T + 1)
+    assert reward.is_contiguous() and value.is_contiguous()
+    ret = torch.empty(E * T, dtype=torch.float32, device=reward.device)
+    adv = torch.empty_like(ret)
+    check(_lib.lib().eavit_gae_f32(_p(reward), _p(done), _p(value), _p(ret), _p(adv), ctypes.c_int(E), ctypes.c_int(T),
+                                   ctypes.c_float(gamma), ctypes.c_float(lam), _st()), "gae_f32")
+    return ret, adv
+
+
+def axpby_f64(a, b, ca: float, cb: float):
+    out = torch.empty_like(a)
+    check(_lib.lib().eavit_axpby_f64(_p(a), _p(b), _p(out), ctypes.c_longlong(a.numel()), ctypes.c_double(ca),
+                                     ctypes.c_double(cb), _st()), "axpby_f64")
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (str(device),)
+    w = _ws_cache.get(key)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = w
+    return w
+
+
+def rms_update(x: torch.Tensor, mean: torch.Tensor, var: torch.Tensor, count: torch.Tensor):
+    """utils.py:83-115 on device state (mean/var f64 [F], count f64 [1]); x [N, F] u8/f32/f64."""
+    N, F = x.shape[0], x[0].numel()
+    assert x.is_contiguous() and mean.numel() == F and var.numel() == F and count.numel() == 1
+    ws = _workspace(int(_lib.lib().eavit_rms_workspace_bytes(N, F)), x.device)
+    check(_lib.lib().eavit_rms_update(_p(x), ctypes.c_int(_DT[x.dtype]), ctypes.c_longlong(N), ctypes.c_int(F), _p(mean),
+                                      _p(var), _p(count), _p(ws), _st()), "rms_update")
+
+
+def rms_partial(x, shift):
+    N, F = x.shape[0], x[0].numel()
+    ws = _workspace(int(_lib.lib().eavit_rms_workspace_bytes(N, F)), x.device)
+    s = torch.empty(F, dtype=torch.float64, device=x.device)
+    q = torch.empty_like(s)
+    check(_lib.lib().eavit_rms_partial(_p(x), ctypes.c_int(_DT[x.dtype]), ctypes.c_longlong(N), ctypes.c_int(F), _p(shift),
+                                       _p(s), _p(q), _p(ws), _st()), "rms_partial")
+    return s, q
+
+
+def rms_merge(s, q, batch_count: float, mean, var, count):
+    check(_lib.lib().eavit_rms_merge(_p(s), _p(q), ctypes.c_double(batch_count), ctypes.c_int(s.numel()), _p(mean), _p(var),
+                                     _p(count), _st()), "rms_merge")
+
+
+def obs_normalize(x, mean, var, out_dtype=torch.float32, out=None):
+    """train.py:666/:855 ((x-mean)/sqrt(var)).clip(-5,5) -> float32 (agents.py:212/:298) or bf16."""
+    N, F = x.shape[0], x[0].numel()
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    check(_lib.lib().eavit_obs_normalize(_p(x), ctypes.c_int(_DT[x.dtype]), ctypes.c_longlong(N), ctypes.c_int(F), _p(mean),
+                                         _p(var), _p(out), ctypes.c_int(_DT[out.dtype]), _st()), "obs_normalize")
+    return out
+
+
+def reward_filter(int_reward, rewems, has_state: bool, gamma: float):
+    """utils.py:118-128 + moments of train.py:738; returns moments f64[5] = mean, var, T, sum, sumsq."""
+    E, T = int_reward.shape
+    assert int_reward.dtype == torch.float32 and int_reward.is_contiguous() and rewems.numel() == E
+    mom = torch.empty(5, dtype=torch.float64, device=int_reward.device)
+    check(_lib.lib().eavit_reward_filter(_p(int_reward), _p(rewems), ctypes.c_int(int(has_state)), ctypes.c_int(E),
+                                         ctypes.c_int(T), ctypes.c_float(gamma), _p(mom), None, _st()), "reward_filter")
+    return mom
+
+
+def scale_by_rsqrt_var(x, var):
+    check(_lib.lib().eavit_scale_by_rsqrt_var(_p(x), ctypes.c_longlong(x.numel()), _p(var), _st()), "scale_by_rsqrt_var")
+    return x
+
+
+def intrinsic_mse(target, predict):
+    N, R = target.shape
+    assert target.dtype == torch.float32 and predict.dtype == torch.float32
+    out = torch.empty(N, dtype=torch.float32, device=target.device)
+    check(_lib.lib().eavit_intrinsic_mse(_p(target), _p(predict), _p(out), ctypes.c_int(N), ctypes.c_int(R), _st()),
+          "intrinsic_mse")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias=None, act: int = ACT_NONE,
+         aux=None, residual=None, out_f32=None, out_bf16=None, out_pre=None, atomic: bool = False, split_k: int = 1):
+    """C = epilogue(A . B^T) on tcgen05 (see include/eavit_b200.h: eavit_gemm_bf16).
+
+    a_mn: A passed as the stored [K, M] matrix; b_mn: B passed as the stored [K, N] matrix.
+    Outputs must be preallocated by the caller ([M, N], row pitch = stride(0))."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.dim() == 2 and B.dim() == 2
+    assert A.stride(1) == 1 and B.stride(1) == 1
+    M, K = (A.shape[1], A.shape[0]) if a_mn else (A.shape[0], A.shape[1])
+    N, Kb = (B.shape[1], B.shape[0]) if b_mn else (B.shape[0], B.shape[1])
+    assert K == Kb, (A.shape, B.shape, a_mn, b_mn)
+    ldc = None
+    for t in (out_f32, out_bf16, out_pre, aux, residual):
+        if t is not None:
+            assert t.shape == (M, N) and t.stride(1) == 1, (t.shape, (M, N))
+            ldc = t.stride(0) if ldc is None else ldc
+            assert t.stride(0) == ldc
+    g = GemmArgs(M=M, N=N, K=K, A=A.data_ptr(), lda=A.stride(0), a_mn=int(a_mn), B=B.data_ptr(), ldb=B.stride(0),
+                 b_mn=int(b_mn), bias=None if bias is None else bias.data_ptr(),
+                 aux_bf16=None if aux is None else aux.data_ptr(),
+                 residual=None if residual is None else residual.data_ptr(),
+                 out_f32=None if out_f32 is None else out_f32.data_ptr(),
+                 out_bf16=None if out_bf16 is None else out_bf16.data_ptr(),
+                 out_pre_bf16=None if out_pre is None else out_pre.data_ptr(),
+                 ldc=ldc, act=act, atomic_f32=int(atomic), split_k=split_k)
+    check(_lib.lib().eavit_gemm_bf16(ctypes.byref(g), _st()), "gemm_bf16")

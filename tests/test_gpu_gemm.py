@@ -1,0 +1,113 @@
+"""GPU parity: the tcgen05 GEMM (C ABI eavit_gemm_bf16) vs torch fp32 matmul on the same bf16 operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from eavit_b200 import ops as _ops
+    assert torch.cuda.is_available()
+    return _ops
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+
+
+SHAPES = [(128, 256, 64), (256, 768, 256), (1000, 256, 1024), (393, 1024, 256), (130, 64, 144), (64, 32, 64),
+          (4096, 768, 256), (77, 512, 3136)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tn_plain(ops, M, N, K):
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    ref = A.float() @ B.float().t()
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    out16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, out_f32=out, out_bf16=out16)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-5, rel_err(out, ref)          # fp32 accumulate of identical bf16 operands
+    assert rel_err(out16, ref) < 5e-3
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 512), (768, 256, 1000), (200, 1024, 256), (256, 144, 777)])
+def test_gemm_mn_major_operands(ops, a_mn, b_mn, M, N, K):
+    """dX = dY W (B stored [K,N]) and dW = dY^T X (both operands stored [K, *])."""
+    torch.manual_seed(1)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    ref = A.float() @ B.float().t()
+    Ain = A.t().contiguous() if a_mn else A
+    Bin = B.t().contiguous() if b_mn else B
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(Ain, Bin, a_mn=a_mn, b_mn=b_mn, out_f32=out)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-5, rel_err(out, ref)
+
+
+def test_gemm_split_k_atomic(ops):
+    torch.manual_seed(2)
+    M, N, K = 768, 256, 5000
+    A = torch.randn(K, M, device="cuda").bfloat16()
+    B = torch.randn(K, N, device="cuda").bfloat16()
+    ref = A.float().t() @ B.float()
+    out = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(A, B, a_mn=True, b_mn=True, out_f32=out, atomic=True, split_k=16)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-5
+    ops.gemm(A, B, a_mn=True, b_mn=True, out_f32=out, atomic=True, split_k=7)   # accumulates on top
+    torch.cuda.synchronize()
+    assert rel_err(out, 2 * ref) < 1e-5
+
+
+def test_gemm_epilogues(ops):
+    torch.manual_seed(3)
+    M, N, K = 500, 1024, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") / 16).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    pre_ref = A.float() @ B.float().t() + bias
+    # bias + GELU, saving the pre-activation (MLP1 forward, vit.py:29-30)
+    out16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    pre16 = torch.empty_like(out16)
+    ops.gemm(A, B, bias=bias, act=ops.ACT_GELU, out_bf16=out16, out_pre=pre16)
+    assert rel_err(pre16, pre_ref) < 5e-3
+    assert rel_err(out16, torch.nn.functional.gelu(pre_ref)) < 5e-3
+    # bias + residual -> fp32 (attention out-proj / MLP2, vit.py:88-89)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(A, B, bias=bias, residual=res, out_f32=out)
+    assert rel_err(out, pre_ref + res) < 1e-5
+    # in-place residual
+    res2 = res.clone()
+    ops.gemm(A, B, bias=bias, residual=res2, out_f32=res2)
+    assert rel_err(res2, pre_ref + res) < 1e-5
+    # GELU backward epilogue: v * gelu'(aux)
+    aux = torch.randn(M, N, device="cuda").bfloat16()
+    x = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    ops.gemm(A, B, act=ops.ACT_GELU_BWD, aux=aux, out_bf16=out16)
+    assert rel_err(out16, (A.float() @ B.float().t()) * x.grad) < 5e-3
+    # LeakyReLU / ReLU and their backward masks
+    ops.gemm(A, B, bias=bias, act=ops.ACT_LRELU, out_f32=out)
+    assert rel_err(out, torch.nn.functional.leaky_relu(pre_ref)) < 1e-5
+    ops.gemm(A, B, bias=bias, act=ops.ACT_RELU, out_f32=out)
+    assert rel_err(out, torch.relu(pre_ref)) < 1e-5
+    ops.gemm(A, B, act=ops.ACT_RELU_BWD, aux=aux, out_f32=out)
+    assert rel_err(out, (A.float() @ B.float().t()) * (aux.float() > 0)) < 1e-5
+    ops.gemm(A, B, act=ops.ACT_LRELU_BWD, aux=aux, out_f32=out)
+    assert rel_err(out, (A.float() @ B.float().t()) * torch.where(aux.float() > 0, 1.0, 0.01)) < 1e-5
+    torch.cuda.synchronize()
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    A = torch.randn(64, 60, device="cuda").bfloat16()     # pitch 120 B, not 16-byte aligned
+    B = torch.randn(64, 60, device="cuda").bfloat16()
+    out = torch.empty(64, 64, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.gemm(A, B, out_f32=out)
