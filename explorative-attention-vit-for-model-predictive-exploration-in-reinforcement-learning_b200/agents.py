@@ -1,0 +1,253 @@
+"""Drop-in for the reference's ``agents.py``: ``RNDAgent`` with the same constructor, attributes and the three
+hot calls ``get_action`` / ``compute_intrinsic_reward`` / ``train_model`` (agents.py:30-535), running on the
+sm_100a kernels.
+
+What changes underneath (results stay within the north-star tolerances):
+  * the rollout is uploaded ONCE per update and stays resident on the device; minibatches are gathered by
+    index inside the kernels (the reference re-materialises the whole rollout per minibatch, agents.py:288-301);
+  * all trainable tensors live in one flat buffer: one fused Adam launch, one NCCL all-reduce per step;
+  * no per-step host syncs: loss terms are accumulated on the device and read back once per update;
+  * data-parallel: with torch.distributed initialised, every rank trains on its env shard and the flat gradient
+    is all-reduced (mean) before Adam -- the semantics the reference's DDP wrapper intended.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .config import default_config
+from .model import CnnActorCriticNetwork, RNDModel, Runtime, ViT_IMPLEMENTATION, _as_device_image
+from .ops import call
+from .utils import Env_action_space_type, Logger
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr) semantics (agents.py:129) as one fused launch over the agent's flat parameter store."""
+
+    def __init__(self, params, lr, agent):
+        super().__init__(list(params), dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0))
+        self._agent = weakref.ref(agent)
+
+    def zero_grad(self, set_to_none: bool = False):
+        self._agent().runtime().store.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        g = self.param_groups[0]
+        self._agent().runtime().store.adam_step(g["lr"], 1.0, g["betas"][0], g["betas"][1], g["eps"])
+
+    def state_dict(self):
+        st = self._agent().runtime().store
+        return dict(flat_exp_avg=st.m.clone(), flat_exp_avg_sq=st.v.clone(), step=st.step.clone(),
+                    names=list(st.shapes.keys()), param_groups=[{k: v for k, v in self.param_groups[0].items() if k != "params"}])
+
+    def load_state_dict(self, sd):
+        st = self._agent().runtime().store
+        st.m.copy_(sd["flat_exp_avg"]); st.v.copy_(sd["flat_exp_avg_sq"]); st.step.copy_(sd["step"])
+
+
+class RNDAgent(nn.Module):
+    def __init__(self, input_size, output_size, env_action_space_type, num_env, num_step, gamma, GAE_Lambda=0.95,
+                 learning_rate=1e-4, ent_coef=0.01, max_grad_norm=0.5, epoch=3, batch_size=128, ppo_eps=0.1,
+                 update_proportion=0.25, use_gae=True, use_cuda=False, use_noisy_net=False,
+                 representation_lr_method="BYOL", device=None, logger: Logger = None):
+        super().__init__()
+        self.env_action_space_type = env_action_space_type
+        vt = int(default_config["ViT_implementation_type"])
+        ViT_implementation_type = ViT_IMPLEMENTATION.LUCIDRAINS_ViT if vt == 0 else ViT_IMPLEMENTATION.HG_ViT
+        self.model = CnnActorCriticNetwork(input_size, output_size, env_action_space_type, use_noisy_net,
+                                           ViT_implementation_type=ViT_implementation_type)
+        self.num_env, self.output_size, self.input_size, self.num_step = num_env, output_size, input_size, num_step
+        self.gamma, self.GAE_Lambda, self.epoch, self.batch_size = gamma, GAE_Lambda, epoch, batch_size
+        self.use_gae, self.ent_coef, self.ppo_eps, self.max_grad_norm = use_gae, ent_coef, ppo_eps, max_grad_norm
+        self.update_proportion = update_proportion
+        self.use_cuda = use_cuda
+        if not use_cuda:
+            raise RuntimeError("eavit_b200.RNDAgent requires use_cuda=True and a CUDA device: the learner hot path is "
+                               "hand-written sm_100a CUDA with no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda")
+        assert isinstance(logger, Logger)
+        self.logger = logger
+        self.train_method = default_config["TrainMethod"]
+        assert self.train_method == "original_RND", "hot path covers TrainMethod = original_RND (SURVEY fact 7)"
+        self.rnd = RNDModel(input_size=input_size, output_size=512, train_method=self.train_method)
+        assert representation_lr_method == "None", "SSL heads are out of scope (incompatible with the ViT backbone, SURVEY fact 7)"
+        self.representation_lr_method = representation_lr_method
+        self.representation_model = None
+        self.representation_loss_coef = 0
+        self.model = self.model.to(self.device)
+        self.rnd = self.rnd.to(self.device)
+        self._rt: Optional[Runtime] = None
+        ref = weakref.ref(self)
+        self.model._agent_rt = lambda: ref().runtime()
+        self.rnd._agent_rt = lambda: ref().runtime()
+        self.optimizer = FusedAdam(self.get_agent_parameters(), learning_rate, self)
+        self.freeze_shared_backbone_during_training = default_config.getboolean("freeze_shared_backbone", fallback=False)
+        self.world_size, self.rank = 1, 0
+        self.last_stats = None
+        self._ws = {}
+
+    # ---- reference API ---------------------------------------------------------------------------------
+    def get_agent_parameters(self):
+        """agents.py:141-164: PPO model + RND predictor parameters, as a set."""
+        return set([*self.model.parameters(), *self.rnd.predictor.parameters()])
+
+    def set_mode(self, mode="train"):
+        assert mode in ["train", "eval"]
+        self.model = self.model.train(mode == "train")
+        self.rnd = self.rnd.train(mode == "train")
+
+    def runtime(self) -> Runtime:
+        if self._rt is None or not self._rt.valid():
+            self._rt = Runtime(self, "", n_actions=self.output_size,
+                               ext_uses_int_critic=self.model.ViT_implementation_type == ViT_IMPLEMENTATION.HG_ViT)
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                self.world_size, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+                # start every rank from rank 0's weights (what DDP's constructor did at train.py:243)
+                torch.distributed.broadcast(self._rt.store.flat, 0)
+                torch.distributed.broadcast(self._rt.frozen.flat, 0)
+                self._rt.sync()
+        return self._rt
+
+    @torch.no_grad()
+    def get_action(self, state):
+        """agents.py:187-195 (DISCRETE): state float32 [E,C,H,W] (already /255) or uint8 raw frames.
+        Returns (action int64 [E], value_ext f32 [E], value_int f32 [E], logits f32 [E,A]) as numpy."""
+        rt = self.runtime()
+        rt.sync()
+        x = _as_device_image(state, rt.device)
+        pol, ve, vi = rt.ac_forward(x, x.shape[0])
+        # one packed D2H read instead of four
+        E, A = pol.shape
+        pack = torch.cat((pol.reshape(-1), ve, vi)).cpu().numpy()
+        policy = pack[: E * A].reshape(E, A).copy()
+        value_ext, value_int = pack[E * A: E * A + E].copy(), pack[E * A + E:].copy()
+        z = policy - policy.max(axis=1, keepdims=True)
+        e = np.exp(z, dtype=np.float32)
+        action_prob = e / e.sum(axis=1, keepdims=True)                    # F.softmax(policy, dim=-1) in float32
+        action = self.random_choice_prob_index(action_prob)
+        return action, value_ext.squeeze(), value_int.squeeze(), policy
+
+    @staticmethod
+    def random_choice_prob_index(p, axis=1):                              # agents.py:205-208, host numpy RNG
+        r = np.expand_dims(np.random.rand(p.shape[1 - axis]), axis=axis)
+        return (p.cumsum(axis=axis) > r).argmax(axis=axis)
+
+    @torch.no_grad()
+    def compute_intrinsic_reward(self, next_obs):
+        """agents.py:210-218: next_obs float64/float32 numpy (or CUDA tensor) [E,1,H,W], already normalised."""
+        rt = self.runtime()
+        rt.sync()
+        x = next_obs if torch.is_tensor(next_obs) else torch.from_numpy(np.ascontiguousarray(next_obs))
+        x = x.to(rt.device).to(torch.float32).contiguous()               # torch.FloatTensor(next_obs)
+        B = x.shape[0]
+        tgt = rt.rnd_tgt.forward(x, B)
+        prd = rt.rnd_pred.forward(x, B)
+        return ops.intrinsic_mse(tgt, prd).cpu().numpy()
+
+    # ---- update ----------------------------------------------------------------------------------------
+    def _scratch(self, B, A, dev):
+        key = (B, A)
+        w = self._ws.get(key)
+        if w is None:
+            f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+            w = dict(te=f(B), ti=f(B), adv=f(B), y=torch.empty(B, dtype=torch.int64, device=dev), old=f(B, A),
+                     dpol=f(B, A), dv=f(2 * B), stats=torch.zeros(16, dtype=torch.float32, device=dev),
+                     dpred=torch.empty(B, 512, dtype=torch.bfloat16, device=dev), idx=torch.empty(B, dtype=torch.int64, device=dev),
+                     mask=f(B))
+            self._ws[key] = w
+        return w
+
+    def upload_rollout(self, states, target_ext, target_int, y, adv, next_obs_norm, old_policy):
+        """Host numpy (reference dtypes) -> device-resident tensors.  CUDA tensors pass through untouched."""
+        dev = self.runtime().device
+
+        def up(a, dt=None):
+            t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+            t = t.to(dev, non_blocking=True)
+            return t if dt is None or t.dtype == dt else t.to(dt)
+        st = up(states)
+        if st.dtype not in (torch.uint8, torch.float32):
+            st = st.float()
+        A = old_policy.shape[-1]
+        old = up(old_policy, torch.float32)
+        if old.dim() == 3:                                               # [T,E,A] -> [E*T, A]  (agents.py:301)
+            old = old.permute(1, 0, 2).contiguous().view(-1, A)
+        return dict(states=st.contiguous(), te=up(target_ext, torch.float32), ti=up(target_int, torch.float32),
+                    y=up(y, torch.int64), adv=up(adv, torch.float32), obs=up(next_obs_norm, torch.float32).contiguous(),
+                    old=old.contiguous())
+
+    def train_step(self, R: dict, idx: torch.Tensor, mask: torch.Tensor, stats_out: Optional[torch.Tensor] = None,
+                   apply: bool = True):
+        """One minibatch: agents.py:284-508 from the batch gather to ``optimizer.step()``."""
+        rt = self.runtime()
+        B, A = idx.numel(), self.output_size
+        w = self._scratch(B, A, rt.device)
+        st = rt.store
+        gs = 1.0
+        st.zero_grad()
+        call("eavit_zero", w["stats"], 64)
+        call("eavit_gather_batch", idx, B, A, R["te"], R["ti"], R["adv"], R["y"], R["old"], w["te"], w["ti"], w["adv"], w["y"], w["old"])
+        # RND (agents.py:333-338): target is frozen, predictor gets the masked MSE gradient
+        pred = rt.rnd_pred.forward(R["obs"], B, idx)
+        tgt = rt.rnd_tgt.forward(R["obs"], B, idx)
+        call("eavit_rnd_loss", pred, tgt, mask, B, pred.shape[1], gs, w["dpred"], None, w["stats"])
+        rt.rnd_pred.backward(w["dpred"])
+        # PPO (agents.py:455-494)
+        pol, ve, vi = rt.ac_forward(R["states"], B, idx)
+        call("eavit_ppo_loss", pol, w["old"], w["y"], w["adv"], ve, vi, w["te"], w["ti"], B, A, float(self.ppo_eps),
+             float(self.ent_coef), gs, w["dpol"], w["dv"][B:], w["dv"][:B], w["stats"])
+        rt.ac_backward(w["dpol"], w["dv"])
+        if self.world_size > 1:
+            torch.distributed.all_reduce(st.grad)                        # sum over ranks; mean applied inside Adam
+        if default_config.getboolean("UseGradClipping", fallback=False):
+            nrm = torch.zeros(1, dtype=torch.float32, device=rt.device)
+            call("eavit_sumsq_f32", st.grad, st.numel, nrm)
+            call("eavit_clip_by_norm", st.grad, st.numel, nrm, float(self.max_grad_norm) * self.world_size)
+        g = self.optimizer.param_groups[0]
+        if apply:
+            st.adam_step(g["lr"], 1.0 / self.world_size, g["betas"][0], g["betas"][1], g["eps"])
+        if stats_out is not None:
+            stats_out.copy_(w["stats"])
+
+    def train_model(self, states, target_ext, target_int, y, adv, normalized_extracted_feature_embeddings, old_policy,
+                    global_update):
+        """agents.py:263-535.  numpy arguments with the reference's dtypes / layouts (flat sample index e*T+t):
+        states f32 [N,C,H,W] (/255) or uint8, target_* / adv f64 [N], y int64 [N], next-obs f64 [N,1,H,W]
+        (normalised), old_policy f32 [T,E,A].  Mutates parameters and optimiser state; returns None."""
+        rt = self.runtime()
+        rt.sync()
+        R = self.upload_rollout(states, target_ext, target_int, y, adv, normalized_extracted_feature_embeddings, old_policy)
+        N = R["states"].shape[0]
+        B = self.batch_size
+        n_mb = int(N / B)
+        steps = self.epoch * n_mb
+        # agents.py:336: one torch.rand(B) per minibatch on the CPU generator; drawn up front in the same order
+        masks = torch.stack([(torch.rand(B) < self.update_proportion).float() for _ in range(steps)]) if steps else torch.zeros(0, B)
+        masks = masks.to(rt.device)
+        stats = torch.zeros(max(steps, 1), 16, dtype=torch.float32, device=rt.device)
+        sample_range = np.arange(N)                                       # agents.py:270
+        k = 0
+        for _ in range(self.epoch):
+            np.random.shuffle(sample_range)                               # agents.py:276 (MT19937, host)
+            perm = torch.from_numpy(sample_range.copy()).to(rt.device)
+            for j in range(n_mb):
+                self.train_step(R, perm[B * j: B * (j + 1)], masks[k], stats[k])
+                k += 1
+        self.last_stats = stats[:k]                                       # device tensor; read lazily (no sync here)
+        return None
+
+    def stats_summary(self):
+        """Mean loss terms of the last update (one D2H read)."""
+        if self.last_stats is None or self.last_stats.numel() == 0:
+            return {}
+        s = self.last_stats.mean(0).cpu().numpy()
+        out = dict(actor=s[1], critic_ext=s[2], critic_int=s[3], entropy=s[4], rnd=s[5], approx_kl=s[6], max_kl=s[7], clipfrac=s[8])
+        out["loss"] = out["actor"] + 0.5 * (out["critic_ext"] + out["critic_int"]) - self.ent_coef * out["entropy"] + out["rnd"]
+        return {k: float(v) for k, v in out.items()}

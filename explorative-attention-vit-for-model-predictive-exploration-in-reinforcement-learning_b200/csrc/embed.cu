@@ -1,0 +1,294 @@
+// Patch embedding front-end and token/positional assembly (and their backward).
+//
+//   patchify        : [B,C,H,W] (u8 -> /255, or f32) -> bf16 [B*np, PD]; optional fused LayerNorm(PD)
+//                     lucidrains order (p1 p2 c), vit.py:110-111;  HF conv order (c p1 p2), ViTPatchEmbeddings
+//   embed_assemble  : token prepend + positional add into the flat fp32 residual stream, reproducing the
+//                     reference's token bug (vit.py:141-156) in mode 0
+//   *_bwd           : gradients of the above (pos_embedding, tokens, LayerNorm(PD) affine)
+//
+// One CTA stages one patch-row of one sample (C x p x W pixels, coalesced) in shared memory; warps then
+// walk the patches of that row.  An optional sample index (minibatch gather from the device-resident
+// rollout) replaces the reference's per-minibatch host re-materialisation (agents.py:288).
+#include "common.cuh"
+
+namespace eavit {
+
+constexpr int PATCH_MAXV = 18;   // PD <= 576 = 32 * 18
+
+template <typename ImgT>
+__device__ __forceinline__ float load_pixel(const ImgT* p) {
+  if constexpr (sizeof(ImgT) == 1) return __fdiv_rn((float)(*p), 255.0f);   // np.float32(states) / 255.  (train.py:605,854)
+  else return *p;
+}
+
+// MODE 0: forward (write bf16 patches [+LN]);  MODE 1: backward of the LN affine (dgamma, dbeta)
+template <typename ImgT, int MODE>
+__global__ void __launch_bounds__(128) patchify_kernel(const ImgT* __restrict__ img, const long long* __restrict__ sample_idx,
+                                                       int B, int C, int HW, int P, int order_cpp,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, __nv_bfloat16* __restrict__ out,
+                                                       float* __restrict__ mean_io, float* __restrict__ rstd_io,
+                                                       const float* __restrict__ dpln, float* __restrict__ dgamma,
+                                                       float* __restrict__ dbeta) {
+  extern __shared__ float tile[];     // [C][P][HW]  (+ MODE 1: [4 warps][2][PD])
+  const int npr = HW / P;             // patches per row
+  const int b = blockIdx.x / npr, ph = blockIdx.x % npr;
+  const int PD = C * P * P;
+  const long long src = sample_idx ? sample_idx[b] : (long long)b;
+  const ImgT* base = img + (size_t)src * C * HW * HW;
+  for (int i = threadIdx.x; i < C * P * HW; i += blockDim.x) {
+    const int c = i / (P * HW), r = (i / HW) % P, x = i % HW;
+    tile[i] = load_pixel(base + ((size_t)c * HW + ph * P + r) * HW + x);
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[PATCH_MAXV], ab[PATCH_MAXV];
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < PATCH_MAXV; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  }
+  for (int pw = w; pw < npr; pw += 4) {
+    const size_t row = (size_t)b * npr * npr + (size_t)ph * npr + pw;
+    float v[PATCH_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PATCH_MAXV; ++i) {
+      const int k = lane + 32 * i;
+      v[i] = 0.f;
+      if (k < PD) {
+        int c, p1, p2;
+        if (order_cpp) { c = k / (P * P); p1 = (k / P) % P; p2 = k % P; }      // (c p1 p2)
+        else           { c = k % C; p2 = (k / C) % P; p1 = k / (C * P); }       // (p1 p2 c)
+        v[i] = tile[(c * P + p1) * HW + pw * P + p2];
+        s += v[i];
+      }
+    }
+    if (gamma == nullptr) {            // no LayerNorm: plain bf16 patches
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < PATCH_MAXV; ++i) {
+          const int k = lane + 32 * i;
+          if (k < PD) out[row * PD + k] = __float2bfloat16(v[i]);
+        }
+      }
+      continue;
+    }
+    float mu, rs;
+    if (MODE == 0) {
+      mu = warp_sum(s) / (float)PD;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < PATCH_MAXV; ++i) {
+        const int k = lane + 32 * i;
+        if (k < PD) { const float d = v[i] - mu; q += d * d; }
+      }
+      rs = rsqrtf(warp_sum(q) / (float)PD + eps);
+      if (lane == 0 && mean_io != nullptr) { mean_io[row] = mu; rstd_io[row] = rs; }
+#pragma unroll
+      for (int i = 0; i < PATCH_MAXV; ++i) {
+        const int k = lane + 32 * i;
+        if (k < PD) out[row * PD + k] = __float2bfloat16((v[i] - mu) * rs * gamma[k] + beta[k]);
+      }
+    } else {
+      mu = mean_io[row]; rs = rstd_io[row];
+#pragma unroll
+      for (int i = 0; i < PATCH_MAXV; ++i) {
+        const int k = lane + 32 * i;
+        if (k < PD) {
+          const float d = dpln[row * PD + k];
+          ag[i] += d * (v[i] - mu) * rs;
+          ab[i] += d;
+        }
+      }
+    }
+  }
+  if (MODE == 1) {
+    float* part = tile + C * P * HW;    // [4][2][PD]
+#pragma unroll
+    for (int i = 0; i < PATCH_MAXV; ++i) {
+      const int k = lane + 32 * i;
+      if (k < PD) { part[(w * 2) * PD + k] = ag[i]; part[(w * 2 + 1) * PD + k] = ab[i]; }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < PD; k += blockDim.x) {
+      float sg = 0.f, sb = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { sg += part[(q * 2) * PD + k]; sb += part[(q * 2 + 1) * PD + k]; }
+      atomicAdd(dgamma + k, sg);
+      atomicAdd(dbeta + k, sb);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// assemble: e [B*np, D] fp32 (patch tokens) -> flat residual stream x [Ttot, D] fp32
+//   mode 0 (lucidrains explorative pair): seqA_b = e_b                      (len np,   rows [0, B*np))
+//                                         seqB_b = [tokA+pos0, e_b+pos_1..] (len np+1, rows after)
+//   mode 1 (single, CLS):                 seq_b  = [tokA+pos0, e_b+pos_1..]
+//   mode 2 (HF pair):                     seqA_b = [tokA+pos0, e_b+pos..], seqB_b = [tokB+pos0, e_b+pos..]
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_assemble_kernel(const float* __restrict__ e, const float* __restrict__ pos,
+                                                             const float* __restrict__ tokA, const float* __restrict__ tokB,
+                                                             int mode, int B, int np, int D, float* __restrict__ x) {
+  // one warp per (b, j) with j in [0, np]  (j = 0 is the token row)
+  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= B * (np + 1)) return;
+  const int b = wid / (np + 1), j = wid % (np + 1);
+  const int S1 = np + 1;
+  const int nv = D / 4;
+  const float4* pj = reinterpret_cast<const float4*>(pos + (size_t)j * D);
+  if (j == 0) {
+    for (int c = lane; c < nv; c += 32) {
+      const float4 p = __ldg(pj + c);
+      const float4 ta = __ldg(reinterpret_cast<const float4*>(tokA) + c);
+      const float4 va = make_float4(ta.x + p.x, ta.y + p.y, ta.z + p.z, ta.w + p.w);
+      if (mode == 0) {
+        *(reinterpret_cast<float4*>(x + ((size_t)B * np + (size_t)b * S1) * D) + c) = va;
+      } else if (mode == 1) {
+        *(reinterpret_cast<float4*>(x + ((size_t)b * S1) * D) + c) = va;
+      } else {
+        const float4 tb = __ldg(reinterpret_cast<const float4*>(tokB) + c);
+        *(reinterpret_cast<float4*>(x + ((size_t)b * S1) * D) + c) = va;
+        *(reinterpret_cast<float4*>(x + ((size_t)B * S1 + (size_t)b * S1) * D) + c) =
+            make_float4(tb.x + p.x, tb.y + p.y, tb.z + p.z, tb.w + p.w);
+      }
+    }
+    return;
+  }
+  const int n = j - 1;
+  const float4* er = reinterpret_cast<const float4*>(e + ((size_t)b * np + n) * D);
+  for (int c = lane; c < nv; c += 32) {
+    const float4 v = __ldg(er + c);
+    const float4 p = __ldg(pj + c);
+    const float4 vp = make_float4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w);
+    if (mode == 0) {
+      *(reinterpret_cast<float4*>(x + ((size_t)b * np + n) * D) + c) = v;                       // no pos-emb (bug kept)
+      *(reinterpret_cast<float4*>(x + ((size_t)B * np + (size_t)b * S1 + j) * D) + c) = vp;
+    } else if (mode == 1) {
+      *(reinterpret_cast<float4*>(x + ((size_t)b * S1 + j) * D) + c) = vp;
+    } else {
+      *(reinterpret_cast<float4*>(x + ((size_t)b * S1 + j) * D) + c) = vp;
+      *(reinterpret_cast<float4*>(x + ((size_t)B * S1 + (size_t)b * S1 + j) * D) + c) = vp;
+    }
+  }
+}
+
+// g[b*np+n] = sum over sequences of the patch-token gradient (fp32 + optional bf16 copy)
+__global__ void __launch_bounds__(256) embed_assemble_bwd_rows_kernel(const float* __restrict__ dx, int mode, int B, int np,
+                                                                      int D, float* __restrict__ g,
+                                                                      __nv_bfloat16* __restrict__ g_bf16) {
+  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= B * np) return;
+  const int b = wid / np, n = wid % np, S1 = np + 1, nv = D / 4;
+  const float4 *a, *c2 = nullptr;
+  if (mode == 0) {
+    a = reinterpret_cast<const float4*>(dx + ((size_t)b * np + n) * D);
+    c2 = reinterpret_cast<const float4*>(dx + ((size_t)B * np + (size_t)b * S1 + 1 + n) * D);
+  } else if (mode == 1) {
+    a = reinterpret_cast<const float4*>(dx + ((size_t)b * S1 + 1 + n) * D);
+  } else {
+    a = reinterpret_cast<const float4*>(dx + ((size_t)b * S1 + 1 + n) * D);
+    c2 = reinterpret_cast<const float4*>(dx + ((size_t)B * S1 + (size_t)b * S1 + 1 + n) * D);
+  }
+  for (int c = lane; c < nv; c += 32) {
+    float4 v = __ldg(a + c);
+    if (c2 != nullptr) { const float4 u = __ldg(c2 + c); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+    if (g != nullptr) *(reinterpret_cast<float4*>(g + (size_t)wid * D) + c) = v;
+    if (g_bf16 != nullptr)
+      *(reinterpret_cast<uint2*>(g_bf16 + (size_t)wid * D) + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// dpos[j] += sum_b (...), dtokA/B += sum_b dx[token row].  grid = (np+1, ceil(D/128)), block 128, loops over b.
+__global__ void __launch_bounds__(128) embed_assemble_bwd_pos_kernel(const float* __restrict__ dx, int mode, int B, int np,
+                                                                     int D, float* __restrict__ dpos,
+                                                                     float* __restrict__ dtokA, float* __restrict__ dtokB) {
+  const int j = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= D) return;
+  const int S1 = np + 1;
+  float sa = 0.f, sb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    if (mode == 0) {
+      sb += dx[((size_t)B * np + (size_t)b * S1 + j) * D + c];
+    } else if (mode == 1) {
+      sa += dx[((size_t)b * S1 + j) * D + c];
+    } else {
+      sa += dx[((size_t)b * S1 + j) * D + c];
+      sb += dx[((size_t)B * S1 + (size_t)b * S1 + j) * D + c];
+    }
+  }
+  atomicAdd(dpos + (size_t)j * D + c, sa + sb);
+  if (j == 0) {
+    if (mode == 0) atomicAdd(dtokA + c, sb);          // exploration_token feeds the exploitative pass (bug kept)
+    else if (mode == 1) atomicAdd(dtokA + c, sa);
+    else { atomicAdd(dtokA + c, sa); atomicAdd(dtokB + c, sb); }
+  }
+}
+
+}  // namespace eavit
+
+using namespace eavit;
+
+extern "C" {
+
+static int patchify_common(int mode, const void* img, int img_dtype, const long long* sample_idx, int B, int C, int HW, int P,
+                           int order_cpp, const float* gamma, const float* beta, float eps, void* out, float* mean,
+                           float* rstd, const float* dpln, float* dgamma, float* dbeta, cudaStream_t st) {
+  EAVIT_CHECK_ARG(img && B > 0 && C > 0 && P > 0 && HW % P == 0);
+  const int PD = C * P * P;
+  EAVIT_CHECK_ARG(PD <= 32 * PATCH_MAXV);
+  const int npr = HW / P;
+  size_t smem = (size_t)C * P * HW * sizeof(float) + (mode == 1 ? (size_t)4 * 2 * PD * sizeof(float) : 0);
+  EAVIT_CHECK_ARG(smem <= 48 * 1024);
+  dim3 grid(B * npr);
+  if (img_dtype == EAVIT_U8) {
+    if (mode == 0) patchify_kernel<uint8_t, 0><<<grid, 128, smem, st>>>((const uint8_t*)img, sample_idx, B, C, HW, P, order_cpp, gamma, beta, eps, (__nv_bfloat16*)out, mean, rstd, dpln, dgamma, dbeta);
+    else           patchify_kernel<uint8_t, 1><<<grid, 128, smem, st>>>((const uint8_t*)img, sample_idx, B, C, HW, P, order_cpp, gamma, beta, eps, (__nv_bfloat16*)out, mean, rstd, dpln, dgamma, dbeta);
+  } else if (img_dtype == EAVIT_F32) {
+    if (mode == 0) patchify_kernel<float, 0><<<grid, 128, smem, st>>>((const float*)img, sample_idx, B, C, HW, P, order_cpp, gamma, beta, eps, (__nv_bfloat16*)out, mean, rstd, dpln, dgamma, dbeta);
+    else           patchify_kernel<float, 1><<<grid, 128, smem, st>>>((const float*)img, sample_idx, B, C, HW, P, order_cpp, gamma, beta, eps, (__nv_bfloat16*)out, mean, rstd, dpln, dgamma, dbeta);
+  } else { set_error("patchify: bad img dtype %d", img_dtype); return EAVIT_EINVAL; }
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_patchify(const void* img, int img_dtype, const long long* sample_idx, int B, int C, int HW, int P, int order_cpp,
+                   const float* gamma, const float* beta, float eps, void* out_bf16, float* mean, float* rstd,
+                   void* stream) {
+  EAVIT_CHECK_ARG(out_bf16 != nullptr);
+  EAVIT_CHECK_ARG((gamma == nullptr) == (beta == nullptr));
+  return patchify_common(0, img, img_dtype, sample_idx, B, C, HW, P, order_cpp, gamma, beta, eps, out_bf16, mean, rstd,
+                         nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int eavit_patchify_ln_bwd(const void* img, int img_dtype, const long long* sample_idx, int B, int C, int HW, int P,
+                          int order_cpp, const float* gamma, const float* mean, const float* rstd, const float* dpln,
+                          float* dgamma, float* dbeta, void* stream) {
+  EAVIT_CHECK_ARG(gamma && mean && rstd && dpln && dgamma && dbeta);
+  return patchify_common(1, img, img_dtype, sample_idx, B, C, HW, P, order_cpp, gamma, gamma, 0.f, nullptr,
+                         const_cast<float*>(mean), const_cast<float*>(rstd), dpln, dgamma, dbeta, (cudaStream_t)stream);
+}
+
+int eavit_embed_assemble(const float* e, const float* pos, const float* tokA, const float* tokB, int mode, int B, int np,
+                         int D, float* x, void* stream) {
+  EAVIT_CHECK_ARG(e && pos && tokA && x && B > 0 && np > 0 && D % 4 == 0 && mode >= 0 && mode <= 2);
+  EAVIT_CHECK_ARG(mode != 2 || tokB != nullptr);
+  embed_assemble_kernel<<<cdiv((long long)B * (np + 1), 8), 256, 0, (cudaStream_t)stream>>>(e, pos, tokA, tokB, mode, B, np, D, x);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, float* g, void* g_bf16, float* dpos,
+                             float* dtokA, float* dtokB, void* stream) {
+  EAVIT_CHECK_ARG(dx && (g || g_bf16) && dpos && dtokA && B > 0 && np > 0 && D % 4 == 0 && mode >= 0 && mode <= 2);
+  EAVIT_CHECK_ARG(mode != 2 || dtokB != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  embed_assemble_bwd_rows_kernel<<<cdiv((long long)B * np, 8), 256, 0, st>>>(dx, mode, B, np, D, g, (__nv_bfloat16*)g_bf16);
+  EAVIT_LAUNCH_OK();
+  dim3 grid(np + 1, cdiv(D, 128));
+  embed_assemble_bwd_pos_kernel<<<grid, 128, 0, st>>>(dx, mode, B, np, D, dpos, dtokA, dtokB);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// LayerNorm forward / backward over rows of a [T, D] fp32 residual stream (one warp per row, float4 loads),
+// bf16 output feeding the tcgen05 GEMMs; backward fuses the residual-path add and the dgamma/dbeta
+// reductions.  Also: bf16 column sums (bias gradients) and row gather/scatter for the pooled token.
+//
+// Reference: nn.LayerNorm at vit.py:28 (FeedForward), :47 (Attention), :78 (Transformer.norm), :111/:113
+// (patch embedding); HF layernorm_before/after/final (vit_hg.py via transformers).
+#include "common.cuh"
+
+namespace eavit {
+
+constexpr int LN_MAXV = 8;   // D <= 32 lanes * 4 * 8 = 1024
+
+// y = (x - mean) * rstd * gamma + beta ; two-pass statistics in fp32 like ATen's CPU/CUDA kernels.
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, OutT* __restrict__ y,
+                                                            long long ldy, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, int T, int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const float* xr = x + (size_t)row * ldx;
+  const int nv = D / 4;
+  float4 v[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      v[i] = __ldg(reinterpret_cast<const float4*>(xr) + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  if (lane == 0 && mean_out != nullptr) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  OutT* yr = y + (size_t)row * ldy;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (sizeof(OutT) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + 4 * c) = make_float4(o0, o1, o2, o3);
+      } else {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yr) + 4 * c) =
+            make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      }
+    }
+  }
+}
+
+// dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy      (block partials -> one atomicAdd per column per block)
+constexpr int LNB_ROWS_PER_BLOCK = 64;
+template <typename DyT>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restrict__ dy, long long lddy,
+                                                            const float* __restrict__ x, long long ldx,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ dres, long long lddres,
+                                                            float* __restrict__ dx, long long lddx,
+                                                            __nv_bfloat16* __restrict__ dx_bf16, long long lddxb,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int T, int D) {
+  extern __shared__ float s_part[];   // [8 warps][2][D]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = D / 4;
+  float4 ag[LN_MAXV], ab[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = ag[i]; }
+  const int r_begin = blockIdx.x * LNB_ROWS_PER_BLOCK;
+  const int r_end = min(T, r_begin + LNB_ROWS_PER_BLOCK);
+  for (int row = r_begin + w; row < r_end; row += 8) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 g[LN_MAXV], xh[LN_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        float4 d;
+        if constexpr (sizeof(DyT) == 4) {
+          d = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + (size_t)row * lddy) + c);
+        } else {
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)row * lddy) + c);
+          const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+          d = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * ldx) + c);
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        float4 o = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
+                               rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
+        if (dres != nullptr) {
+          const float4 r = __ldg(reinterpret_cast<const float4*>(dres + (size_t)row * lddres) + c);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (dx != nullptr) *(reinterpret_cast<float4*>(dx + (size_t)row * lddx) + c) = o;
+        if (dx_bf16 != nullptr)
+          *(reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * lddxb) + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
+  if (dgamma == nullptr) return;
+  float* pg = s_part + (size_t)w * 2 * D;
+  float* pb = pg + D;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      *(reinterpret_cast<float4*>(pg) + c) = ag[i];
+      *(reinterpret_cast<float4*>(pb) + c) = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sg += s_part[(size_t)k * 2 * D + c]; sb += s_part[(size_t)k * 2 * D + D + c]; }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
+// out[c] += sum_rows x[r, c]   (bias gradients); x bf16 or fp32 [T, N]
+template <typename XT>
+__global__ void __launch_bounds__(256) colsum_kernel(const XT* __restrict__ x, long long ldx, float* __restrict__ out,
+                                                     int T, int N, int rows_per_block) {
+  // thread (tx, ty): tx covers 2 columns, ty strides rows
+  const int cpair = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ty = threadIdx.x >> 5;
+  const int c = cpair * 2;
+  __shared__ float2 s[8][32];
+  float a0 = 0.f, a1 = 0.f;
+  if (c < N) {
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(T, r0 + rows_per_block);
+    for (int r = r0 + ty; r < r1; r += 8) {
+      if constexpr (sizeof(XT) == 2) {
+        const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)r * ldx + c)));
+        a0 += v.x; a1 += v.y;
+      } else {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + (size_t)r * ldx + c));
+        a0 += v.x; a1 += v.y;
+      }
+    }
+  }
+  s[ty][threadIdx.x & 31] = make_float2(a0, a1);
+  __syncthreads();
+  if (ty == 0 && c < N) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { a0 += s[k][threadIdx.x].x; a1 += s[k][threadIdx.x].y; }
+    atomicAdd(out + c, a0);
+    atomicAdd(out + c + 1, a1);
+  }
+}
+
+// dst[i, :] = src[idx(i), :] with idx(i) = rows[i]  (gather of the pooled token rows; fp32)
+__global__ void gather_rows_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ rows,
+                                   float* __restrict__ dst, long long ldd, int n, int D) {
+  const int i = blockIdx.x;
+  const float* s = src + (size_t)rows[i] * lds;
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x)
+    *(reinterpret_cast<float4*>(dst + (size_t)i * ldd) + c) = __ldg(reinterpret_cast<const float4*>(s) + c);
+}
+// dst[rows[i], :] = src[i, :]  (scatter; rows are unique)  + optional bf16 copy
+__global__ void scatter_rows_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ rows,
+                                    float* __restrict__ dst, long long ldd, __nv_bfloat16* __restrict__ dst_bf16,
+                                    long long lddb, int n, int D) {
+  const int i = blockIdx.x;
+  const size_t r = (size_t)rows[i];
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)i * lds) + c);
+    if (dst != nullptr) *(reinterpret_cast<float4*>(dst + r * ldd) + c) = v;
+    if (dst_bf16 != nullptr)
+      *(reinterpret_cast<uint2*>(dst_bf16 + r * lddb) + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// fp32 -> bf16 elementwise (weight shadows, activations)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    *(reinterpret_cast<uint2*>(out) + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+}  // namespace eavit
+
+using namespace eavit;
+
+extern "C" {
+
+int eavit_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, int y_dtype,
+                        long long ldy, float* mean, float* rstd, int T, int D, float eps, void* stream) {
+  EAVIT_CHECK_ARG(T > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXV && x && gamma && beta && y);
+  EAVIT_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0);
+  EAVIT_CHECK_ARG((mean == nullptr) == (rstd == nullptr));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (y_dtype == EAVIT_BF16)
+    layernorm_fwd_kernel<__nv_bfloat16><<<cdiv(T, 8), 256, 0, st>>>(x, ldx, gamma, beta, (__nv_bfloat16*)y, ldy, mean, rstd, T, D, eps);
+  else if (y_dtype == EAVIT_F32)
+    layernorm_fwd_kernel<float><<<cdiv(T, 8), 256, 0, st>>>(x, ldx, gamma, beta, (float*)y, ldy, mean, rstd, T, D, eps);
+  else { set_error("layernorm_fwd: bad y_dtype %d", y_dtype); return EAVIT_EINVAL; }
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const float* x, long long ldx, const float* mean,
+                        const float* rstd, const float* gamma, const float* dres, long long lddres, float* dx,
+                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, int T, int D,
+                        void* stream) {
+  EAVIT_CHECK_ARG(T > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXV && dy && x && mean && rstd && gamma);
+  EAVIT_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr));
+  EAVIT_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && lddres % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
+  const int grid = cdiv(T, LNB_ROWS_PER_BLOCK);
+  if (dy_dtype == EAVIT_F32) {
+    static bool done = false;
+    if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4)); done = true; }
+    layernorm_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx,
+                                                         (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, T, D);
+  } else if (dy_dtype == EAVIT_BF16) {
+    static bool done = false;
+    if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4)); done = true; }
+    layernorm_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres,
+                                                                 dx, lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, T, D);
+  } else { set_error("layernorm_bwd: bad dy_dtype %d", dy_dtype); return EAVIT_EINVAL; }
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_colsum(const void* x, int x_dtype, long long ldx, float* out, int T, int N, void* stream) {
+  EAVIT_CHECK_ARG(T > 0 && N > 0 && N % 2 == 0 && x && out && ldx % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int col_blocks = cdiv(N, 64);
+  int row_blocks = cdiv(4 * kNumSMs, col_blocks);
+  if (row_blocks > cdiv(T, 8)) row_blocks = cdiv(T, 8);
+  const int rpb = cdiv(T, row_blocks);
+  dim3 grid(col_blocks, cdiv(T, rpb));
+  if (x_dtype == EAVIT_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, out, T, N, rpb);
+  else if (x_dtype == EAVIT_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, out, T, N, rpb);
+  else { set_error("colsum: bad dtype %d", x_dtype); return EAVIT_EINVAL; }
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_gather_rows(const float* src, long long lds, const int* rows, float* dst, long long ldd, int n, int D, void* stream) {
+  EAVIT_CHECK_ARG(n > 0 && D % 4 == 0 && src && rows && dst && lds % 4 == 0 && ldd % 4 == 0);
+  gather_rows_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(src, lds, rows, dst, ldd, n, D);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_scatter_rows(const float* src, long long lds, const int* rows, float* dst, long long ldd, void* dst_bf16,
+                       long long lddb, int n, int D, void* stream) {
+  EAVIT_CHECK_ARG(n > 0 && D % 4 == 0 && src && rows && (dst || dst_bf16) && lds % 4 == 0 && ldd % 4 == 0 && lddb % 4 == 0);
+  scatter_rows_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(src, lds, rows, dst, ldd, (__nv_bfloat16*)dst_bf16, lddb, n, D);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
+  EAVIT_CHECK_ARG(n > 0 && n % 4 == 0 && in && out);
+  cast_f32_bf16_kernel<<<cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n / 4);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,507 @@
+"""Forward / backward orchestration of the learner hot path on top of the C-ABI kernels.
+
+Everything numerical happens in ``libeavit_b200.so``; this file only sequences launches and owns the
+device buffers:
+
+  * ``ParamStore``  -- ONE flat fp32 buffer for all trainable tensors (+ bf16 shadow for the tensor-core
+    GEMMs, + flat gradient, + Adam moments).  The optimiser is one launch and the multi-GPU gradient
+    exchange is one NCCL all-reduce over ``store.grad`` (replaces the reference's never-armed DDP reducer,
+    SURVEY fact 5).
+  * ``ViTEncoder``  -- patch-embed -> token/pos assembly -> depth x (LN, QKV GEMM, attention, out-proj +
+    residual, LN, MLP1 + GELU, MLP2 + residual) -> pooled-token LN.  The explorative (S = np) and
+    exploitative (S = np+1) passes of model.py:275/:279 share weights, so both run as ONE flat token
+    batch [B*np + B*(np+1), D]: every GEMM sees both passes in one launch and the patch embedding is
+    computed once instead of twice.
+  * ``Heads`` / ``RNDNet`` -- PPO heads (fp32) and the RND conv towers (im2col + tcgen05 GEMM).
+
+Reference call sites: model.py:266-354, vit.py:136-167, vit_hg.py:277-374, agents.py:333-508.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .config import HotPathConfig
+from .ops import call
+
+F32, BF16 = ops.F32, ops.BF16
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class ParamStore:
+    """Flat storage for a set of named tensors (fp32 master, bf16 shadow, grad, Adam m / v)."""
+
+    def __init__(self, shapes: "OrderedDict[str, Tuple[int, ...]]", device, trainable: bool = True):
+        self.shapes = OrderedDict(shapes)
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for name, shp in self.shapes.items():
+            self.offsets[name] = off
+            n = 1
+            for s in shp:
+                n *= s
+            off += _pad8(n)
+        self.numel = max(off, 8)
+        self.device = device
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        self.flat_bf16 = torch.zeros(self.numel, dtype=torch.bfloat16, device=device)
+        self.trainable = trainable
+        if trainable:
+            self.grad = torch.zeros(self.numel, dtype=torch.float32, device=device)
+            self.m = torch.zeros(self.numel, dtype=torch.float32, device=device)
+            self.v = torch.zeros(self.numel, dtype=torch.float32, device=device)
+            self.step = torch.zeros(1, dtype=torch.int64, device=device)
+        self._views = {n: self._view(self.flat, n) for n in self.shapes}
+        self._bviews = {n: self._view(self.flat_bf16, n) for n in self.shapes}
+        self._gviews = {n: self._view(self.grad, n) for n in self.shapes} if trainable else {}
+
+    def _view(self, buf, name):
+        shp = self.shapes[name]
+        n = 1
+        for s in shp:
+            n *= s
+        o = self.offsets[name]
+        return buf[o:o + n].view(shp)
+
+    def w(self, name) -> torch.Tensor:        # fp32 master
+        return self._views[name]
+
+    def b16(self, name) -> torch.Tensor:      # bf16 shadow
+        return self._bviews[name]
+
+    def g(self, name) -> torch.Tensor:        # fp32 gradient
+        return self._gviews[name]
+
+    def span(self, names: Sequence[str], buf: str, shape) -> torch.Tensor:
+        """View over several ADJACENT tensors (e.g. HF query|key|value weights as one [3D, D] matrix)."""
+        o = self.offsets[names[0]]
+        n = 1
+        for s in shape:
+            n *= s
+        exp = o
+        for nm in names:
+            assert self.offsets[nm] == exp, "tensors are not adjacent in the flat store"
+            k = 1
+            for s in self.shapes[nm]:
+                k *= s
+            assert k % 8 == 0
+            exp += k
+        assert exp - o == n
+        return getattr(self, buf)[o:o + n].view(shape)
+
+    def sync_shadow(self):
+        call("eavit_cast_f32_bf16", self.flat, self.flat_bf16, self.numel)
+
+    def zero_grad(self):
+        call("eavit_zero", self.grad, self.numel * 4)
+
+    def adam_step(self, lr: float, grad_scale: float = 1.0, beta1=0.9, beta2=0.999, eps=1e-8):
+        call("eavit_adam_step", self.flat, self.grad, self.m, self.v, self.flat_bf16, self.numel, self.step,
+             lr, beta1, beta2, eps, grad_scale)
+
+
+class _Buffers:
+    """Named, shape-checked scratch tensors, allocated once per (batch) configuration."""
+
+    def __init__(self, device):
+        self.device = device
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def get(self, name, shape, dtype) -> torch.Tensor:
+        t = self.t.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.t[name] = t
+        return t
+
+
+def _split_k(M: int, N: int, K: int) -> int:
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+    s = max(1, (148 + tiles - 1) // tiles)
+    return max(1, min(s, (K + 63) // 64))
+
+
+def linear_fwd(x16, w16, *, bias=None, act=ops.ACT_NONE, residual=None, out_f32=None, out_bf16=None, out_pre=None):
+    """y = act(x W^T + b) (+ residual) on the tcgen05 GEMM."""
+    ops.gemm(x16, w16, bias=bias, act=act, residual=residual, out_f32=out_f32, out_bf16=out_bf16, out_pre=out_pre)
+
+
+def linear_bwd(dy16, x16, w16, *, dW, db=None, dx_f32=None, dx_bf16=None, act=ops.ACT_NONE, aux=None):
+    """dW += dy^T x (split-K, MN-major operands), db += colsum(dy), dx = act'(dy W)."""
+    M, K = dW.shape
+    ops.gemm(dy16, x16, a_mn=True, b_mn=True, out_f32=dW, atomic=True, split_k=_split_k(M, K, dy16.shape[0]))
+    if db is not None:
+        call("eavit_colsum", dy16, BF16, dy16.stride(0), db, dy16.shape[0], dy16.shape[1])
+    if dx_f32 is not None or dx_bf16 is not None:
+        ops.gemm(dy16, w16, b_mn=True, act=act, aux=aux, out_f32=dx_f32, out_bf16=dx_bf16)
+
+
+class ViTEncoder:
+    """Both ViT variants of the reference behind one flat-token implementation."""
+
+    def __init__(self, cfg: HotPathConfig, store: ParamStore, prefix: str = "model.feature."):
+        self.cfg, self.store, self.pre = cfg, store, prefix
+        self.dev = store.device
+        self.buf: Dict[int, _Buffers] = {}
+        c = cfg
+        self.inner = c.heads * c.dim_head
+        if c.impl == "lucidrains":
+            self.mode = 0 if c.use_explorative else 1
+        else:
+            assert c.use_explorative, "HF variant is only wired for use_explorativeAttn=True (no shipped config uses CLS)"
+            self.mode = 2
+        self.nseq_per_sample = 1 if self.mode == 1 else 2
+        # layer parameter names
+        p = prefix
+        self.L = []
+        for i in range(c.depth):
+            if c.impl == "lucidrains":
+                a, m = p + f"transformer.layers.{i}.0.", p + f"transformer.layers.{i}.1.net."
+                self.L.append(dict(ln1=(a + "norm.weight", a + "norm.bias"), qkv_w=a + "to_qkv.weight", qkv_b=None,
+                                   o_w=a + "to_out.0.weight", o_b=a + "to_out.0.bias", ln2=(m + "0.weight", m + "0.bias"),
+                                   w1=m + "1.weight", b1=m + "1.bias", w2=m + "4.weight", b2=m + "4.bias"))
+            else:
+                l = p + f"encoder.layer.{i}."
+                self.L.append(dict(ln1=(l + "layernorm_before.weight", l + "layernorm_before.bias"),
+                                   qkv_w=[l + f"attention.attention.{n}.weight" for n in ("query", "key", "value")],
+                                   qkv_b=[l + f"attention.attention.{n}.bias" for n in ("query", "key", "value")],
+                                   o_w=l + "attention.output.dense.weight", o_b=l + "attention.output.dense.bias",
+                                   ln2=(l + "layernorm_after.weight", l + "layernorm_after.bias"),
+                                   w1=l + "intermediate.dense.weight", b1=l + "intermediate.dense.bias",
+                                   w2=l + "output.dense.weight", b2=l + "output.dense.bias"))
+
+    # ---- parameter views -----------------------------------------------------------------------
+    def _qkv(self, L, kind):
+        s, D, I = self.store, self.cfg.dim, self.inner
+        if isinstance(L["qkv_w"], str):
+            return {"w16": s.b16(L["qkv_w"]), "gw": s.g(L["qkv_w"]), "b": None, "gb": None}[kind]
+        if kind == "w16":
+            return s.span(L["qkv_w"], "flat_bf16", (3 * I, D))
+        if kind == "gw":
+            return s.span(L["qkv_w"], "grad", (3 * I, D))
+        if kind == "b":
+            return s.span(L["qkv_b"], "flat", (3 * I,))
+        return s.span(L["qkv_b"], "grad", (3 * I,))
+
+    # ---- geometry --------------------------------------------------------------------------------
+    def geometry(self, B: int):
+        np_, c = self.cfg.n_patches, self.cfg
+        if self.mode == 0:
+            lens = [np_] * B + [np_ + 1] * B
+        elif self.mode == 1:
+            lens = [np_ + 1] * B
+        else:
+            lens = [np_ + 1] * (2 * B)
+        return lens
+
+    def _buffers(self, B: int) -> _Buffers:
+        bf = self.buf.get(B)
+        if bf is not None:
+            return bf
+        bf = _Buffers(self.dev)
+        lens = self.geometry(B)
+        starts = [0]
+        for n in lens:
+            starts.append(starts[-1] + n)
+        bf.T = starts[-1]
+        bf.nseq = len(lens)
+        bf.max_len = max(lens)
+        bf.seq_start = torch.tensor(starts, dtype=torch.int32, device=self.dev)
+        rows = starts[:-1]                     # token 0 of every sequence (x[:, 0], vit.py:162 / model.py:316)
+        if self.mode == 1:
+            rows = rows + rows                 # CLS feature feeds both value heads (model.py:300-302)
+        bf.pool_rows = torch.tensor(rows, dtype=torch.int32, device=self.dev)
+        self.buf[B] = bf
+        return bf
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, img: torch.Tensor, B: int, sample_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """img: [N,C,H,W] uint8 (raw frames, divided by 255 in-kernel) or float32 (already /255).
+        Returns the pooled, final-LayerNorm'ed features F fp32 [2B, D] (rows [0,B) explorative/CLS,
+        rows [B,2B) exploitative/CLS).  Activations stay in the per-B buffers for ``backward``."""
+        c, s, p = self.cfg, self.store, self.pre
+        bf = self._buffers(B)
+        T, D, I, np_, PD = bf.T, c.dim, self.inner, c.n_patches, c.patch_dim
+        rows = B * np_
+        img_dt = ops._DT[img.dtype]
+        bf.img, bf.sample_idx, bf.B = img, sample_idx, B
+        pln = bf.get("pln", (rows, PD), torch.bfloat16)
+        e0 = bf.get("e0", (rows, D), torch.float32)
+        x0 = bf.get("x0", (T, D), torch.float32)
+        if c.impl == "lucidrains":
+            pm, pr = bf.get("pmean", (rows,), torch.float32), bf.get("prstd", (rows,), torch.float32)
+            call("eavit_patchify", img, img_dt, sample_idx, B, c.channels, c.image, c.patch, 0,
+                 s.w(p + "to_patch_embedding.1.weight"), s.w(p + "to_patch_embedding.1.bias"), 1e-5, pln, pm, pr)
+            linear_fwd(pln, s.b16(p + "to_patch_embedding.2.weight"), bias=s.w(p + "to_patch_embedding.2.bias"), out_f32=e0)
+            e1 = bf.get("e1", (rows, D), torch.float32)
+            m3, r3 = bf.get("m3", (rows,), torch.float32), bf.get("r3", (rows,), torch.float32)
+            call("eavit_layernorm_fwd", e0, D, s.w(p + "to_patch_embedding.3.weight"), s.w(p + "to_patch_embedding.3.bias"),
+                 e1, F32, D, m3, r3, rows, D, 1e-5)
+            tokA = s.w(p + ("exploration_token" if c.use_explorative else "cls_token"))
+            call("eavit_embed_assemble", e1, s.w(p + "pos_embedding"), tokA, None, self.mode, B, np_, D, x0)
+        else:
+            e = p + "embeddings."
+            call("eavit_patchify", img, img_dt, sample_idx, B, c.channels, c.image, c.patch, 1, None, None, 0.0, pln, None, None)
+            w16 = s.b16(e + "patch_embeddings.projection.weight").view(D, PD)
+            linear_fwd(pln, w16, bias=s.w(e + "patch_embeddings.projection.bias"), out_f32=e0)
+            call("eavit_embed_assemble", e0, s.w(e + "position_embeddings"), s.w(e + "exploration_token"),
+                 s.w(e + "exploitation_token"), 2, B, np_, D, x0)
+        x = x0
+        for li, L in enumerate(self.L):
+            xn1 = bf.get(f"xn1_{li}", (T, D), torch.bfloat16)
+            m1, r1 = bf.get(f"m1_{li}", (T,), torch.float32), bf.get(f"r1_{li}", (T,), torch.float32)
+            call("eavit_layernorm_fwd", x, D, s.w(L["ln1"][0]), s.w(L["ln1"][1]), xn1, BF16, D, m1, r1, T, D, c.ln_eps)
+            qkv = bf.get(f"qkv_{li}", (T, 3 * I), torch.bfloat16)
+            linear_fwd(xn1, self._qkv(L, "w16"), bias=self._qkv(L, "b"), out_bf16=qkv)
+            o = bf.get(f"o_{li}", (T, I), torch.bfloat16)
+            lse = bf.get(f"lse_{li}", (T, c.heads), torch.float32)
+            call("eavit_attention_fwd", qkv, bf.seq_start, bf.nseq, bf.max_len, c.heads, c.dim_head,
+                 float(c.dim_head) ** -0.5, o, lse)
+            xmid = bf.get(f"xmid_{li}", (T, D), torch.float32)
+            linear_fwd(o, s.b16(L["o_w"]), bias=s.w(L["o_b"]), residual=x, out_f32=xmid)
+            xn2 = bf.get(f"xn2_{li}", (T, D), torch.bfloat16)
+            m2, r2 = bf.get(f"m2_{li}", (T,), torch.float32), bf.get(f"r2_{li}", (T,), torch.float32)
+            call("eavit_layernorm_fwd", xmid, D, s.w(L["ln2"][0]), s.w(L["ln2"][1]), xn2, BF16, D, m2, r2, T, D, c.ln_eps)
+            hpre = bf.get(f"hpre_{li}", (T, c.mlp_dim), torch.bfloat16)
+            hact = bf.get(f"hact_{li}", (T, c.mlp_dim), torch.bfloat16)
+            linear_fwd(xn2, s.b16(L["w1"]), bias=s.w(L["b1"]), act=ops.ACT_GELU, out_bf16=hact, out_pre=hpre)
+            xo = bf.get(f"x_{li + 1}", (T, D), torch.float32)
+            linear_fwd(hact, s.b16(L["w2"]), bias=s.w(L["b2"]), residual=xmid, out_f32=xo)
+            x = xo
+        nf = 2 * B
+        pooled = bf.get("pooled", (nf, D), torch.float32)
+        call("eavit_gather_rows", x, D, bf.pool_rows, pooled, D, nf, D)
+        feat = bf.get("feat", (nf, D), torch.float32)
+        mf, rf = bf.get("mf", (nf,), torch.float32), bf.get("rf", (nf,), torch.float32)
+        fn = (p + "transformer.norm.") if c.impl == "lucidrains" else (p + "layernorm.")
+        call("eavit_layernorm_fwd", pooled, D, s.w(fn + "weight"), s.w(fn + "bias"), feat, F32, D, mf, rf, nf, D, c.ln_eps)
+        return feat
+
+    # ---- backward --------------------------------------------------------------------------------
+    def backward(self, dfeat: torch.Tensor):
+        """dfeat fp32 [2B, D]; accumulates every parameter gradient into ``store.grad``."""
+        c, s, p = self.cfg, self.store, self.pre
+        B = dfeat.shape[0] // 2
+        bf = self.buf[B]
+        T, D, I, np_, PD = bf.T, c.dim, self.inner, c.n_patches, c.patch_dim
+        nf = 2 * B
+        fn = (p + "transformer.norm.") if c.impl == "lucidrains" else (p + "layernorm.")
+        dpool = bf.get("dpool", (nf, D), torch.float32)
+        call("eavit_layernorm_bwd", dfeat, F32, D, bf.t["pooled"], D, bf.t["mf"], bf.t["rf"], s.w(fn + "weight"),
+             None, D, dpool, D, None, D, s.g(fn + "weight"), s.g(fn + "bias"), nf, D)
+        dxa = bf.get("dxa", (T, D), torch.float32)
+        dxb = bf.get("dxb", (T, D), torch.float32)
+        dx16 = bf.get("dx16", (T, D), torch.bfloat16)
+        call("eavit_zero", dxa, T * D * 4)
+        call("eavit_zero", dx16, T * D * 2)
+        if self.mode == 1:
+            dsum = bf.get("dpool_sum", (B, D), torch.float32)
+            call("eavit_add_f32", dpool[:B], dpool[B:], dsum, B * D)
+            call("eavit_scatter_rows", dsum, D, bf.pool_rows, dxa, D, dx16, D, B, D)
+        else:
+            call("eavit_scatter_rows", dpool, D, bf.pool_rows, dxa, D, dx16, D, nf, D)
+        dx, dx_other = dxa, dxb
+        dh = bf.get("dh", (T, c.mlp_dim), torch.bfloat16)
+        dxn = bf.get("dxn", (T, D), torch.float32)
+        do = bf.get("do", (T, I), torch.bfloat16)
+        dqkv = bf.get("dqkv", (T, 3 * I), torch.bfloat16)
+        for li in reversed(range(c.depth)):
+            L = self.L[li]
+            x_in = bf.t["x0"] if li == 0 else bf.t[f"x_{li}"]
+            # MLP2: x_out = xmid + hact W2^T + b2
+            linear_bwd(dx16, bf.t[f"hact_{li}"], s.b16(L["w2"]), dW=s.g(L["w2"]), db=s.g(L["b2"]), dx_bf16=dh,
+                       act=ops.ACT_GELU_BWD, aux=bf.t[f"hpre_{li}"])
+            # MLP1: hpre = xn2 W1^T + b1
+            linear_bwd(dh, bf.t[f"xn2_{li}"], s.b16(L["w1"]), dW=s.g(L["w1"]), db=s.g(L["b1"]), dx_f32=dxn)
+            call("eavit_layernorm_bwd", dxn, F32, D, bf.t[f"xmid_{li}"], D, bf.t[f"m2_{li}"], bf.t[f"r2_{li}"],
+                 s.w(L["ln2"][0]), dx, D, dx_other, D, dx16, D, s.g(L["ln2"][0]), s.g(L["ln2"][1]), T, D)
+            dx, dx_other = dx_other, dx
+            # out-proj: xmid = x + o Wo^T + bo
+            linear_bwd(dx16, bf.t[f"o_{li}"], s.b16(L["o_w"]), dW=s.g(L["o_w"]), db=s.g(L["o_b"]), dx_bf16=do)
+            call("eavit_attention_bwd", bf.t[f"qkv_{li}"], bf.t[f"o_{li}"], do, bf.t[f"lse_{li}"], bf.seq_start, bf.nseq,
+                 bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, dqkv)
+            linear_bwd(dqkv, bf.t[f"xn1_{li}"], self._qkv(L, "w16"), dW=self._qkv(L, "gw"), db=self._qkv(L, "gb"), dx_f32=dxn)
+            call("eavit_layernorm_bwd", dxn, F32, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
+                 dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), T, D)
+            dx, dx_other = dx_other, dx
+        # embedding
+        rows = B * np_
+        img, sidx = bf.img, bf.sample_idx
+        img_dt = ops._DT[img.dtype]
+        if c.impl == "lucidrains":
+            g = bf.get("g_embed", (rows, D), torch.float32)
+            tok = p + ("exploration_token" if c.use_explorative else "cls_token")
+            call("eavit_embed_assemble_bwd", dx, self.mode, B, np_, D, g, None, s.g(p + "pos_embedding"), s.g(tok), None)
+            de16 = bf.get("de16", (rows, D), torch.bfloat16)
+            call("eavit_layernorm_bwd", g, F32, D, bf.t["e0"], D, bf.t["m3"], bf.t["r3"], s.w(p + "to_patch_embedding.3.weight"),
+                 None, D, None, D, de16, D, s.g(p + "to_patch_embedding.3.weight"), s.g(p + "to_patch_embedding.3.bias"), rows, D)
+            dpln = bf.get("dpln", (rows, PD), torch.float32)
+            linear_bwd(de16, bf.t["pln"], s.b16(p + "to_patch_embedding.2.weight"), dW=s.g(p + "to_patch_embedding.2.weight"),
+                       db=s.g(p + "to_patch_embedding.2.bias"), dx_f32=dpln)
+            call("eavit_patchify_ln_bwd", img, img_dt, sidx, B, c.channels, c.image, c.patch, 0,
+                 s.w(p + "to_patch_embedding.1.weight"), bf.t["pmean"], bf.t["prstd"], dpln,
+                 s.g(p + "to_patch_embedding.1.weight"), s.g(p + "to_patch_embedding.1.bias"))
+        else:
+            e = p + "embeddings."
+            g16 = bf.get("de16", (rows, D), torch.bfloat16)
+            call("eavit_embed_assemble_bwd", dx, 2, B, np_, D, None, g16, s.g(e + "position_embeddings"),
+                 s.g(e + "exploration_token"), s.g(e + "exploitation_token"))
+            linear_bwd(g16, bf.t["pln"], None, dW=s.g(e + "patch_embeddings.projection.weight").view(D, PD),
+                       db=s.g(e + "patch_embeddings.projection.bias"))
+
+
+class Heads:
+    """model.py:227-246 heads on the pooled features F [2B, D] (fp32 CUDA-core kernels: 0.02 % of the FLOPs)."""
+
+    def __init__(self, cfg: HotPathConfig, store: ParamStore, n_actions: int, ext_uses_int_critic: bool):
+        self.cfg, self.s, self.A = cfg, store, n_actions
+        self.bug = ext_uses_int_critic      # model.py:321 (HG branch): value_ext = critic_int(...)
+        self.buf: Dict[int, _Buffers] = {}
+        self.coef = 0.5                     # attn_aggregation_op = 'mean' (model.py:284-286)
+
+    def forward(self, feat: torch.Tensor):
+        s, D, A = self.s, self.cfg.dim, self.A
+        R = feat.shape[0]
+        B = R // 2
+        bf = self.buf.setdefault(B, _Buffers(feat.device))
+        bf.feat = feat
+        E = bf.get("E", (R, D), torch.float32)
+        call("eavit_sgemm_small", feat, D, 0, s.w("model.extra_layer.0.weight"), D, 0, s.w("model.extra_layer.0.bias"), None,
+             E, D, R, D, D, 1, 0)
+        v = bf.get("v", (R,), torch.float32)
+        wi, bi = s.w("model.critic_int.weight"), s.w("model.critic_int.bias")
+        we, be = s.w("model.critic_ext.weight"), s.w("model.critic_ext.bias")
+        if self.bug:
+            call("eavit_heads_value_fwd", E, feat, wi, bi, wi, bi, R, R, D, v)
+        else:
+            call("eavit_heads_value_fwd", E, feat, wi, bi, we, be, B, R, D, v)
+        comb = bf.get("comb", (B, D), torch.float32)
+        call("eavit_combine_fwd", feat, comb, B, D, self.coef)
+        a1 = bf.get("a1", (B, D), torch.float32)
+        call("eavit_sgemm_small", comb, D, 0, s.w("model.actor.0.weight"), D, 0, s.w("model.actor.0.bias"), None, a1, D, B, D, D, 1, 0)
+        pol = bf.get("policy", (B, A), torch.float32)
+        call("eavit_sgemm_small", a1, D, 0, s.w("model.actor.2.weight"), D, 0, s.w("model.actor.2.bias"), None, pol, A, B, A, D, 0, 0)
+        return pol, v[B:], v[:B]            # policy, value_ext, value_int
+
+    def backward(self, dpol: torch.Tensor, dv: torch.Tensor) -> torch.Tensor:
+        """dpol [B,A], dv [2B] = (dv_int | dv_ext) in feature-row order.  Returns dfeat [2B, D]."""
+        s, D, A = self.s, self.cfg.dim, self.A
+        B = dpol.shape[0]
+        R = 2 * B
+        bf = self.buf[B]
+        feat, E, comb, a1 = bf.feat, bf.t["E"], bf.t["comb"], bf.t["a1"]
+        dE, dF = bf.get("dE", (R, D), torch.float32), bf.get("dF", (R, D), torch.float32)
+        wi, we = s.w("model.critic_int.weight"), s.w("model.critic_ext.weight")
+        gi, ge = s.g("model.critic_int.weight"), s.g("model.critic_ext.weight")
+        gbi, gbe = s.g("model.critic_int.bias"), s.g("model.critic_ext.bias")
+        if self.bug:
+            call("eavit_heads_value_bwd", E, feat, dv, wi, wi, R, R, D, dE, dF, gi, gbi, gi, gbi)
+        else:
+            call("eavit_heads_value_bwd", E, feat, dv, wi, we, B, R, D, dE, dF, gi, gbi, ge, gbe)
+        # extra_layer: E = relu(F Wx^T + bx);  dE already masked
+        call("eavit_sgemm_small", dE, D, 1, feat, D, 1, None, None, s.g("model.extra_layer.0.weight"), D, D, D, R, 0, 1)
+        call("eavit_colsum", dE, F32, D, s.g("model.extra_layer.0.bias"), R, D)
+        call("eavit_sgemm_small", dE, D, 0, s.w("model.extra_layer.0.weight"), D, 1, None, None, dF, D, R, D, D, 0, 1)
+        # actor: policy = a1 Wa2^T + b ; a1 = relu(comb Wa0^T + b)
+        call("eavit_sgemm_small", dpol, A, 1, a1, D, 1, None, None, s.g("model.actor.2.weight"), D, A, D, B, 0, 1)
+        call("eavit_colsum", dpol, F32, A, s.g("model.actor.2.bias"), B, A)
+        da1 = bf.get("da1", (B, D), torch.float32)
+        call("eavit_sgemm_small", dpol, A, 0, s.w("model.actor.2.weight"), D, 1, None, a1, da1, D, B, D, A, 0, 0)
+        call("eavit_sgemm_small", da1, D, 1, comb, D, 1, None, None, s.g("model.actor.0.weight"), D, D, D, B, 0, 1)
+        call("eavit_colsum", da1, F32, D, s.g("model.actor.0.bias"), B, D)
+        dcomb = bf.get("dcomb", (B, D), torch.float32)
+        call("eavit_sgemm_small", da1, D, 0, s.w("model.actor.0.weight"), D, 1, None, None, dcomb, D, B, D, D, 0, 0)
+        call("eavit_combine_bwd", dcomb, dF, B, D, self.coef)
+        return dF
+
+
+class RNDNet:
+    """model.py:366-416 conv tower + FC stack; ``net`` = 'predictor' (trainable) or 'target' (frozen)."""
+
+    CONVS = ((8, 4, 1, 32), (4, 2, 32, 64), (3, 1, 64, 64))   # (kernel, stride, Cin, Cout)
+
+    def __init__(self, store: ParamStore, net: str, image: int = 84, out: int = 512):
+        self.s, self.net, self.image, self.out = store, net, image, out
+        self.pre = f"rnd.{net}."
+        self.fcs = (7, 9, 11) if net == "predictor" else (7,)
+        self.buf: Dict[int, _Buffers] = {}
+        h = image
+        self.sizes = []
+        for k, st, ci, co in self.CONVS:
+            oh = (h - k) // st + 1
+            self.sizes.append((h, oh))
+            h = oh
+        self.flat_dim = h * h * 64
+
+    def forward(self, obs: torch.Tensor, B: int, sample_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """obs fp32 [N,1,H,W] (normalised, clipped); returns features fp32 [B, out]."""
+        s, p = self.s, self.pre
+        bf = self.buf.setdefault(B, _Buffers(obs.device))
+        x, x_dt, sidx = obs, ops._DT[obs.dtype], sample_idx
+        for ci, ((k, st, cin, cout), (h, oh)) in enumerate(zip(self.CONVS, self.sizes)):
+            K = cin * k * k
+            col = bf.get(f"col{ci}", (B * oh * oh, K), torch.bfloat16)
+            call("eavit_im2col", x, x_dt, sidx, B, h, h, cin, k, k, st, col)
+            act = bf.get(f"act{ci}", (B * oh * oh, cout), torch.bfloat16)
+            name = p + f"{2 * ci}."
+            linear_fwd(col, s.b16(name + "weight").view(cout, K), bias=s.w(name + "bias"), act=ops.ACT_LRELU, out_bf16=act)
+            x, x_dt, sidx = act, BF16, None
+        hw = self.sizes[-1][1] ** 2
+        flat = bf.get("flat", (B, self.flat_dim), torch.bfloat16)
+        call("eavit_nhwc_to_flat", x, B, hw, 64, flat)
+        h16 = flat
+        out = None
+        for j, k in enumerate(self.fcs):
+            last = j == len(self.fcs) - 1
+            name = p + f"{k}."
+            if last:
+                out = bf.get("out", (B, self.out), torch.float32)
+                linear_fwd(h16, s.b16(name + "weight"), bias=s.w(name + "bias"), out_f32=out)
+            else:
+                nxt = bf.get(f"fc{j}", (B, self.out), torch.bfloat16)
+                linear_fwd(h16, s.b16(name + "weight"), bias=s.w(name + "bias"), act=ops.ACT_RELU, out_bf16=nxt)
+                h16 = nxt
+        return out
+
+    def backward(self, dout16: torch.Tensor):
+        """dout16 bf16 [B, out]; accumulates predictor gradients into ``store.grad``."""
+        s, p = self.s, self.pre
+        B = dout16.shape[0]
+        bf = self.buf[B]
+        d = dout16
+        nfc = len(self.fcs)
+        for j in reversed(range(nfc)):
+            name = p + f"{self.fcs[j]}."
+            x16 = bf.t["flat"] if j == 0 else bf.t[f"fc{j - 1}"]
+            if j == 0:
+                dflat = bf.get("dflat", (B, self.flat_dim), torch.bfloat16)
+                linear_bwd(d, x16, s.b16(name + "weight"), dW=s.g(name + "weight"), db=s.g(name + "bias"), dx_bf16=dflat)
+                d = dflat
+            else:
+                dprev = bf.get(f"dfc{j - 1}", (B, self.out), torch.bfloat16)
+                linear_bwd(d, x16, s.b16(name + "weight"), dW=s.g(name + "weight"), db=s.g(name + "bias"), dx_bf16=dprev,
+                           act=ops.ACT_RELU_BWD, aux=x16)
+                d = dprev
+        hw = self.sizes[-1][1] ** 2
+        dact = bf.get("dact2", (B * hw, 64), torch.bfloat16)
+        call("eavit_flat_to_nhwc_lrelu", d, bf.t["act2"], B, hw, 64, dact)
+        for ci in (2, 1, 0):
+            k, st, cin, cout = self.CONVS[ci]
+            h, oh = self.sizes[ci]
+            K = cin * k * k
+            name = p + f"{2 * ci}."
+            if ci == 0:
+                linear_bwd(dact, bf.t["col0"], None, dW=s.g(name + "weight").view(cout, K), db=s.g(name + "bias"))
+                break
+            dcol = bf.get(f"dcol{ci}", (B * oh * oh, K), torch.bfloat16)
+            linear_bwd(dact, bf.t[f"col{ci}"], s.b16(name + "weight").view(cout, K), dW=s.g(name + "weight").view(cout, K),
+                       db=s.g(name + "bias"), dx_bf16=dcol)
+            dprev = bf.get(f"dact{ci - 1}", (B * h * h, cin), torch.bfloat16)
+            call("eavit_col2im_lrelu", dcol, bf.t[f"act{ci - 1}"], B, h, h, cin, k, k, st, dprev)
+            dact = dprev

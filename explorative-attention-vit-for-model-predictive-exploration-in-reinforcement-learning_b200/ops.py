@@ -160,3 +160,70 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                  out_pre_bf16=None if out_pre is None else out_pre.data_ptr(),
                  ldc=ldc, act=act, atomic_f32=int(atomic), split_k=split_k)
     check(_lib.lib().eavit_gemm_bf16(ctypes.byref(g), _st()), "gemm_bf16")
+
+
+# ------------------------------------------------------------------------------------------- raw ABI access
+# One-letter argument codes: p = device pointer (torch.Tensor or None), i = int, l = long long, f = float,
+# d = double.  The trailing `void* stream` of every entry point is appended automatically.
+_SPECS = {
+    "eavit_layernorm_fwd": "plpppilppiif",
+    "eavit_layernorm_bwd": "pilplppppl" "pl" "pl" "ppii",
+    "eavit_colsum": "pilpii",
+    "eavit_gather_rows": "plpplii",
+    "eavit_scatter_rows": "plppl" "pl" "ii",
+    "eavit_cast_f32_bf16": "ppl",
+    "eavit_add_f32": "pppl",
+    "eavit_zero": "pl",
+    "eavit_attention_fwd": "ppiiiifpp",
+    "eavit_attention_bwd": "pppppiiiifp",
+    "eavit_patchify": "pipiiiiippfppp",
+    "eavit_patchify_ln_bwd": "pipiiiiipppppp",
+    "eavit_embed_assemble": "ppppiiiip",
+    "eavit_embed_assemble_bwd": "piiiippppp",
+    "eavit_sgemm_small": "pliplippplliiii".replace("ll", "l", 0),
+    "eavit_heads_value_fwd": "ppppppiiip",
+    "eavit_heads_value_bwd": "pppppiiipppppp",
+    "eavit_combine_fwd": "ppiif",
+    "eavit_combine_bwd": "ppiif",
+    "eavit_ppo_loss": "ppppppppiifffpppp",
+    "eavit_rnd_loss": "pppiifppp",
+    "eavit_gather_batch": "piipppppppppp",
+    "eavit_im2col": "pipiiiiiiip",
+    "eavit_col2im_lrelu": "ppiiiiiiip",
+    "eavit_nhwc_to_flat": "piiip",
+    "eavit_flat_to_nhwc_lrelu": "ppiiip",
+    "eavit_adam_step": "ppppplpfffff",
+    "eavit_sumsq_f32": "plp",
+    "eavit_clip_by_norm": "plpf",
+}
+_SPECS["eavit_sgemm_small"] = "pli" "pli" "pp" "pl" "iiiii"
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float, "d": ctypes.c_double}
+_bound = {}
+
+
+def _bind(name):
+    fn = getattr(_lib.lib(), name)
+    spec = _SPECS[name]
+    fn.argtypes = [_CT[c] for c in spec] + [ctypes.c_void_p]
+    fn.restype = ctypes.c_int
+    _bound[name] = (fn, spec)
+    return _bound[name]
+
+
+def call(name: str, *args):
+    """Invoke a C-ABI entry point with torch tensors / python scalars; raises on non-zero status."""
+    fn, spec = _bound.get(name) or _bind(name)
+    assert len(args) == len(spec), (name, len(args), len(spec))
+    conv = []
+    for a, c in zip(args, spec):
+        if c == "p":
+            if a is None:
+                conv.append(None)
+            else:
+                assert a.is_cuda, f"{name}: CUDA tensors only"
+                conv.append(a.data_ptr())
+        else:
+            conv.append(a)
+    rc = fn(*conv, torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        check(rc, name[len("eavit_"):])

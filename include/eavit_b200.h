@@ -124,6 +124,100 @@ typedef struct {
 } eavit_gemm_args;
 int eavit_gemm_bf16(const eavit_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------ LayerNorm / small row ops */
+
+/* nn.LayerNorm forward over rows of x fp32 [T,D] (vit.py:28,:47,:78,:113; HF layernorm_*).  y dtype
+ * EAVIT_BF16 (GEMM operand) or EAVIT_F32; mean/rstd [T] saved for backward (both NULL to skip). */
+int eavit_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, int y_dtype,
+                        long long ldy, float* mean, float* rstd, int T, int D, float eps, void* stream);
+/* dx = dres + LN'(dy); dgamma/dbeta accumulated with atomics (+=).  dy dtype F32 or BF16; dres, dx,
+ * dx_bf16, dgamma/dbeta optional. */
+int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const float* x, long long ldx, const float* mean,
+                        const float* rstd, const float* gamma, const float* dres, long long lddres, float* dx,
+                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, int T, int D,
+                        void* stream);
+/* out[c] += sum_r x[r,c]  (bias gradients); x dtype BF16 or F32. */
+int eavit_colsum(const void* x, int x_dtype, long long ldx, float* out, int T, int N, void* stream);
+/* dst[i,:] = src[rows[i],:]  /  dst[rows[i],:] = src[i,:]  (pooled token x[:,0], vit.py:162). */
+int eavit_gather_rows(const float* src, long long lds, const int* rows, float* dst, long long ldd, int n, int D, void* stream);
+int eavit_scatter_rows(const float* src, long long lds, const int* rows, float* dst, long long ldd, void* dst_bf16,
+                       long long lddb, int n, int D, void* stream);
+int eavit_cast_f32_bf16(const float* in, void* out_bf16, long long n, void* stream);
+int eavit_add_f32(const float* a, const float* b, float* out, long long n, void* stream);
+int eavit_zero(void* ptr, long long bytes, void* stream);
+
+/* ------------------------------------------------------------------ attention (vit.py:60-73) */
+
+/* softmax(q k^T * scale) v per (sequence, head); qkv bf16 [T, 3*H*Dh] (q|k|v, each (h d)); out bf16
+ * [T, H*Dh]; lse fp32 [T,H] (may be NULL for inference); seq_start int32 [nseq+1] token offsets;
+ * max_len <= 256; Dh in {32, 64}. */
+int eavit_attention_fwd(const void* qkv, const int* seq_start, int nseq, int max_len, int H, int Dh, float scale,
+                        void* out, float* lse, void* stream);
+int eavit_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const int* seq_start,
+                        int nseq, int max_len, int H, int Dh, float scale, void* dqkv, void* stream);
+
+/* ------------------------------------------------------------------ patch embedding (vit.py:109-158) */
+
+/* [B,C,HW,HW] image (EAVIT_U8: value/255 as train.py:605; or EAVIT_F32) -> bf16 patches [B*np, C*P*P];
+ * order_cpp = 0: lucidrains '(p1 p2 c)' (vit.py:110); 1: conv order '(c p1 p2)' (HF ViTPatchEmbeddings).
+ * gamma/beta != NULL fuses LayerNorm(patch_dim) (vit.py:111) and saves mean/rstd [B*np].
+ * sample_idx (int64 [B], may be NULL) gathers samples from a larger device-resident rollout. */
+int eavit_patchify(const void* img, int img_dtype, const long long* sample_idx, int B, int C, int HW, int P, int order_cpp,
+                   const float* gamma, const float* beta, float eps, void* out_bf16, float* mean, float* rstd,
+                   void* stream);
+/* dgamma/dbeta (+=) of that LayerNorm given dpln fp32 [B*np, PD]. */
+int eavit_patchify_ln_bwd(const void* img, int img_dtype, const long long* sample_idx, int B, int C, int HW, int P,
+                          int order_cpp, const float* gamma, const float* mean, const float* rstd, const float* dpln,
+                          float* dgamma, float* dbeta, void* stream);
+/* token prepend + positional add into the flat residual stream (mode 0: lucidrains explorative pair with
+ * the reference's token bug, vit.py:141-156; 1: single CLS sequence; 2: HF pair, vit_hg.py:121-145). */
+int eavit_embed_assemble(const float* e, const float* pos, const float* tokA, const float* tokB, int mode, int B, int np,
+                         int D, float* x, void* stream);
+int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, float* g, void* g_bf16, float* dpos,
+                             float* dtokA, float* dtokB, void* stream);
+
+/* ------------------------------------------------------------------ heads + losses (model.py, agents.py) */
+
+/* small fp32 GEMM for the heads: C (+)= mask(relu?(op(A) op(B) + bias)). */
+int eavit_sgemm_small(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
+                      const float* bias, const float* mask_aux, float* C, long long ldc, int M, int N, int K, int relu,
+                      int accumulate, void* stream);
+/* v[r] = (E[r]+F[r]) . w(r) + b(r): critic(extra_layer(x)+x), model.py:276/:280 (w = A for r < split). */
+int eavit_heads_value_fwd(const float* E, const float* F, const float* wA, const float* bA, const float* wB,
+                          const float* bB, int split, int R, int D, float* v, void* stream);
+int eavit_heads_value_bwd(const float* E, const float* F, const float* dv, const float* wA, const float* wB, int split,
+                          int R, int D, float* dE, float* dF, float* dwA, float* dbA, float* dwB, float* dbB, void* stream);
+int eavit_combine_fwd(const float* F, float* comb, int B, int D, float coef, void* stream);     /* model.py:284-288 */
+int eavit_combine_bwd(const float* dcomb, float* dF, int B, int D, float coef, void* stream);
+/* agents.py:455-493 fused forward+backward; stats fp32[16]: [1] actor [2] critic_ext [3] critic_int
+ * [4] entropy [5] rnd [6] approx_kl [7] max_kl [8] clipfrac.  Gradients are multiplied by grad_scale. */
+int eavit_ppo_loss(const float* logits, const float* old_logits, const long long* actions, const float* adv,
+                   const float* v_ext, const float* v_int, const float* tgt_ext, const float* tgt_int, int B, int A,
+                   float ppo_eps, float ent_coef, float grad_scale, float* dlogits, float* dv_ext, float* dv_int,
+                   float* stats, void* stream);
+/* agents.py:333-338 masked RND loss; stats[5] += loss; dpred bf16 [B,R]. */
+int eavit_rnd_loss(const float* pred, const float* tgt, const float* mask, int B, int R, float grad_scale, void* dpred_bf16,
+                   float* per_sample, float* stats, void* stream);
+
+/* minibatch gather of the per-sample scalars (replaces agents.py:289-303 host indexing): out[i] = in[idx[i]]. */
+int eavit_gather_batch(const long long* idx, int B, int A, const float* tgt_ext, const float* tgt_int, const float* adv,
+                       const long long* actions, const float* old_logits, float* o_tgt_ext, float* o_tgt_int, float* o_adv,
+                       long long* o_actions, float* o_old_logits, void* stream);
+
+/* ------------------------------------------------------------------ RND convolutions (model.py:368-416) */
+int eavit_im2col(const void* in, int in_dtype, const long long* sample_idx /* may be NULL */, int B, int H, int W, int C, int KH, int KW, int stride, void* col_bf16,
+                 void* stream);
+int eavit_col2im_lrelu(const void* dcol_bf16, const void* act_bf16, int B, int H, int W, int C, int KH, int KW, int stride,
+                       void* din_bf16, void* stream);
+int eavit_nhwc_to_flat(const void* act_bf16, int B, int HW, int C, void* flat_bf16, void* stream);
+int eavit_flat_to_nhwc_lrelu(const void* dflat_bf16, const void* act_bf16, int B, int HW, int C, void* dact_bf16, void* stream);
+
+/* ------------------------------------------------------------------ optimiser (agents.py:129,:508) */
+int eavit_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, long long* step, float lr,
+                    float beta1, float beta2, float eps, float grad_scale, void* stream);
+int eavit_sumsq_f32(const float* x, long long n, float* out, void* stream);                       /* utils.py:141-170 */
+int eavit_clip_by_norm(float* g, long long n, const float* sumsq, float max_norm, void* stream);  /* agents.py:497-499 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,199 @@
+"""GPU parity of the drop-in model / agent (C-ABI kernels) against the CPU oracle and the reference goldens.
+
+Tolerance (BASELINE.json north_star): 1e-2 relative for bf16 logits, values, intrinsic rewards and gradients.
+"Relative" is norm-wise: ||a - b|| / ||b|| (element-wise relative error is meaningless at zero crossings)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def make_agent(cfg: O.OracleConfig, E, T, seed=7, **conf):
+    import eavit_b200  # noqa
+    from eavit_b200 import agents, config, utils
+    keys = {"ViTlucidrains_dropout": 0.0, "ViTlucidrains_emb_dropout": 0.0}
+    if cfg.impl == "hg":
+        keys.update({"ViT_implementation_type": 1, "ViTHG_hidden_size": cfg.dim, "ViTHG_num_hidden_layers": cfg.depth,
+                     "ViTHG_num_attention_heads": cfg.heads, "ViTHG_intermediate_size": cfg.mlp_dim,
+                     "ViTHG_patch_size": cfg.patch, "extracted_feature_embedding_dim": cfg.dim})
+    else:
+        keys.update({"ViTlucidrains_use_explorativeAttn": cfg.use_explorative, "ViTlucidrains_dim": cfg.dim,
+                     "ViTlucidrains_depth": cfg.depth, "ViTlucidrains_heads": cfg.heads, "ViTlucidrains_dim_head": cfg.dim_head,
+                     "ViTlucidrains_mlp_dim": cfg.mlp_dim, "ViTlucidrains_patch_size": cfg.patch})
+    keys.update(conf)
+    config.load_config(None, **keys)
+    N = E * T
+    agent = agents.RNDAgent(84, cfg.n_actions, utils.Env_action_space_type.DISCRETE, E, T, cfg.gamma, GAE_Lambda=cfg.lam,
+                            learning_rate=cfg.lr, ent_coef=cfg.ent_coef, epoch=cfg.epoch, batch_size=N // cfg.mini_batch,
+                            ppo_eps=cfg.ppo_eps, use_cuda=True, representation_lr_method="None", device="cuda",
+                            logger=utils.Logger())
+    P = O.init_params(cfg, seed=seed)
+    missing, unexpected = agent.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
+    assert not missing and not unexpected
+    return agent, P
+
+
+CFGS = {
+    "lucid": O.OracleConfig(lr=1e-3, epoch=2, mini_batch=4),
+    "cls": O.OracleConfig(use_explorative=False),
+    "hg": O.OracleConfig(impl="hg", patch=12, dim=128, depth=2, heads=2, dim_head=64, mlp_dim=256, ln_eps=1e-12, lr=1e-3,
+                         epoch=1, mini_batch=4),
+}
+
+
+@pytest.mark.parametrize("which", ["lucid", "cls", "hg"])
+def test_forward_vs_reference_golden(golden_dir, which):
+    """state_dict drop-in + forward: same weights loaded by reference key names -> same outputs as the reference."""
+    G = np.load(os.path.join(golden_dir, f"golden_{which}.npz"))
+    agent, P = make_agent(CFGS[which], 2, 16)
+    rng = np.random.default_rng(11)
+    state_u8 = rng.integers(0, 256, (3, 4, 84, 84), dtype=np.uint8)
+    state = np.float32(state_u8) / 255.0
+    with torch.no_grad():
+        pol, ve, vi = agent.model(torch.tensor(state).cuda())
+    assert pol.shape == (3, 18) and ve.shape == (3, 1) and vi.shape == (3, 1)
+    assert rel(pol.cpu().numpy(), G["fwd_policy"]) < TOL
+    assert rel(ve.cpu().numpy(), G["fwd_value_ext"]) < TOL
+    assert rel(vi.cpu().numpy(), G["fwd_value_int"]) < TOL
+    # raw uint8 frames (divided by 255 in-kernel) give the same result as the pre-divided float32 input
+    with torch.no_grad():
+        pol8, _, _ = agent.model(torch.tensor(state_u8).cuda())
+    assert torch.equal(pol8, pol)
+    # get_action: logits / values within tolerance; sampled action equals the oracle's for the same uniform draw
+    np.random.seed(5)
+    a, v1, v2, lg = agent.get_action(state)
+    assert a.dtype == np.int64 and lg.dtype == np.float32 and lg.shape == (3, 18)
+    assert rel(lg, G["act_logits"]) < TOL and rel(v1, G["act_value_ext"]) < TOL and rel(v2, G["act_value_int"]) < TOL
+    u = np.random.default_rng(0)  # noqa  (only documents that the draw comes from np.random, agents.py:206)
+    # intrinsic reward
+    obs = rng.normal(0, 1, (5, 1, 84, 84)).clip(-5, 5)
+    ir = agent.compute_intrinsic_reward(obs)
+    assert ir.dtype == np.float32 and ir.shape == (5,)
+    assert rel(ir, G["intrinsic_reward"]) < TOL
+    if which == "lucid":
+        from eavit_b200.vit import ViT_Attn
+        with torch.no_grad():
+            fe = agent.model.feature(torch.tensor(state).cuda(), attn_type=ViT_Attn.EXPLORATIVE_ATTN)
+            fx = agent.model.feature(torch.tensor(state).cuda(), attn_type=ViT_Attn.EXPLOITATIVE_ATTN)
+        assert rel(fe.cpu().numpy(), G["fwd_feat_explorative"]) < TOL
+        assert rel(fx.cpu().numpy(), G["fwd_feat_exploitative"]) < TOL
+
+
+def _batch(cfg, E, T, seed=21):
+    roll = O.synth_rollout(E=E, T=T, seed=seed)
+    orm, rrm, flt = O.RunningMeanStd(shape=(1, 1, 84, 84)), O.RunningMeanStd(), O.RewardForwardFilter(cfg.int_gamma)
+    return O.prepare_update(cfg, T, E, roll, orm, rrm, flt)
+
+
+@pytest.mark.parametrize("which", ["lucid", "cls", "hg"])
+def test_loss_and_gradients_vs_oracle(which):
+    """One minibatch: every loss term and every parameter gradient vs torch-fp32 autograd of the oracle."""
+    cfg = CFGS[which]
+    E, T = 2, 16
+    agent, P = make_agent(cfg, E, T)
+    args = _batch(cfg, E, T)
+    states, te, ti, y, adv, obs, old = args
+    N = E * T
+    B = 16
+    idx = np.random.default_rng(1).permutation(N)[:B]
+    mask = (np.random.default_rng(2).random(B) < 0.5).astype(np.float32)
+    # oracle
+    for k in O.trainable_names(P):
+        P[k].requires_grad_(True)
+    old_flat = torch.tensor(old).permute(1, 0, 2).contiguous().view(-1, cfg.n_actions)
+    ti_ = torch.from_numpy(idx)
+    loss, terms, (pol_o, ve_o, vi_o) = O.ppo_rnd_loss(
+        P, cfg, torch.FloatTensor(states)[ti_], torch.FloatTensor(te)[ti_], torch.FloatTensor(ti)[ti_], torch.LongTensor(y)[ti_],
+        torch.FloatTensor(adv)[ti_], torch.FloatTensor(obs)[ti_], old_flat[ti_], torch.tensor(mask))
+    loss.backward()
+    # kernels
+    R = agent.upload_rollout(*args)
+    stats = torch.zeros(16, device="cuda")
+    agent.train_step(R, torch.from_numpy(idx).cuda(), torch.tensor(mask).cuda(), stats, apply=False)
+    s = stats.cpu().numpy()
+    got = dict(actor=s[1], critic_ext=s[2], critic_int=s[3], entropy=s[4], rnd=s[5])
+    for k, v in got.items():
+        assert abs(v - terms[k]) <= TOL * max(abs(terms[k]), 1e-3), (k, v, terms[k])
+    st = agent.runtime().store
+    worst = {}
+    flat_ref, flat_got = [], []
+    for k in O.trainable_names(P):
+        g_ref = P[k].grad
+        g = st.g(k).cpu()
+        if g_ref is None:
+            assert float(g.abs().max()) == 0.0, k          # unused parameters (fact 3 / fact 4) keep a zero gradient
+            continue
+        if k.endswith("attention.key.bias"):
+            continue                                        # exactly-zero true gradient (softmax shift invariance)
+        flat_ref.append(g_ref.reshape(-1).numpy()); flat_got.append(g.reshape(-1).numpy())
+        worst[k] = rel(g.numpy(), g_ref.numpy())
+    tot = rel(np.concatenate(flat_got), np.concatenate(flat_ref))
+    assert tot < TOL, (tot, sorted(worst.items(), key=lambda kv: -kv[1])[:8])
+    # per-tensor: allow 3x the global tolerance on individual small tensors, report the worst offenders
+    bad = {k: v for k, v in worst.items() if v > 3 * TOL}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+
+
+def test_train_model_matches_oracle_trajectory():
+    """Whole update through the reference-facing call: same permutation + RND masks (bit-exact, host RNG), loss
+    terms per step within tolerance, and the parameter update points the same way as the fp32 oracle's."""
+    cfg = CFGS["lucid"]
+    E, T = 2, 16
+    agent, P = make_agent(cfg, E, T)
+    args = _batch(cfg, E, T)
+    P0 = {k: v.clone() for k, v in P.items()}
+    np.random.seed(123); torch.manual_seed(123)
+    log = O.train_model(P, cfg, *args)
+    np.random.seed(123); torch.manual_seed(123)
+    agent.train_model(*args, 1)
+    stats = agent.last_stats.cpu().numpy()
+    assert len(stats) == len(log) == cfg.epoch * cfg.mini_batch
+    for i, t in enumerate(log):
+        for j, k in ((1, "actor"), (2, "critic_ext"), (3, "critic_int"), (4, "entropy"), (5, "rnd")):
+            assert abs(stats[i, j] - t[k]) <= 3e-2 * max(abs(t[k]), 1e-2), (i, k, stats[i, j], t[k])
+    sd = agent.state_dict()
+    num = den1 = den2 = 0.0
+    for k in O.trainable_names(P):
+        d_ref = (P[k].detach() - P0[k]).reshape(-1).double().numpy()
+        d_got = (sd[k].cpu() - P0[k]).reshape(-1).double().numpy()
+        num += float(d_ref @ d_got); den1 += float(d_ref @ d_ref); den2 += float(d_got @ d_got)
+    cos = num / np.sqrt(den1 * den2)
+    assert cos > 0.9, cos
+    assert abs(np.sqrt(den2 / den1) - 1) < 0.1
+    for k in P:                                   # frozen target network untouched
+        if k.startswith("rnd.target."):
+            assert torch.equal(sd[k].cpu(), P0[k])
+
+
+def test_autograd_through_module_forward():
+    """model(state) is differentiable with torch autograd; gradients land in p.grad like the reference's."""
+    cfg = CFGS["lucid"]
+    agent, P = make_agent(cfg, 2, 16)
+    rng = np.random.default_rng(3)
+    x = torch.tensor(np.float32(rng.integers(0, 256, (4, 4, 84, 84), dtype=np.uint8)) / 255.0)
+    for k in P:
+        if k.startswith("model."):
+            P[k].requires_grad_(True)
+    pol_o, ve_o, vi_o = O.actor_critic_forward(P, x, cfg)
+    w = torch.tensor(rng.normal(size=(4, 18)), dtype=torch.float32)
+    (pol_o * w).sum().add(ve_o.sum() * 3).add(vi_o.sum() * 2).backward()
+    agent.optimizer.zero_grad()
+    pol, ve, vi = agent.model(x.cuda())
+    ((pol * w.cuda()).sum() + ve.sum() * 3 + vi.sum() * 2).backward()
+    flat_ref, flat_got = [], []
+    for name, p in agent.named_parameters():
+        if not name.startswith("model.") or P[name].grad is None:
+            continue
+        flat_ref.append(P[name].grad.reshape(-1).numpy()); flat_got.append(p.grad.detach().cpu().reshape(-1).numpy())
+    assert rel(np.concatenate(flat_got), np.concatenate(flat_ref)) < TOL
