@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Headline benchmark: PPO+RND update samples/sec of the ViT explorative-attention RND agent on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo (sm_100a kernels through the C ABI)
+    python bench.py --impl reference --steps K --warmup W   # the reference's CPU path (oracle port), host cores
+
+Workload (BASELINE.json configs[2]; configs[1] -- the CNN actor-critic -- is dead code in the
+reference and has no reference arm): lucidrains explorative-attention ViT (dim 256, depth 3, 8x32 heads, mlp 1024,
+patch 6 -> 196/197 tokens) + PPO heads + RND predictor/target, 128 envs x 128 steps per GPU (N = 16 384 samples),
+MiniBatch 32 -> 512 samples per optimiser step, dropout keys = 0.0 (the parity configuration).
+
+A "step" = one minibatch optimiser step (agents.py:284-508): batch gather, RND fwd/bwd, ViT fwd/bwd (both
+attention passes), heads, PPO/RND loss, [gradient all-reduce], Adam.   value = steps * 512 * n_gpus / time.
+`value` is timed with the rollout resident in HBM; `e2e` times the reference-facing `RNDAgent.train_model(...)`
+call with HOST numpy buffers (pinned) -- H2D of the whole rollout + all Epoch x MiniBatch steps + D2H of the stats.
+Multi-GPU: weak scaling, every rank owns 128 envs, one NCCL all-reduce of the flat gradient per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+E_PER_GPU, T, A = 128, 128, 18
+MINI_BATCH, EPOCH = 32, 4
+FLOPS_PER_SAMPLE = 6.36e9 + 58.2e6      # ViT+heads fwd+bwd + RND training, per sample
+WORKLOAD = ("cfg3: lucidrains explorative-attention ViT (expGlados3) RND agent, 128 envs x 128 steps per GPU, "
+            "minibatch 512, 4 epochs, dropout keys 0.0")
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.samples, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[1]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": sorted(reasons),
+                "power_w_max": max(float(s[3]) for s in self.samples), "samples": len(sm)}
+
+
+def synth_update_args(E, seed):
+    """Synthetic rollout in the reference's train_model argument dtypes/layouts, in pinned host memory."""
+    rng = np.random.default_rng(seed)
+    N = E * T
+
+    def pinned(shape, dtype):
+        t = torch.empty(shape, dtype=dtype)
+        try:
+            t = t.pin_memory()
+        except Exception:
+            pass
+        return t
+    states = pinned((N, 4, 84, 84), torch.float32)
+    u8 = rng.integers(0, 256, (N, 4, 84, 84), dtype=np.uint8)
+    np.divide(u8, np.float32(255.0), out=states.numpy(), dtype=np.float32)        # np.float32(total_state) / 255.
+    obs = pinned((N, 1, 84, 84), torch.float64)
+    obs.numpy()[...] = rng.normal(0, 1, (N, 1, 84, 84)).clip(-5, 5)
+    te = rng.normal(0, 1, N)
+    ti = rng.normal(0, 1, N)
+    adv = rng.normal(0, 1, N)
+    y = rng.integers(0, A, N).astype(np.int64)
+    old = rng.normal(0, 1, (T, E, A)).astype(np.float32)
+    return (states.numpy(), te, ti, y, adv, obs.numpy(), old), u8
+
+
+def make_agent(E):
+    import eavit_b200  # noqa: F401
+    from eavit_b200 import agents, config, utils
+    conf = os.path.join(ROOT, "configs", "expGlados3_lucidrains_explorative.conf")
+    config.load_config(conf, ViTlucidrains_dropout=0.0, ViTlucidrains_emb_dropout=0.0)
+    c = config.default_config
+    N = E * T
+    utils.set_seed(42)
+    agent = agents.RNDAgent(84, A, utils.Env_action_space_type.DISCRETE, E, T, float(c["Gamma"]), GAE_Lambda=float(c["GAELambda"]),
+                            learning_rate=float(c["LearningRate"]), ent_coef=float(c["Entropy"]), epoch=int(c["Epoch"]),
+                            batch_size=int(N / int(c["MiniBatch"])), ppo_eps=float(c["PPOEps"]), use_cuda=True,
+                            representation_lr_method="None", device=f"cuda:{torch.cuda.current_device()}", logger=utils.Logger())
+    return agent
+
+
+def cpu_reference(steps, warmup, batch=32, threads=None):
+    """The reference's CPU path for the same step (oracle port of agents.py:284-508, torch fp32, all host threads),
+    on a bounded sample: `steps` minibatches of `batch` samples of the same model."""
+    from oracle import oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig()
+    P = O.init_params(cfg, seed=7)
+    names = O.trainable_names(P)
+    for k in names:
+        P[k].requires_grad_(True)
+    opt = torch.optim.Adam([P[k] for k in names], lr=cfg.lr)
+    rng = np.random.default_rng(0)
+    n = batch
+    s = torch.tensor(np.float32(rng.integers(0, 256, (n, 4, 84, 84), dtype=np.uint8)) / 255.0)
+    obs = torch.tensor(rng.normal(0, 1, (n, 1, 84, 84)).clip(-5, 5), dtype=torch.float32)
+    te, ti, adv = (torch.tensor(rng.normal(0, 1, n), dtype=torch.float32) for _ in range(3))
+    y = torch.tensor(rng.integers(0, A, n))
+    old = torch.tensor(rng.normal(0, 1, (n, A)), dtype=torch.float32)
+
+    def step():
+        mask = (torch.rand(n) < cfg.update_proportion).float()
+        opt.zero_grad()
+        loss, _, _ = O.ppo_rnd_loss(P, cfg, s, te, ti, y, adv, obs, old, mask)
+        loss.backward()
+        opt.step()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": steps * n / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} optimiser steps x {n} samples of the cfg3 model (oracle port of agents.py:284-508, torch fp32, "
+                      f"dropout 0), {warmup} warm-up steps", "ms_per_step": dt / steps * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table here (json)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        k = max(1, min(args.steps, 8))
+        r = cpu_reference(k, max(1, min(args.warmup, 2)))
+        line = {"impl": "reference", "metric": "PPO+RND update samples/sec", "value": r["value"], "unit": "samples/s",
+                "n_gpus": args.gpus, "steps": k, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD}, "cpu_baseline": {k2: r[k2] for k2 in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from eavit_b200 import _lib, ops
+
+    E = E_PER_GPU
+    N = E * T
+    B = N // MINI_BATCH
+    agent = make_agent(E)
+    upd_args, u8 = synth_update_args(E, seed=100 + rank)
+    rt = agent.runtime()
+    rt.sync()
+    dev = rt.device
+    R = agent.upload_rollout(*upd_args)
+    perm = torch.from_numpy(np.random.default_rng(5).permutation(N)).to(dev)
+    masks = (torch.rand(args.steps + args.warmup + 8, B) < 0.25).float().to(dev)
+    n_mb = N // B
+
+    def step(i):
+        j = i % n_mb
+        agent.train_step(R, perm[B * j: B * (j + 1)], masks[i % masks.shape[0]])
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.stop_flag = True
+    value = args.steps * B * world / (ms * 1e-3)
+
+    # ---- per-kernel attribution (CUDA events around every launch, separate pass) -> roofline of the dominant kernel
+    pk, pk_kind = peaks()
+    ops.profile_start()
+    nprof = 3
+    for i in range(nprof):
+        step(i)
+    table = ops.profile_stop()
+    tot_ms = sum(v[1] for v in table.values())
+    groups = {}
+    for label, (n, tms, flops) in table.items():
+        g = label.split(" ")[0]
+        a = groups.setdefault(g, [0, 0.0, 0.0])
+        a[0] += n; a[1] += tms; a[2] += flops * n
+    dom_label, (dn, dms, dfl) = max(((l, v) for l, v in table.items() if v[2] > 0), key=lambda kv: kv[1][1])
+    gemm = groups.get("gemm_bf16_tcgen05", [0, 0.0, 0.0])
+    achieved = dfl * dn / (dms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom_label, "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": f"{pk_kind} burst bf16 (kernel timed alone per launch)",
+                "avg_launch_us": dms / dn * 1e3, "share_of_step": dms / tot_ms,
+                "all_gemm": {"launches_per_step": gemm[0] / nprof, "share_of_step": gemm[1] / tot_ms,
+                             "achieved_tflops": gemm[2] / (gemm[1] * 1e-3) / 1e12 if gemm[1] > 0 else None},
+                "step_model_tflops": FLOPS_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12,
+                "step_frac_of_sustained_peak": FLOPS_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
+    if args.profile_out and rank == 0:
+        rows = sorted(((l, n / nprof, tms / nprof, fl) for l, (n, tms, fl) in table.items()), key=lambda r: -r[2])
+        json.dump({"per_step": [{"kernel": l, "launches": n, "ms": tms, "tflops": (fl * n / (tms * 1e-3) / 1e12 if fl else None)}
+                                for l, n, tms, fl in rows], "sum_ms": tot_ms / nprof}, open(args.profile_out, "w"), indent=1)
+
+    # ---- end to end through the reference-facing call (host buffers in, stats out)
+    e2e = None
+    if not args.no_e2e:
+        agent.epoch = EPOCH
+        barrier()
+        t0 = time.perf_counter()
+        agent.train_model(*upd_args, 1)
+        stats = agent.stats_summary()                  # D2H read of the update's loss terms
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            dt = float(t.item())
+        n_steps = EPOCH * n_mb
+        h2d = sum(a.nbytes for a in upd_args)
+        e2e = {"value": N * EPOCH * world / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d / n_steps,
+               "d2h_bytes_per_step": 16 * 4, "call": "RNDAgent.train_model(states f32, target_ext f64, target_int f64, y i64, adv f64, "
+               "next_obs f64, old_policy f32) -- numpy host buffers (pinned), one full update = 128 optimiser steps",
+               "seconds": dt, "loss": stats.get("loss")}
+
+    if rank != 0:
+        return
+    cpu = None if args.no_cpu else cpu_reference(4, 1)
+    line = {"metric": "PPO+RND update samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B * world, "envs_per_gpu": E, "num_step": T, "parallelism": f"dp{world}",
+                       "l2": "inputs larger than L2 (>= 5 GB of activations per step)", "timing": "CUDA events, max over ranks"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary()}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

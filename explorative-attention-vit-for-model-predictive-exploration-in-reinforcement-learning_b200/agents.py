@@ -40,7 +40,9 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
-        self._agent().runtime().store.adam_step(g["lr"], 1.0, g["betas"][0], g["betas"][1], g["eps"])
+        rt = self._agent().runtime()
+        rt.store.adam_step(g["lr"], 1.0, g["betas"][0], g["betas"][1], g["eps"])
+        rt.rnd_pred.refresh_weights()
 
     def state_dict(self):
         st = self._agent().runtime().store
@@ -213,6 +215,7 @@ class RNDAgent(nn.Module):
         g = self.optimizer.param_groups[0]
         if apply:
             st.adam_step(g["lr"], 1.0 / self.world_size, g["betas"][0], g["betas"][1], g["eps"])
+            rt.rnd_pred.refresh_weights()
         if stats_out is not None:
             stats_out.copy_(w["stats"])
 

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_fwd_kernel(const __n
 }
 
 // Backward: recompute P from (q, k, lse).  Phase A (per query row): dQ.  Phase B (per key row): dK, dV.
-//   D_i = sum_d dO_i O_i ; dS = P * (dP - D) ; dQ = scale dS K ; dK = scale dS^T Q ; dV = P^T dO
+//   D_i = sum_j P_ij dP_ij (== sum_d dO_i O_i) ; dS = P * (dP - D) ; dQ = scale dS K ; dK = scale dS^T Q ; dV = P^T dO
 template <int DH>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                      const __nv_bfloat16* __restrict__ o,
@@ -127,24 +127,17 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_kernel(const __n
     sV[j * LD + 2 * d2] = v.x; sV[j * LD + 2 * d2 + 1] = v.y;
     sdO[j * LD + 2 * d2] = g.x; sdO[j * LD + 2 * d2 + 1] = g.y;
   }
-  for (int i = w; i < S; i += ATT_WARPS) {   // D_i and lse, one warp per row
-    float a = 0.f;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const size_t idx = (size_t)(t0 + i) * ldo + h * DH + lane + 32 * r;
-      a += __bfloat162float(o[idx]) * __bfloat162float(dout[idx]);
-    }
-    a = warp_sum(a);
-    if (lane == 0) { sD[i] = a; sL[i] = lse[(size_t)(t0 + i) * H + h]; }
-  }
+  for (int i = threadIdx.x; i < S; i += blockDim.x) sL[i] = lse[(size_t)(t0 + i) * H + h];
   __syncthreads();
   float* myA = sA + w * SM;
   float* myB = sB + w * SM;
-  // ---- phase A: dQ_i = scale * sum_j dS_ij K_j
+  // ---- phase A: dQ_i = scale * sum_j dS_ij K_j.  D_i = sum_j P_ij dP_ij is taken from the SAME recomputed P
+  // that multiplies (dP - D), so the softmax Jacobian is applied consistently (no bf16-rounded O involved).
   for (int i = w; i < S; i += ATT_WARPS) {
     const float* qi = sQ + i * LD;
     const float* gi = sdO + i * LD;
-    const float li = sL[i], Di = sD[i];
+    const float li = sL[i];
+    float dsum = 0.f;
 #pragma unroll
     for (int jj = 0; jj < ATT_MAXS / 32; ++jj) {
       const int j = lane + 32 * jj;
@@ -155,15 +148,19 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_kernel(const __n
 #pragma unroll
         for (int d = 0; d < DH; ++d) { s += qi[d] * kr[d]; dp += gi[d] * vr[d]; }
         const float p = __expf(s - li);
-        myA[j] = p * (dp - Di);
+        myA[j] = p;
+        myB[j] = dp;
+        dsum += p * dp;
       }
     }
+    const float Di = warp_sum(dsum);
+    if (lane == 0) sD[i] = Di;
     __syncwarp();
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
     for (int j = 0; j < S; ++j) {
-      const float ds = myA[j];
+      const float ds = myA[j] * (myB[j] - Di);
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] += ds * sK[j * LD + lane + 32 * r];
     }
@@ -172,6 +169,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_kernel(const __n
     for (int r = 0; r < R; ++r) dq[lane + 32 * r] = __float2bfloat16(acc[r] * scale);
     __syncwarp();
   }
+  __syncthreads();     // every D_i is needed by phase B
   // ---- phase B: dK_j = sum_i dS_ij (scale Q_i) ; dV_j = sum_i P_ij dO_i
   for (int j = w; j < S; j += ATT_WARPS) {
     const float* kj = sK + j * LD;

@@ -422,7 +422,13 @@ class Heads:
 
 
 class RNDNet:
-    """model.py:366-416 conv tower + FC stack; ``net`` = 'predictor' (trainable) or 'target' (frozen)."""
+    """model.py:366-416 conv tower + FC stack; ``net`` = 'predictor' (trainable) or 'target' (frozen).
+
+    Forward operands are bf16x3 splits ([hi|hi|lo] x [hi|lo|hi], one GEMM with K' = 3K): the (Leaky)ReLU masks of
+    this plain ReLU network flip wherever a pre-activation's rounding error exceeds its magnitude, and with single
+    bf16 operands (2^-9) those flips alone put ~3 % error on the predictor gradients.  The towers are < 1 % of the
+    update's FLOPs, so near-fp32 pre-activations cost nothing measurable.  Backward GEMMs use plain bf16 (hi parts).
+    """
 
     CONVS = ((8, 4, 1, 32), (4, 2, 32, 64), (3, 1, 64, 64))   # (kernel, stride, Cin, Cout)
 
@@ -438,35 +444,52 @@ class RNDNet:
             self.sizes.append((h, oh))
             h = oh
         self.flat_dim = h * h * 64
+        self.w3: Dict[str, torch.Tensor] = {}
+        for idx in (0, 2, 4) + self.fcs:
+            w = store.w(self.pre + f"{idx}.weight")
+            n, k = w.shape[0], w[0].numel()
+            self.w3[f"{idx}"] = torch.empty(n, 3 * k, dtype=torch.bfloat16, device=store.device)
+        self.refresh_weights()
+
+    def refresh_weights(self):
+        """fp32 master weights -> [hi | lo | hi] bf16 GEMM operands (after load / every optimiser step)."""
+        for idx, w3 in self.w3.items():
+            w = self.s.w(self.pre + f"{idx}.weight")
+            n, k = w.shape[0], w[0].numel()
+            call("eavit_split3_rows", w, k, n, k, w3, 1)
 
     def forward(self, obs: torch.Tensor, B: int, sample_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
         """obs fp32 [N,1,H,W] (normalised, clipped); returns features fp32 [B, out]."""
         s, p = self.s, self.pre
         bf = self.buf.setdefault(B, _Buffers(obs.device))
-        x, x_dt, sidx = obs, ops._DT[obs.dtype], sample_idx
+        assert obs.dtype == torch.float32
+        x, sidx = obs, sample_idx
         for ci, ((k, st, cin, cout), (h, oh)) in enumerate(zip(self.CONVS, self.sizes)):
             K = cin * k * k
-            col = bf.get(f"col{ci}", (B * oh * oh, K), torch.bfloat16)
-            call("eavit_im2col", x, x_dt, sidx, B, h, h, cin, k, k, st, col)
-            act = bf.get(f"act{ci}", (B * oh * oh, cout), torch.bfloat16)
-            name = p + f"{2 * ci}."
-            linear_fwd(col, s.b16(name + "weight").view(cout, K), bias=s.w(name + "bias"), act=ops.ACT_LRELU, out_bf16=act)
-            x, x_dt, sidx = act, BF16, None
+            col = bf.get(f"col{ci}", (B * oh * oh, 3 * K), torch.bfloat16)
+            call("eavit_im2col", x, F32, sidx, B, h, h, cin, k, k, st, col, 1)
+            a32 = bf.get(f"act32_{ci}", (B * oh * oh, cout), torch.float32)
+            a16 = bf.get(f"act{ci}", (B * oh * oh, cout), torch.bfloat16)
+            ops.gemm(col, self.w3[f"{2 * ci}"], bias=s.w(p + f"{2 * ci}.bias"), act=ops.ACT_LRELU, out_f32=a32, out_bf16=a16)
+            x, sidx = a32, None
         hw = self.sizes[-1][1] ** 2
-        flat = bf.get("flat", (B, self.flat_dim), torch.bfloat16)
-        call("eavit_nhwc_to_flat", x, B, hw, 64, flat)
-        h16 = flat
+        flat32 = bf.get("flat32", (B, self.flat_dim), torch.float32)
+        call("eavit_nhwc_to_flat_f32", x, B, hw, 64, flat32)
+        h3 = bf.get("flat", (B, 3 * self.flat_dim), torch.bfloat16)
+        call("eavit_split3_rows", flat32, self.flat_dim, B, self.flat_dim, h3, 0)
         out = None
         for j, k in enumerate(self.fcs):
             last = j == len(self.fcs) - 1
-            name = p + f"{k}."
+            bias = s.w(p + f"{k}.bias")
             if last:
                 out = bf.get("out", (B, self.out), torch.float32)
-                linear_fwd(h16, s.b16(name + "weight"), bias=s.w(name + "bias"), out_f32=out)
+                ops.gemm(h3, self.w3[f"{k}"], bias=bias, out_f32=out)
             else:
-                nxt = bf.get(f"fc{j}", (B, self.out), torch.bfloat16)
-                linear_fwd(h16, s.b16(name + "weight"), bias=s.w(name + "bias"), act=ops.ACT_RELU, out_bf16=nxt)
-                h16 = nxt
+                f32 = bf.get(f"fc32_{j}", (B, self.out), torch.float32)
+                f16 = bf.get(f"fc16_{j}", (B, self.out), torch.bfloat16)
+                ops.gemm(h3, self.w3[f"{k}"], bias=bias, act=ops.ACT_RELU, out_f32=f32, out_bf16=f16)
+                h3 = bf.get(f"fc{j}", (B, 3 * self.out), torch.bfloat16)
+                call("eavit_split3_rows", f32, self.out, B, self.out, h3, 0)
         return out
 
     def backward(self, dout16: torch.Tensor):
@@ -478,7 +501,7 @@ class RNDNet:
         nfc = len(self.fcs)
         for j in reversed(range(nfc)):
             name = p + f"{self.fcs[j]}."
-            x16 = bf.t["flat"] if j == 0 else bf.t[f"fc{j - 1}"]
+            x16 = bf.t["flat"][:, : self.flat_dim] if j == 0 else bf.t[f"fc{j - 1}"][:, : self.out]   # hi parts
             if j == 0:
                 dflat = bf.get("dflat", (B, self.flat_dim), torch.bfloat16)
                 linear_bwd(d, x16, s.b16(name + "weight"), dW=s.g(name + "weight"), db=s.g(name + "bias"), dx_bf16=dflat)
@@ -486,7 +509,7 @@ class RNDNet:
             else:
                 dprev = bf.get(f"dfc{j - 1}", (B, self.out), torch.bfloat16)
                 linear_bwd(d, x16, s.b16(name + "weight"), dW=s.g(name + "weight"), db=s.g(name + "bias"), dx_bf16=dprev,
-                           act=ops.ACT_RELU_BWD, aux=x16)
+                           act=ops.ACT_RELU_BWD, aux=bf.t[f"fc16_{j - 1}"])
                 d = dprev
         hw = self.sizes[-1][1] ** 2
         dact = bf.get("dact2", (B * hw, 64), torch.bfloat16)
@@ -496,11 +519,12 @@ class RNDNet:
             h, oh = self.sizes[ci]
             K = cin * k * k
             name = p + f"{2 * ci}."
+            col_hi = bf.t[f"col{ci}"][:, :K]
             if ci == 0:
-                linear_bwd(dact, bf.t["col0"], None, dW=s.g(name + "weight").view(cout, K), db=s.g(name + "bias"))
+                linear_bwd(dact, col_hi, None, dW=s.g(name + "weight").view(cout, K), db=s.g(name + "bias"))
                 break
             dcol = bf.get(f"dcol{ci}", (B * oh * oh, K), torch.bfloat16)
-            linear_bwd(dact, bf.t[f"col{ci}"], s.b16(name + "weight").view(cout, K), dW=s.g(name + "weight").view(cout, K),
+            linear_bwd(dact, col_hi, s.b16(name + "weight").view(cout, K), dW=s.g(name + "weight").view(cout, K),
                        db=s.g(name + "bias"), dx_bf16=dcol)
             dprev = bf.get(f"dact{ci - 1}", (B * h * h, cin), torch.bfloat16)
             call("eavit_col2im_lrelu", dcol, bf.t[f"act{ci - 1}"], B, h, h, cin, k, k, st, dprev)

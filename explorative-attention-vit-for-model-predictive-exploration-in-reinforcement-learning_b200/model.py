@@ -120,6 +120,9 @@ class Runtime:
         self.store.sync_shadow()
         if self.frozen is not None:
             self.frozen.sync_shadow()
+        if self.rnd_pred is not None:
+            self.rnd_pred.refresh_weights()
+            self.rnd_tgt.refresh_weights()
         # gradients may have been detached by optimizer.zero_grad(set_to_none=True)
         for n, p in self.params.items():
             if n in self.store.shapes and (p.grad is None or p.grad.data_ptr() != self.store.g(n).data_ptr()):

@@ -17,6 +17,46 @@ ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_LRELU, ACT_LRELU_BWD, ACT_RELU, ACT_RELU_B
 _DT = {torch.uint8: U8, torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 
 
+# ------------------------------------------------------------------------------------------- launch profiler
+# bench.py uses this to attribute device time to kernels with CUDA events on the launching stream.
+_PROF = None
+
+
+def profile_start():
+    global _PROF
+    _PROF = []
+
+
+def profile_stop():
+    """-> {label: (launches, total_ms, flops_per_launch)} ; synchronises."""
+    global _PROF
+    rec, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    out = {}
+    for label, e0, e1, flops in rec or []:
+        n, ms, f = out.get(label, (0, 0.0, flops))
+        out[label] = (n + 1, ms + e0.elapsed_time(e1), flops)
+    return out
+
+
+class _Timed:
+    __slots__ = ("label", "flops", "e0")
+
+    def __init__(self, label, flops=0.0):
+        self.label, self.flops = label, flops
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _PROF is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROF.append((self.label, self.e0, e1, self.flops))
+
+
 def _p(t: Optional[torch.Tensor]):
     if t is None:
         return None
@@ -159,6 +199,11 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                  out_bf16=None if out_bf16 is None else out_bf16.data_ptr(),
                  out_pre_bf16=None if out_pre is None else out_pre.data_ptr(),
                  ldc=ldc, act=act, atomic_f32=int(atomic), split_k=split_k)
+    if _PROF is not None:
+        with _Timed(f"gemm_bf16_tcgen05 M={M} N={N} K={K} {'mn' if a_mn else 'k'}{'mn' if b_mn else 'k'} act={act}"
+                    f"{' splitk' if split_k > 1 else ''}", 2.0 * M * N * K):
+            check(_lib.lib().eavit_gemm_bf16(ctypes.byref(g), _st()), "gemm_bf16")
+        return
     check(_lib.lib().eavit_gemm_bf16(ctypes.byref(g), _st()), "gemm_bf16")
 
 
@@ -188,7 +233,9 @@ _SPECS = {
     "eavit_ppo_loss": "ppppppppiifffpppp",
     "eavit_rnd_loss": "pppiifppp",
     "eavit_gather_batch": "piipppppppppp",
-    "eavit_im2col": "pipiiiiiiip",
+    "eavit_im2col": "pipiiiiiiipi",
+    "eavit_split3_rows": "pliipi",
+    "eavit_nhwc_to_flat_f32": "piiip",
     "eavit_col2im_lrelu": "ppiiiiiiip",
     "eavit_nhwc_to_flat": "piiip",
     "eavit_flat_to_nhwc_lrelu": "ppiiip",
@@ -224,6 +271,10 @@ def call(name: str, *args):
                 conv.append(a.data_ptr())
         else:
             conv.append(a)
-    rc = fn(*conv, torch.cuda.current_stream().cuda_stream)
+    if _PROF is not None:
+        with _Timed(name[len("eavit_"):]):
+            rc = fn(*conv, torch.cuda.current_stream().cuda_stream)
+    else:
+        rc = fn(*conv, torch.cuda.current_stream().cuda_stream)
     if rc != 0:
         check(rc, name[len("eavit_"):])

@@ -206,7 +206,11 @@ int eavit_gather_batch(const long long* idx, int B, int A, const float* tgt_ext,
 
 /* ------------------------------------------------------------------ RND convolutions (model.py:368-416) */
 int eavit_im2col(const void* in, int in_dtype, const long long* sample_idx /* may be NULL */, int B, int H, int W, int C, int KH, int KW, int stride, void* col_bf16,
-                 void* stream);
+                 int split3 /* 1: write [hi|hi|lo] rows of 3*K (bf16x3 operand) */, void* stream);
+/* bf16x3 split of fp32 rows: mode 0 [hi|hi|lo] (activations), mode 1 [hi|lo|hi] (weights); A3.B3^T = hi*hi+hi*lo+lo*hi.
+ * Used for the RND towers, whose (Leaky)ReLU masks need near-fp32 pre-activations for gradient parity. */
+int eavit_split3_rows(const float* in, long long ldi, int R, int K, void* out_bf16, int mode, void* stream);
+int eavit_nhwc_to_flat_f32(const float* act, int B, int HW, int C, float* flat, void* stream);
 int eavit_col2im_lrelu(const void* dcol_bf16, const void* act_bf16, int B, int H, int W, int C, int KH, int KW, int stride,
                        void* din_bf16, void* stream);
 int eavit_nhwc_to_flat(const void* act_bf16, int B, int HW, int C, void* flat_bf16, void* stream);

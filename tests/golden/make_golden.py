@@ -108,7 +108,7 @@ def main():
     G = {}
     # ---- forward: CnnActorCriticNetwork / get_action / compute_intrinsic_reward -----------------
     rng = np.random.default_rng(11)
-    state_u8 = rng.integers(0, 256, (3, 4, 84, 84), dtype=np.uint8)
+    state_u8 = rng.integers(0, 256, (16, 4, 84, 84), dtype=np.uint8)
     state = np.float32(state_u8) / 255.0
     with torch.no_grad():
         pol, ve, vi = agent.model(torch.tensor(state))

@@ -32,7 +32,7 @@ def test_forward_matches_reference(golden_dir, which):
     G, cfg = _load(golden_dir, which), CFGS[which]
     P = O.init_params(cfg, seed=7)
     rng = np.random.default_rng(11)
-    state = np.float32(rng.integers(0, 256, (3, 4, 84, 84), dtype=np.uint8)) / 255.0
+    state = np.float32(rng.integers(0, 256, (16, 4, 84, 84), dtype=np.uint8)) / 255.0
     with torch.no_grad():
         pol, ve, vi = O.actor_critic_forward(P, torch.tensor(state), cfg)
     np.testing.assert_allclose(pol.numpy(), G["fwd_policy"], rtol=1e-4, atol=1e-6)
