@@ -62,11 +62,36 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(t);
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Exact-erf GELU (nn.GELU default) through Abramowitz-Stegun 7.1.26: |erf error| <= 1.5e-7 (fp32 level, far below the
+// bf16 rounding of the stored activation), ~14 instructions with one rcp and one ex2 instead of ~25 for erff().
+// tail(x) = 0.5 * erfc(|x| / sqrt2) is evaluated directly, so Phi(x) has no cancellation for very negative x.
+// e = exp(-x^2 / 2) is shared with the derivative:  gelu'(x) = Phi(x) + x * e / sqrt(2 pi).
+__device__ __forceinline__ float gelu_tail(float x, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  e = ex2_approx(-1.4426950408889634f * z * z);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  return 0.5f * p * t * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float e;
+  const float tail = gelu_tail(x, e);
+  return x * (x >= 0.f ? 1.0f - tail : tail);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;
+  const float tail = gelu_tail(x, e);
+  const float cdf = x >= 0.f ? 1.0f - tail : tail;
+  return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

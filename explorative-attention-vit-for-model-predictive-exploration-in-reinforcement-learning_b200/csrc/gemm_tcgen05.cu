@@ -23,7 +23,9 @@ namespace eavit {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;          // 4 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_TILE_FLOATS = 32 * 32;   // 32x32 transpose tile per epilogue warp (16-byte chunks XOR-swizzled)
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 struct GemmKernelParams {
@@ -45,9 +47,10 @@ template <int BN>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
   static constexpr int TMEM_COLS = 2 * BN;    // power of two >= 32 for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILE_FLOATS * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float a) {
@@ -70,7 +73,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;                      // [STAGES]   TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;            // [STAGES]   MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;         // [2]        MMA -> epilogue
@@ -86,7 +90,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], EPI_WARPS); }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -163,99 +167,89 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =====================================
-    const int q = warp & 3;                           // TMEM lane quadrant owned by this warp
+    // Two warps per TMEM lane quadrant (they alternate 32-column chunks).  Each chunk is transposed through a padded
+    // shared-memory tile so that global loads / stores are row-contiguous (a warp touches 128 B of ONE row per
+    // instruction instead of 32 rows x 16 B).
+    const int e = warp - 4;
+    const int q = e & 3;                              // TMEM lane quadrant owned by this warp
+    const int par = e >> 2;                           // chunk parity handled by this warp
+    float* tile = epi_smem + e * EPI_TILE_FLOATS;
+    const bool need_aux = (p.act == EAVIT_ACT_GELU_BWD || p.act == EAVIT_ACT_LRELU_BWD || p.act == EAVIT_ACT_RELU_BWD);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
+    for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
+      const int n_blk = tile_i % p.n_tiles, m_blk = (tile_i / p.n_tiles) % p.m_tiles;
       tc::mbar_wait(&acc_full[acc], acc_phase);
       tc::fence_after_sync();
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const size_t row_off = (size_t)row * (size_t)p.ldc;
+      const int row0 = m_blk * BM + q * 32;
+      const int nrows = min(32, p.M - row0);          // may be <= 0 for the M tail
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = par; c < BN / 32; c += 2) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;                        // warp-uniform
         uint32_t r[32];
         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
         tc::tmem_ld_wait();
-        if (row_ok) {
-          const int ncols = min(32, p.N - col0);       // multiple of 8
-          float v[32];
+        // registers (one row per lane) -> swizzled smem tile -> (4 rows x 8 lanes x 16 B) per instruction
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-          }
-          if (p.out_pre != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                uint4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(p.out_pre + row_off + col0 + j) = o;
-              }
-            }
-          }
-          if (p.act != EAVIT_ACT_NONE) {
-            const bool need_aux = (p.act == EAVIT_ACT_GELU_BWD || p.act == EAVIT_ACT_LRELU_BWD || p.act == EAVIT_ACT_RELU_BWD);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (need_aux) {
-                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col0 + j));
-                  float2 t;
-                  t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
-                  t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
-                  t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
-                  t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[j + i] = apply_act(v[j + i], p.act, a[i]);
-              }
-            }
-          }
+        for (int c4 = 0; c4 < 8; ++c4)
+          *reinterpret_cast<uint4*>(tile + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = make_uint4(r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
+        __syncwarp();
+        const int cchunk = lane & 7, rsub = lane >> 3;
+        const int col = col0 + cchunk * 4;
+        if (col < p.N) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          // issue every global read of this chunk first (8 independent 16-byte loads per lane): the epilogue is
+          // latency-bound on HBM unless ~40 KB per SM are in flight
+          float4 res[8];
+          uint2 ax[8];
           if (p.residual != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.residual + row_off + col0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rsub;
+              if (rr < nrows) res[it] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)(row0 + rr) * (size_t)p.ldc + col));
             }
           }
-          if (p.out_f32 != nullptr) {
-            if (p.atomic_f32) {
+          if (need_aux) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) atomicAdd(p.out_f32 + row_off + col0 + j, v[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (j < ncols)
-                  *reinterpret_cast<float4*>(p.out_f32 + row_off + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rsub;
+              if (rr < nrows) ax[it] = __ldg(reinterpret_cast<const uint2*>(p.aux + (size_t)(row0 + rr) * (size_t)p.ldc + col));
             }
           }
-          if (p.out_bf16 != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                uint4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(p.out_bf16 + row_off + col0 + j) = o;
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            if (rr < nrows) {
+              const float4 t = *reinterpret_cast<const float4*>(tile + rr * 32 + ((cchunk ^ (rr & 7)) << 2));
+              float v[4] = {t.x + b4.x, t.y + b4.y, t.z + b4.z, t.w + b4.w};
+              const size_t off = (size_t)(row0 + rr) * (size_t)p.ldc + col;
+              if (p.out_pre != nullptr)
+                *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+              if (p.act != EAVIT_ACT_NONE) {
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
+                if (need_aux) {
+                  const float2 lo = unpack_bf16x2(ax[it].x), hi = unpack_bf16x2(ax[it].y);
+                  a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act, a[i]);
               }
+              if (p.residual != nullptr) { v[0] += res[it].x; v[1] += res[it].y; v[2] += res[it].z; v[3] += res[it].w; }
+              if (p.out_f32 != nullptr) {
+                if (p.atomic_f32) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) atomicAdd(p.out_f32 + off + i, v[i]);
+                } else {
+                  *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+              }
+              if (p.out_bf16 != nullptr)
+                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
             }
           }
         }
+        __syncwarp();
       }
       tc::fence_before_sync();
       __syncwarp();

@@ -11,7 +11,7 @@ namespace eavit {
 constexpr int LN_MAXV = 8;   // D <= 32 lanes * 4 * 8 = 1024
 
 // y = (x - mean) * rstd * gamma + beta ; two-pass statistics in fp32 like ATen's CPU/CUDA kernels.
-template <typename OutT>
+template <typename OutT, int VPL>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, OutT* __restrict__ y,
@@ -21,10 +21,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   if (row >= T) return;
   const float* xr = x + (size_t)row * ldx;
   const int nv = D / 4;
-  float4 v[LN_MAXV];
+  float4 v[VPL];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
     if (c < nv) {
       v[i] = __ldg(reinterpret_cast<const float4*>(xr) + c);
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   const float mean = warp_sum(s) / (float)D;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
     if (c < nv) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   if (lane == 0 && mean_out != nullptr) { mean_out[row] = mean; rstd_out[row] = rstd; }
   OutT* yr = y + (size_t)row * ldy;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
     if (c < nv) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
@@ -63,9 +63,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
-// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy      (block partials -> one atomicAdd per column per block)
-constexpr int LNB_ROWS_PER_BLOCK = 64;
-template <typename DyT>
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy      (block partials -> one atomicAdd per column per CTA)
+template <typename DyT, int VPL>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restrict__ dy, long long lddy,
                                                             const float* __restrict__ x, long long ldx,
                                                             const float* __restrict__ mean,
@@ -79,17 +78,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restric
   extern __shared__ float s_part[];   // [8 warps][2][D]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / 4;
-  float4 ag[LN_MAXV], ab[LN_MAXV];
+  float4 ag[VPL], ab[VPL];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = ag[i]; }
-  const int r_begin = blockIdx.x * LNB_ROWS_PER_BLOCK;
-  const int r_end = min(T, r_begin + LNB_ROWS_PER_BLOCK);
-  for (int row = r_begin + w; row < r_end; row += 8) {
+  for (int i = 0; i < VPL; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = ag[i]; }
+  // persistent grid-stride over rows: the dgamma/dbeta atomics are paid once per CTA, not once per 64 rows
+  for (int row = blockIdx.x * 8 + w; row < T; row += gridDim.x * 8) {
     const float mu = mean[row], rs = rstd[row];
-    float4 g[LN_MAXV], xh[LN_MAXV];
+    float4 g[VPL], xh[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < VPL; ++i) {
       const int c = lane + 32 * i;
       if (c < nv) {
         float4 d;
@@ -113,7 +111,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restric
     s1 = warp_sum(s1) / (float)D;
     s2 = warp_sum(s2) / (float)D;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < VPL; ++i) {
       const int c = lane + 32 * i;
       if (c < nv) {
         float4 o = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
@@ -132,7 +130,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restric
   float* pg = s_part + (size_t)w * 2 * D;
   float* pb = pg + D;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
     if (c < nv) {
       *(reinterpret_cast<float4*>(pg) + c) = ag[i];
@@ -224,11 +222,14 @@ int eavit_layernorm_fwd(const float* x, long long ldx, const float* gamma, const
   EAVIT_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0);
   EAVIT_CHECK_ARG((mean == nullptr) == (rstd == nullptr));
   cudaStream_t st = (cudaStream_t)stream;
-  if (y_dtype == EAVIT_BF16)
-    layernorm_fwd_kernel<__nv_bfloat16><<<cdiv(T, 8), 256, 0, st>>>(x, ldx, gamma, beta, (__nv_bfloat16*)y, ldy, mean, rstd, T, D, eps);
-  else if (y_dtype == EAVIT_F32)
-    layernorm_fwd_kernel<float><<<cdiv(T, 8), 256, 0, st>>>(x, ldx, gamma, beta, (float*)y, ldy, mean, rstd, T, D, eps);
+  const int vpl = cdiv(D / 4, 32);            // float4 vectors per lane: registers (and occupancy) sized for the actual D
+#define EAVIT_LN_FWD(OT, V) layernorm_fwd_kernel<OT, V><<<cdiv(T, 8), 256, 0, st>>>(x, ldx, gamma, beta, (OT*)y, ldy, mean, rstd, T, D, eps)
+#define EAVIT_LN_FWD_V(OT) do { if (vpl <= 1) EAVIT_LN_FWD(OT, 1); else if (vpl <= 2) EAVIT_LN_FWD(OT, 2); else if (vpl <= 4) EAVIT_LN_FWD(OT, 4); else EAVIT_LN_FWD(OT, 8); } while (0)
+  if (y_dtype == EAVIT_BF16) EAVIT_LN_FWD_V(__nv_bfloat16);
+  else if (y_dtype == EAVIT_F32) EAVIT_LN_FWD_V(float);
   else { set_error("layernorm_fwd: bad y_dtype %d", y_dtype); return EAVIT_EINVAL; }
+#undef EAVIT_LN_FWD_V
+#undef EAVIT_LN_FWD
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -242,18 +243,22 @@ int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const floa
   EAVIT_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && lddres % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)8 * 2 * D * sizeof(float);
-  const int grid = cdiv(T, LNB_ROWS_PER_BLOCK);
-  if (dy_dtype == EAVIT_F32) {
-    static bool done = false;
-    if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4)); done = true; }
-    layernorm_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx,
-                                                         (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, T, D);
-  } else if (dy_dtype == EAVIT_BF16) {
-    static bool done = false;
-    if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4)); done = true; }
-    layernorm_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres,
-                                                                 dx, lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, T, D);
-  } else { set_error("layernorm_bwd: bad dy_dtype %d", dy_dtype); return EAVIT_EINVAL; }
+  int grid = cdiv(T, 8);
+  if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
+  const int vpl = cdiv(D / 4, 32);
+  static bool attr_done = false;
+  if (!attr_done) {
+    EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    attr_done = true;
+  }
+#define EAVIT_LN_BWD(DT, V) layernorm_bwd_kernel<DT, V><<<grid, 256, smem, st>>>((const DT*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, T, D)
+#define EAVIT_LN_BWD_V(DT) do { if (vpl <= 1) EAVIT_LN_BWD(DT, 1); else if (vpl <= 2) EAVIT_LN_BWD(DT, 2); else if (vpl <= 4) EAVIT_LN_BWD(DT, 4); else EAVIT_LN_BWD(DT, 8); } while (0)
+  if (dy_dtype == EAVIT_F32) EAVIT_LN_BWD_V(float);
+  else if (dy_dtype == EAVIT_BF16) EAVIT_LN_BWD_V(__nv_bfloat16);
+  else { set_error("layernorm_bwd: bad dy_dtype %d", dy_dtype); return EAVIT_EINVAL; }
+#undef EAVIT_LN_BWD_V
+#undef EAVIT_LN_BWD
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }

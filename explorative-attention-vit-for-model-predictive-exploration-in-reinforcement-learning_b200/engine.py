@@ -261,8 +261,7 @@ class ViTEncoder:
             linear_fwd(xn1, self._qkv(L, "w16"), bias=self._qkv(L, "b"), out_bf16=qkv)
             o = bf.get(f"o_{li}", (T, I), torch.bfloat16)
             lse = bf.get(f"lse_{li}", (T, c.heads), torch.float32)
-            call("eavit_attention_fwd", qkv, bf.seq_start, bf.nseq, bf.max_len, c.heads, c.dim_head,
-                 float(c.dim_head) ** -0.5, o, lse)
+            ops.attention_fwd(qkv, bf.seq_start, bf.nseq, bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, o, lse)
             xmid = bf.get(f"xmid_{li}", (T, D), torch.float32)
             linear_fwd(o, s.b16(L["o_w"]), bias=s.w(L["o_b"]), residual=x, out_f32=xmid)
             xn2 = bf.get(f"xn2_{li}", (T, D), torch.bfloat16)
@@ -324,8 +323,8 @@ class ViTEncoder:
             dx, dx_other = dx_other, dx
             # out-proj: xmid = x + o Wo^T + bo
             linear_bwd(dx16, bf.t[f"o_{li}"], s.b16(L["o_w"]), dW=s.g(L["o_w"]), db=s.g(L["o_b"]), dx_bf16=do)
-            call("eavit_attention_bwd", bf.t[f"qkv_{li}"], bf.t[f"o_{li}"], do, bf.t[f"lse_{li}"], bf.seq_start, bf.nseq,
-                 bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, dqkv)
+            ops.attention_bwd(bf.t[f"qkv_{li}"], bf.t[f"o_{li}"], do, bf.t[f"lse_{li}"], bf.seq_start, bf.nseq,
+                              bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, dqkv)
             linear_bwd(dqkv, bf.t[f"xn1_{li}"], self._qkv(L, "w16"), dW=self._qkv(L, "gw"), db=self._qkv(L, "gb"), dx_f32=dxn)
             call("eavit_layernorm_bwd", dxn, F32, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
                  dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), T, D)

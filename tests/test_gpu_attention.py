@@ -1,0 +1,103 @@
+"""GPU parity: attention kernels (CUDA-core v1 and tcgen05) vs torch fp32 softmax attention on the same bf16 inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from eavit_b200 import ops as _ops
+    return _ops
+
+
+def ref_attention(qkv, starts, H, Dh, scale):
+    T = qkv.shape[0]
+    out = torch.zeros(T, H * Dh, device=qkv.device)
+    lse = torch.zeros(T, H, device=qkv.device)
+    q, k, v = qkv.float().split(H * Dh, dim=1)
+    for s0, s1 in zip(starts[:-1], starts[1:]):
+        for h in range(H):
+            sl = slice(h * Dh, (h + 1) * Dh)
+            sc = (q[s0:s1, sl] @ k[s0:s1, sl].t()) * scale
+            out[s0:s1, sl] = sc.softmax(-1) @ v[s0:s1, sl]
+            lse[s0:s1, h] = torch.logsumexp(sc, -1)
+    return out, lse
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+CASES = [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([197] * 5, 8, 32), ([1, 17, 128, 129, 224], 4, 32),
+         ([64, 200], 3, 64)]
+
+
+@pytest.mark.parametrize("lens,H,Dh", CASES)
+@pytest.mark.parametrize("impl", ["v1", "tc"])
+def test_attention_forward(ops, lens, H, Dh, impl):
+    torch.manual_seed(sum(lens) + H)
+    starts = [0]
+    for n in lens:
+        starts.append(starts[-1] + n)
+    T = starts[-1]
+    qkv = (torch.randn(T, 3 * H * Dh, device="cuda") * 1.5).bfloat16()
+    ss = torch.tensor(starts, dtype=torch.int32, device="cuda")
+    out = torch.full((T, H * Dh), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((T, H), float("nan"), device="cuda")
+    scale = Dh ** -0.5
+    name = "eavit_attention_fwd" if impl == "v1" else "eavit_attention_fwd_tc"
+    ops.call(name, qkv, ss, len(lens), max(lens), H, Dh, scale, out, lse)
+    torch.cuda.synchronize()
+    ro, rl = ref_attention(qkv, starts, H, Dh, scale)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert rel(out, ro) < 6e-3, rel(out, ro)
+    assert (lse - rl).abs().max().item() < 2e-2
+
+
+BWD_CASES = [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([1, 17, 128, 129, 224], 4, 32), ([64, 100], 3, 64)]
+
+
+@pytest.mark.parametrize("lens,H,Dh", BWD_CASES)
+@pytest.mark.parametrize("impl", ["v1", "tc"])
+def test_attention_backward(ops, lens, H, Dh, impl):
+    torch.manual_seed(sum(lens) + H + 1)
+    starts = [0]
+    for n in lens:
+        starts.append(starts[-1] + n)
+    T = starts[-1]
+    qkv = (torch.randn(T, 3 * H * Dh, device="cuda") * 1.2).bfloat16()
+    dout = torch.randn(T, H * Dh, device="cuda").bfloat16()
+    ss = torch.tensor(starts, dtype=torch.int32, device="cuda")
+    scale = Dh ** -0.5
+    x = qkv.float().requires_grad_(True)
+    ro, _ = ref_attention_autograd(x, starts, H, Dh, scale)
+    (ro * dout.float()).sum().backward()
+    out = torch.empty(T, H * Dh, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(T, H, device="cuda")
+    ops.call("eavit_attention_fwd_tc" if impl == "tc" else "eavit_attention_fwd", qkv, ss, len(lens), max(lens), H, Dh, scale, out, lse)
+    dqkv = torch.full((T, 3 * H * Dh), float("nan"), device="cuda", dtype=torch.bfloat16)
+    if impl == "tc":
+        ops.call("eavit_attention_bwd_tc", qkv, dout, lse, ss, len(lens), max(lens), H, Dh, scale, dqkv)
+    else:
+        ops.call("eavit_attention_bwd", qkv, out, dout, lse, ss, len(lens), max(lens), H, Dh, scale, dqkv)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv.float()).all()
+    g = x.grad
+    n = H * Dh
+    for name, sl in (("dq", slice(0, n)), ("dk", slice(n, 2 * n)), ("dv", slice(2 * n, 3 * n))):
+        e = rel(dqkv[:, sl], g[:, sl])
+        assert e < 1.2e-2, (name, e)
+
+
+def ref_attention_autograd(x, starts, H, Dh, scale):
+    q, k, v = x.split(H * Dh, dim=1)
+    outs = []
+    for s0, s1 in zip(starts[:-1], starts[1:]):
+        hs = []
+        for h in range(H):
+            sl = slice(h * Dh, (h + 1) * Dh)
+            sc = (q[s0:s1, sl] @ k[s0:s1, sl].t()) * scale
+            hs.append(sc.softmax(-1) @ v[s0:s1, sl])
+        outs.append(torch.cat(hs, dim=1))
+    return torch.cat(outs, dim=0), None
