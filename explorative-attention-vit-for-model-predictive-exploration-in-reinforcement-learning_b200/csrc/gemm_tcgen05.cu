@@ -65,7 +65,11 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
   }
 }
 
-template <int BN>
+// Epilogue specialisations (compile-time): the epilogue is instruction-issue bound (ncu: 45 % issue-active from only 8
+// warps), so the common fused forms drop every per-element runtime branch of the generic path.
+enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5 };
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmKernelParams p) {
@@ -174,7 +178,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int q = e & 3;                              // TMEM lane quadrant owned by this warp
     const int par = e >> 2;                           // chunk parity handled by this warp
     float* tile = epi_smem + e * EPI_TILE_FLOATS;
-    const bool need_aux = (p.act == EAVIT_ACT_GELU_BWD || p.act == EAVIT_ACT_LRELU_BWD || p.act == EAVIT_ACT_RELU_BWD);
+    constexpr bool GEN = EPI == E_GENERIC;
+    const bool need_aux = GEN ? (p.act == EAVIT_ACT_GELU_BWD || p.act == EAVIT_ACT_LRELU_BWD || p.act == EAVIT_ACT_RELU_BWD) : (EPI == E_GELU_BWD);
+    const bool has_bias = GEN || EPI == E_STORE ? (p.bias != nullptr) : (EPI == E_GELU_FWD || EPI == E_RESID);
+    const bool has_pre = GEN ? (p.out_pre != nullptr) : (EPI == E_GELU_FWD);
+    const bool has_res = GEN ? (p.residual != nullptr) : (EPI == E_RESID);
+    const bool out_f32 = GEN || EPI == E_STORE ? (p.out_f32 != nullptr) : (EPI == E_RESID || EPI == E_ATOMIC);
+    const bool out_b16 = GEN || EPI == E_STORE ? (p.out_bf16 != nullptr) : (EPI == E_GELU_FWD || EPI == E_GELU_BWD);
+    const bool atomic = GEN ? (p.atomic_f32 != 0) : (EPI == E_ATOMIC);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
       const int n_blk = tile_i % p.n_tiles, m_blk = (tile_i / p.n_tiles) % p.m_tiles;
@@ -198,12 +209,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int col = col0 + cchunk * 4;
         if (col < p.N) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
           // issue every global read of this chunk first (8 independent 16-byte loads per lane): the epilogue is
           // latency-bound on HBM unless ~40 KB per SM are in flight
           float4 res[8];
           uint2 ax[8];
-          if (p.residual != nullptr) {
+          if (has_res) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + rsub;
@@ -224,27 +235,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               const float4 t = *reinterpret_cast<const float4*>(tile + rr * 32 + ((cchunk ^ (rr & 7)) << 2));
               float v[4] = {t.x + b4.x, t.y + b4.y, t.z + b4.z, t.w + b4.w};
               const size_t off = (size_t)(row0 + rr) * (size_t)p.ldc + col;
-              if (p.out_pre != nullptr)
+              if (has_pre)
                 *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-              if (p.act != EAVIT_ACT_NONE) {
-                float a[4] = {0.f, 0.f, 0.f, 0.f};
-                if (need_aux) {
-                  const float2 lo = unpack_bf16x2(ax[it].x), hi = unpack_bf16x2(ax[it].y);
-                  a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
-                }
+              if constexpr (EPI == E_GELU_FWD) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act, a[i]);
+                for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
+              } else if constexpr (EPI == E_GELU_BWD) {
+                const float2 lo = unpack_bf16x2(ax[it].x), hi = unpack_bf16x2(ax[it].y);
+                v[0] *= gelu_erf_grad(lo.x); v[1] *= gelu_erf_grad(lo.y); v[2] *= gelu_erf_grad(hi.x); v[3] *= gelu_erf_grad(hi.y);
+              } else if constexpr (GEN) {
+                if (p.act != EAVIT_ACT_NONE) {
+                  float a[4] = {0.f, 0.f, 0.f, 0.f};
+                  if (need_aux) {
+                    const float2 lo = unpack_bf16x2(ax[it].x), hi = unpack_bf16x2(ax[it].y);
+                    a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+                  }
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act, a[i]);
+                }
               }
-              if (p.residual != nullptr) { v[0] += res[it].x; v[1] += res[it].y; v[2] += res[it].z; v[3] += res[it].w; }
-              if (p.out_f32 != nullptr) {
-                if (p.atomic_f32) {
+              if (has_res) { v[0] += res[it].x; v[1] += res[it].y; v[2] += res[it].z; v[3] += res[it].w; }
+              if (out_f32) {
+                if (atomic) {
 #pragma unroll
                   for (int i = 0; i < 4; ++i) atomicAdd(p.out_f32 + off + i, v[i]);
                 } else {
                   *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
                 }
               }
-              if (p.out_bf16 != nullptr)
+              if (out_b16)
                 *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
             }
           }
@@ -308,12 +327,12 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return EAVIT_OK;
 }
 
-template <int BN>
+template <int BN, int EPI>
 static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES));
     attr_done = true;
   }
@@ -347,7 +366,7 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   p.atomic_f32 = a->atomic_f32;
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -370,7 +389,20 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
   EAVIT_CHECK_ARG(!need_aux || a->aux_bf16 != nullptr);
   EAVIT_CHECK_ARG(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->N > 128) return launch_gemm<256>(a, st);
-  if (a->N > 64) return launch_gemm<128>(a, st);
-  return launch_gemm<64>(a, st);
+  if (a->N > 128) {
+    const bool none = a->act == EAVIT_ACT_NONE;
+    const bool plain = !a->residual && !a->aux_bf16 && !a->out_pre_bf16;
+    if (a->atomic_f32 && none && plain && !a->bias && !a->out_bf16) return launch_gemm<256, E_ATOMIC>(a, st);
+    if (a->atomic_f32) return launch_gemm<256, E_GENERIC>(a, st);
+    if (a->act == EAVIT_ACT_GELU && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32)
+      return launch_gemm<256, E_GELU_FWD>(a, st);
+    if (a->act == EAVIT_ACT_GELU_BWD && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
+      return launch_gemm<256, E_GELU_BWD>(a, st);
+    if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)
+      return launch_gemm<256, E_RESID>(a, st);
+    if (none && plain) return launch_gemm<256, E_STORE>(a, st);
+    return launch_gemm<256, E_GENERIC>(a, st);
+  }
+  if (a->N > 64) return launch_gemm<128, E_GENERIC>(a, st);
+  return launch_gemm<64, E_GENERIC>(a, st);
 }
