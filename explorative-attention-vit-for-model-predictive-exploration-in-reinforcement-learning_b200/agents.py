@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import dist, ops
 from .config import default_config
 from .model import CnnActorCriticNetwork, RNDModel, Runtime, ViT_IMPLEMENTATION, _as_device_image
 from .ops import call
@@ -109,11 +109,11 @@ class RNDAgent(nn.Module):
         if self._rt is None or not self._rt.valid():
             self._rt = Runtime(self, "", n_actions=self.output_size,
                                ext_uses_int_critic=self.model.ViT_implementation_type == ViT_IMPLEMENTATION.HG_ViT)
-            if torch.distributed.is_available() and torch.distributed.is_initialized():
-                self.world_size, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+            if dist.is_dist():
+                self.world_size, self.rank = dist.world()
                 # start every rank from rank 0's weights (what DDP's constructor did at train.py:243)
-                torch.distributed.broadcast(self._rt.store.flat, 0)
-                torch.distributed.broadcast(self._rt.frozen.flat, 0)
+                dist.broadcast_(self._rt.store.flat, 0)
+                dist.broadcast_(self._rt.frozen.flat, 0)
                 self._rt.sync()
         return self._rt
 
@@ -207,7 +207,7 @@ class RNDAgent(nn.Module):
              float(self.ent_coef), gs, w["dpol"], w["dv"][B:], w["dv"][:B], w["stats"])
         rt.ac_backward(w["dpol"], w["dv"])
         if self.world_size > 1:
-            torch.distributed.all_reduce(st.grad)                        # sum over ranks; mean applied inside Adam
+            dist.allreduce_sum_(st.grad)                                 # ONE NCCL all-reduce; mean applied inside Adam
         if default_config.getboolean("UseGradClipping", fallback=False):
             nrm = torch.zeros(1, dtype=torch.float32, device=rt.device)
             call("eavit_sumsq_f32", st.grad, st.numel, nrm)

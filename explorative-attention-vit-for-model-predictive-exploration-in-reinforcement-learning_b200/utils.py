@@ -12,7 +12,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import ops
+from . import dist, ops
 from .config import default_config
 
 
@@ -106,6 +106,13 @@ class RunningMeanStd(object):
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(np.ascontiguousarray(x)).to(self._mean.device)
         x = x.contiguous()
+        if dist.is_dist():
+            # every rank holds its env shard: exchange (sum, sumsq about the shared current mean, count) -- SURVEY 8e(2)
+            s, q = ops.rms_partial(x.view(x.shape[0], -1), self._mean)
+            n = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=s.device)
+            dist.allreduce_sum_(s); dist.allreduce_sum_(q); dist.allreduce_sum_(n)
+            ops.rms_merge(s, q, float(n.item()), self._mean, self._var, self._count)
+            return
         ops.rms_update(x.view(x.shape[0], -1), self._mean, self._var, self._count)
 
     def update_from_moments(self, batch_mean, batch_var, batch_count):
@@ -175,6 +182,13 @@ class RewardForwardFilter(object):
             else torch.zeros(E, dtype=torch.float32, device=int_reward.device)
         mom = ops.reward_filter(int_reward.contiguous(), st, has, float(self.gamma))
         self.rewems = st.cpu().numpy()
+        if dist.is_dist():
+            # global moments over all ranks' envs: all-reduce (sum, sumsq), n = T * E_total; count stays T (train.py:739)
+            sums = mom[3:5].clone()
+            dist.allreduce_sum_(sums)
+            n = float(E * T * dist.world()[0])
+            mean = sums[0] / n
+            mom = torch.stack((mean, torch.clamp(sums[1] / n - mean * mean, min=0.0), mom[2], sums[0], sums[1]))
         return mom
 
 

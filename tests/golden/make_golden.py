@@ -79,6 +79,9 @@ def main():
                            "extracted_feature_embedding_dim": 128, "NumStep": 16, "MiniBatch": 4, "Epoch": 1})
         cfg = O.OracleConfig(impl="hg", patch=12, dim=128, depth=2, heads=2, dim_head=64, mlp_dim=256,
                              ln_eps=1e-12, lr=1e-3, epoch=1, mini_batch=4)
+    elif which == "init":
+        conf = write_conf({"ViTlucidrains_dropout": 0.0, "ViTlucidrains_emb_dropout": 0.0})
+        cfg = O.OracleConfig()
     else:
         raise SystemExit(which)
     out_dir = HERE
@@ -90,6 +93,15 @@ def main():
         # transformers 5.x dropped get_head_mask (SURVEY 8c shim); arithmetic unchanged
         vit_hg.ViT_ExplorativeAttn.get_head_mask = lambda self, hm, n, *a, **k: [None] * n
 
+    if which == "init":
+        # initial weights of the reference constructors under set_seed(42) (utils.py:173), as digests
+        utils.set_seed(42)
+        logger = Logger(file_log_path="./logs/golden", tb_log_path="./logs/tb")
+        agent = agents.RNDAgent(84, 18, Env_action_space_type.DISCRETE, 2, 16, 0.999, use_cuda=False, use_noisy_net=False,
+                                representation_lr_method="None", device="cpu", logger=logger)
+        np.savez_compressed(os.path.join(out_dir, "golden_init.npz"), **{k: digest(v.numpy()) for k, v in agent.state_dict().items()})
+        print("wrote golden_init.npz")
+        return
     E, T = 2, 16
     N = E * T
     logger = Logger(file_log_path="./logs/golden", tb_log_path="./logs/tb")

@@ -1,0 +1,128 @@
+"""CPU tests of the host side: config contract, drop-in parameter tree, ABI table, permutation / mask determinism."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_specs_match_header():
+    """Every ctypes argument string in ops._SPECS matches the parameter list declared in include/eavit_b200.h."""
+    from eavit_b200 import _lib, ops
+    txt = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER_PATH).read(), flags=re.S)
+    for name, spec in ops._SPECS.items():
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", txt, flags=re.S)
+        assert m, name
+        params = [p.strip() for p in m.group(1).split(",")]
+        assert params[-1].endswith("stream")
+        params = params[:-1]
+        assert len(params) == len(spec), name
+        for p, c in zip(params, spec):
+            exp = "p" if "*" in p else ("l" if "long long" in p else "i" if p.startswith("int") else "f" if p.startswith("float") else "d")
+            assert exp == c, (name, p, c)
+    declared = set(_lib.declared_symbols())
+    assert set(ops._SPECS) <= declared
+
+
+def test_config_contract():
+    from eavit_b200 import config
+    c = config.load_config(os.path.join(ROOT, "configs", "expGlados3_lucidrains_explorative.conf"))
+    assert c["TrainMethod"] == "original_RND" and int(c["MiniBatch"]) == 32 and int(c["NumStep"]) == 128
+    assert c.getboolean("ViTlucidrains_use_explorativeAttn") is True
+    hp = config.HotPathConfig.from_config()
+    assert (hp.impl, hp.dim, hp.depth, hp.heads, hp.dim_head, hp.mlp_dim, hp.patch, hp.n_patches, hp.patch_dim) == \
+        ("lucidrains", 256, 3, 8, 32, 1024, 6, 196, 144)
+    assert hp.dropout == 0.1          # shipped value; parity / bench runs override it to 0.0
+    c = config.load_config(os.path.join(ROOT, "configs", "vit_hg_explorative.conf"))
+    hp = config.HotPathConfig.from_config()
+    assert (hp.impl, hp.dim, hp.depth, hp.heads, hp.dim_head, hp.n_patches, hp.ln_eps) == ("hg", 1024, 12, 16, 64, 49, 1e-12)
+    config.load_config(None, ViTlucidrains_dropout=0.0)
+    assert float(config.default_config["ViTlucidrains_dropout"]) == 0.0
+
+
+@pytest.mark.parametrize("which", ["lucid", "cls", "hg"])
+def test_state_dict_names_and_shapes_match_reference(which):
+    """Parameter tree == the reference's state_dict (names + shapes pinned by tests/golden/make_golden.py, which
+    load_state_dict(strict=True)'s the same dict into the reference classes)."""
+    from eavit_b200 import config, model, utils
+    cfg = {"lucid": O.OracleConfig(), "cls": O.OracleConfig(use_explorative=False),
+           "hg": O.OracleConfig(impl="hg", patch=12, dim=128, depth=2, heads=2, dim_head=64, mlp_dim=256)}[which]
+    if which == "hg":
+        config.load_config(None, ViT_implementation_type=1, ViTHG_hidden_size=128, ViTHG_num_hidden_layers=2,
+                           ViTHG_num_attention_heads=2, ViTHG_intermediate_size=256, extracted_feature_embedding_dim=128)
+        impl = model.ViT_IMPLEMENTATION.HG_ViT
+    else:
+        config.load_config(None, ViTlucidrains_use_explorativeAttn=cfg.use_explorative)
+        impl = model.ViT_IMPLEMENTATION.LUCIDRAINS_ViT
+    ac = model.CnnActorCriticNetwork(84, 18, utils.Env_action_space_type.DISCRETE, False, ViT_implementation_type=impl)
+    rnd = model.RNDModel(input_size=84, output_size=512, train_method="original_RND")
+    got = {"model." + k: tuple(v.shape) for k, v in ac.state_dict().items()}
+    got.update({"rnd." + k: tuple(v.shape) for k, v in rnd.state_dict().items()})
+    assert got == O.param_shapes(cfg)
+    assert not any(p.requires_grad for p in rnd.target.parameters())       # model.py:453-455
+    assert all(p.requires_grad for p in rnd.predictor.parameters())
+    config.load_config(None)
+
+
+def test_seeded_init_matches_reference(golden_dir):
+    """Constructors consume torch's RNG in the reference's order: same seed -> same initial weights (lucidrains)."""
+    from eavit_b200 import config, model, utils
+    G = np.load(os.path.join(golden_dir, "golden_init.npz"))
+    config.load_config(None, ViTlucidrains_dropout=0.0, ViTlucidrains_emb_dropout=0.0)
+    utils.set_seed(42)
+    ac = model.CnnActorCriticNetwork(84, 18, utils.Env_action_space_type.DISCRETE, False)
+    rnd = model.RNDModel(input_size=84, output_size=512, train_method="original_RND")
+    sd = {"model." + k: v for k, v in ac.state_dict().items()}
+    sd.update({"rnd." + k: v for k, v in rnd.state_dict().items()})
+    for k, v in sd.items():
+        a = v.double().reshape(-1).numpy()
+        idx = np.linspace(0, a.size - 1, 64).astype(np.int64)
+        d = np.concatenate([[np.sqrt((a * a).sum()), a.sum()], a[idx]])
+        np.testing.assert_allclose(d, G[k], rtol=1e-6, atol=1e-7, err_msg=k)
+
+
+def test_minibatch_permutation_and_mask_are_host_rng_bit_exact():
+    """agents.py:270-285 / :336: the index stream is numpy MT19937 shuffles of ONE persistent arange, the RND mask is
+    torch.rand on the CPU generator; the product draws them with the same calls (agents.train_model), so they are
+    bit-identical by construction.  This pins the oracle's stream against a literal transcription."""
+    N, B, epochs = 64, 16, 3
+    np.random.seed(9)
+    torch.manual_seed(9)
+    sample_range = np.arange(N)
+    ref_idx, ref_mask = [], []
+    for _ in range(epochs):
+        np.random.shuffle(sample_range)
+        for j in range(N // B):
+            ref_idx.append(sample_range[B * j:B * (j + 1)].copy())
+            ref_mask.append((torch.rand(B) < 0.25).float())
+    # the product's order of draws: all masks up front (torch stream), shuffles in the loop (numpy stream)
+    np.random.seed(9)
+    torch.manual_seed(9)
+    masks = torch.stack([(torch.rand(B) < 0.25).float() for _ in range(epochs * (N // B))])
+    sr = np.arange(N)
+    got_idx = []
+    for _ in range(epochs):
+        np.random.shuffle(sr)
+        for j in range(N // B):
+            got_idx.append(sr[B * j:B * (j + 1)].copy())
+    assert all(np.array_equal(a, b) for a, b in zip(ref_idx, got_idx))
+    assert torch.equal(masks, torch.stack(ref_mask))
+    assert sorted(np.concatenate(got_idx[: N // B]).tolist()) == list(range(N))      # each epoch covers every sample once
+
+
+def test_no_cpu_fallback():
+    """The product refuses to compute without CUDA instead of silently falling back."""
+    from eavit_b200 import config, model, utils
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    config.load_config(None, ViTlucidrains_dropout=0.0, ViTlucidrains_emb_dropout=0.0)
+    ac = model.CnnActorCriticNetwork(84, 18, utils.Env_action_space_type.DISCRETE, False)
+    with pytest.raises(RuntimeError):
+        ac(torch.zeros(1, 4, 84, 84))
+    with pytest.raises(RuntimeError):
+        utils.make_train_data(np.zeros((2, 4)), np.zeros((2, 4), dtype=bool), np.zeros((2, 5), dtype=np.float32), 0.99, 4, 2)
