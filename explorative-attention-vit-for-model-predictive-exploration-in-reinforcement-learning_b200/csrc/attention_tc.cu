@@ -1,40 +1,69 @@
-// Tensor-core attention for short sequences (S <= 224) on tcgen05 / TMEM, one CTA per (sequence, head) work item.
+// Tensor-core attention for short sequences (S <= 224) on tcgen05 / TMEM, one CTA (512 threads) per (sequence, head).
 //
 // The whole head fits on chip, so there is no online softmax and no K/V loop:
 //   scores  S = Q K^T        tcgen05.mma  128 x NKT x DH   (A = Q tile, B = K, both K-major in 128B-swizzled smem)
-//   softmax                  each thread owns one query row of the TMEM accumulator (tcgen05.ld), exp2 in fp32,
+//   softmax                  threads own (row, column-slice) pieces of the TMEM accumulator (tcgen05.ld), exp2 in fp32,
 //                            un-normalised P written as bf16 into swizzled smem (the A operand of the next MMA)
 //   output  O = P V          tcgen05.mma  128 x 64 x NKP   (B = V used in place as an MN-major operand -- no transpose)
 //   epilogue                 O / rowsum -> bf16, lse = max + log(sum)
-// Two warpgroups process the two 128-row query tiles of a 196/197-token sequence concurrently (TMEM lanes are
-// per-warp-quadrant, so warpgroup g owns tile g); the O accumulator overlays the dead S columns.
+// The kernels are instruction-issue bound (exp2 / convert / pack per score; ncu: tensor pipe 7-11 %, DRAM 8 %), so each
+// TMEM row is shared by several warps (the lane quadrant of warp w is w % 4 for every warp): 16 warps per SM instead of 8.
 // Scores never leave the SM: the reference materialises [B,8,S,S] fp32 (vit.py:66-71).
 #include "common.cuh"
 #include "tc05.cuh"
 
 namespace eavit {
 
-constexpr int ATC_THREADS = 256;
+constexpr int ATC_THREADS = 512;
 constexpr int ATC_MAXKEYS = 224;          // TMEM: 2 tiles x 224 score columns = 448 <= 512
 constexpr int ROWB = 128;                 // bytes per smem row (64 bf16): one 128B swizzle row
+constexpr int P_SLAB = 128 * ROWB;        // [128 rows][64 keys]
 
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a K-major 128B-swizzled slab [rows][128 B]
 __device__ __forceinline__ uint32_t sw_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Cooperative staging of rows [0,S) x DH of NMAT matrices into swizzled smem, split into an asynchronous half (global
+// loads into registers, issued one item AHEAD so that their latency overlaps the previous item's compute -- the kernels
+// run one item per SM at a time and were bound by this serial load -> MMA -> softmax chain) and a commit half.
+template <int DH, int NMAT, int NPF>
+struct RowStager {
+  uint4 v[NPF];
+  uint32_t dst[NPF];
+  __device__ __forceinline__ void load(const int* offs, const __nv_bfloat16* const* srcs, const int* lds, int S, int tid) {
+    constexpr int CH = DH / 8;
+    const int total = S * CH * NMAT;
+#pragma unroll
+    for (int u = 0; u < NPF; ++u) {
+      const int i = tid + u * ATC_THREADS;
+      dst[u] = 0xffffffffu;
+      if (i < total) {
+        const int which = i / (S * CH), rem = i % (S * CH);
+        const int r = rem / CH, c = rem % CH;
+        v[u] = __ldg(reinterpret_cast<const uint4*>(srcs[which] + (size_t)r * lds[which]) + c);
+        dst[u] = offs[which] + sw_off(r, c);
+      }
+    }
+  }
+  __device__ __forceinline__ void commit(uint8_t* smem) {
+#pragma unroll
+    for (int u = 0; u < NPF; ++u)
+      if (dst[u] != 0xffffffffu) *reinterpret_cast<uint4*>(smem + dst[u]) = v[u];
+  }
+};
 
 struct AttSmem {
-  static constexpr int Q_BYTES = 256 * ROWB;              // 2 query tiles
-  static constexpr int K_BYTES = ATC_MAXKEYS * ROWB;
-  static constexpr int V_BYTES = ATC_MAXKEYS * ROWB;
-  static constexpr int P_SLAB = 128 * ROWB;               // [128 rows][64 keys]
-  static constexpr int P_BYTES = 4 * P_SLAB;              // per tile: 256 keys max
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + Q_BYTES;
-  static constexpr int OFF_V = OFF_K + K_BYTES;
-  static constexpr int OFF_P = OFF_V + V_BYTES;           // 2 tiles
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 64 + 1024;       // + alignment slack
+  static constexpr int OFF_Q = 0;                                // [256][128 B]
+  static constexpr int OFF_K = OFF_Q + 256 * ROWB;               // [224][128 B]
+  static constexpr int OFF_V = OFF_K + ATC_MAXKEYS * ROWB;
+  static constexpr int OFF_P = OFF_V + ATC_MAXKEYS * ROWB;       // 2 tiles x 4 slabs
+  static constexpr int OFF_X = OFF_P + 2 * 4 * P_SLAB;           // float [2 halves][256 rows] max, then sum
+  static constexpr int OFF_BAR = OFF_X + 2 * 2 * 256 * 4;
+  static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
 template <int DH>
@@ -43,16 +72,19 @@ attention_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __rest
                         float scale, __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + AttSmem::OFF_BAR);       // [2] scores ready
-  uint64_t* bar_o = bar_s + 2;                                                  // [2] output ready
+  float* sMax = reinterpret_cast<float*>(smem + AttSmem::OFF_X);      // [2][256]
+  float* sSum = sMax + 512;                                            // [2][256]
+  uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + AttSmem::OFF_BAR);
+  uint64_t* bar_o = bar_s + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = warp >> 2;                 // warpgroup = query tile
-  const int quad = warp & 3;                // TMEM lane quadrant
+  const int quad = warp & 3, grp = warp >> 2;   // 4 groups of 4 warps
+  const int g = grp & 1;                        // query tile
+  const int hf = grp >> 1;                      // column half of the tile's score row
   const int row_in_tile = quad * 32 + lane;
+  const int xrow = g * 128 + row_in_tile;
 
-  // zero the operand buffers once: stale rows are multiplied by P = 0 and must be finite
-  for (int i = tid; i < AttSmem::OFF_BAR / 16; i += ATC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < AttSmem::OFF_X / 16; i += ATC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bar_s[i], 1); tc::mbar_init(&bar_o[i], 1); }
     tc::fence_barrier_init();
@@ -65,89 +97,84 @@ attention_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __rest
 
   const int ldq = 3 * H * DH, ldo = H * DH;
   const float c2 = scale * 1.4426950408889634f;      // exp(x*scale) = exp2(x*c2)
-  constexpr int CH = DH / 8;                         // 16-byte chunks per row
   uint32_t phase = 0;
   const int n_items = nseq * H;
+  constexpr int NPF = (ATC_MAXKEYS * (DH / 8) * 3 + ATC_THREADS - 1) / ATC_THREADS;
+  RowStager<DH, 3, NPF> stager;
+  auto prefetch = [&](int it) {
+    const int sq = it / H, hh = it % H;
+    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const __nv_bfloat16* base = qkv + (size_t)tt * ldq + hh * DH;
+    const __nv_bfloat16* srcs[3] = {base, base + H * DH, base + 2 * H * DH};
+    const int offs[3] = {AttSmem::OFF_Q, AttSmem::OFF_K, AttSmem::OFF_V};
+    const int lds[3] = {ldq, ldq, ldq};
+    stager.load(offs, srcs, lds, SS, tid);
+  };
+  if ((int)blockIdx.x < n_items) prefetch(blockIdx.x);
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int seq = item / H, h = item % H;
     const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
-    const int NKT = (S + 31) & ~31;                  // score columns (multiple of 32 -> whole tcgen05.ld chunks)
-    const int NKP = (S + 15) & ~15;                  // keys covered by the P.V MMA (multiple of UMMA_K)
-    // ---- stage Q, K, V rows into swizzled smem (generic proxy)
-    {
-      constexpr int UN = 4;                        // independent 16-byte loads in flight per thread
-      const int total = S * CH * 3;
-      for (int i0 = tid; i0 < total; i0 += ATC_THREADS * UN) {
-        uint4 v[UN];
-        uint32_t dst[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          const int i = i0 + u * ATC_THREADS;
-          dst[u] = 0xffffffffu;
-          if (i < total) {
-            const int which = i / (S * CH), rem = i % (S * CH);
-            const int r = rem / CH, c = rem % CH;
-            v[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(t0 + r) * ldq + which * H * DH + h * DH) + c);
-            dst[u] = (which == 0 ? AttSmem::OFF_Q : (which == 1 ? AttSmem::OFF_K : AttSmem::OFF_V)) + sw_off(r, c);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < UN; ++u)
-          if (dst[u] != 0xffffffffu) *reinterpret_cast<uint4*>(smem + dst[u]) = v[u];
-      }
-    }
+    const int NKT = (S + 31) & ~31;                  // score columns
+    const int NKP = (S + 15) & ~15;                  // keys covered by the P.V MMA
+    stager.commit(smem);
     tc::fence_proxy_async();
     __syncthreads();
-    const bool active = wg * 128 < S;
+    if (item + (int)gridDim.x < n_items) prefetch(item + gridDim.x);     // lands during this item's compute
+    const bool active = g * 128 < S;
     if (active) {
-      const uint32_t s_col = tmem_base + (uint32_t)(wg * ATC_MAXKEYS);
-      if (quad == 0 && lane == 0) {
+      const uint32_t s_col = tmem_base + (uint32_t)(g * ATC_MAXKEYS);
+      const bool issuer = (hf == 0 && quad == 0 && lane == 0);
+      if (issuer) {
         tc::fence_after_sync();
         const uint32_t idesc = tc::make_idesc_bf16(128, NKT, 0, 0);
-        const uint32_t qa = tc::smem_u32(smem + AttSmem::OFF_Q + wg * 128 * ROWB);
+        const uint32_t qa = tc::smem_u32(smem + AttSmem::OFF_Q + g * 128 * ROWB);
         const uint32_t ka = tc::smem_u32(smem + AttSmem::OFF_K);
         const uint64_t adesc = tc::make_sdesc_sw128(qa, 16, 1024), bdesc = tc::make_sdesc_sw128(ka, 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(s_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k > 0);
-        tc::mma_commit(&bar_s[wg]);
+        tc::mma_commit(&bar_s[g]);
       }
-      tc::mbar_wait(&bar_s[wg], phase);
+      tc::mbar_wait(&bar_s[g], phase);
       tc::fence_after_sync();
       const uint32_t lane_addr = s_col + ((uint32_t)(quad * 32) << 16);
-      // pass 1: row max over the valid keys
+      const int half = NKT >> 1, cbeg = hf * half;      // half is a multiple of 16
+      // pass 1: partial row max over this thread's columns
       float mx = -INFINITY;
-      for (int c0 = 0; c0 < NKT; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(lane_addr + c0, r);
+      for (int c0 = cbeg; c0 < cbeg + half; c0 += 16) {
+        uint32_t r[16];
+        tc::tmem_ld_32x16(lane_addr + c0, r);
         tc::tmem_ld_wait();
-        if (c0 + 32 <= S) {
+        if (c0 + 16 <= S) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < 16; ++j)
             if (c0 + j < S) mx = fmaxf(mx, __uint_as_float(r[j]));
         }
       }
-      // pass 2: p = exp2((s - mx) * c2) -> bf16 P tile in swizzled smem, fp32 row sum of the ROUNDED values
+      sMax[hf * 256 + xrow] = mx;
+      named_bar_sync(1 + g, 256);
+      mx = fmaxf(sMax[xrow], sMax[256 + xrow]);
+      // pass 2: p = exp2((s - mx) * c2) -> bf16 P tile in swizzled smem, fp32 sum of the ROUNDED values
       const float mb = mx * c2;
       float sum = 0.f;
-      uint8_t* pbase = smem + AttSmem::OFF_P + wg * AttSmem::P_BYTES;
-      for (int c0 = 0; c0 < NKT; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(lane_addr + c0, r);
+      uint8_t* pbase = smem + AttSmem::OFF_P + g * 4 * P_SLAB;
+      for (int c0 = cbeg; c0 < cbeg + half; c0 += 16) {
+        uint32_t r[16];
+        tc::tmem_ld_32x16(lane_addr + c0, r);
         tc::tmem_ld_wait();
-        uint32_t pk[16];
-        if (c0 + 32 <= S) {
+        uint32_t pk[8];
+        if (c0 + 16 <= S) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
+          for (int j = 0; j < 16; j += 2) {
             pk[j >> 1] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb)), ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb)));
             const float2 q = unpack_bf16x2(pk[j >> 1]);
             sum += q.x + q.y;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
+          for (int j = 0; j < 16; j += 2) {
             const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb)) : 0.f;
             const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb)) : 0.f;
             pk[j >> 1] = pack_bf16x2(p0, p1);
@@ -156,58 +183,317 @@ attention_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __rest
           }
         }
         if (c0 < NKP) {
-          uint8_t* slab = pbase + (c0 >> 6) * AttSmem::P_SLAB;
-          const int cb = (c0 & 63) >> 3;                                   // first 16-byte chunk of this 32-key group
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + q4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          uint8_t* slab = pbase + (c0 >> 6) * P_SLAB;
+          const int cb = (c0 & 63) >> 3;
+          *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
       }
+      sSum[hf * 256 + xrow] = sum;
       // all S reads done (O overlays S) and P visible to the async proxy, then one thread issues P.V
       tc::fence_before_sync();
       tc::fence_proxy_async();
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
-      if (quad == 0 && lane == 0) {
+      named_bar_sync(1 + g, 256);
+      if (issuer) {
         tc::fence_after_sync();
         const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 1);
         const uint32_t pa = tc::smem_u32(pbase);
         const uint32_t va = tc::smem_u32(smem + AttSmem::OFF_V);
         for (int kk = 0; kk < NKP / 16; ++kk) {
-          const uint64_t adesc = tc::make_sdesc_sw128(pa + (kk >> 2) * AttSmem::P_SLAB + (kk & 3) * 32, 16, 1024);
+          const uint64_t adesc = tc::make_sdesc_sw128(pa + (kk >> 2) * P_SLAB + (kk & 3) * 32, 16, 1024);
           const uint64_t bdesc = tc::make_sdesc_sw128(va + kk * 2048, 8192, 1024);
           tc::mma_bf16_ss(s_col, adesc, bdesc, idesc, kk > 0);
         }
-        tc::mma_commit(&bar_o[wg]);
+        tc::mma_commit(&bar_o[g]);
       }
-      tc::mbar_wait(&bar_o[wg], phase);
+      sum = sSum[xrow] + sSum[256 + xrow];
+      tc::mbar_wait(&bar_o[g], phase);
       tc::fence_after_sync();
       {
+        constexpr int HW = DH / 2;                   // output columns per thread
         uint32_t r[32];
-        const int qrow = wg * 128 + row_in_tile;
+        if constexpr (HW == 16) tc::tmem_ld_32x16(lane_addr + hf * HW, r);
+        else tc::tmem_ld_32x32(lane_addr + hf * HW, r);
+        tc::tmem_ld_wait();
+        const int qrow = xrow;
         const float inv = 1.f / sum;
+        if (qrow < S) {
+          __nv_bfloat16* orow = out + (size_t)(t0 + qrow) * ldo + h * DH + hf * HW;
 #pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 32) {
-          tc::tmem_ld_32x32(lane_addr + c0, r);
-          tc::tmem_ld_wait();
-          if (qrow < S) {
-            __nv_bfloat16* orow = out + (size_t)(t0 + qrow) * ldo + h * DH + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
-              o.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
-              o.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
-              o.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
-              *reinterpret_cast<uint4*>(orow + j) = o;
-            }
+          for (int j = 0; j < HW; j += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + j) = o;
           }
+          if (hf == 0 && lse != nullptr) lse[(size_t)(t0 + qrow) * H + h] = mx * scale + __logf(sum);
         }
-        if (qrow < S && lse != nullptr) lse[(size_t)(t0 + qrow) * H + h] = mx * scale + __logf(sum);
       }
       tc::fence_before_sync();
+      phase ^= 1;
     }
-    if (active) phase ^= 1;
     __syncthreads();          // every MMA that read this item's smem has completed (both bar_o waits passed)
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================================
+// Backward.  Per (sequence, head) item and per 128-row query tile g, all 512 threads work on one tile: the four groups
+// of four warps split the key columns of each TMEM row four ways.
+//   S  = Q_g K^T, dP = dO_g V^T                tcgen05.mma 128 x NKT x DH  (TMEM cols [0,NKT) and [224,224+NKT))
+//   P~ = bf16(exp2(S c2 - lse log2e))           -> swizzled smem;   D_i = sum_j P~_ij dP_ij   (quarters exchanged via smem)
+//   dV_kt += P~^T dO_g                          tcgen05.mma 128 x 64 x 128, A = P~ read in place as an MN-major operand
+//   dS = P~ (dP - D)                            -> the same smem buffer once dV has consumed P~
+//   dK_kt += dS^T Q_g ; dQ_g = dS K             A = dS MN-major / K-major, B = Q_g / K in place as MN-major operands
+// dK / dV partial sums of the two query tiles are accumulated in registers (half a key row per thread).
+// =====================================================================================================================
+struct AttBwdSmem {
+  static constexpr int OFF_Q = 0;                                  // [256][128 B]
+  static constexpr int OFF_DO = OFF_Q + 256 * ROWB;                // [256][128 B]
+  static constexpr int OFF_K = OFF_DO + 256 * ROWB;                // [224][128 B]
+  static constexpr int OFF_V = OFF_K + ATC_MAXKEYS * ROWB;
+  static constexpr int OFF_P = OFF_V + ATC_MAXKEYS * ROWB;         // 4 slabs [128][64 keys]
+  static constexpr int OFF_D = OFF_P + 4 * P_SLAB;                 // float [4][128]
+  static constexpr int OFF_BAR = OFF_D + 4 * 128 * 4;
+  static constexpr int TOTAL = OFF_BAR + 64 + 1024;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                        const float* __restrict__ lse, const int* __restrict__ seq_start, int nseq, int H, float scale,
+                        __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* sD = reinterpret_cast<float*>(smem + AttBwdSmem::OFF_D);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttBwdSmem::OFF_BAR);   // [0] S,dP  [1] dV  [2] dK,dQ
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, grp = warp >> 2;      // 4 column groups
+  const int row_in_tile = quad * 32 + lane;
+  const int kt = grp & 1, kh = grp >> 1;           // key tile / column half owned for the dK, dV accumulators
+
+  for (int i = tid; i < AttBwdSmem::OFF_D / 16; i += ATC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+
+  const int ldq = 3 * H * DH, ldo = H * DH;
+  const float c2 = scale * 1.4426950408889634f;
+  constexpr int COL_DP = 224, COL_DV = 0, COL_DK = 128, COL_DQ = 256;
+  constexpr int HC = DH / 2;                       // accumulator columns per thread
+  uint32_t phase = 0;
+  const int n_items = nseq * H;
+  const uint32_t sQ = tc::smem_u32(smem + AttBwdSmem::OFF_Q), sDO = tc::smem_u32(smem + AttBwdSmem::OFF_DO);
+  const uint32_t sK = tc::smem_u32(smem + AttBwdSmem::OFF_K), sV = tc::smem_u32(smem + AttBwdSmem::OFF_V);
+  const uint32_t sP = tc::smem_u32(smem + AttBwdSmem::OFF_P);
+  uint8_t* pbuf = smem + AttBwdSmem::OFF_P;
+
+  constexpr int NPF = ((DH == 64 ? 128 : ATC_MAXKEYS) * (DH / 8) * 4 + ATC_THREADS - 1) / ATC_THREADS;   // Dh = 64 is limited to 128 keys
+  RowStager<DH, 4, NPF> stager;
+  auto prefetch = [&](int it) {
+    const int sq = it / H, hh = it % H;
+    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const __nv_bfloat16* base = qkv + (size_t)tt * ldq + hh * DH;
+    const __nv_bfloat16* srcs[4] = {base, base + H * DH, base + 2 * H * DH, dout + (size_t)tt * ldo + hh * DH};
+    const int offs[4] = {AttBwdSmem::OFF_Q, AttBwdSmem::OFF_K, AttBwdSmem::OFF_V, AttBwdSmem::OFF_DO};
+    const int lds[4] = {ldq, ldq, ldq, ldo};
+    stager.load(offs, srcs, lds, SS, tid);
+  };
+  if ((int)blockIdx.x < n_items) prefetch(blockIdx.x);
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int seq = item / H, h = item % H;
+    const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
+    const int NKT = (S + 31) & ~31, NKP = (S + 15) & ~15;
+    const int NQ = (S + 127) >> 7;                 // query tiles == key tiles
+    stager.commit(smem);
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (item + (int)gridDim.x < n_items) prefetch(item + gridDim.x);     // lands during this item's compute
+
+    float accK[HC], accV[HC];                      // key row kt*128 + row_in_tile, columns [kh*HC, +HC), summed over query tiles
+#pragma unroll
+    for (int d = 0; d < HC; ++d) { accK[d] = 0.f; accV[d] = 0.f; }
+
+    for (int g = 0; g < NQ; ++g) {
+      // ---- (1) S = Q_g K^T, (2) dP = dO_g V^T
+      if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::make_idesc_bf16(128, NKT, 0, 0);
+        const uint64_t aq = tc::make_sdesc_sw128(sQ + g * 128 * ROWB, 16, 1024), bk = tc::make_sdesc_sw128(sK, 16, 1024);
+        const uint64_t ao = tc::make_sdesc_sw128(sDO + g * 128 * ROWB, 16, 1024), bv = tc::make_sdesc_sw128(sV, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base, aq + (uint64_t)(k * 2), bk + (uint64_t)(k * 2), idesc, k > 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base + COL_DP, ao + (uint64_t)(k * 2), bv + (uint64_t)(k * 2), idesc, k > 0);
+        tc::mma_commit(&bars[0]);
+      }
+      tc::mbar_wait(&bars[0], phase);
+      tc::fence_after_sync();
+      const int qrow = g * 128 + row_in_tile;
+      const bool qok = qrow < S;
+      const float l2 = qok ? lse[(size_t)(t0 + qrow) * H + h] * 1.4426950408889634f : INFINITY;   // invalid row: P~ = 0
+      const int quarter = NKT >> 2;                 // multiple of 8
+      const int cbeg = grp * quarter;
+      // ---- pass 1: P~ -> smem, partial D
+      float dpart = 0.f;
+      for (int c0 = cbeg; c0 < cbeg + quarter; c0 += 8) {
+        uint32_t rs[8], rp[8];
+        tc::tmem_ld_32x8(lane_base + c0, rs);
+        tc::tmem_ld_32x8(lane_base + COL_DP + c0, rp);
+        tc::tmem_ld_wait();
+        uint32_t pk[4];
+        if (c0 + 8 <= S) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            pk[j >> 1] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)), ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)));
+            const float2 q = unpack_bf16x2(pk[j >> 1]);
+            dpart = fmaf(q.x, __uint_as_float(rp[j]), fmaf(q.y, __uint_as_float(rp[j + 1]), dpart));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
+            const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
+            const float2 q = unpack_bf16x2(pk[j >> 1]);
+            dpart = fmaf(q.x, __uint_as_float(rp[j]), fmaf(q.y, __uint_as_float(rp[j + 1]), dpart));
+          }
+        }
+        *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      sD[grp * 128 + row_in_tile] = dpart;
+      tc::fence_before_sync();
+      tc::fence_proxy_async();
+      __syncthreads();
+      // ---- (3) dV_kt = P~^T dO_g   (S columns are dead now: accumulators overlay them)
+      if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::make_idesc_bf16(128, 64, 1, 1);
+        for (int t = 0; t < NQ; ++t)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t a = tc::make_sdesc_sw128(sP + 2 * t * P_SLAB + kk * 2048, P_SLAB, 1024);
+            const uint64_t b = tc::make_sdesc_sw128(sDO + g * 128 * ROWB + kk * 2048, 8192, 1024);
+            tc::mma_bf16_ss(tmem_base + COL_DV + t * 64, a, b, idesc, kk > 0);
+          }
+        tc::mma_commit(&bars[1]);
+      }
+      const float Di = (sD[row_in_tile] + sD[128 + row_in_tile]) + (sD[256 + row_in_tile] + sD[384 + row_in_tile]);
+      tc::mbar_wait(&bars[1], phase);             // dV has consumed P~: the buffer can take dS
+      tc::fence_after_sync();
+      // ---- pass 2: dS = P~ (dP - D) -> smem
+      for (int c0 = cbeg; c0 < cbeg + quarter; c0 += 8) {
+        uint32_t rp[8];
+        tc::tmem_ld_32x8(lane_base + COL_DP + c0, rp);
+        uint8_t* addr = pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3);
+        const uint4 pa = *reinterpret_cast<uint4*>(addr);
+        tc::tmem_ld_wait();
+        const uint32_t pin[4] = {pa.x, pa.y, pa.z, pa.w};
+        uint32_t ds[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 p = unpack_bf16x2(pin[j]);
+          ds[j] = pack_bf16x2(p.x * (__uint_as_float(rp[2 * j]) - Di), p.y * (__uint_as_float(rp[2 * j + 1]) - Di));
+        }
+        *reinterpret_cast<uint4*>(addr) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+      }
+      tc::fence_before_sync();
+      tc::fence_proxy_async();
+      __syncthreads();
+      // ---- (4) dK_kt = dS^T Q_g ; (5) dQ_g = dS K
+      if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc_t = tc::make_idesc_bf16(128, 64, 1, 1);
+        for (int t = 0; t < NQ; ++t)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t a = tc::make_sdesc_sw128(sP + 2 * t * P_SLAB + kk * 2048, P_SLAB, 1024);
+            const uint64_t b = tc::make_sdesc_sw128(sQ + g * 128 * ROWB + kk * 2048, 8192, 1024);
+            tc::mma_bf16_ss(tmem_base + COL_DK + t * 64, a, b, idesc_t, kk > 0);
+          }
+        const uint32_t idesc_q = tc::make_idesc_bf16(128, 64, 0, 1);
+        for (int kk = 0; kk < NKP / 16; ++kk) {
+          const uint64_t a = tc::make_sdesc_sw128(sP + (kk >> 2) * P_SLAB + (kk & 3) * 32, 16, 1024);
+          const uint64_t b = tc::make_sdesc_sw128(sK + kk * 2048, 8192, 1024);
+          tc::mma_bf16_ss(tmem_base + COL_DQ, a, b, idesc_q, kk > 0);
+        }
+        tc::mma_commit(&bars[2]);
+      }
+      tc::mbar_wait(&bars[2], phase);
+      tc::fence_after_sync();
+      // ---- drain: dQ rows of this tile (columns split four ways), dK / dV partials into registers
+      {
+        constexpr int QW = DH / 4;                  // 8 or 16 dQ columns per thread
+        uint32_t r[32];
+        if constexpr (QW == 8) tc::tmem_ld_32x8(lane_base + COL_DQ + grp * QW, r);
+        else tc::tmem_ld_32x16(lane_base + COL_DQ + grp * QW, r);
+        tc::tmem_ld_wait();
+        if (qok) {
+          __nv_bfloat16* dq = dqkv + (size_t)(t0 + qrow) * ldq + h * DH + grp * QW;
+#pragma unroll
+          for (int j = 0; j < QW; j += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[j]) * scale, __uint_as_float(r[j + 1]) * scale);
+            o.y = pack_bf16x2(__uint_as_float(r[j + 2]) * scale, __uint_as_float(r[j + 3]) * scale);
+            o.z = pack_bf16x2(__uint_as_float(r[j + 4]) * scale, __uint_as_float(r[j + 5]) * scale);
+            o.w = pack_bf16x2(__uint_as_float(r[j + 6]) * scale, __uint_as_float(r[j + 7]) * scale);
+            *reinterpret_cast<uint4*>(dq + j) = o;
+          }
+        }
+        if (kt < NQ) {
+          if constexpr (HC == 16) {
+            tc::tmem_ld_32x16(lane_base + COL_DV + kt * 64 + kh * HC, r);
+            tc::tmem_ld_32x16(lane_base + COL_DK + kt * 64 + kh * HC, r + 16);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { accV[j] += __uint_as_float(r[j]); accK[j] += __uint_as_float(r[16 + j]); }
+          } else {
+            tc::tmem_ld_32x32(lane_base + COL_DV + kt * 64 + kh * HC, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accV[j % HC] += (j < HC) ? __uint_as_float(r[j]) : 0.f;
+            tc::tmem_ld_32x32(lane_base + COL_DK + kt * 64 + kh * HC, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accK[j % HC] += (j < HC) ? __uint_as_float(r[j]) : 0.f;
+          }
+        }
+      }
+      tc::fence_before_sync();
+      phase ^= 1;
+      __syncthreads();                              // TMEM and smem free for the next tile / item
+    }
+    // ---- store this thread's half key row
+    const int krow = kt * 128 + row_in_tile;
+    if (krow < S) {
+      __nv_bfloat16* dk = dqkv + (size_t)(t0 + krow) * ldq + H * DH + h * DH + kh * HC;
+      __nv_bfloat16* dv = dk + H * DH;
+#pragma unroll
+      for (int j = 0; j < HC; j += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(accK[j] * scale, accK[j + 1] * scale); o.y = pack_bf16x2(accK[j + 2] * scale, accK[j + 3] * scale);
+        o.z = pack_bf16x2(accK[j + 4] * scale, accK[j + 5] * scale); o.w = pack_bf16x2(accK[j + 6] * scale, accK[j + 7] * scale);
+        *reinterpret_cast<uint4*>(dk + j) = o;
+        o.x = pack_bf16x2(accV[j], accV[j + 1]); o.y = pack_bf16x2(accV[j + 2], accV[j + 3]);
+        o.z = pack_bf16x2(accV[j + 4], accV[j + 5]); o.w = pack_bf16x2(accV[j + 6], accV[j + 7]);
+        *reinterpret_cast<uint4*>(dv + j) = o;
+      }
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -243,281 +529,8 @@ extern "C" int eavit_attention_fwd_tc(const void* qkv, const int* seq_start, int
   return EAVIT_OK;
 }
 
-namespace eavit {
-
-// =====================================================================================================================
-// Backward.  Per (sequence, head) item and per 128-row query tile g (all 256 threads work on one tile; the two
-// warpgroups split the key columns of each TMEM row, lane quadrant = warp % 4 for both):
-//   S  = Q_g K^T, dP = dO_g V^T                tcgen05.mma 128 x NKT x DH  (TMEM cols [0,NKT) and [224,224+NKT))
-//   P~ = bf16(exp2(S c2 - lse log2e))           -> swizzled smem;   D_i = sum_j P~_ij dP_ij   (halves exchanged via smem)
-//   dV_kt += P~^T dO_g                          tcgen05.mma 128 x 64 x 128, A = P~ read in place as an MN-major operand
-//   dS = P~ (dP - D)                            -> the same smem buffer once dV has consumed P~
-//   dK_kt += dS^T Q_g ; dQ_g = dS K             A = dS MN-major / K-major, B = Q_g / K in place as MN-major operands
-// dK / dV partial sums of the two query tiles are accumulated in registers (one key row per thread).
-// =====================================================================================================================
-struct AttBwdSmem {
-  static constexpr int OFF_Q = 0;                                  // [256][128 B]
-  static constexpr int OFF_DO = OFF_Q + 256 * ROWB;                // [256][128 B]
-  static constexpr int OFF_K = OFF_DO + 256 * ROWB;                // [224][128 B]
-  static constexpr int OFF_V = OFF_K + ATC_MAXKEYS * ROWB;
-  static constexpr int OFF_P = OFF_V + ATC_MAXKEYS * ROWB;         // 4 slabs [128][64 keys]
-  static constexpr int OFF_D = OFF_P + 4 * AttSmem::P_SLAB;        // float [2][128]
-  static constexpr int OFF_BAR = OFF_D + 2 * 128 * 4;
-  static constexpr int TOTAL = OFF_BAR + 64 + 1024;
-};
-
-template <int DH>
-__global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
-                        const float* __restrict__ lse, const int* __restrict__ seq_start, int nseq, int H, float scale,
-                        __nv_bfloat16* __restrict__ dqkv) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* sD = reinterpret_cast<float*>(smem + AttBwdSmem::OFF_D);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttBwdSmem::OFF_BAR);   // [0] S,dP  [1] dV  [2] dK,dQ
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = warp >> 2, quad = warp & 3;
-  const int row_in_tile = quad * 32 + lane;
-
-  for (int i = tid; i < AttBwdSmem::OFF_BAR / 16; i += ATC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) {
-    for (int i = 0; i < 3; ++i) tc::mbar_init(&bars[i], 1);
-    tc::fence_barrier_init();
-  }
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-
-  const int ldq = 3 * H * DH, ldo = H * DH;
-  const float c2 = scale * 1.4426950408889634f;
-  constexpr int CH = DH / 8;
-  constexpr int COL_DP = 224, COL_DV = 0, COL_DK = 128, COL_DQ = 256;
-  uint32_t phase = 0;
-  const int n_items = nseq * H;
-  const uint32_t sQ = tc::smem_u32(smem + AttBwdSmem::OFF_Q), sDO = tc::smem_u32(smem + AttBwdSmem::OFF_DO);
-  const uint32_t sK = tc::smem_u32(smem + AttBwdSmem::OFF_K), sV = tc::smem_u32(smem + AttBwdSmem::OFF_V);
-  const uint32_t sP = tc::smem_u32(smem + AttBwdSmem::OFF_P);
-  uint8_t* pbuf = smem + AttBwdSmem::OFF_P;
-
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int seq = item / H, h = item % H;
-    const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
-    const int NKT = (S + 31) & ~31, NKP = (S + 15) & ~15;
-    const int NQ = (S + 127) >> 7;                 // query tiles == key tiles
-    // ---- stage Q, K, V, dO
-    {
-      constexpr int UN = 4;
-      const int total = S * CH * 4;
-      for (int i0 = tid; i0 < total; i0 += ATC_THREADS * UN) {
-        uint4 v[UN];
-        uint32_t dst[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          const int i = i0 + u * ATC_THREADS;
-          dst[u] = 0xffffffffu;
-          if (i < total) {
-            const int which = i / (S * CH), rem = i % (S * CH);
-            const int r = rem / CH, c = rem % CH;
-            if (which < 3) v[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(t0 + r) * ldq + which * H * DH + h * DH) + c);
-            else v[u] = __ldg(reinterpret_cast<const uint4*>(dout + (size_t)(t0 + r) * ldo + h * DH) + c);
-            dst[u] = (which == 0 ? AttBwdSmem::OFF_Q : (which == 1 ? AttBwdSmem::OFF_K : (which == 2 ? AttBwdSmem::OFF_V : AttBwdSmem::OFF_DO))) + sw_off(r, c);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < UN; ++u)
-          if (dst[u] != 0xffffffffu) *reinterpret_cast<uint4*>(smem + dst[u]) = v[u];
-      }
-    }
-    tc::fence_proxy_async();
-    __syncthreads();
-
-    float accK[DH], accV[DH];                       // this thread's key row (wg*128 + row_in_tile), summed over query tiles
-#pragma unroll
-    for (int d = 0; d < DH; ++d) { accK[d] = 0.f; accV[d] = 0.f; }
-
-    for (int g = 0; g < NQ; ++g) {
-      // ---- (1) S = Q_g K^T, (2) dP = dO_g V^T
-      if (tid == 0) {
-        tc::fence_after_sync();
-        const uint32_t idesc = tc::make_idesc_bf16(128, NKT, 0, 0);
-        const uint64_t aq = tc::make_sdesc_sw128(sQ + g * 128 * ROWB, 16, 1024), bk = tc::make_sdesc_sw128(sK, 16, 1024);
-        const uint64_t ao = tc::make_sdesc_sw128(sDO + g * 128 * ROWB, 16, 1024), bv = tc::make_sdesc_sw128(sV, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base, aq + (uint64_t)(k * 2), bk + (uint64_t)(k * 2), idesc, k > 0);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base + COL_DP, ao + (uint64_t)(k * 2), bv + (uint64_t)(k * 2), idesc, k > 0);
-        tc::mma_commit(&bars[0]);
-      }
-      tc::mbar_wait(&bars[0], phase);
-      tc::fence_after_sync();
-      const int qrow = g * 128 + row_in_tile;
-      const bool qok = qrow < S;
-      const float l2 = qok ? lse[(size_t)(t0 + qrow) * H + h] * 1.4426950408889634f : INFINITY;   // invalid row: P~ = 0
-      const int half = NKT >> 1;                    // multiple of 16
-      const int cbeg = wg * half;
-      // ---- pass 1: P~ -> smem, partial D
-      float dpart = 0.f;
-      for (int c0 = cbeg; c0 < cbeg + half; c0 += 16) {
-        uint32_t rs[16], rp[16];
-        tc::tmem_ld_32x16(lane_base + c0, rs);
-        tc::tmem_ld_32x16(lane_base + COL_DP + c0, rp);
-        tc::tmem_ld_wait();
-        uint32_t pk[8];
-        if (c0 + 16 <= S) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            pk[j >> 1] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)), ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)));
-            const float2 q = unpack_bf16x2(pk[j >> 1]);
-            dpart = fmaf(q.x, __uint_as_float(rp[j]), fmaf(q.y, __uint_as_float(rp[j + 1]), dpart));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
-            const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
-            pk[j >> 1] = pack_bf16x2(p0, p1);
-            const float2 q = unpack_bf16x2(pk[j >> 1]);
-            dpart = fmaf(q.x, __uint_as_float(rp[j]), fmaf(q.y, __uint_as_float(rp[j + 1]), dpart));
-          }
-        }
-        uint8_t* slab = pbuf + (c0 >> 6) * AttSmem::P_SLAB;
-        const int cb = (c0 & 63) >> 3;
-        *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-      sD[wg * 128 + row_in_tile] = dpart;
-      tc::fence_before_sync();
-      tc::fence_proxy_async();
-      __syncthreads();
-      // ---- (3) dV_kt = P~^T dO_g   (S columns are dead now: accumulators overlay them)
-      if (tid == 0) {
-        tc::fence_after_sync();
-        const uint32_t idesc = tc::make_idesc_bf16(128, 64, 1, 1);
-        for (int kt = 0; kt < NQ; ++kt)
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t a = tc::make_sdesc_sw128(sP + 2 * kt * AttSmem::P_SLAB + kk * 2048, AttSmem::P_SLAB, 1024);
-            const uint64_t b = tc::make_sdesc_sw128(sDO + g * 128 * ROWB + kk * 2048, 8192, 1024);
-            tc::mma_bf16_ss(tmem_base + COL_DV + kt * 64, a, b, idesc, kk > 0);
-          }
-        tc::mma_commit(&bars[1]);
-      }
-      const float Di = sD[row_in_tile] + sD[128 + row_in_tile];
-      tc::mbar_wait(&bars[1], phase);             // dV has consumed P~: the buffer can take dS
-      tc::fence_after_sync();
-      // ---- pass 2: dS = P~ (dP - D) -> smem
-      for (int c0 = cbeg; c0 < cbeg + half; c0 += 16) {
-        uint32_t rp[16];
-        tc::tmem_ld_32x16(lane_base + COL_DP + c0, rp);
-        uint8_t* slab = pbuf + (c0 >> 6) * AttSmem::P_SLAB;
-        const int cb = (c0 & 63) >> 3;
-        uint4 pa = *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb));
-        uint4 pb = *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1));
-        tc::tmem_ld_wait();
-        uint32_t pin[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w}, ds[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 p = unpack_bf16x2(pin[j]);
-          ds[j] = pack_bf16x2(p.x * (__uint_as_float(rp[2 * j]) - Di), p.y * (__uint_as_float(rp[2 * j + 1]) - Di));
-        }
-        *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
-        *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(ds[4], ds[5], ds[6], ds[7]);
-      }
-      tc::fence_before_sync();
-      tc::fence_proxy_async();
-      __syncthreads();
-      // ---- (4) dK_kt = dS^T Q_g ; (5) dQ_g = dS K
-      if (tid == 0) {
-        tc::fence_after_sync();
-        const uint32_t idesc_t = tc::make_idesc_bf16(128, 64, 1, 1);
-        for (int kt = 0; kt < NQ; ++kt)
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t a = tc::make_sdesc_sw128(sP + 2 * kt * AttSmem::P_SLAB + kk * 2048, AttSmem::P_SLAB, 1024);
-            const uint64_t b = tc::make_sdesc_sw128(sQ + g * 128 * ROWB + kk * 2048, 8192, 1024);
-            tc::mma_bf16_ss(tmem_base + COL_DK + kt * 64, a, b, idesc_t, kk > 0);
-          }
-        const uint32_t idesc_q = tc::make_idesc_bf16(128, 64, 0, 1);
-        for (int kk = 0; kk < NKP / 16; ++kk) {
-          const uint64_t a = tc::make_sdesc_sw128(sP + (kk >> 2) * AttSmem::P_SLAB + (kk & 3) * 32, 16, 1024);
-          const uint64_t b = tc::make_sdesc_sw128(sK + kk * 2048, 8192, 1024);
-          tc::mma_bf16_ss(tmem_base + COL_DQ, a, b, idesc_q, kk > 0);
-        }
-        tc::mma_commit(&bars[2]);
-      }
-      tc::mbar_wait(&bars[2], phase);
-      tc::fence_after_sync();
-      // ---- drain: dQ rows of this tile (columns split between the warpgroups), dK / dV partials into registers
-      {
-        constexpr int HW = DH / 2;                  // 16 or 32 columns per warpgroup
-        uint32_t r[32];
-        if constexpr (HW == 16) tc::tmem_ld_32x16(lane_base + COL_DQ + wg * HW, r);
-        else tc::tmem_ld_32x32(lane_base + COL_DQ + wg * HW, r);
-        tc::tmem_ld_wait();
-        if (qok) {
-          __nv_bfloat16* dq = dqkv + (size_t)(t0 + qrow) * ldq + h * DH + wg * HW;
-#pragma unroll
-          for (int j = 0; j < HW; j += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(r[j]) * scale, __uint_as_float(r[j + 1]) * scale);
-            o.y = pack_bf16x2(__uint_as_float(r[j + 2]) * scale, __uint_as_float(r[j + 3]) * scale);
-            o.z = pack_bf16x2(__uint_as_float(r[j + 4]) * scale, __uint_as_float(r[j + 5]) * scale);
-            o.w = pack_bf16x2(__uint_as_float(r[j + 6]) * scale, __uint_as_float(r[j + 7]) * scale);
-            *reinterpret_cast<uint4*>(dq + j) = o;
-          }
-        }
-        if (wg < NQ) {
-#pragma unroll
-          for (int c0 = 0; c0 < DH; c0 += 32) {
-            tc::tmem_ld_32x32(lane_base + COL_DV + wg * 64 + c0, r);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) accV[c0 + j] += __uint_as_float(r[j]);
-            tc::tmem_ld_32x32(lane_base + COL_DK + wg * 64 + c0, r);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) accK[c0 + j] += __uint_as_float(r[j]);
-          }
-        }
-      }
-      tc::fence_before_sync();
-      phase ^= 1;
-      __syncthreads();                              // TMEM and smem free for the next tile / item
-    }
-    // ---- store this thread's key row
-    const int krow = wg * 128 + row_in_tile;
-    if (krow < S) {
-      __nv_bfloat16* dk = dqkv + (size_t)(t0 + krow) * ldq + H * DH + h * DH;
-      __nv_bfloat16* dv = dk + H * DH;
-#pragma unroll
-      for (int j = 0; j < DH; j += 8) {
-        uint4 o;
-        o.x = pack_bf16x2(accK[j] * scale, accK[j + 1] * scale); o.y = pack_bf16x2(accK[j + 2] * scale, accK[j + 3] * scale);
-        o.z = pack_bf16x2(accK[j + 4] * scale, accK[j + 5] * scale); o.w = pack_bf16x2(accK[j + 6] * scale, accK[j + 7] * scale);
-        *reinterpret_cast<uint4*>(dk + j) = o;
-        o.x = pack_bf16x2(accV[j], accV[j + 1]); o.y = pack_bf16x2(accV[j + 2], accV[j + 3]);
-        o.z = pack_bf16x2(accV[j + 4], accV[j + 5]); o.w = pack_bf16x2(accV[j + 6], accV[j + 7]);
-        *reinterpret_cast<uint4*>(dv + j) = o;
-      }
-    }
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) {
-    tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-}  // namespace eavit
-
 extern "C" int eavit_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const int* seq_start, int nseq,
                                       int max_len, int H, int Dh, float scale, void* dqkv, void* stream) {
-  using namespace eavit;
   EAVIT_CHECK_ARG(qkv && dout && lse && seq_start && dqkv && nseq > 0 && H > 0);
   EAVIT_CHECK_ARG(max_len > 0 && max_len <= ATC_MAXKEYS);
   EAVIT_CHECK_ARG(Dh == 32 || (Dh == 64 && max_len <= 128));

@@ -32,21 +32,24 @@ __global__ void __launch_bounds__(128) patchify_kernel(const ImgT* __restrict__ 
                                                        float* __restrict__ dbeta) {
   extern __shared__ float tile[];     // [C][P][HW]  (+ MODE 1: [4 warps][2][PD])
   const int npr = HW / P;             // patches per row
-  const int b = blockIdx.x / npr, ph = blockIdx.x % npr;
   const int PD = C * P * P;
-  const long long src = sample_idx ? sample_idx[b] : (long long)b;
-  const ImgT* base = img + (size_t)src * C * HW * HW;
-  for (int i = threadIdx.x; i < C * P * HW; i += blockDim.x) {
-    const int c = i / (P * HW), r = (i / HW) % P, x = i % HW;
-    tile[i] = load_pixel(base + ((size_t)c * HW + ph * P + r) * HW + x);
-  }
-  __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float ag[PATCH_MAXV], ab[PATCH_MAXV];
   if (MODE == 1) {
 #pragma unroll
     for (int i = 0; i < PATCH_MAXV; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
   }
+  // persistent over (sample, patch-row) items: the MODE 1 atomics are paid once per CTA
+  for (int item = blockIdx.x; item < B * npr; item += gridDim.x) {
+  const int b = item / npr, ph = item % npr;
+  const long long src = sample_idx ? sample_idx[b] : (long long)b;
+  const ImgT* base = img + (size_t)src * C * HW * HW;
+  __syncthreads();                    // previous item's tile fully consumed
+  for (int i = threadIdx.x; i < C * P * HW; i += blockDim.x) {
+    const int c = i / (P * HW), r = (i / HW) % P, x = i % HW;
+    tile[i] = load_pixel(base + ((size_t)c * HW + ph * P + r) * HW + x);
+  }
+  __syncthreads();
   for (int pw = w; pw < npr; pw += 4) {
     const size_t row = (size_t)b * npr * npr + (size_t)ph * npr + pw;
     float v[PATCH_MAXV];
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(128) patchify_kernel(const ImgT* __restrict__ 
         }
       }
     }
+  }
   }
   if (MODE == 1) {
     float* part = tile + C * P * HW;    // [4][2][PD]
@@ -240,7 +244,9 @@ static int patchify_common(int mode, const void* img, int img_dtype, const long 
   const int npr = HW / P;
   size_t smem = (size_t)C * P * HW * sizeof(float) + (mode == 1 ? (size_t)4 * 2 * PD * sizeof(float) : 0);
   EAVIT_CHECK_ARG(smem <= 48 * 1024);
-  dim3 grid(B * npr);
+  int nblk = B * npr;
+  if (nblk > 16 * kNumSMs) nblk = 16 * kNumSMs;
+  dim3 grid(nblk);
   if (img_dtype == EAVIT_U8) {
     if (mode == 0) patchify_kernel<uint8_t, 0><<<grid, 128, smem, st>>>((const uint8_t*)img, sample_idx, B, C, HW, P, order_cpp, gamma, beta, eps, (__nv_bfloat16*)out, mean, rstd, dpln, dgamma, dbeta);
     else           patchify_kernel<uint8_t, 1><<<grid, 128, smem, st>>>((const uint8_t*)img, sample_idx, B, C, HW, P, order_cpp, gamma, beta, eps, (__nv_bfloat16*)out, mean, rstd, dpln, dgamma, dbeta);

@@ -74,13 +74,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restric
                                                             float* __restrict__ dx, long long lddx,
                                                             __nv_bfloat16* __restrict__ dx_bf16, long long lddxb,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            int T, int D) {
-  extern __shared__ float s_part[];   // [8 warps][2][D]
+                                                            float* __restrict__ dxsum, int T, int D) {
+  extern __shared__ float s_part[];   // [8 warps][3][D]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / 4;
-  float4 ag[VPL], ab[VPL];
+  float4 ag[VPL], ab[VPL], ax[VPL];   // dgamma, dbeta, column sums of the output dx (bias gradient of the next GEMM)
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = ag[i]; }
+  for (int i = 0; i < VPL; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = ag[i]; ax[i] = ag[i]; }
   // persistent grid-stride over rows: the dgamma/dbeta atomics are paid once per CTA, not once per 64 rows
   for (int row = blockIdx.x * 8 + w; row < T; row += gridDim.x * 8) {
     const float mu = mean[row], rs = rstd[row];
@@ -120,30 +120,35 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restric
           const float4 r = __ldg(reinterpret_cast<const float4*>(dres + (size_t)row * lddres) + c);
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
+        ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
         if (dx != nullptr) *(reinterpret_cast<float4*>(dx + (size_t)row * lddx) + c) = o;
         if (dx_bf16 != nullptr)
           *(reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * lddxb) + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
     }
   }
-  if (dgamma == nullptr) return;
-  float* pg = s_part + (size_t)w * 2 * D;
+  if (dgamma == nullptr && dxsum == nullptr) return;
+  float* pg = s_part + (size_t)w * 3 * D;
   float* pb = pg + D;
+  float* px = pb + D;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
     if (c < nv) {
       *(reinterpret_cast<float4*>(pg) + c) = ag[i];
       *(reinterpret_cast<float4*>(pb) + c) = ab[i];
+      *(reinterpret_cast<float4*>(px) + c) = ax[i];
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float sg = 0.f, sb = 0.f;
+    float sg = 0.f, sb = 0.f, sx = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { sg += s_part[(size_t)k * 2 * D + c]; sb += s_part[(size_t)k * 2 * D + D + c]; }
-    atomicAdd(dgamma + c, sg);
-    atomicAdd(dbeta + c, sb);
+    for (int k = 0; k < 8; ++k) {
+      sg += s_part[(size_t)k * 3 * D + c]; sb += s_part[(size_t)k * 3 * D + D + c]; sx += s_part[(size_t)k * 3 * D + 2 * D + c];
+    }
+    if (dgamma != nullptr) { atomicAdd(dgamma + c, sg); atomicAdd(dbeta + c, sb); }
+    if (dxsum != nullptr) atomicAdd(dxsum + c, sx);
   }
 }
 
@@ -236,23 +241,23 @@ int eavit_layernorm_fwd(const float* x, long long ldx, const float* gamma, const
 
 int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const float* x, long long ldx, const float* mean,
                         const float* rstd, const float* gamma, const float* dres, long long lddres, float* dx,
-                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, int T, int D,
-                        void* stream) {
+                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, float* dxsum, int T,
+                        int D, void* stream) {
   EAVIT_CHECK_ARG(T > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXV && dy && x && mean && rstd && gamma);
   EAVIT_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr));
   EAVIT_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && lddres % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
+  const size_t smem = (size_t)8 * 3 * D * sizeof(float);
   int grid = cdiv(T, 8);
   if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
   const int vpl = cdiv(D / 4, 32);
   static bool attr_done = false;
   if (!attr_done) {
-    EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
-    EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
     attr_done = true;
   }
-#define EAVIT_LN_BWD(DT, V) layernorm_bwd_kernel<DT, V><<<grid, 256, smem, st>>>((const DT*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, T, D)
+#define EAVIT_LN_BWD(DT, V) layernorm_bwd_kernel<DT, V><<<grid, 256, smem, st>>>((const DT*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, dxsum, T, D)
 #define EAVIT_LN_BWD_V(DT) do { if (vpl <= 1) EAVIT_LN_BWD(DT, 1); else if (vpl <= 2) EAVIT_LN_BWD(DT, 2); else if (vpl <= 4) EAVIT_LN_BWD(DT, 4); else EAVIT_LN_BWD(DT, 8); } while (0)
   if (dy_dtype == EAVIT_F32) EAVIT_LN_BWD_V(float);
   else if (dy_dtype == EAVIT_BF16) EAVIT_LN_BWD_V(__nv_bfloat16);

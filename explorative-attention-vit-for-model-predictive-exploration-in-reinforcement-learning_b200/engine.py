@@ -122,8 +122,9 @@ class _Buffers:
 
 
 def _split_k(M: int, N: int, K: int) -> int:
+    # tiles * splits <= 148: one wave of the persistent grid (149 work items would cost a whole second wave)
     tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
-    s = max(1, (148 + tiles - 1) // tiles)
+    s = max(1, 148 // tiles)
     return max(1, min(s, (K + 63) // 64))
 
 
@@ -293,12 +294,14 @@ class ViTEncoder:
         fn = (p + "transformer.norm.") if c.impl == "lucidrains" else (p + "layernorm.")
         dpool = bf.get("dpool", (nf, D), torch.float32)
         call("eavit_layernorm_bwd", dfeat, F32, D, bf.t["pooled"], D, bf.t["mf"], bf.t["rf"], s.w(fn + "weight"),
-             None, D, dpool, D, None, D, s.g(fn + "weight"), s.g(fn + "bias"), nf, D)
+             None, D, dpool, D, None, D, s.g(fn + "weight"), s.g(fn + "bias"), None, nf, D)
         dxa = bf.get("dxa", (T, D), torch.float32)
         dxb = bf.get("dxb", (T, D), torch.float32)
         dx16 = bf.get("dx16", (T, D), torch.bfloat16)
         call("eavit_zero", dxa, T * D * 4)
         call("eavit_zero", dx16, T * D * 2)
+        # bias gradient of the last layer's MLP2 = column sums of the (sparse) top gradient = column sums of dpool
+        call("eavit_colsum", dpool, F32, D, s.g(self.L[-1]["b2"]), nf, D)
         if self.mode == 1:
             dsum = bf.get("dpool_sum", (B, D), torch.float32)
             call("eavit_add_f32", dpool[:B], dpool[B:], dsum, B * D)
@@ -307,27 +310,28 @@ class ViTEncoder:
             call("eavit_scatter_rows", dpool, D, bf.pool_rows, dxa, D, dx16, D, nf, D)
         dx, dx_other = dxa, dxb
         dh = bf.get("dh", (T, c.mlp_dim), torch.bfloat16)
-        dxn = bf.get("dxn", (T, D), torch.float32)
+        dxn = bf.get("dxn", (T, D), torch.bfloat16)     # LN-backward input (a GEMM output): bf16 halves its traffic
         do = bf.get("do", (T, I), torch.bfloat16)
         dqkv = bf.get("dqkv", (T, 3 * I), torch.bfloat16)
         for li in reversed(range(c.depth)):
             L = self.L[li]
             x_in = bf.t["x0"] if li == 0 else bf.t[f"x_{li}"]
             # MLP2: x_out = xmid + hact W2^T + b2
-            linear_bwd(dx16, bf.t[f"hact_{li}"], s.b16(L["w2"]), dW=s.g(L["w2"]), db=s.g(L["b2"]), dx_bf16=dh,
-                       act=ops.ACT_GELU_BWD, aux=bf.t[f"hpre_{li}"])
+            linear_bwd(dx16, bf.t[f"hact_{li}"], s.b16(L["w2"]), dW=s.g(L["w2"]), db=None, dx_bf16=dh,
+                       act=ops.ACT_GELU_BWD, aux=bf.t[f"hpre_{li}"])      # db2 comes from the producer of dx (LN-bwd / top)
             # MLP1: hpre = xn2 W1^T + b1
-            linear_bwd(dh, bf.t[f"xn2_{li}"], s.b16(L["w1"]), dW=s.g(L["w1"]), db=s.g(L["b1"]), dx_f32=dxn)
-            call("eavit_layernorm_bwd", dxn, F32, D, bf.t[f"xmid_{li}"], D, bf.t[f"m2_{li}"], bf.t[f"r2_{li}"],
-                 s.w(L["ln2"][0]), dx, D, dx_other, D, dx16, D, s.g(L["ln2"][0]), s.g(L["ln2"][1]), T, D)
+            linear_bwd(dh, bf.t[f"xn2_{li}"], s.b16(L["w1"]), dW=s.g(L["w1"]), db=s.g(L["b1"]), dx_bf16=dxn)
+            call("eavit_layernorm_bwd", dxn, BF16, D, bf.t[f"xmid_{li}"], D, bf.t[f"m2_{li}"], bf.t[f"r2_{li}"],
+                 s.w(L["ln2"][0]), dx, D, dx_other, D, dx16, D, s.g(L["ln2"][0]), s.g(L["ln2"][1]), s.g(L["o_b"]), T, D)
             dx, dx_other = dx_other, dx
             # out-proj: xmid = x + o Wo^T + bo
-            linear_bwd(dx16, bf.t[f"o_{li}"], s.b16(L["o_w"]), dW=s.g(L["o_w"]), db=s.g(L["o_b"]), dx_bf16=do)
+            linear_bwd(dx16, bf.t[f"o_{li}"], s.b16(L["o_w"]), dW=s.g(L["o_w"]), db=None, dx_bf16=do)
             ops.attention_bwd(bf.t[f"qkv_{li}"], bf.t[f"o_{li}"], do, bf.t[f"lse_{li}"], bf.seq_start, bf.nseq,
                               bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, dqkv)
-            linear_bwd(dqkv, bf.t[f"xn1_{li}"], self._qkv(L, "w16"), dW=self._qkv(L, "gw"), db=self._qkv(L, "gb"), dx_f32=dxn)
-            call("eavit_layernorm_bwd", dxn, F32, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
-                 dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), T, D)
+            linear_bwd(dqkv, bf.t[f"xn1_{li}"], self._qkv(L, "w16"), dW=self._qkv(L, "gw"), db=self._qkv(L, "gb"), dx_bf16=dxn)
+            db2_prev = s.g(self.L[li - 1]["b2"]) if li > 0 else None      # dx of this LN is the output gradient of layer li-1's MLP2
+            call("eavit_layernorm_bwd", dxn, BF16, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
+                 dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, T, D)
             dx, dx_other = dx_other, dx
         # embedding
         rows = B * np_
@@ -339,7 +343,7 @@ class ViTEncoder:
             call("eavit_embed_assemble_bwd", dx, self.mode, B, np_, D, g, None, s.g(p + "pos_embedding"), s.g(tok), None)
             de16 = bf.get("de16", (rows, D), torch.bfloat16)
             call("eavit_layernorm_bwd", g, F32, D, bf.t["e0"], D, bf.t["m3"], bf.t["r3"], s.w(p + "to_patch_embedding.3.weight"),
-                 None, D, None, D, de16, D, s.g(p + "to_patch_embedding.3.weight"), s.g(p + "to_patch_embedding.3.bias"), rows, D)
+                 None, D, None, D, de16, D, s.g(p + "to_patch_embedding.3.weight"), s.g(p + "to_patch_embedding.3.bias"), None, rows, D)
             dpln = bf.get("dpln", (rows, PD), torch.float32)
             linear_bwd(de16, bf.t["pln"], s.b16(p + "to_patch_embedding.2.weight"), dW=s.g(p + "to_patch_embedding.2.weight"),
                        db=s.g(p + "to_patch_embedding.2.bias"), dx_f32=dpln)

@@ -212,7 +212,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 # d = double.  The trailing `void* stream` of every entry point is appended automatically.
 _SPECS = {
     "eavit_layernorm_fwd": "plpppilppiif",
-    "eavit_layernorm_bwd": "pilplppppl" "pl" "pl" "ppii",
+    "eavit_layernorm_bwd": "pilplppppl" "pl" "pl" "pppii",
     "eavit_colsum": "pilpii",
     "eavit_gather_rows": "plpplii",
     "eavit_scatter_rows": "plppl" "pl" "ii",

@@ -131,11 +131,12 @@ int eavit_gemm_bf16(const eavit_gemm_args* args, void* stream);
 int eavit_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, int y_dtype,
                         long long ldy, float* mean, float* rstd, int T, int D, float eps, void* stream);
 /* dx = dres + LN'(dy); dgamma/dbeta accumulated with atomics (+=).  dy dtype F32 or BF16; dres, dx,
- * dx_bf16, dgamma/dbeta optional. */
+ * dx_bf16, dgamma/dbeta optional.  dxsum (optional) += column sums of dx = the bias gradient of the Linear whose
+ * output fed this residual stream (saves a separate pass over [T,D]). */
 int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const float* x, long long ldx, const float* mean,
                         const float* rstd, const float* gamma, const float* dres, long long lddres, float* dx,
-                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, int T, int D,
-                        void* stream);
+                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, float* dxsum, int T,
+                        int D, void* stream);
 /* out[c] += sum_r x[r,c]  (bias gradients); x dtype BF16 or F32. */
 int eavit_colsum(const void* x, int x_dtype, long long ldx, float* out, int T, int N, void* stream);
 /* dst[i,:] = src[rows[i],:]  /  dst[rows[i],:] = src[i,:]  (pooled token x[:,0], vit.py:162). */
