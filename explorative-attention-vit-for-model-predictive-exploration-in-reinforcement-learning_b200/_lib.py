@@ -24,6 +24,7 @@ class GemmArgs(ctypes.Structure):
         ("B", ctypes.c_void_p), ("ldb", ctypes.c_longlong), ("b_mn", ctypes.c_int),
         ("bias", ctypes.c_void_p), ("aux_bf16", ctypes.c_void_p), ("residual", ctypes.c_void_p),
         ("out_f32", ctypes.c_void_p), ("out_bf16", ctypes.c_void_p), ("out_pre_bf16", ctypes.c_void_p),
+        ("colsum", ctypes.c_void_p),
         ("ldc", ctypes.c_longlong), ("act", ctypes.c_int), ("atomic_f32", ctypes.c_int), ("split_k", ctypes.c_int),
     ]
 

@@ -2,11 +2,13 @@
 //
 //   C[M,N] = epilogue( A . B^T )      A: [M,K] (K-major) or [K,M] (MN-major),  B: [N,K] or [K,N]
 //
-// One CTA per SM, 256 threads:
+// One CTA per SM, 576 threads:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, STAGES-deep mbarrier ring)
-//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers)
-//   warp 2      TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4-7   epilogue       (tcgen05.ld -> bias / activation / residual -> 16-byte global stores)
+//   warp 1      TMEM allocator (2 accumulator stages x BN columns) + MMA issuer (one lane issues tcgen05.mma
+//               128 x BN x 16 and commits to mbarriers)
+//   warps 2-17  epilogue       (tcgen05.ld -> bias / activation / residual -> 16-byte global stores); four warps per
+//               TMEM lane quadrant: at K = 256 the fused epilogues (GELU, GELU', residual) are 2-3x longer than the
+//               mainloop and latency-bound, so they need >= 4 warps per scheduler to keep the issue slots busy
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile
 // i+1 -- at K = 256 (the ViT width) the epilogue is as long as the mainloop, so this overlap is what
 // keeps the tensor pipe busy.  Tiles are scheduled n-fastest so CTAs that share an A row-block run
@@ -23,8 +25,8 @@ namespace eavit {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 384;          // 4 control warps + 8 epilogue warps
-constexpr int EPI_WARPS = 8;
+constexpr int CTRL_WARPS = 2;
+constexpr int MAX_EPI_WARPS = 16;
 constexpr int EPI_TILE_FLOATS = 32 * 32;   // 32x32 transpose tile per epilogue warp (16-byte chunks XOR-swizzled)
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
@@ -38,6 +40,7 @@ struct GemmKernelParams {
   float* out_f32;
   __nv_bfloat16* out_bf16;
   __nv_bfloat16* out_pre;
+  float* colsum;
   long long ldc;
   int act;
   int atomic_f32;
@@ -47,9 +50,9 @@ template <int BN>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
   static constexpr int TMEM_COLS = 2 * BN;    // power of two >= 32 for BN in {64,128,256}
-  static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILE_FLOATS * 4;
+  static constexpr int EPI_BYTES = MAX_EPI_WARPS * EPI_TILE_FLOATS * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -68,13 +71,17 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
 // Epilogue specialisations (compile-time): the epilogue is instruction-issue bound (ncu: 45 % issue-active from only 8
 // warps), so the common fused forms drop every per-element runtime branch of the generic path.
 enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5 };
+// The GELU epilogues are issue/latency-bound (16 instructions + 2 MUFU per element): 16 warps.  The store / residual /
+// atomic epilogues are HBM-bound and want registers for loads in flight instead: 8 warps.
+template <int EPI> struct EpiWarps { static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_BWD) ? 16 : 8; };
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((CTRL_WARPS + EpiWarps<EPI>::N) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int EPI_WARPS = EpiWarps<EPI>::N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -97,7 +104,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], EPI_WARPS); }
     tc::fence_barrier_init();
   }
-  if (warp == 2) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -169,14 +176,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ===================================== epilogue =====================================
-    // Two warps per TMEM lane quadrant (they alternate 32-column chunks).  Each chunk is transposed through a padded
+    // Four warps per TMEM lane quadrant (they interleave 32-column chunks).  Each chunk is transposed through a padded
     // shared-memory tile so that global loads / stores are row-contiguous (a warp touches 128 B of ONE row per
     // instruction instead of 32 rows x 16 B).
-    const int e = warp - 4;
-    const int q = e & 3;                              // TMEM lane quadrant owned by this warp
-    const int par = e >> 2;                           // chunk parity handled by this warp
+    const int e = warp - CTRL_WARPS;
+    const int q = warp & 3;                           // TMEM lane quadrant this warp may read (hardware: warp id % 4)
+    const int par = e >> 2;                           // first 32-column chunk handled by this warp
     float* tile = epi_smem + e * EPI_TILE_FLOATS;
     constexpr bool GEN = EPI == E_GENERIC;
     const bool need_aux = GEN ? (p.act == EAVIT_ACT_GELU_BWD || p.act == EAVIT_ACT_LRELU_BWD || p.act == EAVIT_ACT_RELU_BWD) : (EPI == E_GELU_BWD);
@@ -194,7 +201,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int row0 = m_blk * BM + q * 32;
       const int nrows = min(32, p.M - row0);          // may be <= 0 for the M tail
 #pragma unroll 1
-      for (int c = par; c < BN / 32; c += 2) {
+      for (int c = par; c < BN / 32; c += EPI_WARPS / 4) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;                        // warp-uniform
         uint32_t r[32];
@@ -207,6 +214,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         __syncwarp();
         const int cchunk = lane & 7, rsub = lane >> 3;
         const int col = col0 + cchunk * 4;
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};              // column sums of the stored values (bias gradient)
         if (col < p.N) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
@@ -255,6 +263,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
               }
               if (has_res) { v[0] += res[it].x; v[1] += res[it].y; v[2] += res[it].z; v[3] += res[it].w; }
+              cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
               if (out_f32) {
                 if (atomic) {
 #pragma unroll
@@ -268,6 +277,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
           }
         }
+        if (p.colsum != nullptr) {                         // warp-uniform
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+            cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+          }
+          if (rsub == 0 && col < p.N) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
+          }
+        }
         __syncwarp();
       }
       tc::fence_before_sync();
@@ -279,7 +299,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -361,12 +381,13 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   p.out_f32 = a->out_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.out_pre = reinterpret_cast<__nv_bfloat16*>(a->out_pre_bf16);
+  p.colsum = a->colsum;
   p.ldc = a->ldc;
   p.act = a->act;
   p.atomic_f32 = a->atomic_f32;
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, (CTRL_WARPS + EpiWarps<EPI>::N) * 32, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -384,7 +405,8 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0);
   EAVIT_CHECK_ARG(a->out_f32 != nullptr || a->out_bf16 != nullptr || a->out_pre_bf16 != nullptr);
   EAVIT_CHECK_ARG(a->split_k <= 1 || (a->atomic_f32 && a->out_f32 != nullptr && a->out_bf16 == nullptr &&
-                                      a->out_pre_bf16 == nullptr && a->act == EAVIT_ACT_NONE && a->residual == nullptr));
+                                      a->out_pre_bf16 == nullptr && a->act == EAVIT_ACT_NONE && a->residual == nullptr &&
+                                      a->colsum == nullptr));
   const bool need_aux = (a->act == EAVIT_ACT_GELU_BWD || a->act == EAVIT_ACT_LRELU_BWD || a->act == EAVIT_ACT_RELU_BWD);
   EAVIT_CHECK_ARG(!need_aux || a->aux_bf16 != nullptr);
   EAVIT_CHECK_ARG(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);

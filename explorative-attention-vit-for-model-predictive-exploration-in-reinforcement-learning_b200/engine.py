@@ -133,14 +133,15 @@ def linear_fwd(x16, w16, *, bias=None, act=ops.ACT_NONE, residual=None, out_f32=
     ops.gemm(x16, w16, bias=bias, act=act, residual=residual, out_f32=out_f32, out_bf16=out_bf16, out_pre=out_pre)
 
 
-def linear_bwd(dy16, x16, w16, *, dW, db=None, dx_f32=None, dx_bf16=None, act=ops.ACT_NONE, aux=None):
-    """dW += dy^T x (split-K, MN-major operands), db += colsum(dy), dx = act'(dy W)."""
+def linear_bwd(dy16, x16, w16, *, dW, db=None, dx_f32=None, dx_bf16=None, act=ops.ACT_NONE, aux=None, dx_colsum=None):
+    """dW += dy^T x (split-K, MN-major operands), db += colsum(dy), dx = act'(dy W); dx_colsum += colsum(dx) fused in
+    the dX epilogue (= the bias gradient of the layer below, whose output gradient dx is)."""
     M, K = dW.shape
     ops.gemm(dy16, x16, a_mn=True, b_mn=True, out_f32=dW, atomic=True, split_k=_split_k(M, K, dy16.shape[0]))
     if db is not None:
         call("eavit_colsum", dy16, BF16, dy16.stride(0), db, dy16.shape[0], dy16.shape[1])
     if dx_f32 is not None or dx_bf16 is not None:
-        ops.gemm(dy16, w16, b_mn=True, act=act, aux=aux, out_f32=dx_f32, out_bf16=dx_bf16)
+        ops.gemm(dy16, w16, b_mn=True, act=act, aux=aux, out_f32=dx_f32, out_bf16=dx_bf16, colsum=dx_colsum)
 
 
 class ViTEncoder:
@@ -317,10 +318,11 @@ class ViTEncoder:
             L = self.L[li]
             x_in = bf.t["x0"] if li == 0 else bf.t[f"x_{li}"]
             # MLP2: x_out = xmid + hact W2^T + b2
+            # (db2 comes from the producer of dx: LN-bwd / top; db1 = colsum(dh) from this GEMM's epilogue)
             linear_bwd(dx16, bf.t[f"hact_{li}"], s.b16(L["w2"]), dW=s.g(L["w2"]), db=None, dx_bf16=dh,
-                       act=ops.ACT_GELU_BWD, aux=bf.t[f"hpre_{li}"])      # db2 comes from the producer of dx (LN-bwd / top)
+                       act=ops.ACT_GELU_BWD, aux=bf.t[f"hpre_{li}"], dx_colsum=s.g(L["b1"]))
             # MLP1: hpre = xn2 W1^T + b1
-            linear_bwd(dh, bf.t[f"xn2_{li}"], s.b16(L["w1"]), dW=s.g(L["w1"]), db=s.g(L["b1"]), dx_bf16=dxn)
+            linear_bwd(dh, bf.t[f"xn2_{li}"], s.b16(L["w1"]), dW=s.g(L["w1"]), db=None, dx_bf16=dxn)
             call("eavit_layernorm_bwd", dxn, BF16, D, bf.t[f"xmid_{li}"], D, bf.t[f"m2_{li}"], bf.t[f"r2_{li}"],
                  s.w(L["ln2"][0]), dx, D, dx_other, D, dx16, D, s.g(L["ln2"][0]), s.g(L["ln2"][1]), s.g(L["o_b"]), T, D)
             dx, dx_other = dx_other, dx
@@ -343,10 +345,11 @@ class ViTEncoder:
             call("eavit_embed_assemble_bwd", dx, self.mode, B, np_, D, g, None, s.g(p + "pos_embedding"), s.g(tok), None)
             de16 = bf.get("de16", (rows, D), torch.bfloat16)
             call("eavit_layernorm_bwd", g, F32, D, bf.t["e0"], D, bf.t["m3"], bf.t["r3"], s.w(p + "to_patch_embedding.3.weight"),
-                 None, D, None, D, de16, D, s.g(p + "to_patch_embedding.3.weight"), s.g(p + "to_patch_embedding.3.bias"), None, rows, D)
+                 None, D, None, D, de16, D, s.g(p + "to_patch_embedding.3.weight"), s.g(p + "to_patch_embedding.3.bias"),
+                 s.g(p + "to_patch_embedding.2.bias"), rows, D)
             dpln = bf.get("dpln", (rows, PD), torch.float32)
             linear_bwd(de16, bf.t["pln"], s.b16(p + "to_patch_embedding.2.weight"), dW=s.g(p + "to_patch_embedding.2.weight"),
-                       db=s.g(p + "to_patch_embedding.2.bias"), dx_f32=dpln)
+                       db=None, dx_f32=dpln)
             call("eavit_patchify_ln_bwd", img, img_dt, sidx, B, c.channels, c.image, c.patch, 0,
                  s.w(p + "to_patch_embedding.1.weight"), bf.t["pmean"], bf.t["prstd"], dpln,
                  s.g(p + "to_patch_embedding.1.weight"), s.g(p + "to_patch_embedding.1.bias"))

@@ -175,7 +175,8 @@ def intrinsic_mse(target, predict):
 
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias=None, act: int = ACT_NONE,
-         aux=None, residual=None, out_f32=None, out_bf16=None, out_pre=None, atomic: bool = False, split_k: int = 1):
+         aux=None, residual=None, out_f32=None, out_bf16=None, out_pre=None, colsum=None, atomic: bool = False,
+         split_k: int = 1):
     """C = epilogue(A . B^T) on tcgen05 (see include/eavit_b200.h: eavit_gemm_bf16).
 
     a_mn: A passed as the stored [K, M] matrix; b_mn: B passed as the stored [K, N] matrix.
@@ -198,6 +199,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                  out_f32=None if out_f32 is None else out_f32.data_ptr(),
                  out_bf16=None if out_bf16 is None else out_bf16.data_ptr(),
                  out_pre_bf16=None if out_pre is None else out_pre.data_ptr(),
+                 colsum=None if colsum is None else colsum.data_ptr(),
                  ldc=ldc, act=act, atomic_f32=int(atomic), split_k=split_k)
     if _PROF is not None:
         with _Timed(f"gemm_bf16_tcgen05 M={M} N={N} K={K} {'mn' if a_mn else 'k'}{'mn' if b_mn else 'k'} act={act}"

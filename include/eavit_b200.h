@@ -117,6 +117,7 @@ typedef struct {
   float* out_f32;
   void* out_bf16;
   void* out_pre_bf16;
+  float* colsum;       /* optional [N]: colsum[n] += sum_m (final v) -- the bias gradient when this GEMM produces dY */
   long long ldc;
   int act;
   int atomic_f32;

@@ -105,6 +105,27 @@ def test_gemm_epilogues(ops):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("M,N,K", [(500, 1024, 256), (333, 144, 256), (4100, 256, 1024)])
+def test_gemm_fused_column_sums(ops, M, N, K):
+    """colsum[n] += sum_m of the stored values (bias gradient fused into the dX epilogue); accumulates across calls."""
+    torch.manual_seed(4)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") / 16).bfloat16()
+    aux = torch.randn(M, N, device="cuda").bfloat16()
+    x = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    ref = (A.float() @ B.float().t()) * x.grad
+    out16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cs = torch.zeros(N, device="cuda")
+    ops.gemm(A, B, act=ops.ACT_GELU_BWD, aux=aux, out_bf16=out16, colsum=cs)
+    assert rel_err(out16, ref) < 5e-3
+    assert rel_err(cs, ref.sum(0)) < 2e-3, rel_err(cs, ref.sum(0))
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, out_f32=out, colsum=cs)                    # generic epilogue, accumulates on top
+    assert rel_err(cs, ref.sum(0) + (A.float() @ B.float().t()).sum(0)) < 2e-3
+    torch.cuda.synchronize()
+
+
 def test_gemm_rejects_bad_arguments(ops):
     A = torch.randn(64, 60, device="cuda").bfloat16()     # pitch 120 B, not 16-byte aligned
     B = torch.randn(64, 60, device="cuda").bfloat16()
