@@ -27,34 +27,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Cooperative staging of rows [0,S) x DH of NMAT matrices into swizzled smem, split into an asynchronous half (global
-// loads into registers, issued one item AHEAD so that their latency overlaps the previous item's compute -- the kernels
-// run one item per SM at a time and were bound by this serial load -> MMA -> softmax chain) and a commit half.
-template <int DH, int NMAT, int NPF>
-struct RowStager {
-  uint4 v[NPF];
-  uint32_t dst[NPF];
-  __device__ __forceinline__ void load(const int* offs, const __nv_bfloat16* const* srcs, const int* lds, int S, int tid) {
-    constexpr int CH = DH / 8;
-    const int total = S * CH * NMAT;
-#pragma unroll
-    for (int u = 0; u < NPF; ++u) {
-      const int i = tid + u * ATC_THREADS;
-      dst[u] = 0xffffffffu;
-      if (i < total) {
-        const int which = i / (S * CH), rem = i % (S * CH);
-        const int r = rem / CH, c = rem % CH;
-        v[u] = __ldg(reinterpret_cast<const uint4*>(srcs[which] + (size_t)r * lds[which]) + c);
-        dst[u] = offs[which] + sw_off(r, c);
-      }
-    }
-  }
-  __device__ __forceinline__ void commit(uint8_t* smem) {
-#pragma unroll
-    for (int u = 0; u < NPF; ++u)
-      if (dst[u] != 0xffffffffu) *reinterpret_cast<uint4*>(smem + dst[u]) = v[u];
-  }
-};
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer);
+
+// Operand staging: one elected thread issues TMA box loads (64 bf16 = 128 bytes x 32 rows, 128-byte swizzle) of the item's
+// Q / K / V (/ dO) rows straight out of the [T, 3*H*Dh] activation matrix.  A 128-byte box row holds 64 / Dh heads, so a
+// work item is (sequence, head group): with Dh = 32 two heads share one staged tile and are processed back to back (the
+// second head is the +64-byte K-slice / N-slice of the same swizzled rows).  Rows past the end of the sequence inside the
+// last 32-row box belong to the next sequence (or are zero-filled past T): finite values whose score columns are masked.
+constexpr int BOX_ROWS = 32;
+constexpr int BOX_BYTES = BOX_ROWS * ROWB;
 
 struct AttSmem {
   static constexpr int OFF_Q = 0;                                // [256][128 B]
@@ -68,15 +49,17 @@ struct AttSmem {
 
 template <int DH>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ seq_start, int nseq, int H,
+attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ seq_start, int nseq, int H,
                         float scale, __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+  constexpr int HPB = 64 / DH;                      // heads per 128-byte box row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sMax = reinterpret_cast<float*>(smem + AttSmem::OFF_X);      // [2][256]
   float* sSum = sMax + 512;                                            // [2][256]
   uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + AttSmem::OFF_BAR);
   uint64_t* bar_o = bar_s + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 4);
+  uint64_t* bar_ld = bar_s + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, grp = warp >> 2;   // 4 groups of 4 warps
   const int g = grp & 1;                        // query tile
@@ -86,155 +69,174 @@ attention_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __rest
 
   for (int i = tid; i < AttSmem::OFF_X / 16; i += ATC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
+    tc::prefetch_tmap(&tmQKV);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bar_s[i], 1); tc::mbar_init(&bar_o[i], 1); }
+    tc::mbar_init(bar_ld, 1);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_proxy_async();                       // the zero fill above (generic proxy) precedes TMA writes to the same bytes
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int ldq = 3 * H * DH, ldo = H * DH;
+  const int ldo = H * DH;
+  const int HG = H / HPB;
   const float c2 = scale * 1.4426950408889634f;      // exp(x*scale) = exp2(x*c2)
-  uint32_t phase = 0;
-  const int n_items = nseq * H;
-  constexpr int NPF = (ATC_MAXKEYS * (DH / 8) * 3 + ATC_THREADS - 1) / ATC_THREADS;
-  RowStager<DH, 3, NPF> stager;
-  auto prefetch = [&](int it) {
-    const int sq = it / H, hh = it % H;
+  uint32_t ph0 = 0, ph1 = 0, ph_ld = 0;              // parities of bar_*[0], bar_*[1], bar_ld (uniform across the CTA)
+  const int n_items = nseq * HG;
+  auto issue_loads = [&](int it) {                   // one thread
+    const int sq = it / HG, hg = it - sq * HG;
     const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
-    const __nv_bfloat16* base = qkv + (size_t)tt * ldq + hh * DH;
-    const __nv_bfloat16* srcs[3] = {base, base + H * DH, base + 2 * H * DH};
+    const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
+    tc::mbar_expect_tx(bar_ld, 3 * nb * BOX_BYTES);
     const int offs[3] = {AttSmem::OFF_Q, AttSmem::OFF_K, AttSmem::OFF_V};
-    const int lds[3] = {ldq, ldq, ldq};
-    stager.load(offs, srcs, lds, SS, tid);
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      for (int b = 0; b < nb; ++b)
+        tc::tma_load_2d(smem + offs[m] + b * BOX_BYTES, &tmQKV, bar_ld, m * H * DH + hg * 64, tt + b * BOX_ROWS);
   };
-  if ((int)blockIdx.x < n_items) prefetch(blockIdx.x);
+  if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int seq = item / H, h = item % H;
+    const int seq = item / HG, hg = item - seq * HG;
     const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
     const int NKT = (S + 31) & ~31;                  // score columns
     const int NKP = (S + 15) & ~15;                  // keys covered by the P.V MMA
-    stager.commit(smem);
-    tc::fence_proxy_async();
-    __syncthreads();
-    if (item + (int)gridDim.x < n_items) prefetch(item + gridDim.x);     // lands during this item's compute
+    const bool two_tiles = S > 128;
+    tc::mbar_wait(bar_ld, ph_ld);
+    ph_ld ^= 1;
     const bool active = g * 128 < S;
-    if (active) {
-      const uint32_t s_col = tmem_base + (uint32_t)(g * ATC_MAXKEYS);
-      const bool issuer = (hf == 0 && quad == 0 && lane == 0);
-      if (issuer) {
+#pragma unroll 1
+    for (int hd = 0; hd < HPB; ++hd) {
+      const int h = hg * HPB + hd;
+      const uint32_t hoff = (uint32_t)(hd * DH * 2);   // byte offset of this head inside the 128-byte rows
+      if (active) {
+        const uint32_t phase = g ? ph1 : ph0;
+        const uint32_t s_col = tmem_base + (uint32_t)(g * ATC_MAXKEYS);
+        const bool issuer = (hf == 0 && quad == 0 && lane == 0);
+        if (issuer) {
+          tc::fence_after_sync();
+          const uint32_t idesc = tc::make_idesc_bf16(128, NKT, 0, 0);
+          const uint32_t qa = tc::smem_u32(smem + AttSmem::OFF_Q + g * 128 * ROWB) + hoff;
+          const uint32_t ka = tc::smem_u32(smem + AttSmem::OFF_K) + hoff;
+          const uint64_t adesc = tc::make_sdesc_sw128(qa, 16, 1024), bdesc = tc::make_sdesc_sw128(ka, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(s_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k > 0);
+          tc::mma_commit(&bar_s[g]);
+        }
+        tc::mbar_wait(&bar_s[g], phase);
         tc::fence_after_sync();
-        const uint32_t idesc = tc::make_idesc_bf16(128, NKT, 0, 0);
-        const uint32_t qa = tc::smem_u32(smem + AttSmem::OFF_Q + g * 128 * ROWB);
-        const uint32_t ka = tc::smem_u32(smem + AttSmem::OFF_K);
-        const uint64_t adesc = tc::make_sdesc_sw128(qa, 16, 1024), bdesc = tc::make_sdesc_sw128(ka, 16, 1024);
+        const uint32_t lane_addr = s_col + ((uint32_t)(quad * 32) << 16);
+        const int half = NKT >> 1, cbeg = hf * half;      // half is a multiple of 16
+        // Warps whose 32 query rows all lie beyond the sequence (tile 1 of a 196/197-token sequence: rows >= 224) only keep
+        // the barriers company; their P rows are row-local garbage that never reaches a stored output row.
+        const bool rows_live = g * 128 + quad * 32 < S;
+        // pass 1: partial row max over this thread's columns (TMEM loads software-pipelined against the compares)
+        float mx = -INFINITY;
+        if (rows_live) {
+          tc::tmem_stream16(lane_addr, cbeg, cbeg + half, [&](const uint32_t* r, int c0) {
+            if (c0 + 16 <= S) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(s_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k > 0);
-        tc::mma_commit(&bar_s[g]);
-      }
-      tc::mbar_wait(&bar_s[g], phase);
-      tc::fence_after_sync();
-      const uint32_t lane_addr = s_col + ((uint32_t)(quad * 32) << 16);
-      const int half = NKT >> 1, cbeg = hf * half;      // half is a multiple of 16
-      // pass 1: partial row max over this thread's columns
-      float mx = -INFINITY;
-      for (int c0 = cbeg; c0 < cbeg + half; c0 += 16) {
-        uint32_t r[16];
-        tc::tmem_ld_32x16(lane_addr + c0, r);
-        tc::tmem_ld_wait();
-        if (c0 + 16 <= S) {
+              for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+            } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < S) mx = fmaxf(mx, __uint_as_float(r[j]));
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < S) mx = fmaxf(mx, __uint_as_float(r[j]));
+            }
+          });
         }
-      }
-      sMax[hf * 256 + xrow] = mx;
-      named_bar_sync(1 + g, 256);
-      mx = fmaxf(sMax[xrow], sMax[256 + xrow]);
-      // pass 2: p = exp2((s - mx) * c2) -> bf16 P tile in swizzled smem, fp32 sum of the ROUNDED values
-      const float mb = mx * c2;
-      float sum = 0.f;
-      uint8_t* pbase = smem + AttSmem::OFF_P + g * 4 * P_SLAB;
-      for (int c0 = cbeg; c0 < cbeg + half; c0 += 16) {
-        uint32_t r[16];
-        tc::tmem_ld_32x16(lane_addr + c0, r);
-        tc::tmem_ld_wait();
-        uint32_t pk[8];
-        if (c0 + 16 <= S) {
+        sMax[hf * 256 + xrow] = mx;
+        named_bar_sync(1 + g, 256);
+        mx = fmaxf(sMax[xrow], sMax[256 + xrow]);
+        // pass 2: p = exp2((s - mx) * c2) -> bf16 P tile in swizzled smem; the row sum is taken in fp32 before rounding
+        // (|sum(p~) - sum(p)| / sum(p) ~ 2^-9 / sqrt(S), far below the bf16 rounding of the output)
+        const float mb = mx * c2;
+        float sum = 0.f;
+        uint8_t* pbase = smem + AttSmem::OFF_P + g * 4 * P_SLAB;
+        if (rows_live) {
+          tc::tmem_stream16(lane_addr, cbeg, cbeg + half, [&](const uint32_t* r, int c0) {
+            if (c0 >= NKP) return;                       // beyond the keys the P.V MMA reads
+            uint32_t pk[8];
+            if (c0 + 16 <= S) {
+              float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            pk[j >> 1] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb)), ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb)));
-            const float2 q = unpack_bf16x2(pk[j >> 1]);
-            sum += q.x + q.y;
+              for (int j = 0; j < 16; j += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb));
+                s0 += p0; s1 += p1;
+                pk[j >> 1] = pack_bf16x2(p0, p1);
+              }
+              sum += s0 + s1;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb)) : 0.f;
+                const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb)) : 0.f;
+                sum += p0 + p1;
+                pk[j >> 1] = pack_bf16x2(p0, p1);
+              }
+            }
+            uint8_t* slab = pbase + (c0 >> 6) * P_SLAB;
+            const int cb = (c0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          });
+        }
+        sSum[hf * 256 + xrow] = sum;
+        // all S reads done (O overlays S) and P visible to the async proxy, then one thread issues P.V
+        tc::fence_before_sync();
+        tc::fence_proxy_async();
+        named_bar_sync(1 + g, 256);
+        if (issuer) {
+          tc::fence_after_sync();
+          const uint32_t idesc = tc::make_idesc_bf16(128, DH, 0, 1);
+          const uint32_t pa = tc::smem_u32(pbase);
+          const uint32_t va = tc::smem_u32(smem + AttSmem::OFF_V) + hoff;    // N-slice of this head inside the MN-major rows
+          for (int kk = 0; kk < NKP / 16; ++kk) {
+            const uint64_t adesc = tc::make_sdesc_sw128(pa + (kk >> 2) * P_SLAB + (kk & 3) * 32, 16, 1024);
+            const uint64_t bdesc = tc::make_sdesc_sw128(va + kk * 2048, 8192, 1024);
+            tc::mma_bf16_ss(s_col, adesc, bdesc, idesc, kk > 0);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb)) : 0.f;
-            const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb)) : 0.f;
-            pk[j >> 1] = pack_bf16x2(p0, p1);
-            const float2 q = unpack_bf16x2(pk[j >> 1]);
-            sum += q.x + q.y;
-          }
+          tc::mma_commit(&bar_o[g]);
         }
-        if (c0 < NKP) {
-          uint8_t* slab = pbase + (c0 >> 6) * P_SLAB;
-          const int cb = (c0 & 63) >> 3;
-          *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        sum = sSum[xrow] + sSum[256 + xrow];
+        tc::mbar_wait(&bar_o[g], phase);
+        if (tid == 0 && hd == HPB - 1) {
+          // every MMA that reads this item's Q / K / V has completed once both tiles' P.V have: refill the staging
+          // buffers for the next item while the epilogue below drains TMEM
+          if (two_tiles) tc::mbar_wait(&bar_o[1], ph1);
+          if (item + (int)gridDim.x < n_items) issue_loads(item + gridDim.x);
         }
-      }
-      sSum[hf * 256 + xrow] = sum;
-      // all S reads done (O overlays S) and P visible to the async proxy, then one thread issues P.V
-      tc::fence_before_sync();
-      tc::fence_proxy_async();
-      named_bar_sync(1 + g, 256);
-      if (issuer) {
         tc::fence_after_sync();
-        const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 1);
-        const uint32_t pa = tc::smem_u32(pbase);
-        const uint32_t va = tc::smem_u32(smem + AttSmem::OFF_V);
-        for (int kk = 0; kk < NKP / 16; ++kk) {
-          const uint64_t adesc = tc::make_sdesc_sw128(pa + (kk >> 2) * P_SLAB + (kk & 3) * 32, 16, 1024);
-          const uint64_t bdesc = tc::make_sdesc_sw128(va + kk * 2048, 8192, 1024);
-          tc::mma_bf16_ss(s_col, adesc, bdesc, idesc, kk > 0);
-        }
-        tc::mma_commit(&bar_o[g]);
-      }
-      sum = sSum[xrow] + sSum[256 + xrow];
-      tc::mbar_wait(&bar_o[g], phase);
-      tc::fence_after_sync();
-      {
-        constexpr int HW = DH / 2;                   // output columns per thread
-        uint32_t r[32];
-        if constexpr (HW == 16) tc::tmem_ld_32x16(lane_addr + hf * HW, r);
-        else tc::tmem_ld_32x32(lane_addr + hf * HW, r);
-        tc::tmem_ld_wait();
-        const int qrow = xrow;
-        const float inv = 1.f / sum;
-        if (qrow < S) {
-          __nv_bfloat16* orow = out + (size_t)(t0 + qrow) * ldo + h * DH + hf * HW;
+        if (rows_live) {
+          constexpr int HW = DH / 2;                   // output columns per thread
+          uint32_t r[32];
+          if constexpr (HW == 16) tc::tmem_ld_32x16(lane_addr + hf * HW, r);
+          else tc::tmem_ld_32x32(lane_addr + hf * HW, r);
+          tc::tmem_ld_wait();
+          const int qrow = xrow;
+          const float inv = 1.f / sum;
+          if (qrow < S) {
+            __nv_bfloat16* orow = out + (size_t)(t0 + qrow) * ldo + h * DH + hf * HW;
 #pragma unroll
-          for (int j = 0; j < HW; j += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + j) = o;
+            for (int j = 0; j < HW; j += 8) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+              o.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+              o.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+              o.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + j) = o;
+            }
+            if (hf == 0 && lse != nullptr) lse[(size_t)(t0 + qrow) * H + h] = mx * scale + __logf(sum);
           }
-          if (hf == 0 && lse != nullptr) lse[(size_t)(t0 + qrow) * H + h] = mx * scale + __logf(sum);
         }
+        tc::fence_before_sync();
       }
-      tc::fence_before_sync();
-      phase ^= 1;
+      ph0 ^= 1;
+      if (two_tiles) ph1 ^= 1;
+      __syncthreads();          // TMEM (O overlays S) and the P buffers are free for the next head / item
     }
-    __syncthreads();          // every MMA that read this item's smem has completed (both bar_o waits passed)
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -267,13 +269,14 @@ struct AttBwdSmem {
 
 template <int DH>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const float* __restrict__ lse, const int* __restrict__ seq_start, int nseq, int H, float scale,
                         __nv_bfloat16* __restrict__ dqkv) {
+  constexpr int HPB = 64 / DH;                      // heads per 128-byte box row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sD = reinterpret_cast<float*>(smem + AttBwdSmem::OFF_D);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttBwdSmem::OFF_BAR);   // [0] S,dP  [1] dV  [2] dK,dQ
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttBwdSmem::OFF_BAR);   // [0] S,dP  [1] dV  [2] dK,dQ  [3] loads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, grp = warp >> 2;      // 4 column groups
@@ -282,49 +285,57 @@ attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
 
   for (int i = tid; i < AttBwdSmem::OFF_D / 16; i += ATC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) tc::mbar_init(&bars[i], 1);
+    tc::prefetch_tmap(&tmQKV);
+    tc::prefetch_tmap(&tmDO);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
 
-  const int ldq = 3 * H * DH, ldo = H * DH;
+  const int ldq = 3 * H * DH;
+  const int HG = H / HPB;
   const float c2 = scale * 1.4426950408889634f;
   constexpr int COL_DP = 224, COL_DV = 0, COL_DK = 128, COL_DQ = 256;
   constexpr int HC = DH / 2;                       // accumulator columns per thread
-  uint32_t phase = 0;
-  const int n_items = nseq * H;
+  uint32_t phase = 0, ph_ld = 0;
+  const int n_items = nseq * HG;
   const uint32_t sQ = tc::smem_u32(smem + AttBwdSmem::OFF_Q), sDO = tc::smem_u32(smem + AttBwdSmem::OFF_DO);
   const uint32_t sK = tc::smem_u32(smem + AttBwdSmem::OFF_K), sV = tc::smem_u32(smem + AttBwdSmem::OFF_V);
   const uint32_t sP = tc::smem_u32(smem + AttBwdSmem::OFF_P);
   uint8_t* pbuf = smem + AttBwdSmem::OFF_P;
 
-  constexpr int NPF = ((DH == 64 ? 128 : ATC_MAXKEYS) * (DH / 8) * 4 + ATC_THREADS - 1) / ATC_THREADS;   // Dh = 64 is limited to 128 keys
-  RowStager<DH, 4, NPF> stager;
-  auto prefetch = [&](int it) {
-    const int sq = it / H, hh = it % H;
+  auto issue_loads = [&](int it) {                 // one thread
+    const int sq = it / HG, hg = it - sq * HG;
     const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
-    const __nv_bfloat16* base = qkv + (size_t)tt * ldq + hh * DH;
-    const __nv_bfloat16* srcs[4] = {base, base + H * DH, base + 2 * H * DH, dout + (size_t)tt * ldo + hh * DH};
-    const int offs[4] = {AttBwdSmem::OFF_Q, AttBwdSmem::OFF_K, AttBwdSmem::OFF_V, AttBwdSmem::OFF_DO};
-    const int lds[4] = {ldq, ldq, ldq, ldo};
-    stager.load(offs, srcs, lds, SS, tid);
+    const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
+    tc::mbar_expect_tx(&bars[3], 4 * nb * BOX_BYTES);
+    const int offs[3] = {AttBwdSmem::OFF_Q, AttBwdSmem::OFF_K, AttBwdSmem::OFF_V};
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      for (int b = 0; b < nb; ++b)
+        tc::tma_load_2d(smem + offs[m] + b * BOX_BYTES, &tmQKV, &bars[3], m * H * DH + hg * 64, tt + b * BOX_ROWS);
+    for (int b = 0; b < nb; ++b)
+      tc::tma_load_2d(smem + AttBwdSmem::OFF_DO + b * BOX_BYTES, &tmDO, &bars[3], hg * 64, tt + b * BOX_ROWS);
   };
-  if ((int)blockIdx.x < n_items) prefetch(blockIdx.x);
+  if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int seq = item / H, h = item % H;
+    const int seq = item / HG, hg = item - seq * HG;
     const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
     const int NKT = (S + 31) & ~31, NKP = (S + 15) & ~15;
     const int NQ = (S + 127) >> 7;                 // query tiles == key tiles
-    stager.commit(smem);
-    tc::fence_proxy_async();
-    __syncthreads();
-    if (item + (int)gridDim.x < n_items) prefetch(item + gridDim.x);     // lands during this item's compute
+    tc::mbar_wait(&bars[3], ph_ld);
+    ph_ld ^= 1;
 
+#pragma unroll 1
+    for (int hd = 0; hd < HPB; ++hd) {
+    const int h = hg * HPB + hd;
+    const uint32_t hoff = (uint32_t)(hd * DH * 2);   // byte offset of this head inside the 128-byte rows
     float accK[HC], accV[HC];                      // key row kt*128 + row_in_tile, columns [kh*HC, +HC), summed over query tiles
 #pragma unroll
     for (int d = 0; d < HC; ++d) { accK[d] = 0.f; accV[d] = 0.f; }
@@ -334,47 +345,58 @@ attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
       if (tid == 0) {
         tc::fence_after_sync();
         const uint32_t idesc = tc::make_idesc_bf16(128, NKT, 0, 0);
-        const uint64_t aq = tc::make_sdesc_sw128(sQ + g * 128 * ROWB, 16, 1024), bk = tc::make_sdesc_sw128(sK, 16, 1024);
-        const uint64_t ao = tc::make_sdesc_sw128(sDO + g * 128 * ROWB, 16, 1024), bv = tc::make_sdesc_sw128(sV, 16, 1024);
+        const uint64_t aq = tc::make_sdesc_sw128(sQ + g * 128 * ROWB + hoff, 16, 1024), bk = tc::make_sdesc_sw128(sK + hoff, 16, 1024);
+        const uint64_t ao = tc::make_sdesc_sw128(sDO + g * 128 * ROWB + hoff, 16, 1024), bv = tc::make_sdesc_sw128(sV + hoff, 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base, aq + (uint64_t)(k * 2), bk + (uint64_t)(k * 2), idesc, k > 0);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base + COL_DP, ao + (uint64_t)(k * 2), bv + (uint64_t)(k * 2), idesc, k > 0);
         tc::mma_commit(&bars[0]);
       }
-      tc::mbar_wait(&bars[0], phase);
-      tc::fence_after_sync();
       const int qrow = g * 128 + row_in_tile;
       const bool qok = qrow < S;
       const float l2 = qok ? lse[(size_t)(t0 + qrow) * H + h] * 1.4426950408889634f : INFINITY;   // invalid row: P~ = 0
-      const int quarter = NKT >> 2;                 // multiple of 8
-      const int cbeg = grp * quarter;
-      // ---- pass 1: P~ -> smem, partial D
+      tc::mbar_wait(&bars[0], phase);
+      tc::fence_after_sync();
+      // the four warp groups split the NKT/16 column chunks of each row (3,4,3,4 chunks at NKT = 224)
+      const int nch = NKT >> 4;
+      const int cbeg = ((grp * nch) >> 2) << 4, cend = (((grp + 1) * nch) >> 2) << 4;
+      const bool rows_live = g * 128 + quad * 32 < S;   // warp-uniform: any valid query row in this warp
+      // ---- pass 1: P~ -> smem, partial D  (TMEM loads of chunk i+1 in flight while chunk i is processed)
       float dpart = 0.f;
-      for (int c0 = cbeg; c0 < cbeg + quarter; c0 += 8) {
-        uint32_t rs[8], rp[8];
-        tc::tmem_ld_32x8(lane_base + c0, rs);
-        tc::tmem_ld_32x8(lane_base + COL_DP + c0, rp);
-        tc::tmem_ld_wait();
-        uint32_t pk[4];
-        if (c0 + 8 <= S) {
+      if (rows_live) {
+        tc::tmem_stream16x2(lane_base, COL_DP, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
+          uint32_t pk[8];
+          float d0 = 0.f, d1 = 0.f;
+          if (c0 + 16 <= S) {
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            pk[j >> 1] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)), ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)));
-            const float2 q = unpack_bf16x2(pk[j >> 1]);
-            dpart = fmaf(q.x, __uint_as_float(rp[j]), fmaf(q.y, __uint_as_float(rp[j + 1]), dpart));
-          }
-        } else {
+            for (int j = 0; j < 16; j += 2) {
+              pk[j >> 1] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)), ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)));
+              const float2 q = unpack_bf16x2(pk[j >> 1]);
+              d0 = fmaf(q.x, __uint_as_float(rp[j]), d0);
+              d1 = fmaf(q.y, __uint_as_float(rp[j + 1]), d1);
+            }
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
-            const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
-            pk[j >> 1] = pack_bf16x2(p0, p1);
-            const float2 q = unpack_bf16x2(pk[j >> 1]);
-            dpart = fmaf(q.x, __uint_as_float(rp[j]), fmaf(q.y, __uint_as_float(rp[j + 1]), dpart));
+            for (int j = 0; j < 16; j += 2) {
+              const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
+              const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
+              pk[j >> 1] = pack_bf16x2(p0, p1);
+              const float2 q = unpack_bf16x2(pk[j >> 1]);
+              d0 = fmaf(q.x, __uint_as_float(rp[j]), d0);
+              d1 = fmaf(q.y, __uint_as_float(rp[j + 1]), d1);
+            }
           }
-        }
-        *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dpart += d0 + d1;
+          uint8_t* a = pbuf + (c0 >> 6) * P_SLAB;
+          const int cb = (c0 & 63) >> 3;
+          *reinterpret_cast<uint4*>(a + sw_off(row_in_tile, cb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(a + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        });
+      } else {
+        // no valid query row in this warp: its P~ / dS rows are zero (they feed the dK / dV sums over queries)
+        for (int c0 = cbeg; c0 < cend; c0 += 8)
+          *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(0, 0, 0, 0);
       }
       sD[grp * 128 + row_in_tile] = dpart;
       tc::fence_before_sync();
@@ -383,12 +405,12 @@ attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
       // ---- (3) dV_kt = P~^T dO_g   (S columns are dead now: accumulators overlay them)
       if (tid == 0) {
         tc::fence_after_sync();
-        const uint32_t idesc = tc::make_idesc_bf16(128, 64, 1, 1);
+        const uint32_t idesc = tc::make_idesc_bf16(128, DH, 1, 1);
         for (int t = 0; t < NQ; ++t)
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint64_t a = tc::make_sdesc_sw128(sP + 2 * t * P_SLAB + kk * 2048, P_SLAB, 1024);
-            const uint64_t b = tc::make_sdesc_sw128(sDO + g * 128 * ROWB + kk * 2048, 8192, 1024);
+            const uint64_t b = tc::make_sdesc_sw128(sDO + g * 128 * ROWB + kk * 2048 + hoff, 8192, 1024);
             tc::mma_bf16_ss(tmem_base + COL_DV + t * 64, a, b, idesc, kk > 0);
           }
         tc::mma_commit(&bars[1]);
@@ -397,20 +419,24 @@ attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
       tc::mbar_wait(&bars[1], phase);             // dV has consumed P~: the buffer can take dS
       tc::fence_after_sync();
       // ---- pass 2: dS = P~ (dP - D) -> smem
-      for (int c0 = cbeg; c0 < cbeg + quarter; c0 += 8) {
-        uint32_t rp[8];
-        tc::tmem_ld_32x8(lane_base + COL_DP + c0, rp);
-        uint8_t* addr = pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3);
-        const uint4 pa = *reinterpret_cast<uint4*>(addr);
-        tc::tmem_ld_wait();
-        const uint32_t pin[4] = {pa.x, pa.y, pa.z, pa.w};
-        uint32_t ds[4];
+      if (rows_live) {
+        tc::tmem_stream16(lane_base + COL_DP, cbeg, cend, [&](const uint32_t* rp, int c0) {
+          uint8_t* a = pbuf + (c0 >> 6) * P_SLAB;
+          const int cb = (c0 & 63) >> 3;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 p = unpack_bf16x2(pin[j]);
-          ds[j] = pack_bf16x2(p.x * (__uint_as_float(rp[2 * j]) - Di), p.y * (__uint_as_float(rp[2 * j + 1]) - Di));
-        }
-        *reinterpret_cast<uint4*>(addr) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+          for (int hh = 0; hh < 2; ++hh) {
+            uint8_t* addr = a + sw_off(row_in_tile, cb + hh);
+            const uint4 pa = *reinterpret_cast<uint4*>(addr);
+            const uint32_t pin[4] = {pa.x, pa.y, pa.z, pa.w};
+            uint32_t ds[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 p = unpack_bf16x2(pin[j]);
+              ds[j] = pack_bf16x2(p.x * (__uint_as_float(rp[8 * hh + 2 * j]) - Di), p.y * (__uint_as_float(rp[8 * hh + 2 * j + 1]) - Di));
+            }
+            *reinterpret_cast<uint4*>(addr) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+          }
+        });
       }
       tc::fence_before_sync();
       tc::fence_proxy_async();
@@ -418,23 +444,25 @@ attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
       // ---- (4) dK_kt = dS^T Q_g ; (5) dQ_g = dS K
       if (tid == 0) {
         tc::fence_after_sync();
-        const uint32_t idesc_t = tc::make_idesc_bf16(128, 64, 1, 1);
+        const uint32_t idesc_t = tc::make_idesc_bf16(128, DH, 1, 1);
         for (int t = 0; t < NQ; ++t)
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint64_t a = tc::make_sdesc_sw128(sP + 2 * t * P_SLAB + kk * 2048, P_SLAB, 1024);
-            const uint64_t b = tc::make_sdesc_sw128(sQ + g * 128 * ROWB + kk * 2048, 8192, 1024);
+            const uint64_t b = tc::make_sdesc_sw128(sQ + g * 128 * ROWB + kk * 2048 + hoff, 8192, 1024);
             tc::mma_bf16_ss(tmem_base + COL_DK + t * 64, a, b, idesc_t, kk > 0);
           }
-        const uint32_t idesc_q = tc::make_idesc_bf16(128, 64, 0, 1);
+        const uint32_t idesc_q = tc::make_idesc_bf16(128, DH, 0, 1);
         for (int kk = 0; kk < NKP / 16; ++kk) {
           const uint64_t a = tc::make_sdesc_sw128(sP + (kk >> 2) * P_SLAB + (kk & 3) * 32, 16, 1024);
-          const uint64_t b = tc::make_sdesc_sw128(sK + kk * 2048, 8192, 1024);
+          const uint64_t b = tc::make_sdesc_sw128(sK + kk * 2048 + hoff, 8192, 1024);
           tc::mma_bf16_ss(tmem_base + COL_DQ, a, b, idesc_q, kk > 0);
         }
         tc::mma_commit(&bars[2]);
       }
       tc::mbar_wait(&bars[2], phase);
+      if (tid == 0 && hd == HPB - 1 && g == NQ - 1 && item + (int)gridDim.x < n_items)
+        issue_loads(item + gridDim.x);            // every MMA on this item's operands is done: refill during the drain
       tc::fence_after_sync();
       // ---- drain: dQ rows of this tile (columns split four ways), dK / dV partials into registers
       {
@@ -476,7 +504,7 @@ attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
       }
       tc::fence_before_sync();
       phase ^= 1;
-      __syncthreads();                              // TMEM and smem free for the next tile / item
+      __syncthreads();                              // TMEM and smem free for the next tile / head / item
     }
     // ---- store this thread's half key row
     const int krow = kt * 128 + row_in_tile;
@@ -494,6 +522,7 @@ attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
         *reinterpret_cast<uint4*>(dv + j) = o;
       }
     }
+    }  // heads of the box
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -507,44 +536,59 @@ attention_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
 
 using namespace eavit;
 
-extern "C" int eavit_attention_fwd_tc(const void* qkv, const int* seq_start, int nseq, int max_len, int H, int Dh, float scale,
-                                      void* out, float* lse, void* stream) {
-  EAVIT_CHECK_ARG(qkv && seq_start && out && nseq > 0 && H > 0);
+static int attention_tmaps(const void* qkv, const void* dout, long long T, int H, int Dh, CUtensorMap* tq, CUtensorMap* tdo) {
+  int rc = make_tmap_bf16_2d(tq, qkv, (uint64_t)3 * H * Dh, (uint64_t)T, (uint64_t)3 * H * Dh * 2, BOX_ROWS);
+  if (rc) return rc;
+  if (dout != nullptr) rc = make_tmap_bf16_2d(tdo, dout, (uint64_t)H * Dh, (uint64_t)T, (uint64_t)H * Dh * 2, BOX_ROWS);
+  return rc;
+}
+
+// total tokens = seq_start[nseq]; the host mirror passes it so that no device read-back is needed
+extern "C" int eavit_attention_fwd_tc(const void* qkv, const int* seq_start, int nseq, int max_len, long long total_tokens,
+                                      int H, int Dh, float scale, void* out, float* lse, void* stream) {
+  EAVIT_CHECK_ARG(qkv && seq_start && out && nseq > 0 && H > 0 && total_tokens > 0);
   EAVIT_CHECK_ARG(max_len > 0 && max_len <= ATC_MAXKEYS);
-  EAVIT_CHECK_ARG(Dh == 32 || Dh == 64);
+  EAVIT_CHECK_ARG((Dh == 32 && H % 2 == 0) || Dh == 64);
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  const int items = nseq * H;
+  CUtensorMap tq, tdo;
+  int rc = attention_tmaps(qkv, nullptr, total_tokens, H, Dh, &tq, &tdo);
+  if (rc) return rc;
+  const int items = nseq * (H / (64 / Dh));
   const int grid = items < kNumSMs ? items : kNumSMs;
   if (Dh == 32) {
     static bool done = false;
     if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::TOTAL)); done = true; }
-    attention_fwd_tc_kernel<32><<<grid, ATC_THREADS, AttSmem::TOTAL, st>>>((const __nv_bfloat16*)qkv, seq_start, nseq, H, scale, (__nv_bfloat16*)out, lse);
+    attention_fwd_tc_kernel<32><<<grid, ATC_THREADS, AttSmem::TOTAL, st>>>(tq, seq_start, nseq, H, scale, (__nv_bfloat16*)out, lse);
   } else {
     static bool done = false;
     if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::TOTAL)); done = true; }
-    attention_fwd_tc_kernel<64><<<grid, ATC_THREADS, AttSmem::TOTAL, st>>>((const __nv_bfloat16*)qkv, seq_start, nseq, H, scale, (__nv_bfloat16*)out, lse);
+    attention_fwd_tc_kernel<64><<<grid, ATC_THREADS, AttSmem::TOTAL, st>>>(tq, seq_start, nseq, H, scale, (__nv_bfloat16*)out, lse);
   }
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
 
 extern "C" int eavit_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const int* seq_start, int nseq,
-                                      int max_len, int H, int Dh, float scale, void* dqkv, void* stream) {
-  EAVIT_CHECK_ARG(qkv && dout && lse && seq_start && dqkv && nseq > 0 && H > 0);
+                                      int max_len, long long total_tokens, int H, int Dh, float scale, void* dqkv, void* stream) {
+  EAVIT_CHECK_ARG(qkv && dout && lse && seq_start && dqkv && nseq > 0 && H > 0 && total_tokens > 0);
   EAVIT_CHECK_ARG(max_len > 0 && max_len <= ATC_MAXKEYS);
-  EAVIT_CHECK_ARG(Dh == 32 || (Dh == 64 && max_len <= 128));
+  EAVIT_CHECK_ARG((Dh == 32 && H % 2 == 0) || (Dh == 64 && max_len <= 128));
+  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  const int items = nseq * H;
+  CUtensorMap tq, tdo;
+  int rc = attention_tmaps(qkv, dout, total_tokens, H, Dh, &tq, &tdo);
+  if (rc) return rc;
+  const int items = nseq * (H / (64 / Dh));
   const int grid = items < kNumSMs ? items : kNumSMs;
   if (Dh == 32) {
     static bool done = false;
     if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttBwdSmem::TOTAL)); done = true; }
-    attention_bwd_tc_kernel<32><<<grid, ATC_THREADS, AttBwdSmem::TOTAL, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, lse, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv);
+    attention_bwd_tc_kernel<32><<<grid, ATC_THREADS, AttBwdSmem::TOTAL, st>>>(tq, tdo, lse, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv);
   } else {
     static bool done = false;
     if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttBwdSmem::TOTAL)); done = true; }
-    attention_bwd_tc_kernel<64><<<grid, ATC_THREADS, AttBwdSmem::TOTAL, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, lse, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv);
+    attention_bwd_tc_kernel<64><<<grid, ATC_THREADS, AttBwdSmem::TOTAL, st>>>(tq, tdo, lse, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv);
   }
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;

@@ -222,9 +222,9 @@ _SPECS = {
     "eavit_add_f32": "pppl",
     "eavit_zero": "pl",
     "eavit_attention_fwd": "ppiiiifpp",
-    "eavit_attention_fwd_tc": "ppiiiifpp",
+    "eavit_attention_fwd_tc": "ppiiliifpp",
     "eavit_attention_bwd": "pppppiiiifp",
-    "eavit_attention_bwd_tc": "ppppiiiifp",
+    "eavit_attention_bwd_tc": "ppppiiliifp",
     "eavit_patchify": "pipiiiiippfppp",
     "eavit_patchify_ln_bwd": "pipiiiiipppppp",
     "eavit_embed_assemble": "ppppiiiip",
@@ -288,13 +288,13 @@ def call(name: str, *args):
 def attention_fwd(qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse):
     """tcgen05 kernel when the sequence fits its TMEM plan (S <= 224), CUDA-core kernel for longer sequences."""
     if max_len <= 224:
-        call("eavit_attention_fwd_tc", qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse)
+        call("eavit_attention_fwd_tc", qkv, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, out, lse)
     else:
         call("eavit_attention_fwd", qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse)
 
 
 def attention_bwd(qkv, out, dout, lse, seq_start, nseq, max_len, H, Dh, scale, dqkv):
     if (Dh == 32 and max_len <= 224) or (Dh == 64 and max_len <= 128):
-        call("eavit_attention_bwd_tc", qkv, dout, lse, seq_start, nseq, max_len, H, Dh, scale, dqkv)
+        call("eavit_attention_bwd_tc", qkv, dout, lse, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, dqkv)
     else:
         call("eavit_attention_bwd", qkv, out, dout, lse, seq_start, nseq, max_len, H, Dh, scale, dqkv)

@@ -155,15 +155,17 @@ int eavit_zero(void* ptr, long long bytes, void* stream);
  * max_len <= 256; Dh in {32, 64}. */
 int eavit_attention_fwd(const void* qkv, const int* seq_start, int nseq, int max_len, int H, int Dh, float scale,
                         void* out, float* lse, void* stream);
-/* Same contract on tcgen05 tensor cores (S and O accumulators in TMEM, P staged as a bf16 MMA operand); max_len <= 224. */
-int eavit_attention_fwd_tc(const void* qkv, const int* seq_start, int nseq, int max_len, int H, int Dh, float scale,
-                           void* out, float* lse, void* stream);
+/* Same contract on tcgen05 tensor cores (TMA-staged operands, S and O accumulators in TMEM, P staged as a bf16 MMA
+ * operand); max_len <= 224.  total_tokens = T = seq_start[nseq] (the extent of the TMA tensor map: rows past T are
+ * zero-filled, never read).  Dh = 32 needs an even H (two heads share one 128-byte staged row). */
+int eavit_attention_fwd_tc(const void* qkv, const int* seq_start, int nseq, int max_len, long long total_tokens, int H, int Dh,
+                           float scale, void* out, float* lse, void* stream);
 int eavit_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const int* seq_start,
                         int nseq, int max_len, int H, int Dh, float scale, void* dqkv, void* stream);
 
 /* Backward on tcgen05 (recomputes P from q, k, lse; does not need `out`).  Dh = 32: max_len <= 224; Dh = 64: max_len <= 128. */
 int eavit_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const int* seq_start, int nseq, int max_len,
-                           int H, int Dh, float scale, void* dqkv, void* stream);
+                           long long total_tokens, int H, int Dh, float scale, void* dqkv, void* stream);
 
 /* ------------------------------------------------------------------ patch embedding (vit.py:109-158) */
 

@@ -30,7 +30,7 @@ def rel(a, b):
 
 
 CASES = [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([197] * 5, 8, 32), ([1, 17, 128, 129, 224], 4, 32),
-         ([64, 200], 3, 64)]
+         ([64, 200], 3, 64), ([197, 33, 196, 5] * 40, 8, 32)]        # the last one: > 148 items, every CTA loops
 
 
 @pytest.mark.parametrize("lens,H,Dh", CASES)
@@ -46,8 +46,10 @@ def test_attention_forward(ops, lens, H, Dh, impl):
     out = torch.full((T, H * Dh), float("nan"), device="cuda", dtype=torch.bfloat16)
     lse = torch.full((T, H), float("nan"), device="cuda")
     scale = Dh ** -0.5
-    name = "eavit_attention_fwd" if impl == "v1" else "eavit_attention_fwd_tc"
-    ops.call(name, qkv, ss, len(lens), max(lens), H, Dh, scale, out, lse)
+    if impl == "v1":
+        ops.call("eavit_attention_fwd", qkv, ss, len(lens), max(lens), H, Dh, scale, out, lse)
+    else:
+        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse)
     torch.cuda.synchronize()
     ro, rl = ref_attention(qkv, starts, H, Dh, scale)
     assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
@@ -55,7 +57,8 @@ def test_attention_forward(ops, lens, H, Dh, impl):
     assert (lse - rl).abs().max().item() < 2e-2
 
 
-BWD_CASES = [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([1, 17, 128, 129, 224], 4, 32), ([64, 100], 3, 64)]
+BWD_CASES = [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([1, 17, 128, 129, 224], 4, 32), ([64, 100], 3, 64),
+             ([197, 33, 196, 5] * 40, 8, 32)]
 
 
 @pytest.mark.parametrize("lens,H,Dh", BWD_CASES)
@@ -75,11 +78,12 @@ def test_attention_backward(ops, lens, H, Dh, impl):
     (ro * dout.float()).sum().backward()
     out = torch.empty(T, H * Dh, device="cuda", dtype=torch.bfloat16)
     lse = torch.empty(T, H, device="cuda")
-    ops.call("eavit_attention_fwd_tc" if impl == "tc" else "eavit_attention_fwd", qkv, ss, len(lens), max(lens), H, Dh, scale, out, lse)
     dqkv = torch.full((T, 3 * H * Dh), float("nan"), device="cuda", dtype=torch.bfloat16)
     if impl == "tc":
-        ops.call("eavit_attention_bwd_tc", qkv, dout, lse, ss, len(lens), max(lens), H, Dh, scale, dqkv)
+        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse)
+        ops.call("eavit_attention_bwd_tc", qkv, dout, lse, ss, len(lens), max(lens), T, H, Dh, scale, dqkv)
     else:
+        ops.call("eavit_attention_fwd", qkv, ss, len(lens), max(lens), H, Dh, scale, out, lse)
         ops.call("eavit_attention_bwd", qkv, out, dout, lse, ss, len(lens), max(lens), H, Dh, scale, dqkv)
     torch.cuda.synchronize()
     assert torch.isfinite(dqkv.float()).all()
