@@ -10,7 +10,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeavit_b200.so")
+LIB_PATH = os.environ.get("EAVIT_B200_LIB") or os.path.join(_HERE, "libeavit_b200.so")   # override: instrumented builds (tools/)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "eavit_b200.h")
 
 _lib = None

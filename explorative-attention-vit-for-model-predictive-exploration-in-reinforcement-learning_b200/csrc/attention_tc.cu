@@ -58,7 +58,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
   float* sSum = sMax + 512;                                            // [2][256]
   uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + AttSmem::OFF_BAR);
   uint64_t* bar_o = bar_s + 2;
-  uint64_t* bar_ld = bar_s + 4;
+  uint64_t* bar_qk = bar_s + 4;                  // Q, K staged
+  uint64_t* bar_v = bar_s + 5;                   // V staged
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, grp = warp >> 2;   // 4 groups of 4 warps
@@ -71,7 +72,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
   if (tid == 0) {
     tc::prefetch_tmap(&tmQKV);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bar_s[i], 1); tc::mbar_init(&bar_o[i], 1); }
-    tc::mbar_init(bar_ld, 1);
+    tc::mbar_init(bar_qk, 1);
+    tc::mbar_init(bar_v, 1);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -86,27 +88,36 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
   const float c2 = scale * 1.4426950408889634f;      // exp(x*scale) = exp2(x*c2)
   uint32_t ph0 = 0, ph1 = 0, ph_ld = 0;              // parities of bar_*[0], bar_*[1], bar_ld (uniform across the CTA)
   const int n_items = nseq * HG;
-  auto issue_loads = [&](int it) {                   // one thread
+  // Q and K are dead once the last head's score MMAs have completed, V once its P.V MMAs have: the next item's Q / K
+  // land during the current item's last softmax and its V during the following one (TMA latency fully hidden).
+  auto issue_qk = [&](int it) {                      // one thread
     const int sq = it / HG, hg = it - sq * HG;
     const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
     const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
-    tc::mbar_expect_tx(bar_ld, 3 * nb * BOX_BYTES);
-    const int offs[3] = {AttSmem::OFF_Q, AttSmem::OFF_K, AttSmem::OFF_V};
-#pragma unroll
-    for (int m = 0; m < 3; ++m)
-      for (int b = 0; b < nb; ++b)
-        tc::tma_load_2d(smem + offs[m] + b * BOX_BYTES, &tmQKV, bar_ld, m * H * DH + hg * 64, tt + b * BOX_ROWS);
+    tc::mbar_expect_tx(bar_qk, 2 * nb * BOX_BYTES);
+    for (int b = 0; b < nb; ++b) {
+      tc::tma_load_2d(smem + AttSmem::OFF_Q + b * BOX_BYTES, &tmQKV, bar_qk, hg * 64, tt + b * BOX_ROWS);
+      tc::tma_load_2d(smem + AttSmem::OFF_K + b * BOX_BYTES, &tmQKV, bar_qk, H * DH + hg * 64, tt + b * BOX_ROWS);
+    }
   };
-  if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
+  auto issue_v = [&](int it) {
+    const int sq = it / HG, hg = it - sq * HG;
+    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
+    tc::mbar_expect_tx(bar_v, nb * BOX_BYTES);
+    for (int b = 0; b < nb; ++b)
+      tc::tma_load_2d(smem + AttSmem::OFF_V + b * BOX_BYTES, &tmQKV, bar_v, 2 * H * DH + hg * 64, tt + b * BOX_ROWS);
+  };
+  if (tid == 0 && (int)blockIdx.x < n_items) { issue_qk(blockIdx.x); issue_v(blockIdx.x); }
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int seq = item / HG, hg = item - seq * HG;
     const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
     const int NKT = (S + 31) & ~31;                  // score columns
     const int NKP = (S + 15) & ~15;                  // keys covered by the P.V MMA
     const bool two_tiles = S > 128;
-    tc::mbar_wait(bar_ld, ph_ld);
-    ph_ld ^= 1;
+    tc::mbar_wait(bar_qk, ph_ld);
     const bool active = g * 128 < S;
+    const bool has_next = item + (int)gridDim.x < n_items;
 #pragma unroll 1
     for (int hd = 0; hd < HPB; ++hd) {
       const int h = hg * HPB + hd;
@@ -126,6 +137,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
           tc::mma_commit(&bar_s[g]);
         }
         tc::mbar_wait(&bar_s[g], phase);
+        if (tid == 0 && hd == HPB - 1 && has_next) {
+          if (two_tiles) tc::mbar_wait(&bar_s[1], ph1);   // the other tile's score MMA reads the same K
+          issue_qk(item + gridDim.x);
+        }
         tc::fence_after_sync();
         const uint32_t lane_addr = s_col + ((uint32_t)(quad * 32) << 16);
         const int half = NKT >> 1, cbeg = hf * half;      // half is a multiple of 16
@@ -189,6 +204,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
         tc::fence_proxy_async();
         named_bar_sync(1 + g, 256);
         if (issuer) {
+          if (hd == 0) tc::mbar_wait(bar_v, ph_ld);
           tc::fence_after_sync();
           const uint32_t idesc = tc::make_idesc_bf16(128, DH, 0, 1);
           const uint32_t pa = tc::smem_u32(pbase);
@@ -202,11 +218,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
         }
         sum = sSum[xrow] + sSum[256 + xrow];
         tc::mbar_wait(&bar_o[g], phase);
-        if (tid == 0 && hd == HPB - 1) {
-          // every MMA that reads this item's Q / K / V has completed once both tiles' P.V have: refill the staging
-          // buffers for the next item while the epilogue below drains TMEM
-          if (two_tiles) tc::mbar_wait(&bar_o[1], ph1);
-          if (item + (int)gridDim.x < n_items) issue_loads(item + gridDim.x);
+        if (tid == 0 && hd == HPB - 1 && has_next) {
+          if (two_tiles) tc::mbar_wait(&bar_o[1], ph1);   // both tiles' P.V done: V can be refilled
+          issue_v(item + gridDim.x);
         }
         tc::fence_after_sync();
         if (rows_live) {
@@ -235,8 +249,11 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
       }
       ph0 ^= 1;
       if (two_tiles) ph1 ^= 1;
-      __syncthreads();          // TMEM (O overlays S) and the P buffers are free for the next head / item
+      // TMEM (O overlays S), the P buffer and the max / sum exchange slots are private to the tile group: only the
+      // group has to agree that they are free for the next head / item
+      if (active) named_bar_sync(1 + g, 256);
     }
+    ph_ld ^= 1;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -250,7 +267,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
 // Backward.  Per (sequence, head) item and per 128-row query tile g, all 512 threads work on one tile: the four groups
 // of four warps split the key columns of each TMEM row four ways.
 //   S  = Q_g K^T, dP = dO_g V^T                tcgen05.mma 128 x NKT x DH  (TMEM cols [0,NKT) and [224,224+NKT))
-//   P~ = bf16(exp2(S c2 - lse log2e))           -> swizzled smem;   D_i = sum_j P~_ij dP_ij   (quarters exchanged via smem)
+//   P~ = bf16(exp2(S c2 - lse log2e))           -> swizzled smem;   D_i = sum_j P_ij dP_ij with the fp32 P (sum_j P_ij = 1 to
+//                                                  fp32 accuracy, so dS = P~ (dP - D) carries no D-proportional bias)
 //   dV_kt += P~^T dO_g                          tcgen05.mma 128 x 64 x 128, A = P~ read in place as an MN-major operand
 //   dS = P~ (dP - D)                            -> the same smem buffer once dV has consumed P~
 //   dK_kt += dS^T Q_g ; dQ_g = dS K             A = dS MN-major / K-major, B = Q_g / K in place as MN-major operands
@@ -371,10 +389,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           if (c0 + 16 <= S) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              pk[j >> 1] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)), ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)));
-              const float2 q = unpack_bf16x2(pk[j >> 1]);
-              d0 = fmaf(q.x, __uint_as_float(rp[j]), d0);
-              d1 = fmaf(q.y, __uint_as_float(rp[j + 1]), d1);
+              const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2));
+              pk[j >> 1] = pack_bf16x2(p0, p1);
+              d0 = fmaf(p0, __uint_as_float(rp[j]), d0);
+              d1 = fmaf(p1, __uint_as_float(rp[j + 1]), d1);
             }
           } else {
 #pragma unroll
@@ -382,9 +401,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
               const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
               const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
               pk[j >> 1] = pack_bf16x2(p0, p1);
-              const float2 q = unpack_bf16x2(pk[j >> 1]);
-              d0 = fmaf(q.x, __uint_as_float(rp[j]), d0);
-              d1 = fmaf(q.y, __uint_as_float(rp[j + 1]), d1);
+              d0 = fmaf(p0, __uint_as_float(rp[j]), d0);
+              d1 = fmaf(p1, __uint_as_float(rp[j + 1]), d1);
             }
           }
           dpart += d0 + d1;
@@ -431,8 +449,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             uint32_t ds[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 p = unpack_bf16x2(pin[j]);
-              ds[j] = pack_bf16x2(p.x * (__uint_as_float(rp[8 * hh + 2 * j]) - Di), p.y * (__uint_as_float(rp[8 * hh + 2 * j + 1]) - Di));
+              const float px = __uint_as_float(pin[j] << 16), py = __uint_as_float(pin[j] & 0xffff0000u);
+              ds[j] = pack_bf16x2(px * (__uint_as_float(rp[8 * hh + 2 * j]) - Di), py * (__uint_as_float(rp[8 * hh + 2 * j + 1]) - Di));
             }
             *reinterpret_cast<uint4*>(addr) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
           }

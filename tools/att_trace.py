@@ -1,0 +1,38 @@
+"""Phase timing of the attention backward kernel (needs the -DEAVIT_TRACE build: EAVIT_B200_LIB=tools/_trace/libeavit_b200_trace.so)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import eavit_b200  # noqa
+from eavit_b200 import ops, _lib
+H, DH, B = 8, 32, 512
+lens = [196] * B + [197] * B
+st = [0]
+for n in lens:
+    st.append(st[-1] + n)
+ss = torch.tensor(st, dtype=torch.int32, device="cuda")
+qkv = torch.randn(st[-1], 3 * H * DH, device="cuda").bfloat16()
+o = torch.empty(st[-1], H * DH, device="cuda", dtype=torch.bfloat16)
+lse = torch.empty(st[-1], H, device="cuda")
+do = torch.randn_like(o)
+dqkv = torch.empty_like(qkv)
+ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse)
+which = sys.argv[1] if len(sys.argv) > 1 else "bwd"
+def run():
+    if which == "bwd":
+        ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv)
+    else:
+        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse)
+run()
+torch.cuda.synchronize()
+L = _lib.lib()
+buf = (ctypes.c_longlong * 32)()
+L.eavit_debug_att_trace(buf, 1)
+run()
+L.eavit_debug_att_trace(buf, 0)
+v = list(buf)
+tot = sum(v)
+names = sys.argv[2].split(",") if len(sys.argv) > 2 else [str(i) for i in range(32)]
+for i, x in enumerate(v):
+    if x:
+        print(f"{i:2d} {names[i] if i < len(names) else '':28s} {x:12d} cycles {100.0 * x / tot:5.1f}%")
+print("total cycles (block 0)", tot)
