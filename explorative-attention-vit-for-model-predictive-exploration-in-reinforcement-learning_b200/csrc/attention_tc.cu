@@ -34,6 +34,13 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 // work item is (sequence, head group): with Dh = 32 two heads share one staged tile and are processed back to back (the
 // second head is the +64-byte K-slice / N-slice of the same swizzled rows).  Rows past the end of the sequence inside the
 // last 32-row box belong to the next sequence (or are zero-filled past T): finite values whose score columns are masked.
+// Optional phase timing (-DEAVIT_TRACE, tools/att_trace.py): clock64 deltas of block 0 / thread 0 accumulated per phase.
+#ifdef EAVIT_TRACE
+__device__ long long g_att_trace[32];
+#define TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long _t = clock64(); g_att_trace[i] += _t - tr_prev; tr_prev = _t; } } while (0)
+#else
+#define TR(i) do { } while (0)
+#endif
 constexpr int BOX_ROWS = 32;
 constexpr int BOX_BYTES = BOX_ROWS * ROWB;
 
@@ -347,7 +354,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
     const int NKT = (S + 31) & ~31, NKP = (S + 15) & ~15;
     const int NQ = (S + 127) >> 7;                 // query tiles == key tiles
+#ifdef EAVIT_TRACE
+    long long tr_prev = clock64();
+#endif
     tc::mbar_wait(&bars[3], ph_ld);
+    TR(0);
     ph_ld ^= 1;
 
 #pragma unroll 1
@@ -362,19 +373,24 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       // ---- (1) S = Q_g K^T, (2) dP = dO_g V^T
       if (tid == 0) {
         tc::fence_after_sync();
+        TR(13);
         const uint32_t idesc = tc::make_idesc_bf16(128, NKT, 0, 0);
         const uint64_t aq = tc::make_sdesc_sw128(sQ + g * 128 * ROWB + hoff, 16, 1024), bk = tc::make_sdesc_sw128(sK + hoff, 16, 1024);
         const uint64_t ao = tc::make_sdesc_sw128(sDO + g * 128 * ROWB + hoff, 16, 1024), bv = tc::make_sdesc_sw128(sV + hoff, 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base, aq + (uint64_t)(k * 2), bk + (uint64_t)(k * 2), idesc, k > 0);
+        TR(14);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base + COL_DP, ao + (uint64_t)(k * 2), bv + (uint64_t)(k * 2), idesc, k > 0);
+        TR(15);
         tc::mma_commit(&bars[0]);
       }
+      TR(1);
       const int qrow = g * 128 + row_in_tile;
       const bool qok = qrow < S;
       const float l2 = qok ? lse[(size_t)(t0 + qrow) * H + h] * 1.4426950408889634f : INFINITY;   // invalid row: P~ = 0
       tc::mbar_wait(&bars[0], phase);
+      TR(2);
       tc::fence_after_sync();
       // the four warp groups split the NKT/16 column chunks of each row (3,4,3,4 chunks at NKT = 224)
       const int nch = NKT >> 4;
@@ -417,9 +433,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(0, 0, 0, 0);
       }
       sD[grp * 128 + row_in_tile] = dpart;
+      TR(3);
       tc::fence_before_sync();
       tc::fence_proxy_async();
       __syncthreads();
+      TR(4);
       // ---- (3) dV_kt = P~^T dO_g   (S columns are dead now: accumulators overlay them)
       if (tid == 0) {
         tc::fence_after_sync();
@@ -433,8 +451,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
         tc::mma_commit(&bars[1]);
       }
+      TR(5);
       const float Di = (sD[row_in_tile] + sD[128 + row_in_tile]) + (sD[256 + row_in_tile] + sD[384 + row_in_tile]);
       tc::mbar_wait(&bars[1], phase);             // dV has consumed P~: the buffer can take dS
+      TR(6);
       tc::fence_after_sync();
       // ---- pass 2: dS = P~ (dP - D) -> smem
       if (rows_live) {
@@ -456,9 +476,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
         });
       }
+      TR(7);
       tc::fence_before_sync();
       tc::fence_proxy_async();
       __syncthreads();
+      TR(8);
       // ---- (4) dK_kt = dS^T Q_g ; (5) dQ_g = dS K
       if (tid == 0) {
         tc::fence_after_sync();
@@ -478,7 +500,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         }
         tc::mma_commit(&bars[2]);
       }
+      TR(9);
       tc::mbar_wait(&bars[2], phase);
+      TR(10);
       if (tid == 0 && hd == HPB - 1 && g == NQ - 1 && item + (int)gridDim.x < n_items)
         issue_loads(item + gridDim.x);            // every MMA on this item's operands is done: refill during the drain
       tc::fence_after_sync();
@@ -520,9 +544,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
         }
       }
+      TR(11);
       tc::fence_before_sync();
       phase ^= 1;
       __syncthreads();                              // TMEM and smem free for the next tile / head / item
+      TR(12);
     }
     // ---- store this thread's half key row
     const int krow = kt * 128 + row_in_tile;
@@ -611,3 +637,12 @@ extern "C" int eavit_attention_bwd_tc(const void* qkv, const void* dout, const f
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
+
+#ifdef EAVIT_TRACE
+extern "C" int eavit_debug_att_trace(long long* host32, int reset) {
+  if (reset) { long long z[32] = {0}; cudaMemcpyToSymbol(eavit::g_att_trace, z, sizeof(z)); return 0; }
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host32, eavit::g_att_trace, 32 * sizeof(long long));
+  return 0;
+}
+#endif
