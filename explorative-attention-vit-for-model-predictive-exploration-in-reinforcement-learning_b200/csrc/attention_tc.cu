@@ -37,7 +37,7 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 // Optional phase timing (-DEAVIT_TRACE, tools/att_trace.py): clock64 deltas of block 0 / thread 0 accumulated per phase.
 #ifdef EAVIT_TRACE
 __device__ long long g_att_trace[32];
-#define TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long _t = clock64(); g_att_trace[i] += _t - tr_prev; tr_prev = _t; } } while (0)
+#define TR(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); tr_acc[i] += _t - tr_prev; tr_prev = _t; } } while (0)   // local accumulators: no global round trip inside the timed code
 #else
 #define TR(i) do { } while (0)
 #endif
@@ -349,13 +349,16 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       tc::tma_load_2d(smem + AttBwdSmem::OFF_DO + b * BOX_BYTES, &tmDO, &bars[3], hg * 64, tt + b * BOX_ROWS);
   };
   if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
+#ifdef EAVIT_TRACE
+  long long tr_acc[20] = {0}, tr_prev = 0;
+#endif
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int seq = item / HG, hg = item - seq * HG;
     const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
     const int NKT = (S + 31) & ~31, NKP = (S + 15) & ~15;
     const int NQ = (S + 127) >> 7;                 // query tiles == key tiles
 #ifdef EAVIT_TRACE
-    long long tr_prev = clock64();
+    tr_prev = clock64();
 #endif
     tc::mbar_wait(&bars[3], ph_ld);
     TR(0);
@@ -371,7 +374,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
     for (int g = 0; g < NQ; ++g) {
       // ---- (1) S = Q_g K^T, (2) dP = dO_g V^T
-      if (tid == 0) {
+      if (warp == 0 && tc::elect_one()) {      // warp-uniform election: the MMAs issue without a per-lane replay loop
         tc::fence_after_sync();
         TR(13);
         const uint32_t idesc = tc::make_idesc_bf16(128, NKT, 0, 0);
@@ -388,23 +391,24 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       TR(1);
       const int qrow = g * 128 + row_in_tile;
       const bool qok = qrow < S;
+      const int kq = (min(128, S - g * 128) + 15) >> 4;   // 16-row K steps of the dK / dV MMAs that hold valid queries
       const float l2 = qok ? lse[(size_t)(t0 + qrow) * H + h] * 1.4426950408889634f : INFINITY;   // invalid row: P~ = 0
       tc::mbar_wait(&bars[0], phase);
       TR(2);
       tc::fence_after_sync();
-      // the four warp groups split the NKT/16 column chunks of each row (3,4,3,4 chunks at NKT = 224)
-      const int nch = NKT >> 4;
-      const int cbeg = ((grp * nch) >> 2) << 4, cend = (((grp + 1) * nch) >> 2) << 4;
+      // the four warp groups split the NKT/8 column chunks of each row evenly (7 chunks of 8 at NKT = 224)
+      const int nch = NKT >> 3;
+      const int cbeg = ((grp * nch) >> 2) << 3, cend = (((grp + 1) * nch) >> 2) << 3;
       const bool rows_live = g * 128 + quad * 32 < S;   // warp-uniform: any valid query row in this warp
       // ---- pass 1: P~ -> smem, partial D  (TMEM loads of chunk i+1 in flight while chunk i is processed)
       float dpart = 0.f;
       if (rows_live) {
-        tc::tmem_stream16x2(lane_base, COL_DP, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
-          uint32_t pk[8];
+        tc::tmem_stream16x2<8>(lane_base, COL_DP, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
+          uint32_t pk[4];
           float d0 = 0.f, d1 = 0.f;
-          if (c0 + 16 <= S) {
+          if (c0 + 8 <= S) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
+            for (int j = 0; j < 8; j += 2) {
               const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2));
               const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2));
               pk[j >> 1] = pack_bf16x2(p0, p1);
@@ -413,7 +417,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
+            for (int j = 0; j < 8; j += 2) {
               const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
               const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
               pk[j >> 1] = pack_bf16x2(p0, p1);
@@ -422,10 +426,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             }
           }
           dpart += d0 + d1;
-          uint8_t* a = pbuf + (c0 >> 6) * P_SLAB;
-          const int cb = (c0 & 63) >> 3;
-          *reinterpret_cast<uint4*>(a + sw_off(row_in_tile, cb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(a + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         });
       } else {
         // no valid query row in this warp: its P~ / dS rows are zero (they feed the dK / dV sums over queries)
@@ -439,12 +440,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       __syncthreads();
       TR(4);
       // ---- (3) dV_kt = P~^T dO_g   (S columns are dead now: accumulators overlay them)
-      if (tid == 0) {
+      if (warp == 0 && tc::elect_one()) {      // warp-uniform election: the MMAs issue without a per-lane replay loop
         tc::fence_after_sync();
         const uint32_t idesc = tc::make_idesc_bf16(128, DH, 1, 1);
         for (int t = 0; t < NQ; ++t)
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
+          for (int kk = 0; kk < kq; ++kk) {          // K dimension = the valid query rows of this tile only (the rest of P~ is zero)
             const uint64_t a = tc::make_sdesc_sw128(sP + 2 * t * P_SLAB + kk * 2048, P_SLAB, 1024);
             const uint64_t b = tc::make_sdesc_sw128(sDO + g * 128 * ROWB + kk * 2048 + hoff, 8192, 1024);
             tc::mma_bf16_ss(tmem_base + COL_DV + t * 64, a, b, idesc, kk > 0);
@@ -458,22 +458,17 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       tc::fence_after_sync();
       // ---- pass 2: dS = P~ (dP - D) -> smem
       if (rows_live) {
-        tc::tmem_stream16(lane_base + COL_DP, cbeg, cend, [&](const uint32_t* rp, int c0) {
-          uint8_t* a = pbuf + (c0 >> 6) * P_SLAB;
-          const int cb = (c0 & 63) >> 3;
+        tc::tmem_stream16<8>(lane_base + COL_DP, cbeg, cend, [&](const uint32_t* rp, int c0) {
+          uint8_t* addr = pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3);
+          const uint4 pa = *reinterpret_cast<uint4*>(addr);
+          const uint32_t pin[4] = {pa.x, pa.y, pa.z, pa.w};
+          uint32_t ds[4];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint8_t* addr = a + sw_off(row_in_tile, cb + hh);
-            const uint4 pa = *reinterpret_cast<uint4*>(addr);
-            const uint32_t pin[4] = {pa.x, pa.y, pa.z, pa.w};
-            uint32_t ds[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float px = __uint_as_float(pin[j] << 16), py = __uint_as_float(pin[j] & 0xffff0000u);
-              ds[j] = pack_bf16x2(px * (__uint_as_float(rp[8 * hh + 2 * j]) - Di), py * (__uint_as_float(rp[8 * hh + 2 * j + 1]) - Di));
-            }
-            *reinterpret_cast<uint4*>(addr) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+          for (int j = 0; j < 4; ++j) {
+            const float px = __uint_as_float(pin[j] << 16), py = __uint_as_float(pin[j] & 0xffff0000u);
+            ds[j] = pack_bf16x2(px * (__uint_as_float(rp[2 * j]) - Di), py * (__uint_as_float(rp[2 * j + 1]) - Di));
           }
+          *reinterpret_cast<uint4*>(addr) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
         });
       }
       TR(7);
@@ -482,12 +477,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       __syncthreads();
       TR(8);
       // ---- (4) dK_kt = dS^T Q_g ; (5) dQ_g = dS K
-      if (tid == 0) {
+      if (warp == 0 && tc::elect_one()) {      // warp-uniform election: the MMAs issue without a per-lane replay loop
         tc::fence_after_sync();
         const uint32_t idesc_t = tc::make_idesc_bf16(128, DH, 1, 1);
         for (int t = 0; t < NQ; ++t)
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
+          for (int kk = 0; kk < kq; ++kk) {
             const uint64_t a = tc::make_sdesc_sw128(sP + 2 * t * P_SLAB + kk * 2048, P_SLAB, 1024);
             const uint64_t b = tc::make_sdesc_sw128(sQ + g * 128 * ROWB + kk * 2048 + hoff, 8192, 1024);
             tc::mma_bf16_ss(tmem_base + COL_DK + t * 64, a, b, idesc_t, kk > 0);
@@ -568,6 +562,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     }
     }  // heads of the box
   }
+#ifdef EAVIT_TRACE
+  if (blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 20; ++i) g_att_trace[i] += tr_acc[i];
+#endif
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) {

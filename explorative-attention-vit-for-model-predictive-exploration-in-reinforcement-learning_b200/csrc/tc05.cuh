@@ -123,8 +123,14 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// wait::ld that also carries a data dependency on the 16 destination registers of an earlier tcgen05.ld, so that neither
+// wait::ld that also carries a data dependency on the destination registers of an earlier tcgen05.ld, so that neither
 // nvcc nor ptxas can schedule their first use above the wait (used by the software-pipelined TMEM readers).
+__device__ __forceinline__ void tmem_ld_wait_dep8(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
@@ -132,46 +138,52 @@ __device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t* r) {
                :
                : "memory");
 }
-// Software-pipelined reader of TMEM columns [cbeg, cend) (multiples of 16) of this thread's lane: the load of chunk
-// i+1 is in flight while f(regs, c0) consumes chunk i.  NSRC = 1: one accumulator; NSRC = 2: a second accumulator
-// `off2` columns further (S and dP of the attention backward) -> f(regs_a, regs_b, c0).
-template <typename F>
+template <int W> __device__ __forceinline__ void tmem_ld_w(uint32_t taddr, uint32_t* r) {
+  if constexpr (W == 8) tmem_ld_32x8(taddr, r); else tmem_ld_32x16(taddr, r);
+}
+template <int W> __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* r) {
+  if constexpr (W == 8) tmem_ld_wait_dep8(r); else tmem_ld_wait_dep16(r);
+}
+// Software-pipelined reader of TMEM columns [cbeg, cend) (multiples of W = 8 or 16) of this thread's lane: the load of
+// chunk i+1 is in flight while f(regs, c0) consumes chunk i.
+template <int W = 16, typename F>
 __device__ __forceinline__ void tmem_stream16(uint32_t addr, int cbeg, int cend, F&& f) {
-  uint32_t ra[16], rb[16];
+  uint32_t ra[W], rb[W];
   if (cbeg >= cend) return;
-  tmem_ld_32x16(addr + cbeg, ra);
-  tmem_ld_wait_dep16(ra);
-  for (int c0 = cbeg; c0 < cend; c0 += 32) {
-    const bool has_b = c0 + 16 < cend;
-    if (has_b) tmem_ld_32x16(addr + c0 + 16, rb);
+  tmem_ld_w<W>(addr + cbeg, ra);
+  tmem_ld_wait_dep<W>(ra);
+  for (int c0 = cbeg; c0 < cend; c0 += 2 * W) {
+    const bool has_b = c0 + W < cend;
+    if (has_b) tmem_ld_w<W>(addr + c0 + W, rb);
     f(ra, c0);
     if (!has_b) break;
-    tmem_ld_wait_dep16(rb);
-    const bool has_a = c0 + 32 < cend;
-    if (has_a) tmem_ld_32x16(addr + c0 + 32, ra);
-    f(rb, c0 + 16);
-    if (has_a) tmem_ld_wait_dep16(ra);
+    tmem_ld_wait_dep<W>(rb);
+    const bool has_a = c0 + 2 * W < cend;
+    if (has_a) tmem_ld_w<W>(addr + c0 + 2 * W, ra);
+    f(rb, c0 + W);
+    if (has_a) tmem_ld_wait_dep<W>(ra);
   }
 }
-template <typename F>
+// Two accumulators `off2` columns apart (S and dP of the attention backward) -> f(regs_a, regs_b, c0).
+template <int W = 16, typename F>
 __device__ __forceinline__ void tmem_stream16x2(uint32_t addr, uint32_t off2, int cbeg, int cend, F&& f) {
-  uint32_t ra[16], rb[16], pa[16], pb[16];
+  uint32_t ra[W], rb[W], pa[W], pb[W];
   if (cbeg >= cend) return;
-  tmem_ld_32x16(addr + cbeg, ra);
-  tmem_ld_32x16(addr + off2 + cbeg, pa);
-  tmem_ld_wait_dep16(ra);
-  tmem_ld_wait_dep16(pa);
-  for (int c0 = cbeg; c0 < cend; c0 += 32) {
-    const bool has_b = c0 + 16 < cend;
-    if (has_b) { tmem_ld_32x16(addr + c0 + 16, rb); tmem_ld_32x16(addr + off2 + c0 + 16, pb); }
+  tmem_ld_w<W>(addr + cbeg, ra);
+  tmem_ld_w<W>(addr + off2 + cbeg, pa);
+  tmem_ld_wait_dep<W>(ra);
+  tmem_ld_wait_dep<W>(pa);
+  for (int c0 = cbeg; c0 < cend; c0 += 2 * W) {
+    const bool has_b = c0 + W < cend;
+    if (has_b) { tmem_ld_w<W>(addr + c0 + W, rb); tmem_ld_w<W>(addr + off2 + c0 + W, pb); }
     f(ra, pa, c0);
     if (!has_b) break;
-    tmem_ld_wait_dep16(rb);
-    tmem_ld_wait_dep16(pb);
-    const bool has_a = c0 + 32 < cend;
-    if (has_a) { tmem_ld_32x16(addr + c0 + 32, ra); tmem_ld_32x16(addr + off2 + c0 + 32, pa); }
-    f(rb, pb, c0 + 16);
-    if (has_a) { tmem_ld_wait_dep16(ra); tmem_ld_wait_dep16(pa); }
+    tmem_ld_wait_dep<W>(rb);
+    tmem_ld_wait_dep<W>(pb);
+    const bool has_a = c0 + 2 * W < cend;
+    if (has_a) { tmem_ld_w<W>(addr + c0 + 2 * W, ra); tmem_ld_w<W>(addr + off2 + c0 + 2 * W, pa); }
+    f(rb, pb, c0 + W);
+    if (has_a) { tmem_ld_wait_dep<W>(ra); tmem_ld_wait_dep<W>(pa); }
   }
 }
 
