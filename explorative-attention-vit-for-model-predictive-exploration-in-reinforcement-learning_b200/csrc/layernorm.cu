@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy      (block partials -> one atomicAdd per column per CTA)
 template <typename DyT, int VPL>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restrict__ dy, long long lddy,
+__global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) layernorm_bwd_kernel(const DyT* __restrict__ dy, long long lddy,
                                                             const float* __restrict__ x, long long ldx,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd,
@@ -81,9 +81,35 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restric
   float4 ag[VPL], ab[VPL], ax[VPL];   // dgamma, dbeta, column sums of the output dx (bias gradient of the next GEMM)
 #pragma unroll
   for (int i = 0; i < VPL; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = ag[i]; ax[i] = ag[i]; }
-  // persistent grid-stride over rows: the dgamma/dbeta atomics are paid once per CTA, not once per 64 rows
-  for (int row = blockIdx.x * 8 + w; row < T; row += gridDim.x * 8) {
-    const float mu = mean[row], rs = rstd[row];
+  // persistent grid-stride over rows (the dgamma/dbeta atomics are paid once per CTA), with the NEXT row's operands
+  // loaded into a second register set before the current row's reductions: a warp keeps two rows (5 KB at D = 256)
+  // in flight instead of alternating between a load phase and a shuffle/compute phase
+  float4 gm[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = lane + 32 * i;
+    gm[i] = c < nv ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  constexpr bool kPrefetch = VPL <= 2;       // wider rows would not fit two register sets
+  struct Raw { float4 xv[VPL], r[VPL]; float mu, rs; float4 d32[sizeof(DyT) == 4 ? VPL : 1]; uint2 d16[sizeof(DyT) == 4 ? 1 : VPL]; };
+  auto load = [&](int row, Raw& R) {
+    R.mu = mean[row]; R.rs = rstd[row];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        if constexpr (sizeof(DyT) == 4) {
+          R.d32[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + (size_t)row * lddy) + c);
+        } else {
+          R.d16[i] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)row * lddy) + c);
+        }
+        R.xv[i] = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * ldx) + c);
+        if (dres != nullptr) R.r[i] = __ldg(reinterpret_cast<const float4*>(dres + (size_t)row * lddres) + c);
+      }
+    }
+  };
+  auto process = [&](int row, const Raw& R) {
+    const float mu = R.mu, rs = R.rs;
     float4 g[VPL], xh[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -92,16 +118,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restric
       if (c < nv) {
         float4 d;
         if constexpr (sizeof(DyT) == 4) {
-          d = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + (size_t)row * lddy) + c);
+          d = R.d32[i];
         } else {
-          const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)row * lddy) + c);
-          const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+          const float2 lo = unpack_bf16x2(R.d16[i].x), hi = unpack_bf16x2(R.d16[i].y);
           d = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * ldx) + c);
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 xv = R.xv[i];
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
         s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
         s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
         ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
@@ -116,14 +140,36 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const DyT* __restric
       if (c < nv) {
         float4 o = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
                                rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
-        if (dres != nullptr) {
-          const float4 r = __ldg(reinterpret_cast<const float4*>(dres + (size_t)row * lddres) + c);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
+        if (dres != nullptr) { o.x += R.r[i].x; o.y += R.r[i].y; o.z += R.r[i].z; o.w += R.r[i].w; }
         ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
         if (dx != nullptr) *(reinterpret_cast<float4*>(dx + (size_t)row * lddx) + c) = o;
         if (dx_bf16 != nullptr)
           *(reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * lddxb) + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  };
+  {
+    const int stride = gridDim.x * 8;
+    int row = blockIdx.x * 8 + w;
+    if constexpr (kPrefetch) {
+      Raw A, B;
+      if (row < T) load(row, A);
+      while (row < T) {
+        int nrow = row + stride;
+        if (nrow < T) load(nrow, B);
+        process(row, A);
+        row = nrow;
+        if (row >= T) break;
+        nrow = row + stride;
+        if (nrow < T) load(nrow, A);
+        process(row, B);
+        row = nrow;
+      }
+    } else {
+      for (; row < T; row += stride) {
+        Raw A;
+        load(row, A);
+        process(row, A);
       }
     }
   }
@@ -248,8 +294,6 @@ int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const floa
   EAVIT_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && lddres % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)8 * 3 * D * sizeof(float);
-  int grid = cdiv(T, 8);
-  if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
   const int vpl = cdiv(D / 4, 32);
   static bool attr_done = false;
   if (!attr_done) {
@@ -257,7 +301,10 @@ int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const floa
     EAVIT_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
     attr_done = true;
   }
-#define EAVIT_LN_BWD(DT, V) layernorm_bwd_kernel<DT, V><<<grid, 256, smem, st>>>((const DT*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, dxsum, T, D)
+  // persistent grid = exactly the CTAs that are co-resident (a partial second wave would run at a fraction of the bandwidth)
+#define EAVIT_LN_BWD(DT, V) do { int occ = 1; EAVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_bwd_kernel<DT, V>, 256, smem)); \
+    int grid = cdiv(T, 8); if (occ < 1) occ = 1; if (grid > occ * kNumSMs) grid = occ * kNumSMs; \
+    layernorm_bwd_kernel<DT, V><<<grid, 256, smem, st>>>((const DT*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, dxsum, T, D); } while (0)
 #define EAVIT_LN_BWD_V(DT) do { if (vpl <= 1) EAVIT_LN_BWD(DT, 1); else if (vpl <= 2) EAVIT_LN_BWD(DT, 2); else if (vpl <= 4) EAVIT_LN_BWD(DT, 4); else EAVIT_LN_BWD(DT, 8); } while (0)
   if (dy_dtype == EAVIT_F32) EAVIT_LN_BWD_V(float);
   else if (dy_dtype == EAVIT_BF16) EAVIT_LN_BWD_V(__nv_bfloat16);
