@@ -8,37 +8,49 @@
 namespace eavit {
 
 // col[(b,oy,ox), c*KH*KW + i*KW + j] = in[b, oy*s+i, ox*s+j, c]
+// One CTA per (sample, output row): the KH input rows it needs are staged in shared memory with coalesced loads, the
+// (c, ki, kj) -> patch offset table is computed once per CTA (no per-element integer division), and every thread
+// emits 16-byte stores of 8 consecutive K entries (hi / hi / lo segments of the bf16x3 operand when split3).
 template <typename InT>
 __global__ void __launch_bounds__(256) im2col_kernel(const InT* __restrict__ in, const long long* __restrict__ sample_idx, int B, int H, int W, int C, int KH, int KW,
                                                      int stride, int OH, int OW, __nv_bfloat16* __restrict__ col, int split3) {
+  extern __shared__ float im_sm[];
   const int K = C * KH * KW;
-  const long long total = (long long)B * OH * OW * (K / 2);
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int k2 = (int)(i % (K / 2));
-  const long long m = i / (K / 2);
-  const int ox = (int)(m % OW), oy = (int)((m / OW) % OH);
-  const long long b = m / ((long long)OW * OH);
-  const long long sb = sample_idx ? sample_idx[b] : b;
-  float v[2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int k = 2 * k2 + t;
-    const int c = k / (KH * KW), r = k % (KH * KW), ki = r / KW, kj = r % KW;
-    const size_t idx = (((size_t)sb * H + (oy * stride + ki)) * W + (ox * stride + kj)) * C + c;
-    if constexpr (sizeof(InT) == 4) v[t] = in[idx]; else v[t] = __bfloat162float(in[idx]);
+  const int npatch = KH * W * C;
+  float* patch = im_sm;                                   // [KH][W][C]
+  int* koff = reinterpret_cast<int*>(im_sm + npatch);     // [K]
+  const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
+  const long long sb = sample_idx ? sample_idx[b] : (long long)b;
+  const InT* src = in + ((size_t)sb * H + (size_t)oy * stride) * W * C;
+  for (int i = threadIdx.x; i < npatch; i += blockDim.x) {
+    if constexpr (sizeof(InT) == 4) patch[i] = __ldg(src + i); else patch[i] = __bfloat162float(src[i]);
   }
-  if (!split3) {
-    *reinterpret_cast<uint32_t*>(col + (size_t)m * K + 2 * k2) = pack_bf16x2(v[0], v[1]);
-  } else {
-    // bf16x3 operand: [hi | hi | lo] so that A3 . B3^T (B3 = [hi | lo | hi]) = hi*hi + hi*lo + lo*hi
-    const uint32_t hi = pack_bf16x2(v[0], v[1]);
-    const float2 h = unpack_bf16x2(hi);
-    const uint32_t lo = pack_bf16x2(v[0] - h.x, v[1] - h.y);
-    __nv_bfloat16* row = col + (size_t)m * 3 * K;
-    *reinterpret_cast<uint32_t*>(row + 2 * k2) = hi;
-    *reinterpret_cast<uint32_t*>(row + K + 2 * k2) = hi;
-    *reinterpret_cast<uint32_t*>(row + 2 * K + 2 * k2) = lo;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int c = k / (KH * KW), r = k - c * (KH * KW), ki = r / KW, kj = r - ki * KW;
+    koff[k] = (ki * W + kj) * C + c;
+  }
+  __syncthreads();
+  const int K8 = K >> 3;
+  const size_t ldc = split3 ? (size_t)3 * K : (size_t)K;
+  for (int e = threadIdx.x; e < OW * K8; e += blockDim.x) {
+    const int ox = e / K8, k0 = (e - ox * K8) << 3;
+    const float* p = patch + ox * stride * C;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[koff[k0 + j]];
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      lo[j] = pack_bf16x2(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u));
+    }
+    __nv_bfloat16* row = col + ((size_t)blockIdx.x * OW + ox) * ldc + k0;
+    *reinterpret_cast<uint4*>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (split3) {
+      // bf16x3 operand: [hi | hi | lo] so that A3 . B3^T (B3 = [hi | lo | hi]) = hi*hi + hi*lo + lo*hi
+      *reinterpret_cast<uint4*>(row + K) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(row + 2 * K) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 
@@ -69,32 +81,43 @@ __global__ void __launch_bounds__(256) nhwc_to_flat_f32_kernel(const float* __re
 }
 
 // d_in[b,y,x,c] = lrelu'(act[b,y,x,c]) * sum_{i,j} dcol[(b,(y-i)/s,(x-j)/s), c*KH*KW + i*KW + j]
+// One CTA per (sample, input row): the <= ceil(KH/s) output rows of dcol that touch it are staged in shared memory with
+// coalesced 16-byte loads (the direct gather read 2 bytes per 32-byte sector), then every thread sums its taps.
 __global__ void __launch_bounds__(256) col2im_lrelu_kernel(const __nv_bfloat16* __restrict__ dcol, const __nv_bfloat16* __restrict__ act,
                                                            int B, int H, int W, int C, int KH, int KW, int stride, int OH,
                                                            int OW, __nv_bfloat16* __restrict__ din) {
-  const long long total = (long long)B * H * W * C;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % C);
-  const int x = (int)((i / C) % W), y = (int)((i / ((long long)C * W)) % H);
-  const long long b = i / ((long long)C * W * H);
+  extern __shared__ __align__(16) unsigned char c2_sm_raw[];
+  __nv_bfloat16* rows = reinterpret_cast<__nv_bfloat16*>(c2_sm_raw);     // [n_oy][OW][K]
   const int K = C * KH * KW;
-  float acc = 0.f;
-  for (int ki = 0; ki < KH; ++ki) {
-    const int ty = y - ki;
-    if (ty < 0 || ty % stride != 0) continue;
-    const int oy = ty / stride;
-    if (oy >= OH) continue;
-    for (int kj = 0; kj < KW; ++kj) {
-      const int tx = x - kj;
-      if (tx < 0 || tx % stride != 0) continue;
-      const int ox = tx / stride;
-      if (ox >= OW) continue;
-      acc += __bfloat162float(dcol[(((size_t)b * OH + oy) * OW + ox) * K + c * KH * KW + ki * KW + kj]);
-    }
+  const int b = blockIdx.x / H, y = blockIdx.x - b * H;
+  int oy_lo = y - KH + 1;
+  oy_lo = oy_lo <= 0 ? 0 : (oy_lo + stride - 1) / stride;
+  int oy_hi = y / stride;
+  if (oy_hi > OH - 1) oy_hi = OH - 1;
+  const int n_oy = oy_hi - oy_lo + 1;                                      // may be <= 0 at the bottom border
+  if (n_oy > 0) {
+    const uint4* src = reinterpret_cast<const uint4*>(dcol + ((size_t)b * OH + oy_lo) * OW * K);
+    uint4* dst = reinterpret_cast<uint4*>(rows);
+    const int n16 = n_oy * OW * K / 8;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
   }
-  const float a = __bfloat162float(act[i]);
-  din[i] = __float2bfloat16(a > 0.f ? acc : 0.01f * acc);
+  __syncthreads();
+  const size_t base = ((size_t)b * H + y) * W * C;
+  for (int e = threadIdx.x; e < W * C; e += blockDim.x) {
+    const int x = e / C, c = e - x * C;
+    int ox_lo = x - KW + 1;
+    ox_lo = ox_lo <= 0 ? 0 : (ox_lo + stride - 1) / stride;
+    int ox_hi = x / stride;
+    if (ox_hi > OW - 1) ox_hi = OW - 1;
+    float acc = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const int ki = y - oy * stride;
+      const __nv_bfloat16* r = rows + (size_t)(oy - oy_lo) * OW * K + c * KH * KW + ki * KW;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) acc += __bfloat162float(r[ox * K + (x - ox * stride)]);
+    }
+    const float a = __bfloat162float(act[base + e]);
+    din[base + e] = __float2bfloat16(a > 0.f ? acc : 0.01f * acc);
+  }
 }
 
 // Flatten of NCHW: flat[b, c*HW + p] = act[b, p, c]   (model.py:387 Flatten after NHWC conv output)
@@ -126,12 +149,15 @@ extern "C" {
 
 int eavit_im2col(const void* in, int in_dtype, const long long* sample_idx, int B, int H, int W, int C, int KH, int KW, int stride, void* col,
                  int split3, void* stream) {
-  EAVIT_CHECK_ARG(in && col && B > 0 && H >= KH && W >= KW && stride > 0 && (C * KH * KW) % 2 == 0);
+  EAVIT_CHECK_ARG(in && col && B > 0 && H >= KH && W >= KW && stride > 0 && (C * KH * KW) % 8 == 0);
+  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(col) & 15) == 0);
   const int OH = (H - KH) / stride + 1, OW = (W - KW) / stride + 1;
-  const long long total = (long long)B * OH * OW * (C * KH * KW / 2);
+  const size_t smem = ((size_t)KH * W * C + (size_t)C * KH * KW) * 4;
+  EAVIT_CHECK_ARG(smem <= 48 * 1024);
+  const int grid = B * OH;
   cudaStream_t st = (cudaStream_t)stream;
-  if (in_dtype == EAVIT_F32) im2col_kernel<float><<<cdiv(total, 256), 256, 0, st>>>((const float*)in, sample_idx, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)col, split3);
-  else if (in_dtype == EAVIT_BF16) im2col_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, st>>>((const __nv_bfloat16*)in, sample_idx, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)col, split3);
+  if (in_dtype == EAVIT_F32) im2col_kernel<float><<<grid, 256, smem, st>>>((const float*)in, sample_idx, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)col, split3);
+  else if (in_dtype == EAVIT_BF16) im2col_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)in, sample_idx, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)col, split3);
   else { set_error("im2col: bad dtype %d", in_dtype); return EAVIT_EINVAL; }
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
@@ -155,8 +181,11 @@ int eavit_col2im_lrelu(const void* dcol, const void* act, int B, int H, int W, i
                        void* stream) {
   EAVIT_CHECK_ARG(dcol && act && din && B > 0 && H >= KH && W >= KW && stride > 0);
   const int OH = (H - KH) / stride + 1, OW = (W - KW) / stride + 1;
-  const long long total = (long long)B * H * W * C;
-  col2im_lrelu_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol, (const __nv_bfloat16*)act, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)din);
+  const int K = C * KH * KW;
+  EAVIT_CHECK_ARG(K % 8 == 0 && (reinterpret_cast<uintptr_t>(dcol) & 15) == 0);
+  const size_t smem = (size_t)((KH + stride - 1) / stride) * OW * K * 2;
+  EAVIT_CHECK_ARG(smem <= 48 * 1024);
+  col2im_lrelu_kernel<<<B * H, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol, (const __nv_bfloat16*)act, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)din);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
