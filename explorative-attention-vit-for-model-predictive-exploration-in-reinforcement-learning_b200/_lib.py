@@ -25,7 +25,8 @@ class GemmArgs(ctypes.Structure):
         ("bias", ctypes.c_void_p), ("aux_bf16", ctypes.c_void_p), ("residual", ctypes.c_void_p),
         ("out_f32", ctypes.c_void_p), ("out_bf16", ctypes.c_void_p), ("out_pre_bf16", ctypes.c_void_p),
         ("colsum", ctypes.c_void_p),
-        ("ldc", ctypes.c_longlong), ("act", ctypes.c_int), ("atomic_f32", ctypes.c_int), ("split_k", ctypes.c_int),
+        ("ldc", ctypes.c_longlong), ("drop_p", ctypes.c_float), ("drop_seed", ctypes.c_ulonglong),
+        ("act", ctypes.c_int), ("atomic_f32", ctypes.c_int), ("split_k", ctypes.c_int),
     ]
 
 

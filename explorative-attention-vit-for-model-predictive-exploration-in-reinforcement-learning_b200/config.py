@@ -81,8 +81,16 @@ class HotPathConfig:
     mlp_dim: int
     use_explorative: bool
     ln_eps: float
-    dropout: float
-    emb_dropout: float
+    dropout: float            # after to_out / MLP2 (vit.py:33,56; HF hidden_dropout_prob)
+    emb_dropout: float        # after the positional add (vit.py:158)
+    attn_dropout: float = -1.0   # on the attention probabilities (vit.py:45); < 0: same as `dropout`
+    act_dropout: float = -1.0    # after GELU (vit.py:31); < 0: same as `dropout`; HF has none
+
+    def __post_init__(self):
+        if self.attn_dropout < 0:
+            self.attn_dropout = self.dropout
+        if self.act_dropout < 0:
+            self.act_dropout = self.dropout
 
     @property
     def n_patches(self) -> int:
@@ -109,4 +117,5 @@ class HotPathConfig:
             patch=int(c["ViTHG_patch_size"]), dim=hidden, depth=int(c["ViTHG_num_hidden_layers"]), heads=heads,
             dim_head=hidden // heads, mlp_dim=int(c["ViTHG_intermediate_size"]),
             use_explorative=Config(c).getboolean("ViTHG_use_explorativeAttn"), ln_eps=float(c["ViTHG_layer_norm_eps"]),
-            dropout=float(c["ViTHG_hidden_dropout_prob"]), emb_dropout=float(c["ViTHG_hidden_dropout_prob"]))
+            dropout=float(c["ViTHG_hidden_dropout_prob"]), emb_dropout=float(c["ViTHG_hidden_dropout_prob"]),
+            attn_dropout=float(c["ViTHG_attention_probs_dropout_prob"]), act_dropout=0.0)

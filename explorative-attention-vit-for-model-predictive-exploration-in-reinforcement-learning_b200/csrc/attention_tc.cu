@@ -54,10 +54,12 @@ struct AttSmem {
   static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
-template <int DH>
+// DROP: nn.Dropout on the attention probabilities (vit.py:45,70 / HF attention_probs_dropout_prob): the row sum (softmax
+// denominator) uses the full probabilities, the P.V operand is masked.  Mask element = (token row t0 + q, column h*256 + k).
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ seq_start, int nseq, int H,
-                        float scale, __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+                        float scale, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, const DropCfg drop) {
   constexpr int HPB = 64 / DH;                      // heads per 128-byte box row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -176,6 +178,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
         const float mb = mx * c2;
         float sum = 0.f;
         uint8_t* pbase = smem + AttSmem::OFF_P + g * 4 * P_SLAB;
+        uint32_t rk = 0;
+        if constexpr (DROP) rk = drop_row_key(drop, (uint32_t)(t0 + xrow));
+        const uint32_t hcol = (uint32_t)h * 256u;
         if (rows_live) {
           tc::tmem_stream16(lane_addr, cbeg, cbeg + half, [&](const uint32_t* r, int c0) {
             if (c0 >= NKP) return;                       // beyond the keys the P.V MMA reads
@@ -184,18 +189,26 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
               float s0 = 0.f, s1 = 0.f;
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb));
+                float p0 = ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb));
+                float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb));
                 s0 += p0; s1 += p1;
+                if constexpr (DROP) {
+                  const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+                  p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
+                }
                 pk[j >> 1] = pack_bf16x2(p0, p1);
               }
               sum += s0 + s1;
             } else {
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb)) : 0.f;
-                const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb)) : 0.f;
+                float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb)) : 0.f;
+                float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb)) : 0.f;
                 sum += p0 + p1;
+                if constexpr (DROP) {
+                  const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+                  p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
+                }
                 pk[j >> 1] = pack_bf16x2(p0, p1);
               }
             }
@@ -292,11 +305,14 @@ struct AttBwdSmem {
   static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
-template <int DH>
+// DROP: with dropout mask M on the probabilities, dV = (P o M)^T dO, D_i = sum_j P_ij M_ij dP_ij and dS = P o (M o dP - D):
+// pass 1 stages the MASKED P~ for the dV MMA; pass 2 needs the unmasked P again and recomputes it from S, which stays
+// intact because the dV accumulators live in the last 64 TMEM columns instead of overlaying S.
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const float* __restrict__ lse, const int* __restrict__ seq_start, int nseq, int H, float scale,
-                        __nv_bfloat16* __restrict__ dqkv) {
+                        __nv_bfloat16* __restrict__ dqkv, const DropCfg drop) {
   constexpr int HPB = 64 / DH;                      // heads per 128-byte box row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -326,7 +342,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   const int ldq = 3 * H * DH;
   const int HG = H / HPB;
   const float c2 = scale * 1.4426950408889634f;
-  constexpr int COL_DP = 224, COL_DV = 0, COL_DK = 128, COL_DQ = 256;
+  constexpr int COL_DP = 224, COL_DV = 448, COL_DK = 0, COL_DQ = 128;   // dV: 2 x Dh (Dh = 32) or 1 x 64 columns at 448
   constexpr int HC = DH / 2;                       // accumulator columns per thread
   uint32_t phase = 0, ph_ld = 0;
   const int n_items = nseq * HG;
@@ -402,6 +418,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const bool rows_live = g * 128 + quad * 32 < S;   // warp-uniform: any valid query row in this warp
       // ---- pass 1: P~ -> smem, partial D  (TMEM loads of chunk i+1 in flight while chunk i is processed)
       float dpart = 0.f;
+      uint32_t rk = 0;
+      if constexpr (DROP) rk = drop_row_key(drop, (uint32_t)(t0 + qrow));
+      const uint32_t hcol = (uint32_t)h * 256u;
       if (rows_live) {
         tc::tmem_stream16x2<8>(lane_base, COL_DP, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
           uint32_t pk[4];
@@ -409,8 +428,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           if (c0 + 8 <= S) {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2));
+              float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2));
+              float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2));
+              if constexpr (DROP) {
+                const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+                p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
+              }
               pk[j >> 1] = pack_bf16x2(p0, p1);
               d0 = fmaf(p0, __uint_as_float(rp[j]), d0);
               d1 = fmaf(p1, __uint_as_float(rp[j + 1]), d1);
@@ -418,8 +441,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           } else {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
-              const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
-              const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
+              float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
+              float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
+              if constexpr (DROP) {
+                const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+                p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
+              }
               pk[j >> 1] = pack_bf16x2(p0, p1);
               d0 = fmaf(p0, __uint_as_float(rp[j]), d0);
               d1 = fmaf(p1, __uint_as_float(rp[j + 1]), d1);
@@ -439,7 +466,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       tc::fence_proxy_async();
       __syncthreads();
       TR(4);
-      // ---- (3) dV_kt = P~^T dO_g   (S columns are dead now: accumulators overlay them)
+      // ---- (3) dV_kt = P~^T dO_g   (accumulators in the spare TMEM columns 448..511)
       if (warp == 0 && tc::elect_one()) {      // warp-uniform election: the MMAs issue without a per-lane replay loop
         tc::fence_after_sync();
         const uint32_t idesc = tc::make_idesc_bf16(128, DH, 1, 1);
@@ -447,7 +474,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           for (int kk = 0; kk < kq; ++kk) {          // K dimension = the valid query rows of this tile only (the rest of P~ is zero)
             const uint64_t a = tc::make_sdesc_sw128(sP + 2 * t * P_SLAB + kk * 2048, P_SLAB, 1024);
             const uint64_t b = tc::make_sdesc_sw128(sDO + g * 128 * ROWB + kk * 2048 + hoff, 8192, 1024);
-            tc::mma_bf16_ss(tmem_base + COL_DV + t * 64, a, b, idesc, kk > 0);
+            tc::mma_bf16_ss(tmem_base + COL_DV + t * DH, a, b, idesc, kk > 0);
           }
         tc::mma_commit(&bars[1]);
       }
@@ -457,7 +484,20 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       TR(6);
       tc::fence_after_sync();
       // ---- pass 2: dS = P~ (dP - D) -> smem
-      if (rows_live) {
+      if (rows_live && DROP) {
+        tc::tmem_stream16x2<8>(lane_base, COL_DP, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
+          uint32_t ds[4];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
+            const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
+            const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+            ds[j >> 1] = pack_bf16x2(p0 * fmaf(drop_even(drop, bits), __uint_as_float(rp[j]), -Di),
+                                     p1 * fmaf(drop_odd(drop, bits), __uint_as_float(rp[j + 1]), -Di));
+          }
+          *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+        });
+      } else if (rows_live) {
         tc::tmem_stream16<8>(lane_base + COL_DP, cbeg, cend, [&](const uint32_t* rp, int c0) {
           uint8_t* addr = pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3);
           const uint4 pa = *reinterpret_cast<uint4*>(addr);
@@ -521,13 +561,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         }
         if (kt < NQ) {
           if constexpr (HC == 16) {
-            tc::tmem_ld_32x16(lane_base + COL_DV + kt * 64 + kh * HC, r);
+            tc::tmem_ld_32x16(lane_base + COL_DV + kt * DH + kh * HC, r);
             tc::tmem_ld_32x16(lane_base + COL_DK + kt * 64 + kh * HC, r + 16);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) { accV[j] += __uint_as_float(r[j]); accK[j] += __uint_as_float(r[16 + j]); }
           } else {
-            tc::tmem_ld_32x32(lane_base + COL_DV + kt * 64 + kh * HC, r);
+            tc::tmem_ld_32x32(lane_base + COL_DV + kt * DH + kh * HC, r);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) accV[j % HC] += (j < HC) ? __uint_as_float(r[j]) : 0.f;
@@ -585,55 +625,66 @@ static int attention_tmaps(const void* qkv, const void* dout, long long T, int H
   return rc;
 }
 
+template <int DH, bool DROP>
+static int launch_att_fwd(const CUtensorMap& tq, const int* seq_start, int nseq, int H, float scale, void* out, float* lse,
+                          const DropCfg& drop, int grid, cudaStream_t st) {
+  static bool done = false;
+  if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::TOTAL)); done = true; }
+  attention_fwd_tc_kernel<DH, DROP><<<grid, ATC_THREADS, AttSmem::TOTAL, st>>>(tq, seq_start, nseq, H, scale, (__nv_bfloat16*)out, lse, drop);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+template <int DH, bool DROP>
+static int launch_att_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const float* lse, const int* seq_start, int nseq, int H,
+                          float scale, void* dqkv, const DropCfg& drop, int grid, cudaStream_t st) {
+  static bool done = false;
+  if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttBwdSmem::TOTAL)); done = true; }
+  attention_bwd_tc_kernel<DH, DROP><<<grid, ATC_THREADS, AttBwdSmem::TOTAL, st>>>(tq, tdo, lse, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv, drop);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
 // total tokens = seq_start[nseq]; the host mirror passes it so that no device read-back is needed
 extern "C" int eavit_attention_fwd_tc(const void* qkv, const int* seq_start, int nseq, int max_len, long long total_tokens,
-                                      int H, int Dh, float scale, void* out, float* lse, void* stream) {
+                                      int H, int Dh, float scale, void* out, float* lse, float drop_p,
+                                      unsigned long long drop_seed, void* stream) {
   EAVIT_CHECK_ARG(qkv && seq_start && out && nseq > 0 && H > 0 && total_tokens > 0);
   EAVIT_CHECK_ARG(max_len > 0 && max_len <= ATC_MAXKEYS);
   EAVIT_CHECK_ARG((Dh == 32 && H % 2 == 0) || Dh == 64);
+  EAVIT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tq, tdo;
   int rc = attention_tmaps(qkv, nullptr, total_tokens, H, Dh, &tq, &tdo);
   if (rc) return rc;
+  const DropCfg drop = make_drop(drop_p, drop_seed);
   const int items = nseq * (H / (64 / Dh));
   const int grid = items < kNumSMs ? items : kNumSMs;
-  if (Dh == 32) {
-    static bool done = false;
-    if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::TOTAL)); done = true; }
-    attention_fwd_tc_kernel<32><<<grid, ATC_THREADS, AttSmem::TOTAL, st>>>(tq, seq_start, nseq, H, scale, (__nv_bfloat16*)out, lse);
-  } else {
-    static bool done = false;
-    if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::TOTAL)); done = true; }
-    attention_fwd_tc_kernel<64><<<grid, ATC_THREADS, AttSmem::TOTAL, st>>>(tq, seq_start, nseq, H, scale, (__nv_bfloat16*)out, lse);
-  }
-  EAVIT_LAUNCH_OK();
-  return EAVIT_OK;
+  if (Dh == 32) return drop.thresh ? launch_att_fwd<32, true>(tq, seq_start, nseq, H, scale, out, lse, drop, grid, st)
+                                   : launch_att_fwd<32, false>(tq, seq_start, nseq, H, scale, out, lse, drop, grid, st);
+  return drop.thresh ? launch_att_fwd<64, true>(tq, seq_start, nseq, H, scale, out, lse, drop, grid, st)
+                     : launch_att_fwd<64, false>(tq, seq_start, nseq, H, scale, out, lse, drop, grid, st);
 }
 
 extern "C" int eavit_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const int* seq_start, int nseq,
-                                      int max_len, long long total_tokens, int H, int Dh, float scale, void* dqkv, void* stream) {
+                                      int max_len, long long total_tokens, int H, int Dh, float scale, void* dqkv, float drop_p,
+                                      unsigned long long drop_seed, void* stream) {
   EAVIT_CHECK_ARG(qkv && dout && lse && seq_start && dqkv && nseq > 0 && H > 0 && total_tokens > 0);
   EAVIT_CHECK_ARG(max_len > 0 && max_len <= ATC_MAXKEYS);
   EAVIT_CHECK_ARG((Dh == 32 && H % 2 == 0) || (Dh == 64 && max_len <= 128));
+  EAVIT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tq, tdo;
   int rc = attention_tmaps(qkv, dout, total_tokens, H, Dh, &tq, &tdo);
   if (rc) return rc;
+  const DropCfg drop = make_drop(drop_p, drop_seed);
   const int items = nseq * (H / (64 / Dh));
   const int grid = items < kNumSMs ? items : kNumSMs;
-  if (Dh == 32) {
-    static bool done = false;
-    if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttBwdSmem::TOTAL)); done = true; }
-    attention_bwd_tc_kernel<32><<<grid, ATC_THREADS, AttBwdSmem::TOTAL, st>>>(tq, tdo, lse, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv);
-  } else {
-    static bool done = false;
-    if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttBwdSmem::TOTAL)); done = true; }
-    attention_bwd_tc_kernel<64><<<grid, ATC_THREADS, AttBwdSmem::TOTAL, st>>>(tq, tdo, lse, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv);
-  }
-  EAVIT_LAUNCH_OK();
-  return EAVIT_OK;
+  if (Dh == 32) return drop.thresh ? launch_att_bwd<32, true>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, grid, st)
+                                   : launch_att_bwd<32, false>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, grid, st);
+  return drop.thresh ? launch_att_bwd<64, true>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, grid, st)
+                     : launch_att_bwd<64, false>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, grid, st);
 }
 
 #ifdef EAVIT_TRACE

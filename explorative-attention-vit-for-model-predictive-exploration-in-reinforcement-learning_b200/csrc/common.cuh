@@ -94,6 +94,42 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
+// ---------------------------------------------------------------------------------------------------- dropout
+// nn.Dropout (vit.py:31,33,45,56,158; HF hidden / attention-probs dropout) as a counter-based mask: the keep decision of
+// element (row r, column c) of a dropout SITE is a pure function of (seed, r, c), so the backward kernels regenerate
+// the forward mask instead of storing it and every kernel layout (epilogue tiles, TMEM rows, LN warps) sees the same
+// bits.  One 32-bit hash serves a column pair (16 bits each): keep iff bits >= thresh, thresh = round(p * 65536)
+// (p = 0.1 -> 6554 / 65536 = 0.100006); kept values are scaled by 1 / (1 - thresh / 65536) (exactly unbiased).
+// `eavit_dropout_mask` materialises the same mask for tests (the oracle is run with identical masks).
+struct DropCfg {
+  uint32_t thresh;      // 0 = dropout off
+  uint32_t seed_lo, seed_hi;
+  float scale;
+};
+__host__ __device__ inline DropCfg make_drop(float p, unsigned long long seed) {
+  DropCfg d;
+  const float pc = p < 0.f ? 0.f : (p > 0.999f ? 0.999f : p);
+  d.thresh = (uint32_t)(pc * 65536.0f + 0.5f);
+  d.seed_lo = (uint32_t)seed;
+  d.seed_hi = (uint32_t)(seed >> 32);
+  d.scale = 1.0f / (1.0f - (float)d.thresh * (1.0f / 65536.0f));
+  return d;
+}
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_row_key(const DropCfg& d, uint32_t r) { return lowbias32(r ^ d.seed_lo) + d.seed_hi; }
+// 32 bits for columns (2*cp, 2*cp + 1) of a row whose key is `rk`
+__device__ __forceinline__ uint32_t drop_bits(uint32_t rk, uint32_t cp) { return lowbias32(rk + cp * 0x9E3779B9u); }
+__device__ __forceinline__ float drop_even(const DropCfg& d, uint32_t bits) { return (bits & 0xffffu) >= d.thresh ? d.scale : 0.f; }
+__device__ __forceinline__ float drop_odd(const DropCfg& d, uint32_t bits) { return (bits >> 16) >= d.thresh ? d.scale : 0.f; }
+// mask factors (0 or 1/(1-p)) for 4 consecutive columns c0..c0+3 (c0 % 4 == 0) of row key rk
+__device__ __forceinline__ void drop4(const DropCfg& d, uint32_t rk, uint32_t c0, float* m) {
+  const uint32_t b0 = drop_bits(rk, c0 >> 1), b1 = drop_bits(rk, (c0 >> 1) + 1);
+  m[0] = drop_even(d, b0); m[1] = drop_odd(d, b0); m[2] = drop_even(d, b1); m[3] = drop_odd(d, b1);
+}
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace eavit

@@ -42,6 +42,7 @@ struct GemmKernelParams {
   __nv_bfloat16* out_pre;
   float* colsum;
   long long ldc;
+  DropCfg drop;
   int act;
   int atomic_f32;
 };
@@ -262,6 +263,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                   for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act, a[i]);
                 }
               }
+              if (p.drop.thresh != 0) {                 // warp-uniform; nn.Dropout after the Linear / activation
+                float dm[4];
+                drop4(p.drop, drop_row_key(p.drop, (uint32_t)(row0 + rr)), (uint32_t)col, dm);
+                v[0] *= dm[0]; v[1] *= dm[1]; v[2] *= dm[2]; v[3] *= dm[3];
+              }
               if (has_res) { v[0] += res[it].x; v[1] += res[it].y; v[2] += res[it].z; v[3] += res[it].w; }
               cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
               if (out_f32) {
@@ -382,6 +388,7 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.out_pre = reinterpret_cast<__nv_bfloat16*>(a->out_pre_bf16);
   p.colsum = a->colsum;
+  p.drop = make_drop(a->drop_p, a->drop_seed);
   p.ldc = a->ldc;
   p.act = a->act;
   p.atomic_f32 = a->atomic_f32;
@@ -406,7 +413,8 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
   EAVIT_CHECK_ARG(a->out_f32 != nullptr || a->out_bf16 != nullptr || a->out_pre_bf16 != nullptr);
   EAVIT_CHECK_ARG(a->split_k <= 1 || (a->atomic_f32 && a->out_f32 != nullptr && a->out_bf16 == nullptr &&
                                       a->out_pre_bf16 == nullptr && a->act == EAVIT_ACT_NONE && a->residual == nullptr &&
-                                      a->colsum == nullptr));
+                                      a->colsum == nullptr && a->drop_p == 0.f));
+  EAVIT_CHECK_ARG(a->drop_p >= 0.f && a->drop_p < 1.f);
   const bool need_aux = (a->act == EAVIT_ACT_GELU_BWD || a->act == EAVIT_ACT_LRELU_BWD || a->act == EAVIT_ACT_RELU_BWD);
   EAVIT_CHECK_ARG(!need_aux || a->aux_bf16 != nullptr);
   EAVIT_CHECK_ARG(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) layernorm_bwd_kernel(
                                                             float* __restrict__ dx, long long lddx,
                                                             __nv_bfloat16* __restrict__ dx_bf16, long long lddxb,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            float* __restrict__ dxsum, int T, int D) {
+                                                            float* __restrict__ dxsum, const DropCfg drop, int T, int D) {
   extern __shared__ float s_part[];   // [8 warps][3][D]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D / 4;
@@ -141,8 +141,15 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) layernorm_bwd_kernel(
         float4 o = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
                                rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
         if (dres != nullptr) { o.x += R.r[i].x; o.y += R.r[i].y; o.z += R.r[i].z; o.w += R.r[i].w; }
-        ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
         if (dx != nullptr) *(reinterpret_cast<float4*>(dx + (size_t)row * lddx) + c) = o;
+        // The bf16 copy (and its column sums) is the gradient w.r.t. the OUTPUT of the Linear that fed this residual
+        // stream: with dropout between that Linear and the residual add (vit.py:33,56) it carries the forward mask.
+        if (drop.thresh != 0) {
+          float dm[4];
+          drop4(drop, drop_row_key(drop, (uint32_t)row), (uint32_t)(4 * c), dm);
+          o.x *= dm[0]; o.y *= dm[1]; o.z *= dm[2]; o.w *= dm[3];
+        }
+        ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
         if (dx_bf16 != nullptr)
           *(reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * lddxb) + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
@@ -252,6 +259,31 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, long long lds
   }
 }
 
+// dst[i, c] = src[i, c] * dropmask(rows ? rows[i] : row0 + i, c)   (embedding dropout, vit.py:158; top-gradient rows)
+__global__ void __launch_bounds__(256) dropout_apply_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ rows,
+                                                            int row0, float* __restrict__ dst, long long ldd, int n, int D,
+                                                            const DropCfg drop) {
+  const int nv = D / 4;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)n * nv; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / nv), c = (int)(e - (long long)i * nv);
+    const uint32_t r = rows ? (uint32_t)rows[i] : (uint32_t)(row0 + i);
+    float4 v = *(reinterpret_cast<const float4*>(src + (size_t)i * lds) + c);
+    float dm[4];
+    drop4(drop, drop_row_key(drop, r), (uint32_t)(4 * c), dm);
+    v.x *= dm[0]; v.y *= dm[1]; v.z *= dm[2]; v.w *= dm[3];
+    *(reinterpret_cast<float4*>(dst + (size_t)i * ldd) + c) = v;
+  }
+}
+__global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ out, long long ld, int row0, int n, int col0, int ncols,
+                                                           const DropCfg drop) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)n * ncols; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / ncols), j = (int)(e - (long long)i * ncols);
+    const uint32_t c = (uint32_t)(col0 + j);
+    const uint32_t bits = drop_bits(drop_row_key(drop, (uint32_t)(row0 + i)), c >> 1);
+    out[(size_t)i * ld + j] = (c & 1) ? drop_odd(drop, bits) : drop_even(drop, bits);
+  }
+}
+
 // fp32 -> bf16 elementwise (weight shadows, activations)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -287,11 +319,13 @@ int eavit_layernorm_fwd(const float* x, long long ldx, const float* gamma, const
 
 int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const float* x, long long ldx, const float* mean,
                         const float* rstd, const float* gamma, const float* dres, long long lddres, float* dx,
-                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, float* dxsum, int T,
-                        int D, void* stream) {
+                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, float* dxsum, float drop_p,
+                        unsigned long long drop_seed, int T, int D, void* stream) {
   EAVIT_CHECK_ARG(T > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXV && dy && x && mean && rstd && gamma);
   EAVIT_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr));
   EAVIT_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && lddres % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0);
+  EAVIT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
+  const DropCfg drop = make_drop(drop_p, drop_seed);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)8 * 3 * D * sizeof(float);
   const int vpl = cdiv(D / 4, 32);
@@ -304,7 +338,7 @@ int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const floa
   // persistent grid = exactly the CTAs that are co-resident (a partial second wave would run at a fraction of the bandwidth)
 #define EAVIT_LN_BWD(DT, V) do { int occ = 1; EAVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_bwd_kernel<DT, V>, 256, smem)); \
     int grid = cdiv(T, 8); if (occ < 1) occ = 1; if (grid > occ * kNumSMs) grid = occ * kNumSMs; \
-    layernorm_bwd_kernel<DT, V><<<grid, 256, smem, st>>>((const DT*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, dxsum, T, D); } while (0)
+    layernorm_bwd_kernel<DT, V><<<grid, 256, smem, st>>>((const DT*)dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, dxsum, drop, T, D); } while (0)
 #define EAVIT_LN_BWD_V(DT) do { if (vpl <= 1) EAVIT_LN_BWD(DT, 1); else if (vpl <= 2) EAVIT_LN_BWD(DT, 2); else if (vpl <= 4) EAVIT_LN_BWD(DT, 4); else EAVIT_LN_BWD(DT, 8); } while (0)
   if (dy_dtype == EAVIT_F32) EAVIT_LN_BWD_V(float);
   else if (dy_dtype == EAVIT_BF16) EAVIT_LN_BWD_V(__nv_bfloat16);
@@ -333,6 +367,26 @@ int eavit_colsum(const void* x, int x_dtype, long long ldx, float* out, int T, i
 int eavit_gather_rows(const float* src, long long lds, const int* rows, float* dst, long long ldd, int n, int D, void* stream) {
   EAVIT_CHECK_ARG(n > 0 && D % 4 == 0 && src && rows && dst && lds % 4 == 0 && ldd % 4 == 0);
   gather_rows_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(src, lds, rows, dst, ldd, n, D);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_dropout_apply(const float* src, long long lds, const int* rows, int row0, float* dst, long long ldd, int n, int D,
+                        float p, unsigned long long seed, void* stream) {
+  EAVIT_CHECK_ARG(src && dst && n > 0 && D > 0 && D % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && p >= 0.f && p < 1.f);
+  long long blocks = ((long long)n * (D / 4) + 255) / 256;
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  dropout_apply_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, rows, row0, dst, ldd, n, D, make_drop(p, seed));
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_dropout_mask(float* out, long long ld, int row0, int n, int col0, int ncols, float p, unsigned long long seed,
+                       void* stream) {
+  EAVIT_CHECK_ARG(out && n > 0 && ncols > 0 && p >= 0.f && p < 1.f);
+  long long blocks = ((long long)n * ncols + 255) / 256;
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  dropout_mask_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, ld, row0, n, col0, ncols, make_drop(p, seed));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }

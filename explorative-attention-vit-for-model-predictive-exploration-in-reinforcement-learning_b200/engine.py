@@ -128,12 +128,15 @@ def _split_k(M: int, N: int, K: int) -> int:
     return max(1, min(s, (K + 63) // 64))
 
 
-def linear_fwd(x16, w16, *, bias=None, act=ops.ACT_NONE, residual=None, out_f32=None, out_bf16=None, out_pre=None):
-    """y = act(x W^T + b) (+ residual) on the tcgen05 GEMM."""
-    ops.gemm(x16, w16, bias=bias, act=act, residual=residual, out_f32=out_f32, out_bf16=out_bf16, out_pre=out_pre)
+def linear_fwd(x16, w16, *, bias=None, act=ops.ACT_NONE, residual=None, out_f32=None, out_bf16=None, out_pre=None,
+               drop_p=0.0, drop_seed=0):
+    """y = dropout(act(x W^T + b)) (+ residual) on the tcgen05 GEMM."""
+    ops.gemm(x16, w16, bias=bias, act=act, residual=residual, out_f32=out_f32, out_bf16=out_bf16, out_pre=out_pre,
+             drop_p=drop_p, drop_seed=drop_seed)
 
 
-def linear_bwd(dy16, x16, w16, *, dW, db=None, dx_f32=None, dx_bf16=None, act=ops.ACT_NONE, aux=None, dx_colsum=None):
+def linear_bwd(dy16, x16, w16, *, dW, db=None, dx_f32=None, dx_bf16=None, act=ops.ACT_NONE, aux=None, dx_colsum=None,
+               drop_p=0.0, drop_seed=0):
     """dW += dy^T x (split-K, MN-major operands), db += colsum(dy), dx = act'(dy W); dx_colsum += colsum(dx) fused in
     the dX epilogue (= the bias gradient of the layer below, whose output gradient dx is)."""
     M, K = dW.shape
@@ -141,7 +144,8 @@ def linear_bwd(dy16, x16, w16, *, dW, db=None, dx_f32=None, dx_bf16=None, act=op
     if db is not None:
         call("eavit_colsum", dy16, BF16, dy16.stride(0), db, dy16.shape[0], dy16.shape[1])
     if dx_f32 is not None or dx_bf16 is not None:
-        ops.gemm(dy16, w16, b_mn=True, act=act, aux=aux, out_f32=dx_f32, out_bf16=dx_bf16, colsum=dx_colsum)
+        ops.gemm(dy16, w16, b_mn=True, act=act, aux=aux, out_f32=dx_f32, out_bf16=dx_bf16, colsum=dx_colsum,
+                 drop_p=drop_p, drop_seed=drop_seed)
 
 
 class ViTEncoder:
@@ -223,12 +227,27 @@ class ViTEncoder:
         return bf
 
     # ---- forward ---------------------------------------------------------------------------------
-    def forward(self, img: torch.Tensor, B: int, sample_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    # dropout sites (vit.py:31,33,45,56,158): one well-mixed seed per (forward call, layer, site); the backward
+    # regenerates the masks from the seeds saved in the per-B buffers
+    SITE_EMB, SITE_ATTN_P, SITE_ATTN_OUT, SITE_ACT, SITE_FF_OUT = 0, 1, 2, 3, 4
+
+    def _site(self, bf, li: int, kind: int):
+        """(p, seed) of a dropout site for the forward call recorded in ``bf`` (p = 0 when dropout is off)."""
+        if bf.drop_base is None:
+            return 0.0, 0
+        c = self.cfg
+        p = (c.emb_dropout, c.attn_dropout, c.dropout, c.act_dropout, c.dropout)[kind]
+        return (p, ops.site_seed(bf.drop_base, li * 8 + kind)) if p > 0 else (0.0, 0)
+
+    def forward(self, img: torch.Tensor, B: int, sample_idx: Optional[torch.Tensor] = None,
+                drop_base: Optional[int] = None) -> torch.Tensor:
         """img: [N,C,H,W] uint8 (raw frames, divided by 255 in-kernel) or float32 (already /255).
         Returns the pooled, final-LayerNorm'ed features F fp32 [2B, D] (rows [0,B) explorative/CLS,
-        rows [B,2B) exploitative/CLS).  Activations stay in the per-B buffers for ``backward``."""
+        rows [B,2B) exploitative/CLS).  Activations stay in the per-B buffers for ``backward``.
+        ``drop_base``: None = dropout off (eval mode / p = 0); an integer = this call's dropout stream."""
         c, s, p = self.cfg, self.store, self.pre
         bf = self._buffers(B)
+        bf.drop_base = drop_base
         T, D, I, np_, PD = bf.T, c.dim, self.inner, c.n_patches, c.patch_dim
         rows = B * np_
         img_dt = ops._DT[img.dtype]
@@ -254,6 +273,9 @@ class ViTEncoder:
             linear_fwd(pln, w16, bias=s.w(e + "patch_embeddings.projection.bias"), out_f32=e0)
             call("eavit_embed_assemble", e0, s.w(e + "position_embeddings"), s.w(e + "exploration_token"),
                  s.w(e + "exploitation_token"), 2, B, np_, D, x0)
+        pe, se = self._site(bf, 0, self.SITE_EMB)
+        if pe > 0:
+            call("eavit_dropout_apply", x0, D, None, 0, x0, D, T, D, pe, se)
         x = x0
         for li, L in enumerate(self.L):
             xn1 = bf.get(f"xn1_{li}", (T, D), torch.bfloat16)
@@ -263,17 +285,22 @@ class ViTEncoder:
             linear_fwd(xn1, self._qkv(L, "w16"), bias=self._qkv(L, "b"), out_bf16=qkv)
             o = bf.get(f"o_{li}", (T, I), torch.bfloat16)
             lse = bf.get(f"lse_{li}", (T, c.heads), torch.float32)
-            ops.attention_fwd(qkv, bf.seq_start, bf.nseq, bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, o, lse)
+            pa, sa = self._site(bf, li, self.SITE_ATTN_P)
+            ops.attention_fwd(qkv, bf.seq_start, bf.nseq, bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, o, lse,
+                              drop_p=pa, drop_seed=sa)
             xmid = bf.get(f"xmid_{li}", (T, D), torch.float32)
-            linear_fwd(o, s.b16(L["o_w"]), bias=s.w(L["o_b"]), residual=x, out_f32=xmid)
+            po, so = self._site(bf, li, self.SITE_ATTN_OUT)
+            linear_fwd(o, s.b16(L["o_w"]), bias=s.w(L["o_b"]), residual=x, out_f32=xmid, drop_p=po, drop_seed=so)
             xn2 = bf.get(f"xn2_{li}", (T, D), torch.bfloat16)
             m2, r2 = bf.get(f"m2_{li}", (T,), torch.float32), bf.get(f"r2_{li}", (T,), torch.float32)
             call("eavit_layernorm_fwd", xmid, D, s.w(L["ln2"][0]), s.w(L["ln2"][1]), xn2, BF16, D, m2, r2, T, D, c.ln_eps)
             hpre = bf.get(f"hpre_{li}", (T, c.mlp_dim), torch.bfloat16)
             hact = bf.get(f"hact_{li}", (T, c.mlp_dim), torch.bfloat16)
-            linear_fwd(xn2, s.b16(L["w1"]), bias=s.w(L["b1"]), act=ops.ACT_GELU, out_bf16=hact, out_pre=hpre)
+            ph, sh = self._site(bf, li, self.SITE_ACT)
+            linear_fwd(xn2, s.b16(L["w1"]), bias=s.w(L["b1"]), act=ops.ACT_GELU, out_bf16=hact, out_pre=hpre, drop_p=ph, drop_seed=sh)
             xo = bf.get(f"x_{li + 1}", (T, D), torch.float32)
-            linear_fwd(hact, s.b16(L["w2"]), bias=s.w(L["b2"]), residual=xmid, out_f32=xo)
+            pf, sf = self._site(bf, li, self.SITE_FF_OUT)
+            linear_fwd(hact, s.b16(L["w2"]), bias=s.w(L["b2"]), residual=xmid, out_f32=xo, drop_p=pf, drop_seed=sf)
             x = xo
         nf = 2 * B
         pooled = bf.get("pooled", (nf, D), torch.float32)
@@ -295,20 +322,30 @@ class ViTEncoder:
         fn = (p + "transformer.norm.") if c.impl == "lucidrains" else (p + "layernorm.")
         dpool = bf.get("dpool", (nf, D), torch.float32)
         call("eavit_layernorm_bwd", dfeat, F32, D, bf.t["pooled"], D, bf.t["mf"], bf.t["rf"], s.w(fn + "weight"),
-             None, D, dpool, D, None, D, s.g(fn + "weight"), s.g(fn + "bias"), None, nf, D)
+             None, D, dpool, D, None, D, s.g(fn + "weight"), s.g(fn + "bias"), None, 0.0, 0, nf, D)
         dxa = bf.get("dxa", (T, D), torch.float32)
         dxb = bf.get("dxb", (T, D), torch.float32)
         dx16 = bf.get("dx16", (T, D), torch.bfloat16)
         call("eavit_zero", dxa, T * D * 4)
         call("eavit_zero", dx16, T * D * 2)
-        # bias gradient of the last layer's MLP2 = column sums of the (sparse) top gradient = column sums of dpool
-        call("eavit_colsum", dpool, F32, D, s.g(self.L[-1]["b2"]), nf, D)
+        # The top gradient is sparse (pooled rows only).  dxa = gradient of the residual stream; dx16 / db2 = gradient of
+        # the last MLP2 output = the same rows under that layer's output-dropout mask (vit.py:33).
+        top, ntop = dpool, nf
         if self.mode == 1:
-            dsum = bf.get("dpool_sum", (B, D), torch.float32)
-            call("eavit_add_f32", dpool[:B], dpool[B:], dsum, B * D)
-            call("eavit_scatter_rows", dsum, D, bf.pool_rows, dxa, D, dx16, D, B, D)
+            top, ntop = bf.get("dpool_sum", (B, D), torch.float32), B
+            call("eavit_add_f32", dpool[:B], dpool[B:], top, B * D)
+        pf, sf = self._site(bf, c.depth - 1, self.SITE_FF_OUT)
+        top16 = top
+        if pf > 0:
+            top16 = bf.get("dpool_drop", (ntop, D), torch.float32)
+            call("eavit_dropout_apply", top, D, bf.pool_rows, 0, top16, D, ntop, D, pf, sf)
+        # bias gradient of the last layer's MLP2 = column sums of its (sparse) output gradient
+        call("eavit_colsum", top16, F32, D, s.g(self.L[-1]["b2"]), ntop, D)
+        if top16 is top:
+            call("eavit_scatter_rows", top, D, bf.pool_rows, dxa, D, dx16, D, ntop, D)
         else:
-            call("eavit_scatter_rows", dpool, D, bf.pool_rows, dxa, D, dx16, D, nf, D)
+            call("eavit_scatter_rows", top, D, bf.pool_rows, dxa, D, None, D, ntop, D)
+            call("eavit_scatter_rows", top16, D, bf.pool_rows, None, D, dx16, D, ntop, D)
         dx, dx_other = dxa, dxb
         dh = bf.get("dh", (T, c.mlp_dim), torch.bfloat16)
         dxn = bf.get("dxn", (T, D), torch.bfloat16)     # LN-backward input (a GEMM output): bf16 halves its traffic
@@ -319,23 +356,30 @@ class ViTEncoder:
             x_in = bf.t["x0"] if li == 0 else bf.t[f"x_{li}"]
             # MLP2: x_out = xmid + hact W2^T + b2
             # (db2 comes from the producer of dx: LN-bwd / top; db1 = colsum(dh) from this GEMM's epilogue)
+            ph, sh = self._site(bf, li, self.SITE_ACT)
             linear_bwd(dx16, bf.t[f"hact_{li}"], s.b16(L["w2"]), dW=s.g(L["w2"]), db=None, dx_bf16=dh,
-                       act=ops.ACT_GELU_BWD, aux=bf.t[f"hpre_{li}"], dx_colsum=s.g(L["b1"]))
+                       act=ops.ACT_GELU_BWD, aux=bf.t[f"hpre_{li}"], dx_colsum=s.g(L["b1"]), drop_p=ph, drop_seed=sh)
             # MLP1: hpre = xn2 W1^T + b1
             linear_bwd(dh, bf.t[f"xn2_{li}"], s.b16(L["w1"]), dW=s.g(L["w1"]), db=None, dx_bf16=dxn)
+            po, so = self._site(bf, li, self.SITE_ATTN_OUT)     # dx16 / db_o: gradient of the out-proj output (masked)
             call("eavit_layernorm_bwd", dxn, BF16, D, bf.t[f"xmid_{li}"], D, bf.t[f"m2_{li}"], bf.t[f"r2_{li}"],
-                 s.w(L["ln2"][0]), dx, D, dx_other, D, dx16, D, s.g(L["ln2"][0]), s.g(L["ln2"][1]), s.g(L["o_b"]), T, D)
+                 s.w(L["ln2"][0]), dx, D, dx_other, D, dx16, D, s.g(L["ln2"][0]), s.g(L["ln2"][1]), s.g(L["o_b"]), po, so, T, D)
             dx, dx_other = dx_other, dx
             # out-proj: xmid = x + o Wo^T + bo
             linear_bwd(dx16, bf.t[f"o_{li}"], s.b16(L["o_w"]), dW=s.g(L["o_w"]), db=None, dx_bf16=do)
+            pa, sa = self._site(bf, li, self.SITE_ATTN_P)
             ops.attention_bwd(bf.t[f"qkv_{li}"], bf.t[f"o_{li}"], do, bf.t[f"lse_{li}"], bf.seq_start, bf.nseq,
-                              bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, dqkv)
+                              bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, dqkv, drop_p=pa, drop_seed=sa)
             linear_bwd(dqkv, bf.t[f"xn1_{li}"], self._qkv(L, "w16"), dW=self._qkv(L, "gw"), db=self._qkv(L, "gb"), dx_bf16=dxn)
             db2_prev = s.g(self.L[li - 1]["b2"]) if li > 0 else None      # dx of this LN is the output gradient of layer li-1's MLP2
+            pf, sf = self._site(bf, li - 1, self.SITE_FF_OUT) if li > 0 else (0.0, 0)   # dx16 / db2: layer li-1's MLP2 output
             call("eavit_layernorm_bwd", dxn, BF16, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
-                 dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, T, D)
+                 dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, pf, sf, T, D)
             dx, dx_other = dx_other, dx
-        # embedding
+        # embedding (dropout after the positional add, vit.py:158)
+        pe, se = self._site(bf, 0, self.SITE_EMB)
+        if pe > 0:
+            call("eavit_dropout_apply", dx, D, None, 0, dx, D, T, D, pe, se)
         rows = B * np_
         img, sidx = bf.img, bf.sample_idx
         img_dt = ops._DT[img.dtype]
@@ -346,7 +390,7 @@ class ViTEncoder:
             de16 = bf.get("de16", (rows, D), torch.bfloat16)
             call("eavit_layernorm_bwd", g, F32, D, bf.t["e0"], D, bf.t["m3"], bf.t["r3"], s.w(p + "to_patch_embedding.3.weight"),
                  None, D, None, D, de16, D, s.g(p + "to_patch_embedding.3.weight"), s.g(p + "to_patch_embedding.3.bias"),
-                 s.g(p + "to_patch_embedding.2.bias"), rows, D)
+                 s.g(p + "to_patch_embedding.2.bias"), 0.0, 0, rows, D)
             dpln = bf.get("dpln", (rows, PD), torch.float32)
             linear_bwd(de16, bf.t["pln"], s.b16(p + "to_patch_embedding.2.weight"), dW=s.g(p + "to_patch_embedding.2.weight"),
                        db=None, dx_f32=dpln)

@@ -8,6 +8,7 @@ accumulates parameter gradients straight into ``p.grad`` (views of the flat grad
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from enum import Enum
 from typing import Dict, List, Optional, Tuple
@@ -87,8 +88,13 @@ class Runtime:
                                      patch=hp["patch"], dim=hp["dim"], depth=hp["depth"], heads=hp["heads"], dim_head=hp["dim_head"],
                                      mlp_dim=hp["mlp_dim"], use_explorative=feat.use_explorativeAttn,
                                      ln_eps=(1e-5 if isinstance(feat, ViT) else feat.config.layer_norm_eps),
-                                     dropout=hp["dropout"], emb_dropout=hp["emb_dropout"])
+                                     dropout=hp["dropout"], emb_dropout=hp["emb_dropout"],
+                                     attn_dropout=hp.get("attn_dropout", -1.0), act_dropout=hp.get("act_dropout", -1.0))
             self.encoder = ViTEncoder(self.cfg, self.store, "model.feature.")
+            self._feat = feat
+            # dropout stream: one counter per Runtime, offset by torch's seed and the rank (ranks draw independent masks)
+            self._drop_seed0 = (torch.initial_seed() * 1000003 + int(os.environ.get("RANK", "0")) * 7919) & ((1 << 48) - 1)
+            self._drop_calls = 0
             if "model.actor.0.weight" in self.params:
                 A = self.params["model.actor.2.weight"].shape[0] if n_actions is None else n_actions
                 self.heads = Heads(self.cfg, self.store, A, ext_uses_int_critic)
@@ -129,34 +135,25 @@ class Runtime:
                 p.grad = self.store.g(n)
 
     # ---- actor-critic ----------------------------------------------------------------------------
+    def next_drop_base(self):
+        """Dropout stream id of the next forward call: None when dropout is off (eval mode or every p = 0).  Like the
+        reference, dropout follows the module's train/eval flag -- the rollout runs in train mode too."""
+        c = self.cfg
+        if not self._feat.training or max(c.dropout, c.emb_dropout, c.attn_dropout, c.act_dropout) <= 0:
+            return None
+        if os.environ.get("EAVIT_DROPOUT_AS_IDENTITY", "0") == "1":
+            return None
+        self._drop_calls += 1
+        return self._drop_seed0 + self._drop_calls
+
     def ac_forward(self, state: torch.Tensor, B: int, sample_idx=None):
-        if self.cfg.dropout > 0 or self.cfg.emb_dropout > 0:
-            _dropout_guard(self.cfg)
-        feat = self.encoder.forward(state, B, sample_idx)
+        feat = self.encoder.forward(state, B, sample_idx, drop_base=self.next_drop_base())
         return self.heads.forward(feat)          # policy [B,A], value_ext [B], value_int [B]  (views of scratch)
 
     def ac_backward(self, dpol: torch.Tensor, dv: torch.Tensor):
         """dv fp32 [2B] = (d value_int | d value_ext)."""
         dfeat = self.heads.backward(dpol, dv)
         self.encoder.backward(dfeat)
-
-
-_warned = False
-
-
-def _dropout_guard(cfg):
-    """The kernels implement the dropout-free arithmetic (the parity configuration)."""
-    import os
-    global _warned
-    if os.environ.get("EAVIT_DROPOUT_AS_IDENTITY", "0") == "1":
-        if not _warned:
-            print("eavit_b200: dropout keys > 0 are treated as identity (EAVIT_DROPOUT_AS_IDENTITY=1)")
-            _warned = True
-        return
-    raise NotImplementedError(
-        f"dropout={cfg.dropout}, emb_dropout={cfg.emb_dropout}: the B200 kernels implement dropout = 0 (the parity "
-        "configuration). Set the ViT*_dropout keys to 0.0, or export EAVIT_DROPOUT_AS_IDENTITY=1 to run the shipped "
-        "configs with dropout disabled.")
 
 
 def _runtime_for(module: nn.Module, prefix: str, **kw) -> Runtime:
@@ -181,7 +178,7 @@ def standalone_vit_features(vit_module: nn.Module, img) -> torch.Tensor:
     rt.sync()
     x = _as_device_image(img, rt.device)
     with torch.no_grad():
-        return rt.encoder.forward(x, x.shape[0]).clone()
+        return rt.encoder.forward(x, x.shape[0], drop_base=rt.next_drop_base()).clone()
 
 
 class _ActorCriticFn(torch.autograd.Function):

@@ -176,7 +176,7 @@ def intrinsic_mse(target, predict):
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias=None, act: int = ACT_NONE,
          aux=None, residual=None, out_f32=None, out_bf16=None, out_pre=None, colsum=None, atomic: bool = False,
-         split_k: int = 1):
+         split_k: int = 1, drop_p: float = 0.0, drop_seed: int = 0):
     """C = epilogue(A . B^T) on tcgen05 (see include/eavit_b200.h: eavit_gemm_bf16).
 
     a_mn: A passed as the stored [K, M] matrix; b_mn: B passed as the stored [K, N] matrix.
@@ -200,7 +200,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                  out_bf16=None if out_bf16 is None else out_bf16.data_ptr(),
                  out_pre_bf16=None if out_pre is None else out_pre.data_ptr(),
                  colsum=None if colsum is None else colsum.data_ptr(),
-                 ldc=ldc, act=act, atomic_f32=int(atomic), split_k=split_k)
+                 ldc=ldc, drop_p=float(drop_p), drop_seed=int(drop_seed) & _M64, act=act, atomic_f32=int(atomic), split_k=split_k)
     if _PROF is not None:
         with _Timed(f"gemm_bf16_tcgen05 M={M} N={N} K={K} {'mn' if a_mn else 'k'}{'mn' if b_mn else 'k'} act={act}"
                     f"{' splitk' if split_k > 1 else ''}", 2.0 * M * N * K):
@@ -214,7 +214,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 # d = double.  The trailing `void* stream` of every entry point is appended automatically.
 _SPECS = {
     "eavit_layernorm_fwd": "plpppilppiif",
-    "eavit_layernorm_bwd": "pilplppppl" "pl" "pl" "pppii",
+    "eavit_layernorm_bwd": "pilplppppl" "pl" "pl" "ppp" "fu" "ii",
+    "eavit_dropout_apply": "plpiplii" "fu",
+    "eavit_dropout_mask": "pliiii" "fu",
     "eavit_colsum": "pilpii",
     "eavit_gather_rows": "plpplii",
     "eavit_scatter_rows": "plppl" "pl" "ii",
@@ -222,9 +224,9 @@ _SPECS = {
     "eavit_add_f32": "pppl",
     "eavit_zero": "pl",
     "eavit_attention_fwd": "ppiiiifpp",
-    "eavit_attention_fwd_tc": "ppiiliifpp",
+    "eavit_attention_fwd_tc": "ppiiliifpp" "fu",
     "eavit_attention_bwd": "pppppiiiifp",
-    "eavit_attention_bwd_tc": "ppppiiliifp",
+    "eavit_attention_bwd_tc": "ppppiiliifp" "fu",
     "eavit_patchify": "pipiiiiippfppp",
     "eavit_patchify_ln_bwd": "pipiiiiipppppp",
     "eavit_embed_assemble": "ppppiiiip",
@@ -248,7 +250,8 @@ _SPECS = {
     "eavit_clip_by_norm": "plpf",
 }
 _SPECS["eavit_sgemm_small"] = "pli" "pli" "pp" "pl" "iiiii"
-_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float, "d": ctypes.c_double}
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float, "d": ctypes.c_double,
+       "u": ctypes.c_ulonglong}
 _bound = {}
 
 
@@ -284,17 +287,42 @@ def call(name: str, *args):
         check(rc, name[len("eavit_"):])
 
 
+# ------------------------------------------------------------------------------------------- dropout
+_M64 = (1 << 64) - 1
+
+
+def site_seed(base: int, site: int) -> int:
+    """Well-mixed 64-bit seed of one dropout site of one forward call (splitmix64 of base * 4096 + site)."""
+    z = (int(base) * 4096 + int(site) + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def dropout_mask(n: int, ncols: int, p: float, seed: int, row0: int = 0, col0: int = 0, device="cuda") -> torch.Tensor:
+    """The mask factors (0 or 1/(1-p)) the fused kernels apply at rows [row0, row0+n), columns [col0, col0+ncols)."""
+    out = torch.empty(n, ncols, dtype=torch.float32, device=device)
+    call("eavit_dropout_mask", out, ncols, row0, n, col0, ncols, float(p), int(seed) & _M64)
+    return out
+
+
 # ------------------------------------------------------------------------------------------- attention dispatch
-def attention_fwd(qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse):
+def attention_fwd(qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse, drop_p: float = 0.0, drop_seed: int = 0):
     """tcgen05 kernel when the sequence fits its TMEM plan (S <= 224), CUDA-core kernel for longer sequences."""
     if max_len <= 224:
-        call("eavit_attention_fwd_tc", qkv, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, out, lse)
+        call("eavit_attention_fwd_tc", qkv, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, out, lse, float(drop_p),
+             int(drop_seed) & _M64)
     else:
+        if drop_p > 0:
+            raise NotImplementedError("attention-probability dropout is implemented by the tcgen05 kernels (sequence <= 224 tokens)")
         call("eavit_attention_fwd", qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse)
 
 
-def attention_bwd(qkv, out, dout, lse, seq_start, nseq, max_len, H, Dh, scale, dqkv):
+def attention_bwd(qkv, out, dout, lse, seq_start, nseq, max_len, H, Dh, scale, dqkv, drop_p: float = 0.0, drop_seed: int = 0):
     if (Dh == 32 and max_len <= 224) or (Dh == 64 and max_len <= 128):
-        call("eavit_attention_bwd_tc", qkv, dout, lse, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, dqkv)
+        call("eavit_attention_bwd_tc", qkv, dout, lse, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, dqkv, float(drop_p),
+             int(drop_seed) & _M64)
     else:
+        if drop_p > 0:
+            raise NotImplementedError("attention-probability dropout is implemented by the tcgen05 kernels")
         call("eavit_attention_bwd", qkv, out, dout, lse, seq_start, nseq, max_len, H, Dh, scale, dqkv)

@@ -99,7 +99,8 @@ class ViT_ExplorativeAttn(nn.Module):
         self.hp = dict(image=config.image_size, patch=config.patch_size, channels=config.num_channels, dim=config.hidden_size,
                        depth=config.num_hidden_layers, heads=config.num_attention_heads,
                        dim_head=config.hidden_size // config.num_attention_heads, mlp_dim=config.intermediate_size,
-                       dropout=config.hidden_dropout_prob, emb_dropout=config.hidden_dropout_prob)
+                       dropout=config.hidden_dropout_prob, emb_dropout=config.hidden_dropout_prob,
+                       attn_dropout=config.attention_probs_dropout_prob, act_dropout=0.0)   # HF has no dropout after GELU
         self._rt = None
 
     def _init_weights(self, module):   # vit_hg.py:179-224

@@ -103,7 +103,7 @@ int eavit_intrinsic_mse(const float* target, const float* predict, float* out, i
  *   b_mn = 0: B is row-major [N,K] (pitch ldb)          -- nn.Linear weight, y = x W^T
  *   b_mn = 1: B is row-major [K,N] (pitch ldb)          -- dX = dY W
  * epilogue, per element v = acc:  v += bias[n];  out_pre_bf16 = v;  v = act(v, aux[m,n]);
- *   v += residual[m,n];  out_f32 / out_bf16 = v   (atomic_f32 != 0: out_f32 += v with red.add and
+ *   v *= dropmask(m,n) (drop_p > 0);  v += residual[m,n];  out_f32 / out_bf16 = v   (atomic_f32 != 0: out_f32 += v with red.add and
  *   split_k > 1 slices of K).  Any of bias/aux/residual/out_* may be NULL.  ldc = pitch of every
  *   [M,N] epilogue tensor in elements.  Requirements: pitches * 2 bytes % 16 == 0, N % 8 == 0.
  * Replaces every nn.Linear / matmul on the ViT path (vit.py:29-32, :52-57, :112) and the RND FCs. */
@@ -119,6 +119,8 @@ typedef struct {
   void* out_pre_bf16;
   float* colsum;       /* optional [N]: colsum[n] += sum_m (final v) -- the bias gradient when this GEMM produces dY */
   long long ldc;
+  float drop_p;        /* nn.Dropout probability applied to v after the activation (or its derivative) and before the */
+  unsigned long long drop_seed; /* residual add; mask(m, n) is a pure function of (drop_seed, m, n) -- see eavit_dropout_mask */
   int act;
   int atomic_f32;
   int split_k;
@@ -133,11 +135,12 @@ int eavit_layernorm_fwd(const float* x, long long ldx, const float* gamma, const
                         long long ldy, float* mean, float* rstd, int T, int D, float eps, void* stream);
 /* dx = dres + LN'(dy); dgamma/dbeta accumulated with atomics (+=).  dy dtype F32 or BF16; dres, dx,
  * dx_bf16, dgamma/dbeta optional.  dxsum (optional) += column sums of dx = the bias gradient of the Linear whose
- * output fed this residual stream (saves a separate pass over [T,D]). */
+ * output fed this residual stream (saves a separate pass over [T,D]).  drop_p > 0: dx_bf16 and dxsum carry the forward
+ * dropout mask of that Linear's output (site seed drop_seed); the fp32 residual gradient dx does not. */
 int eavit_layernorm_bwd(const void* dy, int dy_dtype, long long lddy, const float* x, long long ldx, const float* mean,
                         const float* rstd, const float* gamma, const float* dres, long long lddres, float* dx,
-                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, float* dxsum, int T,
-                        int D, void* stream);
+                        long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, float* dxsum, float drop_p,
+                        unsigned long long drop_seed, int T, int D, void* stream);
 /* out[c] += sum_r x[r,c]  (bias gradients); x dtype BF16 or F32. */
 int eavit_colsum(const void* x, int x_dtype, long long ldx, float* out, int T, int N, void* stream);
 /* dst[i,:] = src[rows[i],:]  /  dst[rows[i],:] = src[i,:]  (pooled token x[:,0], vit.py:162). */
@@ -159,13 +162,28 @@ int eavit_attention_fwd(const void* qkv, const int* seq_start, int nseq, int max
  * operand); max_len <= 224.  total_tokens = T = seq_start[nseq] (the extent of the TMA tensor map: rows past T are
  * zero-filled, never read).  Dh = 32 needs an even H (two heads share one 128-byte staged row). */
 int eavit_attention_fwd_tc(const void* qkv, const int* seq_start, int nseq, int max_len, long long total_tokens, int H, int Dh,
-                           float scale, void* out, float* lse, void* stream);
+                           float scale, void* out, float* lse, float drop_p, unsigned long long drop_seed, void* stream);
 int eavit_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const int* seq_start,
                         int nseq, int max_len, int H, int Dh, float scale, void* dqkv, void* stream);
 
 /* Backward on tcgen05 (recomputes P from q, k, lse; does not need `out`).  Dh = 32: max_len <= 224; Dh = 64: max_len <= 128. */
 int eavit_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const int* seq_start, int nseq, int max_len,
-                           long long total_tokens, int H, int Dh, float scale, void* dqkv, void* stream);
+                           long long total_tokens, int H, int Dh, float scale, void* dqkv, float drop_p,
+                           unsigned long long drop_seed, void* stream);
+/* drop_p > 0 (both kernels): nn.Dropout on the attention probabilities (vit.py:45,70); mask element = (token row,
+ * h * 256 + key) of the site seed, regenerated in the backward. */
+
+/* ------------------------------------------------------------------ dropout (vit.py:31,33,45,56,158) */
+
+/* Every dropout site is a counter-based mask: keep(r, c) is a pure function of (seed, r, c) (16 hash bits per element,
+ * p quantised to round(p*65536)/65536, kept values scaled by 1/(1-p)).  The fused kernels (GEMM epilogue, LayerNorm
+ * backward, attention) evaluate it in place; these two entry points apply / materialise the SAME mask:
+ *   eavit_dropout_apply: dst[i, c] = src[i, c] * mask(rows ? rows[i] : row0 + i, c)   (in place allowed)
+ *   eavit_dropout_mask : out[i, j] = mask(row0 + i, col0 + j)  in {0, 1/(1-p)}          (tests / oracle hook) */
+int eavit_dropout_apply(const float* src, long long lds, const int* rows, int row0, float* dst, long long ldd, int n, int D,
+                        float p, unsigned long long seed, void* stream);
+int eavit_dropout_mask(float* out, long long ld, int row0, int n, int col0, int ncols, float p, unsigned long long seed,
+                       void* stream);
 
 /* ------------------------------------------------------------------ patch embedding (vit.py:109-158) */
 

@@ -195,6 +195,16 @@ def init_params(cfg: OracleConfig, seed: int = 0, dtype=torch.float32) -> Dict[s
 # ----------------------------------------------------------------------------------------------
 EXPLORATIVE, EXPLOITATIVE, CLS = 0, 1, 2   # vit.py:14-17 ViT_Attn values
 
+# nn.Dropout sites of the reference (vit.py:31,33,45,56,158; HF hidden / attention-probs dropout).  torch's Philox stream
+# cannot be reproduced by another implementation, so parity with dropout ON is checked with EXPLICIT masks: a test installs
+# DROPOUT_HOOK(kind, layer, x, pass_id) -> x * mask, fed with the very masks the CUDA kernels generate.  None = identity
+# (dropout 0, the configuration every golden fixture uses).
+DROPOUT_HOOK = None
+
+
+def _drop(kind: str, layer: int, x: torch.Tensor, pass_id) -> torch.Tensor:
+    return x if DROPOUT_HOOK is None else DROPOUT_HOOK(kind, layer, x, pass_id)
+
 
 def patchify_lucid(img: torch.Tensor, p: int) -> torch.Tensor:
     """vit.py:110 -- 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (channel fastest)."""
@@ -226,10 +236,10 @@ def lucid_embed(P, img, attn_type: int, cfg: OracleConfig, pre="model.feature.")
             raise Exception("Must use attn_type=CLS")                            # vit.py:153
         tok = P[pre + "cls_token"].expand(b, 1, cfg.dim)
         x = torch.cat((tok, x), dim=1) + P[pre + "pos_embedding"][:, : n + 1]
-    return x
+    return _drop("emb", 0, x, attn_type)                                         # vit.py:158
 
 
-def lucid_attention(P, x, i: int, cfg: OracleConfig, pre="model.feature.") -> torch.Tensor:
+def lucid_attention(P, x, i: int, cfg: OracleConfig, pre="model.feature.", pass_id=None) -> torch.Tensor:
     """vit.py:60-73."""
     a = pre + f"transformer.layers.{i}.0."
     h, d = cfg.heads, cfg.dim_head
@@ -238,25 +248,25 @@ def lucid_attention(P, x, i: int, cfg: OracleConfig, pre="model.feature.") -> to
     qkv = F.linear(y, P[a + "to_qkv.weight"])
     q, k, v = (t.reshape(b, n, h, d).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
     dots = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
-    attn = dots.softmax(dim=-1)
+    attn = _drop("attn_p", i, dots.softmax(dim=-1), pass_id)                     # vit.py:69-70
     out = torch.matmul(attn, v).transpose(1, 2).reshape(b, n, h * d)
-    return F.linear(out, P[a + "to_out.0.weight"], P[a + "to_out.0.bias"])
+    return _drop("attn_out", i, F.linear(out, P[a + "to_out.0.weight"], P[a + "to_out.0.bias"]), pass_id)   # vit.py:54-57
 
 
-def lucid_ff(P, x, i: int, cfg: OracleConfig, pre="model.feature.") -> torch.Tensor:
+def lucid_ff(P, x, i: int, cfg: OracleConfig, pre="model.feature.", pass_id=None) -> torch.Tensor:
     """vit.py:27-37 (nn.GELU default = exact erf)."""
     m = pre + f"transformer.layers.{i}.1.net."
     y = F.layer_norm(x, (cfg.dim,), P[m + "0.weight"], P[m + "0.bias"], 1e-5)
-    y = F.gelu(F.linear(y, P[m + "1.weight"], P[m + "1.bias"]))
-    return F.linear(y, P[m + "4.weight"], P[m + "4.bias"])
+    y = _drop("act", i, F.gelu(F.linear(y, P[m + "1.weight"], P[m + "1.bias"])), pass_id)                  # vit.py:30-31
+    return _drop("ff_out", i, F.linear(y, P[m + "4.weight"], P[m + "4.bias"]), pass_id)                    # vit.py:32-33
 
 
 def lucid_vit(P, img, attn_type: int, cfg: OracleConfig, pre="model.feature.") -> torch.Tensor:
     """vit.py:136-167 with num_classes = -1, pool = 'cls'."""
     x = lucid_embed(P, img, attn_type, cfg, pre)
     for i in range(cfg.depth):                                                   # vit.py:86-89
-        x = lucid_attention(P, x, i, cfg, pre) + x
-        x = lucid_ff(P, x, i, cfg, pre) + x
+        x = lucid_attention(P, x, i, cfg, pre, attn_type) + x
+        x = lucid_ff(P, x, i, cfg, pre, attn_type) + x
     x = F.layer_norm(x, (cfg.dim,), P[pre + "transformer.norm.weight"], P[pre + "transformer.norm.bias"], 1e-5)
     return x[:, 0]                                                               # vit.py:162
 
@@ -278,8 +288,9 @@ def hg_vit(P, img, cfg: OracleConfig, pre="model.feature.") -> Tuple[torch.Tenso
     x = x.flatten(2).transpose(1, 2)                                             # [B, n, D]
     b = x.shape[0]
     outs = []
-    for tok in ("exploration_token", "exploitation_token"):                     # vit_hg.py:121-145
+    for pass_id, tok in enumerate(("exploration_token", "exploitation_token")):  # vit_hg.py:121-145
         s = torch.cat((P[e + tok].expand(b, -1, -1), x), dim=1) + P[e + "position_embeddings"]
+        s = _drop("emb", 0, s, pass_id)                                          # ViTEmbeddings dropout (hidden_dropout_prob)
         for i in range(cfg.depth):
             l = pre + f"encoder.layer.{i}."
             y = F.layer_norm(s, (D,), P[l + "layernorm_before.weight"], P[l + "layernorm_before.bias"], cfg.ln_eps)
@@ -288,12 +299,12 @@ def hg_vit(P, img, cfg: OracleConfig, pre="model.feature.") -> Tuple[torch.Tenso
             k = F.linear(y, P[l + "attention.attention.key.weight"], P[l + "attention.attention.key.bias"])
             v = F.linear(y, P[l + "attention.attention.value.weight"], P[l + "attention.attention.value.bias"])
             q, k, v = (t.reshape(b, n, h, d).transpose(1, 2) for t in (q, k, v))
-            pr = (torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d)).softmax(dim=-1)
+            pr = _drop("attn_p", i, (torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d)).softmax(dim=-1), pass_id)
             o = torch.matmul(pr, v).transpose(1, 2).reshape(b, n, D)
-            s = F.linear(o, P[l + "attention.output.dense.weight"], P[l + "attention.output.dense.bias"]) + s
+            s = _drop("attn_out", i, F.linear(o, P[l + "attention.output.dense.weight"], P[l + "attention.output.dense.bias"]), pass_id) + s
             y = F.layer_norm(s, (D,), P[l + "layernorm_after.weight"], P[l + "layernorm_after.bias"], cfg.ln_eps)
             y = F.gelu(F.linear(y, P[l + "intermediate.dense.weight"], P[l + "intermediate.dense.bias"]))
-            s = F.linear(y, P[l + "output.dense.weight"], P[l + "output.dense.bias"]) + s
+            s = _drop("ff_out", i, F.linear(y, P[l + "output.dense.weight"], P[l + "output.dense.bias"]), pass_id) + s
         outs.append(F.layer_norm(s, (D,), P[pre + "layernorm.weight"], P[pre + "layernorm.bias"], cfg.ln_eps))
     return outs[0], outs[1]
 

@@ -49,7 +49,7 @@ def test_attention_forward(ops, lens, H, Dh, impl):
     if impl == "v1":
         ops.call("eavit_attention_fwd", qkv, ss, len(lens), max(lens), H, Dh, scale, out, lse)
     else:
-        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse)
+        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse, 0.0, 0)
     torch.cuda.synchronize()
     ro, rl = ref_attention(qkv, starts, H, Dh, scale)
     assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
@@ -80,8 +80,8 @@ def test_attention_backward(ops, lens, H, Dh, impl):
     lse = torch.empty(T, H, device="cuda")
     dqkv = torch.full((T, 3 * H * Dh), float("nan"), device="cuda", dtype=torch.bfloat16)
     if impl == "tc":
-        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse)
-        ops.call("eavit_attention_bwd_tc", qkv, dout, lse, ss, len(lens), max(lens), T, H, Dh, scale, dqkv)
+        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse, 0.0, 0)
+        ops.call("eavit_attention_bwd_tc", qkv, dout, lse, ss, len(lens), max(lens), T, H, Dh, scale, dqkv, 0.0, 0)
     else:
         ops.call("eavit_attention_fwd", qkv, ss, len(lens), max(lens), H, Dh, scale, out, lse)
         ops.call("eavit_attention_bwd", qkv, out, dout, lse, ss, len(lens), max(lens), H, Dh, scale, dqkv)

@@ -23,7 +23,8 @@ def test_abi_specs_match_header():
         params = params[:-1]
         assert len(params) == len(spec), name
         for p, c in zip(params, spec):
-            exp = "p" if "*" in p else ("l" if "long long" in p else "i" if p.startswith("int") else "f" if p.startswith("float") else "d")
+            exp = "p" if "*" in p else ("u" if "unsigned long long" in p else "l" if "long long" in p else "i" if p.startswith("int")
+                                        else "f" if p.startswith("float") else "d")
             assert exp == c, (name, p, c)
     declared = set(_lib.declared_symbols())
     assert set(ops._SPECS) <= declared

@@ -15,13 +15,13 @@ o = torch.empty(st[-1], H * DH, device="cuda", dtype=torch.bfloat16)
 lse = torch.empty(st[-1], H, device="cuda")
 do = torch.randn_like(o)
 dqkv = torch.empty_like(qkv)
-ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse)
+ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse, 0.0, 0)
 which = sys.argv[1] if len(sys.argv) > 1 else "bwd"
 def run():
     if which == "bwd":
-        ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv)
+        ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0)
     else:
-        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse)
+        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse, 0.0, 0)
 run()
 torch.cuda.synchronize()
 L = _lib.lib()

@@ -48,9 +48,9 @@ if which in ("all", "attn"):
     do = torch.randn_like(o)
     dqkv = torch.empty_like(qkv)
     fl = sum(4.0 * n * n * DH * H for n in lens)
-    timed("attention_fwd_tc  (1024 seq x 8 heads)", lambda: ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse), fl,
+    timed("attention_fwd_tc  (1024 seq x 8 heads)", lambda: ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse, 0.0, 0), fl,
           qkv.numel() * 2 + o.numel() * 2)
-    timed("attention_bwd_tc", lambda: ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv), 2.5 * fl,
+    timed("attention_bwd_tc", lambda: ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0), 2.5 * fl,
           2 * qkv.numel() * 2 + o.numel() * 2)
 
 if which in ("all", "gemm"):
@@ -97,5 +97,5 @@ if which in ("all", "ln"):
     dx16 = torch.empty(T, D, device="cuda", dtype=torch.bfloat16)
     dg, db, dsum = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
     timed("layernorm_bwd (dy bf16, dres, dx f32+bf16)",
-          lambda: ops.call("eavit_layernorm_bwd", dy, BF16, D, x, D, m, r, g, dres, D, dx, D, dx16, D, dg, db, dsum, T, D), None, T * D * (2 + 4 + 4 + 4 + 2))
+          lambda: ops.call("eavit_layernorm_bwd", dy, BF16, D, x, D, m, r, g, dres, D, dx, D, dx16, D, dg, db, dsum, 0.0, 0, T, D), None, T * D * (2 + 4 + 4 + 4 + 2))
 print("done")
