@@ -261,6 +261,42 @@ def main():
         json.dump({"per_step": [{"kernel": l, "launches": n, "ms": tms, "tflops": (fl * n / (tms * 1e-3) / 1e12 if fl else None)}
                                 for l, n, tms, fl in rows], "sum_ms": tot_ms / nprof}, open(args.profile_out, "w"), indent=1)
 
+    # ---- secondary numbers: (M2) bare ViT fwd+bwd obs/s, and the same step with the shipped dropout keys (0.1)
+    def timed_loop(fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        barrier()
+        t = a.elapsed_time(b)
+        if world > 1:
+            tt = torch.tensor([t], device=dev)
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            t = float(tt.item())
+        return t / n
+    dpol = torch.randn(B, A, device=dev) * 1e-3
+    dv = torch.randn(2 * B, device=dev) * 1e-3
+
+    def vit_only(i):
+        j = i % n_mb
+        rt.ac_forward(R["states"], B, perm[B * j: B * (j + 1)])
+        rt.ac_backward(dpol, dv)
+    vit_only(0)
+    vit_ms = timed_loop(vit_only, max(4, args.steps // 2))
+    vit = {"metric": "ViT fwd+bwd obs/sec (both attention passes + heads)", "value": B * world / (vit_ms * 1e-3), "ms": vit_ms,
+           "model_tflops": 6.36e9 * B / (vit_ms * 1e-3) / 1e12,
+           "frac_of_sustained_bf16_peak": 6.36e9 * B / (vit_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
+    c = rt.cfg
+    saved = (c.dropout, c.emb_dropout, c.attn_dropout, c.act_dropout)
+    c.dropout = c.emb_dropout = c.attn_dropout = c.act_dropout = 0.1          # the shipped expGlados3 keys
+    for i in range(2):
+        step(i)
+    drop_ms = timed_loop(step, max(4, args.steps // 2))
+    c.dropout, c.emb_dropout, c.attn_dropout, c.act_dropout = saved
+    with_dropout = {"dropout": 0.1, "value": B * world / (drop_ms * 1e-3), "unit": "samples/s", "ms_per_step": drop_ms}
+
     # ---- end to end through the reference-facing call (host buffers in, stats out)
     e2e = None
     if not args.no_e2e:
@@ -282,6 +318,9 @@ def main():
                "next_obs f64, old_policy f32) -- numpy host buffers (pinned), one full update = 128 optimiser steps",
                "seconds": dt, "loss": stats.get("loss")}
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     cpu = None if args.no_cpu else cpu_reference(4, 1)
@@ -290,7 +329,8 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B * world, "envs_per_gpu": E, "num_step": T, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2 (>= 5 GB of activations per step)", "timing": "CUDA events, max over ranks"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary()}
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "vit_fwd_bwd": vit, "with_shipped_dropout": with_dropout}
     print(json.dumps(line))
 
 

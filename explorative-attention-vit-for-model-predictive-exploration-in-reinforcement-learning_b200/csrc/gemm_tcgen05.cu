@@ -76,7 +76,7 @@ enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, 
 // atomic epilogues are HBM-bound and want registers for loads in flight instead: 8 warps.
 template <int EPI> struct EpiWarps { static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_BWD) ? 16 : 8; };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool DROP>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
 __global__ void __launch_bounds__((CTRL_WARPS + EpiWarps<EPI>::N) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmKernelParams p) {
@@ -263,7 +263,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                   for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act, a[i]);
                 }
               }
-              if (p.drop.thresh != 0) {                 // warp-uniform; nn.Dropout after the Linear / activation
+              if constexpr (DROP) {                     // nn.Dropout after the Linear / activation
                 float dm[4];
                 drop4(p.drop, drop_row_key(p.drop, (uint32_t)(row0 + rr)), (uint32_t)col, dm);
                 v[0] *= dm[0]; v[1] *= dm[1]; v[2] *= dm[2]; v[3] *= dm[3];
@@ -353,12 +353,12 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return EAVIT_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool DROP = false>
 static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES));
     attr_done = true;
   }
@@ -394,7 +394,7 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   p.atomic_f32 = a->atomic_f32;
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, (CTRL_WARPS + EpiWarps<EPI>::N) * 32, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_kernel<BN, EPI, DROP><<<grid, (CTRL_WARPS + EpiWarps<EPI>::N) * 32, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -419,20 +419,21 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
   EAVIT_CHECK_ARG(!need_aux || a->aux_bf16 != nullptr);
   EAVIT_CHECK_ARG(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool drop = make_drop(a->drop_p, a->drop_seed).thresh != 0;
   if (a->N > 128) {
     const bool none = a->act == EAVIT_ACT_NONE;
     const bool plain = !a->residual && !a->aux_bf16 && !a->out_pre_bf16;
     if (a->atomic_f32 && none && plain && !a->bias && !a->out_bf16) return launch_gemm<256, E_ATOMIC>(a, st);
     if (a->atomic_f32) return launch_gemm<256, E_GENERIC>(a, st);
     if (a->act == EAVIT_ACT_GELU && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32)
-      return launch_gemm<256, E_GELU_FWD>(a, st);
+      return drop ? launch_gemm<256, E_GELU_FWD, true>(a, st) : launch_gemm<256, E_GELU_FWD>(a, st);
     if (a->act == EAVIT_ACT_GELU_BWD && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
-      return launch_gemm<256, E_GELU_BWD>(a, st);
+      return drop ? launch_gemm<256, E_GELU_BWD, true>(a, st) : launch_gemm<256, E_GELU_BWD>(a, st);
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)
-      return launch_gemm<256, E_RESID>(a, st);
-    if (none && plain) return launch_gemm<256, E_STORE>(a, st);
-    return launch_gemm<256, E_GENERIC>(a, st);
+      return drop ? launch_gemm<256, E_RESID, true>(a, st) : launch_gemm<256, E_RESID>(a, st);
+    if (none && plain && !drop) return launch_gemm<256, E_STORE>(a, st);
+    return drop ? launch_gemm<256, E_GENERIC, true>(a, st) : launch_gemm<256, E_GENERIC>(a, st);
   }
-  if (a->N > 64) return launch_gemm<128, E_GENERIC>(a, st);
-  return launch_gemm<64, E_GENERIC>(a, st);
+  if (a->N > 64) return drop ? launch_gemm<128, E_GENERIC, true>(a, st) : launch_gemm<128, E_GENERIC>(a, st);
+  return drop ? launch_gemm<64, E_GENERIC, true>(a, st) : launch_gemm<64, E_GENERIC>(a, st);
 }
