@@ -68,29 +68,37 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Exact-erf GELU (nn.GELU default) through Abramowitz-Stegun 7.1.26: |erf error| <= 1.5e-7 (fp32 level, far below the
-// bf16 rounding of the stored activation), ~14 instructions with one rcp and one ex2 instead of ~25 for erff().
-// tail(x) = 0.5 * erfc(|x| / sqrt2) is evaluated directly, so Phi(x) has no cancellation for very negative x.
-// e = exp(-x^2 / 2) is shared with the derivative:  gelu'(x) = Phi(x) + x * e / sqrt(2 pi).
+// bf16 rounding of the stored activation).  The GEMM epilogues that evaluate it are instruction-issue bound (ncu: 80 %
+// issue-active), so the constants are folded until 13 instructions remain (one rcp, one ex2):
+//   tail(x) = 0.5 * erfc(|x| / sqrt2) = (a1' t + ... + a5' t^5) * e,  t = 1 / (1 + 0.2316419 |x|),  e = exp(-x^2 / 2)
+//   gelu(x) = max(x, 0) - |x| * tail(x)          (no cancellation for very negative x, no select)
+//   gelu'(x) = Phi(x) + x * e / sqrt(2 pi),      Phi(x) = [x >= 0] - copysign(tail, x)
 __device__ __forceinline__ float gelu_tail(float x, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  e = ex2_approx(-1.4426950408889634f * z * z);
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  return 0.5f * p * t * e;
+  const float t = rcp_approx(fmaf(fabsf(x), 0.2316418882f, 1.0f));     // 0.3275911 / sqrt(2)
+  const float a = x * 0.8493218003f;                                   // sqrt(log2(e) / 2): e = 2^(-a^2)
+  e = ex2_approx(-(a * a));
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);                    // 0.5 * A&S coefficients
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  return p * t * e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
   float e;
   const float tail = gelu_tail(x, e);
-  return x * (x >= 0.f ? 1.0f - tail : tail);
+  return fmaf(-fabsf(x), tail, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float e;
   const float tail = gelu_tail(x, e);
-  const float cdf = x >= 0.f ? 1.0f - tail : tail;
+  const float cdf = (x >= 0.f ? 1.0f : 0.0f) - copysignf(tail, x);
   return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 

@@ -205,6 +205,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int c = par; c < BN / 32; c += EPI_WARPS / 4) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;                        // warp-uniform
+        const int cchunk = lane & 7, rsub = lane >> 3;
+        const int col = col0 + cchunk * 4;
+        constexpr bool CS = GEN || EPI == E_GELU_BWD;    // epilogues that can carry a fused column sum
+        const size_t off0 = (size_t)(row0 + rsub) * (size_t)p.ldc + col;      // row rr = rsub + 4 * it
+        const size_t ostep = 4 * (size_t)p.ldc;
+        // Issue every global read of this chunk FIRST (8 independent 16-byte loads per lane: the epilogue is latency-
+        // bound on HBM unless ~40 KB per SM are in flight) -- before the TMEM load and the __syncwarp of the transpose,
+        // which also stops the scheduler from sinking them between the stores further down.
+        float4 res[8];
+        uint2 ax[8];
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load = [&](int it) {
+          if (has_res) res[it] = __ldg(reinterpret_cast<const float4*>(p.residual + off0 + it * ostep));
+          if (need_aux) ax[it] = __ldg(reinterpret_cast<const uint2*>(p.aux + off0 + it * ostep));
+        };
+        if (col < p.N) {
+          if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          if (has_res || need_aux) {
+            if (nrows >= 32) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) load(it);
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                if (it * 4 + rsub < nrows) load(it);
+            }
+          }
+        }
         uint32_t r[32];
         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
         tc::tmem_ld_wait();
@@ -213,74 +241,57 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int c4 = 0; c4 < 8; ++c4)
           *reinterpret_cast<uint4*>(tile + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = make_uint4(r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
         __syncwarp();
-        const int cchunk = lane & 7, rsub = lane >> 3;
-        const int col = col0 + cchunk * 4;
         float cs[4] = {0.f, 0.f, 0.f, 0.f};              // column sums of the stored values (bias gradient)
         if (col < p.N) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          // issue every global read of this chunk first (8 independent 16-byte loads per lane): the epilogue is
-          // latency-bound on HBM unless ~40 KB per SM are in flight
-          float4 res[8];
-          uint2 ax[8];
-          if (has_res) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rsub;
-              if (rr < nrows) res[it] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)(row0 + rr) * (size_t)p.ldc + col));
-            }
-          }
-          if (need_aux) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rsub;
-              if (rr < nrows) ax[it] = __ldg(reinterpret_cast<const uint2*>(p.aux + (size_t)(row0 + rr) * (size_t)p.ldc + col));
-            }
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
+          auto body = [&](int it) {
             const int rr = it * 4 + rsub;
-            if (rr < nrows) {
-              const float4 t = *reinterpret_cast<const float4*>(tile + rr * 32 + ((cchunk ^ (rr & 7)) << 2));
-              float v[4] = {t.x + b4.x, t.y + b4.y, t.z + b4.z, t.w + b4.w};
-              const size_t off = (size_t)(row0 + rr) * (size_t)p.ldc + col;
-              if (has_pre)
-                *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-              if constexpr (EPI == E_GELU_FWD) {
+            const float4 t = *reinterpret_cast<const float4*>(tile + rr * 32 + ((cchunk ^ (rr & 7)) << 2));
+            float v[4] = {t.x + b4.x, t.y + b4.y, t.z + b4.z, t.w + b4.w};
+            const size_t off = off0 + it * ostep;
+            if (has_pre)
+              *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            if constexpr (EPI == E_GELU_FWD) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
-              } else if constexpr (EPI == E_GELU_BWD) {
-                const float2 lo = unpack_bf16x2(ax[it].x), hi = unpack_bf16x2(ax[it].y);
-                v[0] *= gelu_erf_grad(lo.x); v[1] *= gelu_erf_grad(lo.y); v[2] *= gelu_erf_grad(hi.x); v[3] *= gelu_erf_grad(hi.y);
-              } else if constexpr (GEN) {
-                if (p.act != EAVIT_ACT_NONE) {
-                  float a[4] = {0.f, 0.f, 0.f, 0.f};
-                  if (need_aux) {
-                    const float2 lo = unpack_bf16x2(ax[it].x), hi = unpack_bf16x2(ax[it].y);
-                    a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
-                  }
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act, a[i]);
+              for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
+            } else if constexpr (EPI == E_GELU_BWD) {
+              v[0] *= gelu_erf_grad(__uint_as_float(ax[it].x << 16)); v[1] *= gelu_erf_grad(__uint_as_float(ax[it].x & 0xffff0000u));
+              v[2] *= gelu_erf_grad(__uint_as_float(ax[it].y << 16)); v[3] *= gelu_erf_grad(__uint_as_float(ax[it].y & 0xffff0000u));
+            } else if constexpr (GEN) {
+              if (p.act != EAVIT_ACT_NONE) {
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
+                if (need_aux) {
+                  const float2 lo = unpack_bf16x2(ax[it].x), hi = unpack_bf16x2(ax[it].y);
+                  a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
                 }
-              }
-              if constexpr (DROP) {                     // nn.Dropout after the Linear / activation
-                float dm[4];
-                drop4(p.drop, drop_row_key(p.drop, (uint32_t)(row0 + rr)), (uint32_t)col, dm);
-                v[0] *= dm[0]; v[1] *= dm[1]; v[2] *= dm[2]; v[3] *= dm[3];
-              }
-              if (has_res) { v[0] += res[it].x; v[1] += res[it].y; v[2] += res[it].z; v[3] += res[it].w; }
-              cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
-              if (out_f32) {
-                if (atomic) {
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) atomicAdd(p.out_f32 + off + i, v[i]);
-                } else {
-                  *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
-                }
+                for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act, a[i]);
               }
-              if (out_b16)
-                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
             }
+            if constexpr (DROP) {                     // nn.Dropout after the Linear / activation
+              float dm[4];
+              drop4(p.drop, drop_row_key(p.drop, (uint32_t)(row0 + rr)), (uint32_t)col, dm);
+              v[0] *= dm[0]; v[1] *= dm[1]; v[2] *= dm[2]; v[3] *= dm[3];
+            }
+            if (has_res) { v[0] += res[it].x; v[1] += res[it].y; v[2] += res[it].z; v[3] += res[it].w; }
+            if constexpr (CS) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
+            if (out_f32) {
+              if (atomic) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) atomicAdd(p.out_f32 + off + i, v[i]);
+              } else {
+                *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
+              }
+            }
+            if (out_b16)
+              *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+          };
+          if (nrows >= 32) {                               // full tile rows (all but the last M tile): no per-row predicates
+#pragma unroll
+            for (int it = 0; it < 8; ++it) body(it);
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (it * 4 + rsub < nrows) body(it);
           }
         }
         if (p.colsum != nullptr) {                         // warp-uniform
@@ -425,6 +436,8 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
     const bool plain = !a->residual && !a->aux_bf16 && !a->out_pre_bf16;
     if (a->atomic_f32 && none && plain && !a->bias && !a->out_bf16) return launch_gemm<256, E_ATOMIC>(a, st);
     if (a->atomic_f32) return launch_gemm<256, E_GENERIC>(a, st);
+    if (a->colsum != nullptr && a->act != EAVIT_ACT_GELU_BWD)      // only the GELU' and generic epilogues carry column sums
+      return drop ? launch_gemm<256, E_GENERIC, true>(a, st) : launch_gemm<256, E_GENERIC>(a, st);
     if (a->act == EAVIT_ACT_GELU && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32)
       return drop ? launch_gemm<256, E_GELU_FWD, true>(a, st) : launch_gemm<256, E_GELU_FWD>(a, st);
     if (a->act == EAVIT_ACT_GELU_BWD && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
