@@ -72,10 +72,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, grp = warp >> 2;   // 4 groups of 4 warps
-  const int g = grp & 1;                        // query tile
+  const int g = grp & 1;                        // warp group (8 warps): owns TMEM region g, P buffer g, barriers g
   const int hf = grp >> 1;                      // column half of the tile's score row
   const int row_in_tile = quad * 32 + lane;
-  const int xrow = g * 128 + row_in_tile;
+  const int xslot = g * 128 + row_in_tile;      // max / sum exchange slot (private to the group)
 
   for (int i = tid; i < AttSmem::OFF_X / 16; i += ATC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
@@ -124,21 +124,32 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
     const int NKT = (S + 31) & ~31;                  // score columns
     const int NKP = (S + 15) & ~15;                  // keys covered by the P.V MMA
     const bool two_tiles = S > 128;
+    const int nt = two_tiles ? 2 : 1;
     tc::mbar_wait(bar_qk, ph_ld);
-    const bool active = g * 128 < S;
     const bool has_next = item + (int)gridDim.x < n_items;
+    // Work split.  Dh = 32 (two heads per staged row): group g owns head g and walks its query tiles, group 0 upwards
+    // and group 1 downwards -- with 196/197 tokens one group is in its long (128-row) tile while the other is in its
+    // short one, so their MMA round trips and softmax phases interleave instead of running in lock step.
+    // Dh = 64 (one head per item): group g owns query tile g.
+    const int nsub0 = HPB == 2 ? nt : 1, nsub1 = HPB == 2 ? nt : (nt - 1);
+    const int nsub = g ? nsub1 : nsub0;
+    const int hd = HPB == 2 ? g : 0;
+    const int h = hg * HPB + hd;
+    const uint32_t hoff = (uint32_t)(hd * DH * 2);     // byte offset of this head inside the 128-byte rows
+    const int v_issuer_grp = nsub1 > 0 ? 1 : 0;        // the group that finishes last refills V (group 1 ends on its long tile)
 #pragma unroll 1
-    for (int hd = 0; hd < HPB; ++hd) {
-      const int h = hg * HPB + hd;
-      const uint32_t hoff = (uint32_t)(hd * DH * 2);   // byte offset of this head inside the 128-byte rows
-      if (active) {
-        const uint32_t phase = g ? ph1 : ph0;
+    for (int j = 0; j < nsub; ++j) {
+      const int tl = HPB == 2 ? (g ? nt - 1 - j : j) : g;      // query tile of this sub-item
+      const int xrow = tl * 128 + row_in_tile;
+      const bool last = j == nsub - 1;
+      {
+        const uint32_t phase = (g ? ph1 : ph0) ^ (uint32_t)(j & 1);
         const uint32_t s_col = tmem_base + (uint32_t)(g * ATC_MAXKEYS);
         const bool issuer = (hf == 0 && quad == 0 && lane == 0);
         if (issuer) {
           tc::fence_after_sync();
           const uint32_t idesc = tc::make_idesc_bf16(128, NKT, 0, 0);
-          const uint32_t qa = tc::smem_u32(smem + AttSmem::OFF_Q + g * 128 * ROWB) + hoff;
+          const uint32_t qa = tc::smem_u32(smem + AttSmem::OFF_Q + tl * 128 * ROWB) + hoff;
           const uint32_t ka = tc::smem_u32(smem + AttSmem::OFF_K) + hoff;
           const uint64_t adesc = tc::make_sdesc_sw128(qa, 16, 1024), bdesc = tc::make_sdesc_sw128(ka, 16, 1024);
 #pragma unroll
@@ -146,8 +157,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
           tc::mma_commit(&bar_s[g]);
         }
         tc::mbar_wait(&bar_s[g], phase);
-        if (tid == 0 && hd == HPB - 1 && has_next) {
-          if (two_tiles) tc::mbar_wait(&bar_s[1], ph1);   // the other tile's score MMA reads the same K
+        if (tid == 0 && last && has_next) {
+          // Q / K are dead once EVERY score MMA of the item is complete: the other group's last one as well
+          if (nsub1 > 0) tc::mbar_wait(&bar_s[1], ph1 ^ (uint32_t)((nsub1 - 1) & 1));
           issue_qk(item + gridDim.x);
         }
         tc::fence_after_sync();
@@ -155,7 +167,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
         const int half = NKT >> 1, cbeg = hf * half;      // half is a multiple of 16
         // Warps whose 32 query rows all lie beyond the sequence (tile 1 of a 196/197-token sequence: rows >= 224) only keep
         // the barriers company; their P rows are row-local garbage that never reaches a stored output row.
-        const bool rows_live = g * 128 + quad * 32 < S;
+        const bool rows_live = tl * 128 + quad * 32 < S;
         // pass 1: partial row max over this thread's columns (TMEM loads software-pipelined against the compares)
         float mx = -INFINITY;
         if (rows_live) {
@@ -170,9 +182,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
             }
           });
         }
-        sMax[hf * 256 + xrow] = mx;
+        sMax[hf * 256 + xslot] = mx;
         named_bar_sync(1 + g, 256);
-        mx = fmaxf(sMax[xrow], sMax[256 + xrow]);
+        mx = fmaxf(sMax[xslot], sMax[256 + xslot]);
         // pass 2: p = exp2((s - mx) * c2) -> bf16 P tile in swizzled smem; the row sum is taken in fp32 before rounding
         // (|sum(p~) - sum(p)| / sum(p) ~ 2^-9 / sqrt(S), far below the bf16 rounding of the output)
         const float mb = mx * c2;
@@ -218,13 +230,13 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
             *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           });
         }
-        sSum[hf * 256 + xrow] = sum;
+        sSum[hf * 256 + xslot] = sum;
         // all S reads done (O overlays S) and P visible to the async proxy, then one thread issues P.V
         tc::fence_before_sync();
         tc::fence_proxy_async();
         named_bar_sync(1 + g, 256);
         if (issuer) {
-          if (hd == 0) tc::mbar_wait(bar_v, ph_ld);
+          if (j == 0) tc::mbar_wait(bar_v, ph_ld);
           tc::fence_after_sync();
           const uint32_t idesc = tc::make_idesc_bf16(128, DH, 0, 1);
           const uint32_t pa = tc::smem_u32(pbase);
@@ -236,10 +248,12 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
           }
           tc::mma_commit(&bar_o[g]);
         }
-        sum = sSum[xrow] + sSum[256 + xrow];
+        sum = sSum[xslot] + sSum[256 + xslot];
         tc::mbar_wait(&bar_o[g], phase);
-        if (tid == 0 && hd == HPB - 1 && has_next) {
-          if (two_tiles) tc::mbar_wait(&bar_o[1], ph1);   // both tiles' P.V done: V can be refilled
+        if (issuer && g == v_issuer_grp && last && has_next) {
+          // V is dead once every P.V MMA of the item is complete: wait for the other group's last one, then refill
+          const int og = g ^ 1, onsub = og ? nsub1 : nsub0;
+          if (onsub > 0) tc::mbar_wait(&bar_o[og], (og ? ph1 : ph0) ^ (uint32_t)((onsub - 1) & 1));
           issue_v(item + gridDim.x);
         }
         tc::fence_after_sync();
@@ -267,12 +281,12 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
         }
         tc::fence_before_sync();
       }
-      ph0 ^= 1;
-      if (two_tiles) ph1 ^= 1;
-      // TMEM (O overlays S), the P buffer and the max / sum exchange slots are private to the tile group: only the
-      // group has to agree that they are free for the next head / item
-      if (active) named_bar_sync(1 + g, 256);
+      // TMEM (O overlays S), the P buffer and the max / sum exchange slots are private to the group: only the group
+      // has to agree that they are free for the next sub-item / item
+      named_bar_sync(1 + g, 256);
     }
+    ph0 ^= (uint32_t)(nsub0 & 1);
+    ph1 ^= (uint32_t)(nsub1 & 1);
     ph_ld ^= 1;
   }
   tc::fence_before_sync();
