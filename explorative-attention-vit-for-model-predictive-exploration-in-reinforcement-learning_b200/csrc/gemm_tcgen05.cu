@@ -349,6 +349,10 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
                       uint32_t box_outer) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return EAVIT_ECUDA;
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context current on the calling thread.  Threads that
+  // have only been handed work (torch's autograd worker threads) may not have touched the runtime yet.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {64, box_outer};

@@ -127,3 +127,13 @@ def test_no_cpu_fallback():
         ac(torch.zeros(1, 4, 84, 84))
     with pytest.raises(RuntimeError):
         utils.make_train_data(np.zeros((2, 4)), np.zeros((2, 4), dtype=bool), np.zeros((2, 5), dtype=np.float32), 0.99, 4, 2)
+
+
+def test_torch_custom_ops_are_registered_and_cuda_only():
+    """torch.ops.eavit_b200.* exist after import (torch.library) and refuse CPU tensors: no fallback path."""
+    import eavit_b200  # noqa: F401
+    for name in ("linear", "layer_norm", "attention", "gae", "intrinsic_mse", "obs_normalize"):
+        assert hasattr(torch.ops.eavit_b200, name), name
+    x = torch.randn(4, 8).bfloat16()
+    with pytest.raises(NotImplementedError):
+        torch.ops.eavit_b200.linear(x, x, None)
