@@ -32,6 +32,11 @@ import torch  # noqa: E402
 E_PER_GPU, T, A = 128, 128, 18
 MINI_BATCH, EPOCH = 32, 4
 FLOPS_PER_SAMPLE = 6.36e9 + 58.2e6      # ViT+heads fwd+bwd + RND training, per sample
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the cfg3 shapes (ncu --set full, profiles/)
+NCU_DRAM_BYTES_PER_LAUNCH = {
+    "attention_bwd_tc": 686.3e6, "attention_fwd_tc": 396.6e6,
+    "gemm_bf16_tcgen05 M=201216 N=1024 K=256 kmn act=2": 895.3e6, "gemm_bf16_tcgen05 M=201216 N=1024 K=256 kk act=1": 874.3e6,
+}
 WORKLOAD = ("cfg3: lucidrains explorative-attention ViT (expGlados3) RND agent, 128 envs x 128 steps per GPU, "
             "minibatch 512, 4 epochs, dropout keys 0.0")
 
@@ -62,7 +67,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
@@ -157,7 +162,7 @@ def cpu_reference(steps, warmup, batch=32, threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
@@ -246,11 +251,14 @@ def main():
         g = label.split(" ")[0]
         a = groups.setdefault(g, [0, 0.0, 0.0])
         a[0] += n; a[1] += tms; a[2] += flops * n
+    # dominant kernel = largest share of the step among the dense-contraction kernels (every one carries its algorithmic FLOPs)
     dom_label, (dn, dms, dfl) = max(((l, v) for l, v in table.items() if v[2] > 0), key=lambda kv: kv[1][1])
     gemm = groups.get("gemm_bf16_tcgen05", [0, 0.0, 0.0])
-    achieved = dfl * dn / (dms * 1e-3) / 1e12
+    achieved = dfl / (dms / dn * 1e-3) / 1e12
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r1_ncu_full_top_kernels.md)
+    traffic = next((v for k, v in NCU_DRAM_BYTES_PER_LAUNCH.items() if dom_label.startswith(k)), None)
     roofline = {"bound": "tensor", "kernel": dom_label, "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": f"{pk_kind} burst bf16 (kernel timed alone per launch)",
+                "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "peak_source": f"{pk_kind} burst bf16 (kernel timed alone per launch)",
                 "avg_launch_us": dms / dn * 1e3, "share_of_step": dms / tot_ms,
                 "all_gemm": {"launches_per_step": gemm[0] / nprof, "share_of_step": gemm[1] / tot_ms,
                              "achieved_tflops": gemm[2] / (gemm[1] * 1e-3) / 1e12 if gemm[1] > 0 else None},

@@ -264,6 +264,9 @@ def _bind(name):
     return _bound[name]
 
 
+_FLOPS_HINT = {}      # one-shot algorithmic FLOP count for the next profiled launch of an entry point (bench.py roofline)
+
+
 def call(name: str, *args):
     """Invoke a C-ABI entry point with torch tensors / python scalars; raises on non-zero status."""
     fn, spec = _bound.get(name) or _bind(name)
@@ -279,7 +282,7 @@ def call(name: str, *args):
         else:
             conv.append(a)
     if _PROF is not None:
-        with _Timed(name[len("eavit_"):]):
+        with _Timed(name[len("eavit_"):], _FLOPS_HINT.pop(name, 0.0)):
             rc = fn(*conv, torch.cuda.current_stream().cuda_stream)
     else:
         rc = fn(*conv, torch.cuda.current_stream().cuda_stream)
@@ -310,6 +313,8 @@ def dropout_mask(n: int, ncols: int, p: float, seed: int, row0: int = 0, col0: i
 def attention_fwd(qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse, drop_p: float = 0.0, drop_seed: int = 0):
     """tcgen05 kernel when the sequence fits its TMEM plan (S <= 224), CUDA-core kernel for longer sequences."""
     if max_len <= 224:
+        if _PROF is not None:      # 4 * S^2 * Dh per (sequence, head): QK^T and PV (S = max_len; cfg3: 196/197 vs 197)
+            _FLOPS_HINT["eavit_attention_fwd_tc"] = 4.0 * nseq * H * max_len * max_len * Dh
         call("eavit_attention_fwd_tc", qkv, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, out, lse, float(drop_p),
              int(drop_seed) & _M64)
     else:
@@ -320,6 +325,8 @@ def attention_fwd(qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse, drop_p:
 
 def attention_bwd(qkv, out, dout, lse, seq_start, nseq, max_len, H, Dh, scale, dqkv, drop_p: float = 0.0, drop_seed: int = 0):
     if (Dh == 32 and max_len <= 224) or (Dh == 64 and max_len <= 128):
+        if _PROF is not None:      # S, dP (recomputed), dV, dK, dQ: 5 contractions of 2 * S^2 * Dh
+            _FLOPS_HINT["eavit_attention_bwd_tc"] = 10.0 * nseq * H * max_len * max_len * Dh
         call("eavit_attention_bwd_tc", qkv, dout, lse, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, dqkv, float(drop_p),
              int(drop_seed) & _M64)
     else:
