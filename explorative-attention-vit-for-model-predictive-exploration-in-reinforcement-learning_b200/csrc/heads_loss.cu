@@ -9,51 +9,63 @@ namespace eavit {
 // C[M,N] (+)= mask(act(op(A) . op(B) + bias))      fp32, 32x32 tiles, 16x16 threads x (2x2) outputs
 //   transA = 0: A[M,K] pitch lda ; 1: A stored [K,M]
 //   transB = 0: B[N,K] pitch ldb (nn.Linear weight) ; 1: B stored [K,N]
+// 64 x 64 output tile per CTA, 4 x 4 micro-tile per thread, K in steps of 16; blockIdx.z splits K (accumulate only,
+// atomicAdd) so that the weight-gradient shapes (M = N = 256, K = rows) fill the machine instead of 16 CTAs.
 __global__ void __launch_bounds__(256) sgemm_small_kernel(const float* __restrict__ A, long long lda, int transA,
                                                           const float* __restrict__ B, long long ldb, int transB,
                                                           const float* __restrict__ bias, const float* __restrict__ mask_aux,
                                                           float* __restrict__ C, long long ldc, int M, int N, int K, int relu,
-                                                          int accumulate) {
-  __shared__ float sA[16][33];   // [k][m]
-  __shared__ float sB[16][33];   // [k][n]
+                                                          int accumulate, int k_per_split) {
+  __shared__ float sA[16][68];   // [k][m]
+  __shared__ float sB[16][68];   // [k][n]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 512; i += 256) {
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+    for (int i = threadIdx.x; i < 1024; i += 256) {
       int kk, mm;
-      if (transA) { mm = i & 31; kk = i >> 5; } else { kk = i & 15; mm = i >> 4; }
+      if (transA) { mm = i & 63; kk = i >> 6; } else { kk = i & 15; mm = i >> 4; }
       const int gm = m0 + mm, gk = k0 + kk;
       float v = 0.f;
-      if (gm < M && gk < K) v = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      if (gm < M && gk < kend) v = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
       sA[kk][mm] = v;
       int nn;
-      if (transB) { nn = i & 31; kk = i >> 5; } else { kk = i & 15; nn = i >> 4; }
-      const int gn = n0 + nn;
-      const int gk2 = k0 + kk;
+      if (transB) { nn = i & 63; kk = i >> 6; } else { kk = i & 15; nn = i >> 4; }
+      const int gn = n0 + nn, gk2 = k0 + kk;
       v = 0.f;
-      if (gn < N && gk2 < K) v = transB ? B[(size_t)gk2 * ldb + gn] : B[(size_t)gn * ldb + gk2];
+      if (gn < N && gk2 < kend) v = transB ? B[(size_t)gk2 * ldb + gn] : B[(size_t)gn * ldb + gk2];
       sB[kk][nn] = v;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      const float a0 = sA[kk][ty], a1 = sA[kk][ty + 16], b0 = sB[kk][tx], b1 = sB[kk][tx + 16];
-      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty + 16 * i]; b[i] = sB[kk][tx + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < 4; ++j) {
       const int gm = m0 + ty + 16 * i, gn = n0 + tx + 16 * j;
       if (gm < M && gn < N) {
         float v = acc[i][j];
+        float* c = C + (size_t)gm * ldc + gn;
+        if (gridDim.z > 1) { atomicAdd(c, v); continue; }      // split-K: plain accumulation only (checked on the host)
         if (bias != nullptr) v += bias[gn];
         if (relu) v = fmaxf(v, 0.f);
         if (mask_aux != nullptr && !(mask_aux[(size_t)gm * ldc + gn] > 0.f)) v = 0.f;
-        float* c = C + (size_t)gm * ldc + gn;
         *c = accumulate ? (*c + v) : v;
       }
     }
@@ -80,28 +92,28 @@ __global__ void __launch_bounds__(256) heads_value_bwd_kernel(const float* __res
                                                               float* __restrict__ dE, float* __restrict__ dF,
                                                               float* __restrict__ dwA, float* __restrict__ dbA,
                                                               float* __restrict__ dwB, float* __restrict__ dbB) {
-  // blockIdx.x in {0,1}: half A = rows [0,split), half B = rows [split,R)
-  const int r0 = blockIdx.x == 0 ? 0 : split, r1 = blockIdx.x == 0 ? split : R;
-  const float* w = blockIdx.x == 0 ? wA : wB;
-  float* dw = blockIdx.x == 0 ? dwA : dwB;
-  float* db = blockIdx.x == 0 ? dbA : dbB;
-  if (r1 <= r0) return;
+  // one CTA per chunk of 32 rows (was: 2 CTAs looping over R/2 rows each -- 125 us of pure latency); the weight / bias
+  // gradients of the two critics are combined with one atomicAdd per column per CTA.  Rows [0,split) use head A.
+  const int r0 = blockIdx.x * 32, r1 = min(R, r0 + 32);
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    const float wc = w[c];
-    float acc = 0.f;
+    const float wa = wA[c], wb = wB[c];
+    float accA = 0.f, accB = 0.f;
     for (int r = r0; r < r1; ++r) {
       const float e = E[(size_t)r * D + c], f = F[(size_t)r * D + c], g = dv[r];
-      const float dh = g * wc;
+      const bool isA = r < split;
+      const float dh = g * (isA ? wa : wb);
       dF[(size_t)r * D + c] = dh;
       dE[(size_t)r * D + c] = e > 0.f ? dh : 0.f;
-      acc += g * (e + f);
+      if (isA) accA += g * (e + f); else accB += g * (e + f);
     }
-    dw[c] += acc;
+    if (r0 < split) atomicAdd(dwA + c, accA);
+    if (r1 > split) atomicAdd(dwB + c, accB);
   }
   if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += dv[r];
-    db[0] += s;
+    float sa = 0.f, sb = 0.f;
+    for (int r = r0; r < r1; ++r) { if (r < split) sa += dv[r]; else sb += dv[r]; }
+    if (r0 < split) atomicAdd(dbA, sa);
+    if (r1 > split) atomicAdd(dbB, sb);
   }
 }
 
@@ -271,8 +283,18 @@ int eavit_sgemm_small(const float* A, long long lda, int transA, const float* B,
                       const float* bias, const float* mask_aux, float* C, long long ldc, int M, int N, int K, int relu,
                       int accumulate, void* stream) {
   EAVIT_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0);
-  dim3 grid(cdiv(N, 32), cdiv(M, 32));
-  sgemm_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, transA, B, ldb, transB, bias, mask_aux, C, ldc, M, N, K, relu, accumulate);
+  // split K when the output has too few tiles to fill the GPU (weight gradients: K = number of rows) -- accumulate only
+  const int tiles = cdiv(N, 64) * cdiv(M, 64);
+  int splits = 1;
+  if (accumulate && !bias && !mask_aux && !relu && tiles < kNumSMs && K >= 256) {
+    splits = kNumSMs / tiles;
+    if (splits > K / 64) splits = K / 64;
+    if (splits < 1) splits = 1;
+  }
+  int kps = cdiv(cdiv(K, splits), 16) * 16;
+  splits = cdiv(K, kps);
+  dim3 grid(cdiv(N, 64), cdiv(M, 64), splits);
+  sgemm_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, transA, B, ldb, transB, bias, mask_aux, C, ldc, M, N, K, relu, accumulate, kps);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -288,7 +310,7 @@ int eavit_heads_value_fwd(const float* E, const float* F, const float* wA, const
 int eavit_heads_value_bwd(const float* E, const float* F, const float* dv, const float* wA, const float* wB, int split,
                           int R, int D, float* dE, float* dF, float* dwA, float* dbA, float* dwB, float* dbB, void* stream) {
   EAVIT_CHECK_ARG(E && F && dv && wA && wB && dE && dF && dwA && dbA && dwB && dbB && R > 0 && D > 0);
-  heads_value_bwd_kernel<<<2, 256, 0, (cudaStream_t)stream>>>(E, F, dv, wA, wB, split, R, D, dE, dF, dwA, dbA, dwB, dbB);
+  heads_value_bwd_kernel<<<cdiv(R, 32), 256, 0, (cudaStream_t)stream>>>(E, F, dv, wA, wB, split, R, D, dE, dF, dwA, dbA, dwB, dbB);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
