@@ -74,7 +74,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
 enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5 };
 // The GELU epilogues are issue/latency-bound (16 instructions + 2 MUFU per element): 16 warps.  The store / residual /
 // atomic epilogues are HBM-bound and want registers for loads in flight instead: 8 warps.
-template <int EPI> struct EpiWarps { static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_BWD) ? 16 : 8; };
+template <int EPI> struct EpiWarps { static constexpr int N = (EPI == E_GELU_FWD || EPI == E_STORE) ? 16 : (EPI == E_GELU_BWD ? 12 : 8); };
 
 template <int BN, int EPI, bool DROP>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
 __global__ void __launch_bounds__((CTRL_WARPS + EpiWarps<EPI>::N) * 32, 1)
