@@ -203,6 +203,47 @@ __global__ void __launch_bounds__(256) rms_partial_kernel(const T* __restrict__ 
   for (int i = 0; i < V; ++i) { o[cv * V + i] = s[i]; o[F + cv * V + i] = q[i]; }
 }
 
+// uint8 frames: sum(x) and sum(x^2) over a row split are accumulated EXACTLY in 32-bit integers (<= 65025 * rows), then
+// shifted algebraically in float64:  sum(x - s) = Sx - n s,  sum((x - s)^2) = Sxx - 2 s Sx + n s^2.  One IMAD per element
+// instead of an int->double conversion and three double-precision operations (the first version reached 0.8-1.6 TB/s).
+__global__ void __launch_bounds__(256) rms_partial_u8_kernel(const uint8_t* __restrict__ x, long long N, int F,
+                                                             const double* __restrict__ shift,
+                                                             double* __restrict__ ws, int rows_per_split) {
+  constexpr int V = 4;                                       // 4 pixels (one 32-bit load) per thread: F/4 column threads
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cv * V >= F) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_split;
+  const long long r1 = min(N, r0 + rows_per_split);
+  uint32_t s[V] = {0u, 0u, 0u, 0u}, q[V] = {0u, 0u, 0u, 0u};
+  const uint8_t* p = x + r0 * F + (long long)cv * V;
+  auto acc = [&](uint32_t w) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t b = (w >> (8 * j)) & 0xffu;
+      s[j] += b;
+      q[j] += b * b;
+    }
+  };
+  long long r = r0;
+  for (; r + 16 <= r1; r += 16) {                            // 16 independent loads in flight per thread
+    uint32_t u[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) u[k] = __ldg(reinterpret_cast<const uint32_t*>(p + (long long)k * F));
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc(u[k]);
+    p += 16LL * F;
+  }
+  for (; r < r1; ++r) { acc(__ldg(reinterpret_cast<const uint32_t*>(p))); p += F; }
+  const double n = (double)(r1 - r0);
+  double* o = ws + (long long)blockIdx.y * 2 * F;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const double sh = shift[cv * V + i], sx = (double)s[i], sxx = (double)q[i];
+    o[cv * V + i] = sx - n * sh;
+    o[F + cv * V + i] = fma(n * sh, sh, fma(-2.0 * sh, sx, sxx));
+  }
+}
+
 // Deterministic merge over splits; mode 0 -> write (sum, sumsq) for the moment all-reduce,
 // mode 1 -> Chan merge into the running state (utils.py:101-115).
 __global__ void rms_reduce_kernel(const double* __restrict__ ws, int splits, int F, double batch_count,
@@ -235,7 +276,7 @@ __global__ void add_count_kernel(double* count, double n_b) { count[0] = n_b + c
 
 static int rms_splits(long long N, int F, int V) {
   const int col_blocks = cdiv(cdiv(F, V), 256);
-  long long want = (4LL * kNumSMs + col_blocks - 1) / col_blocks;   // ~4 CTAs per SM
+  long long want = (8LL * kNumSMs + col_blocks - 1) / col_blocks;   // ~8 CTAs per SM (loads are not software-pipelined)
   if (want > N) want = N;
   if (want < 1) want = 1;
   if (want > 1024) want = 1024;
@@ -245,14 +286,21 @@ static int rms_splits(long long N, int F, int V) {
 template <typename T>
 static int rms_partial_launch(const void* x, long long N, int F, const double* shift, double* ws, int& splits,
                               cudaStream_t st) {
-  constexpr int V = VecLoad<T>::V;
+  constexpr int V = sizeof(T) == 1 ? 4 : VecLoad<T>::V;
   EAVIT_CHECK_ARG(F % V == 0);
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   splits = rms_splits(N, F, V);
-  const int rows = cdiv(N, splits);
+  if (sizeof(T) == 1) splits = (splits + 1) / 2;                      // 4 CTAs / SM: 16 rows in flight per thread already
+  int rows = cdiv(N, splits);
+  if (sizeof(T) == 1 && rows < 64 && N >= 64) rows = 64;              // keep the workspace (2 F doubles per split) small
   splits = cdiv(N, rows);
   dim3 grid(cdiv(cdiv(F, V), 256), splits);
-  rms_partial_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), N, F, shift, ws, rows);
+  if constexpr (sizeof(T) == 1) {
+    EAVIT_CHECK_ARG(rows <= 65536);                                   // 32-bit sums of squares stay exact
+    rms_partial_u8_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), N, F, shift, ws, rows);
+  } else {
+    rms_partial_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), N, F, shift, ws, rows);
+  }
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -279,17 +327,23 @@ __global__ void __launch_bounds__(256) obs_normalize_kernel(const T* __restrict_
   constexpr int V = VecLoad<T>::V;
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   if (cv * V >= F) return;
-  double m[V], sd[V];
+  double m[V], sd[V], ri[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) { m[i] = mean[cv * V + i]; sd[i] = sqrt(var[cv * V + i]); }   // np.sqrt(obs_rms.var)
+  for (int i = 0; i < V; ++i) {
+    m[i] = mean[cv * V + i];
+    sd[i] = sqrt(var[cv * V + i]);                                   // np.sqrt(obs_rms.var)
+    ri[i] = __drcp_rn(sd[i]);
+  }
   const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(N, r0 + rows_per_split);
-  for (long long r = r0; r < r1; ++r) {
-    double a[V];
-    VecLoad<T>::load(x + r * F + (long long)cv * V, a);
+  auto emit = [&](const double* a, long long r) {
     float y[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      double z = __ddiv_rn(a[i] - m[i], sd[i]);                     // (x - mean) / sqrt(var), float64
+      // (x - mean) / sqrt(var) in float64, correctly rounded: q = n * (1/sd), one exact-residual correction
+      // (Markstein) -- the same result as __ddiv_rn without its ~30-instruction slow path per element
+      const double n = a[i] - m[i];
+      const double q = n * ri[i];
+      double z = fma(fma(-q, sd[i], n), ri[i], q);
       z = fmin(fmax(z, -5.0), 5.0);                                  // .clip(-5, 5)
       y[i] = (float)z;                                               // torch.FloatTensor(...)
     }
@@ -316,7 +370,66 @@ __global__ void __launch_bounds__(256) obs_normalize_kernel(const T* __restrict_
           *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(o) + i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
       }
     }
+  };
+  constexpr int U = V >= 16 ? 2 : 4;                                  // rows in flight per thread (register budget)
+  long long r = r0;
+  for (; r + U <= r1; r += U) {
+    double a[U][V];
+#pragma unroll
+    for (int k = 0; k < U; ++k) VecLoad<T>::load(x + (r + k) * F + (long long)cv * V, a[k]);
+#pragma unroll
+    for (int k = 0; k < U; ++k) emit(a[k], r + k);
   }
+  for (; r < r1; ++r) {
+    double a[V];
+    VecLoad<T>::load(x + r * F + (long long)cv * V, a);
+    emit(a, r);
+  }
+}
+
+// uint8 frames, many rows: every pixel column has only 256 possible inputs, so each CTA builds the exact float64 result
+// for its 32 columns x 256 values once (a 32 KB / 16 KB table in shared memory) and then streams its rows with one
+// shared-memory lookup per element -- no double-precision work per element, identical bits.
+template <typename O>
+__global__ void __launch_bounds__(256) obs_normalize_u8_lut_kernel(const uint8_t* __restrict__ x, long long N, int F,
+                                                                   const double* __restrict__ mean,
+                                                                   const double* __restrict__ var, O* __restrict__ out,
+                                                                   int rows_per_split) {
+  __shared__ O lut[32 * 256];                                          // [value][column]: lanes of a warp hit distinct banks
+  const int c0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 32 * 256; i += blockDim.x) {
+    const int c = i & 31, v = i >> 5;
+    float y = 0.f;
+    if (c0 + c < F) {
+      const double m = mean[c0 + c], sd = sqrt(var[c0 + c]);
+      double z = __ddiv_rn((double)v - m, sd);
+      z = fmin(fmax(z, -5.0), 5.0);
+      y = (float)z;
+    }
+    if constexpr (sizeof(O) == 4) lut[i] = y; else lut[i] = __float2bfloat16(y);
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 7, rsub = threadIdx.x >> 3;             // 8 threads x 4 pixels cover the 32 columns of a row
+  const int c = c0 + cg * 4;
+  if (c >= F) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(N, r0 + rows_per_split);
+  auto emit = [&](uint32_t w, long long r) {
+    O y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = lut[((w >> (8 * j)) & 0xffu) * 32 + cg * 4 + j];
+    O* o = out + r * F + c;
+    if constexpr (sizeof(O) == 4) *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+    else *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(y);
+  };
+  long long r = r0 + rsub;
+  for (; r + 7 * 32 < r1; r += 8 * 32) {                               // 8 rows in flight per thread
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __ldg(reinterpret_cast<const uint32_t*>(x + (r + 32 * k) * F + c));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) emit(w[k], r + 32 * k);
+  }
+  for (; r < r1; r += 32) emit(__ldg(reinterpret_cast<const uint32_t*>(x + r * F + c)), r);
 }
 
 template <typename T, typename O>
@@ -325,6 +438,19 @@ static int obs_normalize_launch(const void* x, long long N, int F, const double*
   constexpr int V = VecLoad<T>::V;
   EAVIT_CHECK_ARG(F % V == 0);
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if constexpr (sizeof(T) == 1) {
+    if (N >= 2048 && F % 4 == 0) {                                     // table build (8192 divisions / CTA) amortised over >= 1024 rows
+      int splits = (int)((N + 2047) / 2048);
+      const int colg = cdiv(F, 32);
+      while (splits > 1 && (long long)splits * colg > 16LL * kNumSMs && N / splits < 1024) --splits;
+      const int rows = cdiv(N, splits);
+      dim3 grid(colg, cdiv(N, rows));
+      obs_normalize_u8_lut_kernel<O><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), N, F, mean, var,
+                                                           reinterpret_cast<O*>(out), rows);
+      EAVIT_LAUNCH_OK();
+      return EAVIT_OK;
+    }
+  }
   int splits = rms_splits(N, F, V) * 2;
   if (splits > N) splits = (int)N;
   const int rows = cdiv(N, splits);
