@@ -118,6 +118,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
       tc::tma_load_2d(smem + AttSmem::OFF_V + b * BOX_BYTES, &tmQKV, bar_v, 2 * H * DH + hg * 64, tt + b * BOX_ROWS);
   };
   if (tid == 0 && (int)blockIdx.x < n_items) { issue_qk(blockIdx.x); issue_v(blockIdx.x); }
+#ifdef EAVIT_TRACE
+  long long tr_acc[20] = {0}, tr_prev = clock64();
+#endif
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int seq = item / HG, hg = item - seq * HG;
     const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
@@ -126,6 +129,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
     const bool two_tiles = S > 128;
     const int nt = two_tiles ? 2 : 1;
     tc::mbar_wait(bar_qk, ph_ld);
+    TR(0);
     const bool has_next = item + (int)gridDim.x < n_items;
     // Work split.  Dh = 32 (two heads per staged row): group g owns head g and walks its query tiles, group 0 upwards
     // and group 1 downwards -- with 196/197 tokens one group is in its long (128-row) tile while the other is in its
@@ -156,7 +160,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
           for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(s_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k > 0);
           tc::mma_commit(&bar_s[g]);
         }
+        TR(1);
         tc::mbar_wait(&bar_s[g], phase);
+        TR(2);
         if (tid == 0 && last && has_next) {
           // Q / K are dead once EVERY score MMA of the item is complete: the other group's last one as well
           if (nsub1 > 0) tc::mbar_wait(&bar_s[1], ph1 ^ (uint32_t)((nsub1 - 1) & 1));
@@ -173,8 +179,12 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
         if (rows_live) {
           tc::tmem_stream16(lane_addr, cbeg, cbeg + half, [&](const uint32_t* r, int c0) {
             if (c0 + 16 <= S) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+              // four independent max chains (a single one serialises 112 dependent FMNMX per row)
+              float m0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), m1 = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
+              float m2 = fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), m3 = fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7]));
+              m0 = fmaxf(m0, fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9]))); m1 = fmaxf(m1, fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
+              m2 = fmaxf(m2, fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13]))); m3 = fmaxf(m3, fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
+              mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
@@ -183,7 +193,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
           });
         }
         sMax[hf * 256 + xslot] = mx;
+        TR(3);
         named_bar_sync(1 + g, 256);
+        TR(4);
         mx = fmaxf(sMax[xslot], sMax[256 + xslot]);
         // pass 2: p = exp2((s - mx) * c2) -> bf16 P tile in swizzled smem; the row sum is taken in fp32 before rounding
         // (|sum(p~) - sum(p)| / sum(p) ~ 2^-9 / sqrt(S), far below the bf16 rounding of the output)
@@ -198,19 +210,19 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
             if (c0 >= NKP) return;                       // beyond the keys the P.V MMA reads
             uint32_t pk[8];
             if (c0 + 16 <= S) {
-              float s0 = 0.f, s1 = 0.f;
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
                 float p0 = ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb));
                 float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb));
-                s0 += p0; s1 += p1;
+                if (j & 2) { s2 += p0; s3 += p1; } else { s0 += p0; s1 += p1; }
                 if constexpr (DROP) {
                   const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
                   p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
                 }
                 pk[j >> 1] = pack_bf16x2(p0, p1);
               }
-              sum += s0 + s1;
+              sum += (s0 + s1) + (s2 + s3);
             } else {
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
@@ -231,10 +243,12 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
           });
         }
         sSum[hf * 256 + xslot] = sum;
+        TR(5);
         // all S reads done (O overlays S) and P visible to the async proxy, then one thread issues P.V
         tc::fence_before_sync();
         tc::fence_proxy_async();
         named_bar_sync(1 + g, 256);
+        TR(6);
         if (issuer) {
           if (j == 0) tc::mbar_wait(bar_v, ph_ld);
           tc::fence_after_sync();
@@ -249,7 +263,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
           tc::mma_commit(&bar_o[g]);
         }
         sum = sSum[xslot] + sSum[256 + xslot];
+        TR(7);
         tc::mbar_wait(&bar_o[g], phase);
+        TR(8);
         if (issuer && g == v_issuer_grp && last && has_next) {
           // V is dead once every P.V MMA of the item is complete: wait for the other group's last one, then refill
           const int og = g ^ 1, onsub = og ? nsub1 : nsub0;
@@ -283,12 +299,18 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
       }
       // TMEM (O overlays S), the P buffer and the max / sum exchange slots are private to the group: only the group
       // has to agree that they are free for the next sub-item / item
+      TR(9);
       named_bar_sync(1 + g, 256);
+      TR(10);
     }
     ph0 ^= (uint32_t)(nsub0 & 1);
     ph1 ^= (uint32_t)(nsub1 & 1);
     ph_ld ^= 1;
   }
+#ifdef EAVIT_TRACE
+  if (blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 20; ++i) g_att_trace[i] += tr_acc[i];
+#endif
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) {
