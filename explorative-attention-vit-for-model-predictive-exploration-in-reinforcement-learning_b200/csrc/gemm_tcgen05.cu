@@ -233,13 +233,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
           }
         }
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        tc::tmem_ld_wait();
-        // registers (one row per lane) -> swizzled smem tile -> (4 rows x 8 lanes x 16 B) per instruction
+        // registers (one row per lane) -> swizzled smem tile -> (4 rows x 8 lanes x 16 B) per instruction; two 16-column
+        // halves so that only 16 accumulator registers are live next to the prefetched residual / aux values
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4)
-          *reinterpret_cast<uint4*>(tile + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = make_uint4(r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[16];
+          tc::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32 + hh * 16), r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            *reinterpret_cast<uint4*>(tile + lane * 32 + (((hh * 4 + c4) ^ (lane & 7)) << 2)) = make_uint4(r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
+        }
         __syncwarp();
         float cs[4] = {0.f, 0.f, 0.f, 0.f};              // column sums of the stored values (bias gradient)
         if (col < p.N) {
