@@ -122,10 +122,25 @@ class _Buffers:
 
 
 def _split_k(M: int, N: int, K: int) -> int:
-    # tiles * splits <= 148: one wave of the persistent grid (149 work items would cost a whole second wave)
+    """K splits of a weight-gradient GEMM: the smallest count whose work items (tiles * splits) fill the persistent
+    148-CTA grid to >= 90 % in whole waves (149 items would cost a second wave; 96 tiles alone leave a third of the SMs
+    idle, 96 * 3 = 288 items fill two waves to 97 %), with at least 8 k-blocks per split."""
     tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
-    s = max(1, 148 // tiles)
-    return max(1, min(s, (K + 63) // 64))
+    kb = (K + 63) // 64
+    one_wave = max(1, min(148 // tiles, kb))
+    if tiles * one_wave >= 0.85 * 148:
+        return one_wave
+    best, best_eff = one_wave, tiles * one_wave / 148.0
+    for sp in range(one_wave + 1, 149):
+        if kb // sp < 8:
+            break
+        items = tiles * sp
+        eff = items / (148.0 * ((items + 147) // 148))
+        if eff >= 0.9:
+            return sp
+        if eff > best_eff + 1e-9:
+            best, best_eff = sp, eff
+    return best
 
 
 def linear_fwd(x16, w16, *, bias=None, act=ops.ACT_NONE, residual=None, out_f32=None, out_bf16=None, out_pre=None,
