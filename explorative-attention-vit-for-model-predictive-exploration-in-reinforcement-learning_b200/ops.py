@@ -227,6 +227,8 @@ _SPECS = {
     "eavit_attention_fwd_tc": "ppiiliifpp" "fu",
     "eavit_attention_bwd": "pppppiiiifp",
     "eavit_attention_bwd_tc": "ppppiiliifp" "fu",
+    "eavit_attention_row0_fwd": "ppiiiifp" "fu",
+    "eavit_attention_row0_bwd": "pppiiiifp" "fu",
     "eavit_patchify": "pipiiiiippfppp",
     "eavit_patchify_ln_bwd": "pipiiiiipppppp",
     "eavit_embed_assemble": "ppppiiiip",

@@ -173,6 +173,16 @@ int eavit_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, 
 /* drop_p > 0 (both kernels): nn.Dropout on the attention probabilities (vit.py:45,70); mask element = (token row,
  * h * 256 + key) of the site seed, regenerated in the backward. */
 
+/* Attention of the POOLED query only: the reference reads token 0 of every sequence after the last layer (x[:, 0],
+ * vit.py:162), so that layer's attention output (and everything token-wise after it) is dead for query rows >= 1.
+ *   fwd: out0 bf16 [nseq, H*Dh] = softmax(q_0 k^T * scale) v            (q_0 = first token of each sequence)
+ *   bwd: dqkv bf16 [T, 3*H*Dh]  <- dout0 [nseq, H*Dh]; dq is zero except the first row of each sequence; dk, dv dense.
+ * CUDA-core kernels (matrix-vector work), one warp per (sequence, head); max_len <= 512; drop_* as in the _tc kernels. */
+int eavit_attention_row0_fwd(const void* qkv, const int* seq_start, int nseq, int max_len, int H, int Dh, float scale,
+                             void* out0, float drop_p, unsigned long long drop_seed, void* stream);
+int eavit_attention_row0_bwd(const void* qkv, const void* dout0, const int* seq_start, int nseq, int max_len, int H, int Dh,
+                             float scale, void* dqkv, float drop_p, unsigned long long drop_seed, void* stream);
+
 /* ------------------------------------------------------------------ dropout (vit.py:31,33,45,56,158) */
 
 /* Every dropout site is a counter-based mask: keep(r, c) is a pure function of (seed, r, c) (16 hash bits per element,

@@ -105,3 +105,48 @@ def ref_attention_autograd(x, starts, H, Dh, scale):
             hs.append(sc.softmax(-1) @ v[s0:s1, sl])
         outs.append(torch.cat(hs, dim=1))
     return torch.cat(outs, dim=0), None
+
+
+@pytest.mark.parametrize("lens,H,Dh", [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([1, 17, 128, 129, 224, 300], 4, 32)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_attention_pooled_row_only(ops, lens, H, Dh, p):
+    """Last-layer attention for query row 0 of each sequence: forward equals row 0 of full attention, backward equals the
+    full backward fed with a gradient that is zero outside row 0 (dq zero elsewhere, dk / dv dense)."""
+    torch.manual_seed(sum(lens) + 7)
+    seed = ops.site_seed(3, 5)
+    starts = [0]
+    for n in lens:
+        starts.append(starts[-1] + n)
+    T, nseq = starts[-1], len(lens)
+    qkv = (torch.randn(T, 3 * H * Dh, device="cuda") * 1.2).bfloat16()
+    ss = torch.tensor(starts, dtype=torch.int32, device="cuda")
+    scale = Dh ** -0.5
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.split(H * Dh, dim=1)
+    rows = []
+    for s0, s1 in zip(starts[:-1], starts[1:]):
+        hs = []
+        for h in range(H):
+            sl = slice(h * Dh, (h + 1) * Dh)
+            pr = ((q[s0:s0 + 1, sl] @ k[s0:s1, sl].t()) * scale).softmax(-1)
+            if p > 0:
+                pr = pr * ops.dropout_mask(1, s1 - s0, p, seed, row0=s0, col0=h * 256)
+            hs.append(pr @ v[s0:s1, sl])
+        rows.append(torch.cat(hs, dim=1))
+    ref = torch.cat(rows, dim=0)                                  # [nseq, H*Dh]
+    d0 = torch.randn(nseq, H * Dh, device="cuda").bfloat16()
+    (ref * d0.float()).sum().backward()
+    out0 = torch.full((nseq, H * Dh), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dqkv = torch.full((T, 3 * H * Dh), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.call("eavit_attention_row0_fwd", qkv, ss, nseq, max(lens), H, Dh, scale, out0, p, seed)
+    ops.call("eavit_attention_row0_bwd", qkv, d0, ss, nseq, max(lens), H, Dh, scale, dqkv, p, seed)
+    torch.cuda.synchronize()
+    assert rel(out0, ref) < 6e-3, rel(out0, ref)
+    assert torch.isfinite(dqkv.float()).all()
+    n = H * Dh
+    for name, sl in (("dq", slice(0, n)), ("dk", slice(n, 2 * n)), ("dv", slice(2 * n, 3 * n))):
+        e = rel(dqkv[:, sl], x.grad[:, sl])
+        assert e < 8e-3, (name, e)
+    not_first = torch.ones(T, dtype=torch.bool, device="cuda")
+    not_first[torch.tensor(starts[:-1], device="cuda")] = False
+    assert (dqkv[not_first][:, :n] == 0).all()                    # exact zeros for query rows >= 1
