@@ -18,6 +18,7 @@ Reference call sites: model.py:266-354, vit.py:136-167, vit_hg.py:277-374, agent
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -178,6 +179,10 @@ class ViTEncoder:
             assert c.use_explorative, "HF variant is only wired for use_explorativeAttn=True (no shipped config uses CLS)"
             self.mode = 2
         self.nseq_per_sample = 1 if self.mode == 1 else 2
+        # Only token 0 of each sequence is read after the last layer (x[:, 0], vit.py:162): that layer's out-projection,
+        # LayerNorm and MLP run on the pooled rows only and its attention with one query row per (sequence, head) --
+        # identical loss and gradients, a third of the ViT's token-wise work and one of three attention launches removed.
+        self.prune_last = os.environ.get("EAVIT_PRUNE_LAST", "1") != "0"
         # layer parameter names
         p = prefix
         self.L = []
@@ -238,6 +243,9 @@ class ViTEncoder:
         if self.mode == 1:
             rows = rows + rows                 # CLS feature feeds both value heads (model.py:300-302)
         bf.pool_rows = torch.tensor(rows, dtype=torch.int32, device=self.dev)
+        bf.first_rows = torch.tensor(starts[:-1], dtype=torch.int32, device=self.dev)     # token 0 of every sequence, once
+        nseq = len(lens)
+        bf.pool_map = torch.tensor([i % nseq for i in range(2 * B)], dtype=torch.int32, device=self.dev)  # feature row -> sequence
         self.buf[B] = bf
         return bf
 
@@ -298,6 +306,9 @@ class ViTEncoder:
             call("eavit_layernorm_fwd", x, D, s.w(L["ln1"][0]), s.w(L["ln1"][1]), xn1, BF16, D, m1, r1, T, D, c.ln_eps)
             qkv = bf.get(f"qkv_{li}", (T, 3 * I), torch.bfloat16)
             linear_fwd(xn1, self._qkv(L, "w16"), bias=self._qkv(L, "b"), out_bf16=qkv)
+            if self.prune_last and li == c.depth - 1:
+                x = self._last_layer_pooled_fwd(bf, li, L, x, qkv)
+                break
             o = bf.get(f"o_{li}", (T, I), torch.bfloat16)
             lse = bf.get(f"lse_{li}", (T, c.heads), torch.float32)
             pa, sa = self._site(bf, li, self.SITE_ATTN_P)
@@ -319,12 +330,72 @@ class ViTEncoder:
             x = xo
         nf = 2 * B
         pooled = bf.get("pooled", (nf, D), torch.float32)
-        call("eavit_gather_rows", x, D, bf.pool_rows, pooled, D, nf, D)
+        if self.prune_last:                                   # x = last layer's output for the pooled rows only [nseq, D]
+            call("eavit_gather_rows", x, D, bf.pool_map, pooled, D, nf, D)
+        else:
+            call("eavit_gather_rows", x, D, bf.pool_rows, pooled, D, nf, D)
         feat = bf.get("feat", (nf, D), torch.float32)
         mf, rf = bf.get("mf", (nf,), torch.float32), bf.get("rf", (nf,), torch.float32)
         fn = (p + "transformer.norm.") if c.impl == "lucidrains" else (p + "layernorm.")
         call("eavit_layernorm_fwd", pooled, D, s.w(fn + "weight"), s.w(fn + "bias"), feat, F32, D, mf, rf, nf, D, c.ln_eps)
         return feat
+
+    def _last_layer_pooled_fwd(self, bf, li, L, x, qkv):
+        """Last layer after the QKV GEMM, for token 0 of every sequence only: [nseq, *] compact buffers."""
+        c, s = self.cfg, self.store
+        D, I, nc = c.dim, self.inner, bf.nseq
+        o0 = bf.get("o0", (nc, I), torch.bfloat16)
+        pa, sa = self._site(bf, li, self.SITE_ATTN_P)
+        call("eavit_attention_row0_fwd", qkv, bf.seq_start, nc, bf.max_len, c.heads, c.dim_head, float(c.dim_head) ** -0.5, o0,
+             pa, sa)
+        xc = bf.get("xc", (nc, D), torch.float32)
+        call("eavit_gather_rows", x, D, bf.first_rows, xc, D, nc, D)
+        xmid = bf.get("xmid_c", (nc, D), torch.float32)
+        po, so = self._site(bf, li, self.SITE_ATTN_OUT)
+        linear_fwd(o0, s.b16(L["o_w"]), bias=s.w(L["o_b"]), residual=xc, out_f32=xmid, drop_p=po, drop_seed=so)
+        xn2 = bf.get("xn2_c", (nc, D), torch.bfloat16)
+        m2, r2 = bf.get("m2_c", (nc,), torch.float32), bf.get("r2_c", (nc,), torch.float32)
+        call("eavit_layernorm_fwd", xmid, D, s.w(L["ln2"][0]), s.w(L["ln2"][1]), xn2, BF16, D, m2, r2, nc, D, c.ln_eps)
+        hpre = bf.get("hpre_c", (nc, c.mlp_dim), torch.bfloat16)
+        hact = bf.get("hact_c", (nc, c.mlp_dim), torch.bfloat16)
+        ph, sh = self._site(bf, li, self.SITE_ACT)
+        linear_fwd(xn2, s.b16(L["w1"]), bias=s.w(L["b1"]), act=ops.ACT_GELU, out_bf16=hact, out_pre=hpre, drop_p=ph, drop_seed=sh)
+        xl = bf.get("xl_c", (nc, D), torch.float32)
+        pf, sf = self._site(bf, li, self.SITE_FF_OUT)
+        linear_fwd(hact, s.b16(L["w2"]), bias=s.w(L["b2"]), residual=xmid, out_f32=xl, drop_p=pf, drop_seed=sf)
+        return xl
+
+    def _last_layer_pooled_bwd(self, bf, li, L, top, dqkv, dxa):
+        """Backward of ``_last_layer_pooled_fwd``.  top fp32 [nseq, D] = gradient of the layer's pooled outputs.  Writes the
+        dense dqkv [T, 3I] and leaves the pooled rows' residual gradient scattered into the zeroed dxa [T, D]."""
+        c, s = self.cfg, self.store
+        D, I, nc, T = c.dim, self.inner, bf.nseq, bf.T
+        pf, sf = self._site(bf, li, self.SITE_FF_OUT)
+        top_m = top
+        if pf > 0:                                            # gradient of the MLP2 output: under its dropout mask
+            top_m = bf.get("top_drop_c", (nc, D), torch.float32)
+            call("eavit_dropout_apply", top, D, None, 0, top_m, D, nc, D, pf, sf)
+        call("eavit_colsum", top_m, F32, D, s.g(L["b2"]), nc, D)
+        top16 = bf.get("top16_c", (nc, D), torch.bfloat16)
+        call("eavit_cast_f32_bf16", top_m, top16, nc * D)
+        dh = bf.get("dh_c", (nc, c.mlp_dim), torch.bfloat16)
+        ph, sh = self._site(bf, li, self.SITE_ACT)
+        linear_bwd(top16, bf.t["hact_c"], s.b16(L["w2"]), dW=s.g(L["w2"]), db=None, dx_bf16=dh, act=ops.ACT_GELU_BWD,
+                   aux=bf.t["hpre_c"], dx_colsum=s.g(L["b1"]), drop_p=ph, drop_seed=sh)
+        dxn = bf.get("dxn_c", (nc, D), torch.bfloat16)
+        linear_bwd(dh, bf.t["xn2_c"], s.b16(L["w1"]), dW=s.g(L["w1"]), db=None, dx_bf16=dxn)
+        dxc = bf.get("dxc", (nc, D), torch.float32)
+        dx16 = bf.get("dx16_c", (nc, D), torch.bfloat16)
+        po, so = self._site(bf, li, self.SITE_ATTN_OUT)
+        call("eavit_layernorm_bwd", dxn, BF16, D, bf.t["xmid_c"], D, bf.t["m2_c"], bf.t["r2_c"], s.w(L["ln2"][0]),
+             top, D, dxc, D, dx16, D, s.g(L["ln2"][0]), s.g(L["ln2"][1]), s.g(L["o_b"]), po, so, nc, D)
+        do0 = bf.get("do0", (nc, I), torch.bfloat16)
+        linear_bwd(dx16, bf.t["o0"], s.b16(L["o_w"]), dW=s.g(L["o_w"]), db=None, dx_bf16=do0)
+        pa, sa = self._site(bf, li, self.SITE_ATTN_P)
+        call("eavit_attention_row0_bwd", bf.t[f"qkv_{li}"], do0, bf.seq_start, nc, bf.max_len, c.heads, c.dim_head,
+             float(c.dim_head) ** -0.5, dqkv, pa, sa)
+        call("eavit_zero", dxa, T * D * 4)
+        call("eavit_scatter_rows", dxc, D, bf.first_rows, dxa, D, None, D, nc, D)
 
     # ---- backward --------------------------------------------------------------------------------
     def backward(self, dfeat: torch.Tensor):
@@ -341,26 +412,28 @@ class ViTEncoder:
         dxa = bf.get("dxa", (T, D), torch.float32)
         dxb = bf.get("dxb", (T, D), torch.float32)
         dx16 = bf.get("dx16", (T, D), torch.bfloat16)
-        call("eavit_zero", dxa, T * D * 4)
-        call("eavit_zero", dx16, T * D * 2)
-        # The top gradient is sparse (pooled rows only).  dxa = gradient of the residual stream; dx16 / db2 = gradient of
-        # the last MLP2 output = the same rows under that layer's output-dropout mask (vit.py:33).
+        # The top gradient is sparse (pooled rows only).
         top, ntop = dpool, nf
         if self.mode == 1:
             top, ntop = bf.get("dpool_sum", (B, D), torch.float32), B
             call("eavit_add_f32", dpool[:B], dpool[B:], top, B * D)
-        pf, sf = self._site(bf, c.depth - 1, self.SITE_FF_OUT)
-        top16 = top
-        if pf > 0:
-            top16 = bf.get("dpool_drop", (ntop, D), torch.float32)
-            call("eavit_dropout_apply", top, D, bf.pool_rows, 0, top16, D, ntop, D, pf, sf)
-        # bias gradient of the last layer's MLP2 = column sums of its (sparse) output gradient
-        call("eavit_colsum", top16, F32, D, s.g(self.L[-1]["b2"]), ntop, D)
-        if top16 is top:
-            call("eavit_scatter_rows", top, D, bf.pool_rows, dxa, D, dx16, D, ntop, D)
-        else:
-            call("eavit_scatter_rows", top, D, bf.pool_rows, dxa, D, None, D, ntop, D)
-            call("eavit_scatter_rows", top16, D, bf.pool_rows, None, D, dx16, D, ntop, D)
+        if not self.prune_last:
+            # dense path: dxa = gradient of the residual stream; dx16 / db2 = gradient of the last MLP2 output = the same
+            # rows under that layer's output-dropout mask (vit.py:33)
+            call("eavit_zero", dxa, T * D * 4)
+            call("eavit_zero", dx16, T * D * 2)
+            pf, sf = self._site(bf, c.depth - 1, self.SITE_FF_OUT)
+            top16 = top
+            if pf > 0:
+                top16 = bf.get("dpool_drop", (ntop, D), torch.float32)
+                call("eavit_dropout_apply", top, D, bf.pool_rows, 0, top16, D, ntop, D, pf, sf)
+            # bias gradient of the last layer's MLP2 = column sums of its (sparse) output gradient
+            call("eavit_colsum", top16, F32, D, s.g(self.L[-1]["b2"]), ntop, D)
+            if top16 is top:
+                call("eavit_scatter_rows", top, D, bf.pool_rows, dxa, D, dx16, D, ntop, D)
+            else:
+                call("eavit_scatter_rows", top, D, bf.pool_rows, dxa, D, None, D, ntop, D)
+                call("eavit_scatter_rows", top16, D, bf.pool_rows, None, D, dx16, D, ntop, D)
         dx, dx_other = dxa, dxb
         dh = bf.get("dh", (T, c.mlp_dim), torch.bfloat16)
         dxn = bf.get("dxn", (T, D), torch.bfloat16)     # LN-backward input (a GEMM output): bf16 halves its traffic
@@ -369,6 +442,16 @@ class ViTEncoder:
         for li in reversed(range(c.depth)):
             L = self.L[li]
             x_in = bf.t["x0"] if li == 0 else bf.t[f"x_{li}"]
+            if self.prune_last and li == c.depth - 1:
+                # pooled rows only down to the attention, then the ordinary dense QKV / LN1 backward
+                self._last_layer_pooled_bwd(bf, li, L, top, dqkv, dx)
+                linear_bwd(dqkv, bf.t[f"xn1_{li}"], self._qkv(L, "w16"), dW=self._qkv(L, "gw"), db=self._qkv(L, "gb"), dx_bf16=dxn)
+                db2_prev = s.g(self.L[li - 1]["b2"]) if li > 0 else None
+                pf, sf = self._site(bf, li - 1, self.SITE_FF_OUT) if li > 0 else (0.0, 0)
+                call("eavit_layernorm_bwd", dxn, BF16, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
+                     dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, pf, sf, T, D)
+                dx, dx_other = dx_other, dx
+                continue
             # MLP2: x_out = xmid + hact W2^T + b2
             # (db2 comes from the producer of dx: LN-bwd / top; db1 = colsum(dh) from this GEMM's epilogue)
             ph, sh = self._site(bf, li, self.SITE_ACT)

@@ -185,6 +185,14 @@ def test_train_step_with_dropout_matches_oracle_with_same_masks(which):
             row0 = 0 if pass_id == O.EXPLORATIVE else B * np_
         else:
             n, row0 = S1, pass_id * B * S1
+        if layer == cfg.depth - 1 and kind in ("attn_out", "act", "ff_out") and rt.encoder.prune_last:
+            # last layer: only token 0 of each sequence is computed (compact rows = sequence index); other tokens are dead
+            m = torch.ones(x.shape)
+            seq0 = (0 if pass_id in (O.EXPLORATIVE, 0) else B) if which == "lucid" else pass_id * B
+            if which == "lucid" and pass_id == O.EXPLOITATIVE:
+                seq0 = B
+            m[:, 0, :] = ops.dropout_mask(x.shape[0], x.shape[2], pr, seed, row0=seq0).cpu()
+            return x * m
         if kind == "attn_p":                                  # x [b, h, n, n]; element (token row, h*256 + key)
             b, h = x.shape[0], x.shape[1]
             m = torch.stack([torch.stack([ops.dropout_mask(n, n, pr, seed, row0=row0 + bi * n, col0=hi * 256) for hi in range(h)])
