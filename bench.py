@@ -31,7 +31,20 @@ import torch  # noqa: E402
 
 E_PER_GPU, T, A = 128, 128, 18
 MINI_BATCH, EPOCH = 32, 4
-FLOPS_PER_SAMPLE = 6.36e9 + 58.2e6      # ViT+heads fwd+bwd + RND training, per sample
+FLOPS_PER_SAMPLE = 6.36e9 + 58.2e6      # ViT+heads fwd+bwd + RND training, per sample (NOMINAL:
+                                        # every token of every layer, as the reference computes it)
+
+
+def executed_fraction(D=256, inner=256, mlp=1024, depth=3, s_a=196, s_b=197):
+    """Share of the nominal ViT FLOPs the engine executes: the last layer's out-projection, MLP and attention rows are
+    computed for the pooled token only (the reference computes and discards the other 391 of 393 tokens per sample)."""
+    qkv, proj, ff = 2 * D * 3 * inner, 2 * inner * D, 4 * D * mlp
+    tot = dead = 0.0
+    for S in (s_a, s_b):
+        per_tok = qkv + proj + ff + 4 * S * inner
+        tot += depth * S * per_tok
+        dead += (S - 1) * (proj + ff + 4 * S * inner)
+    return 1.0 - dead / tot
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the cfg3 shapes (ncu --set full, profiles/)
 NCU_DRAM_BYTES_PER_LAUNCH = {
     "attention_bwd_tc": 686.3e6, "attention_fwd_tc": 396.6e6,
@@ -263,6 +276,8 @@ def main():
                 "all_gemm": {"launches_per_step": gemm[0] / nprof, "share_of_step": gemm[1] / tot_ms,
                              "achieved_tflops": gemm[2] / (gemm[1] * 1e-3) / 1e12 if gemm[1] > 0 else None},
                 "step_model_tflops": FLOPS_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12,
+                "step_executed_tflops": FLOPS_PER_SAMPLE * executed_fraction() * B / (ms / args.steps * 1e-3) / 1e12,
+                "executed_fraction_of_nominal_flops": executed_fraction(),
                 "step_frac_of_sustained_peak": FLOPS_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
     if args.profile_out and rank == 0:
         rows = sorted(((l, n / nprof, tms / nprof, fl) for l, (n, tms, fl) in table.items()), key=lambda r: -r[2])
