@@ -10,56 +10,44 @@
 //              dq_0 = scale sum_j ds_j k_j,   dk_j = scale ds_j q_0,   dv_j = p_j m_j do_0,   dq_{i>0} = 0
 //
 // K and V still come from every token, so the gradient flowing back into the residual stream is dense and layers below
-// are untouched.  This is a matrix-vector problem (2 * S * Dh MACs per head), so it runs on CUDA cores: one warp per
-// (sequence, head), lanes over keys for the scores, lanes over head dimensions for the weighted sums; the kernels are
-// bound by streaming K / V (forward: 206 MB at the cfg3 shape) and writing dqkv (backward: 309 MB).
+// are untouched.  This is a matrix-vector problem (2 * S * Dh MACs per head), so it runs on CUDA cores and is bound by
+// streaming K / V (forward: 206 MB at the cfg3 shape) and writing dqkv (backward: 309 MB).  One CTA per sequence, all
+// heads together: a warp reads one key's K (or V) section as 16 bytes per lane -- whole 512-byte row pieces, every
+// sector used -- with several keys in flight per warp; the DH / 8 lanes of a head combine by shuffles, the scores of all
+// heads sit in shared memory, softmax runs one warp per head, and the backward writes dq / dk / dv rows as 16-byte
+// stores of the same shape.
 #include "common.cuh"
 
 namespace eavit {
 
 constexpr int R0_WARPS = 8;
-constexpr int R0_MAXPL = 16;          // keys per lane: sequences up to 512 tokens
+constexpr int R0_THREADS = R0_WARPS * 32;
+constexpr int R0_MAXLEN = 512;
+constexpr int R0_UN = 4;              // keys in flight per warp
 
-// sum_d row[d] * q[d]; row = DH bf16 in global memory (one key / value row), q = DH floats in shared memory (all lanes of a
-// warp read the same q element in the same iteration: broadcast, conflict-free)
-template <int DH>
-__device__ __forceinline__ float dot_row(const __nv_bfloat16* row, const float* q) {
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ float dot8(const uint4& u, const float* q) {
+  float f[8];
+  bf16x8_to_f32(u, f);
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-  for (int c = 0; c < DH / 8; ++c) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(row) + c);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      a0 = fmaf(__uint_as_float(w[i] << 16), q[c * 8 + 2 * i], a0);
-      a1 = fmaf(__uint_as_float(w[i] & 0xffff0000u), q[c * 8 + 2 * i + 1], a1);
-    }
-  }
+  for (int i = 0; i < 8; i += 2) { a0 = fmaf(f[i], q[i], a0); a1 = fmaf(f[i + 1], q[i + 1], a1); }
   return a0 + a1;
 }
-
-// normalised p_j = softmax_j(q_0 . k_j * scale) for this lane's keys j = lane + 32 i
+__device__ __forceinline__ uint4 scaled8(float s, const float* q) {
+  return make_uint4(pack_bf16x2(s * q[0], s * q[1]), pack_bf16x2(s * q[2], s * q[3]), pack_bf16x2(s * q[4], s * q[5]),
+                    pack_bf16x2(s * q[6], s * q[7]));
+}
+// sum over the LPH = DH / 8 consecutive lanes that share a head
 template <int DH>
-__device__ __forceinline__ void row0_softmax(const __nv_bfloat16* kbase, int ldq, int S, const float* q, float scale, int lane,
-                                             float* p) {
-  float mx = -INFINITY;
+__device__ __forceinline__ float head_sum(float v) {
 #pragma unroll
-  for (int i = 0; i < R0_MAXPL; ++i) {
-    const int j = lane + 32 * i;
-    p[i] = -INFINITY;
-    if (j < S) { p[i] = dot_row<DH>(kbase + (size_t)j * ldq, q) * scale; mx = fmaxf(mx, p[i]); }
-  }
-  mx = warp_max(mx);
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < R0_MAXPL; ++i) {
-    const int j = lane + 32 * i;
-    p[i] = (j < S) ? __expf(p[i] - mx) : 0.f;
-    sum += p[i];
-  }
-  const float inv = 1.0f / warp_sum(sum);
-#pragma unroll
-  for (int i = 0; i < R0_MAXPL; ++i) p[i] *= inv;
+  for (int o = DH / 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
 // dropout factor (0 or 1/(1-p)) of attention-probability element (token row key `rk`, column h*256 + j) -- the same
@@ -71,149 +59,303 @@ __device__ __forceinline__ float row0_mask(const DropCfg& drop, uint32_t rk, int
   return (c & 1) ? drop_odd(drop, bits) : drop_even(drop, bits);
 }
 
-template <int DH>
-__global__ void __launch_bounds__(R0_WARPS * 32) attention_row0_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                          const int* __restrict__ seq_start, int nseq, int H,
-                                                                          float scale, __nv_bfloat16* __restrict__ out0,
-                                                                          const DropCfg drop) {
-  constexpr int DPL = DH / 32;                     // head dimensions per lane
-  __shared__ float s_q[R0_WARPS][DH];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * R0_WARPS + w;
-  if (item >= nseq * H) return;
-  const int seq = item / H, h = item - seq * H;
-  const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
-  const int ldq = 3 * H * DH;
-  const __nv_bfloat16* qrow = qkv + (size_t)t0 * ldq + h * DH;
+// Column chunk c (256 bf16 = 512 bytes of a K / V / Q section) x lane -> columns [c*256 + lane*8, +8), head (c*256 + lane*8) / DH.
+// NCH = ceil(H * DH / 256) chunks per section (1 for the lucidrains ViT, 4 for the HF-style one); lanes past H * DH idle.
+// Shared memory: sc[H][SP] scores -> probabilities (-> ds in the backward), dp[H][SP] (backward), red[R0_WARPS][H*DH].
+template <int DH, int NCH, bool BWD>
+__device__ __forceinline__ void row0_scores(const __nv_bfloat16* __restrict__ kbase, const __nv_bfloat16* __restrict__ vbase,
+                                            int ldq, int HD, int S, int SP, const float (*q)[8], const float (*g)[8],
+                                            float scale, float* sc, float* dp, int warp, int lane) {
+  constexpr int LPH = DH / 8, HPC = 256 / DH;
+  for (int j0 = warp; j0 < S; j0 += R0_WARPS * R0_UN) {
+    uint4 kk[R0_UN][NCH], vv[R0_UN][NCH];
 #pragma unroll
-  for (int e = 0; e < DPL; ++e) s_q[w][lane + 32 * e] = __bfloat162float(qrow[lane + 32 * e]);
-  __syncwarp();
-  float p[R0_MAXPL];
-  row0_softmax<DH>(qrow + H * DH, ldq, S, s_q[w], scale, lane, p);
-  const uint32_t rk = drop_row_key(drop, (uint32_t)t0);
+    for (int u = 0; u < R0_UN; ++u) {
+      const int j = j0 + u * R0_WARPS;
 #pragma unroll
-  for (int i = 0; i < R0_MAXPL; ++i) p[i] *= row0_mask(drop, rk, h, lane + 32 * i);
-  // o_0[d] = sum_j p_j m_j v_j[d]: lanes over d, p_j broadcast from its owner lane
-  const __nv_bfloat16* vbase = qrow + 2 * H * DH;
-  float o[DPL];
+      for (int c = 0; c < NCH; ++c) {
+        kk[u][c] = make_uint4(0, 0, 0, 0);
+        if (BWD) vv[u][c] = make_uint4(0, 0, 0, 0);
+        if (j < S && c * 256 + lane * 8 < HD) {
+          kk[u][c] = __ldg(reinterpret_cast<const uint4*>(kbase + (size_t)j * ldq + c * 256) + lane);
+          if (BWD) vv[u][c] = __ldg(reinterpret_cast<const uint4*>(vbase + (size_t)j * ldq + c * 256) + lane);
+        }
+      }
+    }
 #pragma unroll
-  for (int e = 0; e < DPL; ++e) o[e] = 0.f;
+    for (int u = 0; u < R0_UN; ++u) {
+      const int j = j0 + u * R0_WARPS;
 #pragma unroll
-  for (int i = 0; i < R0_MAXPL; ++i) {
-    if (32 * i >= S) break;
-    const int n = min(32, S - 32 * i);
-    for (int l = 0; l < n; ++l) {
-      const float pj = __shfl_sync(0xffffffffu, p[i], l);
-      const __nv_bfloat16* vr = vbase + (size_t)(32 * i + l) * ldq;
-#pragma unroll
-      for (int e = 0; e < DPL; ++e) o[e] = fmaf(pj, __bfloat162float(vr[lane + 32 * e]), o[e]);
+      for (int c = 0; c < NCH; ++c) {
+        const float s = head_sum<DH>(dot8(kk[u][c], q[c]));
+        float d = 0.f;
+        if (BWD) d = head_sum<DH>(dot8(vv[u][c], g[c]));
+        if (j < S && (lane % LPH) == 0 && c * 256 + lane * 8 < HD) {
+          const int h = c * HPC + lane / LPH;
+          sc[h * SP + j] = s * scale;
+          if (BWD) dp[h * SP + j] = d;
+        }
+      }
     }
   }
-#pragma unroll
-  for (int e = 0; e < DPL; ++e) out0[(size_t)seq * H * DH + h * DH + lane + 32 * e] = __float2bfloat16(o[e]);
 }
 
-template <int DH>
-__global__ void __launch_bounds__(R0_WARPS * 32) attention_row0_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                          const __nv_bfloat16* __restrict__ dout0,
-                                                                          const int* __restrict__ seq_start, int nseq, int H,
-                                                                          float scale, __nv_bfloat16* __restrict__ dqkv,
-                                                                          const DropCfg drop) {
-  constexpr int DPL = DH / 32;
-  __shared__ float s_q[R0_WARPS][DH], s_g[R0_WARPS][DH];             // q_0 and do_0 of this warp's (sequence, head)
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * R0_WARPS + w;
-  if (item >= nseq * H) return;
-  const int seq = item / H, h = item - seq * H;
+template <int DH, int NCH>
+__global__ void __launch_bounds__(R0_THREADS) attention_row0_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                       const int* __restrict__ seq_start, int H, int SP,
+                                                                       float scale, __nv_bfloat16* __restrict__ out0,
+                                                                       const DropCfg drop) {
+  constexpr int LPH = DH / 8, HPC = 256 / DH;
+  extern __shared__ float r0_smem[];
+  const int HD = H * DH;
+  float* sc = r0_smem;                              // [H][SP]
+  float* red = sc + H * SP;                         // [R0_WARPS][HD]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = blockIdx.x;
   const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
-  const int ldq = 3 * H * DH;
-  const __nv_bfloat16* qrow = qkv + (size_t)t0 * ldq + h * DH;
-  const __nv_bfloat16* kbase = qrow + H * DH;
-  const __nv_bfloat16* vbase = qrow + 2 * H * DH;
-  float ql[DPL], gl[DPL];                                            // this lane's dimensions of q_0 / do_0
+  const int ldq = 3 * HD;
+  const __nv_bfloat16* qrow = qkv + (size_t)t0 * ldq;
+  const __nv_bfloat16* kbase = qrow + HD;
+  const __nv_bfloat16* vbase = qrow + 2 * HD;
+  float q[NCH][8];
 #pragma unroll
-  for (int e = 0; e < DPL; ++e) {
-    ql[e] = __bfloat162float(qrow[lane + 32 * e]);
-    gl[e] = __bfloat162float(dout0[(size_t)seq * H * DH + h * DH + lane + 32 * e]);
-    s_q[w][lane + 32 * e] = ql[e];
-    s_g[w][lane + 32 * e] = gl[e];
-  }
-  __syncwarp();
-  float p[R0_MAXPL], pm[R0_MAXPL], ds[R0_MAXPL];
-  row0_softmax<DH>(kbase, ldq, S, s_q[w], scale, lane, p);
+  for (int c = 0; c < NCH; ++c)
+    bf16x8_to_f32(c * 256 + lane * 8 < HD ? __ldg(reinterpret_cast<const uint4*>(qrow + c * 256) + lane) : make_uint4(0, 0, 0, 0), q[c]);
+  row0_scores<DH, NCH, false>(kbase, vbase, ldq, HD, S, SP, q, q, scale, sc, nullptr, warp, lane);
+  __syncthreads();
+  // softmax, one warp per head; the stored weight is p_j m_j (the denominator uses the full probabilities)
   const uint32_t rk = drop_row_key(drop, (uint32_t)t0);
-  float dsum = 0.f;
-#pragma unroll
-  for (int i = 0; i < R0_MAXPL; ++i) {
-    const int j = lane + 32 * i;
-    const float m = row0_mask(drop, rk, h, j);
-    const float dp = (j < S) ? dot_row<DH>(vbase + (size_t)j * ldq, s_g[w]) : 0.f;   // gradient w.r.t. the dropped p_j m_j
-    pm[i] = p[i] * m;                                                 // weight of v_j in o_0 = weight of do_0 in dv_j
-    ds[i] = m * dp;                                                   // gradient w.r.t. the softmax output p_j
-    dsum = fmaf(p[i], ds[i], dsum);
+  for (int h = warp; h < H; h += R0_WARPS) {
+    float* row = sc + h * SP;
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) { const float e = __expf(row[j] - mx); row[j] = e; sum += e; }
+    const float inv = 1.0f / warp_sum(sum);
+    for (int j = lane; j < S; j += 32) row[j] *= inv * row0_mask(drop, rk, h, j);
   }
-  const float D = warp_sum(dsum);
+  __syncthreads();
+  // o_0 = sum_j (p_j m_j) v_j: every warp sums its keys, then the warps are combined through shared memory
+  float acc[NCH][8];
 #pragma unroll
-  for (int i = 0; i < R0_MAXPL; ++i) ds[i] = p[i] * (ds[i] - D) * scale;   // softmax Jacobian; scale folded in
-  // lanes over head dimensions: dq_0 accumulation; dk_j / dv_j rows written as contiguous 2*DH-byte segments
-  __nv_bfloat16* dq = dqkv + (size_t)t0 * ldq + h * DH;
-  __nv_bfloat16* dk = dq + H * DH;
-  __nv_bfloat16* dv = dq + 2 * H * DH;
-  float dq0[DPL];
+  for (int c = 0; c < NCH; ++c)
 #pragma unroll
-  for (int e = 0; e < DPL; ++e) dq0[e] = 0.f;
-  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+    for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+  for (int j0 = warp; j0 < S; j0 += R0_WARPS * R0_UN) {
+    uint4 vv[R0_UN][NCH];
 #pragma unroll
-  for (int i = 0; i < R0_MAXPL; ++i) {
-    if (32 * i >= S) break;
-    const int n = min(32, S - 32 * i);
-    for (int l = 0; l < n; ++l) {
-      const float dsj = __shfl_sync(0xffffffffu, ds[i], l);
-      const float pmj = __shfl_sync(0xffffffffu, pm[i], l);
-      const size_t ro = (size_t)(32 * i + l) * ldq;
+    for (int u = 0; u < R0_UN; ++u) {
+      const int j = j0 + u * R0_WARPS;
 #pragma unroll
-      for (int e = 0; e < DPL; ++e) {
-        const int d = lane + 32 * e;
-        dq0[e] = fmaf(dsj, __bfloat162float(kbase[ro + d]), dq0[e]);
-        dk[ro + d] = __float2bfloat16(dsj * ql[e]);
-        dv[ro + d] = __float2bfloat16(pmj * gl[e]);
-        if (32 * i + l > 0) dq[ro + d] = zero;                        // query rows >= 1 carry no gradient
+      for (int c = 0; c < NCH; ++c)
+        vv[u][c] = (j < S && c * 256 + lane * 8 < HD) ? __ldg(reinterpret_cast<const uint4*>(vbase + (size_t)j * ldq + c * 256) + lane) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < R0_UN; ++u) {
+      const int j = j0 + u * R0_WARPS;
+      if (j >= S) break;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c * 256 + lane * 8 >= HD) continue;
+        const float pj = sc[(c * HPC + lane / LPH) * SP + j];
+        float f[8];
+        bf16x8_to_f32(vv[u][c], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(pj, f[i], acc[c][i]);
       }
     }
   }
 #pragma unroll
-  for (int e = 0; e < DPL; ++e) dq[lane + 32 * e] = __float2bfloat16(dq0[e]);
+  for (int c = 0; c < NCH; ++c) {
+    if (c * 256 + lane * 8 >= HD) continue;
+    float4* dst = reinterpret_cast<float4*>(red + warp * HD + c * 256 + lane * 8);
+    dst[0] = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+    dst[1] = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < HD; d += R0_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < R0_WARPS; ++w) s += red[w * HD + d];
+    out0[(size_t)seq * HD + d] = __float2bfloat16(s);
+  }
+}
+
+template <int DH, int NCH>
+__global__ void __launch_bounds__(R0_THREADS) attention_row0_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                       const __nv_bfloat16* __restrict__ dout0,
+                                                                       const int* __restrict__ seq_start, int H, int SP,
+                                                                       float scale, __nv_bfloat16* __restrict__ dqkv,
+                                                                       const DropCfg drop) {
+  constexpr int LPH = DH / 8, HPC = 256 / DH;
+  extern __shared__ float r0_smem[];
+  const int HD = H * DH;
+  float* sc = r0_smem;                              // [H][SP]  scores -> p -> ds (scale folded in)
+  float* dp = sc + H * SP;                          // [H][SP]  do_0 . v_j -> p_j m_j
+  float* red = dp + H * SP;                         // [R0_WARPS][HD]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = blockIdx.x;
+  const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
+  const int ldq = 3 * HD;
+  const __nv_bfloat16* qrow = qkv + (size_t)t0 * ldq;
+  const __nv_bfloat16* kbase = qrow + HD;
+  const __nv_bfloat16* vbase = qrow + 2 * HD;
+  float q[NCH][8], g[NCH][8];                       // this lane's columns of q_0 / do_0
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const bool act = c * 256 + lane * 8 < HD;
+    bf16x8_to_f32(act ? __ldg(reinterpret_cast<const uint4*>(qrow + c * 256) + lane) : make_uint4(0, 0, 0, 0), q[c]);
+    bf16x8_to_f32(act ? __ldg(reinterpret_cast<const uint4*>(dout0 + (size_t)seq * HD + c * 256) + lane) : make_uint4(0, 0, 0, 0), g[c]);
+  }
+  row0_scores<DH, NCH, true>(kbase, vbase, ldq, HD, S, SP, q, g, scale, sc, dp, warp, lane);
+  __syncthreads();
+  // per head: p = softmax(s); dp_j <- m_j dp_j (gradient w.r.t. p_j); D = sum_j p_j dp_j; ds_j = p_j (dp_j - D) * scale
+  const uint32_t rk = drop_row_key(drop, (uint32_t)t0);
+  for (int h = warp; h < H; h += R0_WARPS) {
+    float* row = sc + h * SP;
+    float* drow = dp + h * SP;
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) { const float e = __expf(row[j] - mx); row[j] = e; sum += e; }
+    const float inv = 1.0f / warp_sum(sum);
+    float dsum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      const float p = row[j] * inv;
+      row[j] = p;
+      dsum = fmaf(p, row0_mask(drop, rk, h, j) * drow[j], dsum);
+    }
+    const float D = warp_sum(dsum);
+    for (int j = lane; j < S; j += 32) {
+      const float p = row[j], m = row0_mask(drop, rk, h, j);
+      row[j] = p * (m * drow[j] - D) * scale;
+      drow[j] = p * m;                              // weight of v_j in o_0 = weight of do_0 in dv_j
+    }
+  }
+  __syncthreads();
+  // dk_j = ds_j q_0, dv_j = (p_j m_j) do_0, dq_{j>0} = 0 as 16-byte stores; dq_0 = sum_j ds_j k_j
+  __nv_bfloat16* dq = dqkv + (size_t)t0 * ldq;
+  __nv_bfloat16* dk = dq + HD;
+  __nv_bfloat16* dv = dq + 2 * HD;
+  float acc[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+  for (int j0 = warp; j0 < S; j0 += R0_WARPS * R0_UN) {
+    uint4 kk[R0_UN][NCH];
+#pragma unroll
+    for (int u = 0; u < R0_UN; ++u) {
+      const int j = j0 + u * R0_WARPS;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        kk[u][c] = (j < S && c * 256 + lane * 8 < HD) ? __ldg(reinterpret_cast<const uint4*>(kbase + (size_t)j * ldq + c * 256) + lane) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < R0_UN; ++u) {
+      const int j = j0 + u * R0_WARPS;
+      if (j >= S) break;
+      const size_t ro = (size_t)j * ldq;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c * 256 + lane * 8 >= HD) continue;
+        const int h = c * HPC + lane / LPH;
+        const float dsj = sc[h * SP + j], pmj = dp[h * SP + j];
+        float f[8];
+        bf16x8_to_f32(kk[u][c], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(dsj, f[i], acc[c][i]);
+        reinterpret_cast<uint4*>(dk + ro + c * 256)[lane] = scaled8(dsj, q[c]);
+        reinterpret_cast<uint4*>(dv + ro + c * 256)[lane] = scaled8(pmj, g[c]);
+        if (j > 0) reinterpret_cast<uint4*>(dq + ro + c * 256)[lane] = make_uint4(0, 0, 0, 0);   // query rows >= 1 carry no gradient
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (c * 256 + lane * 8 >= HD) continue;
+    float4* dst = reinterpret_cast<float4*>(red + warp * HD + c * 256 + lane * 8);
+    dst[0] = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+    dst[1] = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < HD; d += R0_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < R0_WARPS; ++w) s += red[w * HD + d];
+    dq[d] = __float2bfloat16(s);
+  }
 }
 
 }  // namespace eavit
 
 using namespace eavit;
 
-extern "C" int eavit_attention_row0_fwd(const void* qkv, const int* seq_start, int nseq, int max_len, int H, int Dh, float scale,
-                                        void* out0, float drop_p, unsigned long long drop_seed, void* stream) {
-  EAVIT_CHECK_ARG(qkv && seq_start && out0 && nseq > 0 && H > 0 && (Dh == 32 || Dh == 64));
-  EAVIT_CHECK_ARG(max_len > 0 && max_len <= 32 * R0_MAXPL && drop_p >= 0.f && drop_p < 1.f);
-  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0);
-  const DropCfg drop = make_drop(drop_p, drop_seed);
-  const int grid = cdiv((long long)nseq * H, R0_WARPS);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (Dh == 32) attention_row0_fwd_kernel<32><<<grid, R0_WARPS * 32, 0, st>>>((const __nv_bfloat16*)qkv, seq_start, nseq, H, scale, (__nv_bfloat16*)out0, drop);
-  else          attention_row0_fwd_kernel<64><<<grid, R0_WARPS * 32, 0, st>>>((const __nv_bfloat16*)qkv, seq_start, nseq, H, scale, (__nv_bfloat16*)out0, drop);
+// chunks of 256 columns per section: the kernels are instantiated for 1, 2 and 4 (H * Dh = 256, 512, 1024)
+#define R0_ARGS_OK()                                                                                        \
+  EAVIT_CHECK_ARG(nseq > 0 && H > 0 && (Dh == 32 || Dh == 64));                                             \
+  EAVIT_CHECK_ARG(H * Dh <= 256 || H * Dh == 512 || H * Dh == 1024);                                        \
+  EAVIT_CHECK_ARG(max_len > 0 && max_len <= R0_MAXLEN && drop_p >= 0.f && drop_p < 1.f)
+
+template <int DH, int NCH>
+static int row0_fwd_go(const void* qkv, const int* seq_start, int nseq, int H, int SP, float scale, void* out0, const DropCfg& drop,
+                       cudaStream_t st) {
+  const size_t smem = ((size_t)H * SP + (size_t)R0_WARPS * H * DH) * sizeof(float);
+  EAVIT_CUDA(cudaFuncSetAttribute(attention_row0_fwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_row0_fwd_kernel<DH, NCH><<<nseq, R0_THREADS, smem, st>>>((const __nv_bfloat16*)qkv, seq_start, H, SP, scale,
+                                                                      (__nv_bfloat16*)out0, drop);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
+}
+template <int DH, int NCH>
+static int row0_bwd_go(const void* qkv, const void* dout0, const int* seq_start, int nseq, int H, int SP, float scale, void* dqkv,
+                       const DropCfg& drop, cudaStream_t st) {
+  const size_t smem = ((size_t)2 * H * SP + (size_t)R0_WARPS * H * DH) * sizeof(float);
+  EAVIT_CUDA(cudaFuncSetAttribute(attention_row0_bwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_row0_bwd_kernel<DH, NCH><<<nseq, R0_THREADS, smem, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout0,
+                                                                      seq_start, H, SP, scale, (__nv_bfloat16*)dqkv, drop);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+extern "C" int eavit_attention_row0_fwd(const void* qkv, const int* seq_start, int nseq, int max_len, int H, int Dh, float scale,
+                                        void* out0, float drop_p, unsigned long long drop_seed, void* stream) {
+  EAVIT_CHECK_ARG(qkv && seq_start && out0);
+  R0_ARGS_OK();
+  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0);
+  const DropCfg drop = make_drop(drop_p, drop_seed);
+  const int SP = (max_len + 3) & ~3;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nch = (H * Dh + 255) / 256;
+  if (Dh == 32) {
+    if (nch == 1) return row0_fwd_go<32, 1>(qkv, seq_start, nseq, H, SP, scale, out0, drop, st);
+    if (nch == 2) return row0_fwd_go<32, 2>(qkv, seq_start, nseq, H, SP, scale, out0, drop, st);
+    return row0_fwd_go<32, 4>(qkv, seq_start, nseq, H, SP, scale, out0, drop, st);
+  }
+  if (nch == 1) return row0_fwd_go<64, 1>(qkv, seq_start, nseq, H, SP, scale, out0, drop, st);
+  if (nch == 2) return row0_fwd_go<64, 2>(qkv, seq_start, nseq, H, SP, scale, out0, drop, st);
+  return row0_fwd_go<64, 4>(qkv, seq_start, nseq, H, SP, scale, out0, drop, st);
 }
 
 extern "C" int eavit_attention_row0_bwd(const void* qkv, const void* dout0, const int* seq_start, int nseq, int max_len, int H,
                                         int Dh, float scale, void* dqkv, float drop_p, unsigned long long drop_seed,
                                         void* stream) {
-  EAVIT_CHECK_ARG(qkv && dout0 && seq_start && dqkv && nseq > 0 && H > 0 && (Dh == 32 || Dh == 64));
-  EAVIT_CHECK_ARG(max_len > 0 && max_len <= 32 * R0_MAXPL && drop_p >= 0.f && drop_p < 1.f);
-  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0);
+  EAVIT_CHECK_ARG(qkv && dout0 && seq_start && dqkv);
+  R0_ARGS_OK();
+  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dout0) & 15) == 0);
   const DropCfg drop = make_drop(drop_p, drop_seed);
-  const int grid = cdiv((long long)nseq * H, R0_WARPS);
+  const int SP = (max_len + 3) & ~3;
   cudaStream_t st = (cudaStream_t)stream;
-  if (Dh == 32) attention_row0_bwd_kernel<32><<<grid, R0_WARPS * 32, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout0, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv, drop);
-  else          attention_row0_bwd_kernel<64><<<grid, R0_WARPS * 32, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout0, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv, drop);
-  EAVIT_LAUNCH_OK();
-  return EAVIT_OK;
+  const int nch = (H * Dh + 255) / 256;
+  if (Dh == 32) {
+    if (nch == 1) return row0_bwd_go<32, 1>(qkv, dout0, seq_start, nseq, H, SP, scale, dqkv, drop, st);
+    if (nch == 2) return row0_bwd_go<32, 2>(qkv, dout0, seq_start, nseq, H, SP, scale, dqkv, drop, st);
+    return row0_bwd_go<32, 4>(qkv, dout0, seq_start, nseq, H, SP, scale, dqkv, drop, st);
+  }
+  if (nch == 1) return row0_bwd_go<64, 1>(qkv, dout0, seq_start, nseq, H, SP, scale, dqkv, drop, st);
+  if (nch == 2) return row0_bwd_go<64, 2>(qkv, dout0, seq_start, nseq, H, SP, scale, dqkv, drop, st);
+  return row0_bwd_go<64, 4>(qkv, dout0, seq_start, nseq, H, SP, scale, dqkv, drop, st);
 }
