@@ -150,7 +150,7 @@ class RNDAgent(nn.Module):
         x = x.to(rt.device).to(torch.float32).contiguous()               # torch.FloatTensor(next_obs)
         B = x.shape[0]
         tgt = rt.rnd_tgt.forward(x, B)
-        prd = rt.rnd_pred.forward(x, B)
+        prd = rt.rnd_pred.forward(x, B, col0=rt.rnd_tgt.buf[B].t["col0"])
         return ops.intrinsic_mse(tgt, prd).cpu().numpy()
 
     # ---- update ----------------------------------------------------------------------------------------
@@ -198,7 +198,7 @@ class RNDAgent(nn.Module):
         call("eavit_gather_batch", idx, B, A, R["te"], R["ti"], R["adv"], R["y"], R["old"], w["te"], w["ti"], w["adv"], w["y"], w["old"])
         # RND (agents.py:333-338): target is frozen, predictor gets the masked MSE gradient
         pred = rt.rnd_pred.forward(R["obs"], B, idx)
-        tgt = rt.rnd_tgt.forward(R["obs"], B, idx)
+        tgt = rt.rnd_tgt.forward(R["obs"], B, idx, col0=rt.rnd_pred.buf[B].t["col0"])
         call("eavit_rnd_loss", pred, tgt, mask, B, pred.shape[1], gs, w["dpred"], None, w["stats"])
         rt.rnd_pred.backward(w["dpred"])
         # PPO (agents.py:455-494)

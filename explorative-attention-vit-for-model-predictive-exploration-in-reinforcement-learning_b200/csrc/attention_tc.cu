@@ -407,7 +407,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int seq = item / HG, hg = item - seq * HG;
     const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
-    const int NKT = (S + 31) & ~31, NKP = (S + 15) & ~15;
+    const int NKP = (S + 15) & ~15, NKT = NKP;     // score columns = keys covered by the dQ MMA (multiple of 16: 208 at S = 196 / 197)
     const int NQ = (S + 127) >> 7;                 // query tiles == key tiles
 #ifdef EAVIT_TRACE
     tr_prev = clock64();

@@ -9,15 +9,18 @@ namespace eavit {
 // C[M,N] (+)= mask(act(op(A) . op(B) + bias))      fp32, 32x32 tiles, 16x16 threads x (2x2) outputs
 //   transA = 0: A[M,K] pitch lda ; 1: A stored [K,M]
 //   transB = 0: B[N,K] pitch ldb (nn.Linear weight) ; 1: B stored [K,N]
-// 64 x 64 output tile per CTA, 4 x 4 micro-tile per thread, K in steps of 16; blockIdx.z splits K (accumulate only,
+// 64 x 64 output tile per CTA, 4 x 4 micro-tile per thread, K in steps of 32; blockIdx.z splits K (accumulate only,
 // atomicAdd) so that the weight-gradient shapes (M = N = 256, K = rows) fill the machine instead of 16 CTAs.
 __global__ void __launch_bounds__(256) sgemm_small_kernel(const float* __restrict__ A, long long lda, int transA,
                                                           const float* __restrict__ B, long long ldb, int transB,
                                                           const float* __restrict__ bias, const float* __restrict__ mask_aux,
                                                           float* __restrict__ C, long long ldc, int M, int N, int K, int relu,
                                                           int accumulate, int k_per_split) {
-  __shared__ float sA[16][68];   // [k][m]
-  __shared__ float sB[16][68];   // [k][n]
+  // These GEMMs are latency-bound (a handful of CTAs, K = 256 .. 1024): K advances 32 at a time and the next step's
+  // operands are fetched into registers (16 independent loads per thread) while the current step is multiplied.
+  constexpr int SK = 32, LD = 65;        // odd pitch: conflict-free for both the k-fastest and the m-fastest fill
+  __shared__ float sA[SK][LD];   // [k][m]
+  __shared__ float sB[SK][LD];   // [k][n]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
@@ -26,24 +29,33 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(const float* __restric
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = kbeg; k0 < kend; k0 += 16) {
-    for (int i = threadIdx.x; i < 1024; i += 256) {
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = threadIdx.x + 256 * r;
       int kk, mm;
-      if (transA) { mm = i & 63; kk = i >> 6; } else { kk = i & 15; mm = i >> 4; }
+      if (transA) { mm = i & 63; kk = i >> 6; } else { kk = i & 31; mm = i >> 5; }
       const int gm = m0 + mm, gk = k0 + kk;
-      float v = 0.f;
-      if (gm < M && gk < kend) v = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-      sA[kk][mm] = v;
+      ra[r] = (gm < M && gk < kend) ? __ldg(transA ? A + (size_t)gk * lda + gm : A + (size_t)gm * lda + gk) : 0.f;
       int nn;
-      if (transB) { nn = i & 63; kk = i >> 6; } else { kk = i & 15; nn = i >> 4; }
+      if (transB) { nn = i & 63; kk = i >> 6; } else { kk = i & 31; nn = i >> 5; }
       const int gn = n0 + nn, gk2 = k0 + kk;
-      v = 0.f;
-      if (gn < N && gk2 < kend) v = transB ? B[(size_t)gk2 * ldb + gn] : B[(size_t)gn * ldb + gk2];
-      sB[kk][nn] = v;
+      rb[r] = (gn < N && gk2 < kend) ? __ldg(transB ? B + (size_t)gk2 * ldb + gn : B + (size_t)gn * ldb + gk2) : 0.f;
+    }
+  };
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += SK) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = threadIdx.x + 256 * r;
+      if (transA) sA[i >> 6][i & 63] = ra[r]; else sA[i & 31][i >> 5] = ra[r];
+      if (transB) sB[i >> 6][i & 63] = rb[r]; else sB[i & 31][i >> 5] = rb[r];
     }
     __syncthreads();
+    if (k0 + SK < kend) fetch(k0 + SK);
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
+    for (int kk = 0; kk < SK; ++kk) {
       float a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty + 16 * i]; b[i] = sB[kk][tx + 16 * i]; }
@@ -291,7 +303,7 @@ int eavit_sgemm_small(const float* A, long long lda, int transA, const float* B,
     if (splits > K / 64) splits = K / 64;
     if (splits < 1) splits = 1;
   }
-  int kps = cdiv(cdiv(K, splits), 16) * 16;
+  int kps = cdiv(cdiv(K, splits), 32) * 32;
   splits = cdiv(K, kps);
   dim3 grid(cdiv(N, 64), cdiv(M, 64), splits);
   sgemm_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, transA, B, ldb, transB, bias, mask_aux, C, ldc, M, N, K, relu, accumulate, kps);

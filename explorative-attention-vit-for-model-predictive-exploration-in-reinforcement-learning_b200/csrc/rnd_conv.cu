@@ -71,6 +71,31 @@ __global__ void __launch_bounds__(256) split3_rows_kernel(const float* __restric
   *reinterpret_cast<uint32_t*>(row + 2 * K + 2 * k2) = mode == 0 ? lo : hi;
 }
 
+// x <- act(x + bias) in place; optional bf16 copy and [hi | hi | lo] rows (see eavit_bias_act_split3)
+__global__ void __launch_bounds__(256) bias_act_split3_kernel(float* __restrict__ x, long long ldx, const float* __restrict__ bias,
+                                                              int act, __nv_bfloat16* __restrict__ out16,
+                                                              __nv_bfloat16* __restrict__ out3, int R, int K) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * (K / 2)) return;
+  const int k2 = (int)(i % (K / 2));
+  const long long r = i / (K / 2);
+  float2 v = *reinterpret_cast<const float2*>(x + r * ldx + 2 * k2);
+  if (bias != nullptr) { v.x += bias[2 * k2]; v.y += bias[2 * k2 + 1]; }
+  if (act == EAVIT_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+  else if (act == EAVIT_ACT_LRELU) { v.x = v.x > 0.f ? v.x : 0.01f * v.x; v.y = v.y > 0.f ? v.y : 0.01f * v.y; }
+  *reinterpret_cast<float2*>(x + r * ldx + 2 * k2) = v;
+  const uint32_t hi = pack_bf16x2(v.x, v.y);
+  if (out16 != nullptr) *reinterpret_cast<uint32_t*>(out16 + (size_t)r * K + 2 * k2) = hi;
+  if (out3 != nullptr) {
+    const float2 h = unpack_bf16x2(hi);
+    const uint32_t lo = pack_bf16x2(v.x - h.x, v.y - h.y);
+    __nv_bfloat16* row = out3 + (size_t)r * 3 * K;
+    *reinterpret_cast<uint32_t*>(row + 2 * k2) = hi;
+    *reinterpret_cast<uint32_t*>(row + K + 2 * k2) = hi;
+    *reinterpret_cast<uint32_t*>(row + 2 * K + 2 * k2) = lo;
+  }
+}
+
 __global__ void __launch_bounds__(256) nhwc_to_flat_f32_kernel(const float* __restrict__ act, int B, int HW, int C,
                                                                float* __restrict__ flat) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,6 +191,16 @@ int eavit_im2col(const void* in, int in_dtype, const long long* sample_idx, int 
 int eavit_split3_rows(const float* in, long long ldi, int R, int K, void* out_bf16, int mode, void* stream) {
   EAVIT_CHECK_ARG(in && out_bf16 && R > 0 && K > 0 && K % 2 == 0 && ldi % 2 == 0 && (mode == 0 || mode == 1));
   split3_rows_kernel<<<cdiv((long long)R * (K / 2), 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, R, K, (__nv_bfloat16*)out_bf16, mode);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_bias_act_split3(float* x, long long ldx, const float* bias, int act, void* out_bf16, void* out3_bf16, int R, int K,
+                          void* stream) {
+  EAVIT_CHECK_ARG(x && R > 0 && K > 0 && K % 2 == 0 && ldx % 2 == 0);
+  EAVIT_CHECK_ARG(act == EAVIT_ACT_NONE || act == EAVIT_ACT_RELU || act == EAVIT_ACT_LRELU);
+  bias_act_split3_kernel<<<cdiv((long long)R * (K / 2), 256), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, bias, act, (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)out3_bf16, R, K);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }

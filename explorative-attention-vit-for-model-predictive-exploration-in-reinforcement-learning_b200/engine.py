@@ -606,16 +606,22 @@ class RNDNet:
             n, k = w.shape[0], w[0].numel()
             call("eavit_split3_rows", w, k, n, k, w3, 1)
 
-    def forward(self, obs: torch.Tensor, B: int, sample_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """obs fp32 [N,1,H,W] (normalised, clipped); returns features fp32 [B, out]."""
+    def forward(self, obs: torch.Tensor, B: int, sample_idx: Optional[torch.Tensor] = None,
+                col0: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """obs fp32 [N,1,H,W] (normalised, clipped); returns features fp32 [B, out].
+        ``col0``: the first convolution's patch matrix of the SAME observations, already built by the other tower
+        (``self.buf[B].t["col0"]`` of that tower) -- predictor and target read identical inputs (model.py:457-461)."""
         s, p = self.s, self.pre
         bf = self.buf.setdefault(B, _Buffers(obs.device))
         assert obs.dtype == torch.float32
         x, sidx = obs, sample_idx
         for ci, ((k, st, cin, cout), (h, oh)) in enumerate(zip(self.CONVS, self.sizes)):
             K = cin * k * k
-            col = bf.get(f"col{ci}", (B * oh * oh, 3 * K), torch.bfloat16)
-            call("eavit_im2col", x, F32, sidx, B, h, h, cin, k, k, st, col, 1)
+            if ci == 0 and col0 is not None:
+                col = bf.t["col0"] = col0
+            else:
+                col = bf.get(f"col{ci}", (B * oh * oh, 3 * K), torch.bfloat16)
+                call("eavit_im2col", x, F32, sidx, B, h, h, cin, k, k, st, col, 1)
             a32 = bf.get(f"act32_{ci}", (B * oh * oh, cout), torch.float32)
             a16 = bf.get(f"act{ci}", (B * oh * oh, cout), torch.bfloat16)
             ops.gemm(col, self.w3[f"{2 * ci}"], bias=s.w(p + f"{2 * ci}.bias"), act=ops.ACT_LRELU, out_f32=a32, out_bf16=a16)
@@ -627,17 +633,21 @@ class RNDNet:
         call("eavit_split3_rows", flat32, self.flat_dim, B, self.flat_dim, h3, 0)
         out = None
         for j, k in enumerate(self.fcs):
+            # M = B rows give only B/128 x 2 output tiles: split K over the idle SMs (atomic fp32 accumulation into a zeroed
+            # buffer), then one small kernel adds the bias, applies the ReLU and emits the next layer's bf16x3 rows
             last = j == len(self.fcs) - 1
             bias = s.w(p + f"{k}.bias")
+            w3 = self.w3[f"{k}"]
+            f32 = bf.get("out" if last else f"fc32_{j}", (B, self.out), torch.float32)
+            call("eavit_zero", f32, f32.numel() * 4)
+            ops.gemm(h3, w3, out_f32=f32, atomic=True, split_k=_split_k(B, self.out, h3.shape[1]))
             if last:
-                out = bf.get("out", (B, self.out), torch.float32)
-                ops.gemm(h3, self.w3[f"{k}"], bias=bias, out_f32=out)
+                call("eavit_bias_act_split3", f32, self.out, bias, ops.ACT_NONE, None, None, B, self.out)
+                out = f32
             else:
-                f32 = bf.get(f"fc32_{j}", (B, self.out), torch.float32)
                 f16 = bf.get(f"fc16_{j}", (B, self.out), torch.bfloat16)
-                ops.gemm(h3, self.w3[f"{k}"], bias=bias, act=ops.ACT_RELU, out_f32=f32, out_bf16=f16)
                 h3 = bf.get(f"fc{j}", (B, 3 * self.out), torch.bfloat16)
-                call("eavit_split3_rows", f32, self.out, B, self.out, h3, 0)
+                call("eavit_bias_act_split3", f32, self.out, bias, ops.ACT_RELU, f16, h3, B, self.out)
         return out
 
     def backward(self, dout16: torch.Tensor):

@@ -243,6 +243,7 @@ _SPECS = {
     "eavit_gather_batch": "piipppppppppp",
     "eavit_im2col": "pipiiiiiiipi",
     "eavit_split3_rows": "pliipi",
+    "eavit_bias_act_split3": "plpippii",
     "eavit_nhwc_to_flat_f32": "piiip",
     "eavit_col2im_lrelu": "ppiiiiiiip",
     "eavit_nhwc_to_flat": "piiip",

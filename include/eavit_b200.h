@@ -249,6 +249,11 @@ int eavit_im2col(const void* in, int in_dtype, const long long* sample_idx /* ma
 /* bf16x3 split of fp32 rows: mode 0 [hi|hi|lo] (activations), mode 1 [hi|lo|hi] (weights); A3.B3^T = hi*hi+hi*lo+lo*hi.
  * Used for the RND towers, whose (Leaky)ReLU masks need near-fp32 pre-activations for gradient parity. */
 int eavit_split3_rows(const float* in, long long ldi, int R, int K, void* out_bf16, int mode, void* stream);
+/* Finisher of a split-K (atomically accumulated) fully-connected layer of the RND towers (model.py:380-416):
+ * x <- act(x + bias) in place (fp32, act = EAVIT_ACT_NONE / RELU / LRELU); optional bf16 copy [R,K] and bf16x3 activation
+ * rows [hi|hi|lo] [R,3K] for the next layer. */
+int eavit_bias_act_split3(float* x, long long ldx, const float* bias, int act, void* out_bf16 /* may be NULL */,
+                          void* out3_bf16 /* may be NULL */, int R, int K, void* stream);
 int eavit_nhwc_to_flat_f32(const float* act, int B, int HW, int C, float* flat, void* stream);
 int eavit_col2im_lrelu(const void* dcol_bf16, const void* act_bf16, int B, int H, int W, int C, int KH, int KW, int stride,
                        void* din_bf16, void* stream);
