@@ -15,6 +15,8 @@ from __future__ import annotations
 import weakref
 from typing import Optional
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -52,6 +54,29 @@ class FusedAdam(torch.optim.Optimizer):
     def load_state_dict(self, sd):
         st = self._agent().runtime().store
         st.m.copy_(sd["flat_exp_avg"]); st.v.copy_(sd["flat_exp_avg_sq"]); st.step.copy_(sd["step"])
+
+
+class _CapturedCall:
+    """fn(static device input) -> device tensor, captured once as a CUDA graph (fixed shapes, buffers and weights)."""
+
+    def __init__(self, fn, example: torch.Tensor):
+        self.x = example.clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=example.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                    # warm-up: scratch buffers, smem attributes, epoch word
+            for _ in range(2):
+                fn(self.x)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(self.x)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 class RNDAgent(nn.Module):
@@ -117,17 +142,48 @@ class RNDAgent(nn.Module):
                 self._rt.sync()
         return self._rt
 
+    # ---- rollout side: one captured CUDA graph per call shape -------------------------------------
+    # get_action / compute_intrinsic_reward run once per env step on E samples: ~45 / ~25 small launches whose host cost
+    # exceeds their GPU time.  Each is captured once per (batch, dtype) and replayed: H2D into the static input, one
+    # graph launch, one packed D2H.  With dropout active (the reference rolls out in train mode, fact 6) the captured
+    # seeds are constants, so the graph starts with a dropout-epoch bump and every replay draws fresh masks.
+    # EAVIT_ROLLOUT_GRAPH=0 (or an active kernel profile) keeps the eager launches.
+    def _graphed(self, kind: str, x: torch.Tensor, fn):
+        rt = self.runtime()
+        if os.environ.get("EAVIT_ROLLOUT_GRAPH", "1") != "1" or ops._PROF is not None:
+            return fn(x)
+        if getattr(self, "_graph_rt", None) is not rt:
+            self._graphs, self._graph_rt = {}, rt
+        key = (kind, tuple(x.shape), x.dtype, bool(self.model.training))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = _CapturedCall(fn, x)
+        return g(x)
+
+    def _act_device(self, x: torch.Tensor) -> torch.Tensor:
+        rt = self.runtime()
+        if rt.dropout_active():
+            call("eavit_dropout_epoch_bump")
+        pol, ve, vi = rt.ac_forward(x, x.shape[0])
+        return torch.cat((pol.reshape(-1), ve, vi))                       # one packed D2H read instead of four
+
+    def _rnd_device(self, x: torch.Tensor) -> torch.Tensor:
+        rt = self.runtime()
+        x = x.to(torch.float32)                                           # torch.FloatTensor(next_obs), agents.py:212
+        B = x.shape[0]
+        tgt = rt.rnd_tgt.forward(x, B)
+        prd = rt.rnd_pred.forward(x, B, col0=rt.rnd_tgt.buf[B].t["col0"])
+        return ops.intrinsic_mse(tgt, prd)
+
     @torch.no_grad()
     def get_action(self, state):
         """agents.py:187-195 (DISCRETE): state float32 [E,C,H,W] (already /255) or uint8 raw frames.
         Returns (action int64 [E], value_ext f32 [E], value_int f32 [E], logits f32 [E,A]) as numpy."""
         rt = self.runtime()
-        rt.sync()
+        rt.sync_if_changed()
         x = _as_device_image(state, rt.device)
-        pol, ve, vi = rt.ac_forward(x, x.shape[0])
-        # one packed D2H read instead of four
-        E, A = pol.shape
-        pack = torch.cat((pol.reshape(-1), ve, vi)).cpu().numpy()
+        E, A = x.shape[0], self.output_size
+        pack = self._graphed("act", x, self._act_device).cpu().numpy()
         policy = pack[: E * A].reshape(E, A).copy()
         value_ext, value_int = pack[E * A: E * A + E].copy(), pack[E * A + E:].copy()
         z = policy - policy.max(axis=1, keepdims=True)
@@ -145,13 +201,10 @@ class RNDAgent(nn.Module):
     def compute_intrinsic_reward(self, next_obs):
         """agents.py:210-218: next_obs float64/float32 numpy (or CUDA tensor) [E,1,H,W], already normalised."""
         rt = self.runtime()
-        rt.sync()
+        rt.sync_if_changed()
         x = next_obs if torch.is_tensor(next_obs) else torch.from_numpy(np.ascontiguousarray(next_obs))
-        x = x.to(rt.device).to(torch.float32).contiguous()               # torch.FloatTensor(next_obs)
-        B = x.shape[0]
-        tgt = rt.rnd_tgt.forward(x, B)
-        prd = rt.rnd_pred.forward(x, B, col0=rt.rnd_tgt.buf[B].t["col0"])
-        return ops.intrinsic_mse(tgt, prd).cpu().numpy()
+        x = x.to(rt.device).contiguous()
+        return self._graphed("rnd", x, self._rnd_device).cpu().numpy()
 
     # ---- update ----------------------------------------------------------------------------------------
     def _scratch(self, B, A, dev):

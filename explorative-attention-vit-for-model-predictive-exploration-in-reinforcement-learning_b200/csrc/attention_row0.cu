@@ -303,7 +303,11 @@ template <int DH, int NCH>
 static int row0_fwd_go(const void* qkv, const int* seq_start, int nseq, int H, int SP, float scale, void* out0, const DropCfg& drop,
                        cudaStream_t st) {
   const size_t smem = ((size_t)H * SP + (size_t)R0_WARPS * H * DH) * sizeof(float);
-  EAVIT_CUDA(cudaFuncSetAttribute(attention_row0_fwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set = 0;              // raise the limit only when a larger request appears (never during graph capture replays)
+  if (smem > smem_set) {
+    EAVIT_CUDA(cudaFuncSetAttribute(attention_row0_fwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   attention_row0_fwd_kernel<DH, NCH><<<nseq, R0_THREADS, smem, st>>>((const __nv_bfloat16*)qkv, seq_start, H, SP, scale,
                                                                       (__nv_bfloat16*)out0, drop);
   EAVIT_LAUNCH_OK();
@@ -313,7 +317,11 @@ template <int DH, int NCH>
 static int row0_bwd_go(const void* qkv, const void* dout0, const int* seq_start, int nseq, int H, int SP, float scale, void* dqkv,
                        const DropCfg& drop, cudaStream_t st) {
   const size_t smem = ((size_t)2 * H * SP + (size_t)R0_WARPS * H * DH) * sizeof(float);
-  EAVIT_CUDA(cudaFuncSetAttribute(attention_row0_bwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    EAVIT_CUDA(cudaFuncSetAttribute(attention_row0_bwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   attention_row0_bwd_kernel<DH, NCH><<<nseq, R0_THREADS, smem, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout0,
                                                                       seq_start, H, SP, scale, (__nv_bfloat16*)dqkv, drop);
   EAVIT_LAUNCH_OK();

@@ -109,11 +109,17 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // bits.  One 32-bit hash serves a column pair (16 bits each): keep iff bits >= thresh, thresh = round(p * 65536)
 // (p = 0.1 -> 6554 / 65536 = 0.100006); kept values are scaled by 1 / (1 - thresh / 65536) (exactly unbiased).
 // `eavit_dropout_mask` materialises the same mask for tests (the oracle is run with identical masks).
+// `epoch` points at a per-device counter owned by the library (api.cu).  It is folded into every row key, so a CAPTURED
+// launch (CUDA graph of the rollout forward, whose by-value seeds are frozen at capture time) still draws fresh masks on
+// every replay once the graph bumps the counter (eavit_dropout_epoch_bump).  It stays 0 outside graphs: eager forward /
+// backward pairs and the parity tests see the seeds they pass.
 struct DropCfg {
   uint32_t thresh;      // 0 = dropout off
   uint32_t seed_lo, seed_hi;
   float scale;
+  const uint32_t* epoch;   // device pointer, NULL when dropout is off
 };
+const uint32_t* drop_epoch_ptr();      // host: device address of the current device's epoch word (allocated on first use)
 __host__ __device__ inline DropCfg make_drop(float p, unsigned long long seed) {
   DropCfg d;
   const float pc = p < 0.f ? 0.f : (p > 0.999f ? 0.999f : p);
@@ -121,13 +127,20 @@ __host__ __device__ inline DropCfg make_drop(float p, unsigned long long seed) {
   d.seed_lo = (uint32_t)seed;
   d.seed_hi = (uint32_t)(seed >> 32);
   d.scale = 1.0f / (1.0f - (float)d.thresh * (1.0f / 65536.0f));
+  d.epoch = nullptr;
+#ifndef __CUDA_ARCH__
+  if (d.thresh) d.epoch = drop_epoch_ptr();
+#endif
   return d;
 }
 __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
-__device__ __forceinline__ uint32_t drop_row_key(const DropCfg& d, uint32_t r) { return lowbias32(r ^ d.seed_lo) + d.seed_hi; }
+__device__ __forceinline__ uint32_t drop_row_key(const DropCfg& d, uint32_t r) {
+  const uint32_t e = d.epoch ? __ldg(d.epoch) : 0u;
+  return lowbias32((r ^ d.seed_lo) + e * 0x85EBCA6Bu) + d.seed_hi;
+}
 // 32 bits for columns (2*cp, 2*cp + 1) of a row whose key is `rk`
 __device__ __forceinline__ uint32_t drop_bits(uint32_t rk, uint32_t cp) { return lowbias32(rk + cp * 0x9E3779B9u); }
 __device__ __forceinline__ float drop_even(const DropCfg& d, uint32_t bits) { return (bits & 0xffffu) >= d.thresh ? d.scale : 0.f; }

@@ -121,8 +121,21 @@ class Runtime:
         st = self.store if n0 in self.store.shapes else self.frozen
         return self._first.data_ptr() == st.w(n0).data_ptr()
 
+    def _param_versions(self) -> int:
+        """Sum of the autograd version counters of every parameter: load_state_dict, torch optimisers and any in-place op
+        on a Parameter bump them; the fused Adam step (which maintains the shadows itself) does not."""
+        return sum(p._version for p in self.params.values())
+
+    def sync_if_changed(self):
+        """``sync()`` only when a parameter was written from outside since the last sync -- the rollout calls this once per
+        env step (12 launches saved per call).  Writes through ``p.data`` bypass the version counters: call ``sync()``."""
+        v = self._param_versions()
+        if v != getattr(self, "_synced_version", None):
+            self.sync()
+
     def sync(self):
         """Refresh the bf16 shadows after the fp32 masters were written from outside (load_state_dict, ...)."""
+        self._synced_version = self._param_versions()
         self.store.sync_shadow()
         if self.frozen is not None:
             self.frozen.sync_shadow()
@@ -135,6 +148,11 @@ class Runtime:
                 p.grad = self.store.g(n)
 
     # ---- actor-critic ----------------------------------------------------------------------------
+    def dropout_active(self) -> bool:
+        c = self.cfg
+        return bool(self._feat.training and max(c.dropout, c.emb_dropout, c.attn_dropout, c.act_dropout) > 0
+                    and os.environ.get("EAVIT_DROPOUT_AS_IDENTITY", "0") != "1")
+
     def next_drop_base(self):
         """Dropout stream id of the next forward call: None when dropout is off (eval mode or every p = 0).  Like the
         reference, dropout follows the module's train/eval flag -- the rollout runs in train mode too."""

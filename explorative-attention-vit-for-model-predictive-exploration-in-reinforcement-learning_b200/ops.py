@@ -242,6 +242,8 @@ _SPECS = {
     "eavit_rnd_loss": "pppiifppp",
     "eavit_gather_batch": "piipppppppppp",
     "eavit_im2col": "pipiiiiiiipi",
+    "eavit_dropout_epoch_bump": "",
+    "eavit_dropout_epoch_set": "i",
     "eavit_split3_rows": "pliipi",
     "eavit_bias_act_split3": "plpippii",
     "eavit_nhwc_to_flat_f32": "piiip",

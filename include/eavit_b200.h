@@ -190,6 +190,11 @@ int eavit_attention_row0_bwd(const void* qkv, const void* dout0, const int* seq_
  * backward, attention) evaluate it in place; these two entry points apply / materialise the SAME mask:
  *   eavit_dropout_apply: dst[i, c] = src[i, c] * mask(rows ? rows[i] : row0 + i, c)   (in place allowed)
  *   eavit_dropout_mask : out[i, j] = mask(row0 + i, col0 + j)  in {0, 1/(1-p)}          (tests / oracle hook) */
+/* Dropout epoch: a per-device counter folded into every mask (mask = f(seed, epoch, row, col)); 0 unless set.  A CUDA
+ * graph of the rollout forward (seeds frozen at capture) captures one `bump` so that every replay draws new masks, the way
+ * each eager call of the reference's nn.Dropout does (vit.py:158; rollout in train mode, agents.py:187-195). */
+int eavit_dropout_epoch_bump(void* stream);
+int eavit_dropout_epoch_set(int value, void* stream);
 int eavit_dropout_apply(const float* src, long long lds, const int* rows, int row0, float* dst, long long ldd, int n, int D,
                         float p, unsigned long long seed, void* stream);
 int eavit_dropout_mask(float* out, long long ld, int row0, int n, int col0, int ncols, float p, unsigned long long seed,
