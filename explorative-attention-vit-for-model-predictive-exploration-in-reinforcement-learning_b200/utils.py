@@ -3,9 +3,13 @@ RewardForwardFilter, global_grad_norm_, set_seed, Env_action_space_type, Logger)
 kernels.  numpy in / numpy out like the reference; device-resident variants avoid the host round trip."""
 from __future__ import annotations
 
+import contextlib
 import logging
 import os
+import pickle
 import random
+import sys
+import types
 from enum import Enum
 from typing import Optional
 
@@ -243,3 +247,81 @@ class Logger:
 
     def step_pytorch_profiler(self, *a, **k):
         pass
+
+
+# ---------------------------------------------------------------------------------------------- checkpoints
+# train.py:883-960 / :198-238: a checkpoint is one ``torch.save`` dict -- the agent's state_dicts plus the PICKLED
+# ``obs_rms`` / ``reward_rms`` (RunningMeanStd) and ``discounted_reward`` (RewardForwardFilter) objects, which the pickle
+# stream names by the reference's module path ``utils.<Class>``.  The two helpers keep that format loadable both ways:
+# a reference checkpoint restores this package's device-backed objects, and a checkpoint written here restores the
+# reference's own numpy classes (attribute for attribute: usage / mean / var / count / train_method, rewems / gamma).
+_CKPT_CLASSES = ("RunningMeanStd", "RewardForwardFilter")
+
+
+class _RefUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if module == "utils" and name in _CKPT_CLASSES:
+            return globals()[name]
+        return super().find_class(module, name)
+
+
+_ref_pickle = types.ModuleType("eavit_b200_ref_pickle")
+_ref_pickle.__dict__.update({k: getattr(pickle, k) for k in dir(pickle) if not k.startswith("__")})
+_ref_pickle.Unpickler = _RefUnpickler
+_ref_pickle.load = lambda f, **kw: _RefUnpickler(f, **kw).load()
+
+
+def load_checkpoint(path, map_location=None) -> dict:
+    """``torch.load`` of a checkpoint written by the reference (train.py:926-959) or by ``save_checkpoint``: tensors as
+    usual, ``utils.RunningMeanStd`` / ``utils.RewardForwardFilter`` pickles come back as this package's classes."""
+    return torch.load(path, map_location=map_location, weights_only=False, pickle_module=_ref_pickle)
+
+
+@contextlib.contextmanager
+def _reference_class_paths():
+    """Make ``utils.RunningMeanStd`` / ``utils.RewardForwardFilter`` resolvable while pickling, without importing the
+    reference: plain attribute-bag classes under that module path (pickle stores the path + ``__dict__`` only)."""
+    prev = sys.modules.get("utils")
+    mod = prev
+    added = []
+    if mod is None:
+        mod = types.ModuleType("utils")
+        sys.modules["utils"] = mod
+    for name in _CKPT_CLASSES:
+        if not hasattr(mod, name):
+            setattr(mod, name, type(name, (object,), {"__module__": "utils", "__qualname__": name}))
+            added.append(name)
+    try:
+        yield mod
+    finally:
+        for name in added:
+            delattr(mod, name)
+        if prev is None:
+            del sys.modules["utils"]
+
+
+def _as_reference_object(obj, mod):
+    if isinstance(obj, RunningMeanStd):
+        cls = getattr(mod, "RunningMeanStd")
+        if isinstance(obj, cls):                       # this package already IS the importable ``utils``
+            return obj
+        st = obj.__getstate__()
+        st.pop("shape")
+        ref = cls.__new__(cls)
+        ref.__dict__.update(st)
+        return ref
+    if isinstance(obj, RewardForwardFilter):
+        cls = getattr(mod, "RewardForwardFilter")
+        if isinstance(obj, cls):
+            return obj
+        ref = cls.__new__(cls)
+        ref.__dict__.update(rewems=None if obj.rewems is None else np.array(obj.rewems), gamma=obj.gamma)
+        return ref
+    return obj
+
+
+def save_checkpoint(ckpt_dict: dict, path) -> None:
+    """``torch.save(ckpt_dict, path)`` (train.py:958-959) with the statistics objects written in the reference's own
+    pickle format, so that ``torch.load`` inside the reference's train.py:198-238 restores its numpy classes."""
+    with _reference_class_paths() as mod:
+        torch.save({k: _as_reference_object(v, mod) for k, v in ckpt_dict.items()}, path)
