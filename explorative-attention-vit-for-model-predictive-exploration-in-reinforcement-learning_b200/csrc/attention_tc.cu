@@ -56,10 +56,16 @@ struct AttSmem {
 
 // DROP: nn.Dropout on the attention probabilities (vit.py:45,70 / HF attention_probs_dropout_prob): the row sum (softmax
 // denominator) uses the full probabilities, the P.V operand is masked.  Mask element = (token row t0 + q, column h*256 + k).
-template <int DH, bool DROP>
+// SEG: short equal-length sequences are PACKED -- a work item is `pack` consecutive sequences (they are contiguous in the
+// token matrix) treated as one sequence of pack * seg tokens under a block-diagonal mask: row i attends to the keys of
+// its own segment [lo, hi) only.  Masked probabilities are exact zeros, so every later product (P.V, and dV / dK / dQ in
+// the backward) is unchanged; the per-item latency chain (TMA -> MMA -> softmax -> MMA), which is all a 50-token
+// sequence costs, is paid once per pack instead of once per sequence (HF-style ViT: 50 tokens -> 4 per item).
+template <int DH, bool DROP, bool SEG>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ seq_start, int nseq, int H,
-                        float scale, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, const DropCfg drop) {
+                        float scale, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, const DropCfg drop,
+                        int pack, int seg) {
   constexpr int HPB = 64 / DH;                      // heads per 128-byte box row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -96,12 +102,12 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
   const int HG = H / HPB;
   const float c2 = scale * 1.4426950408889634f;      // exp(x*scale) = exp2(x*c2)
   uint32_t ph0 = 0, ph1 = 0, ph_ld = 0;              // parities of bar_*[0], bar_*[1], bar_ld (uniform across the CTA)
-  const int n_items = nseq * HG;
+  const int n_items = ((nseq + pack - 1) / pack) * HG;
   // Q and K are dead once the last head's score MMAs have completed, V once its P.V MMAs have: the next item's Q / K
   // land during the current item's last softmax and its V during the following one (TMA latency fully hidden).
   auto issue_qk = [&](int it) {                      // one thread
     const int sq = it / HG, hg = it - sq * HG;
-    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const int tt = seq_start[sq * pack], SS = seq_start[min(nseq, sq * pack + pack)] - tt;
     const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
     tc::mbar_expect_tx(bar_qk, 2 * nb * BOX_BYTES);
     for (int b = 0; b < nb; ++b) {
@@ -111,7 +117,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
   };
   auto issue_v = [&](int it) {
     const int sq = it / HG, hg = it - sq * HG;
-    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const int tt = seq_start[sq * pack], SS = seq_start[min(nseq, sq * pack + pack)] - tt;
     const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
     tc::mbar_expect_tx(bar_v, nb * BOX_BYTES);
     for (int b = 0; b < nb; ++b)
@@ -123,7 +129,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
 #endif
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int seq = item / HG, hg = item - seq * HG;
-    const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
+    const int t0 = seq_start[seq * pack], S = seq_start[min(nseq, seq * pack + pack)] - t0;
     const int NKT = (S + 31) & ~31;                  // score columns
     const int NKP = (S + 15) & ~15;                  // keys covered by the P.V MMA
     const bool two_tiles = S > 128;
@@ -146,6 +152,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
       const int tl = HPB == 2 ? (g ? nt - 1 - j : j) : g;      // query tile of this sub-item
       const int xrow = tl * 128 + row_in_tile;
       const bool last = j == nsub - 1;
+      int lo = 0, hi = S;                              // keys this row attends to
+      if constexpr (SEG) {
+        if (xrow < S) { lo = (xrow / seg) * seg; hi = min(lo + seg, S); }     // rows past the end keep [0, S): finite garbage, never stored
+      }
       {
         const uint32_t phase = (g ? ph1 : ph0) ^ (uint32_t)(j & 1);
         const uint32_t s_col = tmem_base + (uint32_t)(g * ATC_MAXKEYS);
@@ -178,7 +188,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
         float mx = -INFINITY;
         if (rows_live) {
           tc::tmem_stream16(lane_addr, cbeg, cbeg + half, [&](const uint32_t* r, int c0) {
-            if (c0 + 16 <= S) {
+            if (SEG && (c0 + 16 <= lo || c0 >= hi)) return;      // another sequence's keys
+            if (SEG ? (c0 >= lo && c0 + 16 <= hi) : (c0 + 16 <= S)) {
               // four independent max chains (a single one serialises 112 dependent FMNMX per row)
               float m0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), m1 = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
               float m2 = fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), m3 = fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7]));
@@ -188,7 +199,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (c0 + j < S) mx = fmaxf(mx, __uint_as_float(r[j]));
+                if (c0 + j >= lo && c0 + j < hi) mx = fmaxf(mx, __uint_as_float(r[j]));
             }
           });
         }
@@ -208,8 +219,16 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
         if (rows_live) {
           tc::tmem_stream16(lane_addr, cbeg, cbeg + half, [&](const uint32_t* r, int c0) {
             if (c0 >= NKP) return;                       // beyond the keys the P.V MMA reads
+            uint8_t* slab = pbase + (c0 >> 6) * P_SLAB;
+            const int cb = (c0 & 63) >> 3;
+            if (SEG && (c0 + 16 <= lo || c0 >= hi)) {            // another sequence's keys: exact zeros, no math
+              *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(0, 0, 0, 0);
+              return;
+            }
             uint32_t pk[8];
-            if (c0 + 16 <= S) {
+            const uint32_t dcol = hcol + (uint32_t)(c0 - lo);      // dropout column = key index inside the row's own sequence (lo is even)
+            if (SEG ? (c0 >= lo && c0 + 16 <= hi) : (c0 + 16 <= S)) {
               float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
@@ -217,7 +236,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
                 float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb));
                 if (j & 2) { s2 += p0; s3 += p1; } else { s0 += p0; s1 += p1; }
                 if constexpr (DROP) {
-                  const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+                  const uint32_t bits = drop_bits(rk, (dcol + (uint32_t)j) >> 1);
                   p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
                 }
                 pk[j >> 1] = pack_bf16x2(p0, p1);
@@ -226,18 +245,16 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
             } else {
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb)) : 0.f;
-                float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb)) : 0.f;
+                float p0 = (c0 + j >= lo && c0 + j < hi) ? ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mb)) : 0.f;
+                float p1 = (c0 + j + 1 >= lo && c0 + j + 1 < hi) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), c2, -mb)) : 0.f;
                 sum += p0 + p1;
                 if constexpr (DROP) {
-                  const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+                  const uint32_t bits = drop_bits(rk, (dcol + (uint32_t)j) >> 1);
                   p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
                 }
                 pk[j >> 1] = pack_bf16x2(p0, p1);
               }
             }
-            uint8_t* slab = pbase + (c0 >> 6) * P_SLAB;
-            const int cb = (c0 & 63) >> 3;
             *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           });
@@ -344,11 +361,11 @@ struct AttBwdSmem {
 // DROP: with dropout mask M on the probabilities, dV = (P o M)^T dO, D_i = sum_j P_ij M_ij dP_ij and dS = P o (M o dP - D):
 // pass 1 stages the MASKED P~ for the dV MMA; pass 2 needs the unmasked P again and recomputes it from S, which stays
 // intact because the dV accumulators live in the last 64 TMEM columns instead of overlaying S.
-template <int DH, bool DROP>
+template <int DH, bool DROP, bool SEG>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const float* __restrict__ lse, const int* __restrict__ seq_start, int nseq, int H, float scale,
-                        __nv_bfloat16* __restrict__ dqkv, const DropCfg drop) {
+                        __nv_bfloat16* __restrict__ dqkv, const DropCfg drop, int pack, int seg) {
   constexpr int HPB = 64 / DH;                      // heads per 128-byte box row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -381,7 +398,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   constexpr int COL_DP = 224, COL_DV = 448, COL_DK = 0, COL_DQ = 128;   // dV: 2 x Dh (Dh = 32) or 1 x 64 columns at 448
   constexpr int HC = DH / 2;                       // accumulator columns per thread
   uint32_t phase = 0, ph_ld = 0;
-  const int n_items = nseq * HG;
+  const int n_items = ((nseq + pack - 1) / pack) * HG;
   const uint32_t sQ = tc::smem_u32(smem + AttBwdSmem::OFF_Q), sDO = tc::smem_u32(smem + AttBwdSmem::OFF_DO);
   const uint32_t sK = tc::smem_u32(smem + AttBwdSmem::OFF_K), sV = tc::smem_u32(smem + AttBwdSmem::OFF_V);
   const uint32_t sP = tc::smem_u32(smem + AttBwdSmem::OFF_P);
@@ -389,7 +406,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
   auto issue_loads = [&](int it) {                 // one thread
     const int sq = it / HG, hg = it - sq * HG;
-    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const int tt = seq_start[sq * pack], SS = seq_start[min(nseq, sq * pack + pack)] - tt;
     const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
     tc::mbar_expect_tx(&bars[3], 4 * nb * BOX_BYTES);
     const int offs[3] = {AttBwdSmem::OFF_Q, AttBwdSmem::OFF_K, AttBwdSmem::OFF_V};
@@ -406,7 +423,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 #endif
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int seq = item / HG, hg = item - seq * HG;
-    const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
+    const int t0 = seq_start[seq * pack], S = seq_start[min(nseq, seq * pack + pack)] - t0;
     const int NKP = (S + 15) & ~15, NKT = NKP;     // score columns = keys covered by the dQ MMA (multiple of 16: 208 at S = 196 / 197)
     const int NQ = (S + 127) >> 7;                 // query tiles == key tiles
 #ifdef EAVIT_TRACE
@@ -443,6 +460,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       TR(1);
       const int qrow = g * 128 + row_in_tile;
       const bool qok = qrow < S;
+      int lo = 0, hi = S;                            // keys of this row's own sequence (SEG: packed sequences, block-diagonal mask)
+      if constexpr (SEG) {
+        if (qok) { lo = (qrow / seg) * seg; hi = min(lo + seg, S); }
+      }
       const int kq = (min(128, S - g * 128) + 15) >> 4;   // 16-row K steps of the dK / dV MMAs that hold valid queries
       const float l2 = qok ? lse[(size_t)(t0 + qrow) * H + h] * 1.4426950408889634f : INFINITY;   // invalid row: P~ = 0
       tc::mbar_wait(&bars[0], phase);
@@ -459,15 +480,20 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const uint32_t hcol = (uint32_t)h * 256u;
       if (rows_live) {
         tc::tmem_stream16x2<8>(lane_base, COL_DP, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
+          if (SEG && (c0 + 8 <= lo || c0 >= hi)) {             // another sequence's keys: P~ = 0 (and dS stays 0 in pass 2)
+            *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(0, 0, 0, 0);
+            return;
+          }
           uint32_t pk[4];
           float d0 = 0.f, d1 = 0.f;
-          if (c0 + 8 <= S) {
+          const uint32_t dcol = hcol + (uint32_t)(c0 - lo);
+          if (SEG ? (c0 >= lo && c0 + 8 <= hi) : (c0 + 8 <= S)) {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
               float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2));
               float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2));
               if constexpr (DROP) {
-                const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+                const uint32_t bits = drop_bits(rk, (dcol + (uint32_t)j) >> 1);
                 p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
               }
               pk[j >> 1] = pack_bf16x2(p0, p1);
@@ -477,10 +503,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           } else {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
-              float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
-              float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
+              float p0 = (c0 + j >= lo && c0 + j < hi) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
+              float p1 = (c0 + j + 1 >= lo && c0 + j + 1 < hi) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
               if constexpr (DROP) {
-                const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+                const uint32_t bits = drop_bits(rk, (dcol + (uint32_t)j) >> 1);
                 p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
               }
               pk[j >> 1] = pack_bf16x2(p0, p1);
@@ -522,12 +548,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       // ---- pass 2: dS = P~ (dP - D) -> smem
       if (rows_live && DROP) {
         tc::tmem_stream16x2<8>(lane_base, COL_DP, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
+          if (SEG && (c0 + 8 <= lo || c0 >= hi)) return;
           uint32_t ds[4];
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
-            const float p0 = (c0 + j < S) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
-            const float p1 = (c0 + j + 1 < S) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
-            const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j)) >> 1);
+            const float p0 = (c0 + j >= lo && c0 + j < hi) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
+            const float p1 = (c0 + j + 1 >= lo && c0 + j + 1 < hi) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
+            const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j - lo)) >> 1);
             ds[j >> 1] = pack_bf16x2(p0 * fmaf(drop_even(drop, bits), __uint_as_float(rp[j]), -Di),
                                      p1 * fmaf(drop_odd(drop, bits), __uint_as_float(rp[j + 1]), -Di));
           }
@@ -535,6 +562,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         });
       } else if (rows_live) {
         tc::tmem_stream16<8>(lane_base + COL_DP, cbeg, cend, [&](const uint32_t* rp, int c0) {
+          if (SEG && (c0 + 8 <= lo || c0 >= hi)) return;
           uint8_t* addr = pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3);
           const uint4 pa = *reinterpret_cast<uint4*>(addr);
           const uint32_t pin[4] = {pa.x, pa.y, pa.z, pa.w};
@@ -661,23 +689,46 @@ static int attention_tmaps(const void* qkv, const void* dout, long long T, int H
   return rc;
 }
 
+// Sequences per work item: > 1 only when every sequence has the same even length (total == nseq * max_len) and several fit
+// into the `limit` tokens one item can hold.
+static int att_pack(int nseq, int max_len, long long total_tokens, int limit) {
+  if (total_tokens != (long long)nseq * max_len || (max_len & 1) || 2 * max_len > limit) return 1;
+  return limit / max_len;
+}
+
+template <int DH, bool DROP, bool SEG>
+static int launch_att_fwd2(const CUtensorMap& tq, const int* seq_start, int nseq, int H, float scale, void* out, float* lse,
+                           const DropCfg& drop, int pack, int seg, cudaStream_t st) {
+  static bool done = false;
+  if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel<DH, DROP, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::TOTAL)); done = true; }
+  const int items = ((nseq + pack - 1) / pack) * (H / (64 / DH));
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  attention_fwd_tc_kernel<DH, DROP, SEG><<<grid, ATC_THREADS, AttSmem::TOTAL, st>>>(tq, seq_start, nseq, H, scale, (__nv_bfloat16*)out, lse, drop, pack, seg);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
 template <int DH, bool DROP>
 static int launch_att_fwd(const CUtensorMap& tq, const int* seq_start, int nseq, int H, float scale, void* out, float* lse,
-                          const DropCfg& drop, int grid, cudaStream_t st) {
+                          const DropCfg& drop, int pack, int seg, cudaStream_t st) {
+  return pack > 1 ? launch_att_fwd2<DH, DROP, true>(tq, seq_start, nseq, H, scale, out, lse, drop, pack, seg, st)
+                  : launch_att_fwd2<DH, DROP, false>(tq, seq_start, nseq, H, scale, out, lse, drop, 1, 0, st);
+}
+template <int DH, bool DROP, bool SEG>
+static int launch_att_bwd2(const CUtensorMap& tq, const CUtensorMap& tdo, const float* lse, const int* seq_start, int nseq, int H,
+                           float scale, void* dqkv, const DropCfg& drop, int pack, int seg, cudaStream_t st) {
   static bool done = false;
-  if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::TOTAL)); done = true; }
-  attention_fwd_tc_kernel<DH, DROP><<<grid, ATC_THREADS, AttSmem::TOTAL, st>>>(tq, seq_start, nseq, H, scale, (__nv_bfloat16*)out, lse, drop);
+  if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<DH, DROP, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttBwdSmem::TOTAL)); done = true; }
+  const int items = ((nseq + pack - 1) / pack) * (H / (64 / DH));
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  attention_bwd_tc_kernel<DH, DROP, SEG><<<grid, ATC_THREADS, AttBwdSmem::TOTAL, st>>>(tq, tdo, lse, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv, drop, pack, seg);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
 template <int DH, bool DROP>
 static int launch_att_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const float* lse, const int* seq_start, int nseq, int H,
-                          float scale, void* dqkv, const DropCfg& drop, int grid, cudaStream_t st) {
-  static bool done = false;
-  if (!done) { EAVIT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttBwdSmem::TOTAL)); done = true; }
-  attention_bwd_tc_kernel<DH, DROP><<<grid, ATC_THREADS, AttBwdSmem::TOTAL, st>>>(tq, tdo, lse, seq_start, nseq, H, scale, (__nv_bfloat16*)dqkv, drop);
-  EAVIT_LAUNCH_OK();
-  return EAVIT_OK;
+                          float scale, void* dqkv, const DropCfg& drop, int pack, int seg, cudaStream_t st) {
+  return pack > 1 ? launch_att_bwd2<DH, DROP, true>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, pack, seg, st)
+                  : launch_att_bwd2<DH, DROP, false>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, 1, 0, st);
 }
 
 // total tokens = seq_start[nseq]; the host mirror passes it so that no device read-back is needed
@@ -694,12 +745,11 @@ extern "C" int eavit_attention_fwd_tc(const void* qkv, const int* seq_start, int
   int rc = attention_tmaps(qkv, nullptr, total_tokens, H, Dh, &tq, &tdo);
   if (rc) return rc;
   const DropCfg drop = make_drop(drop_p, drop_seed);
-  const int items = nseq * (H / (64 / Dh));
-  const int grid = items < kNumSMs ? items : kNumSMs;
-  if (Dh == 32) return drop.thresh ? launch_att_fwd<32, true>(tq, seq_start, nseq, H, scale, out, lse, drop, grid, st)
-                                   : launch_att_fwd<32, false>(tq, seq_start, nseq, H, scale, out, lse, drop, grid, st);
-  return drop.thresh ? launch_att_fwd<64, true>(tq, seq_start, nseq, H, scale, out, lse, drop, grid, st)
-                     : launch_att_fwd<64, false>(tq, seq_start, nseq, H, scale, out, lse, drop, grid, st);
+  const int pack = att_pack(nseq, max_len, total_tokens, ATC_MAXKEYS), seg = max_len;
+  if (Dh == 32) return drop.thresh ? launch_att_fwd<32, true>(tq, seq_start, nseq, H, scale, out, lse, drop, pack, seg, st)
+                                   : launch_att_fwd<32, false>(tq, seq_start, nseq, H, scale, out, lse, drop, pack, seg, st);
+  return drop.thresh ? launch_att_fwd<64, true>(tq, seq_start, nseq, H, scale, out, lse, drop, pack, seg, st)
+                     : launch_att_fwd<64, false>(tq, seq_start, nseq, H, scale, out, lse, drop, pack, seg, st);
 }
 
 extern "C" int eavit_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const int* seq_start, int nseq,
@@ -715,12 +765,11 @@ extern "C" int eavit_attention_bwd_tc(const void* qkv, const void* dout, const f
   int rc = attention_tmaps(qkv, dout, total_tokens, H, Dh, &tq, &tdo);
   if (rc) return rc;
   const DropCfg drop = make_drop(drop_p, drop_seed);
-  const int items = nseq * (H / (64 / Dh));
-  const int grid = items < kNumSMs ? items : kNumSMs;
-  if (Dh == 32) return drop.thresh ? launch_att_bwd<32, true>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, grid, st)
-                                   : launch_att_bwd<32, false>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, grid, st);
-  return drop.thresh ? launch_att_bwd<64, true>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, grid, st)
-                     : launch_att_bwd<64, false>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, grid, st);
+  const int pack = att_pack(nseq, max_len, total_tokens, Dh == 64 ? 128 : ATC_MAXKEYS), seg = max_len;
+  if (Dh == 32) return drop.thresh ? launch_att_bwd<32, true>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, pack, seg, st)
+                                   : launch_att_bwd<32, false>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, pack, seg, st);
+  return drop.thresh ? launch_att_bwd<64, true>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, pack, seg, st)
+                     : launch_att_bwd<64, false>(tq, tdo, lse, seq_start, nseq, H, scale, dqkv, drop, pack, seg, st);
 }
 
 #ifdef EAVIT_TRACE

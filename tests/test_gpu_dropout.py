@@ -113,7 +113,8 @@ def ref_attention_drop(qkv, starts, H, Dh, scale, mask_fn):
     return torch.cat(outs, dim=0)
 
 
-@pytest.mark.parametrize("lens,H,Dh", [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([1, 17, 128, 129, 224], 4, 32)])
+@pytest.mark.parametrize("lens,H,Dh", [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([1, 17, 128, 129, 224], 4, 32),
+                                        ([50] * 5, 2, 64), ([64] * 7, 4, 32)])      # the last two run packed (block-diagonal mask)
 def test_attention_probability_dropout(ops, lens, H, Dh):
     torch.manual_seed(sum(lens))
     p, seed = 0.1, ops.site_seed(31, 9)
