@@ -93,3 +93,57 @@ def test_graph_replays_draw_fresh_dropout_masks():
     assert rel(pols.mean(0), clean) < 0.5 * rel(pols[0], clean) + 1e-3
     eager = np.stack([_eager(agent.get_action, states)[3] for _ in range(2)])
     assert np.array_equal(eager[0], eager[1]) and np.array_equal(eager[0], clean)     # eval mode: no dropout, no epoch effect
+
+
+def test_device_rollout_buffer_matches_reference_glue():
+    """DeviceRollout (per-step env-major writes + finish()) == the oracle's restatement of train.py:707-779 / :855 fed with
+    the same step-major buffers; then the tuple drives train_model directly (CUDA tensors, uint8 frames)."""
+    import eavit_b200  # noqa
+    from eavit_b200 import config, rollout, utils
+    cfg = CFGS["lucid"]
+    E, T, A = 4, 8, cfg.n_actions
+    roll = O.synth_rollout(E=E, T=T, seed=33)
+    rng = np.random.default_rng(5)
+    warm = rng.integers(0, 256, (40, 1, 84, 84)).astype(np.float64)      # initial observation statistics (train.py:127-180)
+    prev_r = rng.random((E, T)).astype(np.float32)                        # an earlier update: the filter state persists
+    # ---- oracle
+    o_obs, o_rrm, o_f = O.RunningMeanStd(shape=(1, 1, 84, 84)), O.RunningMeanStd(), O.RewardForwardFilter(cfg.int_gamma)
+    o_obs.update(warm)
+    O.normalize_int_reward(prev_r, o_f, o_rrm)
+    ref = O.prepare_update(cfg, T, E, roll, o_obs, o_rrm, o_f)
+    # ---- device
+    config.load_config(None, TrainMethod="original_RND")
+    d_obs, d_rrm = utils.RunningMeanStd(shape=(1, 1, 84, 84), usage="obs_rms"), utils.RunningMeanStd(usage="reward_rms")
+    d_f = utils.RewardForwardFilter(cfg.int_gamma)
+    d_obs.update(warm)
+    mom = d_f.filter_rollout(torch.tensor(prev_r, device="cuda")).cpu().numpy()
+    d_rrm.update_from_moments(float(mom[0]), float(mom[1]), int(mom[2]))
+    buf = rollout.DeviceRollout(E, T, A)
+    ve, vi = roll["total_ext_values"].reshape(T + 1, E), roll["total_int_values"].reshape(T + 1, E)
+    for t in range(T):
+        sl = slice(t * E, (t + 1) * E)
+        buf.add(t, roll["total_state"][sl], roll["total_next_obs"][sl], roll["total_reward"][sl], roll["total_done"][sl],
+                roll["total_action"][sl], ve[t], vi[t], roll["total_policy"][sl], roll["total_int_reward"][sl])
+    buf.add_last_values(ve[T], vi[T])
+    got = buf.finish(d_obs, d_rrm, d_f, cfg.gamma, cfg.int_gamma, cfg.lam, cfg.ext_coef, cfg.int_coef)
+    states, te, ti, y, adv, obs, old = [g.cpu().numpy() for g in got]
+    r_states, r_te, r_ti, r_y, r_adv, r_obs, r_old = ref
+    assert states.dtype == np.uint8 and np.array_equal(np.float32(states) / np.float32(255.0), r_states)     # layout e*T+t, exact
+    assert np.array_equal(y, r_y)
+    assert np.array_equal(old, r_old.transpose(1, 0, 2).reshape(E * T, A))                                    # agents.py:301
+    assert np.array_equal(te, r_te)                                       # extrinsic GAE: float64, bit-exact
+    np.testing.assert_allclose(ti, r_ti, rtol=2e-5)                       # intrinsic: through the float32 reward moments
+    np.testing.assert_allclose(adv, r_adv, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(obs, np.float32(r_obs), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(d_rrm.var, o_rrm.var, rtol=1e-5)
+    assert d_rrm.count == o_rrm.count and np.allclose(d_f.rewems, o_f.rewems, rtol=1e-6)
+    np.testing.assert_allclose(d_obs.mean, o_obs.mean, rtol=1e-12, atol=1e-12)
+    # ---- and the tuple is a valid train_model argument list (device tensors, no host copies)
+    agent, P = make_agent(cfg, E, T)
+    before = agent.state_dict()["model.actor.2.weight"].clone()
+    np.random.seed(0); torch.manual_seed(0)
+    agent.train_model(*got, 0)
+    torch.cuda.synchronize()
+    assert not torch.equal(before, agent.state_dict()["model.actor.2.weight"])
+    s = agent.stats_summary()
+    assert np.isfinite(s["loss"])
