@@ -317,6 +317,13 @@ def main():
     for i in range(2):
         step(i)
     drop_ms = timed_loop(step, max(4, args.steps // 2))
+    if args.profile_out and rank == 0:                 # per-kernel table of the dropout-0.1 step, next to the dropout-0 one
+        ops.profile_start()
+        step(0)
+        dtab = ops.profile_stop()
+        drows = sorted(((l, n, tms) for l, (n, tms, fl) in dtab.items()), key=lambda r: -r[2])
+        json.dump({"per_step": [{"kernel": l, "launches": n, "ms": tms, "tflops": None} for l, n, tms in drows],
+                   "sum_ms": sum(r[2] for r in drows)}, open(args.profile_out.replace(".json", "_dropout.json"), "w"), indent=1)
     c.dropout, c.emb_dropout, c.attn_dropout, c.act_dropout = saved
     with_dropout = {"dropout": 0.1, "value": B * world / (drop_ms * 1e-3), "unit": "samples/s", "ms_per_step": drop_ms}
 

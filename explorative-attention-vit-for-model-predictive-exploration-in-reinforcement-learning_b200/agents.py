@@ -207,15 +207,23 @@ class RNDAgent(nn.Module):
         return self._graphed("rnd", x, self._rnd_device).cpu().numpy()
 
     # ---- update ----------------------------------------------------------------------------------------
+    def _side_stream(self, rt):
+        s = getattr(rt, "_side", None)
+        if s is None:
+            s = rt._side = torch.cuda.Stream(device=rt.device)
+        return s
+
     def _scratch(self, B, A, dev):
         key = (B, A)
         w = self._ws.get(key)
         if w is None:
             f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
             w = dict(te=f(B), ti=f(B), adv=f(B), y=torch.empty(B, dtype=torch.int64, device=dev), old=f(B, A),
-                     dpol=f(B, A), dv=f(2 * B), stats=torch.zeros(16, dtype=torch.float32, device=dev),
+                     dpol=f(B, A), dv=f(2 * B),
                      dpred=torch.empty(B, 512, dtype=torch.bfloat16, device=dev), idx=torch.empty(B, dtype=torch.int64, device=dev),
                      mask=f(B))
+            both = torch.zeros(32, dtype=torch.float32, device=dev)
+            w["stats"], w["rnd_stats"] = both[:16], both[16:]
             self._ws[key] = w
         return w
 
@@ -247,18 +255,34 @@ class RNDAgent(nn.Module):
         st = rt.store
         gs = 1.0
         st.zero_grad()
-        call("eavit_zero", w["stats"], 64)
+        call("eavit_zero", w["stats"], 128)                                 # stats | rnd_stats (adjacent)
         call("eavit_gather_batch", idx, B, A, R["te"], R["ti"], R["adv"], R["y"], R["old"], w["te"], w["ti"], w["adv"], w["y"], w["old"])
         # RND (agents.py:333-338): target is frozen, predictor gets the masked MSE gradient
-        pred = rt.rnd_pred.forward(R["obs"], B, idx)
-        tgt = rt.rnd_tgt.forward(R["obs"], B, idx, col0=rt.rnd_pred.buf[B].t["col0"])
-        call("eavit_rnd_loss", pred, tgt, mask, B, pred.shape[1], gs, w["dpred"], None, w["stats"])
-        rt.rnd_pred.backward(w["dpred"])
+        # The RND towers (~50 small launches, < 1 % of the FLOPs) and the ViT + heads are independent until the optimiser
+        # step: the towers run on a second stream so that their launch-latency-bound kernels fill the tails of the big
+        # ViT kernels instead of sitting serially in front of them.  Their loss term goes to its own stats slot (5) and
+        # their gradients to the predictor's slice of the flat gradient, so the two streams never write the same bytes.
+        cur = torch.cuda.current_stream()
+        side = self._side_stream(rt) if ops._PROF is None and os.environ.get("EAVIT_RND_STREAM", "1") == "1" else None
+        if side is not None:
+            side.wait_stream(cur)
+            torch.cuda.set_stream(side)
+        try:
+            pred = rt.rnd_pred.forward(R["obs"], B, idx)
+            tgt = rt.rnd_tgt.forward(R["obs"], B, idx, col0=rt.rnd_pred.buf[B].t["col0"])
+            call("eavit_rnd_loss", pred, tgt, mask, B, pred.shape[1], gs, w["dpred"], None, w["rnd_stats"])
+            rt.rnd_pred.backward(w["dpred"])
+        finally:
+            if side is not None:
+                torch.cuda.set_stream(cur)
         # PPO (agents.py:455-494)
         pol, ve, vi = rt.ac_forward(R["states"], B, idx)
         call("eavit_ppo_loss", pol, w["old"], w["y"], w["adv"], ve, vi, w["te"], w["ti"], B, A, float(self.ppo_eps),
              float(self.ent_coef), gs, w["dpol"], w["dv"][B:], w["dv"][:B], w["stats"])
         rt.ac_backward(w["dpol"], w["dv"])
+        if side is not None:
+            cur.wait_stream(side)
+        call("eavit_add_f32", w["stats"], w["rnd_stats"], w["stats"], 16)
         if self.world_size > 1:
             dist.allreduce_sum_(st.grad)                                 # ONE NCCL all-reduce; mean applied inside Adam
         if default_config.getboolean("UseGradClipping", fallback=False):

@@ -60,3 +60,36 @@ timed("  rt.sync() only", lambda: rt.sync())
 print(f"per env step (1 get_action + 1 intrinsic reward): {(a + b) * 1e3:.3f} ms -> rollout of {T} steps = {(a + b) * T * 1e3:.1f} ms")
 if hasattr(agent, "rollout_step"):
     timed("rollout_step (CUDA graph, both calls)", lambda: agent.rollout_step(states, obs))
+
+# ---- update-side glue: DeviceRollout.finish() vs the reference's numpy path (oracle restatement of
+# train.py:707-779 / :855) on the same rollout
+if os.environ.get("EAVIT_BENCH_GLUE", "1") == "1":
+    from eavit_b200 import rollout
+    from oracle import oracle as O
+    cfg = O.OracleConfig()
+    roll = O.synth_rollout(E=E, T=T, seed=1)
+    d_obs, d_rrm = utils.RunningMeanStd(shape=(1, 1, 84, 84), usage="obs_rms"), utils.RunningMeanStd(usage="reward_rms")
+    d_f = utils.RewardForwardFilter(cfg.int_gamma)
+    buf = rollout.DeviceRollout(E, T, A)
+    ve, vi = roll["total_ext_values"].reshape(T + 1, E), roll["total_int_values"].reshape(T + 1, E)
+    u8s, u8o = roll["total_state"].astype(np.uint8), roll["total_next_obs"].astype(np.uint8)
+    t0 = time.perf_counter()
+    for t in range(T):
+        sl = slice(t * E, (t + 1) * E)
+        buf.add(t, u8s[sl], u8o[sl], roll["total_reward"][sl], roll["total_done"][sl], roll["total_action"][sl], ve[t], vi[t],
+                roll["total_policy"][sl], roll["total_int_reward"][sl])
+    buf.add_last_values(ve[T], vi[T])
+    torch.cuda.synchronize()
+    t_add = time.perf_counter() - t0
+    for _ in range(2):
+        got = buf.finish(d_obs, d_rrm, d_f, cfg.gamma, cfg.int_gamma, cfg.lam, cfg.ext_coef, cfg.int_coef)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = buf.finish(d_obs, d_rrm, d_f, cfg.gamma, cfg.int_gamma, cfg.lam, cfg.ext_coef, cfg.int_coef)
+    torch.cuda.synchronize()
+    t_fin = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = O.prepare_update(cfg, T, E, roll, O.RunningMeanStd(shape=(1, 1, 84, 84)), O.RunningMeanStd(), O.RewardForwardFilter(cfg.int_gamma))
+    t_ref = time.perf_counter() - t0
+    print(f"update glue at {E} envs x {T} steps: {T} x add() (uint8 frames from host) {t_add * 1e3:.1f} ms total, "
+          f"finish() {t_fin * 1e3:.2f} ms on device; reference numpy path (oracle port, host) {t_ref * 1e3:.0f} ms")
