@@ -348,7 +348,14 @@ def main():
                "next_obs f64, old_policy f32) -- numpy host buffers (pinned), one full update = 128 optimiser steps",
                "seconds": dt, "loss": stats.get("loss")}
 
+    in_sync = None
     if world > 1:
+        # data-parallel invariant: same initial weights + all-reduced gradients -> bit-identical weights on every rank
+        flat = rt.store.flat
+        lo, hi = flat.clone(), flat.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     if rank != 0:
@@ -360,7 +367,7 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": B * world, "envs_per_gpu": E, "num_step": T, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2 (>= 5 GB of activations per step)", "timing": "CUDA events, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
-            "vit_fwd_bwd": vit, "with_shipped_dropout": with_dropout}
+            "vit_fwd_bwd": vit, "with_shipped_dropout": with_dropout, "weights_in_sync_across_ranks": in_sync}
     print(json.dumps(line))
 
 

@@ -207,6 +207,24 @@ class RNDAgent(nn.Module):
         return self._graphed("rnd", x, self._rnd_device).cpu().numpy()
 
     # ---- update ----------------------------------------------------------------------------------------
+    @staticmethod
+    def _rnd_grad_range(st):
+        """[lo, hi) of the RND predictor's tensors in the flat store, or None when they are not one contiguous block."""
+        cached = getattr(st, "_rnd_range", False)
+        if cached is not False:
+            return cached
+        offs = sorted((o, n) for n, o in st.offsets.items())
+        ends = [o for o, _ in offs[1:]] + [st.numel]
+        rnd = [(o, e) for (o, n), e in zip(offs, ends) if n.startswith("rnd.predictor.")]
+        rng = None
+        if rnd:
+            lo, hi = rnd[0][0], rnd[-1][1]
+            inside = [n for (o, n) in offs if lo <= o < hi]
+            if all(n.startswith("rnd.predictor.") for n in inside) and len(inside) == len(rnd):
+                rng = (lo, hi)
+        st._rnd_range = rng
+        return rng
+
     def _side_stream(self, rt):
         s = getattr(rt, "_side", None)
         if s is None:
@@ -262,6 +280,7 @@ class RNDAgent(nn.Module):
         # step: the towers run on a second stream so that their launch-latency-bound kernels fill the tails of the big
         # ViT kernels instead of sitting serially in front of them.  Their loss term goes to its own stats slot (5) and
         # their gradients to the predictor's slice of the flat gradient, so the two streams never write the same bytes.
+        early = None
         cur = torch.cuda.current_stream()
         side = self._side_stream(rt) if ops._PROF is None and os.environ.get("EAVIT_RND_STREAM", "1") == "1" else None
         if side is not None:
@@ -272,6 +291,11 @@ class RNDAgent(nn.Module):
             tgt = rt.rnd_tgt.forward(R["obs"], B, idx, col0=rt.rnd_pred.buf[B].t["col0"])
             call("eavit_rnd_loss", pred, tgt, mask, B, pred.shape[1], gs, w["dpred"], None, w["rnd_stats"])
             rt.rnd_pred.backward(w["dpred"])
+            early = self._rnd_grad_range(st) if (side is not None and self.world_size > 1) else None
+            if early is not None:
+                # the predictor's gradient is complete long before the ViT backward ends: exchange its slice of the flat
+                # buffer now, on the towers' stream, so that only the ViT + heads slices are left for the end of the step
+                dist.allreduce_sum_(st.grad[early[0]:early[1]])
         finally:
             if side is not None:
                 torch.cuda.set_stream(cur)
@@ -283,8 +307,14 @@ class RNDAgent(nn.Module):
         if side is not None:
             cur.wait_stream(side)
         call("eavit_add_f32", w["stats"], w["rnd_stats"], w["stats"], 16)
-        if self.world_size > 1:
-            dist.allreduce_sum_(st.grad)                                 # ONE NCCL all-reduce; mean applied inside Adam
+        if self.world_size > 1:                                          # NCCL all-reduce (sum); the mean is applied inside Adam
+            if early is None:
+                dist.allreduce_sum_(st.grad)
+            else:
+                if early[0] > 0:
+                    dist.allreduce_sum_(st.grad[:early[0]])
+                if early[1] < st.numel:
+                    dist.allreduce_sum_(st.grad[early[1]:])
         if default_config.getboolean("UseGradClipping", fallback=False):
             nrm = torch.zeros(1, dtype=torch.float32, device=rt.device)
             call("eavit_sumsq_f32", st.grad, st.numel, nrm)
