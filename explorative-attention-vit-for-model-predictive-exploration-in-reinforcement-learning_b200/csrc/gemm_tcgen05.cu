@@ -110,6 +110,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM allocation, descriptor prefetch) may run while the
+  // previous kernel of the stream drains; its results are only touched below this wait.  The next kernel is released
+  // for its own prologue right away -- it cannot become resident on an SM before this CTA's shared memory is gone.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -413,7 +418,17 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   p.atomic_f32 = a->atomic_f32;
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  gemm_bf16_tcgen05_kernel<BN, EPI, DROP><<<grid, (CTRL_WARPS + EpiWarps<EPI>::N) * 32, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3((CTRL_WARPS + EpiWarps<EPI>::N) * 32);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP>, tmA, tmB, p));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
