@@ -480,19 +480,21 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const uint32_t hcol = (uint32_t)h * 256u;
       if (rows_live) {
         tc::tmem_stream16x2<8>(lane_base, COL_DP, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
-          if (SEG && (c0 + 8 <= lo || c0 >= hi)) {             // another sequence's keys: P~ = 0 (and dS stays 0 in pass 2)
-            *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(0, 0, 0, 0);
-            return;
-          }
-          uint32_t pk[4];
+          uint32_t pk[4] = {0u, 0u, 0u, 0u};
+          uint32_t pu[4] = {0u, 0u, 0u, 0u};               // DROP: the unmasked P~ of this chunk (see below)
           float d0 = 0.f, d1 = 0.f;
           const uint32_t dcol = hcol + (uint32_t)(c0 - lo);
-          if (SEG ? (c0 >= lo && c0 + 8 <= hi) : (c0 + 8 <= S)) {
+          // (lanes of a warp sit in different sequences when SEG: every path below falls through to the common tail, the
+          // TMEM store there is warp-collective)
+          if (SEG && (c0 + 8 <= lo || c0 >= hi)) {
+            // another sequence's keys: P~ = 0 (and dS stays 0 in pass 2)
+          } else if (SEG ? (c0 >= lo && c0 + 8 <= hi) : (c0 + 8 <= S)) {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
               float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2));
               float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2));
               if constexpr (DROP) {
+                pu[j >> 1] = pack_bf16x2(p0, p1);
                 const uint32_t bits = drop_bits(rk, (dcol + (uint32_t)j) >> 1);
                 p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
               }
@@ -506,6 +508,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
               float p0 = (c0 + j >= lo && c0 + j < hi) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
               float p1 = (c0 + j + 1 >= lo && c0 + j + 1 < hi) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
               if constexpr (DROP) {
+                pu[j >> 1] = pack_bf16x2(p0, p1);
                 const uint32_t bits = drop_bits(rk, (dcol + (uint32_t)j) >> 1);
                 p0 *= drop_even(drop, bits); p1 *= drop_odd(drop, bits);
               }
@@ -516,7 +519,17 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
           dpart += d0 + d1;
           *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          // DROP: pass 2 needs the UNMASKED probabilities (dS = P (M dP - D) also for the dropped entries).  They go back
+          // into TMEM as packed bf16 pairs, over the first half of this thread's own score columns: chunk i (score columns
+          // cbeg + 8 i ..) lands at cbeg + 4 i .., always behind the columns this thread still has to read, and no other
+          // thread touches this row's [cbeg, cend).  Pass 2 then costs one half-width TMEM read instead of re-reading S,
+          // re-evaluating exp2 and re-hashing the mask.
+          if constexpr (DROP) {
+            __syncwarp();
+            tc::tmem_st_32x4(lane_base + (uint32_t)(cbeg + ((c0 - cbeg) >> 1)), pu);
+          }
         });
+        if constexpr (DROP) tc::tmem_st_wait();
       } else {
         // no valid query row in this warp: its P~ / dS rows are zero (they feed the dK / dV sums over queries)
         for (int c0 = cbeg; c0 < cend; c0 += 8)
@@ -547,18 +560,20 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       tc::fence_after_sync();
       // ---- pass 2: dS = P~ (dP - D) -> smem
       if (rows_live && DROP) {
-        tc::tmem_stream16x2<8>(lane_base, COL_DP, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
-          if (SEG && (c0 + 8 <= lo || c0 >= hi)) return;
+        // unmasked P~ from TMEM (stashed by pass 1), the keep decision from the masked P~ still in shared memory
+        // (zero = dropped, or a probability that rounded to zero -- dS is zero either way)
+        tc::tmem_stream8_half(lane_base + COL_DP, lane_base + (uint32_t)cbeg, cbeg, cend, [&](const uint32_t* rp, const uint32_t* pp, int c0) {
+          uint8_t* addr = pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3);
+          const uint4 pm = *reinterpret_cast<uint4*>(addr);
+          const uint32_t pmw[4] = {pm.x, pm.y, pm.z, pm.w};
           uint32_t ds[4];
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const float p0 = (c0 + j >= lo && c0 + j < hi) ? ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -l2)) : 0.f;
-            const float p1 = (c0 + j + 1 >= lo && c0 + j + 1 < hi) ? ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -l2)) : 0.f;
-            const uint32_t bits = drop_bits(rk, (hcol + (uint32_t)(c0 + j - lo)) >> 1);
-            ds[j >> 1] = pack_bf16x2(p0 * fmaf(drop_even(drop, bits), __uint_as_float(rp[j]), -Di),
-                                     p1 * fmaf(drop_odd(drop, bits), __uint_as_float(rp[j + 1]), -Di));
+          for (int j = 0; j < 4; ++j) {
+            const float px = __uint_as_float(pp[j] << 16), py = __uint_as_float(pp[j] & 0xffff0000u);
+            const float mx = (pmw[j] & 0xffffu) ? drop.scale : 0.f, my = (pmw[j] >> 16) ? drop.scale : 0.f;
+            ds[j] = pack_bf16x2(px * fmaf(mx, __uint_as_float(rp[2 * j]), -Di), py * fmaf(my, __uint_as_float(rp[2 * j + 1]), -Di));
           }
-          *reinterpret_cast<uint4*>(pbuf + (c0 >> 6) * P_SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+          *reinterpret_cast<uint4*>(addr) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
         });
       } else if (rows_live) {
         tc::tmem_stream16<8>(lane_base + COL_DP, cbeg, cend, [&](const uint32_t* rp, int c0) {

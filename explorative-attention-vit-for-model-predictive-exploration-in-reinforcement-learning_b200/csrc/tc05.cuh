@@ -122,6 +122,18 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// 32 lanes x 4 columns
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+// registers -> TMEM: thread i of the warp writes row (lane base + i), columns [col, col+4)
+__device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait::ld that also carries a data dependency on the destination registers of an earlier tcgen05.ld, so that neither
 // nvcc nor ptxas can schedule their first use above the wait (used by the software-pipelined TMEM readers).
@@ -137,6 +149,9 @@ __device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t* r) {
                  "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep4(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : : "memory");
 }
 template <int W> __device__ __forceinline__ void tmem_ld_w(uint32_t taddr, uint32_t* r) {
   if constexpr (W == 8) tmem_ld_32x8(taddr, r); else tmem_ld_32x16(taddr, r);
@@ -184,6 +199,31 @@ __device__ __forceinline__ void tmem_stream16x2(uint32_t addr, uint32_t off2, in
     if (has_a) { tmem_ld_w<W>(addr + c0 + 2 * W, ra); tmem_ld_w<W>(addr + off2 + c0 + 2 * W, pa); }
     f(rb, pb, c0 + W);
     if (has_a) { tmem_ld_wait_dep<W>(ra); tmem_ld_wait_dep<W>(pa); }
+  }
+}
+
+// Columns [cbeg, cend) (multiples of 8) of accumulator `addr_a`, 8 at a time, together with the 4-column chunks of a
+// HALF-WIDTH companion that starts at `addr_h` (bf16 pairs packed by the same thread: chunk i lives at addr_h + 4 i)
+// -> f(regs_a[8], regs_h[4], c0); the loads of chunk i+1 are in flight while chunk i is consumed.
+template <typename F>
+__device__ __forceinline__ void tmem_stream8_half(uint32_t addr_a, uint32_t addr_h, int cbeg, int cend, F&& f) {
+  uint32_t ra[8], rb[8], ha[4], hb[4];
+  if (cbeg >= cend) return;
+  tmem_ld_32x8(addr_a + cbeg, ra);
+  tmem_ld_32x4(addr_h, ha);
+  tmem_ld_wait_dep8(ra);
+  tmem_ld_wait_dep4(ha);
+  for (int c0 = cbeg; c0 < cend; c0 += 16) {
+    const bool has_b = c0 + 8 < cend;
+    if (has_b) { tmem_ld_32x8(addr_a + c0 + 8, rb); tmem_ld_32x4(addr_h + ((c0 + 8 - cbeg) >> 1), hb); }
+    f(ra, ha, c0);
+    if (!has_b) break;
+    tmem_ld_wait_dep8(rb);
+    tmem_ld_wait_dep4(hb);
+    const bool has_a = c0 + 16 < cend;
+    if (has_a) { tmem_ld_32x8(addr_a + c0 + 16, ra); tmem_ld_32x4(addr_h + ((c0 + 16 - cbeg) >> 1), ha); }
+    f(rb, hb, c0 + 8);
+    if (has_a) { tmem_ld_wait_dep8(ra); tmem_ld_wait_dep4(ha); }
   }
 }
 
