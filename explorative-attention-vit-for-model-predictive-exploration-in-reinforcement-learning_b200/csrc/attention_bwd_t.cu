@@ -1,0 +1,340 @@
+// Attention backward with TRANSPOSED scores (keys on the TMEM lanes), Dh = 32, sequences up to 208 tokens, no dropout.
+//
+// attention_tc.cu's backward keeps queries on the lanes: P~ and dS must both pass through ONE shared-memory buffer (they
+// are MN-major A operands of dV = P~^T dO and dK = dS^T Q), which forces  S,dP MMA -> pass 1 (P~, D) -> dV MMA -> pass 2
+// (dS) -> dK,dQ MMA  with three MMA round trips and two softmax passes per (head, query tile).  With the scores transposed,
+//     S^T = K Q^T,   dP^T = V dO^T              (M = 128 keys of a key tile, N = all queries of the sequence)
+// P~^T and dS^T have the keys on the lanes -- exactly the layout of a TMEM-resident A operand -- so
+//     dV_kt = P~^T dO   and   dK_kt = dS^T Q    read A from TENSOR MEMORY (tcgen05.mma with [tmem] A),
+// written there by tcgen05.st as packed bf16 pairs over the first half of each thread's own score columns; only dS^T also
+// goes to shared memory (dQ = dS K needs queries on M: the same buffer read as an MN-major A operand).  The row statistic
+// D_i = sum_j P_ij dP_ij = sum_d O_id dO_id comes from a tiny pre-kernel, so ONE pass produces P~^T and dS^T together:
+//     per (head, key tile):   S^T, dP^T MMA -> one pass -> dV, dK, dQ MMAs -> drain        (two MMA round trips, one pass)
+// dV / dK are complete per key tile (their K dimension is the whole sequence) and are stored straight from TMEM; dQ is
+// summed over the two key tiles in registers.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace eavit {
+
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer);
+
+namespace bt {
+
+constexpr int THREADS = 512;
+constexpr int MAXQ = 208;                   // queries (score columns) per sequence: S^T and dP^T take 2 x 208 TMEM columns
+constexpr int ROWB = 128;                   // bytes per staged row: 64 bf16 = two heads of 32
+constexpr int SLAB = 128 * ROWB;            // [128 rows][64 columns] bf16, 128-byte swizzle
+constexpr int BOX_ROWS = 32;
+constexpr int BOX_BYTES = BOX_ROWS * ROWB;
+constexpr int DH = 32;
+constexpr int COL_S = 0, COL_DP = 208, COL_DV = 416, COL_DK = 448, COL_DQ0 = 480;     // dQ tile 1: last 32 columns of S
+
+__device__ __forceinline__ uint32_t sw_off(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+struct Smem {
+  static constexpr int OFF_Q = 0;                               // [256][128 B]
+  static constexpr int OFF_DO = OFF_Q + 256 * ROWB;             // [256][128 B]
+  static constexpr int OFF_K = OFF_DO + 256 * ROWB;             // [224][128 B] (tile 1 of an MMA reads on into V / dS: finite)
+  static constexpr int OFF_V = OFF_K + 224 * ROWB;
+  static constexpr int OFF_DS = OFF_V + 224 * ROWB;             // dS^T: 4 slabs [128 keys][64 queries]
+  static constexpr int OFF_L = OFF_DS + 4 * SLAB;               // float [2 heads][256]  lse * log2(e)   (+inf past the end)
+  static constexpr int OFF_D = OFF_L + 2 * 256 * 4;             // float [2 heads][256]  D
+  static constexpr int OFF_BAR = OFF_D + 2 * 256 * 4;
+  static constexpr int TOTAL = OFF_BAR + 64 + 1024;
+};
+
+// k-steps (16 queries) of warp group g: with two query tiles the LAST group takes >= 4 so that the second half of its
+// columns (free once its scores are consumed) holds the 32-column dQ accumulator of query tile 1.
+__device__ __forceinline__ void ksplit(int nks, bool two_q, int* kb /*[5]*/) {
+  if (two_q) {
+    const int k3 = max(4, (nks + 3) >> 2), rest = nks - k3;
+    kb[0] = 0; kb[1] = (rest + 2) / 3; kb[2] = kb[1] + (rest + 1) / 3; kb[3] = rest; kb[4] = nks;
+  } else {
+    for (int g = 0; g <= 4; ++g) kb[g] = (g * nks) >> 2;
+  }
+}
+
+// D[t, h] = sum_d out[t, h, d] * dout[t, h, d]   (one warp per token row, 8 columns per lane, Dh / 8 lanes per head)
+__global__ void __launch_bounds__(256) dvec_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                                   long long T, int H, float* __restrict__ dvec) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const int HD = H * DH;
+  for (int c0 = lane * 8; c0 < HD; c0 += 256) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(out + row * HD + c0));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(dout + row * HD + c0));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s = fmaf(__uint_as_float(aw[i] << 16), __uint_as_float(bw[i] << 16), s);
+      s = fmaf(__uint_as_float(aw[i] & 0xffff0000u), __uint_as_float(bw[i] & 0xffff0000u), s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if ((lane & 3) == 0) dvec[row * H + (c0 >> 5)] = s;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                       const float* __restrict__ lse, const float* __restrict__ dvec, const int* __restrict__ seq_start, int nseq,
+                       int H, float scale, __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* sL = reinterpret_cast<float*>(smem + Smem::OFF_L);
+  float* sD = reinterpret_cast<float*>(smem + Smem::OFF_D);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);      // [0] S^T,dP^T  [1] dV,dK,dQ  [2] loads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, grp = warp >> 2;
+  const int row_in_tile = quad * 32 + lane;
+
+  for (int i = tid; i < Smem::OFF_L / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    tc::prefetch_tmap(&tmQKV);
+    tc::prefetch_tmap(&tmDO);
+    for (int i = 0; i < 3; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+
+  const int ldq = 3 * H * DH;
+  const int HG = H / 2;
+  const float c2 = scale * 1.4426950408889634f;
+  uint32_t phase = 0, ph_ld = 0;
+  const int n_items = nseq * HG;
+  const uint32_t sQ = tc::smem_u32(smem + Smem::OFF_Q), sDO = tc::smem_u32(smem + Smem::OFF_DO);
+  const uint32_t sK = tc::smem_u32(smem + Smem::OFF_K), sV = tc::smem_u32(smem + Smem::OFF_V);
+  const uint32_t sDS = tc::smem_u32(smem + Smem::OFF_DS);
+  uint8_t* dsbuf = smem + Smem::OFF_DS;
+
+  auto issue_loads = [&](int it) {                 // one thread
+    const int sq = it / HG, hg = it - sq * HG;
+    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
+    tc::mbar_expect_tx(&bars[2], 4 * nb * BOX_BYTES);
+    const int offs[3] = {Smem::OFF_Q, Smem::OFF_K, Smem::OFF_V};
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      for (int b = 0; b < nb; ++b)
+        tc::tma_load_2d(smem + offs[m] + b * BOX_BYTES, &tmQKV, &bars[2], m * H * DH + hg * 64, tt + b * BOX_ROWS);
+    for (int b = 0; b < nb; ++b)
+      tc::tma_load_2d(smem + Smem::OFF_DO + b * BOX_BYTES, &tmDO, &bars[2], hg * 64, tt + b * BOX_ROWS);
+  };
+  if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int seq = item / HG, hg = item - seq * HG;
+    const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
+    const int NQP = (S + 15) & ~15, nks = NQP >> 4;          // score columns (queries), k-steps of the dV / dK MMAs
+    const int NT = (S + 127) >> 7;                           // key tiles == query tiles
+    int kb[5];
+    ksplit(nks, NT == 2, kb);
+    const int cbeg = kb[grp] * 16, cend = kb[grp + 1] * 16;  // this thread's query columns
+    const uint32_t col_dq1 = (uint32_t)(NQP - 32);           // dQ accumulator of query tile 1 (inside the last group's columns)
+    // row statistics of both heads of the pair: lse * log2(e) (+inf past the end: P = 0) and D
+    for (int i = tid; i < 2 * 256; i += THREADS) {
+      const int hd = i >> 8, q = i & 255;
+      const bool ok = q < S;
+      sL[i] = ok ? lse[(size_t)(t0 + q) * H + hg * 2 + hd] * 1.4426950408889634f : INFINITY;
+      sD[i] = ok ? dvec[(size_t)(t0 + q) * H + hg * 2 + hd] : 0.f;
+    }
+    tc::mbar_wait(&bars[2], ph_ld);
+    ph_ld ^= 1;
+    __syncthreads();                                         // sL / sD visible
+
+#pragma unroll 1
+    for (int hd = 0; hd < 2; ++hd) {
+      const int h = hg * 2 + hd;
+      const uint32_t hoff = (uint32_t)(hd * DH * 2);         // byte offset of this head inside the 128-byte rows
+      const float* hL = sL + hd * 256;
+      const float* hD = sD + hd * 256;
+      float accQ[2][8];                                      // dQ rows (tile, row_in_tile), columns [grp*8, +8), summed over key tiles
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { accQ[0][i] = 0.f; accQ[1][i] = 0.f; }
+
+#pragma unroll 1
+      for (int kt = 0; kt < NT; ++kt) {
+        // ---- (1) S^T = K_kt Q^T, dP^T = V_kt dO^T     (M = 128 keys, N = NQP queries, K = Dh)
+        if (warp == 0 && tc::elect_one()) {
+          tc::fence_after_sync();
+          const uint32_t idesc = tc::make_idesc_bf16(128, NQP, 0, 0);
+          const uint64_t ak = tc::make_sdesc_sw128(sK + kt * 128 * ROWB + hoff, 16, 1024), bq = tc::make_sdesc_sw128(sQ + hoff, 16, 1024);
+          const uint64_t av = tc::make_sdesc_sw128(sV + kt * 128 * ROWB + hoff, 16, 1024), bo = tc::make_sdesc_sw128(sDO + hoff, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base + COL_S, ak + (uint64_t)(k * 2), bq + (uint64_t)(k * 2), idesc, k > 0);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base + COL_DP, av + (uint64_t)(k * 2), bo + (uint64_t)(k * 2), idesc, k > 0);
+          tc::mma_commit(&bars[0]);
+        }
+        const int krow = kt * 128 + row_in_tile;             // this thread's key
+        const bool kok = krow < S;
+        const int nkeys = min(128, S - kt * 128);            // valid keys of the tile
+        const int kq = (nkeys + 15) >> 4;                    // 16-key K steps of the dQ MMA
+        const bool rows_live = kt * 128 + quad * 32 < S;     // warp-uniform: any valid key in this warp
+        tc::mbar_wait(&bars[0], phase);
+        tc::fence_after_sync();
+        // ---- the pass: P~^T -> TMEM (over S^T), dS^T -> TMEM (over dP^T) and shared memory
+        if (rows_live) {
+          tc::tmem_stream16x2<8>(lane_base + COL_S, COL_DP - COL_S, cbeg, cend, [&](const uint32_t* rs, const uint32_t* rp, int c0) {
+            const float4 l0 = *reinterpret_cast<const float4*>(hL + c0), l1 = *reinterpret_cast<const float4*>(hL + c0 + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(hD + c0), d1 = *reinterpret_cast<const float4*>(hD + c0 + 4);
+            const float lq[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const float dq[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            uint32_t pu[4], du[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -lq[j]));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -lq[j + 1]));
+              pu[j >> 1] = pack_bf16x2(p0, p1);
+              du[j >> 1] = pack_bf16x2(p0 * (__uint_as_float(rp[j]) - dq[j]), p1 * (__uint_as_float(rp[j + 1]) - dq[j + 1]));
+            }
+            if (!kok) {                                      // a key past the end of the sequence: exact zeros (dQ sums over keys)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { pu[j] = 0u; du[j] = 0u; }
+            }
+            *reinterpret_cast<uint4*>(dsbuf + (c0 >> 6) * SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(du[0], du[1], du[2], du[3]);
+            // packed pairs go back over the first half of this thread's own columns: chunk i (columns cbeg + 8 i ..) lands
+            // at cbeg + 4 i .., always behind the columns this thread still has to read
+            __syncwarp();
+            const uint32_t half = (uint32_t)(cbeg + ((c0 - cbeg) >> 1));
+            tc::tmem_st_32x4(lane_base + COL_S + half, pu);
+            tc::tmem_st_32x4(lane_base + COL_DP + half, du);
+          });
+          tc::tmem_st_wait();
+        }
+        tc::fence_before_sync();
+        tc::fence_proxy_async();
+        __syncthreads();
+        // ---- (2) dV_kt = P~^T dO, dK_kt = dS^T Q  (A from TMEM, K = queries);  dQ_t += dS_t K_kt  (A = dS^T buffer, MN-major)
+        if (warp == 0 && tc::elect_one()) {
+          tc::fence_after_sync();
+          const uint32_t idesc_t = tc::make_idesc_bf16(128, DH, 0, 1);      // A K-major (TMEM), B MN-major
+          bool first = true;
+          for (int g = 0; g < 4; ++g) {
+            for (int ks = kb[g]; ks < kb[g + 1]; ++ks) {
+              const uint32_t a_col = (uint32_t)(kb[g] * 16 + (ks - kb[g]) * 8);
+              const uint64_t bdo = tc::make_sdesc_sw128(sDO + ks * 2048 + hoff, 8192, 1024);
+              tc::mma_bf16_ts(tmem_base + COL_DV, tmem_base + COL_S + a_col, bdo, idesc_t, first ? 0u : 1u);
+              first = false;
+            }
+          }
+          first = true;
+          for (int g = 0; g < 4; ++g) {
+            for (int ks = kb[g]; ks < kb[g + 1]; ++ks) {
+              const uint32_t a_col = (uint32_t)(kb[g] * 16 + (ks - kb[g]) * 8);
+              const uint64_t bq = tc::make_sdesc_sw128(sQ + ks * 2048 + hoff, 8192, 1024);
+              tc::mma_bf16_ts(tmem_base + COL_DK, tmem_base + COL_DP + a_col, bq, idesc_t, first ? 0u : 1u);
+              first = false;
+            }
+          }
+          const uint32_t idesc_q = tc::make_idesc_bf16(128, DH, 1, 1);      // A MN-major (queries), B MN-major
+          for (int t = 0; t < NT; ++t) {
+            const uint32_t dcol = t == 0 ? (uint32_t)COL_DQ0 : col_dq1;
+            for (int kk = 0; kk < kq; ++kk) {
+              const uint64_t a = tc::make_sdesc_sw128(sDS + 2 * t * SLAB + kk * 2048, SLAB, 1024);
+              const uint64_t b = tc::make_sdesc_sw128(sK + (kt * 128 + kk * 16) * ROWB + hoff, 8192, 1024);
+              tc::mma_bf16_ss(tmem_base + dcol, a, b, idesc_q, kk > 0);
+            }
+          }
+          tc::mma_commit(&bars[1]);
+        }
+        tc::mbar_wait(&bars[1], phase);
+        if (tid == 0 && hd == 1 && kt == NT - 1 && item + (int)gridDim.x < n_items)
+          issue_loads(item + gridDim.x);            // every MMA on this item's operands is done: refill during the drain
+        tc::fence_after_sync();
+        // ---- drain: dV / dK rows of this key tile straight to global, dQ partials into registers
+        {
+          uint32_t rv[8], rk[8], q0[8], q1[8];
+          tc::tmem_ld_32x8(lane_base + COL_DV + grp * 8, rv);
+          tc::tmem_ld_32x8(lane_base + COL_DK + grp * 8, rk);
+          tc::tmem_ld_32x8(lane_base + COL_DQ0 + grp * 8, q0);
+          if (NT == 2) tc::tmem_ld_32x8(lane_base + col_dq1 + grp * 8, q1);
+          tc::tmem_ld_wait();
+          if (kok) {
+            __nv_bfloat16* dk = dqkv + (size_t)(t0 + krow) * ldq + H * DH + h * DH + grp * 8;
+            __nv_bfloat16* dv = dk + H * DH;
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(rk[0]) * scale, __uint_as_float(rk[1]) * scale);
+            o.y = pack_bf16x2(__uint_as_float(rk[2]) * scale, __uint_as_float(rk[3]) * scale);
+            o.z = pack_bf16x2(__uint_as_float(rk[4]) * scale, __uint_as_float(rk[5]) * scale);
+            o.w = pack_bf16x2(__uint_as_float(rk[6]) * scale, __uint_as_float(rk[7]) * scale);
+            *reinterpret_cast<uint4*>(dk) = o;
+            o.x = pack_bf16x2(__uint_as_float(rv[0]), __uint_as_float(rv[1])); o.y = pack_bf16x2(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
+            o.z = pack_bf16x2(__uint_as_float(rv[4]), __uint_as_float(rv[5])); o.w = pack_bf16x2(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
+            *reinterpret_cast<uint4*>(dv) = o;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            accQ[0][i] += __uint_as_float(q0[i]);
+            if (NT == 2) accQ[1][i] += __uint_as_float(q1[i]);
+          }
+        }
+        tc::fence_before_sync();
+        phase ^= 1;
+        __syncthreads();                              // TMEM and the dS buffer are free for the next key tile / head / item
+      }
+      // ---- dQ rows of this head
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int qrow = t * 128 + row_in_tile;
+        if (t < NT && qrow < S) {
+          uint4 o;
+          o.x = pack_bf16x2(accQ[t][0] * scale, accQ[t][1] * scale); o.y = pack_bf16x2(accQ[t][2] * scale, accQ[t][3] * scale);
+          o.z = pack_bf16x2(accQ[t][4] * scale, accQ[t][5] * scale); o.w = pack_bf16x2(accQ[t][6] * scale, accQ[t][7] * scale);
+          *reinterpret_cast<uint4*>(dqkv + (size_t)(t0 + qrow) * ldq + h * DH + grp * 8) = o;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace bt
+}  // namespace eavit
+
+using namespace eavit;
+
+extern "C" int eavit_attention_bwd_tct(const void* qkv, const void* out, const void* dout, const float* lse, float* dvec_ws,
+                                       const int* seq_start, int nseq, int max_len, long long total_tokens, int H, int Dh,
+                                       float scale, void* dqkv, void* stream) {
+  EAVIT_CHECK_ARG(qkv && out && dout && lse && dvec_ws && seq_start && dqkv && nseq > 0 && H > 0 && total_tokens > 0);
+  EAVIT_CHECK_ARG(Dh == 32 && H % 2 == 0 && max_len > 0 && max_len <= bt::MAXQ);
+  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tq, tdo;
+  int rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)3 * H * Dh, (uint64_t)total_tokens, (uint64_t)3 * H * Dh * 2, bt::BOX_ROWS);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tdo, dout, (uint64_t)H * Dh, (uint64_t)total_tokens, (uint64_t)H * Dh * 2, bt::BOX_ROWS);
+  if (rc) return rc;
+  bt::dvec_kernel<<<cdiv(total_tokens, 8), 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, total_tokens, H, dvec_ws);
+  EAVIT_LAUNCH_OK();
+  static bool done = false;
+  if (!done) {
+    EAVIT_CUDA(cudaFuncSetAttribute(bt::attention_bwd_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt::Smem::TOTAL));
+    done = true;
+  }
+  const int items = nseq * (H / 2);
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  bt::attention_bwd_t_kernel<<<grid, bt::THREADS, bt::Smem::TOTAL, st>>>(tq, tdo, lse, dvec_ws, seq_start, nseq, H, scale,
+                                                                         (__nv_bfloat16*)dqkv);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}

@@ -30,7 +30,11 @@ def rel(a, b):
 
 
 CASES = [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([197] * 5, 8, 32), ([1, 17, 128, 129, 224], 4, 32),
-         ([64, 200], 3, 64), ([197, 33, 196, 5] * 40, 8, 32)]        # the last one: > 148 items, every CTA loops
+         ([64, 200], 3, 64), ([197, 33, 196, 5] * 40, 8, 32),        # > 148 items, every CTA loops
+         ([50] * 9, 4, 64),                    # equal even lengths: packed 4 (fwd) / 2 (bwd) per work item, ragged last pack
+         ([64] * 7, 4, 32),                    # packed 3 per item, two query tiles
+         ([16] * 30, 2, 32),                   # packed 14 per item
+         ([129, 144, 150, 176, 192, 208], 2, 32)]   # two key tiles with every k-step count 9..13 (transposed-score backward)
 
 
 @pytest.mark.parametrize("lens,H,Dh", CASES)
@@ -58,12 +62,15 @@ def test_attention_forward(ops, lens, H, Dh, impl):
 
 
 BWD_CASES = [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([1, 17, 128, 129, 224], 4, 32), ([64, 100], 3, 64),
-             ([197, 33, 196, 5] * 40, 8, 32)]
+             ([197, 33, 196, 5] * 40, 8, 32), ([50] * 9, 4, 64), ([64] * 7, 4, 32), ([16] * 30, 2, 32),
+             ([129, 144, 150, 176, 192, 208], 2, 32), ([1, 17, 128, 129, 208, 2, 31, 160], 4, 32)]
 
 
 @pytest.mark.parametrize("lens,H,Dh", BWD_CASES)
-@pytest.mark.parametrize("impl", ["v1", "tc"])
+@pytest.mark.parametrize("impl", ["v1", "tc", "tct"])
 def test_attention_backward(ops, lens, H, Dh, impl):
+    if impl == "tct" and (Dh != 32 or max(lens) > 208 or H % 2):
+        pytest.skip("transposed-score backward: Dh = 32, up to 208 tokens")
     torch.manual_seed(sum(lens) + H + 1)
     starts = [0]
     for n in lens:
@@ -79,7 +86,11 @@ def test_attention_backward(ops, lens, H, Dh, impl):
     out = torch.empty(T, H * Dh, device="cuda", dtype=torch.bfloat16)
     lse = torch.empty(T, H, device="cuda")
     dqkv = torch.full((T, 3 * H * Dh), float("nan"), device="cuda", dtype=torch.bfloat16)
-    if impl == "tc":
+    if impl == "tct":
+        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse, 0.0, 0)
+        ws = torch.empty(T, H, device="cuda")
+        ops.call("eavit_attention_bwd_tct", qkv, out, dout, lse, ws, ss, len(lens), max(lens), T, H, Dh, scale, dqkv)
+    elif impl == "tc":
         ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse, 0.0, 0)
         ops.call("eavit_attention_bwd_tc", qkv, dout, lse, ss, len(lens), max(lens), T, H, Dh, scale, dqkv, 0.0, 0)
     else:
