@@ -21,6 +21,14 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 
 namespace bt {
 
+// Optional phase timing (-DEAVIT_TRACE, tools/att_trace.py bwdt): clock64 deltas of block 0 / thread 0 per phase.
+#ifdef EAVIT_TRACE
+__device__ long long g_bt_trace[32];
+#define BTR(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); tr_acc[i] += _t - tr_prev; tr_prev = _t; } } while (0)
+#else
+#define BTR(i) do { } while (0)
+#endif
+
 constexpr int THREADS = 512;
 constexpr int MAXQ = 208;                   // queries (score columns) per sequence: S^T and dP^T take 2 x 208 TMEM columns
 constexpr int ROWB = 128;                   // bytes per staged row: 64 bf16 = two heads of 32
@@ -40,9 +48,9 @@ struct Smem {
   static constexpr int OFF_K = OFF_DO + 256 * ROWB;             // [224][128 B] (tile 1 of an MMA reads on into V / dS: finite)
   static constexpr int OFF_V = OFF_K + 224 * ROWB;
   static constexpr int OFF_DS = OFF_V + 224 * ROWB;             // dS^T: 4 slabs [128 keys][64 queries]
-  static constexpr int OFF_L = OFF_DS + 4 * SLAB;               // float [2 heads][256]  lse * log2(e)   (+inf past the end)
-  static constexpr int OFF_D = OFF_L + 2 * 256 * 4;             // float [2 heads][256]  D
-  static constexpr int OFF_BAR = OFF_D + 2 * 256 * 4;
+  static constexpr int OFF_L = OFF_DS + 4 * SLAB;               // float [2 buffers][2 heads][256]  lse * log2(e)   (+inf past the end)
+  static constexpr int OFF_D = OFF_L + 2 * 2 * 256 * 4;         // float [2 buffers][2 heads][256]  D
+  static constexpr int OFF_BAR = OFF_D + 2 * 2 * 256 * 4;
   static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
@@ -98,7 +106,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   if (tid == 0) {
     tc::prefetch_tmap(&tmQKV);
     tc::prefetch_tmap(&tmDO);
-    for (int i = 0; i < 3; ++i) tc::mbar_init(&bars[i], 1);
+    tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 2); tc::mbar_init(&bars[2], 1);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -133,7 +141,18 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       tc::tma_load_2d(smem + Smem::OFF_DO + b * BOX_BYTES, &tmDO, &bars[2], hg * 64, tt + b * BOX_ROWS);
   };
   if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
+  if ((int)blockIdx.x < n_items) {                 // row statistics of the first item -> buffer 0
+    const int sq = blockIdx.x / HG, hg0 = blockIdx.x - sq * HG;
+    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const int hd = tid >> 8, q = tid & 255;
+    const bool ok = q < SS;
+    sL[tid] = ok ? lse[(size_t)(tt + q) * H + hg0 * 2 + hd] * 1.4426950408889634f : INFINITY;
+    sD[tid] = ok ? dvec[(size_t)(tt + q) * H + hg0 * 2 + hd] : 0.f;
+  }
 
+#ifdef EAVIT_TRACE
+  long long tr_acc[16] = {0}, tr_prev = clock64();
+#endif
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int seq = item / HG, hg = item - seq * HG;
     const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
@@ -143,23 +162,32 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     ksplit(nks, NT == 2, kb);
     const int cbeg = kb[grp] * 16, cend = kb[grp + 1] * 16;  // this thread's query columns
     const uint32_t col_dq1 = (uint32_t)(NQP - 32);           // dQ accumulator of query tile 1 (inside the last group's columns)
-    // row statistics of both heads of the pair: lse * log2(e) (+inf past the end: P = 0) and D
-    for (int i = tid; i < 2 * 256; i += THREADS) {
-      const int hd = i >> 8, q = i & 255;
-      const bool ok = q < S;
-      sL[i] = ok ? lse[(size_t)(t0 + q) * H + hg * 2 + hd] * 1.4426950408889634f : INFINITY;
-      sD[i] = ok ? dvec[(size_t)(t0 + q) * H + hg * 2 + hd] : 0.f;
-    }
+    // Row statistics of both heads of the pair -- lse * log2(e) (+inf past the end: P = 0) and D -- one entry per thread,
+    // double-buffered: the NEXT item's entry is fetched into registers now and parked in the other buffer after the first
+    // key tile, so its global-load latency never sits in front of a round.
+    const int sbuf = (int)(ph_ld & 1);
     tc::mbar_wait(&bars[2], ph_ld);
     ph_ld ^= 1;
-    __syncthreads();                                         // sL / sD visible
+    __syncthreads();                                         // this item's sL / sD (written during the previous item) visible
+    const int nitem = item + (int)gridDim.x;
+    float nl = INFINITY, nd = 0.f;
+    if (nitem < n_items) {
+      const int nsq = nitem / HG, nhg = nitem - nsq * HG;
+      const int nt0 = seq_start[nsq], nS = seq_start[nsq + 1] - nt0;
+      const int hd = tid >> 8, q = tid & 255;
+      if (q < nS) {                                          // raw values: nothing below depends on them until they are parked
+        nl = __ldg(lse + (size_t)(nt0 + q) * H + nhg * 2 + hd);
+        nd = __ldg(dvec + (size_t)(nt0 + q) * H + nhg * 2 + hd);
+      }
+    }
+    BTR(0);
 
 #pragma unroll 1
     for (int hd = 0; hd < 2; ++hd) {
       const int h = hg * 2 + hd;
       const uint32_t hoff = (uint32_t)(hd * DH * 2);         // byte offset of this head inside the 128-byte rows
-      const float* hL = sL + hd * 256;
-      const float* hD = sD + hd * 256;
+      const float* hL = sL + sbuf * 512 + hd * 256;
+      const float* hD = sD + sbuf * 512 + hd * 256;
       float accQ[2][8];                                      // dQ rows (tile, row_in_tile), columns [grp*8, +8), summed over key tiles
 #pragma unroll
       for (int i = 0; i < 8; ++i) { accQ[0][i] = 0.f; accQ[1][i] = 0.f; }
@@ -178,12 +206,14 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           for (int k = 0; k < DH / 16; ++k) tc::mma_bf16_ss(tmem_base + COL_DP, av + (uint64_t)(k * 2), bo + (uint64_t)(k * 2), idesc, k > 0);
           tc::mma_commit(&bars[0]);
         }
+        BTR(1);
         const int krow = kt * 128 + row_in_tile;             // this thread's key
         const bool kok = krow < S;
         const int nkeys = min(128, S - kt * 128);            // valid keys of the tile
         const int kq = (nkeys + 15) >> 4;                    // 16-key K steps of the dQ MMA
         const bool rows_live = kt * 128 + quad * 32 < S;     // warp-uniform: any valid key in this warp
         tc::mbar_wait(&bars[0], phase);
+        BTR(2);
         tc::fence_after_sync();
         // ---- the pass: P~^T -> TMEM (over S^T), dS^T -> TMEM (over dP^T) and shared memory
         if (rows_live) {
@@ -214,9 +244,11 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           });
           tc::tmem_st_wait();
         }
+        BTR(3);
         tc::fence_before_sync();
         tc::fence_proxy_async();
         __syncthreads();
+        BTR(4);
         // ---- (2) dV_kt = P~^T dO, dK_kt = dS^T Q  (A from TMEM, K = queries);  dQ_t += dS_t K_kt  (A = dS^T buffer, MN-major)
         if (warp == 0 && tc::elect_one()) {
           tc::fence_after_sync();
@@ -239,6 +271,10 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
               first = false;
             }
           }
+          tc::mma_commit(&bars[1]);
+        }
+        if (warp == 4 && tc::elect_one()) {                                   // second issuer: the two run concurrently
+          tc::fence_after_sync();
           const uint32_t idesc_q = tc::make_idesc_bf16(128, DH, 1, 1);      // A MN-major (queries), B MN-major
           for (int t = 0; t < NT; ++t) {
             const uint32_t dcol = t == 0 ? (uint32_t)COL_DQ0 : col_dq1;
@@ -250,7 +286,9 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           }
           tc::mma_commit(&bars[1]);
         }
+        BTR(5);
         tc::mbar_wait(&bars[1], phase);
+        BTR(6);
         if (tid == 0 && hd == 1 && kt == NT - 1 && item + (int)gridDim.x < n_items)
           issue_loads(item + gridDim.x);            // every MMA on this item's operands is done: refill during the drain
         tc::fence_after_sync();
@@ -281,9 +319,12 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             if (NT == 2) accQ[1][i] += __uint_as_float(q1[i]);
           }
         }
+        if (hd == 0 && kt == 0) { sL[(sbuf ^ 1) * 512 + tid] = nl * 1.4426950408889634f; sD[(sbuf ^ 1) * 512 + tid] = nd; }
+        BTR(7);
         tc::fence_before_sync();
         phase ^= 1;
         __syncthreads();                              // TMEM and the dS buffer are free for the next key tile / head / item
+        BTR(8);
       }
       // ---- dQ rows of this head
 #pragma unroll
@@ -298,6 +339,10 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       }
     }
   }
+#ifdef EAVIT_TRACE
+  if (blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 16; ++i) g_bt_trace[i] += tr_acc[i];
+#endif
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) {
@@ -338,3 +383,12 @@ extern "C" int eavit_attention_bwd_tct(const void* qkv, const void* out, const v
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
+
+#ifdef EAVIT_TRACE
+extern "C" int eavit_debug_bt_trace(long long* host32, int reset) {
+  if (reset) { long long z[32] = {0}; cudaMemcpyToSymbol(eavit::bt::g_bt_trace, z, sizeof(z)); return 0; }
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host32, eavit::bt::g_bt_trace, 32 * sizeof(long long));
+  return 0;
+}
+#endif

@@ -18,7 +18,10 @@ dqkv = torch.empty_like(qkv)
 ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse, 0.0, 0)
 which = sys.argv[1] if len(sys.argv) > 1 else "bwd"
 def run():
-    if which == "bwd":
+    if which == "bwdt":
+        ws = torch.empty(qkv.shape[0], H, device="cuda")
+        ops.call("eavit_attention_bwd_tct", qkv, o, do, lse, ws, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv)
+    elif which == "bwd":
         ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0)
     else:
         ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse, 0.0, 0)
@@ -26,9 +29,10 @@ run()
 torch.cuda.synchronize()
 L = _lib.lib()
 buf = (ctypes.c_longlong * 32)()
-L.eavit_debug_att_trace(buf, 1)
+dbg = L.eavit_debug_bt_trace if which == "bwdt" else L.eavit_debug_att_trace
+dbg(buf, 1)
 run()
-L.eavit_debug_att_trace(buf, 0)
+dbg(buf, 0)
 v = list(buf)
 tot = sum(v)
 names = sys.argv[2].split(",") if len(sys.argv) > 2 else [str(i) for i in range(32)]
