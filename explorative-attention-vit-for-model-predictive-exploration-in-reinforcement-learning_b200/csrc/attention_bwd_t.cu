@@ -8,7 +8,7 @@
 //     dV_kt = P~^T dO   and   dK_kt = dS^T Q    read A from TENSOR MEMORY (tcgen05.mma with [tmem] A),
 // written there by tcgen05.st as packed bf16 pairs over the first half of each thread's own score columns; only dS^T also
 // goes to shared memory (dQ = dS K needs queries on M: the same buffer read as an MN-major A operand).  The row statistic
-// D_i = sum_j P_ij dP_ij = sum_d O_id dO_id comes from a tiny pre-kernel, so ONE pass produces P~^T and dS^T together:
+// D_i = sum_j P_ij dP_ij = sum_d O_id dO_id is formed from the staged O and dO tiles, so ONE pass produces P~^T and dS^T together:
 //     per (head, key tile):   S^T, dP^T MMA -> one pass -> dV, dK, dQ MMAs -> drain        (two MMA round trips, one pass)
 // dV / dK are complete per key tile (their K dimension is the whole sequence) and are stored straight from TMEM; dQ is
 // summed over the two key tiles in registers.
@@ -47,10 +47,11 @@ struct Smem {
   static constexpr int OFF_DO = OFF_Q + 256 * ROWB;             // [256][128 B]
   static constexpr int OFF_K = OFF_DO + 256 * ROWB;             // [224][128 B] (tile 1 of an MMA reads on into V / dS: finite)
   static constexpr int OFF_V = OFF_K + 224 * ROWB;
-  static constexpr int OFF_DS = OFF_V + 224 * ROWB;             // dS^T: 4 slabs [128 keys][64 queries]
+  static constexpr int OFF_O = OFF_V + 224 * ROWB;              // [224][128 B]  attention output (for D = rowsum(O * dO))
+  static constexpr int OFF_DS = OFF_O + 224 * ROWB;             // dS^T: 4 slabs [128 keys][64 queries]
   static constexpr int OFF_L = OFF_DS + 4 * SLAB;               // float [2 buffers][2 heads][256]  lse * log2(e)   (+inf past the end)
-  static constexpr int OFF_D = OFF_L + 2 * 2 * 256 * 4;         // float [2 buffers][2 heads][256]  D
-  static constexpr int OFF_BAR = OFF_D + 2 * 2 * 256 * 4;
+  static constexpr int OFF_D = OFF_L + 2 * 2 * 256 * 4;         // float [2 heads][256]  D
+  static constexpr int OFF_BAR = OFF_D + 2 * 256 * 4;
   static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
@@ -65,33 +66,10 @@ __device__ __forceinline__ void ksplit(int nks, bool two_q, int* kb /*[5]*/) {
   }
 }
 
-// D[t, h] = sum_d out[t, h, d] * dout[t, h, d]   (one warp per token row, 8 columns per lane, Dh / 8 lanes per head)
-__global__ void __launch_bounds__(256) dvec_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                                                   long long T, int H, float* __restrict__ dvec) {
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= T) return;
-  const int HD = H * DH;
-  for (int c0 = lane * 8; c0 < HD; c0 += 256) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(out + row * HD + c0));
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(dout + row * HD + c0));
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      s = fmaf(__uint_as_float(aw[i] << 16), __uint_as_float(bw[i] << 16), s);
-      s = fmaf(__uint_as_float(aw[i] & 0xffff0000u), __uint_as_float(bw[i] & 0xffff0000u), s);
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if ((lane & 3) == 0) dvec[row * H + (c0 >> 5)] = s;
-  }
-}
-
 __global__ void __launch_bounds__(THREADS, 1)
 attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                       const float* __restrict__ lse, const float* __restrict__ dvec, const int* __restrict__ seq_start, int nseq,
-                       int H, float scale, __nv_bfloat16* __restrict__ dqkv) {
+                       const __grid_constant__ CUtensorMap tmO, const float* __restrict__ lse, const int* __restrict__ seq_start,
+                       int nseq, int H, float scale, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sL = reinterpret_cast<float*>(smem + Smem::OFF_L);
@@ -106,6 +84,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   if (tid == 0) {
     tc::prefetch_tmap(&tmQKV);
     tc::prefetch_tmap(&tmDO);
+    tc::prefetch_tmap(&tmO);
     tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 2); tc::mbar_init(&bars[2], 1);
     tc::fence_barrier_init();
   }
@@ -131,14 +110,16 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     const int sq = it / HG, hg = it - sq * HG;
     const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
     const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
-    tc::mbar_expect_tx(&bars[2], 4 * nb * BOX_BYTES);
+    tc::mbar_expect_tx(&bars[2], 5 * nb * BOX_BYTES);
     const int offs[3] = {Smem::OFF_Q, Smem::OFF_K, Smem::OFF_V};
 #pragma unroll
     for (int m = 0; m < 3; ++m)
       for (int b = 0; b < nb; ++b)
         tc::tma_load_2d(smem + offs[m] + b * BOX_BYTES, &tmQKV, &bars[2], m * H * DH + hg * 64, tt + b * BOX_ROWS);
-    for (int b = 0; b < nb; ++b)
+    for (int b = 0; b < nb; ++b) {
       tc::tma_load_2d(smem + Smem::OFF_DO + b * BOX_BYTES, &tmDO, &bars[2], hg * 64, tt + b * BOX_ROWS);
+      tc::tma_load_2d(smem + Smem::OFF_O + b * BOX_BYTES, &tmO, &bars[2], hg * 64, tt + b * BOX_ROWS);
+    }
   };
   if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
   if ((int)blockIdx.x < n_items) {                 // row statistics of the first item -> buffer 0
@@ -147,7 +128,6 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     const int hd = tid >> 8, q = tid & 255;
     const bool ok = q < SS;
     sL[tid] = ok ? lse[(size_t)(tt + q) * H + hg0 * 2 + hd] * 1.4426950408889634f : INFINITY;
-    sD[tid] = ok ? dvec[(size_t)(tt + q) * H + hg0 * 2 + hd] : 0.f;
   }
 
 #ifdef EAVIT_TRACE
@@ -162,23 +142,41 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     ksplit(nks, NT == 2, kb);
     const int cbeg = kb[grp] * 16, cend = kb[grp + 1] * 16;  // this thread's query columns
     const uint32_t col_dq1 = (uint32_t)(NQP - 32);           // dQ accumulator of query tile 1 (inside the last group's columns)
-    // Row statistics of both heads of the pair -- lse * log2(e) (+inf past the end: P = 0) and D -- one entry per thread,
-    // double-buffered: the NEXT item's entry is fetched into registers now and parked in the other buffer after the first
-    // key tile, so its global-load latency never sits in front of a round.
+    // Row statistics of both heads of the pair, one entry per thread.  lse * log2(e) (+inf past the end: P = 0) is
+    // double-buffered: the NEXT item's entry is fetched into a register now and parked in the other buffer after the
+    // first key tile, so its global-load latency never sits in front of a round.  D = rowsum(O * dO) comes from the two
+    // staged tiles (16-byte chunk c of row q sits at chunk c ^ (q & 7) of the swizzled row).
     const int sbuf = (int)(ph_ld & 1);
     tc::mbar_wait(&bars[2], ph_ld);
     ph_ld ^= 1;
-    __syncthreads();                                         // this item's sL / sD (written during the previous item) visible
+    {
+      const int hd = tid >> 8, q = tid & 255;
+      float dsum = 0.f;
+      if (q < S) {
+        const uint8_t* orow = smem + Smem::OFF_O + (q >> 3) * 1024 + (q & 7) * 128;
+        const uint8_t* grow = smem + Smem::OFF_DO + (q >> 3) * 1024 + (q & 7) * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = ((hd * 4 + j) ^ (q & 7)) << 4;
+          const uint4 a = *reinterpret_cast<const uint4*>(orow + ch), b = *reinterpret_cast<const uint4*>(grow + ch);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            dsum = fmaf(__uint_as_float(aw[i] << 16), __uint_as_float(bw[i] << 16), dsum);
+            dsum = fmaf(__uint_as_float(aw[i] & 0xffff0000u), __uint_as_float(bw[i] & 0xffff0000u), dsum);
+          }
+        }
+      }
+      sD[tid] = dsum;
+    }
+    __syncthreads();                                         // sL (written during the previous item) and sD visible
     const int nitem = item + (int)gridDim.x;
-    float nl = INFINITY, nd = 0.f;
+    float nl = INFINITY;
     if (nitem < n_items) {
       const int nsq = nitem / HG, nhg = nitem - nsq * HG;
       const int nt0 = seq_start[nsq], nS = seq_start[nsq + 1] - nt0;
       const int hd = tid >> 8, q = tid & 255;
-      if (q < nS) {                                          // raw values: nothing below depends on them until they are parked
-        nl = __ldg(lse + (size_t)(nt0 + q) * H + nhg * 2 + hd);
-        nd = __ldg(dvec + (size_t)(nt0 + q) * H + nhg * 2 + hd);
-      }
+      if (q < nS) nl = __ldg(lse + (size_t)(nt0 + q) * H + nhg * 2 + hd);      // raw: nothing depends on it until it is parked
     }
     BTR(0);
 
@@ -187,7 +185,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       const int h = hg * 2 + hd;
       const uint32_t hoff = (uint32_t)(hd * DH * 2);         // byte offset of this head inside the 128-byte rows
       const float* hL = sL + sbuf * 512 + hd * 256;
-      const float* hD = sD + sbuf * 512 + hd * 256;
+      const float* hD = sD + hd * 256;
       float accQ[2][8];                                      // dQ rows (tile, row_in_tile), columns [grp*8, +8), summed over key tiles
 #pragma unroll
       for (int i = 0; i < 8; ++i) { accQ[0][i] = 0.f; accQ[1][i] = 0.f; }
@@ -319,7 +317,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             if (NT == 2) accQ[1][i] += __uint_as_float(q1[i]);
           }
         }
-        if (hd == 0 && kt == 0) { sL[(sbuf ^ 1) * 512 + tid] = nl * 1.4426950408889634f; sD[(sbuf ^ 1) * 512 + tid] = nd; }
+        if (hd == 0 && kt == 0) sL[(sbuf ^ 1) * 512 + tid] = nl * 1.4426950408889634f;
         BTR(7);
         tc::fence_before_sync();
         phase ^= 1;
@@ -356,21 +354,21 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
 
 using namespace eavit;
 
-extern "C" int eavit_attention_bwd_tct(const void* qkv, const void* out, const void* dout, const float* lse, float* dvec_ws,
+extern "C" int eavit_attention_bwd_tct(const void* qkv, const void* out, const void* dout, const float* lse,
                                        const int* seq_start, int nseq, int max_len, long long total_tokens, int H, int Dh,
                                        float scale, void* dqkv, void* stream) {
-  EAVIT_CHECK_ARG(qkv && out && dout && lse && dvec_ws && seq_start && dqkv && nseq > 0 && H > 0 && total_tokens > 0);
+  EAVIT_CHECK_ARG(qkv && out && dout && lse && seq_start && dqkv && nseq > 0 && H > 0 && total_tokens > 0);
   EAVIT_CHECK_ARG(Dh == 32 && H % 2 == 0 && max_len > 0 && max_len <= bt::MAXQ);
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap tq, tdo;
+  CUtensorMap tq, tdo, to;
   int rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)3 * H * Dh, (uint64_t)total_tokens, (uint64_t)3 * H * Dh * 2, bt::BOX_ROWS);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tdo, dout, (uint64_t)H * Dh, (uint64_t)total_tokens, (uint64_t)H * Dh * 2, bt::BOX_ROWS);
   if (rc) return rc;
-  bt::dvec_kernel<<<cdiv(total_tokens, 8), 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, total_tokens, H, dvec_ws);
-  EAVIT_LAUNCH_OK();
+  rc = make_tmap_bf16_2d(&to, out, (uint64_t)H * Dh, (uint64_t)total_tokens, (uint64_t)H * Dh * 2, bt::BOX_ROWS);
+  if (rc) return rc;
   static bool done = false;
   if (!done) {
     EAVIT_CUDA(cudaFuncSetAttribute(bt::attention_bwd_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt::Smem::TOTAL));
@@ -378,7 +376,7 @@ extern "C" int eavit_attention_bwd_tct(const void* qkv, const void* out, const v
   }
   const int items = nseq * (H / 2);
   const int grid = items < kNumSMs ? items : kNumSMs;
-  bt::attention_bwd_t_kernel<<<grid, bt::THREADS, bt::Smem::TOTAL, st>>>(tq, tdo, lse, dvec_ws, seq_start, nseq, H, scale,
+  bt::attention_bwd_t_kernel<<<grid, bt::THREADS, bt::Smem::TOTAL, st>>>(tq, tdo, to, lse, seq_start, nseq, H, scale,
                                                                          (__nv_bfloat16*)dqkv);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;

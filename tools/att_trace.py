@@ -19,8 +19,7 @@ ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH,
 which = sys.argv[1] if len(sys.argv) > 1 else "bwd"
 def run():
     if which == "bwdt":
-        ws = torch.empty(qkv.shape[0], H, device="cuda")
-        ops.call("eavit_attention_bwd_tct", qkv, o, do, lse, ws, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv)
+        ops.call("eavit_attention_bwd_tct", qkv, o, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv)
     elif which == "bwd":
         ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0)
     else:
