@@ -210,6 +210,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         const int nkeys = min(128, S - kt * 128);            // valid keys of the tile
         const int kq = (nkeys + 15) >> 4;                    // 16-key K steps of the dQ MMA
         const bool rows_live = kt * 128 + quad * 32 < S;     // warp-uniform: any valid key in this warp
+        const bool all_ok = kt * 128 + quad * 32 + 31 < S;   // warp-uniform: every key of this warp is valid
         tc::mbar_wait(&bars[0], phase);
         BTR(2);
         tc::fence_after_sync();
@@ -228,14 +229,13 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
               pu[j >> 1] = pack_bf16x2(p0, p1);
               du[j >> 1] = pack_bf16x2(p0 * (__uint_as_float(rp[j]) - dq[j]), p1 * (__uint_as_float(rp[j + 1]) - dq[j + 1]));
             }
-            if (!kok) {                                      // a key past the end of the sequence: exact zeros (dQ sums over keys)
+            if (!all_ok && !kok) {                           // a key past the end of the sequence: exact zeros (dQ sums over keys)
 #pragma unroll
               for (int j = 0; j < 4; ++j) { pu[j] = 0u; du[j] = 0u; }
             }
             *reinterpret_cast<uint4*>(dsbuf + (c0 >> 6) * SLAB + sw_off(row_in_tile, (c0 & 63) >> 3)) = make_uint4(du[0], du[1], du[2], du[3]);
             // packed pairs go back over the first half of this thread's own columns: chunk i (columns cbeg + 8 i ..) lands
             // at cbeg + 4 i .., always behind the columns this thread still has to read
-            __syncwarp();
             const uint32_t half = (uint32_t)(cbeg + ((c0 - cbeg) >> 1));
             tc::tmem_st_32x4(lane_base + COL_S + half, pu);
             tc::tmem_st_32x4(lane_base + COL_DP + half, du);
