@@ -52,7 +52,7 @@ struct Smem {
   static constexpr int OFF_L = OFF_DS + 4 * SLAB;               // float [2 buffers][2 heads][256]  lse * log2(e)   (+inf past the end)
   static constexpr int OFF_D = OFF_L + 2 * 2 * 256 * 4;         // float [2 heads][256]  D
   static constexpr int OFF_BAR = OFF_D + 2 * 256 * 4;
-  static constexpr int TOTAL = OFF_BAR + 64 + 1024;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
 };
 
 // k-steps (16 queries) of warp group g: with two query tiles the LAST group takes >= 4 so that the second half of its
@@ -74,8 +74,8 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sL = reinterpret_cast<float*>(smem + Smem::OFF_L);
   float* sD = reinterpret_cast<float*>(smem + Smem::OFF_D);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);      // [0] S^T,dP^T  [1] dV,dK,dQ  [2] loads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);      // [0] S^T,dP^T  [1] dV,dK,dQ  [2] loads  [4..7] pass done, per warp group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, grp = warp >> 2;
   const int row_in_tile = quad * 32 + lane;
@@ -86,6 +86,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     tc::prefetch_tmap(&tmDO);
     tc::prefetch_tmap(&tmO);
     tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 2); tc::mbar_init(&bars[2], 1);
+    for (int g = 0; g < 4; ++g) tc::mbar_init(&bars[4 + g], 128);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -243,34 +244,31 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           tc::tmem_st_wait();
         }
         BTR(3);
+        // this warp group's P~^T / dS^T columns are in TMEM: the issuer starts on them while slower groups still compute
         tc::fence_before_sync();
-        tc::fence_proxy_async();
-        __syncthreads();
-        BTR(4);
-        // ---- (2) dV_kt = P~^T dO, dK_kt = dS^T Q  (A from TMEM, K = queries);  dQ_t += dS_t K_kt  (A = dS^T buffer, MN-major)
+        tc::mbar_arrive(&bars[4 + grp]);
+        // ---- (2) dV_kt = P~^T dO, dK_kt = dS^T Q  (A from TMEM, K = queries), group by group as they finish
         if (warp == 0 && tc::elect_one()) {
-          tc::fence_after_sync();
           const uint32_t idesc_t = tc::make_idesc_bf16(128, DH, 0, 1);      // A K-major (TMEM), B MN-major
           bool first = true;
           for (int g = 0; g < 4; ++g) {
+            tc::mbar_wait(&bars[4 + g], phase);
+            tc::fence_after_sync();
             for (int ks = kb[g]; ks < kb[g + 1]; ++ks) {
               const uint32_t a_col = (uint32_t)(kb[g] * 16 + (ks - kb[g]) * 8);
               const uint64_t bdo = tc::make_sdesc_sw128(sDO + ks * 2048 + hoff, 8192, 1024);
-              tc::mma_bf16_ts(tmem_base + COL_DV, tmem_base + COL_S + a_col, bdo, idesc_t, first ? 0u : 1u);
-              first = false;
-            }
-          }
-          first = true;
-          for (int g = 0; g < 4; ++g) {
-            for (int ks = kb[g]; ks < kb[g + 1]; ++ks) {
-              const uint32_t a_col = (uint32_t)(kb[g] * 16 + (ks - kb[g]) * 8);
               const uint64_t bq = tc::make_sdesc_sw128(sQ + ks * 2048 + hoff, 8192, 1024);
+              tc::mma_bf16_ts(tmem_base + COL_DV, tmem_base + COL_S + a_col, bdo, idesc_t, first ? 0u : 1u);
               tc::mma_bf16_ts(tmem_base + COL_DK, tmem_base + COL_DP + a_col, bq, idesc_t, first ? 0u : 1u);
               first = false;
             }
           }
           tc::mma_commit(&bars[1]);
         }
+        tc::fence_proxy_async();
+        __syncthreads();
+        BTR(4);
+        // ---- dQ_t += dS_t K_kt  (A = the complete dS^T buffer in shared memory, MN-major)
         if (warp == 4 && tc::elect_one()) {                                   // second issuer: the two run concurrently
           tc::fence_after_sync();
           const uint32_t idesc_q = tc::make_idesc_bf16(128, DH, 1, 1);      // A MN-major (queries), B MN-major
