@@ -51,7 +51,8 @@ struct Smem {
   static constexpr int OFF_DS = OFF_O + 224 * ROWB;             // dS^T: 4 slabs [128 keys][64 queries]
   static constexpr int OFF_L = OFF_DS + 4 * SLAB;               // float [2 buffers][2 heads][256]  lse * log2(e)   (+inf past the end)
   static constexpr int OFF_D = OFF_L + 2 * 2 * 256 * 4;         // float [2 heads][256]  D
-  static constexpr int OFF_BAR = OFF_D + 2 * 256 * 4;
+  static constexpr int OFF_RK = OFF_D + 2 * 256 * 4;            // uint32 [256]  dropout row keys of the item's query rows
+  static constexpr int OFF_BAR = OFF_RK + 256 * 4;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;
 };
 
@@ -66,14 +67,19 @@ __device__ __forceinline__ void ksplit(int nks, bool two_q, int* kb /*[5]*/) {
   }
 }
 
+// DROP: nn.Dropout on the attention probabilities (vit.py:45,70): mask element = (token row t0 + q, column h*256 + key), the
+// same element attention_tc.cu evaluates.  dV takes the masked P~ (the stash), dS = P (M dP - D), D = rowsum(O * dO) holds
+// unchanged because O was formed from the masked probabilities.
+template <bool DROP>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmO, const float* __restrict__ lse, const int* __restrict__ seq_start,
-                       int nseq, int H, float scale, __nv_bfloat16* __restrict__ dqkv) {
+                       int nseq, int H, float scale, __nv_bfloat16* __restrict__ dqkv, const DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sL = reinterpret_cast<float*>(smem + Smem::OFF_L);
   float* sD = reinterpret_cast<float*>(smem + Smem::OFF_D);
+  uint32_t* sRK = reinterpret_cast<uint32_t*>(smem + Smem::OFF_RK);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);      // [0] S^T,dP^T  [1] dV,dK,dQ  [2] loads  [4..7] pass done, per warp group
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -169,6 +175,9 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         }
       }
       sD[tid] = dsum;
+      if constexpr (DROP) {
+        if (tid < 256) sRK[tid] = drop_row_key(drop, (uint32_t)(t0 + tid));
+      }
     }
     __syncthreads();                                         // sL (written during the previous item) and sD visible
     const int nitem = item + (int)gridDim.x;
@@ -212,6 +221,9 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         const int kq = (nkeys + 15) >> 4;                    // 16-key K steps of the dQ MMA
         const bool rows_live = kt * 128 + quad * 32 < S;     // warp-uniform: any valid key in this warp
         const bool all_ok = kt * 128 + quad * 32 + 31 < S;   // warp-uniform: every key of this warp is valid
+        // dropout: one 32-bit hash serves the key pair (2j, 2j+1) of a query row; this thread's key picks its 16 bits
+        const uint32_t ck = (uint32_t)(h * 128 + (krow >> 1)) * 0x9E3779B9u;
+        const uint32_t ksh = (krow & 1) ? 16u : 0u;
         tc::mbar_wait(&bars[0], phase);
         BTR(2);
         tc::fence_after_sync();
@@ -223,12 +235,26 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             const float lq[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
             const float dq[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
             uint32_t pu[4], du[4];
+            if constexpr (DROP) {
+              const uint4 k0 = *reinterpret_cast<const uint4*>(sRK + c0), k1 = *reinterpret_cast<const uint4*>(sRK + c0 + 4);
+              const uint32_t rkq[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -lq[j]));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -lq[j + 1]));
-              pu[j >> 1] = pack_bf16x2(p0, p1);
-              du[j >> 1] = pack_bf16x2(p0 * (__uint_as_float(rp[j]) - dq[j]), p1 * (__uint_as_float(rp[j + 1]) - dq[j + 1]));
+              for (int j = 0; j < 8; j += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -lq[j]));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -lq[j + 1]));
+                const float m0 = ((lowbias32(rkq[j] + ck) >> ksh) & 0xffffu) >= drop.thresh ? drop.scale : 0.f;
+                const float m1 = ((lowbias32(rkq[j + 1] + ck) >> ksh) & 0xffffu) >= drop.thresh ? drop.scale : 0.f;
+                pu[j >> 1] = pack_bf16x2(p0 * m0, p1 * m1);
+                du[j >> 1] = pack_bf16x2(p0 * fmaf(m0, __uint_as_float(rp[j]), -dq[j]), p1 * fmaf(m1, __uint_as_float(rp[j + 1]), -dq[j + 1]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -lq[j]));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -lq[j + 1]));
+                pu[j >> 1] = pack_bf16x2(p0, p1);
+                du[j >> 1] = pack_bf16x2(p0 * (__uint_as_float(rp[j]) - dq[j]), p1 * (__uint_as_float(rp[j + 1]) - dq[j + 1]));
+              }
             }
             if (!all_ok && !kok) {                           // a key past the end of the sequence: exact zeros (dQ sums over keys)
 #pragma unroll
@@ -352,11 +378,28 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
 
 using namespace eavit;
 
+template <bool DROP>
+static int launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& to, const float* lse, const int* seq_start,
+                        int nseq, int H, float scale, void* dqkv, const DropCfg& drop, cudaStream_t st) {
+  static bool done = false;
+  if (!done) {
+    EAVIT_CUDA(cudaFuncSetAttribute(bt::attention_bwd_t_kernel<DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt::Smem::TOTAL));
+    done = true;
+  }
+  const int items = nseq * (H / 2);
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  bt::attention_bwd_t_kernel<DROP><<<grid, bt::THREADS, bt::Smem::TOTAL, st>>>(tq, tdo, to, lse, seq_start, nseq, H, scale,
+                                                                               (__nv_bfloat16*)dqkv, drop);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
 extern "C" int eavit_attention_bwd_tct(const void* qkv, const void* out, const void* dout, const float* lse,
                                        const int* seq_start, int nseq, int max_len, long long total_tokens, int H, int Dh,
-                                       float scale, void* dqkv, void* stream) {
+                                       float scale, void* dqkv, float drop_p, unsigned long long drop_seed, void* stream) {
   EAVIT_CHECK_ARG(qkv && out && dout && lse && seq_start && dqkv && nseq > 0 && H > 0 && total_tokens > 0);
   EAVIT_CHECK_ARG(Dh == 32 && H % 2 == 0 && max_len > 0 && max_len <= bt::MAXQ);
+  EAVIT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
@@ -367,17 +410,9 @@ extern "C" int eavit_attention_bwd_tct(const void* qkv, const void* out, const v
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&to, out, (uint64_t)H * Dh, (uint64_t)total_tokens, (uint64_t)H * Dh * 2, bt::BOX_ROWS);
   if (rc) return rc;
-  static bool done = false;
-  if (!done) {
-    EAVIT_CUDA(cudaFuncSetAttribute(bt::attention_bwd_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt::Smem::TOTAL));
-    done = true;
-  }
-  const int items = nseq * (H / 2);
-  const int grid = items < kNumSMs ? items : kNumSMs;
-  bt::attention_bwd_t_kernel<<<grid, bt::THREADS, bt::Smem::TOTAL, st>>>(tq, tdo, to, lse, seq_start, nseq, H, scale,
-                                                                         (__nv_bfloat16*)dqkv);
-  EAVIT_LAUNCH_OK();
-  return EAVIT_OK;
+  const DropCfg drop = make_drop(drop_p, drop_seed);
+  return drop.thresh ? launch_bwd_t<true>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, st)
+                     : launch_bwd_t<false>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, st);
 }
 
 #ifdef EAVIT_TRACE

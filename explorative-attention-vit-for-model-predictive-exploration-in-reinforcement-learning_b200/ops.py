@@ -228,7 +228,7 @@ _SPECS = {
     "eavit_attention_fwd_tc": "ppiiliifpp" "fu",
     "eavit_attention_bwd": "pppppiiiifp",
     "eavit_attention_bwd_tc": "ppppiiliifp" "fu",
-    "eavit_attention_bwd_tct": "pppppiiliifp",
+    "eavit_attention_bwd_tct": "pppppiiliifp" "fu",
     "eavit_attention_row0_fwd": "ppiiiifp" "fu",
     "eavit_attention_row0_bwd": "pppiiiifp" "fu",
     "eavit_patchify": "pipiiiiippfppp",
@@ -331,10 +331,11 @@ def attention_fwd(qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse, drop_p:
 
 
 def attention_bwd(qkv, out, dout, lse, seq_start, nseq, max_len, H, Dh, scale, dqkv, drop_p: float = 0.0, drop_seed: int = 0):
-    if Dh == 32 and max_len <= 208 and drop_p == 0 and H % 2 == 0 and os.environ.get("EAVIT_ATTN_BWD", "t") == "t":
+    if Dh == 32 and max_len <= 208 and H % 2 == 0 and os.environ.get("EAVIT_ATTN_BWD", "t") == "t":
         if _PROF is not None:      # S, dP (recomputed), dV, dK, dQ: 5 contractions of 2 * S^2 * Dh
             _FLOPS_HINT["eavit_attention_bwd_tct"] = 10.0 * nseq * H * max_len * max_len * Dh
-        call("eavit_attention_bwd_tct", qkv, out, dout, lse, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, dqkv)
+        call("eavit_attention_bwd_tct", qkv, out, dout, lse, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, dqkv,
+             float(drop_p), int(drop_seed) & _M64)
     elif (Dh == 32 and max_len <= 224) or (Dh == 64 and max_len <= 128):
         if _PROF is not None:
             _FLOPS_HINT["eavit_attention_bwd_tc"] = 10.0 * nseq * H * max_len * max_len * Dh

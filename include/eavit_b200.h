@@ -171,9 +171,10 @@ int eavit_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, 
                            long long total_tokens, int H, int Dh, float scale, void* dqkv, float drop_p,
                            unsigned long long drop_seed, void* stream);
 /* Backward with transposed scores (keys on the TMEM lanes; P~^T and dS^T are TMEM-resident A operands of dV / dK, one
- * softmax pass per key tile): Dh = 32, max_len <= 208, no dropout.  Needs `out` (D = rowsum(out * dout), formed in-kernel). */
+ * softmax pass per key tile): Dh = 32, max_len <= 208.  Needs `out` (D = rowsum(out * dout), formed in-kernel). */
 int eavit_attention_bwd_tct(const void* qkv, const void* out, const void* dout, const float* lse, const int* seq_start, int nseq,
-                            int max_len, long long total_tokens, int H, int Dh, float scale, void* dqkv, void* stream);
+                            int max_len, long long total_tokens, int H, int Dh, float scale, void* dqkv, float drop_p,
+                            unsigned long long drop_seed, void* stream);
 /* drop_p > 0 (both kernels): nn.Dropout on the attention probabilities (vit.py:45,70); mask element = (token row,
  * h * 256 + key) of the site seed, regenerated in the backward. */
 

@@ -88,7 +88,7 @@ def test_attention_backward(ops, lens, H, Dh, impl):
     dqkv = torch.full((T, 3 * H * Dh), float("nan"), device="cuda", dtype=torch.bfloat16)
     if impl == "tct":
         ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse, 0.0, 0)
-        ops.call("eavit_attention_bwd_tct", qkv, out, dout, lse, ss, len(lens), max(lens), T, H, Dh, scale, dqkv)
+        ops.call("eavit_attention_bwd_tct", qkv, out, dout, lse, ss, len(lens), max(lens), T, H, Dh, scale, dqkv, 0.0, 0)
     elif impl == "tc":
         ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), T, H, Dh, scale, out, lse, 0.0, 0)
         ops.call("eavit_attention_bwd_tc", qkv, dout, lse, ss, len(lens), max(lens), T, H, Dh, scale, dqkv, 0.0, 0)

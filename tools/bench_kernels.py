@@ -52,7 +52,7 @@ if which in ("all", "attn"):
           qkv.numel() * 2 + o.numel() * 2)
     timed("attention_bwd_tc", lambda: ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0), 2.5 * fl,
           2 * qkv.numel() * 2 + o.numel() * 2)
-    timed("attention_bwd_tct (+ D pre-kernel)", lambda: ops.call("eavit_attention_bwd_tct", qkv, o, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv), 2.5 * fl,
+    timed("attention_bwd_tct (+ D pre-kernel)", lambda: ops.call("eavit_attention_bwd_tct", qkv, o, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0), 2.5 * fl,
           2 * qkv.numel() * 2 + 3 * o.numel() * 2)
 
 if which in ("all", "gemm"):
