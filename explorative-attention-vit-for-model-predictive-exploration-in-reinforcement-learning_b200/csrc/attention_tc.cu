@@ -159,6 +159,11 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
       {
         const uint32_t phase = (g ? ph1 : ph0) ^ (uint32_t)(j & 1);
         const uint32_t s_col = tmem_base + (uint32_t)(g * ATC_MAXKEYS);
+        // Dh = 32: P~ never leaves tensor memory -- pass 2 writes it back as packed bf16 pairs over the first half of each
+        // thread's own score columns (tcgen05.st) and O = P~ V takes A from TMEM; the O accumulator sits in the 64 spare
+        // columns behind the two score regions.  Dh = 64 (64-column accumulator) keeps P~ in shared memory and O over S.
+        constexpr bool PT = DH == 32;
+        const uint32_t o_col = PT ? tmem_base + (uint32_t)(2 * ATC_MAXKEYS + g * DH) : s_col;
         const bool issuer = (hf == 0 && quad == 0 && lane == 0);
         if (issuer) {
           tc::fence_after_sync();
@@ -221,14 +226,13 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
             if (c0 >= NKP) return;                       // beyond the keys the P.V MMA reads
             uint8_t* slab = pbase + (c0 >> 6) * P_SLAB;
             const int cb = (c0 & 63) >> 3;
-            if (SEG && (c0 + 16 <= lo || c0 >= hi)) {            // another sequence's keys: exact zeros, no math
-              *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(0, 0, 0, 0);
-              *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(0, 0, 0, 0);
-              return;
-            }
-            uint32_t pk[8];
+            uint32_t pk[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             const uint32_t dcol = hcol + (uint32_t)(c0 - lo);      // dropout column = key index inside the row's own sequence (lo is even)
-            if (SEG ? (c0 >= lo && c0 + 16 <= hi) : (c0 + 16 <= S)) {
+            // (SEG: the lanes of a warp sit in different sequences -- every path falls through to the common tail, whose
+            // TMEM store is warp-collective)
+            if (SEG && (c0 + 16 <= lo || c0 >= hi)) {
+              // another sequence's keys: exact zeros, no math
+            } else if (SEG ? (c0 >= lo && c0 + 16 <= hi) : (c0 + 16 <= S)) {
               float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
@@ -255,15 +259,22 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
                 pk[j >> 1] = pack_bf16x2(p0, p1);
               }
             }
-            *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if constexpr (PT) {
+              // chunk i (columns cbeg + 16 i ..) lands at cbeg + 8 i ..: always behind the columns this thread still reads
+              if constexpr (SEG) __syncwarp();
+              tc::tmem_st_32x8(lane_addr + (uint32_t)(cbeg + ((c0 - cbeg) >> 1)), pk);
+            } else {
+              *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(slab + sw_off(row_in_tile, cb + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
           });
+          if constexpr (PT) tc::tmem_st_wait();
         }
         sSum[hf * 256 + xslot] = sum;
         TR(5);
-        // all S reads done (O overlays S) and P visible to the async proxy, then one thread issues P.V
+        // all S reads done (Dh = 64: O overlays S) and P visible to the tensor core, then one thread issues P.V
         tc::fence_before_sync();
-        tc::fence_proxy_async();
+        if constexpr (!PT) tc::fence_proxy_async();
         named_bar_sync(1 + g, 256);
         TR(6);
         if (issuer) {
@@ -273,9 +284,15 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
           const uint32_t pa = tc::smem_u32(pbase);
           const uint32_t va = tc::smem_u32(smem + AttSmem::OFF_V) + hoff;    // N-slice of this head inside the MN-major rows
           for (int kk = 0; kk < NKP / 16; ++kk) {
-            const uint64_t adesc = tc::make_sdesc_sw128(pa + (kk >> 2) * P_SLAB + (kk & 3) * 32, 16, 1024);
             const uint64_t bdesc = tc::make_sdesc_sw128(va + kk * 2048, 8192, 1024);
-            tc::mma_bf16_ss(s_col, adesc, bdesc, idesc, kk > 0);
+            if constexpr (PT) {
+              const int c16 = kk * 16;                       // packed pairs of columns [c16, +16): 8 TMEM columns inside their half
+              const uint32_t a_col = (uint32_t)(c16 < half ? (c16 >> 1) : half + ((c16 - half) >> 1));
+              tc::mma_bf16_ts(o_col, s_col + a_col, bdesc, idesc, kk > 0);
+            } else {
+              const uint64_t adesc = tc::make_sdesc_sw128(pa + (kk >> 2) * P_SLAB + (kk & 3) * 32, 16, 1024);
+              tc::mma_bf16_ss(s_col, adesc, bdesc, idesc, kk > 0);
+            }
           }
           tc::mma_commit(&bar_o[g]);
         }
@@ -293,8 +310,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
         if (rows_live) {
           constexpr int HW = DH / 2;                   // output columns per thread
           uint32_t r[32];
-          if constexpr (HW == 16) tc::tmem_ld_32x16(lane_addr + hf * HW, r);
-          else tc::tmem_ld_32x32(lane_addr + hf * HW, r);
+          const uint32_t o_lane = o_col + ((uint32_t)(quad * 32) << 16);
+          if constexpr (HW == 16) tc::tmem_ld_32x16(o_lane + hf * HW, r);
+          else tc::tmem_ld_32x32(o_lane + hf * HW, r);
           tc::tmem_ld_wait();
           const int qrow = xrow;
           const float inv = 1.f / sum;
