@@ -146,3 +146,46 @@ def test_collector_feeds_the_device_buffer():
         st = got["states"]
     for p in procs:
         p.join(timeout=10)
+
+
+@pytest.mark.gpu
+def test_whole_loop_with_synthetic_workers():
+    """train.py's loop body end to end on the drop-in pieces: StepCollector -> get_action -> compute_intrinsic_reward on
+    normalised frames -> DeviceRollout -> finish -> train_model, two updates, with synthetic env worker processes."""
+    import eavit_b200  # noqa
+    from eavit_b200 import config, rollout, utils
+    from eavit_b200.envfeed import StepCollector
+    from oracle import oracle as O
+    from test_gpu_model import CFGS, make_agent
+    cfg = CFGS["lucid"]
+    E, T, updates = 2, 4, 2
+    agent, _ = make_agent(cfg, E, T)
+    agent.batch_size = 4
+    config.load_config(None, TrainMethod="original_RND")
+    obs_rms, reward_rms = utils.RunningMeanStd(shape=(1, 1, 84, 84), usage="obs_rms"), utils.RunningMeanStd(usage="reward_rms")
+    filt = utils.RewardForwardFilter(cfg.int_gamma)
+    conns, procs = _spawn(E, T * updates, False)
+    col = StepCollector(conns, device="cuda")
+    states, obs0 = col.initial_states()
+    obs_rms.update(torch.cat([obs0, 255 - obs0]))                       # some initial statistics (train.py:127-180)
+    w0 = agent.state_dict()["model.actor.2.weight"].clone()
+    np.random.seed(1); torch.manual_seed(1)
+    for u in range(updates):
+        buf = rollout.DeviceRollout(E, T, cfg.n_actions)
+        for t in range(T):
+            actions, v_ext, v_int, policy = agent.get_action(states)                 # uint8 frames, /255 in-kernel
+            got = col.step([int(a) for a in actions])
+            r_int = agent.compute_intrinsic_reward(utils.normalize_obs(got["next_obs"], obs_rms))   # train.py:666: stats from before the update
+            buf.add(t, states, got["next_obs"], got["rewards"], got["dones"], actions, v_ext, v_int, policy, r_int)
+            states = got["states"]
+        _, v_ext, v_int, _ = agent.get_action(states)
+        buf.add_last_values(v_ext, v_int)
+        args = buf.finish(obs_rms, reward_rms, filt, cfg.gamma, cfg.int_gamma, cfg.lam, cfg.ext_coef, cfg.int_coef)
+        agent.train_model(*args, u)
+        s = agent.stats_summary()
+        assert np.isfinite(s["loss"])
+    torch.cuda.synchronize()
+    assert not torch.equal(w0, agent.state_dict()["model.actor.2.weight"])
+    assert obs_rms.count > 2 * E * T and reward_rms.count > 2 * T - 1
+    for p in procs:
+        p.join(timeout=10)
