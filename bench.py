@@ -343,10 +343,18 @@ def main():
             dt = float(t.item())
         n_steps = EPOCH * n_mb
         h2d = sum(a.nbytes for a in upd_args)
+        # the upload is the box-dependent part of e2e: measure the host -> device rate of the largest buffer on its own
+        st_host = torch.from_numpy(upd_args[0])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        st_host.to(dev, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbps = upd_args[0].nbytes / (time.perf_counter() - t1) / 1e9
+        pinned_ok = bool(st_host.is_pinned())
         e2e = {"value": N * EPOCH * world / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d / n_steps,
                "d2h_bytes_per_step": 16 * 4, "call": "RNDAgent.train_model(states f32, target_ext f64, target_int f64, y i64, adv f64, "
                "next_obs f64, old_policy f32) -- numpy host buffers (pinned), one full update = 128 optimiser steps",
-               "seconds": dt, "loss": stats.get("loss")}
+               "seconds": dt, "loss": stats.get("loss"), "host_buffers_pinned": pinned_ok, "h2d_gb_per_s": h2d_gbps}
 
     in_sync = None
     if world > 1:
