@@ -6,6 +6,9 @@ import eavit_b200  # noqa
 from eavit_b200 import ops, _lib
 H, DH, B = 8, 32, 512
 lens = [196] * B + [197] * B
+if os.environ.get("ATT_TRACE_SHAPE") == "hg":          # vit_hg at the cfg4 per-GPU shape: 1024 sequences of 50 tokens, 16 heads x 64
+    H, DH, B = 16, 64, 512
+    lens = [50] * (2 * B)
 st = [0]
 for n in lens:
     st.append(st[-1] + n)
@@ -15,15 +18,15 @@ o = torch.empty(st[-1], H * DH, device="cuda", dtype=torch.bfloat16)
 lse = torch.empty(st[-1], H, device="cuda")
 do = torch.randn_like(o)
 dqkv = torch.empty_like(qkv)
-ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse, 0.0, 0)
+ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), qkv.shape[0], H, DH, DH ** -0.5, o, lse, 0.0, 0)
 which = sys.argv[1] if len(sys.argv) > 1 else "bwd"
 def run():
     if which == "bwdt":
-        ops.call("eavit_attention_bwd_tct", qkv, o, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0)
+        ops.call("eavit_attention_bwd_tct", qkv, o, do, lse, ss, len(lens), max(lens), qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0)
     elif which == "bwd":
-        ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0)
+        ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), max(lens), qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0)
     else:
-        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, o, lse, 0.0, 0)
+        ops.call("eavit_attention_fwd_tc", qkv, ss, len(lens), max(lens), qkv.shape[0], H, DH, DH ** -0.5, o, lse, 0.0, 0)
 run()
 torch.cuda.synchronize()
 L = _lib.lib()
