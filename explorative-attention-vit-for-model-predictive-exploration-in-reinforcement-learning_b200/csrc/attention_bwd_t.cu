@@ -1,4 +1,4 @@
-// Attention backward with TRANSPOSED scores (keys on the TMEM lanes), Dh = 32, sequences up to 208 tokens, no dropout.
+// Attention backward with TRANSPOSED scores (keys on the TMEM lanes): Dh = 32 with up to 208 tokens, Dh = 64 with up to 128.
 //
 // attention_tc.cu's backward keeps queries on the lanes: P~ and dS must both pass through ONE shared-memory buffer (they
 // are MN-major A operands of dV = P~^T dO and dK = dS^T Q), which forces  S,dP MMA -> pass 1 (P~, D) -> dV MMA -> pass 2
@@ -35,8 +35,7 @@ constexpr int ROWB = 128;                   // bytes per staged row: 64 bf16 = t
 constexpr int SLAB = 128 * ROWB;            // [128 rows][64 columns] bf16, 128-byte swizzle
 constexpr int BOX_ROWS = 32;
 constexpr int BOX_BYTES = BOX_ROWS * ROWB;
-constexpr int DH = 32;
-constexpr int COL_S = 0, COL_DP = 208, COL_DV = 416, COL_DK = 448, COL_DQ0 = 480;     // dQ tile 1: last 32 columns of S
+constexpr int MAXQ64 = 128;                 // Dh = 64: one key / query tile (three 64-column accumulators beside S^T and dP^T)
 
 __device__ __forceinline__ uint32_t sw_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
@@ -70,11 +69,19 @@ __device__ __forceinline__ void ksplit(int nks, bool two_q, int* kb /*[5]*/) {
 // DROP: nn.Dropout on the attention probabilities (vit.py:45,70): mask element = (token row t0 + q, column h*256 + key), the
 // same element attention_tc.cu evaluates.  dV takes the masked P~ (the stash), dS = P (M dP - D), D = rowsum(O * dO) holds
 // unchanged because O was formed from the masked probabilities.
-template <bool DROP>
+// SEG: `pack` consecutive equal-length sequences (contiguous in the token matrix) form one work item under a block-diagonal
+// mask -- a key attends only to the queries of its own `seg`-token sequence; masked probabilities are exact zeros, so every
+// product is unchanged (see attention_tc.cu).  This is what makes the 50-token sequences of the HF-style ViT worth a tile.
+template <int DH, bool DROP, bool SEG>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmO, const float* __restrict__ lse, const int* __restrict__ seq_start,
-                       int nseq, int H, float scale, __nv_bfloat16* __restrict__ dqkv, const DropCfg drop) {
+                       int nseq, int H, float scale, __nv_bfloat16* __restrict__ dqkv, const DropCfg drop, int pack, int seg) {
+  constexpr int HPB = 64 / DH;                      // heads per staged 128-byte row
+  constexpr int QC = DH / 4;                        // accumulator columns per thread in the drain
+  constexpr int NCHK = DH / 8;                      // 16-byte chunks of one head inside a staged row
+  // TMEM columns: S^T | dP^T | dV | dK | dQ (tile 0); Dh = 32 keeps dQ of query tile 1 in the last 32 columns of S^T
+  constexpr int COL_S = 0, COL_DP = DH == 32 ? 208 : 128, COL_DV = DH == 32 ? 416 : 256, COL_DK = COL_DV + DH, COL_DQ0 = COL_DK + DH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sL = reinterpret_cast<float*>(smem + Smem::OFF_L);
@@ -104,10 +111,10 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
 
   const int ldq = 3 * H * DH;
-  const int HG = H / 2;
+  const int HG = H / HPB;
   const float c2 = scale * 1.4426950408889634f;
   uint32_t phase = 0, ph_ld = 0;
-  const int n_items = nseq * HG;
+  const int n_items = ((nseq + pack - 1) / pack) * HG;
   const uint32_t sQ = tc::smem_u32(smem + Smem::OFF_Q), sDO = tc::smem_u32(smem + Smem::OFF_DO);
   const uint32_t sK = tc::smem_u32(smem + Smem::OFF_K), sV = tc::smem_u32(smem + Smem::OFF_V);
   const uint32_t sDS = tc::smem_u32(smem + Smem::OFF_DS);
@@ -115,7 +122,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
 
   auto issue_loads = [&](int it) {                 // one thread
     const int sq = it / HG, hg = it - sq * HG;
-    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const int tt = seq_start[sq * pack], SS = seq_start[min(nseq, sq * pack + pack)] - tt;
     const int nb = (SS + BOX_ROWS - 1) / BOX_ROWS;
     tc::mbar_expect_tx(&bars[2], 5 * nb * BOX_BYTES);
     const int offs[3] = {Smem::OFF_Q, Smem::OFF_K, Smem::OFF_V};
@@ -131,10 +138,10 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   if (tid == 0 && (int)blockIdx.x < n_items) issue_loads(blockIdx.x);
   if ((int)blockIdx.x < n_items) {                 // row statistics of the first item -> buffer 0
     const int sq = blockIdx.x / HG, hg0 = blockIdx.x - sq * HG;
-    const int tt = seq_start[sq], SS = seq_start[sq + 1] - tt;
+    const int tt = seq_start[sq * pack], SS = seq_start[min(nseq, sq * pack + pack)] - tt;
     const int hd = tid >> 8, q = tid & 255;
-    const bool ok = q < SS;
-    sL[tid] = ok ? lse[(size_t)(tt + q) * H + hg0 * 2 + hd] * 1.4426950408889634f : INFINITY;
+    const bool ok = q < SS && hd < HPB;
+    sL[tid] = ok ? lse[(size_t)(tt + q) * H + hg0 * HPB + hd] * 1.4426950408889634f : INFINITY;
   }
 
 #ifdef EAVIT_TRACE
@@ -142,7 +149,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
 #endif
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int seq = item / HG, hg = item - seq * HG;
-    const int t0 = seq_start[seq], S = seq_start[seq + 1] - t0;
+    const int t0 = seq_start[seq * pack], S = seq_start[min(nseq, seq * pack + pack)] - t0;
     const int NQP = (S + 15) & ~15, nks = NQP >> 4;          // score columns (queries), k-steps of the dV / dK MMAs
     const int NT = (S + 127) >> 7;                           // key tiles == query tiles
     int kb[5];
@@ -159,12 +166,12 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     {
       const int hd = tid >> 8, q = tid & 255;
       float dsum = 0.f;
-      if (q < S) {
+      if (q < S && hd < HPB) {
         const uint8_t* orow = smem + Smem::OFF_O + (q >> 3) * 1024 + (q & 7) * 128;
         const uint8_t* grow = smem + Smem::OFF_DO + (q >> 3) * 1024 + (q & 7) * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int ch = ((hd * 4 + j) ^ (q & 7)) << 4;
+        for (int j = 0; j < NCHK; ++j) {
+          const int ch = ((hd * NCHK + j) ^ (q & 7)) << 4;
           const uint4 a = *reinterpret_cast<const uint4*>(orow + ch), b = *reinterpret_cast<const uint4*>(grow + ch);
           const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -184,21 +191,21 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     float nl = INFINITY;
     if (nitem < n_items) {
       const int nsq = nitem / HG, nhg = nitem - nsq * HG;
-      const int nt0 = seq_start[nsq], nS = seq_start[nsq + 1] - nt0;
+      const int nt0 = seq_start[nsq * pack], nS = seq_start[min(nseq, nsq * pack + pack)] - nt0;
       const int hd = tid >> 8, q = tid & 255;
-      if (q < nS) nl = __ldg(lse + (size_t)(nt0 + q) * H + nhg * 2 + hd);      // raw: nothing depends on it until it is parked
+      if (q < nS && hd < HPB) nl = __ldg(lse + (size_t)(nt0 + q) * H + nhg * HPB + hd);      // raw: nothing depends on it until it is parked
     }
     BTR(0);
 
 #pragma unroll 1
-    for (int hd = 0; hd < 2; ++hd) {
-      const int h = hg * 2 + hd;
+    for (int hd = 0; hd < HPB; ++hd) {
+      const int h = hg * HPB + hd;
       const uint32_t hoff = (uint32_t)(hd * DH * 2);         // byte offset of this head inside the 128-byte rows
       const float* hL = sL + sbuf * 512 + hd * 256;
       const float* hD = sD + hd * 256;
-      float accQ[2][8];                                      // dQ rows (tile, row_in_tile), columns [grp*8, +8), summed over key tiles
+      float accQ[2][QC];                                     // dQ rows (tile, row_in_tile), columns [grp*QC, +QC), summed over key tiles
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { accQ[0][i] = 0.f; accQ[1][i] = 0.f; }
+      for (int i = 0; i < QC; ++i) { accQ[0][i] = 0.f; accQ[1][i] = 0.f; }
 
 #pragma unroll 1
       for (int kt = 0; kt < NT; ++kt) {
@@ -222,8 +229,14 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         const bool rows_live = kt * 128 + quad * 32 < S;     // warp-uniform: any valid key in this warp
         const bool all_ok = kt * 128 + quad * 32 + 31 < S;   // warp-uniform: every key of this warp is valid
         // dropout: one 32-bit hash serves the key pair (2j, 2j+1) of a query row; this thread's key picks its 16 bits
-        const uint32_t ck = (uint32_t)(h * 128 + (krow >> 1)) * 0x9E3779B9u;
-        const uint32_t ksh = (krow & 1) ? 16u : 0u;
+        // (mask column = key index inside the key's own sequence; seg is even, so pairs never straddle two sequences)
+        int qlo = 0, qhi = S;                                // queries this key belongs to
+        if constexpr (SEG) {
+          if (kok) { qlo = (krow / seg) * seg; qhi = min(qlo + seg, S); }
+        }
+        const int kin = krow - qlo;
+        const uint32_t ck = (uint32_t)(h * 128 + (kin >> 1)) * 0x9E3779B9u;
+        const uint32_t ksh = (kin & 1) ? 16u : 0u;
         tc::mbar_wait(&bars[0], phase);
         BTR(2);
         tc::fence_after_sync();
@@ -240,8 +253,12 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
               const uint32_t rkq[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
               for (int j = 0; j < 8; j += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -lq[j]));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -lq[j + 1]));
+                float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -lq[j]));
+                float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -lq[j + 1]));
+                if constexpr (SEG) {
+                  p0 = (c0 + j >= qlo && c0 + j < qhi) ? p0 : 0.f;
+                  p1 = (c0 + j + 1 >= qlo && c0 + j + 1 < qhi) ? p1 : 0.f;
+                }
                 const float m0 = ((lowbias32(rkq[j] + ck) >> ksh) & 0xffffu) >= drop.thresh ? drop.scale : 0.f;
                 const float m1 = ((lowbias32(rkq[j + 1] + ck) >> ksh) & 0xffffu) >= drop.thresh ? drop.scale : 0.f;
                 pu[j >> 1] = pack_bf16x2(p0 * m0, p1 * m1);
@@ -250,8 +267,12 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             } else {
 #pragma unroll
               for (int j = 0; j < 8; j += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -lq[j]));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -lq[j + 1]));
+                float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), c2, -lq[j]));
+                float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), c2, -lq[j + 1]));
+                if constexpr (SEG) {
+                  p0 = (c0 + j >= qlo && c0 + j < qhi) ? p0 : 0.f;
+                  p1 = (c0 + j + 1 >= qlo && c0 + j + 1 < qhi) ? p1 : 0.f;
+                }
                 pu[j >> 1] = pack_bf16x2(p0, p1);
                 du[j >> 1] = pack_bf16x2(p0 * (__uint_as_float(rp[j]) - dq[j]), p1 * (__uint_as_float(rp[j + 1]) - dq[j + 1]));
               }
@@ -311,32 +332,35 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         BTR(5);
         tc::mbar_wait(&bars[1], phase);
         BTR(6);
-        if (tid == 0 && hd == 1 && kt == NT - 1 && item + (int)gridDim.x < n_items)
+        if (tid == 0 && hd == HPB - 1 && kt == NT - 1 && item + (int)gridDim.x < n_items)
           issue_loads(item + gridDim.x);            // every MMA on this item's operands is done: refill during the drain
         tc::fence_after_sync();
         // ---- drain: dV / dK rows of this key tile straight to global, dQ partials into registers
         {
-          uint32_t rv[8], rk[8], q0[8], q1[8];
-          tc::tmem_ld_32x8(lane_base + COL_DV + grp * 8, rv);
-          tc::tmem_ld_32x8(lane_base + COL_DK + grp * 8, rk);
-          tc::tmem_ld_32x8(lane_base + COL_DQ0 + grp * 8, q0);
-          if (NT == 2) tc::tmem_ld_32x8(lane_base + col_dq1 + grp * 8, q1);
+          uint32_t rv[QC], rk[QC], q0[QC], q1[QC];
+          tc::tmem_ld_w<QC>(lane_base + COL_DV + grp * QC, rv);
+          tc::tmem_ld_w<QC>(lane_base + COL_DK + grp * QC, rk);
+          tc::tmem_ld_w<QC>(lane_base + COL_DQ0 + grp * QC, q0);
+          if (NT == 2) tc::tmem_ld_w<QC>(lane_base + col_dq1 + grp * QC, q1);
           tc::tmem_ld_wait();
           if (kok) {
-            __nv_bfloat16* dk = dqkv + (size_t)(t0 + krow) * ldq + H * DH + h * DH + grp * 8;
+            __nv_bfloat16* dk = dqkv + (size_t)(t0 + krow) * ldq + H * DH + h * DH + grp * QC;
             __nv_bfloat16* dv = dk + H * DH;
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(rk[0]) * scale, __uint_as_float(rk[1]) * scale);
-            o.y = pack_bf16x2(__uint_as_float(rk[2]) * scale, __uint_as_float(rk[3]) * scale);
-            o.z = pack_bf16x2(__uint_as_float(rk[4]) * scale, __uint_as_float(rk[5]) * scale);
-            o.w = pack_bf16x2(__uint_as_float(rk[6]) * scale, __uint_as_float(rk[7]) * scale);
-            *reinterpret_cast<uint4*>(dk) = o;
-            o.x = pack_bf16x2(__uint_as_float(rv[0]), __uint_as_float(rv[1])); o.y = pack_bf16x2(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
-            o.z = pack_bf16x2(__uint_as_float(rv[4]), __uint_as_float(rv[5])); o.w = pack_bf16x2(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
-            *reinterpret_cast<uint4*>(dv) = o;
+#pragma unroll
+            for (int j = 0; j < QC; j += 8) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(rk[j]) * scale, __uint_as_float(rk[j + 1]) * scale);
+              o.y = pack_bf16x2(__uint_as_float(rk[j + 2]) * scale, __uint_as_float(rk[j + 3]) * scale);
+              o.z = pack_bf16x2(__uint_as_float(rk[j + 4]) * scale, __uint_as_float(rk[j + 5]) * scale);
+              o.w = pack_bf16x2(__uint_as_float(rk[j + 6]) * scale, __uint_as_float(rk[j + 7]) * scale);
+              *reinterpret_cast<uint4*>(dk + j) = o;
+              o.x = pack_bf16x2(__uint_as_float(rv[j]), __uint_as_float(rv[j + 1])); o.y = pack_bf16x2(__uint_as_float(rv[j + 2]), __uint_as_float(rv[j + 3]));
+              o.z = pack_bf16x2(__uint_as_float(rv[j + 4]), __uint_as_float(rv[j + 5])); o.w = pack_bf16x2(__uint_as_float(rv[j + 6]), __uint_as_float(rv[j + 7]));
+              *reinterpret_cast<uint4*>(dv + j) = o;
+            }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < QC; ++i) {
             accQ[0][i] += __uint_as_float(q0[i]);
             if (NT == 2) accQ[1][i] += __uint_as_float(q1[i]);
           }
@@ -353,10 +377,13 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       for (int t = 0; t < 2; ++t) {
         const int qrow = t * 128 + row_in_tile;
         if (t < NT && qrow < S) {
-          uint4 o;
-          o.x = pack_bf16x2(accQ[t][0] * scale, accQ[t][1] * scale); o.y = pack_bf16x2(accQ[t][2] * scale, accQ[t][3] * scale);
-          o.z = pack_bf16x2(accQ[t][4] * scale, accQ[t][5] * scale); o.w = pack_bf16x2(accQ[t][6] * scale, accQ[t][7] * scale);
-          *reinterpret_cast<uint4*>(dqkv + (size_t)(t0 + qrow) * ldq + h * DH + grp * 8) = o;
+#pragma unroll
+          for (int j = 0; j < QC; j += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(accQ[t][j] * scale, accQ[t][j + 1] * scale); o.y = pack_bf16x2(accQ[t][j + 2] * scale, accQ[t][j + 3] * scale);
+            o.z = pack_bf16x2(accQ[t][j + 4] * scale, accQ[t][j + 5] * scale); o.w = pack_bf16x2(accQ[t][j + 6] * scale, accQ[t][j + 7] * scale);
+            *reinterpret_cast<uint4*>(dqkv + (size_t)(t0 + qrow) * ldq + h * DH + grp * QC + j) = o;
+          }
         }
       }
     }
@@ -378,28 +405,37 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
 
 using namespace eavit;
 
-template <bool DROP>
+template <int DH, bool DROP, bool SEG>
 static int launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& to, const float* lse, const int* seq_start,
-                        int nseq, int H, float scale, void* dqkv, const DropCfg& drop, cudaStream_t st) {
+                        int nseq, int H, float scale, void* dqkv, const DropCfg& drop, int pack, int seg, cudaStream_t st) {
   static bool done = false;
   if (!done) {
-    EAVIT_CUDA(cudaFuncSetAttribute(bt::attention_bwd_t_kernel<DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt::Smem::TOTAL));
+    EAVIT_CUDA(cudaFuncSetAttribute(bt::attention_bwd_t_kernel<DH, DROP, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt::Smem::TOTAL));
     done = true;
   }
-  const int items = nseq * (H / 2);
+  const int items = ((nseq + pack - 1) / pack) * (H / (64 / DH));
   const int grid = items < kNumSMs ? items : kNumSMs;
-  bt::attention_bwd_t_kernel<DROP><<<grid, bt::THREADS, bt::Smem::TOTAL, st>>>(tq, tdo, to, lse, seq_start, nseq, H, scale,
-                                                                               (__nv_bfloat16*)dqkv, drop);
+  bt::attention_bwd_t_kernel<DH, DROP, SEG><<<grid, bt::THREADS, bt::Smem::TOTAL, st>>>(tq, tdo, to, lse, seq_start, nseq, H, scale,
+                                                                                        (__nv_bfloat16*)dqkv, drop, pack, seg);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
+}
+template <int DH>
+static int dispatch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& to, const float* lse, const int* seq_start,
+                          int nseq, int H, float scale, void* dqkv, const DropCfg& drop, int pack, int seg, cudaStream_t st) {
+  if (pack > 1)
+    return drop.thresh ? launch_bwd_t<DH, true, true>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, pack, seg, st)
+                       : launch_bwd_t<DH, false, true>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, pack, seg, st);
+  return drop.thresh ? launch_bwd_t<DH, true, false>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, 1, 0, st)
+                     : launch_bwd_t<DH, false, false>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, 1, 0, st);
 }
 
 extern "C" int eavit_attention_bwd_tct(const void* qkv, const void* out, const void* dout, const float* lse,
                                        const int* seq_start, int nseq, int max_len, long long total_tokens, int H, int Dh,
                                        float scale, void* dqkv, float drop_p, unsigned long long drop_seed, void* stream) {
   EAVIT_CHECK_ARG(qkv && out && dout && lse && seq_start && dqkv && nseq > 0 && H > 0 && total_tokens > 0);
-  EAVIT_CHECK_ARG(Dh == 32 && H % 2 == 0 && max_len > 0 && max_len <= bt::MAXQ);
-  EAVIT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
+  EAVIT_CHECK_ARG((Dh == 32 && H % 2 == 0 && max_len <= bt::MAXQ) || (Dh == 64 && max_len <= bt::MAXQ64));
+  EAVIT_CHECK_ARG(max_len > 0 && drop_p >= 0.f && drop_p < 1.f);
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
@@ -411,8 +447,12 @@ extern "C" int eavit_attention_bwd_tct(const void* qkv, const void* out, const v
   rc = make_tmap_bf16_2d(&to, out, (uint64_t)H * Dh, (uint64_t)total_tokens, (uint64_t)H * Dh * 2, bt::BOX_ROWS);
   if (rc) return rc;
   const DropCfg drop = make_drop(drop_p, drop_seed);
-  return drop.thresh ? launch_bwd_t<true>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, st)
-                     : launch_bwd_t<false>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, st);
+  // sequences per work item: > 1 only when every sequence has the same even length and several fit into one item
+  const int limit = Dh == 32 ? bt::MAXQ : bt::MAXQ64;
+  int pack = 1;
+  if (total_tokens == (long long)nseq * max_len && (max_len & 1) == 0 && 2 * max_len <= limit) pack = limit / max_len;
+  if (Dh == 32) return dispatch_bwd_t<32>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, pack, max_len, st);
+  return dispatch_bwd_t<64>(tq, tdo, to, lse, seq_start, nseq, H, scale, dqkv, drop, pack, max_len, st);
 }
 
 #ifdef EAVIT_TRACE

@@ -331,7 +331,7 @@ def attention_fwd(qkv, seq_start, nseq, max_len, H, Dh, scale, out, lse, drop_p:
 
 
 def attention_bwd(qkv, out, dout, lse, seq_start, nseq, max_len, H, Dh, scale, dqkv, drop_p: float = 0.0, drop_seed: int = 0):
-    if Dh == 32 and max_len <= 208 and H % 2 == 0 and os.environ.get("EAVIT_ATTN_BWD", "t") == "t":
+    if ((Dh == 32 and max_len <= 208 and H % 2 == 0) or (Dh == 64 and max_len <= 128)) and os.environ.get("EAVIT_ATTN_BWD", "t") == "t":
         if _PROF is not None:      # S, dP (recomputed), dV, dK, dQ: 5 contractions of 2 * S^2 * Dh
             _FLOPS_HINT["eavit_attention_bwd_tct"] = 10.0 * nseq * H * max_len * max_len * Dh
         call("eavit_attention_bwd_tct", qkv, out, dout, lse, seq_start, nseq, max_len, qkv.shape[0], H, Dh, scale, dqkv,

@@ -69,8 +69,8 @@ BWD_CASES = [([196, 197, 196, 197], 8, 32), ([50, 50, 50], 2, 64), ([1, 17, 128,
 @pytest.mark.parametrize("lens,H,Dh", BWD_CASES)
 @pytest.mark.parametrize("impl", ["v1", "tc", "tct"])
 def test_attention_backward(ops, lens, H, Dh, impl):
-    if impl == "tct" and (Dh != 32 or max(lens) > 208 or H % 2):
-        pytest.skip("transposed-score backward: Dh = 32, up to 208 tokens")
+    if impl == "tct" and not ((Dh == 32 and max(lens) <= 208 and H % 2 == 0) or (Dh == 64 and max(lens) <= 128)):
+        pytest.skip("transposed-score backward: Dh = 32 up to 208 tokens, Dh = 64 up to 128")
     torch.manual_seed(sum(lens) + H + 1)
     starts = [0]
     for n in lens:
