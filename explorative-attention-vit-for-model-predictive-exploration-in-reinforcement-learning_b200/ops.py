@@ -65,8 +65,23 @@ def _p(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr())
 
 
+# The current stream's raw handle, once per launch (~150 launches per optimiser step): torch.cuda.current_stream() builds a
+# Stream object and re-checks device availability on every call (14 us, 38 % of the host time of a step); the raw query is
+# what torch itself uses underneath.
+try:
+    _raw_stream, _cur_dev = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice
+    _raw_stream  # noqa: B018
+
+
+    def _stream_handle() -> int:
+        return _raw_stream(_cur_dev())
+except AttributeError:                                     # pragma: no cover  (other torch builds)
+    def _stream_handle() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+
 def _st():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(_stream_handle())
 
 
 # ------------------------------------------------------------------------------------------- numerics
@@ -290,9 +305,9 @@ def call(name: str, *args):
             conv.append(a)
     if _PROF is not None:
         with _Timed(name[len("eavit_"):], _FLOPS_HINT.pop(name, 0.0)):
-            rc = fn(*conv, torch.cuda.current_stream().cuda_stream)
+            rc = fn(*conv, _stream_handle())
     else:
-        rc = fn(*conv, torch.cuda.current_stream().cuda_stream)
+        rc = fn(*conv, _stream_handle())
     if rc != 0:
         check(rc, name[len("eavit_"):])
 
