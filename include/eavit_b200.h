@@ -170,7 +170,7 @@ int eavit_attention_bwd(const void* qkv, const void* out, const void* dout, cons
 int eavit_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const int* seq_start, int nseq, int max_len,
                            long long total_tokens, int H, int Dh, float scale, void* dqkv, float drop_p,
                            unsigned long long drop_seed, void* stream);
-/* Backward with transposed scores (keys on the TMEM lanes; P~^T and dS^T are TMEM-resident A operands of dV / dK, one
+/* Backward of Attention.forward (vit.py:60-73 / HF ViTSelfAttention) with transposed scores (keys on the TMEM lanes; P~^T and dS^T are TMEM-resident A operands of dV / dK, one
  * softmax pass per key tile): Dh = 32 with max_len <= 208 or Dh = 64 with max_len <= 128; equal even-length sequences are
  * packed per work item under a block-diagonal mask.  Needs `out` (D = rowsum(out * dout), formed in-kernel). */
 int eavit_attention_bwd_tct(const void* qkv, const void* out, const void* dout, const float* lse, const int* seq_start, int nseq,
