@@ -137,3 +137,19 @@ def test_torch_custom_ops_are_registered_and_cuda_only():
     x = torch.randn(4, 8).bfloat16()
     with pytest.raises(NotImplementedError):
         torch.ops.eavit_b200.linear(x, x, None)
+
+
+def test_rnd_gradient_slice_of_the_flat_store():
+    """The early all-reduce covers exactly the predictor's contiguous block of the flat gradient, or nothing."""
+    from eavit_b200.agents import RNDAgent
+
+    class S:
+        pass
+    st = S(); st.offsets = {"model.a": 0, "model.b": 8, "rnd.predictor.0.weight": 16, "rnd.predictor.0.bias": 48}; st.numel = 56
+    assert RNDAgent._rnd_grad_range(st) == (16, 56)
+    st = S(); st.offsets = {"rnd.predictor.0.weight": 0, "rnd.predictor.0.bias": 32, "model.a": 40}; st.numel = 48
+    assert RNDAgent._rnd_grad_range(st) == (0, 40)
+    st = S(); st.offsets = {"rnd.predictor.0.weight": 0, "model.a": 32, "rnd.predictor.0.bias": 40}; st.numel = 48
+    assert RNDAgent._rnd_grad_range(st) is None                 # interleaved: fall back to one all-reduce of everything
+    st = S(); st.offsets = {"model.a": 0}; st.numel = 8
+    assert RNDAgent._rnd_grad_range(st) is None
