@@ -30,7 +30,16 @@ from .utils import Env_action_space_type, Logger
 
 
 class FusedAdam(torch.optim.Optimizer):
-    """torch.optim.Adam(lr) semantics (agents.py:129) as one fused launch over the agent's flat parameter store."""
+    """torch.optim.Adam(lr) semantics (agents.py:129) as one fused launch over the agent's flat parameter store.
+
+    ``state_dict`` / ``load_state_dict`` speak torch.optim.Adam's own layout (``state[i] = {step, exp_avg, exp_avg_sq}``,
+    ``param_groups[0]['params'] = [0..n)``), so the checkpoint entry ``agent.optimizer.state_dict`` (train.py:931) is a
+    dict ``torch.optim.Adam.load_state_dict`` accepts and vice versa.  Index i is the i-th tensor of the flat store
+    (``eavit_param_names`` records the names).  The reference builds its optimiser from a *set* of parameters
+    (agents.py:141-164), so the index -> tensor mapping of a reference-written state is the hash order of one process and
+    is recorded nowhere: such a state is matched by shape, in store order among equal shapes, with a warning."""
+
+    _TORCH_GROUP_DEFAULTS = dict(amsgrad=False, maximize=False, foreach=None, capturable=False, differentiable=False, fused=None)
 
     def __init__(self, params, lr, agent):
         super().__init__(list(params), dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0))
@@ -42,18 +51,77 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
-        rt = self._agent().runtime()
-        rt.store.adam_step(g["lr"], 1.0, g["betas"][0], g["betas"][1], g["eps"])
+        ag = self._agent()
+        rt = ag.runtime()
+        rt.store.adam_step(g["lr"], 1.0, g["betas"][0], g["betas"][1], g["eps"], ranges=ag._trainable_ranges(rt))
         rt.rnd_pred.refresh_weights()
 
     def state_dict(self):
         st = self._agent().runtime().store
-        return dict(flat_exp_avg=st.m.clone(), flat_exp_avg_sq=st.v.clone(), step=st.step.clone(),
-                    names=list(st.shapes.keys()), param_groups=[{k: v for k, v in self.param_groups[0].items() if k != "params"}])
+        names = list(st.shapes.keys())
+        step = st.step.to(torch.float32).cpu().reshape(())                 # torch keeps `step` as a float32 CPU scalar tensor
+        state = {i: {"step": step.clone(), "exp_avg": st._view(st.m, n).clone(), "exp_avg_sq": st._view(st.v, n).clone()}
+                 for i, n in enumerate(names)}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        for k, v in self._TORCH_GROUP_DEFAULTS.items():
+            group.setdefault(k, v)
+        group["params"] = list(range(len(names)))
+        return {"state": state, "param_groups": [group], "eavit_param_names": names}
 
     def load_state_dict(self, sd):
         st = self._agent().runtime().store
-        st.m.copy_(sd["flat_exp_avg"]); st.v.copy_(sd["flat_exp_avg_sq"]); st.step.copy_(sd["step"])
+        names = list(st.shapes.keys())
+        if "flat_exp_avg" in sd:                                           # round-1 private format
+            if list(sd.get("names", names)) != names or sd["flat_exp_avg"].numel() != st.numel:
+                raise ValueError("FusedAdam.load_state_dict: flat optimiser state was written for a different tensor layout")
+            st.m.copy_(sd["flat_exp_avg"]); st.v.copy_(sd["flat_exp_avg_sq"]); st.step.copy_(sd["step"])
+            return
+        state, groups = sd["state"], sd["param_groups"]
+        saved = sd.get("eavit_param_names")
+        if saved is not None:
+            if len(saved) != len(groups[0]["params"]):
+                raise ValueError("FusedAdam.load_state_dict: eavit_param_names does not match param_groups")
+            index_of = {n: i for n, i in zip(saved, groups[0]["params"])}
+            unknown = [n for n in saved if n not in st.shapes]
+            if unknown:
+                raise ValueError(f"FusedAdam.load_state_dict: state names unknown to this agent: {unknown[:4]}")
+        else:
+            # reference-written state: indices follow that process's set order; match by shape, store order within a shape
+            by_shape = {}
+            for i in groups[0]["params"]:
+                e = state.get(i)
+                if e is not None:
+                    by_shape.setdefault(tuple(e["exp_avg"].shape), []).append(i)
+            index_of = {}
+            ambiguous = False
+            for n in names:
+                cand = by_shape.get(tuple(st.shapes[n]), [])
+                if cand:
+                    ambiguous |= len(cand) > 1
+                    index_of[n] = cand.pop(0)
+            if ambiguous:
+                self._agent().logger.log_msg_to_both_console_and_file(
+                    "FusedAdam.load_state_dict: optimiser state without parameter names (written by the reference from a set of "
+                    "parameters): Adam moments of equal-shaped tensors were assigned in store order", only_rank_0=True)
+        step = 0.0
+        loaded = 0
+        for n in names:
+            e = state.get(index_of.get(n, -1))
+            if e is None:
+                continue                                                   # a tensor the writer never stepped (frozen)
+            if tuple(e["exp_avg"].shape) != tuple(st.shapes[n]):
+                raise ValueError(f"FusedAdam.load_state_dict: {n}: exp_avg shape {tuple(e['exp_avg'].shape)} != {tuple(st.shapes[n])}")
+            st._view(st.m, n).copy_(e["exp_avg"])
+            st._view(st.v, n).copy_(e["exp_avg_sq"])
+            step = max(step, float(e["step"]))
+            loaded += 1
+        if state and not loaded:
+            raise ValueError("FusedAdam.load_state_dict: no state entry matches a tensor of this agent")
+        st.step.fill_(int(step))
+        g = self.param_groups[0]
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in groups[0]:
+                g[k] = tuple(groups[0][k]) if k == "betas" else groups[0][k]
 
 
 class _CapturedCall:
@@ -132,8 +200,14 @@ class RNDAgent(nn.Module):
 
     def runtime(self) -> Runtime:
         if self._rt is None or not self._rt.valid():
+            old = self._rt
             self._rt = Runtime(self, "", n_actions=self.output_size,
                                ext_uses_int_critic=self.model.ViT_implementation_type == ViT_IMPLEMENTATION.HG_ViT)
+            if old is not None and not self._rt.store.adopt_optimizer_state(old.store):
+                # a rebuild (module.to(), load_state_dict(assign=True)) must not silently restart Adam from zero moments
+                raise RuntimeError("eavit_b200.RNDAgent: the parameter layout changed under a live optimiser; "
+                                   "rebuild the agent (or reload the optimiser state) instead")
+            self._frozen_key = None
             if dist.is_dist():
                 self.world_size, self.rank = dist.world()
                 # start every rank from rank 0's weights (what DDP's constructor did at train.py:243)
@@ -158,12 +232,18 @@ class RNDAgent(nn.Module):
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = _CapturedCall(fn, x)
+        # the replay overwrites the (kind, batch) scratch activations and, with dropout, bumps the device epoch word:
+        # a pending autograd backward of the same buffers must notice (model.Runtime.check_gen)
+        rt._bump_gen("ac" if kind == "act" else "rnd", x.shape[0])
+        if kind == "act" and rt.dropout_active():
+            rt._epoch_gen = getattr(rt, "_epoch_gen", 0) + 1
         return g(x)
 
     def _act_device(self, x: torch.Tensor) -> torch.Tensor:
         rt = self.runtime()
         if rt.dropout_active():
             call("eavit_dropout_epoch_bump")
+            rt._epoch_gen = getattr(rt, "_epoch_gen", 0) + 1
         pol, ve, vi = rt.ac_forward(x, x.shape[0])
         return torch.cat((pol.reshape(-1), ve, vi))                       # one packed D2H read instead of four
 
@@ -224,6 +304,21 @@ class RNDAgent(nn.Module):
                 rng = (lo, hi)
         st._rnd_range = rng
         return rng
+
+    def _trainable_ranges(self, rt):
+        """None when every tensor of the store trains; else the merged flat ranges of the tensors that do.  Frozen =
+        ``requires_grad is False`` on the Parameter -- what train.py:261-263 sets on ``model.feature.*`` when the config
+        says ``freeze_shared_backbone = True`` (torch.optim.Adam then skips those tensors, nn.utils.clip_grad_norm_ and
+        global_grad_norm_ ignore them)."""
+        key = tuple(p.requires_grad for n, p in rt.params.items() if n in rt.store.shapes)
+        if getattr(self, "_frozen_key", None) != key:
+            frozen = rt.frozen_names()
+            self._frozen_key = key
+            self._frozen_ranges = rt.store.name_ranges(frozen) if frozen else None
+            self._train_ranges = rt.store.name_ranges([n for n in rt.store.shapes if n not in set(frozen)]) if frozen else None
+            self._backbone_frozen = bool(frozen) and all(
+                (not p.requires_grad) for n, p in rt.params.items() if n.startswith("model.feature."))
+        return self._train_ranges
 
     def _side_stream(self, rt):
         s = getattr(rt, "_side", None)
@@ -303,9 +398,13 @@ class RNDAgent(nn.Module):
         pol, ve, vi = rt.ac_forward(R["states"], B, idx)
         call("eavit_ppo_loss", pol, w["old"], w["y"], w["adv"], ve, vi, w["te"], w["ti"], B, A, float(self.ppo_eps),
              float(self.ent_coef), gs, w["dpol"], w["dv"][B:], w["dv"][:B], w["stats"])
-        rt.ac_backward(w["dpol"], w["dv"])
+        train_ranges = self._trainable_ranges(rt)
+        rt.ac_backward(w["dpol"], w["dv"], backbone=not (train_ranges is not None and self._backbone_frozen))
         if side is not None:
             cur.wait_stream(side)
+        if train_ranges is not None:                                     # frozen tensors: no gradient (torch leaves .grad = None)
+            for lo, hi in self._frozen_ranges:
+                call("eavit_zero", st.grad[lo:hi], (hi - lo) * 4)
         call("eavit_add_f32", w["stats"], w["rnd_stats"], w["stats"], 16)
         if self.world_size > 1:                                          # NCCL all-reduce (sum); the mean is applied inside Adam
             if early is None:
@@ -321,7 +420,7 @@ class RNDAgent(nn.Module):
             call("eavit_clip_by_norm", st.grad, st.numel, nrm, float(self.max_grad_norm) * self.world_size)
         g = self.optimizer.param_groups[0]
         if apply:
-            st.adam_step(g["lr"], 1.0 / self.world_size, g["betas"][0], g["betas"][1], g["eps"])
+            st.adam_step(g["lr"], 1.0 / self.world_size, g["betas"][0], g["betas"][1], g["eps"], ranges=train_ranges)
             rt.rnd_pred.refresh_weights()
         if stats_out is not None:
             stats_out.copy_(w["stats"])

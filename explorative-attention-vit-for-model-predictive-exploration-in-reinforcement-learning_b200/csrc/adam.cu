@@ -81,6 +81,25 @@ int eavit_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, 
   return EAVIT_OK;
 }
 
+// The same update for ONE contiguous range of the flat buffers without advancing the step counter: a store with frozen
+// tensors (train.py:261-263 sets requires_grad = False on model.feature.*; torch.optim.Adam then skips them) is updated
+// as eavit_adam_tick + one eavit_adam_apply per trainable range.
+int eavit_adam_tick(long long* step, void* stream) {
+  EAVIT_CHECK_ARG(step != nullptr);
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_adam_apply(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, const long long* step, float lr,
+                     float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  EAVIT_CHECK_ARG(p && g && m && v && step && n > 0 && n % 4 == 0);
+  adam_kernel<<<cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n / 4, step, lr, beta1, beta2, eps,
+                                                                  grad_scale);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
 int eavit_sumsq_f32(const float* x, long long n, float* out, void* stream) {
   EAVIT_CHECK_ARG(x && out && n > 0 && n % 4 == 0);
   int grid = cdiv(n / 4, 256);

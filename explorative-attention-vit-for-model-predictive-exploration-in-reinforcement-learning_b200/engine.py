@@ -102,9 +102,43 @@ class ParamStore:
     def zero_grad(self):
         call("eavit_zero", self.grad, self.numel * 4)
 
-    def adam_step(self, lr: float, grad_scale: float = 1.0, beta1=0.9, beta2=0.999, eps=1e-8):
-        call("eavit_adam_step", self.flat, self.grad, self.m, self.v, self.flat_bf16, self.numel, self.step,
-             lr, beta1, beta2, eps, grad_scale)
+    def adam_step(self, lr: float, grad_scale: float = 1.0, beta1=0.9, beta2=0.999, eps=1e-8, ranges=None):
+        """One fused Adam launch over the whole flat buffer, or -- with frozen tensors -- one step-counter tick plus one
+        launch per contiguous trainable range (``trainable_ranges``): frozen tensors keep weights AND moments, like
+        torch.optim.Adam skipping parameters without a gradient (train.py:261-263)."""
+        if ranges is None:
+            call("eavit_adam_step", self.flat, self.grad, self.m, self.v, self.flat_bf16, self.numel, self.step,
+                 lr, beta1, beta2, eps, grad_scale)
+            return
+        call("eavit_adam_tick", self.step)
+        for lo, hi in ranges:
+            call("eavit_adam_apply", self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.flat_bf16[lo:hi],
+                 hi - lo, self.step, lr, beta1, beta2, eps, grad_scale)
+
+    def name_ranges(self, names) -> List[Tuple[int, int]]:
+        """Merged [lo, hi) element ranges (padding included) covered by ``names``, in offset order."""
+        order = sorted(self.offsets.items(), key=lambda kv: kv[1])
+        ends = [o for _, o in order[1:]] + [self.numel]
+        pick = set(names)
+        out: List[Tuple[int, int]] = []
+        for (n, lo), hi in zip(order, ends):
+            if n not in pick:
+                continue
+            if out and out[-1][1] == lo:
+                out[-1] = (out[-1][0], hi)
+            else:
+                out.append((lo, hi))
+        return out
+
+    def adopt_optimizer_state(self, old: "ParamStore") -> bool:
+        """Carry Adam moments and the step counter over from the store this one replaces (a Runtime rebuild after
+        ``.to()`` / ``load_state_dict(assign=True)``).  Returns False when the layouts differ."""
+        if not (self.trainable and old.trainable) or list(self.shapes.items()) != list(old.shapes.items()):
+            return False
+        self.m.copy_(old.m)
+        self.v.copy_(old.v)
+        self.step.copy_(old.step)
+        return True
 
 
 class _Buffers:

@@ -70,9 +70,16 @@ class StepCollector:
         self.montezuma = montezuma
         self.ring = ring
         self._slot = 0
-        self._stage = torch.empty(self.E, stack, image, image, dtype=torch.uint8)
-        if self.device is not None and self.device.type == "cuda":
-            self._stage = self._stage.pin_memory()
+        # Two pinned staging batches used alternately, each guarded by the CUDA event of its last upload: the host never
+        # rewrites a buffer whose asynchronous H2D copy may still be in flight (a device-side consumer such as
+        # DeviceRollout.add does not force a sync between steps the way get_action(...).cpu() does).
+        cuda = self.device is not None and self.device.type == "cuda"
+        self._stages = [torch.empty(self.E, stack, image, image, dtype=torch.uint8) for _ in range(2 if cuda else 1)]
+        if cuda:
+            self._stages = [t.pin_memory() for t in self._stages]
+        self._copied = [None] * len(self._stages)
+        self._cur = 0
+        self._stage = self._stages[0]
         self._stage_np = self._stage.numpy()
 
     def initial_states(self):
@@ -86,6 +93,15 @@ class StepCollector:
             st = self._stage.clone()
         else:
             st = self._stage.to(self.device, non_blocking=True)
+            if self.device.type == "cuda":
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self._copied[self._cur] = ev
+                self._cur ^= 1                               # the next step fills the other buffer ...
+                if self._copied[self._cur] is not None:
+                    self._copied[self._cur].synchronize()    # ... once its own upload (two steps ago) has completed
+                self._stage = self._stages[self._cur]
+                self._stage_np = self._stage.numpy()
         return st, st[:, self.stack - 1:self.stack]
 
     def step(self, actions) -> dict:

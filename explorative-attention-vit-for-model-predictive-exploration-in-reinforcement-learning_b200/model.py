@@ -164,14 +164,36 @@ class Runtime:
         self._drop_calls += 1
         return self._drop_seed0 + self._drop_calls
 
+    def _bump_gen(self, kind: str, B: int) -> int:
+        """Activations live in per-batch-size scratch buffers, not in the autograd graph: every forward of (kind, B)
+        gets a generation number so that a backward whose buffers were overwritten since can refuse to run."""
+        g = self._gens = getattr(self, "_gens", {})
+        g[(kind, B)] = g.get((kind, B), 0) + 1
+        return g[(kind, B)]
+
+    def check_gen(self, kind: str, B: int, gen: int, epoch: int):
+        if self._gens.get((kind, B)) != gen:
+            raise RuntimeError(f"eavit_b200: backward of a {kind} forward (batch {B}) whose activations were overwritten by a later "
+                               "forward of the same batch size -- run backward before the next forward (or use RNDAgent.train_step)")
+        if epoch != getattr(self, "_epoch_gen", 0):
+            raise RuntimeError("eavit_b200: a graph-replayed get_action() advanced the dropout epoch between this forward and its "
+                               "backward; the regenerated masks would differ")
+
     def ac_forward(self, state: torch.Tensor, B: int, sample_idx=None):
+        self._bump_gen("ac", B)
         feat = self.encoder.forward(state, B, sample_idx, drop_base=self.next_drop_base())
         return self.heads.forward(feat)          # policy [B,A], value_ext [B], value_int [B]  (views of scratch)
 
-    def ac_backward(self, dpol: torch.Tensor, dv: torch.Tensor):
-        """dv fp32 [2B] = (d value_int | d value_ext)."""
+    def ac_backward(self, dpol: torch.Tensor, dv: torch.Tensor, backbone: bool = True):
+        """dv fp32 [2B] = (d value_int | d value_ext).  ``backbone=False``: the shared feature extractor is frozen
+        (train.py:261-263) -- only the heads are differentiated."""
         dfeat = self.heads.backward(dpol, dv)
-        self.encoder.backward(dfeat)
+        if backbone:
+            self.encoder.backward(dfeat)
+
+    def frozen_names(self) -> List[str]:
+        """Tensors of the trainable store whose Parameter has requires_grad = False (e.g. freeze_shared_backbone)."""
+        return [n for n in self.store.shapes if not self.params[n].requires_grad]
 
 
 def _runtime_for(module: nn.Module, prefix: str, **kw) -> Runtime:
@@ -207,11 +229,13 @@ class _ActorCriticFn(torch.autograd.Function):
         B = state.shape[0]
         pol, ve, vi = rt.ac_forward(state, B)
         ctx.rt, ctx.B = rt, B
+        ctx.gen, ctx.epoch = rt._gens[("ac", B)], getattr(rt, "_epoch_gen", 0)
         return pol.clone(), ve.clone().unsqueeze(1), vi.clone().unsqueeze(1)
 
     @staticmethod
     def backward(ctx, dpol, dve, dvi):
         rt, B = ctx.rt, ctx.B
+        rt.check_gen("ac", B, ctx.gen, ctx.epoch)
         dev = rt.device
         dpol = torch.zeros(B, rt.heads.A, device=dev) if dpol is None else dpol.contiguous().float()
         dv = torch.zeros(2 * B, device=dev)
@@ -304,14 +328,16 @@ class _RNDFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, rt: Runtime, obs):
         B = obs.shape[0]
+        ctx.gen = rt._bump_gen("rnd", B)
         pred = rt.rnd_pred.forward(obs, B).clone()
         tgt = rt.rnd_tgt.forward(obs, B).clone()
-        ctx.rt = rt
+        ctx.rt, ctx.B = rt, B
         return pred, tgt
 
     @staticmethod
     def backward(ctx, dpred, dtgt):
         if dpred is not None:
+            ctx.rt.check_gen("rnd", ctx.B, ctx.gen, getattr(ctx.rt, "_epoch_gen", 0))
             ctx.rt.rnd_pred.backward(dpred.contiguous().to(torch.bfloat16))
         return None, None, None
 
@@ -356,4 +382,5 @@ class RNDModel(nn.Module):
         if torch.is_grad_enabled():
             return _RNDFn.apply(anchor, rt, x)
         B = x.shape[0]
+        rt._bump_gen("rnd", B)
         return rt.rnd_pred.forward(x, B).clone(), rt.rnd_tgt.forward(x, B).clone()

@@ -268,6 +268,8 @@ _SPECS = {
     "eavit_nhwc_to_flat": "piiip",
     "eavit_flat_to_nhwc_lrelu": "ppiiip",
     "eavit_adam_step": "ppppplpfffff",
+    "eavit_adam_tick": "p",
+    "eavit_adam_apply": "ppppplpfffff",
     "eavit_sumsq_f32": "plp",
     "eavit_clip_by_norm": "plpf",
 }

@@ -274,6 +274,12 @@ int eavit_flat_to_nhwc_lrelu(const void* dflat_bf16, const void* act_bf16, int B
 /* ------------------------------------------------------------------ optimiser (agents.py:129,:508) */
 int eavit_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, long long* step, float lr,
                     float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* Frozen tensors (train.py:261-263: requires_grad = False on model.feature.*; torch.optim.Adam skips tensors without a
+ * gradient): eavit_adam_tick advances the shared step counter once, eavit_adam_apply updates one contiguous trainable
+ * range [p, p+n) of the flat buffers without touching the counter.  eavit_adam_step == tick + apply over everything. */
+int eavit_adam_tick(long long* step, void* stream);
+int eavit_adam_apply(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, const long long* step, float lr,
+                     float beta1, float beta2, float eps, float grad_scale, void* stream);
 int eavit_sumsq_f32(const float* x, long long n, float* out, void* stream);                       /* utils.py:141-170 */
 int eavit_clip_by_norm(float* g, long long n, const float* sumsq, float max_norm, void* stream);  /* agents.py:497-499 */
 

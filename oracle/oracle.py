@@ -401,6 +401,42 @@ def ppo_rnd_loss(P, cfg: OracleConfig, s_batch, target_ext, target_int, y, adv, 
     return loss, {k: float(v.detach()) for k, v in terms.items()}, (policy, v_ext, v_int)
 
 
+def ppo_rnd_backward_chunked(P, cfg: OracleConfig, s_batch, target_ext, target_int, y, adv, next_obs, old_logits, mask,
+                             chunk: int = 128):
+    """The same minibatch loss and gradients as ``ppo_rnd_loss(...)[0].backward()``, evaluated ``chunk`` samples at a time
+    (a 512-sample minibatch of the cfg3 model keeps ~10 GB of fp32 autograd state otherwise).  Every PPO term is a mean
+    over the minibatch (agents.py:474-483) and the RND term a masked sum over a minibatch-wide count (agents.py:338), so
+    the chunk losses recombine exactly: PPO terms weighted n_c / B, the RND term by max(sum mask_c, 1) / max(sum mask, 1).
+    The actor-critic and the RND predictor share no parameter, so each part is differentiated with respect to its own
+    tensors only.  Accumulates into ``P[k].grad``; returns the dict of scalar terms."""
+    B = len(s_batch)
+    msum = max(float(mask.sum()), 1.0)
+    ac_params = [P[k] for k in P if k.startswith("model.") and P[k].requires_grad]
+    rnd_params = [P[k] for k in P if k.startswith("rnd.predictor.") and P[k].requires_grad]
+    acc = dict(actor=0.0, critic_ext=0.0, critic_int=0.0, entropy=0.0, rnd=0.0)
+    for lo in range(0, B, chunk):
+        sl = slice(lo, min(B, lo + chunk))
+        w_ppo = (sl.stop - sl.start) / B
+        w_rnd = max(float(mask[sl].sum()), 1.0) / msum
+        loss, terms, _ = ppo_rnd_loss(P, cfg, s_batch[sl], target_ext[sl], target_int[sl], y[sl], adv[sl], next_obs[sl],
+                                      old_logits[sl], mask[sl])
+        # one graph, two differently weighted parts: d loss / d(actor-critic) carries only the PPO terms, d loss / d(predictor)
+        # only the RND term
+        g_ac = torch.autograd.grad(loss, ac_params, retain_graph=True, allow_unused=True)
+        g_rnd = torch.autograd.grad(loss, rnd_params, allow_unused=True)
+        for p_, g in zip(ac_params, g_ac):
+            if g is not None:
+                p_.grad = g * w_ppo if p_.grad is None else p_.grad + g * w_ppo
+        for p_, g in zip(rnd_params, g_rnd):
+            if g is not None:
+                p_.grad = g * w_rnd if p_.grad is None else p_.grad + g * w_rnd
+        for k in ("actor", "critic_ext", "critic_int", "entropy"):
+            acc[k] += terms[k] * w_ppo
+        acc["rnd"] += terms["rnd"] * w_rnd
+    acc["loss"] = acc["actor"] + 0.5 * (acc["critic_ext"] + acc["critic_int"]) - cfg.ent_coef * acc["entropy"] + acc["rnd"]
+    return acc
+
+
 def trainable_names(P) -> list:
     """agents.py:141-164: model.* and rnd.predictor.* (rnd.target is frozen, model.py:453-455)."""
     return [k for k in P if k.startswith("model.") or k.startswith("rnd.predictor.")]

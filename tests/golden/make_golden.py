@@ -58,6 +58,20 @@ def import_reference(conf_path: str):
     return agents, model, utils, vit
 
 
+def HG_FULL_CFG():
+    from oracle import oracle as O
+    return O.OracleConfig(impl="hg", patch=12, dim=1024, depth=12, heads=16, dim_head=64, mlp_dim=3072, ln_eps=1e-12,
+                          lr=1e-4, epoch=1, mini_batch=4)
+
+
+def hg_full_inputs():
+    """8 synthetic 4x84x84 frames (/255) and the weights of the scalar the gradient is taken of."""
+    rng = np.random.default_rng(31)
+    state = np.float32(rng.integers(0, 256, (8, 4, 84, 84), dtype=np.uint8)) / 255.0
+    w = rng.normal(size=(8, 18)).astype(np.float32)
+    return state, w
+
+
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "lucid"
     import torch
@@ -79,6 +93,15 @@ def main():
                            "extracted_feature_embedding_dim": 128, "NumStep": 16, "MiniBatch": 4, "Epoch": 1})
         cfg = O.OracleConfig(impl="hg", patch=12, dim=128, depth=2, heads=2, dim_head=64, mlp_dim=256,
                              ln_eps=1e-12, lr=1e-3, epoch=1, mini_batch=4)
+    elif which == "hg_full":
+        # the SHIPPED vit_hg size (configs/vit_hg_explorative.conf here; reference keys ViTHG_* of
+        # configs/expGlados3/Montezuma/config_originalRND_NoSSL_VitExplorativeAttnLucidrains.conf:36-47): 1024 / 12 L / 16 h / 3072
+        conf = write_conf({"ViT_implementation_type": 1, "ViTHG_hidden_size": 1024, "ViTHG_num_hidden_layers": 12,
+                           "ViTHG_num_attention_heads": 16, "ViTHG_intermediate_size": 3072,
+                           "ViTHG_PreProcHeight": 84, "ViTHG_StateStackSize": 4, "ViTHG_patch_size": 12,
+                           "ViTHG_hidden_dropout_prob": 0.0, "ViTHG_attention_probs_dropout_prob": 0.0,
+                           "extracted_feature_embedding_dim": 1024, "NumStep": 16, "MiniBatch": 4, "Epoch": 1})
+        cfg = HG_FULL_CFG()
     elif which == "init":
         conf = write_conf({"ViTlucidrains_dropout": 0.0, "ViTlucidrains_emb_dropout": 0.0})
         cfg = O.OracleConfig()
@@ -88,7 +111,7 @@ def main():
     agents, model, utils, vit = import_reference(conf)
     from utils import Logger, Env_action_space_type
 
-    if which == "hg":
+    if which in ("hg", "hg_full"):
         import vit_hg
         # transformers 5.x dropped get_head_mask (SURVEY 8c shim); arithmetic unchanged
         vit_hg.ViT_ExplorativeAttn.get_head_mask = lambda self, hm, n, *a, **k: [None] * n
@@ -116,6 +139,20 @@ def main():
         assert tuple(sd[k].shape) == tuple(P[k].shape), k
     agent.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
     agent.set_mode("train")   # as train.py:272; dropout keys are 0 so train == eval numerics
+
+    if which == "hg_full":
+        # forward + full backward of the shipped-size HF-style ViT on 8 samples: outputs and per-tensor gradient digests
+        state, w = hg_full_inputs()
+        agent.optimizer.zero_grad()
+        pol, ve, vi = agent.model(torch.tensor(state))
+        ((pol * torch.tensor(w)).sum() + 3.0 * ve.sum() + 2.0 * vi.sum()).backward()
+        G = {"fwd_policy": pol.detach().numpy(), "fwd_value_ext": ve.detach().numpy(), "fwd_value_int": vi.detach().numpy()}
+        for k, p_ in agent.named_parameters():
+            if k.startswith("model.") and p_.grad is not None:
+                G["grad/" + k] = digest(p_.grad.numpy())
+        np.savez_compressed(os.path.join(out_dir, "golden_hg_full.npz"), **G)
+        print("wrote golden_hg_full.npz", len(G), "entries")
+        return
 
     G = {}
     # ---- forward: CnnActorCriticNetwork / get_action / compute_intrinsic_reward -----------------

@@ -110,3 +110,44 @@ def test_train_model_matches_reference(golden_dir, which):
     P0 = O.init_params(cfg, seed=7)
     k = "model.actor.2.weight"
     assert np.abs(digest(P0[k].numpy()) - G["upd/" + k]).max() > 1e-4
+
+
+def hg_full_cfg():
+    return O.OracleConfig(impl="hg", patch=12, dim=1024, depth=12, heads=16, dim_head=64, mlp_dim=3072, ln_eps=1e-12,
+                          lr=1e-4, epoch=1, mini_batch=4)
+
+
+def hg_full_inputs():
+    rng = np.random.default_rng(31)
+    state = np.float32(rng.integers(0, 256, (8, 4, 84, 84), dtype=np.uint8)) / 255.0
+    w = rng.normal(size=(8, 18)).astype(np.float32)
+    return state, w
+
+
+def test_hg_shipped_size_forward_and_gradients_match_reference(golden_dir):
+    """The HF-style ViT at its SHIPPED size (1024 / 12 layers / 16 heads / 3072, vit_hg.py:277-374, model.py:200-220):
+    outputs and every parameter gradient of the oracle vs the unmodified reference (`make_golden.py hg_full`)."""
+    G, cfg = _load(golden_dir, "hg_full"), hg_full_cfg()
+    P = O.init_params(cfg, seed=7)
+    state, w = hg_full_inputs()
+    for k in P:
+        if k.startswith("model."):
+            P[k].requires_grad_(True)
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    pol, ve, vi = O.actor_critic_forward(P, torch.tensor(state), cfg)
+    np.testing.assert_allclose(pol.detach().numpy(), G["fwd_policy"], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(ve.detach().numpy(), G["fwd_value_ext"], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(vi.detach().numpy(), G["fwd_value_int"], rtol=2e-4, atol=1e-6)
+    ((pol * torch.tensor(w)).sum() + 3.0 * ve.sum() + 2.0 * vi.sum()).backward()
+    keys = [k[len("grad/"):] for k in G.files if k.startswith("grad/")]
+    assert len(keys) > 190
+    gmax = max(float(G["grad/" + k][0]) for k in keys)
+    for k in keys:
+        assert P[k].grad is not None, k
+        d, g = digest(P[k].grad.numpy()), G["grad/" + k]
+        if k.endswith("attention.key.bias"):
+            continue                                  # exactly-zero true gradient (softmax shift invariance): rounding noise
+        assert np.abs(d - g).max() <= 5e-4 * np.abs(g).max() + 1e-7 * gmax, (k, np.abs(d - g).max(), np.abs(g).max())
+    for k in P:                                       # tensors the reference leaves without a gradient stay without one
+        if k.startswith("model.") and ("grad/" + k) not in G.files:
+            assert P[k].grad is None or float(P[k].grad.abs().max()) == 0.0, k
