@@ -8,18 +8,26 @@
 
 namespace eavit {
 
+// The C ABI carries the betas as float32; the decimal constants the caller meant (0.9, 0.999: at most 7 significant
+// digits survive float32 anyway) are recovered so that 1 - beta and beta ** step match torch's double arithmetic.
+static inline double decimal_beta(float b) { return nearbyint((double)b * 1e7) / 1e7; }
+
 __global__ void adam_tick_kernel(long long* step) { step[0] += 1; }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, __nv_bfloat16* __restrict__ p_bf16, long long n4,
-                                                   const long long* __restrict__ step, float lr, float beta1, float beta2,
+                                                   const long long* __restrict__ step, float lr, double beta1, double beta2,
                                                    float eps, float grad_scale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
+  // torch evaluates 1 - beta, beta ** step and the bias corrections in Python doubles and hands float32 scalars to the
+  // tensor ops; (float)(1 - 0.999) and 1.f - 0.999f differ by 1.3e-5 relative, which would sit in exp_avg_sq forever
   const double t = (double)step[0];
-  const float bc1 = (float)(1.0 - pow((double)beta1, t));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
-  const float step_size = lr / bc1;
+  const float bc1 = (float)(1.0 - pow(beta1, t));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, t));
+  const float step_size = (float)((double)lr / (1.0 - pow(beta1, t)));
+  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2), b2f = (float)beta2;
+  (void)bc1;
   float4 pp = reinterpret_cast<float4*>(p)[i];
   float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
   float4 mm = reinterpret_cast<float4*>(m)[i];
@@ -28,8 +36,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float gk = ga[k] * grad_scale;
-    ma[k] = ma[k] + (gk - ma[k]) * (1.f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
-    va[k] = va[k] * beta2 + (1.f - beta2) * gk * gk;         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    ma[k] = ma[k] + (gk - ma[k]) * omb1;                     // exp_avg.lerp_(grad, 1 - beta1)
+    va[k] = va[k] * b2f + omb2 * gk * gk;                    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(va[k]) / bc2_sqrt + eps;
     pa[k] = pa[k] - step_size * (ma[k] / denom);
   }
@@ -76,7 +84,8 @@ int eavit_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, 
   cudaStream_t st = (cudaStream_t)stream;
   adam_tick_kernel<<<1, 1, 0, st>>>(step);
   EAVIT_LAUNCH_OK();
-  adam_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n / 4, step, lr, beta1, beta2, eps, grad_scale);
+  adam_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n / 4, step, lr, decimal_beta(beta1), decimal_beta(beta2), eps,
+                                                grad_scale);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -94,8 +103,8 @@ int eavit_adam_tick(long long* step, void* stream) {
 int eavit_adam_apply(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, const long long* step, float lr,
                      float beta1, float beta2, float eps, float grad_scale, void* stream) {
   EAVIT_CHECK_ARG(p && g && m && v && step && n > 0 && n % 4 == 0);
-  adam_kernel<<<cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n / 4, step, lr, beta1, beta2, eps,
-                                                                  grad_scale);
+  adam_kernel<<<cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n / 4, step, lr, decimal_beta(beta1),
+                                                                  decimal_beta(beta2), eps, grad_scale);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
