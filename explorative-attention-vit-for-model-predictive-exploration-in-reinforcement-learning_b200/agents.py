@@ -54,7 +54,7 @@ class FusedAdam(torch.optim.Optimizer):
         ag = self._agent()
         rt = ag.runtime()
         rt.store.adam_step(g["lr"], 1.0, g["betas"][0], g["betas"][1], g["eps"], ranges=ag._trainable_ranges(rt))
-        rt.rnd_pred.refresh_weights()
+        rt.refresh_after_step()
 
     def state_dict(self):
         st = self._agent().runtime().store
@@ -155,7 +155,7 @@ class RNDAgent(nn.Module):
         super().__init__()
         self.env_action_space_type = env_action_space_type
         vt = int(default_config["ViT_implementation_type"])
-        ViT_implementation_type = ViT_IMPLEMENTATION.LUCIDRAINS_ViT if vt == 0 else ViT_IMPLEMENTATION.HG_ViT
+        ViT_implementation_type = ViT_IMPLEMENTATION(vt)      # 0 lucidrains, 1 HF-style, 2 = the original RND CNN backbone
         self.model = CnnActorCriticNetwork(input_size, output_size, env_action_space_type, use_noisy_net,
                                            ViT_implementation_type=ViT_implementation_type)
         self.num_env, self.output_size, self.input_size, self.num_step = num_env, output_size, input_size, num_step
@@ -421,7 +421,7 @@ class RNDAgent(nn.Module):
         g = self.optimizer.param_groups[0]
         if apply:
             st.adam_step(g["lr"], 1.0 / self.world_size, g["betas"][0], g["betas"][1], g["eps"], ranges=train_ranges)
-            rt.rnd_pred.refresh_weights()
+            rt.refresh_after_step()
         if stats_out is not None:
             stats_out.copy_(w["stats"])
 

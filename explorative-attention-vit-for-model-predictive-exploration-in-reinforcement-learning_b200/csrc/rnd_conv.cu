@@ -54,6 +54,53 @@ __global__ void __launch_bounds__(256) im2col_kernel(const InT* __restrict__ in,
   }
 }
 
+// First convolution of the CNN actor-critic backbone (model.py:110-117, commented out upstream; BASELINE configs[1]):
+// the input is the NCHW frame stack [N, C, H, W], uint8 raw frames (divided by 255 here, bit-identical to
+// np.float32(x) / 255.) or float32.  Same output as im2col_kernel: col[(b,oy,ox), c*KH*KW + i*KW + j].
+template <typename InT>
+__global__ void __launch_bounds__(256) im2col_nchw_kernel(const InT* __restrict__ in, const long long* __restrict__ sample_idx, int B, int H, int W, int C,
+                                                          int KH, int KW, int stride, int OH, int OW, __nv_bfloat16* __restrict__ col, int split3) {
+  extern __shared__ float im_sm[];
+  const int K = C * KH * KW;
+  const int npatch = C * KH * W;
+  float* patch = im_sm;                                   // [C][KH][W]
+  int* koff = reinterpret_cast<int*>(im_sm + npatch);     // [K]
+  const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
+  const long long sb = sample_idx ? sample_idx[b] : (long long)b;
+  const InT* src = in + (size_t)sb * C * H * W + (size_t)oy * stride * W;
+  for (int i = threadIdx.x; i < npatch; i += blockDim.x) {
+    const int c = i / (KH * W), r = i - c * (KH * W);     // r = ki * W + x: KH consecutive image rows of channel c are contiguous
+    const InT v = src[(size_t)c * H * W + r];
+    if constexpr (sizeof(InT) == 1) patch[i] = __fdiv_rn((float)v, 255.0f); else patch[i] = v;
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int c = k / (KH * KW), r = k - c * (KH * KW), ki = r / KW, kj = r - ki * KW;
+    koff[k] = (c * KH + ki) * W + kj;
+  }
+  __syncthreads();
+  const int K8 = K >> 3;
+  const size_t ldc = split3 ? (size_t)3 * K : (size_t)K;
+  for (int e = threadIdx.x; e < OW * K8; e += blockDim.x) {
+    const int ox = e / K8, k0 = (e - ox * K8) << 3;
+    const float* p = patch + ox * stride;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[koff[k0 + j]];
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      lo[j] = pack_bf16x2(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u));
+    }
+    __nv_bfloat16* row = col + ((size_t)blockIdx.x * OW + ox) * ldc + k0;
+    *reinterpret_cast<uint4*>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (split3) {
+      *reinterpret_cast<uint4*>(row + K) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(row + 2 * K) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 // out[r, :] = mode 0: [hi | hi | lo] (activation), mode 1: [hi | lo | hi] (weight) of the fp32 row in[r, :K]
 __global__ void __launch_bounds__(256) split3_rows_kernel(const float* __restrict__ in, long long ldi, int R, int K,
                                                           __nv_bfloat16* __restrict__ out, int mode) {
@@ -110,7 +157,7 @@ __global__ void __launch_bounds__(256) nhwc_to_flat_f32_kernel(const float* __re
 // coalesced 16-byte loads (the direct gather read 2 bytes per 32-byte sector), then every thread sums its taps.
 __global__ void __launch_bounds__(256) col2im_lrelu_kernel(const __nv_bfloat16* __restrict__ dcol, const __nv_bfloat16* __restrict__ act,
                                                            int B, int H, int W, int C, int KH, int KW, int stride, int OH,
-                                                           int OW, __nv_bfloat16* __restrict__ din) {
+                                                           int OW, __nv_bfloat16* __restrict__ din, float slope) {
   extern __shared__ __align__(16) unsigned char c2_sm_raw[];
   __nv_bfloat16* rows = reinterpret_cast<__nv_bfloat16*>(c2_sm_raw);     // [n_oy][OW][K]
   const int K = C * KH * KW;
@@ -141,7 +188,7 @@ __global__ void __launch_bounds__(256) col2im_lrelu_kernel(const __nv_bfloat16* 
       for (int ox = ox_lo; ox <= ox_hi; ++ox) acc += __bfloat162float(r[ox * K + (x - ox * stride)]);
     }
     const float a = __bfloat162float(act[base + e]);
-    din[base + e] = __float2bfloat16(a > 0.f ? acc : 0.01f * acc);
+    din[base + e] = __float2bfloat16(a > 0.f ? acc : slope * acc);
   }
 }
 
@@ -156,14 +203,23 @@ __global__ void __launch_bounds__(256) nhwc_to_flat_kernel(const __nv_bfloat16* 
 }
 // backward: dact[b, p, c] = lrelu'(act[b,p,c]) * dflat[b, c*HW + p]
 __global__ void __launch_bounds__(256) flat_to_nhwc_lrelu_kernel(const __nv_bfloat16* __restrict__ dflat, const __nv_bfloat16* __restrict__ act,
-                                                                 int B, int HW, int C, __nv_bfloat16* __restrict__ dact) {
+                                                                 int B, int HW, int C, __nv_bfloat16* __restrict__ dact, float slope) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * HW * C) return;
   const int c = (int)(i % C), p = (int)((i / C) % HW);
   const long long b = i / ((long long)HW * C);
   const float g = __bfloat162float(dflat[((size_t)b * C + c) * HW + p]);
   const float a = __bfloat162float(act[i]);
-  dact[i] = __float2bfloat16(a > 0.f ? g : 0.01f * g);
+  dact[i] = __float2bfloat16(a > 0.f ? g : slope * g);
+}
+
+// out = bf16(dy * act'(y)) for an activation applied OUTSIDE a GEMM epilogue (the ReLU that ends the CNN backbone)
+__global__ void __launch_bounds__(256) act_bwd_bf16_kernel(const float* __restrict__ dy, const float* __restrict__ y, float slope,
+                                                           __nv_bfloat16* __restrict__ out, long long n2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const float2 g = reinterpret_cast<const float2*>(dy)[i], a = reinterpret_cast<const float2*>(y)[i];
+  reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(a.x > 0.f ? g.x : slope * g.x, a.y > 0.f ? g.y : slope * g.y);
 }
 
 }  // namespace eavit
@@ -212,15 +268,41 @@ int eavit_nhwc_to_flat_f32(const float* act, int B, int HW, int C, float* flat, 
   return EAVIT_OK;
 }
 
+int eavit_im2col_nchw(const void* in, int in_dtype, const long long* sample_idx, int B, int H, int W, int C, int KH, int KW, int stride,
+                      void* col, int split3, void* stream) {
+  EAVIT_CHECK_ARG(in && col && B > 0 && H >= KH && W >= KW && stride > 0 && C > 0 && (C * KH * KW) % 8 == 0);
+  EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(col) & 15) == 0);
+  const int OH = (H - KH) / stride + 1, OW = (W - KW) / stride + 1;
+  const size_t smem = ((size_t)KH * W * C + (size_t)C * KH * KW) * 4;
+  EAVIT_CHECK_ARG(smem <= 48 * 1024);
+  const int grid = B * OH;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == EAVIT_F32) im2col_nchw_kernel<float><<<grid, 256, smem, st>>>((const float*)in, sample_idx, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)col, split3);
+  else if (in_dtype == EAVIT_U8) im2col_nchw_kernel<uint8_t><<<grid, 256, smem, st>>>((const uint8_t*)in, sample_idx, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)col, split3);
+  else { set_error("im2col_nchw: bad dtype %d", in_dtype); return EAVIT_EINVAL; }
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+static int col2im_launch(const void* dcol, const void* act, int B, int H, int W, int C, int KH, int KW, int stride, void* din, float slope,
+                         void* stream);
 int eavit_col2im_lrelu(const void* dcol, const void* act, int B, int H, int W, int C, int KH, int KW, int stride, void* din,
                        void* stream) {
+  return col2im_launch(dcol, act, B, H, W, C, KH, KW, stride, din, 0.01f, stream);
+}
+int eavit_col2im_act(const void* dcol, const void* act, int B, int H, int W, int C, int KH, int KW, int stride, void* din, float slope,
+                     void* stream) {
+  return col2im_launch(dcol, act, B, H, W, C, KH, KW, stride, din, slope, stream);
+}
+static int col2im_launch(const void* dcol, const void* act, int B, int H, int W, int C, int KH, int KW, int stride, void* din, float slope,
+                         void* stream) {
   EAVIT_CHECK_ARG(dcol && act && din && B > 0 && H >= KH && W >= KW && stride > 0);
   const int OH = (H - KH) / stride + 1, OW = (W - KW) / stride + 1;
   const int K = C * KH * KW;
   EAVIT_CHECK_ARG(K % 8 == 0 && (reinterpret_cast<uintptr_t>(dcol) & 15) == 0);
   const size_t smem = (size_t)((KH + stride - 1) / stride) * OW * K * 2;
   EAVIT_CHECK_ARG(smem <= 48 * 1024);
-  col2im_lrelu_kernel<<<B * H, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol, (const __nv_bfloat16*)act, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)din);
+  col2im_lrelu_kernel<<<B * H, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol, (const __nv_bfloat16*)act, B, H, W, C, KH, KW, stride, OH, OW, (__nv_bfloat16*)din, slope);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -232,9 +314,19 @@ int eavit_nhwc_to_flat(const void* act, int B, int HW, int C, void* flat, void* 
   return EAVIT_OK;
 }
 
-int eavit_flat_to_nhwc_lrelu(const void* dflat, const void* act, int B, int HW, int C, void* dact, void* stream) {
+int eavit_flat_to_nhwc_act(const void* dflat, const void* act, int B, int HW, int C, void* dact, float slope, void* stream) {
   EAVIT_CHECK_ARG(dflat && act && dact && B > 0 && HW > 0 && C > 0);
-  flat_to_nhwc_lrelu_kernel<<<cdiv((long long)B * HW * C, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dflat, (const __nv_bfloat16*)act, B, HW, C, (__nv_bfloat16*)dact);
+  flat_to_nhwc_lrelu_kernel<<<cdiv((long long)B * HW * C, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dflat, (const __nv_bfloat16*)act, B, HW, C, (__nv_bfloat16*)dact, slope);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+int eavit_flat_to_nhwc_lrelu(const void* dflat, const void* act, int B, int HW, int C, void* dact, void* stream) {
+  return eavit_flat_to_nhwc_act(dflat, act, B, HW, C, dact, 0.01f, stream);
+}
+
+int eavit_act_bwd_bf16(const float* dy, const float* y, float slope, void* out_bf16, long long n, void* stream) {
+  EAVIT_CHECK_ARG(dy && y && out_bf16 && n > 0 && n % 2 == 0);
+  act_bwd_bf16_kernel<<<cdiv(n / 2, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, slope, (__nv_bfloat16*)out_bf16, n / 2);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }

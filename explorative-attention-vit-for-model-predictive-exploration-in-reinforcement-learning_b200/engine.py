@@ -603,21 +603,27 @@ class Heads:
         return dF
 
 
-class RNDNet:
-    """model.py:366-416 conv tower + FC stack; ``net`` = 'predictor' (trainable) or 'target' (frozen).
+class ConvTower:
+    """conv8s4 - act - conv4s2 - act - conv3s1 - act - Flatten - Linear [- ReLU - Linear ...] as im2col + tcgen05 GEMMs.
+
+    Two users: the RND towers (model.py:366-416: 1 input channel, LeakyReLU, Linear(3136,512) [+ 2 x Linear(512,512)], no final
+    activation) and the CNN actor-critic backbone of BASELINE configs[1] (model.py:110-135, commented out upstream: the 4-frame
+    NCHW stack, ReLU, Linear(3136,256)-ReLU-Linear(256,448)-ReLU).
 
     Forward operands are bf16x3 splits ([hi|hi|lo] x [hi|lo|hi], one GEMM with K' = 3K): the (Leaky)ReLU masks of
-    this plain ReLU network flip wherever a pre-activation's rounding error exceeds its magnitude, and with single
-    bf16 operands (2^-9) those flips alone put ~3 % error on the predictor gradients.  The towers are < 1 % of the
+    these plain ReLU networks flip wherever a pre-activation's rounding error exceeds its magnitude, and with single
+    bf16 operands (2^-9) those flips alone put ~3 % error on the gradients.  The towers are < 1 % of the
     update's FLOPs, so near-fp32 pre-activations cost nothing measurable.  Backward GEMMs use plain bf16 (hi parts).
     """
 
-    CONVS = ((8, 4, 1, 32), (4, 2, 32, 64), (3, 1, 64, 64))   # (kernel, stride, Cin, Cout)
-
-    def __init__(self, store: ParamStore, net: str, image: int = 84, out: int = 512):
-        self.s, self.net, self.image, self.out = store, net, image, out
-        self.pre = f"rnd.{net}."
-        self.fcs = (7, 9, 11) if net == "predictor" else (7,)
+    def __init__(self, store: ParamStore, prefix: str, cin: int, slope: float, fcs: Sequence[int], fc_out: Sequence[int],
+                 final_relu: bool, nchw_input: bool, image: int = 84):
+        self.s, self.pre, self.image = store, prefix, image
+        self.cin, self.slope, self.fcs, self.fc_out = cin, float(slope), tuple(fcs), tuple(fc_out)
+        self.final_relu, self.nchw = final_relu, nchw_input
+        self.conv_act = ops.ACT_LRELU if slope > 0 else ops.ACT_RELU
+        self.CONVS = ((8, 4, cin, 32), (4, 2, 32, 64), (3, 1, 64, 64))   # (kernel, stride, Cin, Cout)
+        self.out = self.fc_out[-1]
         self.buf: Dict[int, _Buffers] = {}
         h = image
         self.sizes = []
@@ -642,12 +648,13 @@ class RNDNet:
 
     def forward(self, obs: torch.Tensor, B: int, sample_idx: Optional[torch.Tensor] = None,
                 col0: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """obs fp32 [N,1,H,W] (normalised, clipped); returns features fp32 [B, out].
+        """obs: [N,1,H,W] fp32 (RND: normalised, clipped) or, with ``nchw_input``, the frame stack [N,C,H,W] uint8 / fp32;
+        returns features fp32 [B, out].
         ``col0``: the first convolution's patch matrix of the SAME observations, already built by the other tower
         (``self.buf[B].t["col0"]`` of that tower) -- predictor and target read identical inputs (model.py:457-461)."""
         s, p = self.s, self.pre
         bf = self.buf.setdefault(B, _Buffers(obs.device))
-        assert obs.dtype == torch.float32
+        assert obs.dtype == torch.float32 or (self.nchw and obs.dtype == torch.uint8)
         x, sidx = obs, sample_idx
         for ci, ((k, st, cin, cout), (h, oh)) in enumerate(zip(self.CONVS, self.sizes)):
             K = cin * k * k
@@ -655,10 +662,13 @@ class RNDNet:
                 col = bf.t["col0"] = col0
             else:
                 col = bf.get(f"col{ci}", (B * oh * oh, 3 * K), torch.bfloat16)
-                call("eavit_im2col", x, F32, sidx, B, h, h, cin, k, k, st, col, 1)
+                if ci == 0 and self.nchw:
+                    call("eavit_im2col_nchw", x, ops._DT[x.dtype], sidx, B, h, h, cin, k, k, st, col, 1)
+                else:
+                    call("eavit_im2col", x, F32, sidx, B, h, h, cin, k, k, st, col, 1)
             a32 = bf.get(f"act32_{ci}", (B * oh * oh, cout), torch.float32)
             a16 = bf.get(f"act{ci}", (B * oh * oh, cout), torch.bfloat16)
-            ops.gemm(col, self.w3[f"{2 * ci}"], bias=s.w(p + f"{2 * ci}.bias"), act=ops.ACT_LRELU, out_f32=a32, out_bf16=a16)
+            ops.gemm(col, self.w3[f"{2 * ci}"], bias=s.w(p + f"{2 * ci}.bias"), act=self.conv_act, out_f32=a32, out_bf16=a16)
             x, sidx = a32, None
         hw = self.sizes[-1][1] ** 2
         flat32 = bf.get("flat32", (B, self.flat_dim), torch.float32)
@@ -672,40 +682,46 @@ class RNDNet:
             last = j == len(self.fcs) - 1
             bias = s.w(p + f"{k}.bias")
             w3 = self.w3[f"{k}"]
-            f32 = bf.get("out" if last else f"fc32_{j}", (B, self.out), torch.float32)
+            n_out = self.fc_out[j]
+            f32 = bf.get("out" if last else f"fc32_{j}", (B, n_out), torch.float32)
             call("eavit_zero", f32, f32.numel() * 4)
-            ops.gemm(h3, w3, out_f32=f32, atomic=True, split_k=_split_k(B, self.out, h3.shape[1]))
+            ops.gemm(h3, w3, out_f32=f32, atomic=True, split_k=_split_k(B, n_out, h3.shape[1]))
             if last:
-                call("eavit_bias_act_split3", f32, self.out, bias, ops.ACT_NONE, None, None, B, self.out)
+                call("eavit_bias_act_split3", f32, n_out, bias, ops.ACT_RELU if self.final_relu else ops.ACT_NONE, None, None, B, n_out)
                 out = f32
             else:
-                f16 = bf.get(f"fc16_{j}", (B, self.out), torch.bfloat16)
-                h3 = bf.get(f"fc{j}", (B, 3 * self.out), torch.bfloat16)
-                call("eavit_bias_act_split3", f32, self.out, bias, ops.ACT_RELU, f16, h3, B, self.out)
+                f16 = bf.get(f"fc16_{j}", (B, n_out), torch.bfloat16)
+                h3 = bf.get(f"fc{j}", (B, 3 * n_out), torch.bfloat16)
+                call("eavit_bias_act_split3", f32, n_out, bias, ops.ACT_RELU, f16, h3, B, n_out)
         return out
 
-    def backward(self, dout16: torch.Tensor):
-        """dout16 bf16 [B, out]; accumulates predictor gradients into ``store.grad``."""
+    def backward(self, dout: torch.Tensor):
+        """dout [B, out]: bf16, or fp32 when the tower ends with a ReLU (masked here by the stored output);
+        accumulates the tower's parameter gradients into ``store.grad``."""
         s, p = self.s, self.pre
-        B = dout16.shape[0]
+        B = dout.shape[0]
         bf = self.buf[B]
-        d = dout16
+        if self.final_relu:
+            d = bf.get("dout16", (B, self.out), torch.bfloat16)
+            call("eavit_act_bwd_bf16", dout, bf.t["out"], 0.0, d, B * self.out)
+        else:
+            d = dout
         nfc = len(self.fcs)
         for j in reversed(range(nfc)):
             name = p + f"{self.fcs[j]}."
-            x16 = bf.t["flat"][:, : self.flat_dim] if j == 0 else bf.t[f"fc{j - 1}"][:, : self.out]   # hi parts
+            x16 = bf.t["flat"][:, : self.flat_dim] if j == 0 else bf.t[f"fc{j - 1}"][:, : self.fc_out[j - 1]]   # hi parts
             if j == 0:
                 dflat = bf.get("dflat", (B, self.flat_dim), torch.bfloat16)
                 linear_bwd(d, x16, s.b16(name + "weight"), dW=s.g(name + "weight"), db=s.g(name + "bias"), dx_bf16=dflat)
                 d = dflat
             else:
-                dprev = bf.get(f"dfc{j - 1}", (B, self.out), torch.bfloat16)
+                dprev = bf.get(f"dfc{j - 1}", (B, self.fc_out[j - 1]), torch.bfloat16)
                 linear_bwd(d, x16, s.b16(name + "weight"), dW=s.g(name + "weight"), db=s.g(name + "bias"), dx_bf16=dprev,
                            act=ops.ACT_RELU_BWD, aux=bf.t[f"fc16_{j - 1}"])
                 d = dprev
         hw = self.sizes[-1][1] ** 2
         dact = bf.get("dact2", (B * hw, 64), torch.bfloat16)
-        call("eavit_flat_to_nhwc_lrelu", d, bf.t["act2"], B, hw, 64, dact)
+        call("eavit_flat_to_nhwc_act", d, bf.t["act2"], B, hw, 64, dact, self.slope)
         for ci in (2, 1, 0):
             k, st, cin, cout = self.CONVS[ci]
             h, oh = self.sizes[ci]
@@ -719,5 +735,45 @@ class RNDNet:
             linear_bwd(dact, col_hi, s.b16(name + "weight").view(cout, K), dW=s.g(name + "weight").view(cout, K),
                        db=s.g(name + "bias"), dx_bf16=dcol)
             dprev = bf.get(f"dact{ci - 1}", (B * h * h, cin), torch.bfloat16)
-            call("eavit_col2im_lrelu", dcol, bf.t[f"act{ci - 1}"], B, h, h, cin, k, k, st, dprev)
+            call("eavit_col2im_act", dcol, bf.t[f"act{ci - 1}"], B, h, h, cin, k, k, st, dprev, self.slope)
             dact = dprev
+
+
+class RNDNet(ConvTower):
+    """model.py:366-416 conv tower + FC stack; ``net`` = 'predictor' (trainable) or 'target' (frozen)."""
+
+    def __init__(self, store: ParamStore, net: str, image: int = 84, out: int = 512):
+        self.net = net
+        fcs = (7, 9, 11) if net == "predictor" else (7,)
+        super().__init__(store, f"rnd.{net}.", cin=1, slope=0.01, fcs=fcs, fc_out=(out,) * len(fcs), final_relu=False,
+                         nchw_input=False, image=image)
+
+
+class CnnEncoder:
+    """The original RND CNN backbone (model.py:110-135, commented out upstream; BASELINE configs[1]) behind the encoder
+    interface the heads expect: ``forward`` returns F fp32 [2B, D] with rows [0,B) == rows [B,2B) == the one feature vector of
+    each sample (policy = actor(x), value = critic(extra_layer(x) + x) for both critics -- the CLS-style head wiring)."""
+
+    def __init__(self, cfg: HotPathConfig, store: ParamStore, prefix: str = "model.feature."):
+        self.cfg, self.store = cfg, store
+        self.tower = ConvTower(store, prefix, cin=cfg.channels, slope=0.0, fcs=(7, 9), fc_out=(256, cfg.dim), final_relu=True,
+                               nchw_input=True, image=cfg.image)
+        self.buf: Dict[int, _Buffers] = {}
+
+    def refresh_weights(self):
+        self.tower.refresh_weights()
+
+    def forward(self, img: torch.Tensor, B: int, sample_idx: Optional[torch.Tensor] = None, drop_base=None) -> torch.Tensor:
+        x = self.tower.forward(img, B, sample_idx)
+        bf = self.buf.setdefault(B, _Buffers(img.device))
+        feat = bf.get("feat", (2 * B, self.cfg.dim), torch.float32)
+        feat[:B].copy_(x)
+        feat[B:].copy_(x)
+        return feat
+
+    def backward(self, dfeat: torch.Tensor):
+        B = dfeat.shape[0] // 2
+        bf = self.buf[B]
+        d = bf.get("dx", (B, self.cfg.dim), torch.float32)
+        call("eavit_add_f32", dfeat[:B], dfeat[B:], d, B * self.cfg.dim)
+        self.tower.backward(d)

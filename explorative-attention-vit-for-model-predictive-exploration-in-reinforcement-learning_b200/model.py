@@ -20,7 +20,7 @@ from torch.nn import init
 
 from . import ops
 from .config import HotPathConfig, default_config
-from .engine import Heads, ParamStore, RNDNet, ViTEncoder
+from .engine import CnnEncoder, Heads, ParamStore, RNDNet, ViTEncoder
 from .ops import call
 from .utils import Env_action_space_type
 from .vit import ViT, ViT_Attn
@@ -30,6 +30,9 @@ from .vit_hg import ViT_ExplorativeAttn, ViTConfigLike
 class ViT_IMPLEMENTATION(Enum):   # model.py:16-18
     LUCIDRAINS_ViT = 0
     HG_ViT = 1
+    # not in the reference's enum: selects the original RND CNN backbone that model.py:110-178 keeps as commented-out code
+    # (BASELINE configs[1]); ``ViT_implementation_type = 2`` in the .conf
+    ORIGINAL_CNN = 2
 
 
 class Flatten(nn.Module):         # model.py:80-82 (parameter-free; kept for state_dict index alignment)
@@ -98,6 +101,16 @@ class Runtime:
             if "model.actor.0.weight" in self.params:
                 A = self.params["model.actor.2.weight"].shape[0] if n_actions is None else n_actions
                 self.heads = Heads(self.cfg, self.store, A, ext_uses_int_critic)
+        elif "model.feature.0.weight" in self.params and "model.feature.9.weight" in self.params:
+            # the original RND CNN backbone (model.py:110-135): no ViT, no dropout
+            w0, w9 = self.params["model.feature.0.weight"], self.params["model.feature.9.weight"]
+            self.cfg = HotPathConfig(impl="cnn", image=84, channels=w0.shape[1], patch=84, dim=w9.shape[0], depth=0, heads=0,
+                                     dim_head=0, mlp_dim=0, use_explorative=False, ln_eps=0.0, dropout=0.0, emb_dropout=0.0)
+            self.encoder = CnnEncoder(self.cfg, self.store, "model.feature.")
+            self._feat = root
+            self._drop_seed0 = self._drop_calls = 0
+            A = self.params["model.actor.2.weight"].shape[0] if n_actions is None else n_actions
+            self.heads = Heads(self.cfg, self.store, A, False)
         if "rnd.predictor.0.weight" in self.params:
             self.rnd_pred = RNDNet(self.store, "predictor")
             self.rnd_tgt = RNDNet(self.frozen, "target")
@@ -142,10 +155,20 @@ class Runtime:
         if self.rnd_pred is not None:
             self.rnd_pred.refresh_weights()
             self.rnd_tgt.refresh_weights()
+        if isinstance(self.encoder, CnnEncoder):
+            self.encoder.refresh_weights()
         # gradients may have been detached by optimizer.zero_grad(set_to_none=True)
         for n, p in self.params.items():
             if n in self.store.shapes and (p.grad is None or p.grad.data_ptr() != self.store.g(n).data_ptr()):
                 p.grad = self.store.g(n)
+
+    def refresh_after_step(self):
+        """bf16x3 operand copies of the conv-tower weights follow the fp32 masters after every optimiser step (the bf16
+        shadow of the flat store is written by the Adam kernel itself)."""
+        if self.rnd_pred is not None:
+            self.rnd_pred.refresh_weights()
+        if isinstance(self.encoder, CnnEncoder):
+            self.encoder.refresh_weights()
 
     # ---- actor-critic ----------------------------------------------------------------------------
     def dropout_active(self) -> bool:
@@ -261,7 +284,14 @@ class CnnActorCriticNetwork(nn.Module):
         self.env_action_space_type = env_action_space_type
         self.ViT_implementation_type = ViT_implementation_type
         c = default_config
-        if ViT_implementation_type == ViT_IMPLEMENTATION.LUCIDRAINS_ViT:       # model.py:183-196
+        if ViT_implementation_type == ViT_IMPLEMENTATION.ORIGINAL_CNN:         # model.py:110-135 (commented out upstream)
+            ViT_dim = int(c["extracted_feature_embedding_dim"])
+            self.feature = nn.Sequential(
+                nn.Conv2d(in_channels=int(c["StateStackSize"]), out_channels=32, kernel_size=8, stride=4), nn.ReLU(),
+                nn.Conv2d(in_channels=32, out_channels=64, kernel_size=4, stride=2), nn.ReLU(),
+                nn.Conv2d(in_channels=64, out_channels=64, kernel_size=3, stride=1), nn.ReLU(),
+                Flatten(), nn.Linear(7 * 7 * 64, 256), nn.ReLU(), nn.Linear(256, ViT_dim), nn.ReLU())
+        elif ViT_implementation_type == ViT_IMPLEMENTATION.LUCIDRAINS_ViT:     # model.py:183-196
             ViT_dim = int(c["ViTlucidrains_dim"])
             self.feature = ViT(image_size=int(c["PreProcHeight"]), patch_size=int(c["ViTlucidrains_patch_size"]),
                                num_classes=int(c["ViTlucidrains_num_classes"]), dim=ViT_dim, depth=int(c["ViTlucidrains_depth"]),
@@ -288,6 +318,11 @@ class CnnActorCriticNetwork(nn.Module):
         self.extra_layer = nn.Sequential(nn.Linear(ViT_dim, ViT_dim), nn.ReLU())                                # model.py:240-243
         self.critic_ext = nn.Linear(ViT_dim, 1)
         self.critic_int = nn.Linear(ViT_dim, 1)
+        if ViT_implementation_type == ViT_IMPLEMENTATION.ORIGINAL_CNN:         # model.py:147-155
+            for p in self.modules():
+                if isinstance(p, (nn.Conv2d, nn.Linear)):
+                    init.orthogonal_(p.weight, np.sqrt(2))
+                    p.bias.data.zero_()
         init.orthogonal_(self.critic_ext.weight, 0.01)                                                          # model.py:249-263
         self.critic_ext.bias.data.zero_()
         init.orthogonal_(self.critic_int.weight, 0.01)

@@ -259,6 +259,10 @@ _SPECS = {
     "eavit_rnd_loss": "pppiifppp",
     "eavit_gather_batch": "piipppppppppp",
     "eavit_im2col": "pipiiiiiiipi",
+    "eavit_im2col_nchw": "pipiiiiiiipi",
+    "eavit_col2im_act": "ppiiiiiiipf",
+    "eavit_flat_to_nhwc_act": "ppiiipf",
+    "eavit_act_bwd_bf16": "ppfpl",
     "eavit_dropout_epoch_bump": "",
     "eavit_dropout_epoch_set": "i",
     "eavit_split3_rows": "pliipi",

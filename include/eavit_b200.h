@@ -269,6 +269,17 @@ int eavit_nhwc_to_flat_f32(const float* act, int B, int HW, int C, float* flat, 
 int eavit_col2im_lrelu(const void* dcol_bf16, const void* act_bf16, int B, int H, int W, int C, int KH, int KW, int stride,
                        void* din_bf16, void* stream);
 int eavit_nhwc_to_flat(const void* act_bf16, int B, int HW, int C, void* flat_bf16, void* stream);
+/* ---- CNN actor-critic backbone (model.py:110-178, kept upstream as commented-out code; BASELINE configs[1]).  Same
+ * im2col + tcgen05 GEMM scheme as the RND towers with a ReLU (slope 0) instead of LeakyReLU (slope 0.01):
+ * eavit_im2col_nchw reads the NCHW frame stack [N,C,H,W] (uint8 raw frames, divided by 255 like np.float32(x)/255., or
+ * float32) and writes the same [B*OH*OW, C*KH*KW] patch matrix as eavit_im2col; the *_act variants take the activation's
+ * negative slope; eavit_act_bwd_bf16: out = bf16(dy * act'(y)) for the ReLU that ends the backbone (model.py:134). */
+int eavit_im2col_nchw(const void* in, int in_dtype, const long long* sample_idx /* may be NULL */, int B, int H, int W, int C, int KH, int KW,
+                      int stride, void* col_bf16, int split3, void* stream);
+int eavit_col2im_act(const void* dcol_bf16, const void* act_bf16, int B, int H, int W, int C, int KH, int KW, int stride,
+                     void* din_bf16, float slope, void* stream);
+int eavit_flat_to_nhwc_act(const void* dflat_bf16, const void* act_bf16, int B, int HW, int C, void* dact_bf16, float slope, void* stream);
+int eavit_act_bwd_bf16(const float* dy, const float* y, float slope, void* out_bf16, long long n, void* stream);
 int eavit_flat_to_nhwc_lrelu(const void* dflat_bf16, const void* act_bf16, int B, int HW, int C, void* dact_bf16, void* stream);
 
 /* ------------------------------------------------------------------ optimiser (agents.py:129,:508) */

@@ -31,7 +31,8 @@ import torch.nn.functional as F
 class OracleConfig:
     """The subset of .conf keys the hot path reads ("Config / flags")."""
 
-    impl: str = "lucidrains"          # ViT_implementation_type: 0 -> "lucidrains", 1 -> "hg"
+    impl: str = "lucidrains"          # ViT_implementation_type: 0 -> "lucidrains", 1 -> "hg"; "cnn" = the original RND
+                                      # CNN backbone the reference keeps as commented-out code (model.py:110-178)
     image: int = 84                   # PreProcHeight
     channels: int = 4                 # StateStackSize
     patch: int = 6                    # ViTlucidrains_patch_size / ViTHG_patch_size
@@ -128,6 +129,20 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
         s[f + "layernorm.bias"] = (D,)
         s[f + "pooler.dense.weight"] = (D, D)
         s[f + "pooler.dense.bias"] = (D,)
+    elif cfg.impl == "cnn":
+        # model.py:110-135 (commented out upstream; BASELINE configs[1], SURVEY 8c "CNN-backbone config"): nn.Sequential
+        # indices 0 conv8s4, 2 conv4s2, 4 conv3s1, 6 Flatten, 7 Linear(3136, 256), 9 Linear(256, dim = 448)
+        f = "model.feature."
+        s[f + "0.weight"] = (32, cfg.channels, 8, 8)
+        s[f + "0.bias"] = (32,)
+        s[f + "2.weight"] = (64, 32, 4, 4)
+        s[f + "2.bias"] = (64,)
+        s[f + "4.weight"] = (64, 64, 3, 3)
+        s[f + "4.bias"] = (64,)
+        s[f + "7.weight"] = (256, 7 * 7 * 64)
+        s[f + "7.bias"] = (256,)
+        s[f + "9.weight"] = (D, 256)
+        s[f + "9.bias"] = (D,)
     else:
         raise ValueError(cfg.impl)
     # heads, model.py:227-246
@@ -183,8 +198,8 @@ def init_params(cfg: OracleConfig, seed: int = 0, dtype=torch.float32) -> Dict[s
                 gain = 0.1          # reference uses orthogonal gain 0.01 (model.py:249-258)
             elif name.startswith("model.extra_layer"):
                 gain = 0.3          # reference: orthogonal gain 0.1 (model.py:260-263)
-            elif name.startswith("rnd."):
-                gain = math.sqrt(2.0)   # model.py:447,451
+            elif name.startswith("rnd.") or (cfg.impl == "cnn" and name.startswith("model.feature.")):
+                gain = math.sqrt(2.0)   # model.py:447,451 (RND towers), model.py:149-156 (CNN backbone)
             a = rng.standard_normal(shape) * (gain / math.sqrt(fan_in))
         out[name] = torch.tensor(a, dtype=dtype)
     return out
@@ -329,6 +344,11 @@ def actor_critic_forward(P, state, cfg: OracleConfig, attn_aggregation_op: str =
     lucidrains/explorative: model.py:272-296.  lucidrains/CLS: model.py:298-304.
     HG: model.py:310-336 incl. the head bug: value_ext uses ``critic_int``.
     """
+    if cfg.impl == "cnn":
+        # model.py:110-135 backbone; forward as in the upstream RND agent the comment block was taken from (README.md:168,
+        # SURVEY 8c): policy = actor(x), value = critic(extra_layer(x) + x) for both critics
+        x = cnn_backbone(P, state)
+        return _heads(P, x, x, x, "critic_ext")
     if cfg.impl == "lucidrains":
         if cfg.use_explorative:
             xe = lucid_vit(P, state, EXPLORATIVE, cfg)
@@ -341,6 +361,16 @@ def actor_critic_forward(P, state, cfg: OracleConfig, attn_aggregation_op: str =
     xe, xx = s_e[:, 0, :], s_x[:, 0, :]                                          # model.py:316,320
     comb = torch.stack((xe, xx), dim=1).mean(dim=1) if attn_aggregation_op == "mean" else xe + xx
     return _heads(P, xe, xx, comb, "critic_int")                                 # model.py:321 (bug kept)
+
+
+def cnn_backbone(P, state, pre="model.feature.") -> torch.Tensor:
+    """model.py:110-135 (commented out upstream): conv8s4-ReLU-conv4s2-ReLU-conv3s1-ReLU-Flatten-Linear(3136,256)-ReLU-
+    Linear(256,448)-ReLU on the stacked frames [B, StateStackSize, 84, 84]."""
+    x = F.relu(F.conv2d(state, P[pre + "0.weight"], P[pre + "0.bias"], stride=4))
+    x = F.relu(F.conv2d(x, P[pre + "2.weight"], P[pre + "2.bias"], stride=2))
+    x = F.relu(F.conv2d(x, P[pre + "4.weight"], P[pre + "4.bias"], stride=1))
+    x = F.relu(F.linear(x.flatten(1), P[pre + "7.weight"], P[pre + "7.bias"]))
+    return F.relu(F.linear(x, P[pre + "9.weight"], P[pre + "9.bias"]))
 
 
 def rnd_net(P, obs, net: str) -> torch.Tensor:

@@ -23,7 +23,9 @@ def make_agent(cfg: O.OracleConfig, E, T, seed=7, **conf):
     import eavit_b200  # noqa
     from eavit_b200 import agents, config, utils
     keys = {"ViTlucidrains_dropout": 0.0, "ViTlucidrains_emb_dropout": 0.0}
-    if cfg.impl == "hg":
+    if cfg.impl == "cnn":
+        keys.update({"ViT_implementation_type": 2, "extracted_feature_embedding_dim": cfg.dim, "StateStackSize": cfg.channels})
+    elif cfg.impl == "hg":
         keys.update({"ViT_implementation_type": 1, "ViTHG_hidden_size": cfg.dim, "ViTHG_num_hidden_layers": cfg.depth,
                      "ViTHG_num_attention_heads": cfg.heads, "ViTHG_intermediate_size": cfg.mlp_dim,
                      "ViTHG_patch_size": cfg.patch, "extracted_feature_embedding_dim": cfg.dim})

@@ -70,6 +70,48 @@ def test_state_dict_names_and_shapes_match_reference(which):
     config.load_config(None)
 
 
+def test_cnn_backbone_constructor_follows_the_commented_reference_code():
+    """BASELINE configs[1]: the CNN actor-critic that model.py:110-178 keeps as commented-out code.  The reference cannot
+    construct it, so the check is against a line-by-line torch restatement of that block under the same seed: same
+    parameter names / shapes as the oracle's table and bit-identical seeded initial weights."""
+    import torch.nn as nn
+    from torch.nn import init
+    from eavit_b200 import config, model, utils
+    config.load_config(None, ViT_implementation_type=2, extracted_feature_embedding_dim=448)
+    utils.set_seed(42)
+    ac = model.CnnActorCriticNetwork(84, 18, utils.Env_action_space_type.DISCRETE, False,
+                                     ViT_implementation_type=model.ViT_IMPLEMENTATION.ORIGINAL_CNN)
+    got = {"model." + k: tuple(v.shape) for k, v in ac.state_dict().items()}
+    want = {k: v for k, v in O.param_shapes(O.OracleConfig(impl="cnn", dim=448)).items() if k.startswith("model.")}
+    assert got == want
+    utils.set_seed(42)
+    D = 448
+    feature = nn.Sequential(nn.Conv2d(4, 32, 8, 4), nn.ReLU(), nn.Conv2d(32, 64, 4, 2), nn.ReLU(), nn.Conv2d(64, 64, 3, 1), nn.ReLU(),
+                            nn.Flatten(), nn.Linear(7 * 7 * 64, 256), nn.ReLU(), nn.Linear(256, D), nn.ReLU())        # :110-135
+    actor = nn.Sequential(nn.Linear(D, D), nn.ReLU(), nn.Linear(D, 18))                                              # :137-141
+    extra = nn.Sequential(nn.Linear(D, D), nn.ReLU())                                                                # :143-146
+    c_ext, c_int = nn.Linear(D, 1), nn.Linear(D, 1)                                                                  # :148-149
+    for m in (*feature, *actor, *extra, c_ext, c_int):              # `for p in self.modules()` order (:151-158)
+        if isinstance(m, (nn.Conv2d, nn.Linear)):
+            init.orthogonal_(m.weight, np.sqrt(2))
+            m.bias.data.zero_()
+    init.orthogonal_(c_ext.weight, 0.01); init.orthogonal_(c_int.weight, 0.01)                                       # :160-164
+    for m in actor:
+        if isinstance(m, nn.Linear):
+            init.orthogonal_(m.weight, 0.01)                                                                         # :166-169
+    for m in extra:
+        if isinstance(m, nn.Linear):
+            init.orthogonal_(m.weight, 0.1)                                                                          # :171-174
+    ref = {**{"feature." + k: v for k, v in feature.state_dict().items()}, **{"actor." + k: v for k, v in actor.state_dict().items()},
+           **{"extra_layer." + k: v for k, v in extra.state_dict().items()}, **{"critic_ext." + k: v for k, v in c_ext.state_dict().items()},
+           **{"critic_int." + k: v for k, v in c_int.state_dict().items()}}
+    sd = ac.state_dict()
+    assert set(sd) == set(ref)
+    for k in sd:
+        assert torch.equal(sd[k], ref[k]), k
+    config.load_config(None)
+
+
 def test_seeded_init_matches_reference(golden_dir):
     """Constructors consume torch's RNG in the reference's order: same seed -> same initial weights (lucidrains)."""
     from eavit_b200 import config, model, utils
