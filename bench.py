@@ -4,16 +4,22 @@
     python bench.py --gpus N --steps K --warmup W          # this repo (sm_100a kernels through the C ABI)
     python bench.py --impl reference --steps K --warmup W   # the reference's CPU path (oracle port), host cores
 
-Workload (BASELINE.json configs[2]; configs[1] -- the CNN actor-critic -- is dead code in the
-reference and has no reference arm): lucidrains explorative-attention ViT (dim 256, depth 3, 8x32 heads, mlp 1024,
-patch 6 -> 196/197 tokens) + PPO heads + RND predictor/target, 128 envs x 128 steps per GPU (N = 16 384 samples),
-MiniBatch 32 -> 512 samples per optimiser step, dropout keys = 0.0 (the parity configuration).
+Workload (BASELINE.json configs[2], SURVEY 8d cfg3 -- the configuration the metric is quoted on): lucidrains
+explorative-attention ViT (dim 256, depth 3, 8x32 heads, mlp 1024, patch 6 -> 196/197 tokens) + PPO heads + RND
+predictor/target, 128 envs x 128 steps per GPU (N = 16 384 samples), MiniBatch 32 -> 512 samples per optimiser step,
+dropout keys = 0.0 (the parity configuration).
 
 A "step" = one minibatch optimiser step (agents.py:284-508): batch gather, RND fwd/bwd, ViT fwd/bwd (both
 attention passes), heads, PPO/RND loss, [gradient all-reduce], Adam.   value = steps * 512 * n_gpus / time.
 `value` is timed with the rollout resident in HBM; `e2e` times the reference-facing `RNDAgent.train_model(...)`
 call with HOST numpy buffers (pinned) -- H2D of the whole rollout + all Epoch x MiniBatch steps + D2H of the stats.
-Multi-GPU: weak scaling, every rank owns 128 envs, one NCCL all-reduce of the flat gradient per step.
+Multi-GPU: weak scaling, every rank owns 128 envs, NCCL all-reduce of the flat gradient per step.
+
+Beside the headline the JSON line carries the other BASELINE configs as records (each measured live by this command):
+`cfg2_cnn_backbone` (configs[1]: original RND CNN backbone, 64 envs x 128 steps), `vit_hg_cfg4` (configs[3]: HF-style ViT
+1024/12L/16h, 256 envs over the N GPUs of the run), `numerics` (RunningMeanStd update / observation normalisation / GAE
+achieved GB/s against the measured copy peak), `sustained` (the same step over >= 200 back-to-back steps) and
+`e2e_device_rollout` (DeviceRollout.finish() -> train_model with CUDA tensors).
 """
 import argparse
 import json
@@ -135,9 +141,15 @@ def make_agent(E):
     return agent
 
 
-def cpu_reference(steps, warmup, batch=32, threads=None):
-    """The reference's CPU path for the same step (oracle port of agents.py:284-508, torch fp32, all host threads),
-    on a bounded sample: `steps` minibatches of `batch` samples of the same model."""
+def cpu_reference(steps, warmup, batch=512, threads=None, rollout=4096):
+    """The reference's CPU path for the same optimiser step, on the box's host cores: the oracle port of agents.py:284-508
+    (torch fp32, all host threads) at the BENCHED minibatch (512 samples), including what the reference does per minibatch
+    before the model runs -- it re-materialises the whole rollout as torch tensors and then indexes the minibatch
+    (agents.py:288-301: ``torch.FloatTensor(states)[batch_indices]`` for every array).  The bounded sample is the rollout
+    length that re-materialisation runs over (`rollout` samples instead of the 16 384 of cfg3, i.e. a quarter of the
+    reference's own per-minibatch copy cost); the model work per step is exactly the benched one.  The 512-sample backward
+    is evaluated in 4 chunks of 128 (identical loss and gradient, see oracle.ppo_rnd_backward_chunked) to bound autograd
+    memory."""
     from oracle import oracle as O
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -149,27 +161,43 @@ def cpu_reference(steps, warmup, batch=32, threads=None):
     opt = torch.optim.Adam([P[k] for k in names], lr=cfg.lr)
     rng = np.random.default_rng(0)
     n = batch
-    s = torch.tensor(np.float32(rng.integers(0, 256, (n, 4, 84, 84), dtype=np.uint8)) / 255.0)
-    obs = torch.tensor(rng.normal(0, 1, (n, 1, 84, 84)).clip(-5, 5), dtype=torch.float32)
-    te, ti, adv = (torch.tensor(rng.normal(0, 1, n), dtype=torch.float32) for _ in range(3))
-    y = torch.tensor(rng.integers(0, A, n))
-    old = torch.tensor(rng.normal(0, 1, (n, A)), dtype=torch.float32)
+    N = max(rollout, n)
+    states = np.float32(rng.integers(0, 256, (N, 4, 84, 84), dtype=np.uint8)) / np.float32(255.0)       # train.py:854 dtype
+    obs = rng.normal(0, 1, (N, 1, 84, 84)).clip(-5, 5)                                                  # float64, train.py:855
+    te, ti, adv = rng.normal(0, 1, N), rng.normal(0, 1, N), rng.normal(0, 1, N)                         # float64
+    y = rng.integers(0, A, N).astype(np.int64)
+    old = rng.normal(0, 1, (N // 16, 16, A)).astype(np.float32)                                         # [T, E, A]
+    sample_range = np.arange(N)
+    t_remat = [0.0]
 
     def step():
+        np.random.shuffle(sample_range)
+        bi = sample_range[:n]
+        t0 = time.perf_counter()
+        s_b = torch.FloatTensor(states)[bi]                                                             # agents.py:288
+        te_b, ti_b = torch.FloatTensor(te)[bi], torch.FloatTensor(ti)[bi]                               # :289-291
+        y_b, adv_b = torch.LongTensor(y)[bi], torch.FloatTensor(adv)[bi]                                # :293-296
+        obs_b = torch.FloatTensor(obs)[bi]                                                              # :298
+        old_b = torch.tensor(old).permute(1, 0, 2).contiguous().view(-1, A)[bi]                         # :301
+        t_remat[0] += time.perf_counter() - t0
         mask = (torch.rand(n) < cfg.update_proportion).float()
         opt.zero_grad()
-        loss, _, _ = O.ppo_rnd_loss(P, cfg, s, te, ti, y, adv, obs, old, mask)
-        loss.backward()
+        O.ppo_rnd_backward_chunked(P, cfg, s_b, te_b, ti_b, y_b, adv_b, obs_b, old_b, mask, chunk=128)
         opt.step()
     for _ in range(warmup):
         step()
+    t_remat[0] = 0.0
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
     return {"value": steps * n / dt, "unit": "samples/s", "cores": threads, "kind": "port",
-            "sample": f"{steps} optimiser steps x {n} samples of the cfg3 model (oracle port of agents.py:284-508, torch fp32, "
-                      f"dropout 0), {warmup} warm-up steps", "ms_per_step": dt / steps * 1e3}
+            "sample": f"{steps} optimiser steps x {n} samples (the benched minibatch) of the cfg3 model: oracle port of agents.py:284-508 "
+                      f"(torch fp32, dropout 0, {threads} threads), minibatch re-materialised from a {N}-sample rollout per step as the "
+                      f"reference does (agents.py:288-301; cfg3 holds 16384), {warmup} warm-up steps; 'port' because /root/reference "
+                      "does not exist on the GPU box -- tests/test_oracle_golden.py pins this port to the unmodified reference",
+            "ms_per_step": dt / steps * 1e3, "ms_per_step_rematerialisation": t_remat[0] / steps * 1e3, "batch": n,
+            "same_config": True}
 
 
 def main():
@@ -189,12 +217,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        k = max(1, min(args.steps, 8))
+        k = max(2, min(args.steps, 8))
         r = cpu_reference(k, max(1, min(args.warmup, 2)))
         line = {"impl": "reference", "metric": "PPO+RND update samples/sec", "value": r["value"], "unit": "samples/s",
                 "n_gpus": args.gpus, "steps": k, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
+                "steps_note": "bounded: at most 8 timed 512-sample optimiser steps (3-5 s each on the host cores)",
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD}, "cpu_baseline": {k2: r[k2] for k2 in ("value", "unit", "cores", "kind", "sample")},
+                "config": {"workload": WORKLOAD, "global_batch": 512},
+                "cpu_baseline": {k2: r[k2] for k2 in ("value", "unit", "cores", "kind", "sample", "same_config", "ms_per_step_rematerialisation")},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -368,7 +398,7 @@ def main():
         torch.distributed.destroy_process_group()
     if rank != 0:
         return
-    cpu = None if args.no_cpu else cpu_reference(4, 1)
+    cpu = None if args.no_cpu else cpu_reference(3, 1)
     line = {"metric": "PPO+RND update samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",

@@ -26,7 +26,9 @@ def test_cnn_forward_u8_and_f32_vs_oracle():
     assert pol.shape == (16, 18) and ve.shape == (16, 1) and vi.shape == (16, 1)
     assert rel(pol.cpu().numpy(), pol_o.numpy()) < TOL
     assert rel(ve.cpu().numpy(), ve_o.numpy()) < TOL and rel(vi.cpu().numpy(), vi_o.numpy()) < TOL
-    assert torch.equal(pol8, pol) and torch.equal(ve8, ve)        # raw frames / 255 in-kernel == np.float32(x) / 255.
+    # raw frames / 255 in-kernel == np.float32(x) / 255. bit for bit in the patch matrix; the outputs agree to summation-order
+    # noise only, because the fully-connected layers accumulate their K splits with red.add
+    assert torch.allclose(pol8, pol, rtol=1e-5, atol=1e-7) and torch.allclose(ve8, ve, rtol=1e-5, atol=1e-7)
     np.random.seed(5)
     a, v1, v2, lg = agent.get_action(state)
     np.random.seed(5)
