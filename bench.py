@@ -200,6 +200,139 @@ def cpu_reference(steps, warmup, batch=512, threads=None, rollout=4096):
             "same_config": True}
 
 
+def numerics_record(pk):
+    """SURVEY 8a rows 12-15 at the cfg3 (128 envs) and cfg5 (1024 envs) rollout sizes: achieved HBM GB/s of the
+    RunningMeanStd update and the observation normalisation for uint8 frames (what the device-resident rollout holds) and
+    float32 (what the reference's numpy path holds), against the measured copy peak; GAE is launch-latency bound
+    (<= 4.5 MB per call) and is reported as microseconds.  CUDA events around single launches, a 256 MB buffer rewritten
+    between launches (L2 flush); bytes = algorithmic read + write of the call."""
+    from eavit_b200 import ops
+    F, Tn = 84 * 84, 128
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, reps=8):
+        fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
+    rows = []
+    for E in (128, 1024):
+        N = E * Tn
+        mean = torch.zeros(F, dtype=torch.float64, device="cuda")
+        var = torch.ones(F, dtype=torch.float64, device="cuda")
+        cnt = torch.full((1,), 1e-4, dtype=torch.float64, device="cuda")
+        for dt, sz, nm in ((torch.uint8, 1, "u8"), (torch.float32, 4, "f32")):
+            x = (torch.rand(N, F, device="cuda") * 255).to(dt)
+            out = torch.empty(N, F, dtype=torch.float32, device="cuda")
+            for name, fn, nbytes in ((f"rms_update {nm}", lambda: ops.rms_update(x, mean, var, cnt), N * F * sz),
+                                     (f"obs_normalize {nm}->f32", lambda: ops.obs_normalize(x, mean, var, out=out), N * F * (sz + 4))):
+                ms = timed(fn)
+                rows.append({"kernel": name, "envs": E, "us": ms * 1e3, "mbytes": nbytes / 1e6, "gbs": nbytes / ms / 1e6,
+                             "frac_of_hbm_peak": nbytes / ms / 1e6 / pk["hbm_gbs"]})
+            del x, out
+        r = torch.rand(E, Tn, device="cuda")
+        v = torch.randn(E, Tn + 1, device="cuda")
+        done = (torch.rand(E, Tn, device="cuda") < 0.05).to(torch.uint8)
+        rows.append({"kernel": "gae_f64 (numpy-promotion exact)", "envs": E, "us": timed(lambda: ops.gae_f64(r.double(), done, v, 0.999, 0.95, 0)) * 1e3,
+                     "bound": "launch latency"})
+        rows.append({"kernel": "gae_f32 warp-shuffle scan", "envs": E, "us": timed(lambda: ops.gae_f32(r, None, v, 0.99, 0.95)) * 1e3,
+                     "bound": "launch latency"})
+    del flush
+    torch.cuda.empty_cache()
+    return {"peak_gbs": pk["hbm_gbs"], "method": "CUDA events per call, 256 MB L2 flush between calls, bytes = algorithmic read + write", "rows": rows}
+
+
+def side_agent(conf_name, E, overrides=None):
+    """A second agent on another BASELINE config.  config.default_config is a module global that constructors read once, so
+    the headline agent is unaffected by the reload."""
+    import eavit_b200  # noqa: F401
+    from eavit_b200 import agents, config, utils
+    if conf_name is None:
+        config.load_config(None, **(overrides or {}))
+    else:
+        config.load_config(os.path.join(ROOT, "configs", conf_name), **(overrides or {}))
+    c = config.default_config
+    N = E * T
+    utils.set_seed(42)
+    return agents.RNDAgent(84, A, utils.Env_action_space_type.DISCRETE, E, T, float(c["Gamma"]), GAE_Lambda=float(c["GAELambda"]),
+                           learning_rate=float(c["LearningRate"]), ent_coef=float(c["Entropy"]), epoch=1, batch_size=N // int(c["MiniBatch"]),
+                           ppo_eps=float(c["PPOEps"]), use_cuda=True, representation_lr_method="None",
+                           device=f"cuda:{torch.cuda.current_device()}", logger=utils.Logger())
+
+
+def side_record(agent, E, world, steps, flops_per_sample, label, barrier):
+    """ms/step of `agent` (device-resident synthetic rollout of E envs x 128 steps, all-reduce included when world > 1)."""
+    dev = agent.runtime().device
+    N = E * T
+    B = agent.batch_size
+    R = dict(states=torch.randint(0, 256, (N, 4, 84, 84), dtype=torch.uint8, device=dev), te=torch.randn(N, device=dev),
+             ti=torch.randn(N, device=dev), adv=torch.randn(N, device=dev), y=torch.randint(0, A, (N,), device=dev),
+             obs=torch.randn(N, 1, 84, 84, device=dev).clamp_(-5, 5), old=torch.randn(N, A, device=dev))
+    perm = torch.randperm(N, device=dev)
+    mask = (torch.rand(B, device=dev) < 0.25).float()
+    n_mb = N // B
+    agent.runtime().sync()
+    for i in range(3):
+        agent.train_step(R, perm[B * (i % n_mb): B * (i % n_mb + 1)], mask)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        agent.train_step(R, perm[B * (i % n_mb): B * (i % n_mb + 1)], mask)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    rec = {"workload": label, "n_gpus": world, "envs_per_gpu": E, "minibatch_per_gpu": B, "steps": steps, "ms_per_step": ms,
+           "value": B * world / (ms * 1e-3), "unit": "samples/s", "params": int(agent.runtime().store.numel)}
+    if flops_per_sample:
+        rec["model_tflops"] = flops_per_sample * B * world / (ms * 1e-3) / 1e12
+        rec["model_tflops_per_gpu"] = rec["model_tflops"] / world
+    del R
+    return rec
+
+
+def device_rollout_e2e(agent, E, barrier):
+    """SURVEY 8f rows 1-2 end to end on the device: a filled DeviceRollout (uint8 frames written env-major at append time)
+    -> finish() (reward filter, both GAE streams, advantage combine, obs statistics + normalisation) -> train_model with
+    the CUDA tensors it returns (no host round trip) -> D2H of the update's loss terms."""
+    from eavit_b200 import rollout, utils
+    dev = agent.runtime().device
+    ro = rollout.DeviceRollout(E, T, A, device=dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    ro.states.copy_(torch.randint(0, 256, ro.states.shape, dtype=torch.uint8, device=dev, generator=g))
+    ro.next_obs.copy_(torch.randint(0, 256, ro.next_obs.shape, dtype=torch.uint8, device=dev, generator=g))
+    ro.reward.copy_(torch.randn(E, T, device=dev, generator=g, dtype=torch.float64))
+    ro.done.copy_((torch.rand(E, T, device=dev, generator=g) < 0.05).to(torch.uint8))
+    ro.action.copy_(torch.randint(0, A, (E, T), device=dev, generator=g))
+    ro.value_ext.copy_(torch.randn(E, T + 1, device=dev, generator=g)); ro.value_int.copy_(torch.randn(E, T + 1, device=dev, generator=g))
+    ro.policy.copy_(torch.randn(E, T, A, device=dev, generator=g)); ro.int_reward.copy_(torch.rand(E, T, device=dev, generator=g))
+    obs_rms, rew_rms = utils.RunningMeanStd(shape=(1, 1, 84, 84), usage="obs_rms"), utils.RunningMeanStd(usage="reward_rms")
+    flt = utils.RewardForwardFilter(0.99)
+    obs_rms.update(ro.next_obs.view(E * T, 1, 84, 84)[: 4 * E])
+    barrier()
+    t0 = time.perf_counter()
+    args = ro.finish(obs_rms, rew_rms, flt, 0.999, 0.99, 0.95, 2.0, 1.0)
+    torch.cuda.synchronize()
+    t_fin = time.perf_counter() - t0
+    agent.train_model(*args, 1)
+    stats = agent.stats_summary()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": E * T * agent.epoch / dt, "unit": "samples/s", "seconds": dt, "finish_seconds": t_fin, "h2d_bytes_per_step": 0,
+            "d2h_bytes_per_step": 16 * 4, "loss": stats.get("loss"),
+            "call": "DeviceRollout.finish(...) -> RNDAgent.train_model(*cuda tensors): uint8 frames resident since append time"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +341,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the cfg2 / cfg4 / numerics records")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table here (json)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -357,13 +491,19 @@ def main():
     c.dropout, c.emb_dropout, c.attn_dropout, c.act_dropout = saved
     with_dropout = {"dropout": 0.1, "value": B * world / (drop_ms * 1e-3), "unit": "samples/s", "ms_per_step": drop_ms}
 
+    # ---- the same step over a long back-to-back loop (>= 200 steps ~ 1.6 s: clocks settle under the power cap)
+    sus_n = max(200, args.steps)
+    sus_ms = timed_loop(step, sus_n)
+    sustained = {"steps": sus_n, "ms_per_step": sus_ms, "value": B * world / (sus_ms * 1e-3), "unit": "samples/s",
+                 "step_executed_tflops": FLOPS_PER_SAMPLE * executed_fraction() * B / (sus_ms * 1e-3) / 1e12,
+                 "step_executed_frac_of_sustained_peak": FLOPS_PER_SAMPLE * executed_fraction() * B / (sus_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
+
     # ---- end to end through the reference-facing call (host buffers in, stats out)
-    e2e = None
-    if not args.no_e2e:
+    def e2e_run(call_args, desc):
         agent.epoch = EPOCH
         barrier()
         t0 = time.perf_counter()
-        agent.train_model(*upd_args, 1)
+        agent.train_model(*call_args, 1)
         stats = agent.stats_summary()                  # D2H read of the update's loss terms
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -372,19 +512,50 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             dt = float(t.item())
         n_steps = EPOCH * n_mb
-        h2d = sum(a.nbytes for a in upd_args)
-        # the upload is the box-dependent part of e2e: measure the host -> device rate of the largest buffer on its own
-        st_host = torch.from_numpy(upd_args[0])
+        h2d = sum(a.nbytes for a in call_args)
+        big = torch.from_numpy(call_args[0])
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        st_host.to(dev, non_blocking=True)
+        big.to(dev, non_blocking=True)
         torch.cuda.synchronize()
-        h2d_gbps = upd_args[0].nbytes / (time.perf_counter() - t1) / 1e9
-        pinned_ok = bool(st_host.is_pinned())
-        e2e = {"value": N * EPOCH * world / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d / n_steps,
-               "d2h_bytes_per_step": 16 * 4, "call": "RNDAgent.train_model(states f32, target_ext f64, target_int f64, y i64, adv f64, "
-               "next_obs f64, old_policy f32) -- numpy host buffers (pinned), one full update = 128 optimiser steps",
-               "seconds": dt, "loss": stats.get("loss"), "host_buffers_pinned": pinned_ok, "h2d_gb_per_s": h2d_gbps}
+        return {"value": N * EPOCH * world / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d / n_steps, "d2h_bytes_per_step": 16 * 4,
+                "call": desc, "seconds": dt, "loss": stats.get("loss"), "host_buffers_pinned": bool(big.is_pinned()),
+                "h2d_gb_per_s": call_args[0].nbytes / (time.perf_counter() - t1) / 1e9, "h2d_bytes_per_update": h2d}
+    e2e = e2e_ref = e2e_dev = None
+    if not args.no_e2e:
+        # what the trainer holds: raw uint8 frames (train.py:585 appends them; the / 255 of train.py:854 happens in the patch
+        # kernel, bit-identical) and the normalised next-obs as float32 (agents.py:298 converts to float32 anyway)
+        def pin(a):
+            t = torch.from_numpy(a)
+            try:
+                t = t.pin_memory()
+            except Exception:
+                pass
+            return t.numpy()
+        st, te_, ti_, y_, adv_, obs_, old_ = upd_args
+        slim = (pin(u8), te_, ti_, y_, adv_, pin(obs_.astype(np.float32)), old_)
+        e2e = e2e_run(slim, "RNDAgent.train_model(states uint8 frames, target_ext f64, target_int f64, y i64, adv f64, next_obs f32, "
+                            "old_policy f32) -- numpy host buffers (pinned), one full update = 128 optimiser steps")
+        e2e_ref = e2e_run(upd_args, "same call with the reference's own argument dtypes: states f32 (/255 on the host), next_obs f64")
+        e2e_dev = device_rollout_e2e(agent, E, barrier)
+
+    # ---- the other BASELINE configs, measured by the same command
+    hg = cnn = None
+    if not args.no_side:
+        R.clear()                                        # free the headline rollout (3 GB) before the side agents allocate
+        torch.cuda.empty_cache()
+        E_hg = max(32, 256 // max(world, 2))            # cfg4: 256 envs over 2 / 4 GPUs; a single GPU runs the 2-GPU per-GPU shape
+        a_hg = side_agent("vit_hg_explorative.conf", E_hg)
+        hg = side_record(a_hg, E_hg, world, 8, 76.43e9, "cfg4: vit_hg HF-style ViT 1024/12L/16h/3072 (50-token sequences) RND agent, "
+                         f"{E_hg} envs x 128 steps per GPU, all-reduce of the 150 M-parameter gradient included", barrier)
+        del a_hg
+        torch.cuda.empty_cache()
+        if world == 1:
+            a_cnn = side_agent(None, 64, {"ViT_implementation_type": 2, "extracted_feature_embedding_dim": 448})
+            cnn = side_record(a_cnn, 64, 1, 50, None, "cfg2: original RND CNN actor-critic backbone (model.py:110-178), 64 envs x 128 steps, "
+                              "minibatch 256", barrier)
+            del a_cnn
+            torch.cuda.empty_cache()
 
     in_sync = None
     if world > 1:
@@ -399,13 +570,16 @@ def main():
     if rank != 0:
         return
     cpu = None if args.no_cpu else cpu_reference(3, 1)
+    numerics = numerics_record(pk) if (world == 1 and not args.no_side) else None
     line = {"metric": "PPO+RND update samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B * world, "envs_per_gpu": E, "num_step": T, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2 (>= 5 GB of activations per step)", "timing": "CUDA events, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
-            "vit_fwd_bwd": vit, "with_shipped_dropout": with_dropout, "weights_in_sync_across_ranks": in_sync}
+            "vit_fwd_bwd": vit, "with_shipped_dropout": with_dropout, "weights_in_sync_across_ranks": in_sync,
+            "sustained": sustained, "e2e_reference_dtypes": e2e_ref, "e2e_device_rollout": e2e_dev, "vit_hg_cfg4": hg,
+            "cfg2_cnn_backbone": cnn, "numerics": numerics}
     print(json.dumps(line))
 
 
