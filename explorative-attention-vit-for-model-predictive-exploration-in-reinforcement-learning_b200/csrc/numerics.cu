@@ -244,6 +244,136 @@ __global__ void __launch_bounds__(256) rms_partial_u8_kernel(const uint8_t* __re
   }
 }
 
+// uint8 frames, F % 16 == 0 (84 x 84 = 441 x 16): the kernel the device-resident rollout actually uses, written for the
+// HBM roofline.  A lane reads 16 pixels per row with ONE 16-byte load (a warp = 512 contiguous bytes of a row), a CTA is
+// 32 column vectors x 8 row lanes, four rows in flight per lane; the sums stay exact 32-bit integers in registers; the 8
+// row lanes are combined through shared memory, and the LAST CTA of a column block to finish (ticket) folds every row split
+// and applies the Chan merge itself -- one launch for the whole update instead of partial + reduce + count.
+//   mode 0: write (sum, sumsq) about `shift`          (eavit_rms_partial, the multi-GPU moment exchange)
+//   mode 1: merge into mean / var / count in place     (eavit_rms_update; `shift` == mean)
+// tickets[0 .. col_blocks) count finished row splits per column block, tickets[63] finished column blocks; each is reset by
+// its last arriver, so the buffer is all-zero again when the kernel ends.
+constexpr int RMS16_ROWL = 8;
+__global__ void __launch_bounds__(256) rms_u8x16_kernel(const uint8_t* __restrict__ x, long long N, int F,
+                                                        const double* __restrict__ shift, double* __restrict__ ws,
+                                                        int rows_per_split, unsigned int* __restrict__ tickets, int mode,
+                                                        double* __restrict__ sum_out, double* __restrict__ sq_out,
+                                                        double* __restrict__ mean, double* __restrict__ var,
+                                                        double* __restrict__ count) {
+  __shared__ uint32_t red[RMS16_ROWL][2][512 + 16];          // +16: the row lanes of a column land in different banks
+  __shared__ int s_last;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 512 + cx * 16;                  // first of this lane's 16 columns
+  const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(N, r0 + rows_per_split);
+  uint32_t s[16], q[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { s[i] = 0u; q[i] = 0u; }
+  if (c0 < F) {
+    auto acc = [&](const uint4& u) {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t b = (w[k] >> (8 * j)) & 0xffu;
+          s[4 * k + j] += b;
+          q[4 * k + j] += b * b;
+        }
+    };
+    const uint8_t* p = x + r0 * F + c0;
+    long long r = r0 + ry;
+    for (; r + 3 * RMS16_ROWL < r1; r += 4 * RMS16_ROWL) {    // 4 independent 16-byte loads in flight per lane
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(p + (r - r0 + (long long)k * RMS16_ROWL) * F));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc(u[k]);
+    }
+    for (; r < r1; r += RMS16_ROWL) acc(__ldg(reinterpret_cast<const uint4*>(p + (r - r0) * F)));
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { red[ry][0][cx * 16 + i + (cx >> 1)] = s[i]; red[ry][1][cx * 16 + i + (cx >> 1)] = q[i]; }
+  __syncthreads();
+  const double n = (double)(r1 - r0);
+  double* o = ws + (long long)blockIdx.y * 2 * F;
+  for (int c = threadIdx.x; c < 512; c += 256) {
+    const int col = blockIdx.x * 512 + c;
+    if (col >= F) break;
+    unsigned long long sx = 0, sxx = 0;
+    const int sc = c + (c >> 5);
+#pragma unroll
+    for (int k = 0; k < RMS16_ROWL; ++k) { sx += red[k][0][sc]; sxx += red[k][1][sc]; }
+    const double sh = shift[col], dsx = (double)sx, dsxx = (double)sxx;
+    __stcg(o + col, dsx - n * sh);                            // sum(x - s) = Sx - n s
+    __stcg(o + F + col, fma(n * sh, sh, fma(-2.0 * sh, dsx, dsxx)));   // sum((x - s)^2) = Sxx - 2 s Sx + n s^2
+  }
+  // ---- last row split of this column block folds the splits (deterministic order) and finishes the update
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&tickets[blockIdx.x], 1u) == gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double n_b = (double)N;
+  const double n_a = mode == 1 ? count[0] : 0.0;
+  for (int c = threadIdx.x; c < 512; c += 256) {
+    const int col = blockIdx.x * 512 + c;
+    if (col >= F) break;
+    double ss = 0.0, qq = 0.0;
+    for (int k = 0; k < (int)gridDim.y; ++k) { ss += __ldcg(ws + (long long)k * 2 * F + col); qq += __ldcg(ws + (long long)k * 2 * F + F + col); }
+    if (mode == 0) { sum_out[col] = ss; sq_out[col] = qq; continue; }
+    const double old_mean = mean[col], old_var = var[col];
+    const double ds = ss / n_b;                               // batch_mean - shift, shift == old_mean
+    const double b_var = fmax(qq / n_b - ds * ds, 0.0);
+    const double tot = n_a + n_b;
+    mean[col] = old_mean + ds * n_b / tot;
+    var[col] = (old_var * n_a + b_var * n_b + ds * ds * n_a * n_b / tot) / tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tickets[blockIdx.x] = 0u;
+    __threadfence();
+    if (atomicAdd(&tickets[63], 1u) == gridDim.x - 1) {      // every column block has read the old count
+      tickets[63] = 0u;
+      if (mode == 1) count[0] = n_b + n_a;
+    }
+  }
+}
+
+static unsigned int* g_rms_tickets[64] = {nullptr};
+static unsigned int* rms_tickets() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (g_rms_tickets[dev] == nullptr) {
+    unsigned int* p = nullptr;
+    if (cudaMalloc(&p, 64 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, 64 * sizeof(unsigned int));
+    g_rms_tickets[dev] = p;
+  }
+  return g_rms_tickets[dev];
+}
+
+// whole update (mode 1) or batch moments (mode 0) of uint8 rows in ONE launch; returns false when the shape does not fit
+static bool rms_u8x16_applicable(const void* x, long long N, int F) {
+  return F % 16 == 0 && cdiv(F, 512) <= 62 && N >= 64 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+static int rms_u8x16_launch(const void* x, long long N, int F, const double* shift, double* ws, int mode, double* sum_out,
+                            double* sq_out, double* mean, double* var, double* count, cudaStream_t st) {
+  unsigned int* tk = rms_tickets();
+  if (tk == nullptr) { set_error("rms: ticket allocation failed"); return EAVIT_ECUDA; }
+  const int colb = cdiv(F, 512);
+  int splits = cdiv(4 * kNumSMs, colb);                       // ~4 CTAs of 256 threads per SM
+  if (splits > 1024) splits = 1024;
+  int rows = cdiv(N, splits);
+  if (rows < 4 * RMS16_ROWL) rows = 4 * RMS16_ROWL;
+  splits = cdiv(N, rows);
+  EAVIT_CHECK_ARG(rows / RMS16_ROWL + 1 <= 65536);           // 32-bit sums of squares stay exact per lane
+  rms_u8x16_kernel<<<dim3(colb, splits), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), N, F, shift, ws, rows, tk, mode, sum_out,
+                                                       sq_out, mean, var, count);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
 // Deterministic merge over splits; mode 0 -> write (sum, sumsq) for the moment all-reduce,
 // mode 1 -> Chan merge into the running state (utils.py:101-115).
 __global__ void rms_reduce_kernel(const double* __restrict__ ws, int splits, int F, double batch_count,
@@ -432,6 +562,92 @@ __global__ void __launch_bounds__(256) obs_normalize_u8_lut_kernel(const uint8_t
   for (; r < r1; r += 32) emit(__ldg(reinterpret_cast<const uint32_t*>(x + r * F + c)), r);
 }
 
+// uint8 frames at rollout size (N >= 8192 rows, F % 4 == 0): the table idea at full width.  Building a CTA-private table
+// costs 256 correctly-rounded float64 divisions per column and has to be amortised over >= 1024 rows per CTA, which leaves
+// too few CTAs; so the table is built ONCE per call in global memory (256 x F floats = 7.2 MB for 84 x 84: L2-resident) by a
+// small kernel, and every streaming CTA copies the slice of its 64 columns (64 KB) into shared memory with coalesced loads.
+// A warp then covers 2 rows x 64 columns: one 32-bit load (4 pixels) and one 16-byte store per lane, four conflict-free
+// table lookups -- the four lanes that share a bank look up DIFFERENT pixels of their word in each step (rotation by
+// (lane / 8) mod 4) and un-rotate the four results with selects.
+__global__ void __launch_bounds__(256) obs_lut_build_kernel(const double* __restrict__ mean, const double* __restrict__ var, int F,
+                                                            float* __restrict__ lut) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= F) return;
+  const double m = mean[c], sd = sqrt(var[c]);
+  const int v0 = blockIdx.y * 32;
+  for (int v = v0; v < v0 + 32; ++v) {
+    double z = __ddiv_rn((double)v - m, sd);
+    z = fmin(fmax(z, -5.0), 5.0);
+    lut[(size_t)v * F + c] = (float)z;
+  }
+}
+
+constexpr int LUTW = 64;                                              // columns per CTA
+template <typename O>
+__global__ void __launch_bounds__(256, 3) obs_normalize_u8_glut_kernel(const uint8_t* __restrict__ x, long long N, int F,
+                                                                       const float* __restrict__ glut, O* __restrict__ out,
+                                                                       int rows_per_split) {
+  extern __shared__ float lut[];                                       // [256 values][64 columns]
+  const int c0 = blockIdx.x * LUTW;
+  for (int i = threadIdx.x; i < 256 * (LUTW / 4); i += blockDim.x) {
+    const int v = i / (LUTW / 4), c4 = (i - v * (LUTW / 4)) * 4;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 + c4 < F) t = __ldg(reinterpret_cast<const float4*>(glut + (size_t)v * F + c0 + c4));     // F % 4 == 0
+    *reinterpret_cast<float4*>(lut + v * LUTW + c4) = t;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = lane & 15, rsub = lane >> 4;                          // 16 lanes x 4 pixels = the 64 columns of a row
+  const int c = c0 + cg * 4;
+  if (c >= F) return;
+  const int rot = ((cg >> 3) + 2 * rsub) & 3;                          // distinct for the 4 lanes that share a bank
+  const float* lcol = lut + cg * 4;
+  const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(N, r0 + rows_per_split);
+  auto emit = [&](uint32_t w, long long r) {
+    const uint32_t wr = __funnelshift_r(w, w, 8 * rot);                // byte s of wr = pixel (s + rot) & 3
+    float t[4];
+#pragma unroll
+    for (int sidx = 0; sidx < 4; ++sidx) t[sidx] = lcol[((wr >> (8 * sidx)) & 0xffu) * LUTW + ((sidx + rot) & 3)];
+    // y[p] = t[(p - rot) & 3]
+    float y[4];
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      const float a = (rot & 1) ? t[(pp + 3) & 3] : t[pp];            // rot 0/2 -> t[pp] / t[pp+2]; rot 1/3 -> t[pp+3] / t[pp+1]
+      const float b = (rot & 1) ? t[(pp + 1) & 3] : t[(pp + 2) & 3];
+      y[pp] = (rot & 2) ? b : a;
+    }
+    O* o = out + r * F + c;
+    if constexpr (sizeof(O) == 4) *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+    else *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
+  };
+  long long r = r0 + warp * 2 + rsub;                                  // a CTA pass = 8 warps x 2 rows
+  for (; r + 7 * 16 < r1; r += 8 * 16) {                               // 8 rows in flight per lane
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __ldg(reinterpret_cast<const uint32_t*>(x + (r + 16 * k) * F + c));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) emit(w[k], r + 16 * k);
+  }
+  for (; r < r1; r += 16) emit(__ldg(reinterpret_cast<const uint32_t*>(x + r * F + c)), r);
+}
+
+static float* g_obs_lut[64] = {nullptr};
+static size_t g_obs_lut_elems[64] = {0};
+// library-owned table buffer (grown on demand, never during stream capture); nullptr -> caller takes the CTA-private path
+static float* obs_lut_buffer(size_t elems, cudaStream_t st) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (g_obs_lut_elems[dev] >= elems) return g_obs_lut[dev];
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
+  float* p = nullptr;
+  if (cudaMalloc(&p, elems * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (g_obs_lut[dev] != nullptr) { cudaDeviceSynchronize(); cudaFree(g_obs_lut[dev]); }
+  g_obs_lut[dev] = p;
+  g_obs_lut_elems[dev] = elems;
+  return p;
+}
+
 template <typename T, typename O>
 static int obs_normalize_launch(const void* x, long long N, int F, const double* mean, const double* var, void* out,
                                 cudaStream_t st) {
@@ -439,6 +655,27 @@ static int obs_normalize_launch(const void* x, long long N, int F, const double*
   EAVIT_CHECK_ARG(F % V == 0);
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if constexpr (sizeof(T) == 1) {
+    if (N >= 8192 && F % 4 == 0 && F >= LUTW) {
+      float* glut = obs_lut_buffer((size_t)256 * F, st);
+      if (glut != nullptr) {
+        static bool attr_done = false;
+        if (!attr_done) {
+          EAVIT_CUDA(cudaFuncSetAttribute(obs_normalize_u8_glut_kernel<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * LUTW * 4));
+          attr_done = true;
+        }
+        obs_lut_build_kernel<<<dim3(cdiv(F, 256), 8), 256, 0, st>>>(mean, var, F, glut);
+        EAVIT_LAUNCH_OK();
+        const int colb = cdiv(F, LUTW);
+        int splits = cdiv(6 * kNumSMs, colb);                          // ~3 resident CTAs per SM, two waves
+        int rows = cdiv(N, splits);
+        if (rows < 1024) rows = 1024;                                  // the 64 KB table copy is amortised over >= 1024 rows
+        rows = (rows + 15) & ~15;
+        obs_normalize_u8_glut_kernel<O><<<dim3(colb, cdiv(N, rows)), 256, 256 * LUTW * 4, st>>>(
+            reinterpret_cast<const uint8_t*>(x), N, F, glut, reinterpret_cast<O*>(out), rows);
+        EAVIT_LAUNCH_OK();
+        return EAVIT_OK;
+      }
+    }
     if (N >= 2048 && F % 4 == 0) {                                     // table build (8192 divisions / CTA) amortised over >= 1024 rows
       int splits = (int)((N + 2047) / 2048);
       const int colg = cdiv(F, 32);
@@ -573,6 +810,8 @@ int eavit_rms_update(const void* x, int x_dtype, long long N, int F, double* mea
                      void* workspace, void* stream) {
   EAVIT_CHECK_ARG(N > 0 && F > 0 && x && mean && var && count && workspace);
   cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == EAVIT_U8 && rms_u8x16_applicable(x, N, F))
+    return rms_u8x16_launch(x, N, F, mean, (double*)workspace, 1, nullptr, nullptr, mean, var, count, st);
   int splits = 0;
   int rc = rms_partial_dispatch(x, x_dtype, N, F, mean, (double*)workspace, splits, st);
   if (rc) return rc;
@@ -588,6 +827,8 @@ int eavit_rms_partial(const void* x, int x_dtype, long long N, int F, const doub
                       void* workspace, void* stream) {
   EAVIT_CHECK_ARG(N > 0 && F > 0 && x && shift && sum && sumsq && workspace);
   cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == EAVIT_U8 && rms_u8x16_applicable(x, N, F))
+    return rms_u8x16_launch(x, N, F, shift, (double*)workspace, 0, sum, sumsq, nullptr, nullptr, nullptr, st);
   int splits = 0;
   int rc = rms_partial_dispatch(x, x_dtype, N, F, shift, (double*)workspace, splits, st);
   if (rc) return rc;

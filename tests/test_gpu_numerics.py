@@ -131,3 +131,37 @@ def test_intrinsic_mse(ops):
     t, p = rng.normal(size=(77, 512)).astype(np.float32), rng.normal(size=(77, 512)).astype(np.float32)
     ref = (torch.tensor(t) - torch.tensor(p)).pow(2).mean(1).numpy()
     np.testing.assert_allclose(ops.intrinsic_mse(dev(t), dev(p)).cpu().numpy(), ref, rtol=1e-5)
+
+
+@pytest.mark.parametrize("N,hw", [(8192, 84), (12345, 84), (16384, 84), (8200, 20), (300, 20), (4100, 6)])
+def test_u8_rollout_size_paths(ops, N, hw):
+    """uint8 frames at rollout size: the single-launch 16-pixels-per-lane RunningMeanStd update (ticketed last-CTA merge,
+    utils.py:83-115) and the global-table normalisation (train.py:666 / :855) -- float64 statistics within round-off of
+    numpy, normalised float32 output bit-identical; ragged row counts, F < one column block, F % 16 != 0 (fallback path)."""
+    rng = np.random.default_rng(N + hw)
+    F = hw * hw
+    x = rng.integers(0, 256, (N, 1, hw, hw), dtype=np.uint8)
+    rms = O.RunningMeanStd(shape=(1, 1, hw, hw))
+    mean = torch.zeros(F, dtype=torch.float64, device="cuda")
+    var = torch.ones(F, dtype=torch.float64, device="cuda")
+    cnt = torch.full((1,), 1e-4, dtype=torch.float64, device="cuda")
+    xd = dev(x)
+    for rep in range(3):                               # repeated calls: tickets must be back at zero, Chan merge chains
+        xx = x if rep != 1 else (255 - x)
+        rms.update(xx.astype(np.float64))
+        ops.rms_update(xd if rep != 1 else 255 - xd, mean, var, cnt)
+    np.testing.assert_allclose(mean.cpu().numpy(), rms.mean.reshape(-1), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(var.cpu().numpy(), rms.var.reshape(-1), rtol=1e-10, atol=1e-10)
+    assert abs(cnt.item() - rms.count) < 1e-6
+    # batch moments about a shift (the multi-GPU exchange) == numpy
+    sh = dev(rms.mean.reshape(-1))
+    s, q = ops.rms_partial(xd.view(N, F), sh)
+    d = x.reshape(N, F).astype(np.float64) - rms.mean.reshape(-1)
+    np.testing.assert_allclose(s.cpu().numpy(), d.sum(0), rtol=1e-9, atol=1e-6)
+    np.testing.assert_allclose(q.cpu().numpy(), (d * d).sum(0), rtol=1e-11)
+    m, v = dev(rms.mean.reshape(-1)), dev(rms.var.reshape(-1))
+    ref = torch.FloatTensor(O.normalize_obs(x.astype(np.float64), rms)).numpy()
+    got = ops.obs_normalize(xd, m, v).cpu().numpy()
+    assert np.array_equal(got, ref)
+    got16 = ops.obs_normalize(xd, m, v, out_dtype=torch.bfloat16)
+    assert torch.equal(got16.cpu(), torch.from_numpy(ref).to(torch.bfloat16))
