@@ -57,6 +57,37 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// ---------------------------------------------------------------------------------------------------- GELU by table
+// The GELU epilogues were instruction-issue bound (ncu r1: 53-66 % issue-active, ~30 instructions and 2 MUFU per element,
+// 180 us of pure issue time for the [201216, 1024] MLP activations against 143 us of HBM time).  Both take their argument
+// as a BFLOAT16 value -- the stored pre-activation `hpre` -- and a bf16 has only 2^16 bit patterns: with |x| clamped to
+// [2^-14, 8) (below: Phi = 0.5 +- 1e-5, gelu' = 0.5 +- 4e-5; above: 0 / 1 to fp32 accuracy) 2 x 2176 entries cover every
+// input.  Each CTA builds the 17 KB fp32 table in its prologue (normcdff / expf, under the previous kernel's tail) and
+// the epilogue does one shared-memory lookup per element:
+//   forward   h = v * Phi(bf16(v))            v = fp32 accumulator + bias; bf16(v) is the pre-activation that is stored anyway
+//   backward  dh = dy * gelu'(hpre)           gelu'(x) = Phi(x) + x phi(x)
+// Evaluating Phi at the rounded argument costs |v| phi(v) |v| 2^-9 <= 6e-4 absolute on h, a quarter of the bf16 rounding of
+// h itself (vit.py:30 nn.GELU(): exact-erf GELU).
+constexpr int GELU_LUT_LO = 0x3880;                 // bf16 bits of 2^-14
+constexpr int GELU_LUT_HI = 0x4100;                 // bf16 bits of 8.0
+constexpr int GELU_LUT_N = GELU_LUT_HI - GELU_LUT_LO;       // 2176 magnitudes per sign
+constexpr int GELU_LUT_BYTES = 2 * GELU_LUT_N * 4;
+
+template <bool GRAD>
+__device__ __forceinline__ void gelu_lut_build(float* lut, int tid, int nthreads) {
+  for (int i = tid; i < 2 * GELU_LUT_N; i += nthreads) {
+    const int sgn = i >= GELU_LUT_N, a = (sgn ? i - GELU_LUT_N : i) + GELU_LUT_LO;
+    const float x = __uint_as_float(((uint32_t)(sgn << 15 | a)) << 16);
+    const float cdf = normcdff(x);
+    lut[i] = GRAD ? fmaf(x * 0.39894228040143268f, __expf(-0.5f * x * x), cdf) : cdf;
+  }
+}
+// table entry for the bf16 value whose bits are the low 16 bits of `b`
+__device__ __forceinline__ float gelu_lut(const float* lut, uint32_t b) {
+  const int a = min(max((int)(b & 0x7fffu), GELU_LUT_LO), GELU_LUT_HI - 1) - GELU_LUT_LO;
+  return lut[a + (int)((b >> 15) & 1u) * GELU_LUT_N];
+}
+
 __device__ __forceinline__ float apply_act(float v, int act, float a) {
   switch (act) {
     case EAVIT_ACT_GELU: return gelu_erf(v);
@@ -76,6 +107,8 @@ enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, 
 // atomic epilogues are HBM-bound and want registers for loads in flight instead: 8 warps.
 template <int EPI> struct EpiWarps { static constexpr int N = (EPI == E_GELU_FWD || EPI == E_STORE) ? 16 : (EPI == E_GELU_BWD ? 12 : 8); };
 
+template <int EPI> struct EpiLut { static constexpr int BYTES = (EPI == E_GELU_FWD || EPI == E_GELU_BWD) ? GELU_LUT_BYTES : 0; };
+
 template <int BN, int EPI, bool DROP>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
 __global__ void __launch_bounds__((CTRL_WARPS + EpiWarps<EPI>::N) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -92,6 +125,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* acc_full = bars + 2 * STAGES;         // [2]        MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2;    // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* gelu_tab = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + 256);   // behind the barrier block
+  if constexpr (EPI == E_GELU_FWD) gelu_lut_build<false>(gelu_tab, threadIdx.x, blockDim.x);
+  if constexpr (EPI == E_GELU_BWD) gelu_lut_build<true>(gelu_tab, threadIdx.x, blockDim.x);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
@@ -257,14 +293,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const float4 t = *reinterpret_cast<const float4*>(tile + rr * 32 + ((cchunk ^ (rr & 7)) << 2));
             float v[4] = {t.x + b4.x, t.y + b4.y, t.z + b4.z, t.w + b4.w};
             const size_t off = off0 + it * ostep;
-            if (has_pre)
-              *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
             if constexpr (EPI == E_GELU_FWD) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
-            } else if constexpr (EPI == E_GELU_BWD) {
-              v[0] *= gelu_erf_grad(__uint_as_float(ax[it].x << 16)); v[1] *= gelu_erf_grad(__uint_as_float(ax[it].x & 0xffff0000u));
-              v[2] *= gelu_erf_grad(__uint_as_float(ax[it].y << 16)); v[3] *= gelu_erf_grad(__uint_as_float(ax[it].y & 0xffff0000u));
+              const uint32_t p01 = pack_bf16x2(v[0], v[1]), p23 = pack_bf16x2(v[2], v[3]);      // the stored pre-activation
+              *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(p01, p23);
+              v[0] *= gelu_lut(gelu_tab, p01); v[1] *= gelu_lut(gelu_tab, p01 >> 16);
+              v[2] *= gelu_lut(gelu_tab, p23); v[3] *= gelu_lut(gelu_tab, p23 >> 16);
+            } else if (has_pre) {
+              *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            }
+            if constexpr (EPI == E_GELU_BWD) {
+              v[0] *= gelu_lut(gelu_tab, ax[it].x); v[1] *= gelu_lut(gelu_tab, ax[it].x >> 16);
+              v[2] *= gelu_lut(gelu_tab, ax[it].y); v[3] *= gelu_lut(gelu_tab, ax[it].y >> 16);
             } else if constexpr (GEN) {
               if (p.act != EAVIT_ACT_NONE) {
                 float a[4] = {0.f, 0.f, 0.f, 0.f};
@@ -383,7 +422,7 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::SMEM_BYTES));
+                                    Cfg::SMEM_BYTES + EpiLut<EPI>::BYTES));
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
@@ -421,7 +460,8 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3((CTRL_WARPS + EpiWarps<EPI>::N) * 32);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES + EpiLut<EPI>::BYTES;
+  static_assert(Cfg::SMEM_BYTES + EpiLut<EPI>::BYTES <= 232448, "over the 227 KB shared-memory limit of a CTA");
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

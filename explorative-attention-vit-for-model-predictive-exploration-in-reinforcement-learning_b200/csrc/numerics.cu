@@ -374,7 +374,8 @@ static int rms_u8x16_launch(const void* x, long long N, int F, const double* shi
   unsigned int* tk = rms_tickets();
   if (tk == nullptr) { set_error("rms: ticket allocation failed"); return EAVIT_ECUDA; }
   const int colb = cdiv(F, 512);
-  int splits = cdiv(4 * kNumSMs, colb);                       // ~4 CTAs of 256 threads per SM
+  int splits = (4 * kNumSMs) / colb;                          // one wave: <= 4 resident CTAs of 256 threads per SM (58 registers)
+  if (splits < 1) splits = 1;
   if (splits > 1024) splits = 1024;
   int rows = cdiv(N, splits);
   if (rows < 4 * RMS16_ROWL) rows = 4 * RMS16_ROWL;
@@ -428,7 +429,8 @@ __global__ void add_count_kernel(double* count, double n_b) { count[0] = n_b + c
 
 static int rms_splits(long long N, int F, int V) {
   const int col_blocks = cdiv(cdiv(F, V), 256);
-  long long want = (8LL * kNumSMs + col_blocks - 1) / col_blocks;   // ~8 CTAs per SM (loads are not software-pipelined)
+  long long want = (8LL * kNumSMs) / col_blocks;                    // <= 8 CTAs per SM = two full waves of 4 resident CTAs (rounding
+                                                                    // UP put 6 CTAs into a third wave: +50 % on a 120 us kernel)
   if (want > N) want = N;
   if (want < 1) want = 1;
   if (want > 1024) want = 1024;
