@@ -320,6 +320,26 @@ class RNDAgent(nn.Module):
                 (not p.requires_grad) for n, p in rt.params.items() if n.startswith("model.feature."))
         return self._train_ranges
 
+    def _layer_ranges(self, rt, li):
+        cache = getattr(rt, "_layer_range_cache", None)
+        if cache is None:
+            cache = rt._layer_range_cache = {}
+        if li not in cache:
+            cache[li] = rt.store.name_ranges(rt.encoder.layer_param_names(li))
+        return cache[li]
+
+    @staticmethod
+    def _complement(ranges, n):
+        """[0, n) minus the given disjoint [lo, hi) ranges, as merged ranges."""
+        out, pos = [], 0
+        for lo, hi in sorted(ranges):
+            if lo > pos:
+                out.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < n:
+            out.append((pos, n))
+        return out
+
     def _side_stream(self, rt):
         s = getattr(rt, "_side", None)
         if s is None:
@@ -399,7 +419,20 @@ class RNDAgent(nn.Module):
         call("eavit_ppo_loss", pol, w["old"], w["y"], w["adv"], ve, vi, w["te"], w["ti"], B, A, float(self.ppo_eps),
              float(self.ent_coef), gs, w["dpol"], w["dv"][B:], w["dv"][:B], w["stats"])
         train_ranges = self._trainable_ranges(rt)
-        rt.ac_backward(w["dpol"], w["dv"], backbone=not (train_ranges is not None and self._backbone_frozen))
+        # Data-parallel: the gradient exchange rides under the backward.  Each transformer layer's tensors are one contiguous
+        # block of the flat gradient; its all-reduce starts on the process group's stream as soon as the layer's last
+        # gradient kernel is enqueued (reverse layer order), so only the embedding / heads remainder is left for the end
+        # (replaces the reference's never-armed DDP reducer, train.py:243).
+        pending, done_ranges = [], []
+        overlap = (self.world_size > 1 and train_ranges is None and os.environ.get("EAVIT_GRAD_OVERLAP", "1") == "1"
+                   and hasattr(rt.encoder, "layer_param_names"))
+
+        def on_layer_done(li):
+            for lo, hi in self._layer_ranges(rt, li):
+                pending.append(dist.allreduce_sum_async(st.grad[lo:hi]))
+                done_ranges.append((lo, hi))
+        rt.ac_backward(w["dpol"], w["dv"], backbone=not (train_ranges is not None and self._backbone_frozen),
+                       on_layer_done=on_layer_done if overlap else None)
         if side is not None:
             cur.wait_stream(side)
         if train_ranges is not None:                                     # frozen tensors: no gradient (torch leaves .grad = None)
@@ -407,13 +440,12 @@ class RNDAgent(nn.Module):
                 call("eavit_zero", st.grad[lo:hi], (hi - lo) * 4)
         call("eavit_add_f32", w["stats"], w["rnd_stats"], w["stats"], 16)
         if self.world_size > 1:                                          # NCCL all-reduce (sum); the mean is applied inside Adam
-            if early is None:
-                dist.allreduce_sum_(st.grad)
-            else:
-                if early[0] > 0:
-                    dist.allreduce_sum_(st.grad[:early[0]])
-                if early[1] < st.numel:
-                    dist.allreduce_sum_(st.grad[early[1]:])
+            if early is not None:
+                done_ranges.append(tuple(early))
+            for lo, hi in self._complement(done_ranges, st.numel):       # whatever has not been exchanged under the backward
+                dist.allreduce_sum_(st.grad[lo:hi])
+            for h in pending:
+                h.wait()
         if default_config.getboolean("UseGradClipping", fallback=False):
             nrm = torch.zeros(1, dtype=torch.float32, device=rt.device)
             call("eavit_sumsq_f32", st.grad, st.numel, nrm)

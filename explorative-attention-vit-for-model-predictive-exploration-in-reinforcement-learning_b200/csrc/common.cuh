@@ -95,6 +95,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float tail = gelu_tail(x, e);
   return fmaf(-fabsf(x), tail, fmaxf(x, 0.f));
 }
+// gelu(x) and gelu'(x) from one tail / exp evaluation (the forward epilogue that also stores the derivative)
+__device__ __forceinline__ float gelu_erf_and_grad(float x, float& grad) {
+  float e;
+  const float tail = gelu_tail(x, e);
+  const float cdf = (x >= 0.f ? 1.0f : 0.0f) - copysignf(tail, x);
+  grad = fmaf(x * 0.39894228040143268f, e, cdf);
+  return fmaf(-fabsf(x), tail, fmaxf(x, 0.f));
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float e;
   const float tail = gelu_tail(x, e);

@@ -45,7 +45,17 @@ struct GemmKernelParams {
   DropCfg drop;
   int act;
   int atomic_f32;
+  int cs_smem;        // column sums requested: per-warp private partial sums in shared memory
 };
+
+// Fused column sums (bias gradients): the first version issued one global red.add per (warp, chunk, column) -- 6 288 adds
+// onto each of the 1 024 addresses of the MLP bias gradient per launch, which serialise in L2 and cost 170 us of the 345 us
+// GELU' GEMM (r2 experiment: the same epilogue without them ran in 186 us); shared-memory float atomics (a CAS loop under
+// contention from the four lane quadrants) were no better.  Now every epilogue warp keeps PRIVATE partial sums in shared
+// memory -- slot (warp, chunk-of-this-warp, column-in-chunk), plain read-modify-write by the one lane that owns the column --
+// and flushes them with global adds only when its CTA moves to another column block or ends.  With 148 persistent CTAs and
+// 1, 2 or 4 column blocks a CTA never changes its column block: 148 adds per address and launch.
+constexpr int SMEM_LIMIT = 232448;                // 227 KB per CTA
 
 template <int BN>
 struct GemmCfg {
@@ -55,43 +65,27 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;    // power of two >= 32 for BN in {64,128,256}
   static constexpr int EPI_BYTES = MAX_EPI_WARPS * EPI_TILE_FLOATS * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
 };
 
-// ---------------------------------------------------------------------------------------------------- GELU by table
-// The GELU epilogues were instruction-issue bound (ncu r1: 53-66 % issue-active, ~30 instructions and 2 MUFU per element,
-// 180 us of pure issue time for the [201216, 1024] MLP activations against 143 us of HBM time).  Both take their argument
-// as a BFLOAT16 value -- the stored pre-activation `hpre` -- and a bf16 has only 2^16 bit patterns: with |x| clamped to
-// [2^-14, 8) (below: Phi = 0.5 +- 1e-5, gelu' = 0.5 +- 4e-5; above: 0 / 1 to fp32 accuracy) 2 x 2176 entries cover every
-// input.  Each CTA builds the 17 KB fp32 table in its prologue (normcdff / expf, under the previous kernel's tail) and
-// the epilogue does one shared-memory lookup per element:
-//   forward   h = v * Phi(bf16(v))            v = fp32 accumulator + bias; bf16(v) is the pre-activation that is stored anyway
-//   backward  dh = dy * gelu'(hpre)           gelu'(x) = Phi(x) + x phi(x)
-// Evaluating Phi at the rounded argument costs |v| phi(v) |v| 2^-9 <= 6e-4 absolute on h, a quarter of the bf16 rounding of
-// h itself (vit.py:30 nn.GELU(): exact-erf GELU).
-constexpr int GELU_LUT_LO = 0x3880;                 // bf16 bits of 2^-14
-constexpr int GELU_LUT_HI = 0x4100;                 // bf16 bits of 8.0
-constexpr int GELU_LUT_N = GELU_LUT_HI - GELU_LUT_LO;       // 2176 magnitudes per sign
-constexpr int GELU_LUT_BYTES = 2 * GELU_LUT_N * 4;
-
-template <bool GRAD>
-__device__ __forceinline__ void gelu_lut_build(float* lut, int tid, int nthreads) {
-  for (int i = tid; i < 2 * GELU_LUT_N; i += nthreads) {
-    const int sgn = i >= GELU_LUT_N, a = (sgn ? i - GELU_LUT_N : i) + GELU_LUT_LO;
-    const float x = __uint_as_float(((uint32_t)(sgn << 15 | a)) << 16);
-    const float cdf = normcdff(x);
-    lut[i] = GRAD ? fmaf(x * 0.39894228040143268f, __expf(-0.5f * x * x), cdf) : cdf;
-  }
-}
-// table entry for the bf16 value whose bits are the low 16 bits of `b`
-__device__ __forceinline__ float gelu_lut(const float* lut, uint32_t b) {
-  const int a = min(max((int)(b & 0x7fffu), GELU_LUT_LO), GELU_LUT_HI - 1) - GELU_LUT_LO;
-  return lut[a + (int)((b >> 15) & 1u) * GELU_LUT_N];
-}
+// shared memory of one CTA: TMA stages | EW transpose tiles | barrier block | EW x CS_SLOTS x 32 private column sums
+template <int BN, int EW>
+struct GemmSmem {
+  static constexpr int EPI_BYTES = EW * EPI_TILE_FLOATS * 4;
+  static constexpr int CS_SLOTS = (BN / 32 + EW / 4 - 1) / (EW / 4);            // 32-column chunks one warp handles per tile
+  static constexpr int CS_BYTES = EW * CS_SLOTS * 32 * 4;
+  static constexpr int OFF_EPI = GemmCfg<BN>::STAGES * GemmCfg<BN>::STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
+  static constexpr int OFF_CS = OFF_BAR + 256;
+  static constexpr int TOTAL = OFF_CS + CS_BYTES + 1024 /*align slack*/;
+  static_assert(TOTAL <= SMEM_LIMIT, "over the 227 KB shared-memory limit of a CTA");
+};
 
 __device__ __forceinline__ float apply_act(float v, int act, float a) {
   switch (act) {
     case EAVIT_ACT_GELU: return gelu_erf(v);
     case EAVIT_ACT_GELU_BWD: return v * gelu_erf_grad(a);
+    case EAVIT_ACT_MUL_AUX: return v * a;
     case EAVIT_ACT_LRELU: return v > 0.f ? v : 0.01f * v;
     case EAVIT_ACT_LRELU_BWD: return a > 0.f ? v : 0.01f * v;
     case EAVIT_ACT_RELU: return fmaxf(v, 0.f);
@@ -102,12 +96,16 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
 
 // Epilogue specialisations (compile-time): the epilogue is instruction-issue bound (ncu: 45 % issue-active from only 8
 // warps), so the common fused forms drop every per-element runtime branch of the generic path.
-enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5 };
+enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5, E_GELU_FWD_D = 6, E_MUL_AUX = 7 };
+// E_GELU_FWD_D / E_MUL_AUX (EAVIT_ACT_GELU_SAVE_GRAD / EAVIT_ACT_MUL_AUX): the forward stores gelu'(v) -- evaluated from the
+// fp32 pre-activation with the exp and tail it computes anyway -- where E_GELU_FWD stores v, and the backward epilogue is
+// one multiply instead of ~19 instructions and 2 MUFU per element.  These epilogues are bound by the serial instruction
+// stream of each warp (r2 experiment, [201216,1024] x K=256: GELU' 325 us, multiply-only 252 us, store-only 186 us).
 // The GELU epilogues are issue/latency-bound (16 instructions + 2 MUFU per element): 16 warps.  The store / residual /
 // atomic epilogues are HBM-bound and want registers for loads in flight instead: 8 warps.
-template <int EPI> struct EpiWarps { static constexpr int N = (EPI == E_GELU_FWD || EPI == E_STORE) ? 16 : (EPI == E_GELU_BWD ? 12 : 8); };
-
-template <int EPI> struct EpiLut { static constexpr int BYTES = (EPI == E_GELU_FWD || EPI == E_GELU_BWD) ? GELU_LUT_BYTES : 0; };
+template <int EPI> struct EpiWarps {
+  static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_STORE) ? 16 : ((EPI == E_GELU_BWD || EPI == E_MUL_AUX) ? 12 : 8);
+};
 
 template <int BN, int EPI, bool DROP>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
 __global__ void __launch_bounds__((CTRL_WARPS + EpiWarps<EPI>::N) * 32, 1)
@@ -118,16 +116,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   constexpr int EPI_WARPS = EpiWarps<EPI>::N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+  using Sm = GemmSmem<BN, EPI_WARPS>;
+  float* epi_smem = reinterpret_cast<float*>(smem + Sm::OFF_EPI);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Sm::OFF_BAR);
   uint64_t* full_bar = bars;                      // [STAGES]   TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;            // [STAGES]   MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;         // [2]        MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2;    // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* gelu_tab = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + 256);   // behind the barrier block
-  if constexpr (EPI == E_GELU_FWD) gelu_lut_build<false>(gelu_tab, threadIdx.x, blockDim.x);
-  if constexpr (EPI == E_GELU_BWD) gelu_lut_build<true>(gelu_tab, threadIdx.x, blockDim.x);
+  float* s_cs = reinterpret_cast<float*>(smem + Sm::OFF_CS);                     // behind the barrier block
+  if (p.cs_smem)
+    for (int i = threadIdx.x; i < Sm::CS_BYTES / 4; i += blockDim.x) s_cs[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
@@ -228,16 +227,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int par = e >> 2;                           // first 32-column chunk handled by this warp
     float* tile = epi_smem + e * EPI_TILE_FLOATS;
     constexpr bool GEN = EPI == E_GENERIC;
-    const bool need_aux = GEN ? (p.act == EAVIT_ACT_GELU_BWD || p.act == EAVIT_ACT_LRELU_BWD || p.act == EAVIT_ACT_RELU_BWD) : (EPI == E_GELU_BWD);
-    const bool has_bias = GEN || EPI == E_STORE ? (p.bias != nullptr) : (EPI == E_GELU_FWD || EPI == E_RESID);
+    const bool need_aux = GEN ? (p.act == EAVIT_ACT_GELU_BWD || p.act == EAVIT_ACT_LRELU_BWD || p.act == EAVIT_ACT_RELU_BWD || p.act == EAVIT_ACT_MUL_AUX)
+                              : (EPI == E_GELU_BWD || EPI == E_MUL_AUX);
+    const bool has_bias = GEN || EPI == E_STORE ? (p.bias != nullptr) : (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_RESID);
     const bool has_pre = GEN ? (p.out_pre != nullptr) : (EPI == E_GELU_FWD);
     const bool has_res = GEN ? (p.residual != nullptr) : (EPI == E_RESID);
     const bool out_f32 = GEN || EPI == E_STORE ? (p.out_f32 != nullptr) : (EPI == E_RESID || EPI == E_ATOMIC);
-    const bool out_b16 = GEN || EPI == E_STORE ? (p.out_bf16 != nullptr) : (EPI == E_GELU_FWD || EPI == E_GELU_BWD);
+    const bool out_b16 = GEN || EPI == E_STORE ? (p.out_bf16 != nullptr) : (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_GELU_BWD || EPI == E_MUL_AUX);
     const bool atomic = GEN ? (p.atomic_f32 != 0) : (EPI == E_ATOMIC);
+    constexpr int CS_SLOTS = Sm::CS_SLOTS;                                         // chunks one warp handles per tile
+    float* my_cs = s_cs + e * CS_SLOTS * 32;                                       // this warp's private partial sums
+    int cs_nblk = -1;                                                              // column block the partial sums belong to
+    auto cs_flush = [&]() {                                                        // warp-uniform
+      if (cs_nblk >= 0) {
+#pragma unroll 1
+        for (int k = 0; k < CS_SLOTS; ++k) {
+          const int col = cs_nblk * BN + (par + k * (EPI_WARPS / 4)) * 32 + lane;
+          const float t = my_cs[k * 32 + lane];
+          my_cs[k * 32 + lane] = 0.f;
+          if (par + k * (EPI_WARPS / 4) < BN / 32 && col < p.N && t != 0.f) atomicAdd(p.colsum + col, t);
+        }
+      }
+      __syncwarp();
+    };
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
       const int n_blk = tile_i % p.n_tiles, m_blk = (tile_i / p.n_tiles) % p.m_tiles;
+      if (p.cs_smem && n_blk != cs_nblk) { cs_flush(); cs_nblk = n_blk; }
       tc::mbar_wait(&acc_full[acc], acc_phase);
       tc::fence_after_sync();
       const int row0 = m_blk * BM + q * 32;
@@ -248,7 +264,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (col0 >= p.N) break;                        // warp-uniform
         const int cchunk = lane & 7, rsub = lane >> 3;
         const int col = col0 + cchunk * 4;
-        constexpr bool CS = GEN || EPI == E_GELU_BWD;    // epilogues that can carry a fused column sum
+        constexpr bool CS = GEN || EPI == E_GELU_BWD || EPI == E_MUL_AUX;    // epilogues that can carry a fused column sum
         const size_t off0 = (size_t)(row0 + rsub) * (size_t)p.ldc + col;      // row rr = rsub + 4 * it
         const size_t ostep = 4 * (size_t)p.ldc;
         // Issue every global read of this chunk FIRST (8 independent 16-byte loads per lane: the epilogue is latency-
@@ -293,19 +309,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const float4 t = *reinterpret_cast<const float4*>(tile + rr * 32 + ((cchunk ^ (rr & 7)) << 2));
             float v[4] = {t.x + b4.x, t.y + b4.y, t.z + b4.z, t.w + b4.w};
             const size_t off = off0 + it * ostep;
-            if constexpr (EPI == E_GELU_FWD) {
-              const uint32_t p01 = pack_bf16x2(v[0], v[1]), p23 = pack_bf16x2(v[2], v[3]);      // the stored pre-activation
-              *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(p01, p23);
-              v[0] *= gelu_lut(gelu_tab, p01); v[1] *= gelu_lut(gelu_tab, p01 >> 16);
-              v[2] *= gelu_lut(gelu_tab, p23); v[3] *= gelu_lut(gelu_tab, p23 >> 16);
-            } else if (has_pre) {
+            if (has_pre && !(GEN && p.act == EAVIT_ACT_GELU_SAVE_GRAD))
               *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-            }
-            if constexpr (EPI == E_GELU_BWD) {
-              v[0] *= gelu_lut(gelu_tab, ax[it].x); v[1] *= gelu_lut(gelu_tab, ax[it].x >> 16);
-              v[2] *= gelu_lut(gelu_tab, ax[it].y); v[3] *= gelu_lut(gelu_tab, ax[it].y >> 16);
+            if constexpr (EPI == E_GELU_FWD) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
+            } else if constexpr (EPI == E_GELU_FWD_D) {
+              float g[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[i] = gelu_erf_and_grad(v[i], g[i]);
+              *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
+            } else if constexpr (EPI == E_MUL_AUX) {
+              v[0] *= __uint_as_float(ax[it].x << 16); v[1] *= __uint_as_float(ax[it].x & 0xffff0000u);
+              v[2] *= __uint_as_float(ax[it].y << 16); v[3] *= __uint_as_float(ax[it].y & 0xffff0000u);
+            } else if constexpr (EPI == E_GELU_BWD) {
+              v[0] *= gelu_erf_grad(__uint_as_float(ax[it].x << 16)); v[1] *= gelu_erf_grad(__uint_as_float(ax[it].x & 0xffff0000u));
+              v[2] *= gelu_erf_grad(__uint_as_float(ax[it].y << 16)); v[3] *= gelu_erf_grad(__uint_as_float(ax[it].y & 0xffff0000u));
             } else if constexpr (GEN) {
-              if (p.act != EAVIT_ACT_NONE) {
+              if (p.act == EAVIT_ACT_GELU_SAVE_GRAD) {
+                float g[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = gelu_erf_and_grad(v[i], g[i]);
+                if (p.out_pre != nullptr)
+                  *reinterpret_cast<uint2*>(p.out_pre + off) = make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
+              } else if (p.act != EAVIT_ACT_NONE) {
                 float a[4] = {0.f, 0.f, 0.f, 0.f};
                 if (need_aux) {
                   const float2 lo = unpack_bf16x2(ax[it].x), hi = unpack_bf16x2(ax[it].y);
@@ -348,9 +375,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
             cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
           }
-          if (rsub == 0 && col < p.N) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
+          if (rsub == 0 && col < p.N) {                 // lanes 0..7 own columns cchunk*4 .. +3 of slot (c - par) / warps-per-quadrant
+            float4* slot = reinterpret_cast<float4*>(my_cs + ((c - par) / (EPI_WARPS / 4)) * 32 + cchunk * 4);
+            float4 t = *slot;
+            t.x += cs[0]; t.y += cs[1]; t.z += cs[2]; t.w += cs[3];
+            *slot = t;
           }
         }
         __syncwarp();
@@ -360,6 +389,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.cs_smem) cs_flush();
   }
 
   tc::fence_before_sync();
@@ -422,7 +452,7 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::SMEM_BYTES + EpiLut<EPI>::BYTES));
+                                    GemmSmem<BN, EpiWarps<EPI>::N>::TOTAL));
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
@@ -455,13 +485,13 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   p.ldc = a->ldc;
   p.act = a->act;
   p.atomic_f32 = a->atomic_f32;
+  p.cs_smem = a->colsum != nullptr ? 1 : 0;
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < kNumSMs ? total : kNumSMs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3((CTRL_WARPS + EpiWarps<EPI>::N) * 32);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES + EpiLut<EPI>::BYTES;
-  static_assert(Cfg::SMEM_BYTES + EpiLut<EPI>::BYTES <= 232448, "over the 227 KB shared-memory limit of a CTA");
+  cfg.dynamicSmemBytes = GemmSmem<BN, EpiWarps<EPI>::N>::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -489,8 +519,9 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
                                       a->out_pre_bf16 == nullptr && a->act == EAVIT_ACT_NONE && a->residual == nullptr &&
                                       a->colsum == nullptr && a->drop_p == 0.f));
   EAVIT_CHECK_ARG(a->drop_p >= 0.f && a->drop_p < 1.f);
-  const bool need_aux = (a->act == EAVIT_ACT_GELU_BWD || a->act == EAVIT_ACT_LRELU_BWD || a->act == EAVIT_ACT_RELU_BWD);
+  const bool need_aux = (a->act == EAVIT_ACT_GELU_BWD || a->act == EAVIT_ACT_LRELU_BWD || a->act == EAVIT_ACT_RELU_BWD || a->act == EAVIT_ACT_MUL_AUX);
   EAVIT_CHECK_ARG(!need_aux || a->aux_bf16 != nullptr);
+  EAVIT_CHECK_ARG(a->act >= EAVIT_ACT_NONE && a->act <= EAVIT_ACT_GELU_SAVE_GRAD);
   EAVIT_CHECK_ARG(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   const bool drop = make_drop(a->drop_p, a->drop_seed).thresh != 0;
@@ -499,12 +530,16 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
     const bool plain = !a->residual && !a->aux_bf16 && !a->out_pre_bf16;
     if (a->atomic_f32 && none && plain && !a->bias && !a->out_bf16) return launch_gemm<256, E_ATOMIC>(a, st);
     if (a->atomic_f32) return launch_gemm<256, E_GENERIC>(a, st);
-    if (a->colsum != nullptr && a->act != EAVIT_ACT_GELU_BWD)      // only the GELU' and generic epilogues carry column sums
+    if (a->colsum != nullptr && a->act != EAVIT_ACT_GELU_BWD && a->act != EAVIT_ACT_MUL_AUX)   // only the GELU' / multiply and generic epilogues carry column sums
       return drop ? launch_gemm<256, E_GENERIC, true>(a, st) : launch_gemm<256, E_GENERIC>(a, st);
     if (a->act == EAVIT_ACT_GELU && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32)
       return drop ? launch_gemm<256, E_GELU_FWD, true>(a, st) : launch_gemm<256, E_GELU_FWD>(a, st);
     if (a->act == EAVIT_ACT_GELU_BWD && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
       return drop ? launch_gemm<256, E_GELU_BWD, true>(a, st) : launch_gemm<256, E_GELU_BWD>(a, st);
+    if (a->act == EAVIT_ACT_GELU_SAVE_GRAD && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32)
+      return drop ? launch_gemm<256, E_GELU_FWD_D, true>(a, st) : launch_gemm<256, E_GELU_FWD_D>(a, st);
+    if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
+      return drop ? launch_gemm<256, E_MUL_AUX, true>(a, st) : launch_gemm<256, E_MUL_AUX>(a, st);
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)
       return drop ? launch_gemm<256, E_RESID, true>(a, st) : launch_gemm<256, E_RESID>(a, st);
     if (none && plain && !drop) return launch_gemm<256, E_STORE>(a, st);

@@ -44,6 +44,15 @@ def allreduce_sum_(t: torch.Tensor):
     return t
 
 
+def allreduce_sum_async(t: torch.Tensor):
+    """Start the sum all-reduce of ``t`` on the process group's own stream, ordered after everything enqueued so far on the
+    current stream; returns the Work handle (``.wait()`` makes the current stream wait for the result), None when not
+    distributed."""
+    if is_dist():
+        return td.all_reduce(t, op=td.ReduceOp.SUM, async_op=True)
+    return None
+
+
 def grad_scale() -> float:
     """Multiplier that turns the all-reduced gradient SUM into the mean over ranks (applied inside Adam)."""
     return 1.0 / world()[0]

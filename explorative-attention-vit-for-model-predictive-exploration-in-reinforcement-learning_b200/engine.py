@@ -357,7 +357,7 @@ class ViTEncoder:
             hpre = bf.get(f"hpre_{li}", (T, c.mlp_dim), torch.bfloat16)
             hact = bf.get(f"hact_{li}", (T, c.mlp_dim), torch.bfloat16)
             ph, sh = self._site(bf, li, self.SITE_ACT)
-            linear_fwd(xn2, s.b16(L["w1"]), bias=s.w(L["b1"]), act=ops.ACT_GELU, out_bf16=hact, out_pre=hpre, drop_p=ph, drop_seed=sh)
+            linear_fwd(xn2, s.b16(L["w1"]), bias=s.w(L["b1"]), act=ops.ACT_GELU_SAVE_GRAD, out_bf16=hact, out_pre=hpre, drop_p=ph, drop_seed=sh)
             xo = bf.get(f"x_{li + 1}", (T, D), torch.float32)
             pf, sf = self._site(bf, li, self.SITE_FF_OUT)
             linear_fwd(hact, s.b16(L["w2"]), bias=s.w(L["b2"]), residual=xmid, out_f32=xo, drop_p=pf, drop_seed=sf)
@@ -393,7 +393,7 @@ class ViTEncoder:
         hpre = bf.get("hpre_c", (nc, c.mlp_dim), torch.bfloat16)
         hact = bf.get("hact_c", (nc, c.mlp_dim), torch.bfloat16)
         ph, sh = self._site(bf, li, self.SITE_ACT)
-        linear_fwd(xn2, s.b16(L["w1"]), bias=s.w(L["b1"]), act=ops.ACT_GELU, out_bf16=hact, out_pre=hpre, drop_p=ph, drop_seed=sh)
+        linear_fwd(xn2, s.b16(L["w1"]), bias=s.w(L["b1"]), act=ops.ACT_GELU_SAVE_GRAD, out_bf16=hact, out_pre=hpre, drop_p=ph, drop_seed=sh)
         xl = bf.get("xl_c", (nc, D), torch.float32)
         pf, sf = self._site(bf, li, self.SITE_FF_OUT)
         linear_fwd(hact, s.b16(L["w2"]), bias=s.w(L["b2"]), residual=xmid, out_f32=xl, drop_p=pf, drop_seed=sf)
@@ -414,7 +414,7 @@ class ViTEncoder:
         call("eavit_cast_f32_bf16", top_m, top16, nc * D)
         dh = bf.get("dh_c", (nc, c.mlp_dim), torch.bfloat16)
         ph, sh = self._site(bf, li, self.SITE_ACT)
-        linear_bwd(top16, bf.t["hact_c"], s.b16(L["w2"]), dW=s.g(L["w2"]), db=None, dx_bf16=dh, act=ops.ACT_GELU_BWD,
+        linear_bwd(top16, bf.t["hact_c"], s.b16(L["w2"]), dW=s.g(L["w2"]), db=None, dx_bf16=dh, act=ops.ACT_MUL_AUX,
                    aux=bf.t["hpre_c"], dx_colsum=s.g(L["b1"]), drop_p=ph, drop_seed=sh)
         dxn = bf.get("dxn_c", (nc, D), torch.bfloat16)
         linear_bwd(dh, bf.t["xn2_c"], s.b16(L["w1"]), dW=s.g(L["w1"]), db=None, dx_bf16=dxn)
@@ -432,8 +432,19 @@ class ViTEncoder:
         call("eavit_scatter_rows", dxc, D, bf.first_rows, dxa, D, None, D, nc, D)
 
     # ---- backward --------------------------------------------------------------------------------
-    def backward(self, dfeat: torch.Tensor):
-        """dfeat fp32 [2B, D]; accumulates every parameter gradient into ``store.grad``."""
+    def layer_param_names(self, li: int) -> List[str]:
+        """Every tensor of transformer layer ``li`` (its gradients are complete once ``backward`` has enqueued that layer)."""
+        out = []
+        for v in self.L[li].values():
+            if v is None:
+                continue
+            out.extend(v if isinstance(v, (list, tuple)) else [v])
+        return out
+
+    def backward(self, dfeat: torch.Tensor, on_layer_done=None):
+        """dfeat fp32 [2B, D]; accumulates every parameter gradient into ``store.grad``.
+        ``on_layer_done(li)`` is called right after the last kernel that writes a gradient of layer ``li`` has been enqueued
+        (reverse layer order) -- the data-parallel path starts that layer's slice of the gradient exchange there."""
         c, s, p = self.cfg, self.store, self.pre
         B = dfeat.shape[0] // 2
         bf = self.buf[B]
@@ -485,12 +496,14 @@ class ViTEncoder:
                 call("eavit_layernorm_bwd", dxn, BF16, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
                      dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, pf, sf, T, D)
                 dx, dx_other = dx_other, dx
+                if on_layer_done is not None:
+                    on_layer_done(li)
                 continue
             # MLP2: x_out = xmid + hact W2^T + b2
             # (db2 comes from the producer of dx: LN-bwd / top; db1 = colsum(dh) from this GEMM's epilogue)
             ph, sh = self._site(bf, li, self.SITE_ACT)
             linear_bwd(dx16, bf.t[f"hact_{li}"], s.b16(L["w2"]), dW=s.g(L["w2"]), db=None, dx_bf16=dh,
-                       act=ops.ACT_GELU_BWD, aux=bf.t[f"hpre_{li}"], dx_colsum=s.g(L["b1"]), drop_p=ph, drop_seed=sh)
+                       act=ops.ACT_MUL_AUX, aux=bf.t[f"hpre_{li}"], dx_colsum=s.g(L["b1"]), drop_p=ph, drop_seed=sh)
             # MLP1: hpre = xn2 W1^T + b1
             linear_bwd(dh, bf.t[f"xn2_{li}"], s.b16(L["w1"]), dW=s.g(L["w1"]), db=None, dx_bf16=dxn)
             po, so = self._site(bf, li, self.SITE_ATTN_OUT)     # dx16 / db_o: gradient of the out-proj output (masked)
@@ -508,6 +521,8 @@ class ViTEncoder:
             call("eavit_layernorm_bwd", dxn, BF16, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
                  dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, pf, sf, T, D)
             dx, dx_other = dx_other, dx
+            if on_layer_done is not None:
+                on_layer_done(li)
         # embedding (dropout after the positional add, vit.py:158)
         pe, se = self._site(bf, 0, self.SITE_EMB)
         if pe > 0:

@@ -207,12 +207,15 @@ class Runtime:
         feat = self.encoder.forward(state, B, sample_idx, drop_base=self.next_drop_base())
         return self.heads.forward(feat)          # policy [B,A], value_ext [B], value_int [B]  (views of scratch)
 
-    def ac_backward(self, dpol: torch.Tensor, dv: torch.Tensor, backbone: bool = True):
+    def ac_backward(self, dpol: torch.Tensor, dv: torch.Tensor, backbone: bool = True, on_layer_done=None):
         """dv fp32 [2B] = (d value_int | d value_ext).  ``backbone=False``: the shared feature extractor is frozen
-        (train.py:261-263) -- only the heads are differentiated."""
+        (train.py:261-263) -- only the heads are differentiated.  ``on_layer_done``: see ViTEncoder.backward."""
         dfeat = self.heads.backward(dpol, dv)
         if backbone:
-            self.encoder.backward(dfeat)
+            if on_layer_done is not None and isinstance(self.encoder, ViTEncoder):
+                self.encoder.backward(dfeat, on_layer_done)
+            else:
+                self.encoder.backward(dfeat)
 
     def frozen_names(self) -> List[str]:
         """Tensors of the trainable store whose Parameter has requires_grad = False (e.g. freeze_shared_backbone)."""

@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import GemmArgs, check
 
 U8, F32, F64, BF16 = 0, 1, 2, 3
-ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_LRELU, ACT_LRELU_BWD, ACT_RELU, ACT_RELU_BWD = range(7)
+ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_LRELU, ACT_LRELU_BWD, ACT_RELU, ACT_RELU_BWD, ACT_MUL_AUX, ACT_GELU_SAVE_GRAD = range(9)
 _DT = {torch.uint8: U8, torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 
 

@@ -42,6 +42,9 @@ extern "C" {
 #define EAVIT_ACT_LRELU_BWD 4   /* v *= (aux > 0 ? 1 : 0.01) */
 #define EAVIT_ACT_RELU 5
 #define EAVIT_ACT_RELU_BWD 6    /* v *= (aux > 0) */
+#define EAVIT_ACT_MUL_AUX 7     /* v *= aux          (backward of EAVIT_ACT_GELU_SAVE_GRAD) */
+#define EAVIT_ACT_GELU_SAVE_GRAD 8   /* v = gelu(v) like EAVIT_ACT_GELU, but out_pre_bf16 receives gelu'(v) instead of v: the MLP
+                                      * backward (vit.py:27-37) then multiplies instead of re-evaluating erf / exp */
 
 const char* eavit_last_error(void);
 int eavit_version(void);

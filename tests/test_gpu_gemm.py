@@ -93,6 +93,19 @@ def test_gemm_epilogues(ops):
     torch.nn.functional.gelu(x).sum().backward()
     ops.gemm(A, B, act=ops.ACT_GELU_BWD, aux=aux, out_bf16=out16)
     assert rel_err(out16, (A.float() @ B.float().t()) * x.grad) < 5e-3
+    # the pair the engine uses: the forward stores gelu'(pre) next to gelu(pre), the backward multiplies (vit.py:27-37)
+    g16 = torch.empty_like(out16)
+    ops.gemm(A, B, bias=bias, act=ops.ACT_GELU_SAVE_GRAD, out_bf16=out16, out_pre=g16)
+    xr = pre_ref.clone().requires_grad_(True)
+    torch.nn.functional.gelu(xr).sum().backward()
+    assert rel_err(out16, torch.nn.functional.gelu(pre_ref)) < 5e-3
+    assert rel_err(g16, xr.grad) < 5e-3
+    dh16 = torch.empty_like(out16)
+    cs = torch.zeros(N, device="cuda")
+    ops.gemm(A, B, act=ops.ACT_MUL_AUX, aux=g16, out_bf16=dh16, colsum=cs)
+    ref_dh = (A.float() @ B.float().t()) * g16.float()
+    assert rel_err(dh16, ref_dh) < 5e-3
+    assert rel_err(cs, ref_dh.sum(0)) < 2e-3
     # LeakyReLU / ReLU and their backward masks
     ops.gemm(A, B, bias=bias, act=ops.ACT_LRELU, out_f32=out)
     assert rel_err(out, torch.nn.functional.leaky_relu(pre_ref)) < 1e-5
@@ -105,7 +118,7 @@ def test_gemm_epilogues(ops):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("M,N,K", [(500, 1024, 256), (333, 144, 256), (4100, 256, 1024)])
+@pytest.mark.parametrize("M,N,K", [(500, 1024, 256), (333, 144, 256), (4100, 256, 1024), (40000, 1024, 256), (700, 4096, 64)])
 def test_gemm_fused_column_sums(ops, M, N, K):
     """colsum[n] += sum_m of the stored values (bias gradient fused into the dX epilogue); accumulates across calls."""
     torch.manual_seed(4)

@@ -1,5 +1,6 @@
 """CPU tests of the host side: config contract, drop-in parameter tree, ABI table, permutation / mask determinism."""
 import os
+from collections import OrderedDict
 import re
 
 import numpy as np
@@ -195,3 +196,28 @@ def test_rnd_gradient_slice_of_the_flat_store():
     assert RNDAgent._rnd_grad_range(st) is None                 # interleaved: fall back to one all-reduce of everything
     st = S(); st.offsets = {"model.a": 0}; st.numel = 8
     assert RNDAgent._rnd_grad_range(st) is None
+
+
+def test_gradient_exchange_ranges_partition_the_flat_buffer():
+    """Overlapped gradient exchange: per-layer blocks + the predictor block + the remainder cover [0, numel) exactly once."""
+    from eavit_b200.agents import RNDAgent
+    from eavit_b200.engine import ParamStore
+    assert RNDAgent._complement([], 40) == [(0, 40)]
+    assert RNDAgent._complement([(8, 16), (24, 40)], 40) == [(0, 8), (16, 24)]
+    assert RNDAgent._complement([(16, 24), (0, 8), (8, 16)], 24) == []
+    shapes = O.param_shapes(O.OracleConfig())
+    train = OrderedDict((k, v) for k, v in shapes.items() if not k.startswith("rnd.target."))
+    st = ParamStore(train, "cpu", trainable=False)
+    covered = []
+    for li in range(3):
+        names = [k for k in train if f"transformer.layers.{li}." in k]
+        r = st.name_ranges(names)
+        assert len(r) == 1, (li, r)                                  # a layer is ONE contiguous block: one all-reduce
+        covered += r
+    rnd = RNDAgent._rnd_grad_range(st)
+    assert rnd is not None
+    covered.append(rnd)
+    rest = RNDAgent._complement(covered, st.numel)
+    total = sorted(covered + rest)
+    assert total[0][0] == 0 and total[-1][1] == st.numel
+    assert all(a[1] == b[0] for a, b in zip(total, total[1:]))       # disjoint and gap-free
