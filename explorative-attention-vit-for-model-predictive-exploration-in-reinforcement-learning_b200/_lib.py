@@ -27,6 +27,8 @@ class GemmArgs(ctypes.Structure):
         ("colsum", ctypes.c_void_p),
         ("ldc", ctypes.c_longlong), ("drop_p", ctypes.c_float), ("drop_seed", ctypes.c_ulonglong),
         ("act", ctypes.c_int), ("atomic_f32", ctypes.c_int), ("split_k", ctypes.c_int),
+        ("ln_gamma", ctypes.c_void_p), ("ln_beta", ctypes.c_void_p), ("ln_mean", ctypes.c_void_p), ("ln_rstd", ctypes.c_void_p),
+        ("ln_eps", ctypes.c_float),
     ]
 
 

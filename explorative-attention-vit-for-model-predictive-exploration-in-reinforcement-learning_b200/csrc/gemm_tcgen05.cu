@@ -46,6 +46,12 @@ struct GemmKernelParams {
   int act;
   int atomic_f32;
   int cs_smem;        // column sums requested: per-warp private partial sums in shared memory
+  // E_RESID_LN: LayerNorm of the freshly formed residual row (N == BN: one tile holds whole rows) -> out_bf16, mean, rstd
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
 };
 
 // Fused column sums (bias gradients): the first version issued one global red.add per (warp, chunk, column) -- 6 288 adds
@@ -77,7 +83,9 @@ struct GemmSmem {
   static constexpr int OFF_EPI = GemmCfg<BN>::STAGES * GemmCfg<BN>::STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
   static constexpr int OFF_CS = OFF_BAR + 256;
-  static constexpr int TOTAL = OFF_CS + CS_BYTES + 1024 /*align slack*/;
+  static constexpr int OFF_LNX = OFF_CS + CS_BYTES;                            // float2 [2 buffers][2 warps][128 rows] row partial sums
+  static constexpr int LNX_BYTES = 2 * 2 * 128 * 8;
+  static constexpr int TOTAL = OFF_LNX + LNX_BYTES + 1024 /*align slack*/;
   static_assert(TOTAL <= SMEM_LIMIT, "over the 227 KB shared-memory limit of a CTA");
 };
 
@@ -96,7 +104,13 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
 
 // Epilogue specialisations (compile-time): the epilogue is instruction-issue bound (ncu: 45 % issue-active from only 8
 // warps), so the common fused forms drop every per-element runtime branch of the generic path.
-enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5, E_GELU_FWD_D = 6, E_MUL_AUX = 7 };
+enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5, E_GELU_FWD_D = 6, E_MUL_AUX = 7, E_RESID_LN = 8 };
+// E_RESID_LN (north_star clause 3: LayerNorm fused into the GEMM epilogue): x' = x + dropout(A W^T + b) as E_RESID, and --
+// because N == BN == 256 == the model width, so the two warps of a lane quadrant hold whole rows between them -- the
+// LayerNorm that consumes x' (vit.py:28 / :47 PreNorm) in the same epilogue: pass 1 stores x' and reduces sum / sum of squares
+// per row (8-lane shuffles + one exchange between the two warps), the accumulator is released, pass 2 re-reads the rows this
+// lane just wrote (L2-resident) and writes the normalised bf16 operand of the next GEMM plus (mean, rstd) for the backward.
+// Deletes the standalone layernorm_fwd launch: 206 MB of fp32 re-read from HBM per LayerNorm.
 // E_GELU_FWD_D / E_MUL_AUX (EAVIT_ACT_GELU_SAVE_GRAD / EAVIT_ACT_MUL_AUX): the forward stores gelu'(v) -- evaluated from the
 // fp32 pre-activation with the exp and tail it computes anyway -- where E_GELU_FWD stores v, and the backward epilogue is
 // one multiply instead of ~19 instructions and 2 MUFU per element.  These epilogues are bound by the serial instruction
@@ -105,6 +119,7 @@ enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, 
 // atomic epilogues are HBM-bound and want registers for loads in flight instead: 8 warps.
 template <int EPI> struct EpiWarps {
   static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_STORE) ? 16 : ((EPI == E_GELU_BWD || EPI == E_MUL_AUX) ? 12 : 8);
+  static_assert(EPI != E_RESID_LN || N == 8, "E_RESID_LN pairs exactly two warps per lane quadrant");
 };
 
 template <int BN, int EPI, bool DROP>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
@@ -229,10 +244,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr bool GEN = EPI == E_GENERIC;
     const bool need_aux = GEN ? (p.act == EAVIT_ACT_GELU_BWD || p.act == EAVIT_ACT_LRELU_BWD || p.act == EAVIT_ACT_RELU_BWD || p.act == EAVIT_ACT_MUL_AUX)
                               : (EPI == E_GELU_BWD || EPI == E_MUL_AUX);
-    const bool has_bias = GEN || EPI == E_STORE ? (p.bias != nullptr) : (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_RESID);
+    constexpr bool LNF = EPI == E_RESID_LN;
+    const bool has_bias = GEN || EPI == E_STORE ? (p.bias != nullptr) : (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_RESID || LNF);
     const bool has_pre = GEN ? (p.out_pre != nullptr) : (EPI == E_GELU_FWD);
-    const bool has_res = GEN ? (p.residual != nullptr) : (EPI == E_RESID);
-    const bool out_f32 = GEN || EPI == E_STORE ? (p.out_f32 != nullptr) : (EPI == E_RESID || EPI == E_ATOMIC);
+    const bool has_res = GEN ? (p.residual != nullptr) : (EPI == E_RESID || LNF);
+    const bool out_f32 = GEN || EPI == E_STORE ? (p.out_f32 != nullptr) : (EPI == E_RESID || EPI == E_ATOMIC || LNF);
     const bool out_b16 = GEN || EPI == E_STORE ? (p.out_bf16 != nullptr) : (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_GELU_BWD || EPI == E_MUL_AUX);
     const bool atomic = GEN ? (p.atomic_f32 != 0) : (EPI == E_ATOMIC);
     constexpr int CS_SLOTS = Sm::CS_SLOTS;                                         // chunks one warp handles per tile
@@ -250,10 +266,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       __syncwarp();
     };
+    float2* lnx = reinterpret_cast<float2*>(smem + Sm::OFF_LNX);
+    int ln_buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
       const int n_blk = tile_i % p.n_tiles, m_blk = (tile_i / p.n_tiles) % p.m_tiles;
       if (p.cs_smem && n_blk != cs_nblk) { cs_flush(); cs_nblk = n_blk; }
+      float ls1[8], ls2[8];                               // E_RESID_LN: partial row sums of rows rsub + 4 it over this warp's columns
+#pragma unroll
+      for (int it = 0; it < 8; ++it) { ls1[it] = 0.f; ls2[it] = 0.f; }
       tc::mbar_wait(&acc_full[acc], acc_phase);
       tc::fence_after_sync();
       const int row0 = m_blk * BM + q * 32;
@@ -349,6 +370,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if (has_res) { v[0] += res[it].x; v[1] += res[it].y; v[2] += res[it].z; v[3] += res[it].w; }
             if constexpr (CS) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
+            if constexpr (LNF) {
+              ls1[it] += (v[0] + v[1]) + (v[2] + v[3]);
+              ls2[it] += fmaf(v[0], v[0], v[1] * v[1]) + fmaf(v[2], v[2], v[3] * v[3]);
+            }
             if (out_f32) {
               if (atomic) {
 #pragma unroll
@@ -388,6 +413,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if constexpr (LNF) {
+        // ---- row statistics: 8 lanes share a row inside the warp, the two warps of the quadrant share it between them
+        const int cchunk = lane & 7, rsub = lane >> 3;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            ls1[it] += __shfl_xor_sync(0xffffffffu, ls1[it], o);
+            ls2[it] += __shfl_xor_sync(0xffffffffu, ls2[it], o);
+          }
+        }
+        float2* mine = lnx + (ln_buf * 2 + par) * 128 + q * 32;
+        const float2* other = lnx + (ln_buf * 2 + (par ^ 1)) * 128 + q * 32;
+        if (cchunk == 0) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) mine[it * 4 + rsub] = make_float2(ls1[it], ls2[it]);
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");          // the two warps of lane quadrant q
+        float mean[8], rstd[8];
+        const float inv_n = 1.0f / (float)BN;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float2 o2 = other[it * 4 + rsub];
+          const float m = (ls1[it] + o2.x) * inv_n;
+          const float var = fmaxf((ls2[it] + o2.y) * inv_n - m * m, 0.f);
+          mean[it] = m;
+          rstd[it] = rsqrtf(var + p.ln_eps);
+        }
+        ln_buf ^= 1;
+        if (par == 0 && cchunk == 0 && p.ln_mean != nullptr) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (it * 4 + rsub < nrows) { p.ln_mean[row0 + it * 4 + rsub] = mean[it]; p.ln_rstd[row0 + it * 4 + rsub] = rstd[it]; }
+        }
+        // ---- pass 2: y = (x' - mean) * rstd * gamma + beta -> bf16, from the rows this lane stored in pass 1
+#pragma unroll 1
+        for (int c = par; c < BN / 32; c += EPI_WARPS / 4) {
+          const int col = c * 32 + cchunk * 4;
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col));
+          const float4 be4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col));
+          const size_t off0 = (size_t)(row0 + rsub) * (size_t)p.ldc + col;
+          const size_t ostep = 4 * (size_t)p.ldc;
+          float4 xv[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (it * 4 + rsub < nrows) xv[it] = __ldcg(reinterpret_cast<const float4*>(p.out_f32 + off0 + it * ostep));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (it * 4 + rsub < nrows) {
+              const float a = rstd[it], b = -mean[it] * rstd[it];
+              const float y0 = fmaf(fmaf(xv[it].x, a, b), g4.x, be4.x), y1 = fmaf(fmaf(xv[it].y, a, b), g4.y, be4.y);
+              const float y2 = fmaf(fmaf(xv[it].z, a, b), g4.z, be4.z), y3 = fmaf(fmaf(xv[it].w, a, b), g4.w, be4.w);
+              *reinterpret_cast<uint2*>(p.out_bf16 + off0 + it * ostep) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+            }
+          }
+        }
+      }
     }
     if (p.cs_smem) cs_flush();
   }
@@ -486,6 +568,7 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   p.act = a->act;
   p.atomic_f32 = a->atomic_f32;
   p.cs_smem = a->colsum != nullptr ? 1 : 0;
+  p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_mean = a->ln_mean; p.ln_rstd = a->ln_rstd; p.ln_eps = a->ln_eps;
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < kNumSMs ? total : kNumSMs;
   cudaLaunchConfig_t cfg = {};
@@ -522,6 +605,11 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
   const bool need_aux = (a->act == EAVIT_ACT_GELU_BWD || a->act == EAVIT_ACT_LRELU_BWD || a->act == EAVIT_ACT_RELU_BWD || a->act == EAVIT_ACT_MUL_AUX);
   EAVIT_CHECK_ARG(!need_aux || a->aux_bf16 != nullptr);
   EAVIT_CHECK_ARG(a->act >= EAVIT_ACT_NONE && a->act <= EAVIT_ACT_GELU_SAVE_GRAD);
+  if (a->ln_gamma != nullptr) {            // fused LayerNorm of the residual row
+    EAVIT_CHECK_ARG(a->N == 256 && a->ln_beta && a->bias && a->residual && a->out_f32 && a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16);
+    EAVIT_CHECK_ARG(a->act == EAVIT_ACT_NONE && !a->atomic_f32 && a->split_k <= 1 && !a->colsum && (a->ln_mean == nullptr) == (a->ln_rstd == nullptr));
+    EAVIT_CHECK_ARG(a->out_f32 != a->residual || true);
+  }
   EAVIT_CHECK_ARG(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   const bool drop = make_drop(a->drop_p, a->drop_seed).thresh != 0;
@@ -540,6 +628,9 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
       return drop ? launch_gemm<256, E_GELU_FWD_D, true>(a, st) : launch_gemm<256, E_GELU_FWD_D>(a, st);
     if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
       return drop ? launch_gemm<256, E_MUL_AUX, true>(a, st) : launch_gemm<256, E_MUL_AUX>(a, st);
+    if (a->ln_gamma != nullptr) {          // checked below: N == 256, bias + residual + fp32 and bf16 outputs, no split-K
+      return drop ? launch_gemm<256, E_RESID_LN, true>(a, st) : launch_gemm<256, E_RESID_LN>(a, st);
+    }
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)
       return drop ? launch_gemm<256, E_RESID, true>(a, st) : launch_gemm<256, E_RESID>(a, st);
     if (none && plain && !drop) return launch_gemm<256, E_STORE>(a, st);

@@ -259,6 +259,36 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, long long lds
   }
 }
 
+// dst[rows[i], :] += src[i, :] for a few rows of a dense gradient (the pooled tokens' residual gradient of the pruned last
+// layer), keeping the two by-products of the LayerNorm backward that produced dst consistent: the bf16 copy of the rows
+// (under the dropout mask of the linear layer below) and that layer's bias gradient (+= column sums of the masked delta).
+// Replaces zero-filling a [T, D] fp32 buffer, scattering into it and streaming it through the LayerNorm backward as `dres`.
+__global__ void __launch_bounds__(64) scatter_add_rows_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ rows,
+                                                              float* __restrict__ dst, long long ldd, __nv_bfloat16* __restrict__ dst_bf16,
+                                                              long long lddb, float* __restrict__ colsum, int n, int D, int rows_per_block,
+                                                              const DropCfg drop) {
+  const int i0 = blockIdx.x * rows_per_block, i1 = min(n, i0 + rows_per_block);
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = i0; i < i1; ++i) {
+      const size_t r = (size_t)rows[i];
+      const float4 d = __ldg(reinterpret_cast<const float4*>(src + (size_t)i * lds) + c);
+      float4 v = *(reinterpret_cast<float4*>(dst + r * ldd) + c);
+      v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+      *(reinterpret_cast<float4*>(dst + r * ldd) + c) = v;
+      float dm[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop.thresh) drop4(drop, drop_row_key(drop, (uint32_t)r), (uint32_t)(4 * c), dm);
+      if (dst_bf16 != nullptr)
+        *(reinterpret_cast<uint2*>(dst_bf16 + r * lddb) + c) = make_uint2(pack_bf16x2(v.x * dm[0], v.y * dm[1]), pack_bf16x2(v.z * dm[2], v.w * dm[3]));
+      acc.x += d.x * dm[0]; acc.y += d.y * dm[1]; acc.z += d.z * dm[2]; acc.w += d.w * dm[3];
+    }
+    if (colsum != nullptr) {
+      atomicAdd(colsum + 4 * c, acc.x); atomicAdd(colsum + 4 * c + 1, acc.y);
+      atomicAdd(colsum + 4 * c + 2, acc.z); atomicAdd(colsum + 4 * c + 3, acc.w);
+    }
+  }
+}
+
 // dst[i, c] = src[i, c] * dropmask(rows ? rows[i] : row0 + i, c)   (embedding dropout, vit.py:158; top-gradient rows)
 __global__ void __launch_bounds__(256) dropout_apply_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ rows,
                                                             int row0, float* __restrict__ dst, long long ldd, int n, int D,
@@ -395,6 +425,17 @@ int eavit_scatter_rows(const float* src, long long lds, const int* rows, float* 
                        long long lddb, int n, int D, void* stream) {
   EAVIT_CHECK_ARG(n > 0 && D % 4 == 0 && src && rows && (dst || dst_bf16) && lds % 4 == 0 && ldd % 4 == 0 && lddb % 4 == 0);
   scatter_rows_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(src, lds, rows, dst, ldd, (__nv_bfloat16*)dst_bf16, lddb, n, D);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_scatter_add_rows(const float* src, long long lds, const int* rows, float* dst, long long ldd, void* dst_bf16, long long lddb,
+                           float* colsum, int n, int D, float drop_p, unsigned long long drop_seed, void* stream) {
+  EAVIT_CHECK_ARG(n > 0 && D % 4 == 0 && src && rows && dst && lds % 4 == 0 && ldd % 4 == 0 && lddb % 4 == 0);
+  EAVIT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
+  const int rpb = 32;
+  scatter_add_rows_kernel<<<cdiv(n, rpb), 64, 0, (cudaStream_t)stream>>>(src, lds, rows, dst, ldd, (__nv_bfloat16*)dst_bf16, lddb, colsum, n, D,
+                                                                        rpb, make_drop(drop_p, drop_seed));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }

@@ -179,10 +179,10 @@ def _split_k(M: int, N: int, K: int) -> int:
 
 
 def linear_fwd(x16, w16, *, bias=None, act=ops.ACT_NONE, residual=None, out_f32=None, out_bf16=None, out_pre=None,
-               drop_p=0.0, drop_seed=0):
-    """y = dropout(act(x W^T + b)) (+ residual) on the tcgen05 GEMM."""
+               drop_p=0.0, drop_seed=0, ln=None):
+    """y = dropout(act(x W^T + b)) (+ residual) on the tcgen05 GEMM; ``ln``: the LayerNorm that consumes y, fused."""
     ops.gemm(x16, w16, bias=bias, act=act, residual=residual, out_f32=out_f32, out_bf16=out_bf16, out_pre=out_pre,
-             drop_p=drop_p, drop_seed=drop_seed)
+             drop_p=drop_p, drop_seed=drop_seed, ln=ln)
 
 
 def linear_bwd(dy16, x16, w16, *, dW, db=None, dx_f32=None, dx_bf16=None, act=ops.ACT_NONE, aux=None, dx_colsum=None,
@@ -334,10 +334,16 @@ class ViTEncoder:
         if pe > 0:
             call("eavit_dropout_apply", x0, D, None, 0, x0, D, T, D, pe, se)
         x = x0
+        # LayerNorm fused into the GEMM that produces its input row (out-proj + residual -> LN2, MLP2 + residual -> the next
+        # layer's LN1): possible when one 256-column tile holds the whole row
+        fuse_ln = D == 256 and os.environ.get("EAVIT_FUSE_LN", "1") == "1"
+        ln1_done = False
         for li, L in enumerate(self.L):
             xn1 = bf.get(f"xn1_{li}", (T, D), torch.bfloat16)
             m1, r1 = bf.get(f"m1_{li}", (T,), torch.float32), bf.get(f"r1_{li}", (T,), torch.float32)
-            call("eavit_layernorm_fwd", x, D, s.w(L["ln1"][0]), s.w(L["ln1"][1]), xn1, BF16, D, m1, r1, T, D, c.ln_eps)
+            if not ln1_done:
+                call("eavit_layernorm_fwd", x, D, s.w(L["ln1"][0]), s.w(L["ln1"][1]), xn1, BF16, D, m1, r1, T, D, c.ln_eps)
+            ln1_done = False
             qkv = bf.get(f"qkv_{li}", (T, 3 * I), torch.bfloat16)
             linear_fwd(xn1, self._qkv(L, "w16"), bias=self._qkv(L, "b"), out_bf16=qkv)
             if self.prune_last and li == c.depth - 1:
@@ -350,17 +356,29 @@ class ViTEncoder:
                               drop_p=pa, drop_seed=sa)
             xmid = bf.get(f"xmid_{li}", (T, D), torch.float32)
             po, so = self._site(bf, li, self.SITE_ATTN_OUT)
-            linear_fwd(o, s.b16(L["o_w"]), bias=s.w(L["o_b"]), residual=x, out_f32=xmid, drop_p=po, drop_seed=so)
             xn2 = bf.get(f"xn2_{li}", (T, D), torch.bfloat16)
             m2, r2 = bf.get(f"m2_{li}", (T,), torch.float32), bf.get(f"r2_{li}", (T,), torch.float32)
-            call("eavit_layernorm_fwd", xmid, D, s.w(L["ln2"][0]), s.w(L["ln2"][1]), xn2, BF16, D, m2, r2, T, D, c.ln_eps)
+            if fuse_ln:
+                linear_fwd(o, s.b16(L["o_w"]), bias=s.w(L["o_b"]), residual=x, out_f32=xmid, out_bf16=xn2, drop_p=po, drop_seed=so,
+                           ln=(s.w(L["ln2"][0]), s.w(L["ln2"][1]), m2, r2, c.ln_eps))
+            else:
+                linear_fwd(o, s.b16(L["o_w"]), bias=s.w(L["o_b"]), residual=x, out_f32=xmid, drop_p=po, drop_seed=so)
+                call("eavit_layernorm_fwd", xmid, D, s.w(L["ln2"][0]), s.w(L["ln2"][1]), xn2, BF16, D, m2, r2, T, D, c.ln_eps)
             hpre = bf.get(f"hpre_{li}", (T, c.mlp_dim), torch.bfloat16)
             hact = bf.get(f"hact_{li}", (T, c.mlp_dim), torch.bfloat16)
             ph, sh = self._site(bf, li, self.SITE_ACT)
             linear_fwd(xn2, s.b16(L["w1"]), bias=s.w(L["b1"]), act=ops.ACT_GELU_SAVE_GRAD, out_bf16=hact, out_pre=hpre, drop_p=ph, drop_seed=sh)
             xo = bf.get(f"x_{li + 1}", (T, D), torch.float32)
             pf, sf = self._site(bf, li, self.SITE_FF_OUT)
-            linear_fwd(hact, s.b16(L["w2"]), bias=s.w(L["b2"]), residual=xmid, out_f32=xo, drop_p=pf, drop_seed=sf)
+            if fuse_ln and li + 1 < c.depth:
+                Ln = self.L[li + 1]
+                linear_fwd(hact, s.b16(L["w2"]), bias=s.w(L["b2"]), residual=xmid, out_f32=xo, drop_p=pf, drop_seed=sf,
+                           out_bf16=bf.get(f"xn1_{li + 1}", (T, D), torch.bfloat16),
+                           ln=(s.w(Ln["ln1"][0]), s.w(Ln["ln1"][1]), bf.get(f"m1_{li + 1}", (T,), torch.float32),
+                               bf.get(f"r1_{li + 1}", (T,), torch.float32), c.ln_eps))
+                ln1_done = True
+            else:
+                linear_fwd(hact, s.b16(L["w2"]), bias=s.w(L["b2"]), residual=xmid, out_f32=xo, drop_p=pf, drop_seed=sf)
             x = xo
         nf = 2 * B
         pooled = bf.get("pooled", (nf, D), torch.float32)
@@ -401,7 +419,7 @@ class ViTEncoder:
 
     def _last_layer_pooled_bwd(self, bf, li, L, top, dqkv, dxa):
         """Backward of ``_last_layer_pooled_fwd``.  top fp32 [nseq, D] = gradient of the layer's pooled outputs.  Writes the
-        dense dqkv [T, 3I] and leaves the pooled rows' residual gradient scattered into the zeroed dxa [T, D]."""
+        dense dqkv [T, 3I] and returns the pooled rows' residual gradient [nseq, D]."""
         c, s = self.cfg, self.store
         D, I, nc, T = c.dim, self.inner, bf.nseq, bf.T
         pf, sf = self._site(bf, li, self.SITE_FF_OUT)
@@ -428,8 +446,7 @@ class ViTEncoder:
         pa, sa = self._site(bf, li, self.SITE_ATTN_P)
         call("eavit_attention_row0_bwd", bf.t[f"qkv_{li}"], do0, bf.seq_start, nc, bf.max_len, c.heads, c.dim_head,
              float(c.dim_head) ** -0.5, dqkv, pa, sa)
-        call("eavit_zero", dxa, T * D * 4)
-        call("eavit_scatter_rows", dxc, D, bf.first_rows, dxa, D, None, D, nc, D)
+        return dxc            # [nseq, D] residual gradient of the pooled rows: added sparsely after the LayerNorm backward
 
     # ---- backward --------------------------------------------------------------------------------
     def layer_param_names(self, li: int) -> List[str]:
@@ -489,12 +506,15 @@ class ViTEncoder:
             x_in = bf.t["x0"] if li == 0 else bf.t[f"x_{li}"]
             if self.prune_last and li == c.depth - 1:
                 # pooled rows only down to the attention, then the ordinary dense QKV / LN1 backward
-                self._last_layer_pooled_bwd(bf, li, L, top, dqkv, dx)
+                dxc = self._last_layer_pooled_bwd(bf, li, L, top, dqkv, dx)
                 linear_bwd(dqkv, bf.t[f"xn1_{li}"], self._qkv(L, "w16"), dW=self._qkv(L, "gw"), db=self._qkv(L, "gb"), dx_bf16=dxn)
                 db2_prev = s.g(self.L[li - 1]["b2"]) if li > 0 else None
                 pf, sf = self._site(bf, li - 1, self.SITE_FF_OUT) if li > 0 else (0.0, 0)
+                # the residual gradient entering this LayerNorm is zero except at the pooled rows: no dense `dres` stream
+                # (206 MB zero fill + 206 MB read at cfg3); the pooled rows are added afterwards
                 call("eavit_layernorm_bwd", dxn, BF16, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
-                     dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, pf, sf, T, D)
+                     None, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, pf, sf, T, D)
+                call("eavit_scatter_add_rows", dxc, D, bf.first_rows, dx_other, D, dx16, D, db2_prev, bf.nseq, D, pf, sf)
                 dx, dx_other = dx_other, dx
                 if on_layer_done is not None:
                     on_layer_done(li)

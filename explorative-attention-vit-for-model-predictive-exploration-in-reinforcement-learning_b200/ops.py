@@ -192,10 +192,11 @@ def intrinsic_mse(target, predict):
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias=None, act: int = ACT_NONE,
          aux=None, residual=None, out_f32=None, out_bf16=None, out_pre=None, colsum=None, atomic: bool = False,
-         split_k: int = 1, drop_p: float = 0.0, drop_seed: int = 0):
+         split_k: int = 1, drop_p: float = 0.0, drop_seed: int = 0, ln=None):
     """C = epilogue(A . B^T) on tcgen05 (see include/eavit_b200.h: eavit_gemm_bf16).
 
     a_mn: A passed as the stored [K, M] matrix; b_mn: B passed as the stored [K, N] matrix.
+    ln = (gamma, beta, mean_out, rstd_out, eps): fused LayerNorm of the residual row (N == 256): out_bf16 = LN(out_f32).
     Outputs must be preallocated by the caller ([M, N], row pitch = stride(0))."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.dim() == 2 and B.dim() == 2
     assert A.stride(1) == 1 and B.stride(1) == 1
@@ -217,9 +218,15 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                  out_pre_bf16=None if out_pre is None else out_pre.data_ptr(),
                  colsum=None if colsum is None else colsum.data_ptr(),
                  ldc=ldc, drop_p=float(drop_p), drop_seed=int(drop_seed) & _M64, act=act, atomic_f32=int(atomic), split_k=split_k)
+    if ln is not None:
+        gamma, beta, mean_o, rstd_o, eps = ln
+        g.ln_gamma, g.ln_beta = gamma.data_ptr(), beta.data_ptr()
+        g.ln_mean = None if mean_o is None else mean_o.data_ptr()
+        g.ln_rstd = None if rstd_o is None else rstd_o.data_ptr()
+        g.ln_eps = float(eps)
     if _PROF is not None:
         with _Timed(f"gemm_bf16_tcgen05 M={M} N={N} K={K} {'mn' if a_mn else 'k'}{'mn' if b_mn else 'k'} act={act}"
-                    f"{' splitk' if split_k > 1 else ''}", 2.0 * M * N * K):
+                    f"{' splitk' if split_k > 1 else ''}{' +ln' if ln is not None else ''}", 2.0 * M * N * K):
             check(_lib.lib().eavit_gemm_bf16(ctypes.byref(g), _st()), "gemm_bf16")
         return
     check(_lib.lib().eavit_gemm_bf16(ctypes.byref(g), _st()), "gemm_bf16")
@@ -236,6 +243,7 @@ _SPECS = {
     "eavit_colsum": "pilpii",
     "eavit_gather_rows": "plpplii",
     "eavit_scatter_rows": "plppl" "pl" "ii",
+    "eavit_scatter_add_rows": "plppl" "pl" "p" "ii" "fu",
     "eavit_cast_f32_bf16": "ppl",
     "eavit_add_f32": "pppl",
     "eavit_zero": "pl",

@@ -127,6 +127,15 @@ typedef struct {
   int act;
   int atomic_f32;
   int split_k;
+  /* Fused PreNorm LayerNorm of the residual row (vit.py:28 / :47 after the residual adds of vit.py:88-89).  With ln_gamma != NULL
+   * (N == 256, bias + residual + out_f32 + out_bf16 given, no activation): out_f32 = residual + dropout(A.B^T + bias) as usual and
+   * out_bf16 = LayerNorm(out_f32 row) * ln_gamma + ln_beta, ln_mean / ln_rstd [M] (optional) = the row statistics the
+   * LayerNorm backward needs.  One tile holds whole rows, so no standalone LayerNorm launch re-reads out_f32 from HBM. */
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
 } eavit_gemm_args;
 int eavit_gemm_bf16(const eavit_gemm_args* args, void* stream);
 
@@ -150,6 +159,12 @@ int eavit_colsum(const void* x, int x_dtype, long long ldx, float* out, int T, i
 int eavit_gather_rows(const float* src, long long lds, const int* rows, float* dst, long long ldd, int n, int D, void* stream);
 int eavit_scatter_rows(const float* src, long long lds, const int* rows, float* dst, long long ldd, void* dst_bf16,
                        long long lddb, int n, int D, void* stream);
+/* dst[rows[i],:] += src[i,:] (rows unique) after a LayerNorm backward wrote dst: also refreshes the bf16 copy of those rows
+ * (under the dropout mask (drop_p, drop_seed) of the linear layer below, vit.py:33) and adds the masked delta's column sums
+ * to that layer's bias gradient.  The pooled-token residual gradient of the last layer (x[:, 0], vit.py:162). */
+int eavit_scatter_add_rows(const float* src, long long lds, const int* rows, float* dst, long long ldd, void* dst_bf16 /* may be NULL */,
+                           long long lddb, float* colsum /* may be NULL */, int n, int D, float drop_p, unsigned long long drop_seed,
+                           void* stream);
 int eavit_cast_f32_bf16(const float* in, void* out_bf16, long long n, void* stream);
 int eavit_add_f32(const float* a, const float* b, float* out, long long n, void* stream);
 int eavit_zero(void* ptr, long long bytes, void* stream);

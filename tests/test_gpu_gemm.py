@@ -145,3 +145,33 @@ def test_gemm_rejects_bad_arguments(ops):
     out = torch.empty(64, 64, device="cuda")
     with pytest.raises(RuntimeError):
         ops.gemm(A, B, out_f32=out)
+
+
+@pytest.mark.parametrize("M,K", [(500, 256), (4100, 1024), (128, 64), (1, 256)])
+def test_gemm_residual_epilogue_with_fused_layernorm(ops, M, K):
+    """x' = residual + A W^T + b (fp32) and LayerNorm(x') * gamma + beta (bf16) + (mean, rstd) from ONE launch (N = 256 = one
+    tile per row): vit.py:88-89 residual adds followed by the PreNorm LayerNorm of vit.py:28 / :47."""
+    torch.manual_seed(M + K)
+    N = 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda") * 3 + 0.7
+    gamma, beta = torch.randn(N, device="cuda") * 0.2 + 1, torch.randn(N, device="cuda") * 0.1
+    out = torch.empty(M, N, device="cuda")
+    xn = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    ops.gemm(A, B, bias=bias, residual=res, out_f32=out, out_bf16=xn, ln=(gamma, beta, mean, rstd, 1e-5))
+    ref = A.float() @ B.float().t() + bias + res
+    assert rel_err(out, ref) < 1e-5
+    ln_ref = torch.nn.functional.layer_norm(out, (N,), gamma, beta, 1e-5)          # of the values the kernel itself stored
+    assert rel_err(xn, ln_ref) < 4e-3                                               # bf16 rounding of the output
+    assert torch.allclose(mean, out.mean(1), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rstd, (out.var(1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-4)
+    # the statistics need not be written
+    xn2 = torch.empty_like(xn)
+    ops.gemm(A, B, bias=bias, residual=res, out_f32=out, out_bf16=xn2, ln=(gamma, beta, None, None, 1e-5))
+    assert torch.equal(xn2, xn)
+    with pytest.raises(RuntimeError):                                               # needs N == 256
+        ops.gemm(A, B[:128], bias=bias[:128], residual=res[:, :128].contiguous(), out_f32=out[:, :128].contiguous(),
+                 out_bf16=xn[:, :128].contiguous(), ln=(gamma[:128], beta[:128], None, None, 1e-5))
