@@ -83,8 +83,8 @@ struct GemmSmem {
   static constexpr int OFF_EPI = GemmCfg<BN>::STAGES * GemmCfg<BN>::STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
   static constexpr int OFF_CS = OFF_BAR + 256;
-  static constexpr int OFF_LNX = OFF_CS + CS_BYTES;                            // float2 [2 buffers][2 warps][128 rows] row partial sums
-  static constexpr int LNX_BYTES = 2 * 2 * 128 * 8;
+  static constexpr int OFF_LNX = OFF_CS + CS_BYTES;                            // float2 [2 buffers][warps per quadrant][128 rows] row partial sums
+  static constexpr int LNX_BYTES = 2 * (EW / 4) * 128 * 8;
   static constexpr int TOTAL = OFF_LNX + LNX_BYTES + 1024 /*align slack*/;
   static_assert(TOTAL <= SMEM_LIMIT, "over the 227 KB shared-memory limit of a CTA");
 };
@@ -118,17 +118,18 @@ enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, 
 // The GELU epilogues are issue/latency-bound (16 instructions + 2 MUFU per element): 16 warps.  The store / residual /
 // atomic epilogues are HBM-bound and want registers for loads in flight instead: 8 warps.
 template <int EPI> struct EpiWarps {
-  static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_STORE) ? 16 : ((EPI == E_GELU_BWD || EPI == E_MUL_AUX) ? 12 : 8);
-  static_assert(EPI != E_RESID_LN || N == 8, "E_RESID_LN pairs exactly two warps per lane quadrant");
+  // measured at [201216, 1024] x K = 256 (r2): multiply-by-aux 250 us with 12 warps, 229 us with 16; residual (+ LayerNorm) epilogues
+  // are best with 8 (142 / 183 us vs 145 / 232 us with 16: their prefetched fp32 rows need the registers)
+  static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_STORE || EPI == E_MUL_AUX) ? 16 : (EPI == E_GELU_BWD ? 12 : 8);
 };
 
-template <int BN, int EPI, bool DROP>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
-__global__ void __launch_bounds__((CTRL_WARPS + EpiWarps<EPI>::N) * 32, 1)
+template <int BN, int EPI, bool DROP, int EW = EpiWarps<EPI>::N>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
+__global__ void __launch_bounds__((CTRL_WARPS + EW) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int EPI_WARPS = EpiWarps<EPI>::N;
+  constexpr int EPI_WARPS = EW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using Sm = GemmSmem<BN, EPI_WARPS>;
@@ -424,20 +425,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             ls2[it] += __shfl_xor_sync(0xffffffffu, ls2[it], o);
           }
         }
-        float2* mine = lnx + (ln_buf * 2 + par) * 128 + q * 32;
-        const float2* other = lnx + (ln_buf * 2 + (par ^ 1)) * 128 + q * 32;
+        constexpr int WQ = EPI_WARPS / 4;                                   // warps per lane quadrant
+        float2* mine = lnx + (ln_buf * WQ + par) * 128 + q * 32;
         if (cchunk == 0) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) mine[it * 4 + rsub] = make_float2(ls1[it], ls2[it]);
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");          // the two warps of lane quadrant q
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(WQ * 32) : "memory");          // the warps of lane quadrant q
         float mean[8], rstd[8];
         const float inv_n = 1.0f / (float)BN;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const float2 o2 = other[it * 4 + rsub];
-          const float m = (ls1[it] + o2.x) * inv_n;
-          const float var = fmaxf((ls2[it] + o2.y) * inv_n - m * m, 0.f);
+          float2 o2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int w2 = 0; w2 < WQ; ++w2) {                                 // same order in every warp: identical statistics
+            const float2 t2 = lnx[(ln_buf * WQ + w2) * 128 + q * 32 + it * 4 + rsub];
+            o2.x += t2.x; o2.y += t2.y;
+          }
+          const float m = o2.x * inv_n;
+          const float var = fmaxf(o2.y * inv_n - m * m, 0.f);
           mean[it] = m;
           rstd[it] = rsqrtf(var + p.ln_eps);
         }
@@ -528,13 +534,13 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return EAVIT_OK;
 }
 
-template <int BN, int EPI, bool DROP = false>
+template <int BN, int EPI, bool DROP = false, int EW = EpiWarps<EPI>::N>
 static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<BN, EpiWarps<EPI>::N>::TOTAL));
+    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    GemmSmem<BN, EW>::TOTAL));
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
@@ -573,15 +579,15 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   const int grid = total < kNumSMs ? total : kNumSMs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3((CTRL_WARPS + EpiWarps<EPI>::N) * 32);
-  cfg.dynamicSmemBytes = GemmSmem<BN, EpiWarps<EPI>::N>::TOTAL;
+  cfg.blockDim = dim3((CTRL_WARPS + EW) * 32);
+  cfg.dynamicSmemBytes = GemmSmem<BN, EW>::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP>, tmA, tmB, p));
+  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW>, tmA, tmB, p));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -628,9 +634,8 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
       return drop ? launch_gemm<256, E_GELU_FWD_D, true>(a, st) : launch_gemm<256, E_GELU_FWD_D>(a, st);
     if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
       return drop ? launch_gemm<256, E_MUL_AUX, true>(a, st) : launch_gemm<256, E_MUL_AUX>(a, st);
-    if (a->ln_gamma != nullptr) {          // checked below: N == 256, bias + residual + fp32 and bf16 outputs, no split-K
+    if (a->ln_gamma != nullptr)            // checked above: N == 256, bias + residual + fp32 and bf16 outputs, no split-K
       return drop ? launch_gemm<256, E_RESID_LN, true>(a, st) : launch_gemm<256, E_RESID_LN>(a, st);
-    }
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)
       return drop ? launch_gemm<256, E_RESID, true>(a, st) : launch_gemm<256, E_RESID>(a, st);
     if (none && plain && !drop) return launch_gemm<256, E_STORE>(a, st);
