@@ -246,17 +246,22 @@ __global__ void __launch_bounds__(256) rms_partial_u8_kernel(const uint8_t* __re
 
 // uint8 frames, F % 16 == 0 (84 x 84 = 441 x 16): the kernel the device-resident rollout actually uses, written for the
 // HBM roofline.  A lane reads 16 pixels per row with ONE 16-byte load (a warp = 512 contiguous bytes of a row), a CTA is
-// 32 column vectors x 8 row lanes, four rows in flight per lane; the sums stay exact 32-bit integers in registers; the 8
-// row lanes are combined through shared memory, and the LAST CTA of a column block to finish (ticket) folds every row split
-// and applies the Chan merge itself -- one launch for the whole update instead of partial + reduce + count.
-//   mode 0: write (sum, sumsq) about `shift`          (eavit_rms_partial, the multi-GPU moment exchange)
-//   mode 1: merge into mean / var / count in place     (eavit_rms_update; `shift` == mean)
-// tickets[0 .. col_blocks) count finished row splits per column block, tickets[63] finished column blocks; each is reset by
-// its last arriver, so the buffer is all-zero again when the kernel ends.
+// 32 column vectors x 8 row lanes with two groups of four rows in flight per lane (the next group's loads are issued
+// before the current one is summed); the sums stay exact 32-bit integers in registers, the 8 row lanes are combined in
+// shared memory, and each CTA adds its column totals to library-owned 64-bit integer accumulators in global memory.
+// Sum(x) and Sum(x^2) of uint8 pixels are EXACT integers, so the order of those atomic adds does not matter: the result is
+// deterministic without the per-split partial sums of the generic kernel (no workspace round trip, no second kernel).
+// The last CTA to finish (one ticket) shifts the totals algebraically in float64
+//     sum(x - s) = Sx - n s,   sum((x - s)^2) = Sxx - 2 s Sx + n s^2
+// and either writes them (mode 0: eavit_rms_partial, the multi-GPU moment exchange) or applies the Chan merge
+// (mode 1: eavit_rms_update; `shift` == mean, utils.py:101-115), then zeroes accumulators and tickets for the next call.
+// The last CTA of each 512-column block does this for its own columns (tickets[0 .. 62)); tickets[63] counts finished
+// column blocks so that `count` is advanced only after every block has read the old value.
 constexpr int RMS16_ROWL = 8;
-__global__ void __launch_bounds__(256) rms_u8x16_kernel(const uint8_t* __restrict__ x, long long N, int F,
-                                                        const double* __restrict__ shift, double* __restrict__ ws,
-                                                        int rows_per_split, unsigned int* __restrict__ tickets, int mode,
+constexpr int RMS16_MAXF = 16384;
+__global__ void __launch_bounds__(256, 3) rms_u8x16_kernel(const uint8_t* __restrict__ x, long long N, int F,
+                                                        const double* __restrict__ shift, unsigned long long* __restrict__ acc,
+                                                        int rows_per_split, unsigned int* __restrict__ ticket, int mode,
                                                         double* __restrict__ sum_out, double* __restrict__ sq_out,
                                                         double* __restrict__ mean, double* __restrict__ var,
                                                         double* __restrict__ count) {
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(256) rms_u8x16_kernel(const uint8_t* __restric
 #pragma unroll
   for (int i = 0; i < 16; ++i) { s[i] = 0u; q[i] = 0u; }
   if (c0 < F) {
-    auto acc = [&](const uint4& u) {
+    auto acc16 = [&](const uint4& u) {
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -281,21 +286,37 @@ __global__ void __launch_bounds__(256) rms_u8x16_kernel(const uint8_t* __restric
         }
     };
     const uint8_t* p = x + r0 * F + c0;
-    long long r = r0 + ry;
-    for (; r + 3 * RMS16_ROWL < r1; r += 4 * RMS16_ROWL) {    // 4 independent 16-byte loads in flight per lane
-      uint4 u[4];
+    const long long nr = r1 - r0;
+    long long r = ry;                                          // row offset inside the split; this lane takes r, r + 8, ...
+    constexpr int G = 4 * RMS16_ROWL;                          // rows covered by one group of four loads
+    uint4 a[4], b[4];
+    const bool have_a = r + 3 * RMS16_ROWL < nr;
+    if (have_a) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(p + (r - r0 + (long long)k * RMS16_ROWL) * F));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc(u[k]);
+      for (int k = 0; k < 4; ++k) a[k] = __ldg(reinterpret_cast<const uint4*>(p + (r + (long long)k * RMS16_ROWL) * F));
     }
-    for (; r < r1; r += RMS16_ROWL) acc(__ldg(reinterpret_cast<const uint4*>(p + (r - r0) * F)));
+    bool cur = have_a;
+    while (cur) {                                              // software pipeline: group b in flight while group a is summed
+      const long long rn = r + G;
+      const bool nxt = rn + 3 * RMS16_ROWL < nr;
+      if (nxt) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b[k] = __ldg(reinterpret_cast<const uint4*>(p + (rn + (long long)k * RMS16_ROWL) * F));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc16(a[k]);
+      r = rn;
+      if (nxt) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = b[k];
+      }
+      cur = nxt;
+    }
+    for (; r < nr; r += RMS16_ROWL) acc16(__ldg(reinterpret_cast<const uint4*>(p + r * F)));
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) { red[ry][0][cx * 16 + i + (cx >> 1)] = s[i]; red[ry][1][cx * 16 + i + (cx >> 1)] = q[i]; }
   __syncthreads();
-  const double n = (double)(r1 - r0);
-  double* o = ws + (long long)blockIdx.y * 2 * F;
   for (int c = threadIdx.x; c < 512; c += 256) {
     const int col = blockIdx.x * 512 + c;
     if (col >= F) break;
@@ -303,14 +324,13 @@ __global__ void __launch_bounds__(256) rms_u8x16_kernel(const uint8_t* __restric
     const int sc = c + (c >> 5);
 #pragma unroll
     for (int k = 0; k < RMS16_ROWL; ++k) { sx += red[k][0][sc]; sxx += red[k][1][sc]; }
-    const double sh = shift[col], dsx = (double)sx, dsxx = (double)sxx;
-    __stcg(o + col, dsx - n * sh);                            // sum(x - s) = Sx - n s
-    __stcg(o + F + col, fma(n * sh, sh, fma(-2.0 * sh, dsx, dsxx)));   // sum((x - s)^2) = Sxx - 2 s Sx + n s^2
+    atomicAdd(acc + col, sx);                                  // exact integers: any order gives the same totals
+    atomicAdd(acc + RMS16_MAXF + col, sxx);
   }
-  // ---- last row split of this column block folds the splits (deterministic order) and finishes the update
+  // ---- the last CTA of a column block (ticket per block) turns its 512 totals into the update: two columns per thread
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&tickets[blockIdx.x], 1u) == gridDim.y - 1) ? 1 : 0;
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket + blockIdx.x, 1u) == gridDim.y - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -319,20 +339,12 @@ __global__ void __launch_bounds__(256) rms_u8x16_kernel(const uint8_t* __restric
   for (int c = threadIdx.x; c < 512; c += 256) {
     const int col = blockIdx.x * 512 + c;
     if (col >= F) break;
-    // 16 independent L2 loads in flight per thread and pass: a serial chain of gridDim.y dependent L2 round trips in this
-    // one tail CTA was 50 of the first version's 70 us
-    double ss = 0.0, qq = 0.0;
-    for (int k0 = 0; k0 < (int)gridDim.y; k0 += 8) {
-      double a[8], b[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool ok = k0 + j < (int)gridDim.y;
-        a[j] = ok ? __ldcg(ws + (long long)(k0 + j) * 2 * F + col) : 0.0;
-        b[j] = ok ? __ldcg(ws + (long long)(k0 + j) * 2 * F + F + col) : 0.0;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { ss += a[j]; qq += b[j]; }
-    }
+    const double sx = (double)__ldcg(acc + col), sxx = (double)__ldcg(acc + RMS16_MAXF + col);   // < 2^53: exact
+    acc[col] = 0ull;
+    acc[RMS16_MAXF + col] = 0ull;
+    const double sh = shift[col];
+    const double ss = sx - n_b * sh;
+    const double qq = fma(n_b * sh, sh, fma(-2.0 * sh, sx, sxx));
     if (mode == 0) { sum_out[col] = ss; sq_out[col] = qq; continue; }
     const double old_mean = mean[col], old_var = var[col];
     const double ds = ss / n_b;                               // batch_mean - shift, shift == old_mean
@@ -343,46 +355,49 @@ __global__ void __launch_bounds__(256) rms_u8x16_kernel(const uint8_t* __restric
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    tickets[blockIdx.x] = 0u;
+    ticket[blockIdx.x] = 0u;
     __threadfence();
-    if (atomicAdd(&tickets[63], 1u) == gridDim.x - 1) {      // every column block has read the old count
-      tickets[63] = 0u;
+    if (atomicAdd(ticket + 63, 1u) == gridDim.x - 1) {       // every column block has read the old count
+      ticket[63] = 0u;
       if (mode == 1) count[0] = n_b + n_a;
     }
   }
 }
 
-static unsigned int* g_rms_tickets[64] = {nullptr};
-static unsigned int* rms_tickets() {
+// library-owned, self-cleaning state of the kernel above: [2][RMS16_MAXF] 64-bit totals + one ticket, per device
+static unsigned long long* g_rms_acc[64] = {nullptr};
+static unsigned long long* rms_acc_buffer() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (g_rms_tickets[dev] == nullptr) {
-    unsigned int* p = nullptr;
-    if (cudaMalloc(&p, 64 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    cudaMemset(p, 0, 64 * sizeof(unsigned int));
-    g_rms_tickets[dev] = p;
+  if (g_rms_acc[dev] == nullptr) {
+    unsigned long long* p = nullptr;
+    const size_t bytes = (size_t)(2 * RMS16_MAXF + 32) * sizeof(unsigned long long);     // totals + 64 32-bit tickets
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, bytes);
+    g_rms_acc[dev] = p;
   }
-  return g_rms_tickets[dev];
+  return g_rms_acc[dev];
 }
 
-// whole update (mode 1) or batch moments (mode 0) of uint8 rows in ONE launch; returns false when the shape does not fit
+// whole update (mode 1) or batch moments (mode 0) of uint8 rows in ONE launch; false when the shape does not fit
 static bool rms_u8x16_applicable(const void* x, long long N, int F) {
-  return F % 16 == 0 && cdiv(F, 512) <= 62 && N >= 64 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  // Sum(x^2) <= 65025 N must stay below 2^53 for the exact double conversion: N < 1.3e11 rows
+  return F % 16 == 0 && F <= RMS16_MAXF && cdiv(F, 512) <= 62 && N >= 64 && N < (1LL << 36) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
-static int rms_u8x16_launch(const void* x, long long N, int F, const double* shift, double* ws, int mode, double* sum_out,
+static int rms_u8x16_launch(const void* x, long long N, int F, const double* shift, int mode, double* sum_out,
                             double* sq_out, double* mean, double* var, double* count, cudaStream_t st) {
-  unsigned int* tk = rms_tickets();
-  if (tk == nullptr) { set_error("rms: ticket allocation failed"); return EAVIT_ECUDA; }
+  unsigned long long* acc = rms_acc_buffer();
+  if (acc == nullptr) { set_error("rms: accumulator allocation failed"); return EAVIT_ECUDA; }
   const int colb = cdiv(F, 512);
-  int splits = (4 * kNumSMs) / colb;                          // one wave: <= 4 resident CTAs of 256 threads per SM (58 registers)
+  int splits = (3 * kNumSMs) / colb;                          // one wave: 3 resident CTAs of 256 threads per SM (<= 85 registers)
   if (splits < 1) splits = 1;
-  if (splits > 1024) splits = 1024;
   int rows = cdiv(N, splits);
   if (rows < 4 * RMS16_ROWL) rows = 4 * RMS16_ROWL;
   splits = cdiv(N, rows);
   EAVIT_CHECK_ARG(rows / RMS16_ROWL + 1 <= 65536);           // 32-bit sums of squares stay exact per lane
-  rms_u8x16_kernel<<<dim3(colb, splits), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), N, F, shift, ws, rows, tk, mode, sum_out,
-                                                       sq_out, mean, var, count);
+  rms_u8x16_kernel<<<dim3(colb, splits), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), N, F, shift, acc, rows,
+                                                       reinterpret_cast<unsigned int*>(acc + 2 * RMS16_MAXF), mode, sum_out, sq_out, mean,
+                                                       var, count);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -396,17 +411,7 @@ __global__ void rms_reduce_kernel(const double* __restrict__ ws, int splits, int
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= F) return;
   double s = 0.0, q = 0.0;
-  for (int k0 = 0; k0 < splits; k0 += 8) {                 // 16 independent loads in flight (same order of additions as a plain loop)
-    double a[8], b[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const bool ok = k0 + j < splits;
-      a[j] = ok ? ws[(long long)(k0 + j) * 2 * F + c] : 0.0;
-      b[j] = ok ? ws[(long long)(k0 + j) * 2 * F + F + c] : 0.0;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s += a[j]; q += b[j]; }
-  }
+  for (int k = 0; k < splits; ++k) { s += ws[(long long)k * 2 * F + c]; q += ws[(long long)k * 2 * F + F + c]; }
   if (mode == 0) { sum_out[c] = s; sq_out[c] = q; return; }
   const double old_mean = mean[c], old_var = var[c], n_a = count[0], n_b = batch_count;
   const double ds = s / n_b;                            // batch_mean - shift, shift == old_mean
@@ -835,7 +840,7 @@ int eavit_rms_update(const void* x, int x_dtype, long long N, int F, double* mea
   EAVIT_CHECK_ARG(N > 0 && F > 0 && x && mean && var && count && workspace);
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == EAVIT_U8 && rms_u8x16_applicable(x, N, F))
-    return rms_u8x16_launch(x, N, F, mean, (double*)workspace, 1, nullptr, nullptr, mean, var, count, st);
+    return rms_u8x16_launch(x, N, F, mean, 1, nullptr, nullptr, mean, var, count, st);
   int splits = 0;
   int rc = rms_partial_dispatch(x, x_dtype, N, F, mean, (double*)workspace, splits, st);
   if (rc) return rc;
@@ -852,7 +857,7 @@ int eavit_rms_partial(const void* x, int x_dtype, long long N, int F, const doub
   EAVIT_CHECK_ARG(N > 0 && F > 0 && x && shift && sum && sumsq && workspace);
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == EAVIT_U8 && rms_u8x16_applicable(x, N, F))
-    return rms_u8x16_launch(x, N, F, shift, (double*)workspace, 0, sum, sumsq, nullptr, nullptr, nullptr, st);
+    return rms_u8x16_launch(x, N, F, shift, 0, sum, sumsq, nullptr, nullptr, nullptr, st);
   int splits = 0;
   int rc = rms_partial_dispatch(x, x_dtype, N, F, shift, (double*)workspace, splits, st);
   if (rc) return rc;
