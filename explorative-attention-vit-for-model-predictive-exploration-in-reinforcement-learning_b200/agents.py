@@ -419,12 +419,14 @@ class RNDAgent(nn.Module):
         call("eavit_ppo_loss", pol, w["old"], w["y"], w["adv"], ve, vi, w["te"], w["ti"], B, A, float(self.ppo_eps),
              float(self.ent_coef), gs, w["dpol"], w["dv"][B:], w["dv"][:B], w["stats"])
         train_ranges = self._trainable_ranges(rt)
-        # Data-parallel: the gradient exchange rides under the backward.  Each transformer layer's tensors are one contiguous
-        # block of the flat gradient; its all-reduce starts on the process group's stream as soon as the layer's last
-        # gradient kernel is enqueued (reverse layer order), so only the embedding / heads remainder is left for the end
-        # (replaces the reference's never-armed DDP reducer, train.py:243).
+        # Data-parallel (replaces the reference's never-armed DDP reducer, train.py:243).  Optional (EAVIT_GRAD_OVERLAP=1): each
+        # transformer layer's tensors are one contiguous block of the flat gradient, and its all-reduce can start on the
+        # process group's stream as soon as the layer's last gradient kernel is enqueued (reverse layer order).  MEASURED AND
+        # LEFT OFF: at 8 GPUs 8.18 ms/step with it, 8.14 without (2 GPUs: 8.05 / 8.04) -- the NCCL kernels take SMs from the
+        # persistent one-CTA-per-SM GEMM / attention kernels they run beside, which costs what the overlap saves; the step's
+        # 0.3 ms over the single-GPU time is the max over ranks of a synchronised step, not the 10 MB exchange itself.
         pending, done_ranges = [], []
-        overlap = (self.world_size > 1 and train_ranges is None and os.environ.get("EAVIT_GRAD_OVERLAP", "1") == "1"
+        overlap = (self.world_size > 1 and train_ranges is None and os.environ.get("EAVIT_GRAD_OVERLAP", "0") == "1"
                    and hasattr(rt.encoder, "layer_param_names"))
 
         def on_layer_done(li):
