@@ -83,9 +83,12 @@ def test_forward_vs_reference_golden(golden_dir, which):
     assert pol.shape == (16, 18) and ve.shape == (16, 1) and vi.shape == (16, 1)
     floor = bf16_floor(CFGS[which], P, torch.tensor(state))
     assert rel(pol.cpu().numpy(), G["fwd_policy"]) < TOL
-    # values: 1e-2, or the ideal-bf16 floor of this weight set when cancellation lifts it above 1e-2 (see bf16_floor)
-    assert rel(ve.cpu().numpy(), G["fwd_value_ext"]) < max(TOL, 1.25 * floor[1]), floor
-    assert rel(vi.cpu().numpy(), G["fwd_value_int"]) < max(TOL, 1.25 * floor[2]), floor
+    # values: 1e-2 -- or, where cancellation in the value heads (|v| ~ 0.05 = a sum of 256 terms of ~0.006) lifts the error of
+    # ANY bf16-operand evaluation of these weights above 1e-2, no worse than that ideal-bf16 emulation of the fp32 oracle.
+    # Measured (profiles/r2_parity_measured.txt): lucid 4.9e-3 / 3.1e-3, hg 4.6e-3 / 3.9e-3 (both under 1e-2);
+    # cls 1.15e-2 / 1.05e-2 against an ideal-bf16 floor of 1.44e-2 / 1.24e-2.
+    assert rel(ve.cpu().numpy(), G["fwd_value_ext"]) < max(TOL, floor[1]), floor
+    assert rel(vi.cpu().numpy(), G["fwd_value_int"]) < max(TOL, floor[2]), floor
     # raw uint8 frames (divided by 255 in-kernel) give the same result as the pre-divided float32 input
     with torch.no_grad():
         pol8, _, _ = agent.model(torch.tensor(state_u8).cuda())
@@ -95,7 +98,7 @@ def test_forward_vs_reference_golden(golden_dir, which):
     a, v1, v2, lg = agent.get_action(state)
     assert a.dtype == np.int64 and lg.dtype == np.float32 and lg.shape == (16, 18)
     assert rel(lg, G["act_logits"]) < TOL
-    assert rel(v1, G["act_value_ext"]) < max(TOL, 1.25 * floor[1]) and rel(v2, G["act_value_int"]) < max(TOL, 1.25 * floor[2])
+    assert rel(v1, G["act_value_ext"]) < max(TOL, floor[1]) and rel(v2, G["act_value_int"]) < max(TOL, floor[2])
     u = np.random.default_rng(0)  # noqa  (only documents that the draw comes from np.random, agents.py:206)
     # intrinsic reward
     obs = rng.normal(0, 1, (5, 1, 84, 84)).clip(-5, 5)
@@ -162,12 +165,15 @@ def test_loss_and_gradients_vs_oracle(which):
     ref_all = np.concatenate(flat_ref)
     tot = rel(np.concatenate(flat_got), ref_all)
     assert tot < TOL, (tot, sorted(worst.items(), key=lambda kv: -kv[1])[:8])
-    # per tensor: within 5x the tolerance, unless the tensor carries < 2 % of the gradient norm (e.g. the q/k weights
+    # per tensor: within 2.5x the tolerance, unless the tensor carries < 2 % of the gradient norm (e.g. the q/k weights
     # of the last layer, whose gradient is a difference of nearly equal softmax-Jacobian terms).  The widest tensors are
     # the ones behind a ReLU fed by bf16 features (extra_layer): a unit whose pre-activation is within the 0.5 % feature
     # error of zero flips its mask, which is a finite gradient difference however small the forward difference.
+    # Measured (profiles/r2_parity_measured.txt): totals 3.5e-3 / 2.2e-3 / 2.8e-3; worst tensor above 2 % of the norm:
+    # extra_layer.0.weight 1.9e-2 / 1.0e-2 / 1.8e-2, every other one <= 1.2e-2; worst small tensor: the HF query bias of
+    # layer 0, 2.2e-2 on 0.03 % of the gradient norm.
     tn = float(np.linalg.norm(ref_all))
-    bad = {k: v for k, v in worst.items() if v > 5 * TOL and float(P[k].grad.norm()) > 0.02 * tn}
+    bad = {k: v for k, v in worst.items() if v > 2.5 * TOL and float(P[k].grad.norm()) > 0.02 * tn}
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
 
 
@@ -187,7 +193,7 @@ def test_train_model_matches_oracle_trajectory():
     assert len(stats) == len(log) == cfg.epoch * cfg.mini_batch
     for i, t in enumerate(log):
         for j, k in ((1, "actor"), (2, "critic_ext"), (3, "critic_int"), (4, "entropy"), (5, "rnd")):
-            assert abs(stats[i, j] - t[k]) <= 3e-2 * max(abs(t[k]), 1e-2), (i, k, stats[i, j], t[k])
+            assert abs(stats[i, j] - t[k]) <= TOL * max(abs(t[k]), 1e-2), (i, k, stats[i, j], t[k])     # measured <= 6.3e-3
     sd = agent.state_dict()
     num = den1 = den2 = 0.0
     for k in O.trainable_names(P):
@@ -195,8 +201,10 @@ def test_train_model_matches_oracle_trajectory():
         d_got = (sd[k].cpu() - P0[k]).reshape(-1).double().numpy()
         num += float(d_ref @ d_got); den1 += float(d_ref @ d_ref); den2 += float(d_got @ d_got)
     cos = num / np.sqrt(den1 * den2)
-    assert cos > 0.9, cos
-    assert abs(np.sqrt(den2 / den1) - 1) < 0.1
+    # Adam's first steps move every weight by ~lr * sign(g), so elements whose gradient is rounding noise take a random
+    # sign: the update is compared as a direction and a length (measured: cosine 0.9964, norm ratio 1.0006)
+    assert cos > 0.99, cos
+    assert abs(np.sqrt(den2 / den1) - 1) < 0.01
     for k in P:                                   # frozen target network untouched
         if k.startswith("rnd.target."):
             assert torch.equal(sd[k].cpu(), P0[k])
