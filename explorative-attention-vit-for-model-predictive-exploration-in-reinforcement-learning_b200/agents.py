@@ -380,14 +380,19 @@ class RNDAgent(nn.Module):
                      old=old.contiguous())
         # The rollout lives in buffers that keep their addresses from update to update (same shapes / dtypes): the captured
         # step graph stays valid across updates.  One device-to-device copy of what was uploaded (0.1 ms at cfg3).
-        R = self.__dict__.setdefault("_rollout_buf", {})
+        pool = self.__dict__.setdefault("_rollout_buf", {})              # one buffer per (name, shape, dtype): raw-frame and float
         theirs = {a.data_ptr() for a in (states, target_ext, target_int, y, adv, next_obs_norm, old_policy) if torch.is_tensor(a)}
+        R = {}                                                           # callers may alternate without invalidating the graphs
         for k, t in fresh.items():
-            b = R.get(k)
-            if b is None or b.shape != t.shape or b.dtype != t.dtype or b.device != t.device:
-                R[k] = t.clone() if t.data_ptr() in theirs else t        # never adopt (and later overwrite) the caller's own tensor
+            sig = (k, tuple(t.shape), t.dtype, t.device)
+            b = pool.get(sig)
+            if b is None:
+                if len(pool) >= 21:                                      # shapes changed for good: let the old buffers go
+                    pool.clear()
+                b = pool[sig] = t.clone() if t.data_ptr() in theirs else t   # never adopt (and later overwrite) the caller's tensor
             else:
                 b.copy_(t, non_blocking=True)
+            R[k] = b
         return R
 
     # ---- the optimiser step as ONE captured CUDA graph ---------------------------------------------------------------
@@ -430,11 +435,22 @@ class RNDAgent(nn.Module):
             # kernel attributes (none of which may happen inside a capture); its gradients are discarded by the next zero_grad
             self._train_step_eager(R, sidx, smask, sstats, False)
             torch.cuda.synchronize(dev)
+            # capture_begin / capture_end directly: the torch.cuda.graph context manager also runs gc.collect() and
+            # empty_cache(), which costs ~0.5 s next to a 3 GB rollout and makes the next upload re-cudaMalloc its buffers
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                if rt.dropout_active():
-                    call("eavit_dropout_epoch_bump")
-                self._train_step_eager(R, sidx, smask, sstats, True)
+            cur = torch.cuda.current_stream(dev)
+            cap = self.__dict__.get("_capture_stream") or torch.cuda.Stream(device=dev)
+            self._capture_stream = cap
+            cap.wait_stream(cur)
+            with torch.cuda.stream(cap):
+                graph.capture_begin()
+                try:
+                    if rt.dropout_active():
+                        call("eavit_dropout_epoch_bump")
+                    self._train_step_eager(R, sidx, smask, sstats, True)
+                finally:
+                    graph.capture_end()
+            cur.wait_stream(cap)
             ent = cache[key] = (graph, sidx, smask, sstats)
         graph, sidx, smask, sstats = ent
         sidx.copy_(idx, non_blocking=True)
