@@ -16,15 +16,22 @@ if which in ("all", "gemm"):
     hact = torch.empty(T, MLP, device="cuda", dtype=torch.bfloat16)
     hpre = torch.empty_like(hact)
     for _ in range(reps):
-        ops.gemm(x, w1, bias=b1, act=ops.ACT_GELU, out_bf16=hact, out_pre=hpre)          # MLP1 fwd
+        ops.gemm(x, w1, bias=b1, act=ops.ACT_GELU_SAVE_GRAD, out_bf16=hact, out_pre=hpre)  # MLP1 fwd: GELU + stored gelu'   <256, 6, 0>
     w2 = (torch.randn(D, MLP, device="cuda") / 32).bfloat16()
     dh = torch.empty_like(hact)
+    cs = torch.zeros(MLP, device="cuda")
     for _ in range(reps):
-        ops.gemm(x, w2, b_mn=True, act=ops.ACT_GELU_BWD, aux=hpre, out_bf16=dh)            # MLP2 dX + GELU'
+        ops.gemm(x, w2, b_mn=True, act=ops.ACT_MUL_AUX, aux=hpre, out_bf16=dh, colsum=cs)  # MLP2 dX * gelu' + bias-gradient sums  <256, 7, 0>
     res = torch.randn(T, D, device="cuda")
     out = torch.empty_like(res)
+    xn = torch.empty(T, D, device="cuda", dtype=torch.bfloat16)
+    g, be = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+    mu, rs = torch.empty(T, device="cuda"), torch.empty(T, device="cuda")
+    b2 = torch.randn(D, device="cuda")
     for _ in range(reps):
-        ops.gemm(hact, w2, bias=torch.randn(D, device="cuda"), residual=res, out_f32=out)  # MLP2 fwd + residual
+        ops.gemm(hact, w2, bias=b2, residual=res, out_f32=out)                             # MLP2 fwd + residual             <256, 4, 0>
+    for _ in range(reps):
+        ops.gemm(hact, w2, bias=b2, residual=res, out_f32=out, out_bf16=xn, ln=(g, be, mu, rs, 1e-5))   # + fused LayerNorm   <256, 8, 0>
     wq = (torch.randn(3 * D, D, device="cuda") / 16).bfloat16()
     qkv = torch.empty(T, 3 * D, device="cuda", dtype=torch.bfloat16)
     for _ in range(reps):
@@ -49,5 +56,28 @@ if which in ("all", "attn"):
     for _ in range(reps):
         ops.call("eavit_attention_bwd_tc", qkv, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0)
         ops.call("eavit_attention_bwd_tct", qkv, o, do, lse, ss, len(lens), 197, qkv.shape[0], H, DH, DH ** -0.5, dqkv, 0.0, 0)
+if which in ("all", "num"):
+    F, N = 84 * 84, 128 * 128
+    xu8 = torch.randint(0, 256, (N, F), dtype=torch.uint8, device="cuda")
+    mean = torch.zeros(F, dtype=torch.float64, device="cuda"); var = torch.ones(F, dtype=torch.float64, device="cuda")
+    cnt = torch.full((1,), 1e-4, dtype=torch.float64, device="cuda")
+    outn = torch.empty(N, F, device="cuda")
+    for _ in range(reps):
+        ops.rms_update(xu8, mean, var, cnt)                                                 # rms_u8x16_kernel
+        ops.obs_normalize(xu8, mean, var, out=outn)                                         # obs_lut_build + obs_normalize_u8_glut
+    xf = xu8.float()
+    for _ in range(reps):
+        ops.rms_update(xf, mean, var, cnt)
+        ops.obs_normalize(xf, mean, var, out=outn)
+    x2 = torch.randn(201216, 256, device="cuda")
+    dy = torch.randn(201216, 256, device="cuda").bfloat16()
+    xo = torch.empty(201216, 256, device="cuda", dtype=torch.bfloat16)
+    m2, r2 = torch.empty(201216, device="cuda"), torch.empty(201216, device="cuda")
+    gam, bet = torch.ones(256, device="cuda"), torch.zeros(256, device="cuda")
+    dgam, dbet, dxs = torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda")
+    dxo, dx16 = torch.empty_like(x2), torch.empty_like(xo)
+    for _ in range(reps):
+        ops.call("eavit_layernorm_fwd", x2, 256, gam, bet, xo, ops.BF16, 256, m2, r2, 201216, 256, 1e-5)
+        ops.call("eavit_layernorm_bwd", dy, ops.BF16, 256, x2, 256, m2, r2, gam, x2, 256, dxo, 256, dx16, 256, dgam, dbet, dxs, 0.0, 0, 201216, 256)
 torch.cuda.synchronize()
 print("done")
