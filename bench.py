@@ -446,7 +446,12 @@ def main():
                 "step_model_tflops": FLOPS_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12,
                 "step_executed_tflops": FLOPS_PER_SAMPLE * executed_fraction() * B / (ms / args.steps * 1e-3) / 1e12,
                 "executed_fraction_of_nominal_flops": executed_fraction(),
-                "step_frac_of_sustained_peak": FLOPS_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
+                "step_frac_of_sustained_peak": FLOPS_PER_SAMPLE * B / (ms / args.steps * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                # every kernel family of the step (CUDA events around each launch, eager pass): launches, time, share, and the
+                # achieved TFLOP/s of the dense contractions
+                "per_kernel": [{"kernel": gname, "launches_per_step": a[0] / nprof, "ms_per_step": a[1] / nprof, "share": a[1] / tot_ms,
+                                "tflops": (a[2] / (a[1] * 1e-3) / 1e12 if a[2] > 0 else None)}
+                               for gname, a in sorted(groups.items(), key=lambda kv: -kv[1][1])[:14]]}
     if args.profile_out and rank == 0:
         rows = sorted(((l, n / nprof, tms / nprof, fl) for l, (n, tms, fl) in table.items()), key=lambda r: -r[2])
         json.dump({"per_step": [{"kernel": l, "launches": n, "ms": tms, "tflops": (fl * n / (tms * 1e-3) / 1e12 if fl else None)}
