@@ -51,10 +51,11 @@ def executed_fraction(D=256, inner=256, mlp=1024, depth=3, s_a=196, s_b=197):
         tot += depth * S * per_tok
         dead += (S - 1) * (proj + ff + 4 * S * inner)
     return 1.0 - dead / tot
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at the cfg3 shapes (ncu --set full, profiles/)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the cfg3 shapes (ncu --set full, profiles/r2_ncu_full_top_kernels.md)
 NCU_DRAM_BYTES_PER_LAUNCH = {
-    "attention_bwd_tct": 793.4e6, "attention_bwd_tc": 686.3e6, "attention_fwd_tc": 396.6e6,
-    "gemm_bf16_tcgen05 M=201216 N=1024 K=256 kmn act=2": 895.3e6, "gemm_bf16_tcgen05 M=201216 N=1024 K=256 kk act=1": 874.3e6,
+    "attention_bwd_tct": 794.0e6, "attention_bwd_tc": 683.0e6, "attention_fwd_tc": 395.9e6,
+    "gemm_bf16_tcgen05 M=201216 N=1024 K=256 kmn act=7": 892.0e6, "gemm_bf16_tcgen05 M=201216 N=1024 K=256 kk act=8": 875.0e6,
+    "gemm_bf16_tcgen05 M=201216 N=256 K=1024 kk act=0 +ln": 895.0e6,
 }
 WORKLOAD = ("cfg3: lucidrains explorative-attention ViT (expGlados3) RND agent, 128 envs x 128 steps per GPU, "
             "minibatch 512, 4 epochs, dropout keys 0.0")
