@@ -69,5 +69,15 @@ def check(rc: int, what: str):
         raise RuntimeError(f"eavit_b200.{what} failed with status {rc}: {lib().eavit_last_error().decode()}")
 
 
-def launch_count() -> int:
-    return int(lib().eavit_launch_count())
+_replayed = 0
+
+
+def add_replayed(n: int) -> None:
+    """Kernel launches executed by a CUDA-graph replay (the library only sees the launches of the capture)."""
+    global _replayed
+    _replayed += int(n)
+
+
+def launch_count(include_replays: bool = True) -> int:
+    """Kernels of this library launched so far: direct launches counted inside the library + kernel nodes of replayed graphs."""
+    return int(lib().eavit_launch_count()) + (_replayed if include_replays else 0)

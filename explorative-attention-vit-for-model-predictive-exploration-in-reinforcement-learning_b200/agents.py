@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import dist, ops
+from . import _lib, dist, ops
 from .config import default_config
 from .model import CnnActorCriticNetwork, RNDModel, Runtime, ViT_IMPLEMENTATION, _as_device_image
 from .ops import call
@@ -138,12 +138,15 @@ class _CapturedCall:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count(include_replays=False)
         with torch.cuda.graph(self.graph):
             self.out = fn(self.x)
+        self.nodes = _lib.launch_count(include_replays=False) - n0
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         self.x.copy_(x, non_blocking=True)
         self.graph.replay()
+        _lib.add_replayed(self.nodes)
         return self.out
 
 
@@ -442,6 +445,7 @@ class RNDAgent(nn.Module):
             cap = self.__dict__.get("_capture_stream") or torch.cuda.Stream(device=dev)
             self._capture_stream = cap
             cap.wait_stream(cur)
+            n0 = _lib.launch_count(include_replays=False)
             with torch.cuda.stream(cap):
                 graph.capture_begin()
                 try:
@@ -451,11 +455,13 @@ class RNDAgent(nn.Module):
                 finally:
                     graph.capture_end()
             cur.wait_stream(cap)
-            ent = cache[key] = (graph, sidx, smask, sstats)
-        graph, sidx, smask, sstats = ent
+            nodes = _lib.launch_count(include_replays=False) - n0      # kernel nodes of the graph = launches of one replay
+            ent = cache[key] = (graph, sidx, smask, sstats, nodes)
+        graph, sidx, smask, sstats, nodes = ent
         sidx.copy_(idx, non_blocking=True)
         smask.copy_(mask, non_blocking=True)
         graph.replay()
+        _lib.add_replayed(nodes)
         rt._bump_gen("ac", B)                                           # a pending autograd backward of these buffers must notice
         if rt.dropout_active():
             rt._epoch_gen = getattr(rt, "_epoch_gen", 0) + 1
