@@ -312,7 +312,19 @@ class ViTEncoder:
         pln = bf.get("pln", (rows, PD), torch.bfloat16)
         e0 = bf.get("e0", (rows, D), torch.float32)
         x0 = bf.get("x0", (T, D), torch.float32)
-        if c.impl == "lucidrains":
+        fused_embed = (c.impl == "lucidrains" and D == 256 and PD % 16 == 0 and PD <= 192 and c.channels * c.patch * c.image <= 2080
+                       and os.environ.get("EAVIT_FUSE_EMBED", "1") == "1")
+        if fused_embed:
+            # patchify + LayerNorm(PD) + Linear + LayerNorm(D) + token / position assembly: one kernel (csrc/embed_fused.cu)
+            pm, pr = bf.get("pmean", (rows,), torch.float32), bf.get("prstd", (rows,), torch.float32)
+            m3, r3 = bf.get("m3", (rows,), torch.float32), bf.get("r3", (rows,), torch.float32)
+            tokA = s.w(p + ("exploration_token" if c.use_explorative else "cls_token"))
+            call("eavit_embed_fused_fwd", img, img_dt, sample_idx, B, c.channels, c.image, c.patch, self.mode,
+                 s.w(p + "to_patch_embedding.1.weight"), s.w(p + "to_patch_embedding.1.bias"), 1e-5,
+                 s.b16(p + "to_patch_embedding.2.weight"), s.w(p + "to_patch_embedding.2.bias"),
+                 s.w(p + "to_patch_embedding.3.weight"), s.w(p + "to_patch_embedding.3.bias"), 1e-5,
+                 s.w(p + "pos_embedding"), tokA, pln, pm, pr, e0, m3, r3, x0)
+        elif c.impl == "lucidrains":
             pm, pr = bf.get("pmean", (rows,), torch.float32), bf.get("prstd", (rows,), torch.float32)
             call("eavit_patchify", img, img_dt, sample_idx, B, c.channels, c.image, c.patch, 0,
                  s.w(p + "to_patch_embedding.1.weight"), s.w(p + "to_patch_embedding.1.bias"), 1e-5, pln, pm, pr)

@@ -257,6 +257,7 @@ _SPECS = {
     "eavit_patchify": "pipiiiiippfppp",
     "eavit_patchify_ln_bwd": "pipiiiiipppppp",
     "eavit_embed_assemble": "ppppiiiip",
+    "eavit_embed_fused_fwd": "pipiiiii" "ppf" "pp" "ppf" "pp" "ppp" "ppp" "p",
     "eavit_embed_assemble_bwd": "piiiippppp",
     "eavit_sgemm_small": "pliplippplliiii".replace("ll", "l", 0),
     "eavit_heads_value_fwd": "ppppppiiip",

@@ -241,6 +241,15 @@ int eavit_patchify_ln_bwd(const void* img, int img_dtype, const long long* sampl
  * the reference's token bug, vit.py:141-156; 1: single CLS sequence; 2: HF pair, vit_hg.py:121-145). */
 int eavit_embed_assemble(const float* e, const float* pos, const float* tokA, const float* tokB, int mode, int B, int np,
                          int D, float* x, void* stream);
+/* The four steps above as ONE kernel for the lucidrains variants (mode 0 explorative pair / 1 CLS; patch_dim % 16 == 0,
+ * patch_dim <= 192, dim == 256): vit.py:109-114 to_patch_embedding (Rearrange, LayerNorm(patch_dim), Linear, LayerNorm(dim)) +
+ * vit.py:141-158 token prepend / positional add.  Image rows staged in shared memory, LayerNorm'ed patches written straight into
+ * the swizzled A tile of a tcgen05 GEMM whose weight is TMA-loaded once per CTA, LayerNorm(dim) + assembly in the epilogue.
+ * Also writes what the backward needs: pln bf16 [B*np, PD] (+ pmean, prstd), e0 fp32 [B*np, 256] (+ m3, r3). */
+int eavit_embed_fused_fwd(const void* img, int img_dtype, const long long* sample_idx /* may be NULL */, int B, int C, int HW, int P,
+                          int mode, const float* g1, const float* b1, float eps1, const void* w_bf16, const float* bias,
+                          const float* g3, const float* b3, float eps3, const float* pos, const float* tok, void* pln_bf16,
+                          float* pmean, float* prstd, float* e0, float* m3, float* r3, float* x0, void* stream);
 int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, float* g, void* g_bf16, float* dpos,
                              float* dtokA, float* dtokB, void* stream);
 
