@@ -2,8 +2,8 @@
 // LayerNorm(patch_dim), Linear(patch_dim, dim), LayerNorm(dim)) + token prepend + positional add (vit.py:141-158), for
 // patch_dim <= 192, dim == 256:
 //
-//   producers (8 warps)   stage the C x P image rows of a patch row in shared memory (coalesced; uint8 frames are divided by
-//                         255 here), LayerNorm(patch_dim) one patch per warp, and write the normalised bf16 patch (a) into the
+//   producers (8 warps)   gather a patch (C x P runs of P contiguous pixels; uint8 frames are divided by 255 here) straight from
+//                         global memory, LayerNorm(patch_dim) one patch per warp, and write the normalised bf16 patch (a) into the
 //                         128-byte-swizzled A tile of the tensor-core GEMM [128 patches x 192] and (b) to global memory for the
 //                         backward (the dW GEMM's operand) together with (mean, rstd)
 //   warp 0                loads the whole weight [256, patch_dim] ONCE per CTA with TMA (3 boxes of 64 x 256, out-of-bounds
@@ -32,16 +32,18 @@ constexpr int PROD_WARPS = 8, EPI_WARPS = 4;
 constexpr int THREADS = (1 + PROD_WARPS + EPI_WARPS) * 32;     // 416
 constexpr int A_BYTES = 3 * TILE_M * 128;    // 3 k-blocks x [128 rows][128 B]
 constexpr int W_BYTES = 3 * D * 128;         // 3 k-blocks x [256 rows][128 B]
-constexpr int MAX_STAGE_FLOATS = 4 * 6 * 84 + 64;          // C x P x HW image rows of one patch row (+ slack)
+
+constexpr int NSTAGE = 4;                    // ring of uint8 patch-row staging buffers (cp.async, prefetch distance 2)
+constexpr int STAGE_BYTES = 2048;            // C * P rows of HW bytes (4 x 6 x 84 = 2016)
 
 struct Smem {
   static constexpr int OFF_W = 0;
   static constexpr int OFF_A = OFF_W + W_BYTES;                    // 2 buffers
   static constexpr int OFF_EPI = OFF_A + 2 * A_BYTES;              // 4 warps x [32][32] fp32 transpose tiles
-  static constexpr int OFF_STAGE = OFF_EPI + EPI_WARPS * 4096;     // float [C*P*HW] image rows
-  static constexpr int OFF_KOFF = OFF_STAGE + MAX_STAGE_FLOATS * 4;   // int [KPAD]
-  static constexpr int OFF_VEC = OFF_KOFF + KPAD * 4;              // float bias[256], g3[256], b3[256]
-  static constexpr int OFF_BAR = OFF_VEC + 3 * D * 4;
+  static constexpr int OFF_STAGE = OFF_EPI + EPI_WARPS * 4096;     // uint8 [NSTAGE][C*P*HW] image rows of a patch row
+  static constexpr int OFF_VEC = OFF_STAGE + NSTAGE * STAGE_BYTES; // float bias[256], g3[256], b3[256]
+  static constexpr int OFF_LUT = OFF_VEC + 3 * D * 4;              // float [256]: b / 255 correctly rounded (np.float32(x) / 255.)
+  static constexpr int OFF_BAR = OFF_LUT + 256 * 4;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;
 };
 static_assert(Smem::TOTAL <= 232448, "shared memory");
@@ -74,8 +76,6 @@ template <typename ImgT>
 __global__ void __launch_bounds__(THREADS, 1) embed_fused_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stage = reinterpret_cast<float*>(smem + Smem::OFF_STAGE);
-  int* koff = reinterpret_cast<int*>(smem + Smem::OFF_KOFF);
   float* s_bias = reinterpret_cast<float*>(smem + Smem::OFF_VEC);
   float* s_g3 = s_bias + D;
   float* s_b3 = s_g3 + D;
@@ -91,10 +91,8 @@ __global__ void __launch_bounds__(THREADS, 1) embed_fused_kernel(const __grid_co
   // zero the A tiles once: the K padding (patch_dim .. 192) must be finite zeros for the MMA
   for (int i = threadIdx.x; i < 2 * A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + Smem::OFF_A)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < D; i += THREADS) { s_bias[i] = p.bias[i]; s_g3[i] = p.g3[i]; s_b3[i] = p.b3[i]; }
-  for (int k = threadIdx.x; k < p.PD; k += THREADS) {                  // (p1 p2 c) element order, vit.py:110
-    const int c = k % p.C, p2 = (k / p.C) % p.P, p1 = k / (p.C * p.P);
-    koff[k] = (c * p.P + p1) * p.HW + p2;
-  }
+  float* s_lut = reinterpret_cast<float*>(smem + Smem::OFF_LUT);
+  for (int i = threadIdx.x; i < 256; i += THREADS) s_lut[i] = __fdiv_rn((float)i, 255.0f);      // one IEEE division per value, not per pixel
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmW);
     tc::mbar_init(w_full, 1);
@@ -139,7 +137,6 @@ __global__ void __launch_bounds__(THREADS, 1) embed_fused_kernel(const __grid_co
   } else if (warp <= PROD_WARPS) {
     // ===================================== producers: patchify + LayerNorm(patch_dim) =====================================
     const int pw = warp - 1;                              // 0..7
-    const int ptid = threadIdx.x - 32;                    // 0..255
     const ImgT* img = reinterpret_cast<const ImgT*>(p.img);
     // token rows: x0[token row of sample b] = token + pos_embedding[0]
     {
@@ -152,17 +149,48 @@ __global__ void __launch_bounds__(THREADS, 1) embed_fused_kernel(const __grid_co
         }
       }
     }
-    // this lane's elements of a patch: k = 2 lane + 64 i + {0, 1}
+    // this lane's elements of a patch: k = 2 lane + 64 i + {0, 1}, (p1 p2 c) order (vit.py:110): pixel (c, p1, p2) of the patch
     float g1v[3][2], b1v[3][2];
+    int goff[3][2];                                       // offset of the element inside the sample image, relative to the patch origin
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int k = 2 * lane + 64 * i + e;
-        g1v[i][e] = k < p.PD ? p.g1[k] : 0.f;
-        b1v[i][e] = k < p.PD ? p.b1[k] : 0.f;
+        const bool ok = k < p.PD;
+        g1v[i][e] = ok ? p.g1[k] : 0.f;
+        b1v[i][e] = ok ? p.b1[k] : 0.f;
+        const int c = k % p.C, p2 = (k / p.C) % p.P, p1 = k / (p.C * p.P);
+        goff[i][e] = ok ? (c * p.HW + p1) * p.HW + p2 : -1;
       }
-    const int rowlen = p.C * p.P * p.HW;                  // floats staged per patch row
+    // The pixels are gathered straight from global memory: a patch is C x P runs of P contiguous pixels, neighbouring patches
+    // share their 32-byte sectors (L1 hits), and nothing synchronises the eight producer warps with each other -- the first
+    // version staged whole image rows in shared memory behind two CTA-wide barriers per patch row and spent 80 us per tile
+    // waiting on them.  Two patches per warp are in flight.
+    auto load_patch = [&](int row, float (&v)[3][2]) {
+      const int b = row / p.np, j = row - b * p.np, prow = j / p.npr, pcol = j - prow * p.npr;
+      const long long src = p.sample_idx ? p.sample_idx[b] : (long long)b;
+      const ImgT* base = img + (size_t)src * p.C * p.HW * p.HW + (size_t)(prow * p.P) * p.HW + pcol * p.P;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) v[i][e] = goff[i][e] >= 0 ? pix(base + goff[i][e]) : 0.f;
+    };
+    // uint8 frames (what the device-resident rollout holds): the C x P image rows of a patch row (2 016 bytes) are staged with
+    // cp.async into a ring of four buffers, two patch rows ahead of the one being normalised -- the gather latency is off the
+    // critical path and every pixel is read from global memory once, as whole 84-byte rows.
+    int soff[3][2];                                       // byte offset of the element inside a staged patch row, relative to the patch
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = 2 * lane + 64 * i + e;
+        const int c = k % p.C, p2 = (k / p.C) % p.P, p1 = k / (p.C * p.P);
+        soff[i][e] = k < p.PD ? (c * p.P + p1) * p.HW + p2 : 0;
+      }
+    const int ptid = threadIdx.x - 32;                    // 0..255
+    const int pieces = (p.C * p.P * p.HW) / 4;            // 4-byte cp.async pieces per patch row (HW % 4 == 0)
+    const int ppr = p.HW / 4;                             // pieces per image row
     int it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
@@ -170,57 +198,97 @@ __global__ void __launch_bounds__(THREADS, 1) embed_fused_kernel(const __grid_co
       tc::mbar_wait(&a_empty[s], ph ^ 1);
       uint8_t* A = smem + Smem::OFF_A + s * A_BYTES;
       const int row_lo = tile * TILE_M, row_hi = min(p.rows, row_lo + TILE_M);
-      // walk the patch rows (sample b, patch row prow) that intersect [row_lo, row_hi)
-      int r = row_lo;
-      while (r < row_hi) {
-        const int b = r / p.np, j = r - b * p.np, prow = j / p.npr, pc0 = j - prow * p.npr;
-        const int n_here = min(p.npr - pc0, row_hi - r);   // patches of this patch row inside the tile
-        const long long src = p.sample_idx ? p.sample_idx[b] : (long long)b;
-        const ImgT* base = img + (size_t)src * p.C * p.HW * p.HW + (size_t)prow * p.P * p.HW;
-        prod_bar();                                        // the previous patch row's staging buffer is consumed
-        for (int i = ptid; i < rowlen; i += PROD_WARPS * 32) {
-          const int cr = i / p.HW, x = i - cr * p.HW;      // cr = c * P + p1
-          const int c = cr / p.P, p1 = cr - c * p.P;
-          stage[i] = pix(base + ((size_t)c * p.HW + p1) * p.HW + x);
-        }
-        prod_bar();
-        for (int q = pw; q < n_here; q += PROD_WARPS) {
-          const int row = r + q;                           // global patch row
-          const float* tp = stage + (pc0 + q) * p.P;
-          float v[3][2];
-          float sum = 0.f;
+      auto finish_patch = [&](int row, const float (&v)[3][2]) {
+        float sum = 0.f;
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i) sum += v[i][0] + v[i][1];
+        const float mu = warp_sum(sum) / (float)p.PD;
+        float qq = 0.f;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int k = 2 * lane + 64 * i + e;
-              v[i][e] = k < p.PD ? tp[koff[k]] : 0.f;
-              sum += v[i][e];
-            }
-          const float mu = warp_sum(sum) / (float)p.PD;
-          float qq = 0.f;
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+          for (int e = 0; e < 2; ++e)
+            if (goff[i][e] >= 0) { const float d = v[i][e] - mu; qq += d * d; }
+        const float rs = rsqrtf(warp_sum(qq) / (float)p.PD + p.eps1);
+        if (lane == 0) { p.pmean[row] = mu; p.prstd[row] = rs; }
+        const int tr = row - row_lo;                       // row inside the tile
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int k = 2 * lane + 64 * i + e;
-              if (k < p.PD) { const float d = v[i][e] - mu; qq += d * d; }
-            }
-          const float rs = rsqrtf(warp_sum(qq) / (float)p.PD + p.eps1);
-          if (lane == 0) { p.pmean[row] = mu; p.prstd[row] = rs; }
-          const int tr = row - row_lo;                     // row inside the tile
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int k = 2 * lane + 64 * i;
-            if (k < p.PD) {
-              const uint32_t pk = pack_bf16x2((v[i][0] - mu) * rs * g1v[i][0] + b1v[i][0], (v[i][1] - mu) * rs * g1v[i][1] + b1v[i][1]);
-              // element k of k-block i: byte 4 lane of the 128-byte row = chunk lane / 4, offset (lane & 3) * 4
-              *reinterpret_cast<uint32_t*>(A + i * (TILE_M * 128) + sw_off(tr, lane >> 2) + (lane & 3) * 4) = pk;
-              *reinterpret_cast<uint32_t*>(p.pln + (size_t)row * p.PD + k) = pk;
-            }
+        for (int i = 0; i < 3; ++i) {
+          if (goff[i][0] >= 0) {
+            const uint32_t pk = pack_bf16x2((v[i][0] - mu) * rs * g1v[i][0] + b1v[i][0], (v[i][1] - mu) * rs * g1v[i][1] + b1v[i][1]);
+            // element k of k-block i: byte 4 lane of the 128-byte row = chunk lane / 4, offset (lane & 3) * 4
+            *reinterpret_cast<uint32_t*>(A + i * (TILE_M * 128) + sw_off(tr, lane >> 2) + (lane & 3) * 4) = pk;
+            *reinterpret_cast<uint32_t*>(p.pln + (size_t)row * p.PD + 2 * lane + 64 * i) = pk;
           }
         }
-        r += n_here;
+      };
+      if constexpr (sizeof(ImgT) == 1) {
+        // patch rows that intersect the tile: (first patch row index r, sample, patch row, first patch column, count)
+        auto prow_of = [&](int r, int& b, int& prow, int& pc0, int& n_here) {
+          b = r / p.np;
+          const int j = r - b * p.np;
+          prow = j / p.npr;
+          pc0 = j - prow * p.npr;
+          n_here = min(p.npr - pc0, row_hi - r);
+        };
+        auto prefetch = [&](int r, int slot) {              // all 256 producer threads
+          if (r < row_hi) {
+            int b, prow, pc0, n_here;
+            prow_of(r, b, prow, pc0, n_here);
+            const long long src = p.sample_idx ? p.sample_idx[b] : (long long)b;
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(p.img) + (size_t)src * p.C * p.HW * p.HW + (size_t)prow * p.P * p.HW;
+            const uint32_t dst = tc::smem_u32(smem + Smem::OFF_STAGE + slot * STAGE_BYTES);
+            for (int i = ptid; i < pieces; i += PROD_WARPS * 32) {
+              const int cr = i / ppr, xw = i - cr * ppr;     // cr = c * P + p1
+              const int c = cr / p.P, p1 = cr - c * p.P;
+              const uint8_t* g = base + ((size_t)c * p.HW + p1) * p.HW + 4 * xw;
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * i), "l"(g) : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");   // always one group per call: the wait counts groups
+        };
+        auto advance = [&](int r) {                         // first patch row index of the NEXT patch row
+          int b, prow, pc0, n_here;
+          prow_of(r, b, prow, pc0, n_here);
+          return r + n_here;
+        };
+        int r0 = row_lo, r1 = row_lo < row_hi ? advance(row_lo) : row_hi, r2 = r1 < row_hi ? advance(r1) : row_hi;
+        int slot = 0;
+        prefetch(r0, 0);
+        prefetch(r1, 1);
+        while (r0 < row_hi) {
+          prefetch(r2, (slot + 2) % NSTAGE);                // two patch rows ahead; its buffer was consumed two barriers ago
+          asm volatile("cp.async.wait_group 2;" ::: "memory");
+          prod_bar();                                       // every producer thread's pieces of patch row r0 have landed
+          int b, prow, pc0, n_here;
+          prow_of(r0, b, prow, pc0, n_here);
+          const uint8_t* st8 = smem + Smem::OFF_STAGE + slot * STAGE_BYTES;
+          for (int q = pw; q < n_here; q += PROD_WARPS) {
+            const uint8_t* tp = st8 + (pc0 + q) * p.P;
+            float v[3][2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) v[i][e] = goff[i][e] >= 0 ? s_lut[tp[soff[i][e]]] : 0.f;
+            finish_patch(r0 + q, v);
+          }
+          r0 = r1; r1 = r2; r2 = r2 < row_hi ? advance(r2) : row_hi;
+          slot = (slot + 1) % NSTAGE;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      } else {
+        for (int row = row_lo + pw; row < row_hi; row += 4 * PROD_WARPS) {     // four patches per warp in flight
+          float va[3][2], vb[3][2], vc[3][2], vd[3][2];
+          const bool hb = row + PROD_WARPS < row_hi, hc = row + 2 * PROD_WARPS < row_hi, hd = row + 3 * PROD_WARPS < row_hi;
+          load_patch(row, va);
+          if (hb) load_patch(row + PROD_WARPS, vb);
+          if (hc) load_patch(row + 2 * PROD_WARPS, vc);
+          if (hd) load_patch(row + 3 * PROD_WARPS, vd);
+          finish_patch(row, va);
+          if (hb) finish_patch(row + PROD_WARPS, vb);
+          if (hc) finish_patch(row + 2 * PROD_WARPS, vc);
+          if (hd) finish_patch(row + 3 * PROD_WARPS, vd);
+        }
       }
       // rows past the end of the last tile keep whatever the buffer held: finite, never stored
       tc::fence_proxy_async();                             // generic-proxy writes of A -> visible to the tensor core
@@ -242,7 +310,16 @@ __global__ void __launch_bounds__(THREADS, 1) embed_fused_kernel(const __grid_co
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * D);
       const int row0 = tile * TILE_M + q * 32;             // first patch row of this warp
       const int my_row = row0 + lane;
-      // ---- pass 1: v = acc + bias; row statistics (this thread owns the whole row); e0 stored through the transpose tile
+      // rows this lane stores in the transposed layout: rl = 4 i8 + rsub -> destination rows and positional row, once per tile
+      int dstB[8], posr[8];
+#pragma unroll
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const int grow = row0 + i8 * 4 + rsub;
+        const int b = grow / p.np, j = grow - b * p.np;
+        posr[i8] = grow < p.rows ? 1 + j : -1;
+        dstB[i8] = (p.mode == 0 ? p.B * p.np : 0) + b * S1 + 1 + j;
+      }
+      // ---- pass 1: row statistics of v = acc + bias (this thread owns the whole row: no cross-thread reduction)
       float sum = 0.f, sq = 0.f;
 #pragma unroll 1
       for (int c = 0; c < D / 32; ++c) {
@@ -250,60 +327,57 @@ __global__ void __launch_bounds__(THREADS, 1) embed_fused_kernel(const __grid_co
         tc::tmem_ld_32x32(taddr + c * 32, rr);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(rr[j]) + s_bias[c * 32 + j];
-          sum += v;
-          sq = fmaf(v, v, sq);
-          rr[j] = __float_as_uint(v);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + c * 32 + j4 * 4);       // broadcast read
+          const float v0 = __uint_as_float(rr[4 * j4]) + bb.x, v1 = __uint_as_float(rr[4 * j4 + 1]) + bb.y;
+          const float v2 = __uint_as_float(rr[4 * j4 + 2]) + bb.z, v3 = __uint_as_float(rr[4 * j4 + 3]) + bb.w;
+          sum += (v0 + v1) + (v2 + v3);
+          sq += fmaf(v0, v0, v1 * v1) + fmaf(v2, v2, v3 * v3);
         }
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4)
-          *reinterpret_cast<uint4*>(tile_s + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = make_uint4(rr[4 * c4], rr[4 * c4 + 1], rr[4 * c4 + 2], rr[4 * c4 + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i8 = 0; i8 < 8; ++i8) {
-          const int rl = i8 * 4 + rsub, grow = row0 + rl;
-          if (grow < p.rows) {
-            const float4 t = *reinterpret_cast<const float4*>(tile_s + rl * 32 + ((cchunk ^ (rl & 7)) << 2));
-            *reinterpret_cast<float4*>(p.e0 + (size_t)grow * D + c * 32 + cchunk * 4) = t;
-          }
-        }
-        __syncwarp();
       }
       const float mean = sum * (1.0f / D);
       const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + p.eps3);
       if (my_row < p.rows) { p.m3[my_row] = mean; p.r3[my_row] = rstd; }
-      // ---- pass 2: y = (v - mean) rstd g3 + b3 -> explorative row as is, exploitative / CLS row + pos_embedding[1 + j]
-      const float a = rstd, bsh = -mean * rstd;
+      // statistics of the rows this lane handles after the transpose (row rl = 4 i8 + rsub lives in lane rl of this warp)
+      float ra[8], rb[8];
+#pragma unroll
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const float m_ = __shfl_sync(0xffffffffu, mean, i8 * 4 + rsub), r_ = __shfl_sync(0xffffffffu, rstd, i8 * 4 + rsub);
+        ra[i8] = r_;
+        rb[i8] = -m_ * r_;
+      }
+      // ---- pass 2: the raw accumulator goes through the transpose tile once; in the row-contiguous layout a lane adds the bias,
+      // stores e0 (the LayerNorm input, kept for the backward), normalises, and stores the token into the explorative row as is
+      // and + pos_embedding[1 + j] into the exploitative / CLS row
 #pragma unroll 1
       for (int c = 0; c < D / 32; ++c) {
+        const int col = c * 32 + cchunk * 4;
+        const float4 bb = *reinterpret_cast<const float4*>(s_bias + col);
+        const float4 gg = *reinterpret_cast<const float4*>(s_g3 + col);
+        const float4 be = *reinterpret_cast<const float4*>(s_b3 + col);
+        float4 pe[8];                                       // positional rows of this chunk: in flight under the TMEM load
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8)
+          if (posr[i8] >= 0) pe[i8] = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)posr[i8] * D + col));
         uint32_t rr[32];
         tc::tmem_ld_32x32(taddr + c * 32, rr);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(rr[j]) + s_bias[c * 32 + j];
-          rr[j] = __float_as_uint(fmaf(fmaf(v, a, bsh), s_g3[c * 32 + j], s_b3[c * 32 + j]));
-        }
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4)
-          *reinterpret_cast<uint4*>(tile_s + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = make_uint4(rr[4 * c4], rr[4 * c4 + 1], rr[4 * c4 + 2], rr[4 * c4 + 3]);
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<uint4*>(tile_s + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = make_uint4(rr[4 * j4], rr[4 * j4 + 1], rr[4 * j4 + 2], rr[4 * j4 + 3]);
         __syncwarp();
 #pragma unroll
         for (int i8 = 0; i8 < 8; ++i8) {
-          const int rl = i8 * 4 + rsub, grow = row0 + rl;
-          if (grow < p.rows) {
-            const int b = grow / p.np, j = grow - b * p.np;
-            const float4 t = *reinterpret_cast<const float4*>(tile_s + rl * 32 + ((cchunk ^ (rl & 7)) << 2));
-            const int col = c * 32 + cchunk * 4;
-            const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(1 + j) * D + col));
-            const float4 tp = make_float4(t.x + pe.x, t.y + pe.y, t.z + pe.z, t.w + pe.w);
-            if (p.mode == 0) {
-              *reinterpret_cast<float4*>(p.x0 + (size_t)grow * D + col) = t;                                       // no pos-emb (bug kept)
-              *reinterpret_cast<float4*>(p.x0 + ((size_t)p.B * p.np + (size_t)b * S1 + 1 + j) * D + col) = tp;
-            } else {
-              *reinterpret_cast<float4*>(p.x0 + ((size_t)b * S1 + 1 + j) * D + col) = tp;
-            }
+          const int rl = i8 * 4 + rsub;
+          if (posr[i8] >= 0) {
+            float4 v = *reinterpret_cast<const float4*>(tile_s + rl * 32 + ((cchunk ^ (rl & 7)) << 2));
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            *reinterpret_cast<float4*>(p.e0 + (size_t)(row0 + rl) * D + col) = v;
+            const float4 t = make_float4(fmaf(fmaf(v.x, ra[i8], rb[i8]), gg.x, be.x), fmaf(fmaf(v.y, ra[i8], rb[i8]), gg.y, be.y),
+                                         fmaf(fmaf(v.z, ra[i8], rb[i8]), gg.z, be.z), fmaf(fmaf(v.w, ra[i8], rb[i8]), gg.w, be.w));
+            if (p.mode == 0) *reinterpret_cast<float4*>(p.x0 + (size_t)(row0 + rl) * D + col) = t;          // no pos-emb (bug kept)
+            *reinterpret_cast<float4*>(p.x0 + (size_t)dstB[i8] * D + col) =
+                make_float4(t.x + pe[i8].x, t.y + pe[i8].y, t.z + pe[i8].z, t.w + pe[i8].w);
           }
         }
         __syncwarp();
@@ -335,7 +409,8 @@ extern "C" int eavit_embed_fused_fwd(const void* img, int img_dtype, const long 
   EAVIT_CHECK_ARG(B > 0 && C > 0 && P > 0 && HW % P == 0 && (mode == 0 || mode == 1));
   EAVIT_CHECK_ARG(img_dtype == EAVIT_U8 || img_dtype == EAVIT_F32);
   const int PD = C * P * P, npr = HW / P, np = npr * npr;
-  EAVIT_CHECK_ARG(PD % 16 == 0 && PD <= ef::KPAD && C * P * HW <= ef::MAX_STAGE_FLOATS);
+  EAVIT_CHECK_ARG(PD % 16 == 0 && PD <= ef::KPAD && HW % 4 == 0 && C * P * HW <= ef::STAGE_BYTES);
+  EAVIT_CHECK_ARG((long long)B * (np + 1) * 2 < (1LL << 31));
   EAVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(w_bf16) & 15) == 0 && (PD * 2) % 16 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmW;
