@@ -172,8 +172,13 @@ def test_loss_and_gradients_vs_oracle(which):
     # Measured (profiles/r2_parity_measured.txt): totals 3.5e-3 / 2.2e-3 / 2.8e-3; worst tensor above 2 % of the norm:
     # extra_layer.0.weight 1.9e-2 / 1.0e-2 / 1.8e-2, every other one <= 1.2e-2; worst small tensor: the HF query bias of
     # layer 0, 2.2e-2 on 0.03 % of the gradient norm.
+    # The two layers right behind the features (a ReLU fed by bf16-accurate inputs) keep the round-1 bound of 5x: which
+    # units flip depends on the last bit of the features, so their error moves between 1e-2 and 2.6e-2 from one kernel
+    # revision to the next (1.9e-2 with the four-launch embedding, 2.6e-2 with the fused one) without any change upstream.
     tn = float(np.linalg.norm(ref_all))
-    bad = {k: v for k, v in worst.items() if v > 2.5 * TOL and float(P[k].grad.norm()) > 0.02 * tn}
+    relu_fed = ("model.extra_layer.0.", "model.actor.0.")
+    bad = {k: v for k, v in worst.items()
+           if v > (5 if k.startswith(relu_fed) else 2.5) * TOL and float(P[k].grad.norm()) > 0.02 * tn}
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
 
 
