@@ -405,8 +405,8 @@ class RNDAgent(nn.Module):
     # two small copies and one graph launch, and the kernels run back to back without launch gaps.  Dropout: the captured
     # seeds are constants, so the graph starts by bumping the device epoch word that every mask folds in (fresh masks per
     # replay, the same word for the forward and the backward of one replay).  EAVIT_STEP_GRAPH=0 keeps eager launches;
-    # ``apply=False`` (gradient inspection), an active kernel profile and data-parallel runs (the NCCL exchange stays
-    # outside graphs unless EAVIT_STEP_GRAPH_DIST=1) run eagerly as well.
+    # ``apply=False`` (gradient inspection), an active kernel profile and data-parallel runs run eagerly as well: capturing
+    # the NCCL exchange (EAVIT_STEP_GRAPH_DIST=1) hung at 2 ranks with the NCCL 2.28 of this image, so it stays opt-in.
     def train_step(self, R: dict, idx: torch.Tensor, mask: torch.Tensor, stats_out: Optional[torch.Tensor] = None,
                    apply: bool = True):
         """One minibatch: agents.py:284-508 from the batch gather to ``optimizer.step()``."""
