@@ -83,7 +83,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   // TMEM columns: S^T | dP^T | dV | dK | dQ (tile 0); Dh = 32 keeps dQ of query tile 1 in the last 32 columns of S^T
   constexpr int COL_S = 0, COL_DP = DH == 32 ? 208 : 128, COL_DV = DH == 32 ? 416 : 256, COL_DK = COL_DV + DH, COL_DQ0 = COL_DK + DH;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST
   float* sL = reinterpret_cast<float*>(smem + Smem::OFF_L);
   float* sD = reinterpret_cast<float*>(smem + Smem::OFF_D);
   uint32_t* sRK = reinterpret_cast<uint32_t*>(smem + Smem::OFF_RK);

@@ -68,7 +68,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __
                         int pack, int seg) {
   constexpr int HPB = 64 / DH;                      // heads per 128-byte box row
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST
   float* sMax = reinterpret_cast<float*>(smem + AttSmem::OFF_X);      // [2][256]
   float* sSum = sMax + 512;                                            // [2][256]
   uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + AttSmem::OFF_BAR);
@@ -386,7 +386,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                         __nv_bfloat16* __restrict__ dqkv, const DropCfg drop, int pack, int seg) {
   constexpr int HPB = 64 / DH;                      // heads per 128-byte box row
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST
   float* sD = reinterpret_cast<float*>(smem + AttBwdSmem::OFF_D);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttBwdSmem::OFF_BAR);   // [0] S,dP  [1] dV  [2] dK,dQ  [3] loads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);

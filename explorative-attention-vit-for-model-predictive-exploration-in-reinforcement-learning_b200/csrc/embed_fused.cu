@@ -75,7 +75,7 @@ __device__ __forceinline__ float pix(const ImgT* p) {
 template <typename ImgT>
 __global__ void __launch_bounds__(THREADS, 1) embed_fused_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST
   float* s_bias = reinterpret_cast<float*>(smem + Smem::OFF_VEC);
   float* s_g3 = s_bias + D;
   float* s_b3 = s_g3 + D;

@@ -75,18 +75,29 @@ struct GemmCfg {
 };
 
 // shared memory of one CTA: TMA stages | EW transpose tiles | barrier block | EW x CS_SLOTS x 32 private column sums
-template <int BN, int EW>
+template <int BN, int EW, bool LEAN = false, bool WS = false>
 struct GemmSmem {
+  // WS (weight-stationary, K <= 4 k-blocks, every CTA keeps one column block): the B operand of all k-blocks is loaded once
+  // into a resident region in front of an A-only ring -- the K = 256 GEMMs otherwise re-read 128 KB of weights from L2 for
+  // every 128 x 256 output tile (604 MB of L2 -> SM traffic per QKV launch next to 103 MB of activations).
+  static constexpr int WS_KB = 4;
+  static constexpr int B_RES_BYTES = WS ? WS_KB * GemmCfg<BN>::B_STAGE_BYTES : 0;
+  static constexpr int RING_STAGE_BYTES = WS ? A_STAGE_BYTES : GemmCfg<BN>::STAGE_BYTES;
+  // LEAN (TMA-store epilogues): no column-sum slots, no LayerNorm exchange; with 8 epilogue warps the 32 KB of staging
+  // leave room for a fourth operand stage at BN = 256
+  static constexpr int STAGES = WS ? (EW <= 8 ? 4 : 2) : GemmCfg<BN>::STAGES + ((LEAN && BN == 256 && EW <= 8) ? 1 : 0);
   static constexpr int EPI_BYTES = EW * EPI_TILE_FLOATS * 4;
   static constexpr int CS_SLOTS = (BN / 32 + EW / 4 - 1) / (EW / 4);            // 32-column chunks one warp handles per tile
-  static constexpr int CS_BYTES = EW * CS_SLOTS * 32 * 4;
-  static constexpr int OFF_EPI = GemmCfg<BN>::STAGES * GemmCfg<BN>::STAGE_BYTES;
+  static constexpr int CS_BYTES = LEAN ? 0 : EW * CS_SLOTS * 32 * 4;
+  static constexpr int OFF_RING = B_RES_BYTES;
+  static constexpr int OFF_EPI = OFF_RING + STAGES * RING_STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
   static constexpr int OFF_CS = OFF_BAR + 256;
   static constexpr int OFF_LNX = OFF_CS + CS_BYTES;                            // float2 [2 buffers][warps per quadrant][128 rows] row partial sums
-  static constexpr int LNX_BYTES = 2 * (EW / 4) * 128 * 8;
+  static constexpr int LNX_BYTES = LEAN ? 0 : 2 * (EW / 4) * 128 * 8;
   static constexpr int TOTAL = OFF_LNX + LNX_BYTES + 1024 /*align slack*/;
   static_assert(TOTAL <= SMEM_LIMIT, "over the 227 KB shared-memory limit of a CTA");
+  static_assert(2 * STAGES + 5 <= 32, "barrier block");
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float a) {
@@ -104,7 +115,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
 
 // Epilogue specialisations (compile-time): the epilogue is instruction-issue bound (ncu: 45 % issue-active from only 8
 // warps), so the common fused forms drop every per-element runtime branch of the generic path.
-enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5, E_GELU_FWD_D = 6, E_MUL_AUX = 7, E_RESID_LN = 8 };
+enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5, E_GELU_FWD_D = 6, E_MUL_AUX = 7, E_RESID_LN = 8, E_STORE_TMA = 9 };
 // E_RESID_LN (north_star clause 3: LayerNorm fused into the GEMM epilogue): x' = x + dropout(A W^T + b) as E_RESID, and --
 // because N == BN == 256 == the model width, so the two warps of a lane quadrant hold whole rows between them -- the
 // LayerNorm that consumes x' (vit.py:28 / :47 PreNorm) in the same epilogue: pass 1 stores x' and reduces sum / sum of squares
@@ -120,19 +131,19 @@ enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, 
 template <int EPI> struct EpiWarps {
   // measured at [201216, 1024] x K = 256 (r2): multiply-by-aux 250 us with 12 warps, 229 us with 16; residual (+ LayerNorm) epilogues
   // are best with 8 (142 / 183 us vs 145 / 232 us with 16: their prefetched fp32 rows need the registers)
-  static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_STORE || EPI == E_MUL_AUX) ? 16 : (EPI == E_GELU_BWD ? 12 : 8);
+  static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_STORE || EPI == E_STORE_TMA || EPI == E_MUL_AUX) ? 16 : (EPI == E_GELU_BWD ? 12 : 8);
 };
 
-template <int BN, int EPI, bool DROP, int EW = EpiWarps<EPI>::N>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
+template <int BN, int EPI, bool DROP, int EW = EpiWarps<EPI>::N, bool WS = false>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
 __global__ void __launch_bounds__((CTRL_WARPS + EW) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmKernelParams p) {
+                         const __grid_constant__ CUtensorMap tmC, const GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
   constexpr int EPI_WARPS = EW;
+  using Sm = GemmSmem<BN, EPI_WARPS, EPI == E_STORE_TMA, WS>;
+  constexpr int STAGES = Sm::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  using Sm = GemmSmem<BN, EPI_WARPS>;
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST
   float* epi_smem = reinterpret_cast<float*>(smem + Sm::OFF_EPI);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Sm::OFF_BAR);
   uint64_t* full_bar = bars;                      // [STAGES]   TMA -> MMA
@@ -140,6 +151,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* acc_full = bars + 2 * STAGES;         // [2]        MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2;    // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* b_full = bars + 2 * STAGES + 5;       // WS: resident B operand landed
   float* s_cs = reinterpret_cast<float*>(smem + Sm::OFF_CS);                     // behind the barrier block
   if (p.cs_smem)
     for (int i = threadIdx.x; i < Sm::CS_BYTES / 4; i += blockDim.x) s_cs[i] = 0.f;
@@ -150,10 +162,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
+    if constexpr (EPI == E_STORE_TMA) tc::prefetch_tmap(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], EPI_WARPS); }
+    tc::mbar_init(b_full, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -171,14 +185,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      auto load_b = [&](uint8_t* sb, uint64_t* bar, int kb, int n_blk) {
+        if (!p.b_mn) {
+          tc::tma_load_2d(sb, &tmB, bar, kb * BK, n_blk * BN);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i)
+            tc::tma_load_2d(sb + i * 8192, &tmB, bar, n_blk * BN + i * 64, kb * BK);
+        }
+      };
+      if constexpr (WS) {                        // gridDim.x % n_tiles == 0: this CTA's column block never changes
+        tc::mbar_expect_tx(b_full, (uint32_t)(p.kb_total * Cfg::B_STAGE_BYTES));
+        for (int kb = 0; kb < p.kb_total; ++kb) load_b(smem + kb * Cfg::B_STAGE_BYTES, b_full, kb, (int)(blockIdx.x % p.n_tiles));
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles, split = tile / (p.n_tiles * p.m_tiles);
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sa = smem + Sm::OFF_RING + stage * Sm::RING_STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          tc::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tc::mbar_expect_tx(&full_bar[stage], Sm::RING_STAGE_BYTES);
           if (!p.a_mn) {
             tc::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
           } else {
@@ -186,13 +213,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int i = 0; i < BM / 64; ++i)
               tc::tma_load_2d(sa + i * 8192, &tmA, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
           }
-          if (!p.b_mn) {
-            tc::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-          } else {
-#pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tc::tma_load_2d(sb + i * 8192, &tmB, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
-          }
+          if constexpr (!WS) load_b(sb, &full_bar[stage], kb, n_blk);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -203,6 +224,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t idesc = tc::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      if constexpr (WS) { tc::mbar_wait(b_full, 0); tc::fence_after_sync(); }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int split = tile / (p.n_tiles * p.m_tiles);
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -212,8 +234,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::fence_after_sync();
-          const uint32_t sa = tc::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t sa = tc::smem_u32(smem + Sm::OFF_RING + stage * Sm::RING_STAGE_BYTES);
+          const uint32_t sb = WS ? tc::smem_u32(smem + kb * Cfg::B_STAGE_BYTES) : sa + A_STAGE_BYTES;
           // K-major:  rows of 128 B, 8-row groups 1024 B apart (SBO); K advance = 32 B inside the swizzle atom.
           // MN-major: 64-element (128 B) MN chunks, 8 k-rows per 1024 B (SBO), MN blocks 8192 B apart (LBO);
           //           K advance = 16 k-rows = 2048 B.
@@ -233,6 +255,58 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if constexpr (EPI == E_STORE_TMA) {
+    // ===================================== epilogue: bf16 store through TMA =====================================
+    // The accumulator is converted in its native layout (lane = row, registers = columns) and written as a 128B-swizzled
+    // [32 rows x 64 columns] bf16 box into this warp's 4 KB staging buffer; one lane hands the box to the TMA unit
+    // (cp.async.bulk.tensor store: address generation, full-line writes and the M / N tail clipping are the hardware's).
+    // ~40 instructions per 32 x 64 box instead of ~640 on the transpose path (per-row address arithmetic, LDS, STG).
+    static_assert(BN % 64 == 0 && EPI_TILE_FLOATS * 4 == 32 * 128, "one 32 x 64 bf16 box per staging buffer");
+    const int e = warp - CTRL_WARPS;
+    const int q = warp & 3;                           // TMEM lane quadrant
+    const int par = e >> 2;
+    constexpr int WQ = EPI_WARPS / 4;
+    uint8_t* stg = reinterpret_cast<uint8_t*>(epi_smem) + e * (EPI_TILE_FLOATS * 4);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
+      const int n_blk = tile_i % p.n_tiles, m_blk = (tile_i / p.n_tiles) % p.m_tiles;
+      tc::mbar_wait(&acc_full[acc], acc_phase);
+      tc::fence_after_sync();
+      const int row0 = m_blk * BM + q * 32;
+#pragma unroll 1
+      for (int g = par; g < BN / 64; g += WQ) {
+        const int col0 = n_blk * BN + g * 64;
+        if (col0 >= p.N) break;                        // warp-uniform
+        if (lane == 0) tc::tma_store_wait_read<0>();   // the previous box has left the staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + g * 64 + hh * 32), r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r[8 * c4 + 0]), __uint_as_float(r[8 * c4 + 1]));
+            v.y = pack_bf16x2(__uint_as_float(r[8 * c4 + 2]), __uint_as_float(r[8 * c4 + 3]));
+            v.z = pack_bf16x2(__uint_as_float(r[8 * c4 + 4]), __uint_as_float(r[8 * c4 + 5]));
+            v.w = pack_bf16x2(__uint_as_float(r[8 * c4 + 6]), __uint_as_float(r[8 * c4 + 7]));
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + c4) ^ (lane & 7)) << 4)) = v;
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row0 < p.M) {
+          tc::tma_store_2d(&tmC, stg, col0, row0);
+          tc::tma_store_commit();
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tc::tma_store_wait_all<0>();
   } else {
     // ===================================== epilogue =====================================
     // Four warps per TMEM lane quadrant (they interleave 32-column chunks).  Each chunk is transposed through a padded
@@ -270,9 +344,36 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     float2* lnx = reinterpret_cast<float2*>(smem + Sm::OFF_LNX);
     int ln_buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    // Global operands of the epilogue (residual / aux) do not depend on the accumulator: the loads of a 32 x 32 chunk are
+    // issued one chunk AHEAD -- into a second register set where the budget allows (PF2), and for every variant the first
+    // chunk of a tile before the wait on its accumulator -- so an HBM round trip is hidden behind the previous chunk's
+    // TMEM read / transpose / stores instead of sitting at the head of every chunk.
+    constexpr bool PF2 = false;   // measured: the second register set spills at 96 registers (MUL_AUX 233 -> 299 us) and costs RESID 145 -> 153 us
+    constexpr int WQ = EPI_WARPS / 4;                                              // warps per lane quadrant
+    float4 res[8], resN[PF2 ? 8 : 1];
+    uint2 ax[8], axN[PF2 ? 8 : 1];
+    auto issue = [&](int t, int c, float4* R, uint2* A) {
+      if (t >= total_tiles || c >= BN / 32) return;
+      const int nb = t % p.n_tiles, mb = (t / p.n_tiles) % p.m_tiles;
+      const int colL = nb * BN + c * 32 + (lane & 7) * 4;
+      if (colL >= p.N) return;
+      const int r0 = mb * BM + q * 32, nr = p.M - r0, rs = lane >> 3;
+      const size_t o0 = (size_t)(r0 + rs) * (size_t)p.ldc + colL, os = 4 * (size_t)p.ldc;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (nr >= 32 || it * 4 + rs < nr) {
+          if (has_res) R[it] = __ldg(reinterpret_cast<const float4*>(p.residual + o0 + it * os));
+          if (need_aux) A[it] = __ldg(reinterpret_cast<const uint2*>(p.aux + o0 + it * os));
+        }
+      }
+    };
+    const bool ep_loads = has_res || need_aux;
+    bool primed = false;                                  // res / ax already hold the first chunk of the upcoming tile
     for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
       const int n_blk = tile_i % p.n_tiles, m_blk = (tile_i / p.n_tiles) % p.m_tiles;
       if (p.cs_smem && n_blk != cs_nblk) { cs_flush(); cs_nblk = n_blk; }
+      if (ep_loads && !primed) issue(tile_i, par, res, ax);
+      primed = false;
       float ls1[8], ls2[8];                               // E_RESID_LN: partial row sums of rows rsub + 4 it over this warp's columns
 #pragma unroll
       for (int it = 0; it < 8; ++it) { ls1[it] = 0.f; ls2[it] = 0.f; }
@@ -289,29 +390,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         constexpr bool CS = GEN || EPI == E_GELU_BWD || EPI == E_MUL_AUX;    // epilogues that can carry a fused column sum
         const size_t off0 = (size_t)(row0 + rsub) * (size_t)p.ldc + col;      // row rr = rsub + 4 * it
         const size_t ostep = 4 * (size_t)p.ldc;
-        // Issue every global read of this chunk FIRST (8 independent 16-byte loads per lane: the epilogue is latency-
-        // bound on HBM unless ~40 KB per SM are in flight) -- before the TMEM load and the __syncwarp of the transpose,
-        // which also stops the scheduler from sinking them between the stores further down.
-        float4 res[8];
-        uint2 ax[8];
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto load = [&](int it) {
-          if (has_res) res[it] = __ldg(reinterpret_cast<const float4*>(p.residual + off0 + it * ostep));
-          if (need_aux) ax[it] = __ldg(reinterpret_cast<const uint2*>(p.aux + off0 + it * ostep));
-        };
-        if (col < p.N) {
-          if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          if (has_res || need_aux) {
-            if (nrows >= 32) {
-#pragma unroll
-              for (int it = 0; it < 8; ++it) load(it);
-            } else {
-#pragma unroll
-              for (int it = 0; it < 8; ++it)
-                if (it * 4 + rsub < nrows) load(it);
-            }
-          }
+        const int cn = c + WQ;
+        const bool more = cn < BN / 32 && n_blk * BN + cn * 32 < p.N;        // this warp has another chunk in this tile
+        if constexpr (PF2) {
+          if (ep_loads) { if (more) issue(tile_i, cn, resN, axN); else issue(tile_i + (int)gridDim.x, par, resN, axN); }
         }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < p.N && has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         // registers (one row per lane) -> swizzled smem tile -> (4 rows x 8 lanes x 16 B) per instruction; two 16-column
         // halves so that only 16 accumulator registers are live next to the prefetched residual / aux values
 #pragma unroll
@@ -395,6 +480,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               if (it * 4 + rsub < nrows) body(it);
           }
         }
+        if (ep_loads) {
+          if constexpr (PF2) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) { res[it] = resN[it]; ax[it] = axN[it]; }
+            if (!more) primed = true;
+          } else {
+            if (more) issue(tile_i, cn, res, ax);
+          }
+        }
         if (p.colsum != nullptr) {                         // warp-uniform
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -425,7 +519,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             ls2[it] += __shfl_xor_sync(0xffffffffu, ls2[it], o);
           }
         }
-        constexpr int WQ = EPI_WARPS / 4;                                   // warps per lane quadrant
         float2* mine = lnx + (ln_buf * WQ + par) * 128 + q * 32;
         if (cchunk == 0) {
 #pragma unroll
@@ -534,13 +627,13 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return EAVIT_OK;
 }
 
-template <int BN, int EPI, bool DROP = false, int EW = EpiWarps<EPI>::N>
+template <int BN, int EPI, bool DROP = false, int EW = EpiWarps<EPI>::N, bool WS = false>
 static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<BN, EW>::TOTAL));
+    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    GemmSmem<BN, EW, EPI == E_STORE_TMA, WS>::TOTAL));
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
@@ -551,6 +644,11 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   if (!a->b_mn) rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, BN);
   else          rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64);
   if (rc) return rc;
+  CUtensorMap tmC = tmA;                     // only the TMA-store epilogue reads it
+  if (EPI == E_STORE_TMA) {
+    rc = make_tmap_bf16_2d(&tmC, a->out_bf16, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc * 2, 32);
+    if (rc) return rc;
+  }
 
   GemmKernelParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -576,18 +674,19 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   p.cs_smem = a->colsum != nullptr ? 1 : 0;
   p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_mean = a->ln_mean; p.ln_rstd = a->ln_rstd; p.ln_eps = a->ln_eps;
   const int total = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total < kNumSMs ? total : kNumSMs;
+  int grid = total < kNumSMs ? total : kNumSMs;
+  if (WS) grid = grid / p.n_tiles * p.n_tiles;           // a CTA keeps its column block: tile % n_tiles == blockIdx.x % n_tiles
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3((CTRL_WARPS + EW) * 32);
-  cfg.dynamicSmemBytes = GemmSmem<BN, EW>::TOTAL;
+  cfg.dynamicSmemBytes = GemmSmem<BN, EW, EPI == E_STORE_TMA, WS>::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW>, tmA, tmB, p));
+  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS>, tmA, tmB, tmC, p));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -638,6 +737,13 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
       return drop ? launch_gemm<256, E_RESID_LN, true>(a, st) : launch_gemm<256, E_RESID_LN>(a, st);
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)
       return drop ? launch_gemm<256, E_RESID, true>(a, st) : launch_gemm<256, E_RESID>(a, st);
+    if (none && plain && !drop && !a->bias && a->out_bf16 && !a->out_f32 && !a->colsum && (a->ldc * 2) % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && !getenv("EAVIT_NO_TMA_STORE"))
+    {
+      const int kbt = cdiv(a->K, BK), nt = cdiv(a->N, 256), tiles = cdiv(a->M, BM) * nt;
+      if (kbt <= 4 && tiles >= kNumSMs && nt <= kNumSMs && !getenv("EAVIT_NO_WS")) return launch_gemm<256, E_STORE_TMA, false, 8, true>(a, st);
+      return launch_gemm<256, E_STORE_TMA, false, 8>(a, st);
+    }
     if (none && plain && !drop) return launch_gemm<256, E_STORE>(a, st);
     return drop ? launch_gemm<256, E_GENERIC, true>(a, st) : launch_gemm<256, E_GENERIC>(a, st);
   }
