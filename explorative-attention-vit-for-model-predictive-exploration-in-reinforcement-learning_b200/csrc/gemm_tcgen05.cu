@@ -75,7 +75,10 @@ struct GemmCfg {
 };
 
 // shared memory of one CTA: TMA stages | EW transpose tiles | barrier block | EW x CS_SLOTS x 32 private column sums
-template <int BN, int EW, bool LEAN = false, bool WS = false>
+// LEAN epilogues (E_*_TMA) work in the accumulator's native layout and move their global operands / results as
+// 128B-swizzled [32 rows x 64 columns] bf16 boxes through the TMA unit: WBUF bytes of staging per warp, no column-sum
+// slots, no LayerNorm exchange -- the shared memory they free goes to operand stages.
+template <int BN, int EW, bool LEAN = false, bool WS = false, int WBUF = EPI_TILE_FLOATS * 4, int XB = 0>
 struct GemmSmem {
   // WS (weight-stationary, K <= 4 k-blocks, every CTA keeps one column block): the B operand of all k-blocks is loaded once
   // into a resident region in front of an A-only ring -- the K = 256 GEMMs otherwise re-read 128 KB of weights from L2 for
@@ -83,21 +86,22 @@ struct GemmSmem {
   static constexpr int WS_KB = 4;
   static constexpr int B_RES_BYTES = WS ? WS_KB * GemmCfg<BN>::B_STAGE_BYTES : 0;
   static constexpr int RING_STAGE_BYTES = WS ? A_STAGE_BYTES : GemmCfg<BN>::STAGE_BYTES;
-  // LEAN (TMA-store epilogues): no column-sum slots, no LayerNorm exchange; with 8 epilogue warps the 32 KB of staging
-  // leave room for a fourth operand stage at BN = 256
-  static constexpr int STAGES = WS ? (EW <= 8 ? 4 : 2) : GemmCfg<BN>::STAGES + ((LEAN && BN == 256 && EW <= 8) ? 1 : 0);
-  static constexpr int EPI_BYTES = EW * EPI_TILE_FLOATS * 4;
+  static constexpr int BAR_BYTES = 384;
+  static constexpr int EPI_BYTES = EW * WBUF;
   static constexpr int CS_SLOTS = (BN / 32 + EW / 4 - 1) / (EW / 4);            // 32-column chunks one warp handles per tile
-  static constexpr int CS_BYTES = LEAN ? 0 : EW * CS_SLOTS * 32 * 4;
+  static constexpr int CS_BYTES = LEAN ? XB : EW * CS_SLOTS * 32 * 4;   // LEAN: XB bytes of per-warp scratch (bias slices)
+  static constexpr int LNX_BYTES = LEAN ? 0 : 2 * (EW / 4) * 128 * 8;
+  static constexpr int FIT = (SMEM_LIMIT - 1024 - BAR_BYTES - B_RES_BYTES - EPI_BYTES - CS_BYTES - LNX_BYTES) / RING_STAGE_BYTES;
+  static constexpr int STAGES = (LEAN || WS) ? (FIT < 4 ? FIT : 4) : GemmCfg<BN>::STAGES;
   static constexpr int OFF_RING = B_RES_BYTES;
   static constexpr int OFF_EPI = OFF_RING + STAGES * RING_STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
-  static constexpr int OFF_CS = OFF_BAR + 256;
+  static constexpr int OFF_CS = OFF_BAR + BAR_BYTES;
   static constexpr int OFF_LNX = OFF_CS + CS_BYTES;                            // float2 [2 buffers][warps per quadrant][128 rows] row partial sums
-  static constexpr int LNX_BYTES = LEAN ? 0 : 2 * (EW / 4) * 128 * 8;
   static constexpr int TOTAL = OFF_LNX + LNX_BYTES + 1024 /*align slack*/;
+  static_assert(STAGES >= 2, "operand ring too short");
   static_assert(TOTAL <= SMEM_LIMIT, "over the 227 KB shared-memory limit of a CTA");
-  static_assert(2 * STAGES + 5 <= 32, "barrier block");
+  static_assert((2 * STAGES + 6 + 2 * EW) * 8 <= BAR_BYTES, "barrier block");
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float a) {
@@ -115,7 +119,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
 
 // Epilogue specialisations (compile-time): the epilogue is instruction-issue bound (ncu: 45 % issue-active from only 8
 // warps), so the common fused forms drop every per-element runtime branch of the generic path.
-enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5, E_GELU_FWD_D = 6, E_MUL_AUX = 7, E_RESID_LN = 8, E_STORE_TMA = 9 };
+enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5, E_GELU_FWD_D = 6, E_MUL_AUX = 7, E_RESID_LN = 8, E_STORE_TMA = 9, E_MUL_AUX_TMA = 10, E_GELU_FWD_D_TMA = 11 };
 // E_RESID_LN (north_star clause 3: LayerNorm fused into the GEMM epilogue): x' = x + dropout(A W^T + b) as E_RESID, and --
 // because N == BN == 256 == the model width, so the two warps of a lane quadrant hold whole rows between them -- the
 // LayerNorm that consumes x' (vit.py:28 / :47 PreNorm) in the same epilogue: pass 1 stores x' and reduces sum / sum of squares
@@ -128,19 +132,25 @@ enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, 
 // stream of each warp (r2 experiment, [201216,1024] x K=256: GELU' 325 us, multiply-only 252 us, store-only 186 us).
 // The GELU epilogues are issue/latency-bound (16 instructions + 2 MUFU per element): 16 warps.  The store / residual /
 // atomic epilogues are HBM-bound and want registers for loads in flight instead: 8 warps.
+template <int EPI> struct EpiTraits {
+  static constexpr bool LEAN = (EPI == E_STORE_TMA || EPI == E_MUL_AUX_TMA || EPI == E_GELU_FWD_D_TMA);
+  static constexpr int XB = (EPI == E_GELU_FWD_D_TMA) ? 16 * 256 : 0;                  // 64 bias values per epilogue warp
+  static constexpr int WBUF = (EPI == E_MUL_AUX_TMA) ? 2 * EPI_TILE_FLOATS * 4 : EPI_TILE_FLOATS * 4;   // aux box double-buffered
+};
 template <int EPI> struct EpiWarps {
   // measured at [201216, 1024] x K = 256 (r2): multiply-by-aux 250 us with 12 warps, 229 us with 16; residual (+ LayerNorm) epilogues
   // are best with 8 (142 / 183 us vs 145 / 232 us with 16: their prefetched fp32 rows need the registers)
-  static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_STORE || EPI == E_STORE_TMA || EPI == E_MUL_AUX) ? 16 : (EPI == E_GELU_BWD ? 12 : 8);
+  static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_STORE || EPI == E_MUL_AUX || EPI == E_GELU_FWD_D_TMA) ? 16 : (EPI == E_GELU_BWD ? 12 : 8);
 };
 
 template <int BN, int EPI, bool DROP, int EW = EpiWarps<EPI>::N, bool WS = false>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
 __global__ void __launch_bounds__((CTRL_WARPS + EW) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, const GemmKernelParams p) {
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
+                         const GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int EPI_WARPS = EW;
-  using Sm = GemmSmem<BN, EPI_WARPS, EPI == E_STORE_TMA, WS>;
+  using Sm = GemmSmem<BN, EPI_WARPS, EpiTraits<EPI>::LEAN, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB>;
   constexpr int STAGES = Sm::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST
@@ -152,6 +162,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* acc_empty = bars + 2 * STAGES + 2;    // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint64_t* b_full = bars + 2 * STAGES + 5;       // WS: resident B operand landed
+  uint64_t* aux_full = bars + 2 * STAGES + 6;     // [EW][2]  E_MUL_AUX_TMA: aux box landed in the warp's buffer
   float* s_cs = reinterpret_cast<float*>(smem + Sm::OFF_CS);                     // behind the barrier block
   if (p.cs_smem)
     for (int i = threadIdx.x; i < Sm::CS_BYTES / 4; i += blockDim.x) s_cs[i] = 0.f;
@@ -162,12 +173,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
-    if constexpr (EPI == E_STORE_TMA) tc::prefetch_tmap(&tmC);
+    if constexpr (EpiTraits<EPI>::LEAN) tc::prefetch_tmap(&tmC);
+    if constexpr (EPI == E_MUL_AUX_TMA || EPI == E_GELU_FWD_D_TMA) tc::prefetch_tmap(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], EPI_WARPS); }
     tc::mbar_init(b_full, 1);
+    if constexpr (EPI == E_MUL_AUX_TMA) for (int i = 0; i < 2 * EPI_WARPS; ++i) tc::mbar_init(&aux_full[i], 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -306,6 +319,187 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tc::tma_store_wait_all<0>();
+  } else if constexpr (EPI == E_GELU_FWD_D_TMA) {
+    // ============ epilogue: h = gelu(acc + bias), g = gelu'(acc + bias), two bf16 outputs through TMA stores ============
+    // Native layout: a lane owns a row, the bias of the warp's 64 columns sits in a warp-private shared-memory slice
+    // (broadcast LDS.128).  The two boxes go through the warp's one staging buffer back to back: h is written and handed
+    // to the TMA unit while g waits in 32 packed registers, then g follows as soon as the unit has read h.
+    const int e = warp - CTRL_WARPS;
+    const int q = warp & 3;
+    const int par = e >> 2;
+    constexpr int WQ = EPI_WARPS / 4;
+    uint8_t* stg = reinterpret_cast<uint8_t*>(epi_smem) + e * EpiTraits<EPI>::WBUF;
+    float* my_bias = s_cs + e * 64;
+    int bias_col0 = -1;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
+      const int n_blk = tile_i % p.n_tiles, m_blk = (tile_i / p.n_tiles) % p.m_tiles;
+      const int row0 = m_blk * BM + q * 32;
+      bool waited = false;
+#pragma unroll 1
+      for (int g = par; g < BN / 64; g += WQ) {
+        const int col0 = n_blk * BN + g * 64;
+        if (col0 >= p.N) break;                        // warp-uniform
+        if (col0 != bias_col0) {                       // warp-uniform: a new 64-column slice of the bias
+          __syncwarp();
+          my_bias[lane] = col0 + lane < p.N ? __ldg(p.bias + col0 + lane) : 0.f;
+          my_bias[lane + 32] = col0 + 32 + lane < p.N ? __ldg(p.bias + col0 + 32 + lane) : 0.f;
+          bias_col0 = col0;
+          __syncwarp();
+        }
+        if (!waited) { tc::mbar_wait(&acc_full[acc], acc_phase); tc::fence_after_sync(); waited = true; }
+        uint32_t gp[32];                               // gelu' of the box, packed bf16 pairs
+        if (lane == 0) tc::tma_store_wait_read<0>();   // the previous box (g of the last item) has left the staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + g * 64 + hh * 32), r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 b0 = *reinterpret_cast<const float4*>(my_bias + hh * 32 + c4 * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(my_bias + hh * 32 + c4 * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float hv[8], gv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hv[i] = gelu_erf_and_grad(__uint_as_float(r[8 * c4 + i]) + bb[i], gv[i]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + c4) ^ (lane & 7)) << 4)) =
+                make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]), pack_bf16x2(hv[6], hv[7]));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gp[hh * 16 + c4 * 4 + i] = pack_bf16x2(gv[2 * i], gv[2 * i + 1]);
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (row0 < p.M) { tc::tma_store_2d(&tmC, stg, col0, row0); tc::tma_store_commit(); }
+          tc::tma_store_wait_read<0>();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(gp[4 * j], gp[4 * j + 1], gp[4 * j + 2], gp[4 * j + 3]);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row0 < p.M) { tc::tma_store_2d(&tmD, stg, col0, row0); tc::tma_store_commit(); }
+      }
+      if (!waited) { tc::mbar_wait(&acc_full[acc], acc_phase); tc::fence_after_sync(); }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tc::tma_store_wait_all<0>();
+  } else if constexpr (EPI == E_MUL_AUX_TMA) {
+    // ============ epilogue: out = acc * aux (the stored gelu'), bf16, + column sums; operands through TMA ============
+    // A work item is a [32 rows x 64 columns] box.  The aux box is TMA-loaded into one of the warp's two 4 KB buffers one
+    // item ahead; the product is formed IN PLACE (LDS 16 B of aux, multiply by the accumulator row this lane owns, STS to
+    // the same address) and the buffer is handed back to the TMA unit as the store source.  The bias gradient (column sums
+    // of the stored values) is read back column-wise from the finished box -- lane l owns columns 2l, 2l+1, 32 conflict-
+    // free LDS.32 -- and kept in registers until the CTA leaves its column block.
+    const int e = warp - CTRL_WARPS;
+    const int q = warp & 3;
+    const int par = e >> 2;
+    constexpr int WQ = EPI_WARPS / 4;
+    constexpr int NG = BN / 64;                               // column groups per tile
+    constexpr int GPW = (NG + WQ - 1) / WQ;                   // groups per warp and tile
+    uint8_t* buf0 = reinterpret_cast<uint8_t*>(epi_smem) + e * EpiTraits<EPI>::WBUF;
+    uint64_t* my_bar = aux_full + 2 * e;
+    uint32_t ph[2] = {0u, 0u};
+    float cs[GPW][2];
+#pragma unroll
+    for (int k = 0; k < GPW; ++k) { cs[k][0] = 0.f; cs[k][1] = 0.f; }
+    int cs_nblk = -1;
+    auto cs_flush = [&]() {
+      if (cs_nblk >= 0 && p.colsum != nullptr) {
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) {
+          const int col = cs_nblk * BN + (par + k * WQ) * 64 + 2 * lane;
+          if (par + k * WQ < NG && col < p.N) { atomicAdd(p.colsum + col, cs[k][0]); atomicAdd(p.colsum + col + 1, cs[k][1]); }
+          cs[k][0] = 0.f; cs[k][1] = 0.f;
+        }
+      }
+    };
+    // item iterator: (tile, k) with group g = par + k * WQ; items whose first column is past N do not exist
+    auto item_ok = [&](int t, int k) { return t < total_tiles && k < GPW && par + k * WQ < NG && (t % p.n_tiles) * BN + (par + k * WQ) * 64 < p.N; };
+    auto aux_load = [&](int t, int k, int b) {                // lane 0
+      const int nb = t % p.n_tiles, mb = (t / p.n_tiles) % p.m_tiles;
+      tc::mbar_expect_tx(&my_bar[b], 4096);
+      tc::tma_load_2d(buf0 + b * 4096, &tmD, &my_bar[b], nb * BN + (par + k * WQ) * 64, mb * BM + q * 32);
+    };
+    // prefetch cursor: always the item after the one being processed (tiles in which this warp has no item are skipped)
+    int pt = blockIdx.x, pk = 0;
+    auto settle = [&]() { while (pt < total_tiles && !item_ok(pt, pk)) { pt += (int)gridDim.x; pk = 0; } };
+    settle();
+    int b = 0;
+    if (lane == 0 && pt < total_tiles) aux_load(pt, pk, 0);
+    ++pk; settle();
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
+      const int n_blk = tile_i % p.n_tiles, m_blk = (tile_i / p.n_tiles) % p.m_tiles;
+      if (n_blk != cs_nblk) { cs_flush(); cs_nblk = n_blk; }
+      tc::mbar_wait(&acc_full[acc], acc_phase);
+      tc::fence_after_sync();
+      const int row0 = m_blk * BM + q * 32;
+#pragma unroll
+      for (int k = 0; k < GPW; ++k) {
+        if (!item_ok(tile_i, k)) break;                        // warp-uniform
+        const int g = par + k * WQ;
+        uint8_t* stg = buf0 + b * 4096;
+        if (pt < total_tiles) {
+          if (lane == 0) {
+            tc::tma_store_wait_read<0>();                      // the store that last read the other buffer (item - 1) is done with it
+            aux_load(pt, pk, b ^ 1);
+          }
+          ++pk; settle();
+        }
+        tc::mbar_wait(&my_bar[b], ph[b]);
+        ph[b] ^= 1u;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + g * 64 + hh * 32), r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4* slot = reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + c4) ^ (lane & 7)) << 4));
+            const uint4 a = *slot;
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r[8 * c4 + 0]) * __uint_as_float(a.x << 16), __uint_as_float(r[8 * c4 + 1]) * __uint_as_float(a.x & 0xffff0000u));
+            v.y = pack_bf16x2(__uint_as_float(r[8 * c4 + 2]) * __uint_as_float(a.y << 16), __uint_as_float(r[8 * c4 + 3]) * __uint_as_float(a.y & 0xffff0000u));
+            v.z = pack_bf16x2(__uint_as_float(r[8 * c4 + 4]) * __uint_as_float(a.z << 16), __uint_as_float(r[8 * c4 + 5]) * __uint_as_float(a.z & 0xffff0000u));
+            v.w = pack_bf16x2(__uint_as_float(r[8 * c4 + 6]) * __uint_as_float(a.w << 16), __uint_as_float(r[8 * c4 + 7]) * __uint_as_float(a.w & 0xffff0000u));
+            *slot = v;
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row0 < p.M) {
+          tc::tma_store_2d(&tmC, stg, n_blk * BN + g * 64, row0);
+          tc::tma_store_commit();
+        }
+        if (p.colsum != nullptr) {                             // rows past M were zero-filled by the aux load: they add 0
+          float s0 = 0.f, s1 = 0.f;
+          const int ch = lane >> 2, w4 = (lane & 3) << 2;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4) + w4);
+            s0 += __uint_as_float(u << 16);
+            s1 += __uint_as_float(u & 0xffff0000u);
+          }
+          cs[k][0] += s0; cs[k][1] += s1;
+        }
+        __syncwarp();
+        b ^= 1;
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    cs_flush();
     if (lane == 0) tc::tma_store_wait_all<0>();
   } else {
     // ===================================== epilogue =====================================
@@ -633,7 +827,7 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<BN, EW, EPI == E_STORE_TMA, WS>::TOTAL));
+                                    GemmSmem<BN, EW, EpiTraits<EPI>::LEAN, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB>::TOTAL));
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
@@ -644,8 +838,16 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   if (!a->b_mn) rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, BN);
   else          rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64);
   if (rc) return rc;
-  CUtensorMap tmC = tmA;                     // only the TMA-store epilogue reads it
-  if (EPI == E_STORE_TMA) {
+  CUtensorMap tmC = tmA, tmD = tmA;          // only the TMA epilogues read them
+  if (EPI == E_MUL_AUX_TMA) {
+    rc = make_tmap_bf16_2d(&tmD, a->aux_bf16, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc * 2, 32);
+    if (rc) return rc;
+  }
+  if (EPI == E_GELU_FWD_D_TMA) {
+    rc = make_tmap_bf16_2d(&tmD, a->out_pre_bf16, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc * 2, 32);
+    if (rc) return rc;
+  }
+  if (EpiTraits<EPI>::LEAN) {
     rc = make_tmap_bf16_2d(&tmC, a->out_bf16, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc * 2, 32);
     if (rc) return rc;
   }
@@ -679,14 +881,14 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3((CTRL_WARPS + EW) * 32);
-  cfg.dynamicSmemBytes = GemmSmem<BN, EW, EPI == E_STORE_TMA, WS>::TOTAL;
+  cfg.dynamicSmemBytes = GemmSmem<BN, EW, EpiTraits<EPI>::LEAN, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB>::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS>, tmA, tmB, tmC, p));
+  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS>, tmA, tmB, tmC, tmD, p));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -729,8 +931,19 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
       return drop ? launch_gemm<256, E_GELU_FWD, true>(a, st) : launch_gemm<256, E_GELU_FWD>(a, st);
     if (a->act == EAVIT_ACT_GELU_BWD && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
       return drop ? launch_gemm<256, E_GELU_BWD, true>(a, st) : launch_gemm<256, E_GELU_BWD>(a, st);
+    if (a->act == EAVIT_ACT_GELU_SAVE_GRAD && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32 && !drop &&
+        (a->ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_pre_bf16) & 15) == 0 &&
+        !getenv("EAVIT_NO_TMA_STORE"))
+      return launch_gemm<256, E_GELU_FWD_D_TMA>(a, st);
     if (a->act == EAVIT_ACT_GELU_SAVE_GRAD && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32)
       return drop ? launch_gemm<256, E_GELU_FWD_D, true>(a, st) : launch_gemm<256, E_GELU_FWD_D>(a, st);
+    const bool tma_ok = (a->ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && !getenv("EAVIT_NO_TMA_STORE");
+    if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16 && !drop && tma_ok &&
+        (reinterpret_cast<uintptr_t>(a->aux_bf16) & 15) == 0) {
+      const int kbt = cdiv(a->K, BK), nt = cdiv(a->N, 256), tiles = cdiv(a->M, BM) * nt;
+      if (kbt <= 4 && tiles >= kNumSMs && nt <= kNumSMs && getenv("EAVIT_MULAUX_WS")) return launch_gemm<256, E_MUL_AUX_TMA, false, 8, true>(a, st);
+      return launch_gemm<256, E_MUL_AUX_TMA, false, 8>(a, st);
+    }
     if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
       return drop ? launch_gemm<256, E_MUL_AUX, true>(a, st) : launch_gemm<256, E_MUL_AUX>(a, st);
     if (a->ln_gamma != nullptr)            // checked above: N == 256, bias + residual + fp32 and bf16 outputs, no split-K

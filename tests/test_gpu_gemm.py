@@ -139,6 +139,46 @@ def test_gemm_fused_column_sums(ops, M, N, K):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("M,N,K,b_mn", [(500, 1024, 256, False), (333, 320, 128, False), (40000, 1024, 256, True), (20000, 768, 256, False),
+                                        (19000, 448, 64, True), (4100, 256, 1024, True), (129, 264, 512, False)])
+def test_gemm_tma_epilogues(ops, M, N, K, b_mn):
+    """The epilogues that work in the accumulator's native layout and move boxes through the TMA unit (plain bf16 store with
+    the weight-stationary operand ring for K <= 256; multiply-by-aux + column sums): M / N tails clipped by the tensor map,
+    column blocks in which a warp owns no box, many tiles per CTA, MN-major B, repeated launches accumulating the sums."""
+    torch.manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    Bop = B.t().contiguous() if b_mn else B
+    ref = A.float() @ B.float().t()
+    out16 = torch.full((M + 3, N), 7.0, device="cuda", dtype=torch.bfloat16)        # guard rows behind the M tail
+    ops.gemm(A, Bop, b_mn=b_mn, out_bf16=out16[:M])
+    assert rel_err(out16[:M], ref) < 5e-3
+    assert bool((out16[M:] == 7.0).all())
+    aux = torch.randn(M, N, device="cuda").bfloat16()
+    cs = torch.zeros(N, device="cuda")
+    dh = torch.full((M + 3, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):
+        ops.gemm(A, Bop, b_mn=b_mn, act=ops.ACT_MUL_AUX, aux=aux, out_bf16=dh[:M], colsum=cs)
+    want = ref * aux.float()
+    assert rel_err(dh[:M], want) < 5e-3
+    assert bool((dh[M:] == 7.0).all())
+    assert rel_err(cs, 2 * want.sum(0)) < 3e-3, rel_err(cs, 2 * want.sum(0))
+    ops.gemm(A, Bop, b_mn=b_mn, act=ops.ACT_MUL_AUX, aux=aux, out_bf16=dh[:M])           # without the column sums
+    assert rel_err(dh[:M], want) < 5e-3
+    # bias + GELU, storing gelu'(pre) next to gelu(pre)
+    bias = torch.randn(N, device="cuda")
+    h = torch.full((M + 3, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    g = torch.full((M + 3, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, Bop, b_mn=b_mn, bias=bias, act=ops.ACT_GELU_SAVE_GRAD, out_bf16=h[:M], out_pre=g[:M])
+    pre = (ref + bias).requires_grad_(True)
+    hr = torch.nn.functional.gelu(pre)
+    hr.sum().backward()
+    assert rel_err(h[:M], hr.detach()) < 5e-3
+    assert rel_err(g[:M], pre.grad) < 5e-3
+    assert bool((h[M:] == 7.0).all()) and bool((g[M:] == 7.0).all())
+    torch.cuda.synchronize()
+
+
 def test_gemm_rejects_bad_arguments(ops):
     A = torch.randn(64, 60, device="cuda").bfloat16()     # pitch 120 B, not 16-byte aligned
     B = torch.randn(64, 60, device="cuda").bfloat16()
