@@ -119,7 +119,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
 
 // Epilogue specialisations (compile-time): the epilogue is instruction-issue bound (ncu: 45 % issue-active from only 8
 // warps), so the common fused forms drop every per-element runtime branch of the generic path.
-enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5, E_GELU_FWD_D = 6, E_MUL_AUX = 7, E_RESID_LN = 8, E_STORE_TMA = 9, E_MUL_AUX_TMA = 10, E_GELU_FWD_D_TMA = 11 };
+enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, E_ATOMIC = 5, E_GELU_FWD_D = 6, E_MUL_AUX = 7, E_RESID_LN = 8, E_STORE_TMA = 9, E_MUL_AUX_TMA = 10, E_GELU_FWD_D_TMA = 11, E_RESID_TMA = 12, E_RESID_LN_TMA = 13 };
 // E_RESID_LN (north_star clause 3: LayerNorm fused into the GEMM epilogue): x' = x + dropout(A W^T + b) as E_RESID, and --
 // because N == BN == 256 == the model width, so the two warps of a lane quadrant hold whole rows between them -- the
 // LayerNorm that consumes x' (vit.py:28 / :47 PreNorm) in the same epilogue: pass 1 stores x' and reduces sum / sum of squares
@@ -133,9 +133,12 @@ enum { E_GENERIC = 0, E_STORE = 1, E_GELU_FWD = 2, E_GELU_BWD = 3, E_RESID = 4, 
 // The GELU epilogues are issue/latency-bound (16 instructions + 2 MUFU per element): 16 warps.  The store / residual /
 // atomic epilogues are HBM-bound and want registers for loads in flight instead: 8 warps.
 template <int EPI> struct EpiTraits {
-  static constexpr bool LEAN = (EPI == E_STORE_TMA || EPI == E_MUL_AUX_TMA || EPI == E_GELU_FWD_D_TMA);
-  static constexpr int XB = (EPI == E_GELU_FWD_D_TMA) ? 16 * 256 : 0;                  // 64 bias values per epilogue warp
-  static constexpr int WBUF = (EPI == E_MUL_AUX_TMA) ? 2 * EPI_TILE_FLOATS * 4 : EPI_TILE_FLOATS * 4;   // aux box double-buffered
+  static constexpr bool RES = (EPI == E_RESID_TMA || EPI == E_RESID_LN_TMA);
+  static constexpr bool LEAN = (EPI == E_STORE_TMA || EPI == E_MUL_AUX_TMA || EPI == E_GELU_FWD_D_TMA || RES);
+  // per-warp scratch behind the barrier block: GELU: 64 bias values per warp (16 warps); residual (+ LayerNorm): 128 bias
+  // values per warp (8 warps) | gamma, beta [2][256] | row-statistics exchange float2 [2][2][128]
+  static constexpr int XB = (EPI == E_GELU_FWD_D_TMA) ? 16 * 256 : (RES ? 8 * 512 + 2048 + 4096 : 0);
+  static constexpr int WBUF = (EPI == E_MUL_AUX_TMA || RES) ? 2 * EPI_TILE_FLOATS * 4 : EPI_TILE_FLOATS * 4;   // aux / residual box double-buffered
 };
 template <int EPI> struct EpiWarps {
   // measured at [201216, 1024] x K = 256 (r2): multiply-by-aux 250 us with 12 warps, 229 us with 16; residual (+ LayerNorm) epilogues
@@ -147,7 +150,7 @@ template <int BN, int EPI, bool DROP, int EW = EpiWarps<EPI>::N, bool WS = false
 __global__ void __launch_bounds__((CTRL_WARPS + EW) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
-                         const GemmKernelParams p) {
+                         const __grid_constant__ CUtensorMap tmE, const GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int EPI_WARPS = EW;
   using Sm = GemmSmem<BN, EPI_WARPS, EpiTraits<EPI>::LEAN, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB>;
@@ -174,13 +177,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
     if constexpr (EpiTraits<EPI>::LEAN) tc::prefetch_tmap(&tmC);
-    if constexpr (EPI == E_MUL_AUX_TMA || EPI == E_GELU_FWD_D_TMA) tc::prefetch_tmap(&tmD);
+    if constexpr (EPI == E_MUL_AUX_TMA || EPI == E_GELU_FWD_D_TMA || EpiTraits<EPI>::RES) tc::prefetch_tmap(&tmD);
+    if constexpr (EPI == E_RESID_LN_TMA) tc::prefetch_tmap(&tmE);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], EPI_WARPS); }
     tc::mbar_init(b_full, 1);
-    if constexpr (EPI == E_MUL_AUX_TMA) for (int i = 0; i < 2 * EPI_WARPS; ++i) tc::mbar_init(&aux_full[i], 1);
+    if constexpr (EPI == E_MUL_AUX_TMA || EpiTraits<EPI>::RES) for (int i = 0; i < 2 * EPI_WARPS; ++i) tc::mbar_init(&aux_full[i], 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -313,6 +317,168 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tc::tma_store_2d(&tmC, stg, col0, row0);
           tc::tma_store_commit();
         }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tc::tma_store_wait_all<0>();
+  } else if constexpr (EpiTraits<EPI>::RES) {
+    // ======= epilogue: x' = residual + acc + bias (fp32) [+ LayerNorm(x') -> bf16, mean, rstd]; operands through TMA =======
+    // Items of a warp (lane quadrant q, column half par) in a tile: four fp32 boxes [32 rows x 32 columns] of its 128
+    // columns -- the residual box is TMA-loaded one item ahead into one of the warp's two 4 KB buffers, x' is formed in
+    // place (the lane owns the row: LDS 16 B, add, STS) and the buffer goes back to the TMA unit as the store source --
+    // and, with LayerNorm, two bf16 boxes [32 x 64].  LayerNorm: the row sums need no shuffle (thread-per-row) and one
+    // exchange with the warp that holds the other 128 columns; x' is parked in TENSOR MEMORY over the accumulator
+    // (tcgen05.st) between the passes, so pass 2 reads it back with tcgen05.ld instead of from global memory.
+    constexpr bool LN = EPI == E_RESID_LN_TMA;
+    static_assert(EPI_WARPS == 8 && BN == 256, "two warps per lane quadrant, 128 columns each");
+    const int e = warp - CTRL_WARPS;
+    const int q = warp & 3;
+    const int par = e >> 2;
+    constexpr int BPW = 4;                                    // fp32 boxes per warp and tile
+    uint8_t* buf0 = reinterpret_cast<uint8_t*>(epi_smem) + e * EpiTraits<EPI>::WBUF;
+    uint64_t* my_bar = aux_full + 2 * e;
+    float* my_bias = s_cs + e * 128;
+    float* s_gb = s_cs + 8 * 128;                             // gamma[256], beta[256]
+    float2* lnx = reinterpret_cast<float2*>(s_cs + 8 * 128 + 512);   // [2][2][128]
+    if constexpr (LN) {
+      const int te = threadIdx.x - CTRL_WARPS * 32;
+      s_gb[te] = te < p.N ? __ldg(p.ln_gamma + te) : 0.f;                 // EPI_WARPS * 32 == 256 == BN
+      s_gb[256 + te] = te < p.N ? __ldg(p.ln_beta + te) : 0.f;
+      asm volatile("bar.sync 5, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    }
+    uint32_t ph0 = 0u, ph1 = 0u;
+    int bias_nblk = -1, ln_buf = 0;
+    auto box_ok = [&](int t, int k) { return t < total_tiles && k < BPW && (t % p.n_tiles) * BN + (par * BPW + k) * 32 < p.N; };
+    auto res_load = [&](int t, int k, int b) {                // lane 0
+      const int nb = t % p.n_tiles, mb = (t / p.n_tiles) % p.m_tiles;
+      tc::mbar_expect_tx(&my_bar[b], 4096);
+      tc::tma_load_2d(buf0 + b * 4096, &tmD, &my_bar[b], nb * BN + (par * BPW + k) * 32, mb * BM + q * 32);
+    };
+    auto next_tile = [&](int t) { t += (int)gridDim.x; while (t < total_tiles && !box_ok(t, 0)) t += (int)gridDim.x; return t; };
+    int b = 0;
+    {
+      int t0 = blockIdx.x;
+      while (t0 < total_tiles && !box_ok(t0, 0)) t0 += (int)gridDim.x;
+      if (lane == 0 && t0 < total_tiles) res_load(t0, 0, 0);
+    }
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
+      const int n_blk = tile_i % p.n_tiles, m_blk = (tile_i / p.n_tiles) % p.m_tiles;
+      const int row0 = m_blk * BM + q * 32;
+      if (box_ok(tile_i, 0)) {
+        if (n_blk != bias_nblk) {                              // warp-uniform: this warp's 128 bias values
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = n_blk * BN + par * 128 + i * 32 + lane;
+            my_bias[i * 32 + lane] = c < p.N ? __ldg(p.bias + c) : 0.f;
+          }
+          bias_nblk = n_blk;
+          __syncwarp();
+        }
+        tc::mbar_wait(&acc_full[acc], acc_phase);
+        tc::fence_after_sync();
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < BPW; ++k) {
+          if (!box_ok(tile_i, k)) break;                       // warp-uniform
+          uint8_t* stg = buf0 + b * 4096;
+          // residual of the next fp32 box: this tile's, or (no LayerNorm passes in between) the next tile's first
+          const bool more = box_ok(tile_i, k + 1);
+          if (lane == 0) {
+            if (more) { tc::tma_store_wait_read<0>(); res_load(tile_i, k + 1, b ^ 1); }
+            else if (!LN) { const int nt = next_tile(tile_i); if (nt < total_tiles) { tc::tma_store_wait_read<0>(); res_load(nt, 0, b ^ 1); } }
+          }
+          if (b == 0) { tc::mbar_wait(&my_bar[0], ph0); ph0 ^= 1u; } else { tc::mbar_wait(&my_bar[1], ph1); ph1 ^= 1u; }
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + (par * BPW + k) * 32);
+          tc::tmem_ld_32x32(taddr, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* slot = reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
+            const float4 rv = *slot;
+            const float4 bv = *reinterpret_cast<const float4*>(my_bias + k * 32 + j * 4);
+            float4 v;
+            v.x = __uint_as_float(r[4 * j + 0]) + bv.x + rv.x; v.y = __uint_as_float(r[4 * j + 1]) + bv.y + rv.y;
+            v.z = __uint_as_float(r[4 * j + 2]) + bv.z + rv.z; v.w = __uint_as_float(r[4 * j + 3]) + bv.w + rv.w;
+            *slot = v;
+            if constexpr (LN) {
+              s1 += (v.x + v.y) + (v.z + v.w);
+              s2 += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+              r[4 * j + 0] = __float_as_uint(v.x); r[4 * j + 1] = __float_as_uint(v.y);
+              r[4 * j + 2] = __float_as_uint(v.z); r[4 * j + 3] = __float_as_uint(v.w);
+            }
+          }
+          if constexpr (LN) tc::tmem_st_32x32(taddr, r);       // park x' over the accumulator for pass 2
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M) {
+            tc::tma_store_2d(&tmC, stg, n_blk * BN + (par * BPW + k) * 32, row0);
+            tc::tma_store_commit();
+          }
+          b ^= 1;
+        }
+        if constexpr (LN) {
+          // ---- row statistics: this lane's 128 columns + the other warp's
+          float2* mine = lnx + (ln_buf * 2 + par) * 128 + q * 32;
+          mine[lane] = make_float2(s1, s2);
+          tc::tmem_st_wait();
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          const float2 t0 = lnx[(ln_buf * 2 + 0) * 128 + q * 32 + lane], t1 = lnx[(ln_buf * 2 + 1) * 128 + q * 32 + lane];
+          ln_buf ^= 1;
+          const float inv_n = 1.0f / (float)BN;
+          const float mean = (t0.x + t1.x) * inv_n;
+          const float var = fmaxf((t0.y + t1.y) * inv_n - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + p.ln_eps);
+          if (par == 0 && p.ln_mean != nullptr && row0 + lane < p.M) { p.ln_mean[row0 + lane] = mean; p.ln_rstd[row0 + lane] = rstd; }
+          const float sa = rstd, sb = -mean * rstd;
+          // ---- pass 2: y = (x' - mean) * rstd * gamma + beta -> bf16, two [32 x 64] boxes
+#pragma unroll 1
+          for (int kk = 0; kk < 2; ++kk) {
+            uint8_t* stg = buf0 + b * 4096;
+            if (lane == 0) {
+              tc::tma_store_wait_read<0>();                    // both buffers are free again
+              if (kk == 1) { const int nt = next_tile(tile_i); if (nt < total_tiles) res_load(nt, 0, b ^ 1); }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t r[32];
+              const int cc = par * 128 + kk * 64 + hh * 32;
+              tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cc), r);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                float y[8];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  const float4 g4 = *reinterpret_cast<const float4*>(s_gb + cc + c4 * 8 + h2 * 4);
+                  const float4 be4 = *reinterpret_cast<const float4*>(s_gb + 256 + cc + c4 * 8 + h2 * 4);
+                  y[4 * h2 + 0] = fmaf(fmaf(__uint_as_float(r[8 * c4 + 4 * h2 + 0]), sa, sb), g4.x, be4.x);
+                  y[4 * h2 + 1] = fmaf(fmaf(__uint_as_float(r[8 * c4 + 4 * h2 + 1]), sa, sb), g4.y, be4.y);
+                  y[4 * h2 + 2] = fmaf(fmaf(__uint_as_float(r[8 * c4 + 4 * h2 + 2]), sa, sb), g4.z, be4.z);
+                  y[4 * h2 + 3] = fmaf(fmaf(__uint_as_float(r[8 * c4 + 4 * h2 + 3]), sa, sb), g4.w, be4.w);
+                }
+                *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + c4) ^ (lane & 7)) << 4)) =
+                    make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+              }
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M) {
+              tc::tma_store_2d(&tmE, stg, par * 128 + kk * 64, row0);
+              tc::tma_store_commit();
+            }
+            b ^= 1;
+          }
+        }
+      } else {
+        tc::mbar_wait(&acc_full[acc], acc_phase);
+        tc::fence_after_sync();
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -821,6 +987,27 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return EAVIT_OK;
 }
 
+// 2-D fp32 tensor map, 128-byte swizzle: dims {inner, outer}, box {32 floats = 128 B, box_outer}
+static int make_tmap_f32_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return EAVIT_ECUDA;
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {32, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32) failed: %d (base %p inner %llu outer %llu pitch %llu)", (int)r, base,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes);
+    return EAVIT_ECUDA;
+  }
+  return EAVIT_OK;
+}
+
 template <int BN, int EPI, bool DROP = false, int EW = EpiWarps<EPI>::N, bool WS = false>
 static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
@@ -847,7 +1034,17 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
     rc = make_tmap_bf16_2d(&tmD, a->out_pre_bf16, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc * 2, 32);
     if (rc) return rc;
   }
-  if (EpiTraits<EPI>::LEAN) {
+  CUtensorMap tmE = tmA;
+  if (EpiTraits<EPI>::RES) {
+    rc = make_tmap_f32_2d(&tmD, a->residual, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc * 4, 32);
+    if (rc) return rc;
+    rc = make_tmap_f32_2d(&tmC, a->out_f32, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc * 4, 32);
+    if (rc) return rc;
+    if (EPI == E_RESID_LN_TMA) {
+      rc = make_tmap_bf16_2d(&tmE, a->out_bf16, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc * 2, 32);
+      if (rc) return rc;
+    }
+  } else if (EpiTraits<EPI>::LEAN) {
     rc = make_tmap_bf16_2d(&tmC, a->out_bf16, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc * 2, 32);
     if (rc) return rc;
   }
@@ -888,7 +1085,7 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS>, tmA, tmB, tmC, tmD, p));
+  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS>, tmA, tmB, tmC, tmD, tmE, p));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -946,6 +1143,12 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
     }
     if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
       return drop ? launch_gemm<256, E_MUL_AUX, true>(a, st) : launch_gemm<256, E_MUL_AUX>(a, st);
+    const bool res_tma = !drop && a->ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 &&
+                         !getenv("EAVIT_NO_TMA_STORE");
+    if (a->ln_gamma != nullptr && res_tma) return launch_gemm<256, E_RESID_LN_TMA, false, 8>(a, st);
+    if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16 && !a->colsum && res_tma)
+      return launch_gemm<256, E_RESID_TMA, false, 8>(a, st);
     if (a->ln_gamma != nullptr)            // checked above: N == 256, bias + residual + fp32 and bf16 outputs, no split-K
       return drop ? launch_gemm<256, E_RESID_LN, true>(a, st) : launch_gemm<256, E_RESID_LN>(a, st);
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)
