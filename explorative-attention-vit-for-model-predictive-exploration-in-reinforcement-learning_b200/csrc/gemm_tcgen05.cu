@@ -78,14 +78,16 @@ struct GemmCfg {
 // LEAN epilogues (E_*_TMA) work in the accumulator's native layout and move their global operands / results as
 // 128B-swizzled [32 rows x 64 columns] bf16 boxes through the TMA unit: WBUF bytes of staging per warp, no column-sum
 // slots, no LayerNorm exchange -- the shared memory they free goes to operand stages.
-template <int BN, int EW, bool LEAN = false, bool WS = false, int WBUF = EPI_TILE_FLOATS * 4, int XB = 0>
+template <int BN, int EW, bool LEAN = false, bool WS = false, int WBUF = EPI_TILE_FLOATS * 4, int XB = 0, bool PAIR = false>
 struct GemmSmem {
+  // PAIR (split-K weight gradients): a work item is TWO 128-row tiles of one column block -- both TMEM accumulators -- so a
+  // stage holds 256 x 64 of A next to the shared 256 x 64 of B: the B operand is read once per 256 output rows.
   // WS (weight-stationary, K <= 4 k-blocks, every CTA keeps one column block): the B operand of all k-blocks is loaded once
   // into a resident region in front of an A-only ring -- the K = 256 GEMMs otherwise re-read 128 KB of weights from L2 for
   // every 128 x 256 output tile (604 MB of L2 -> SM traffic per QKV launch next to 103 MB of activations).
   static constexpr int WS_KB = 4;
   static constexpr int B_RES_BYTES = WS ? WS_KB * GemmCfg<BN>::B_STAGE_BYTES : 0;
-  static constexpr int RING_STAGE_BYTES = WS ? A_STAGE_BYTES : GemmCfg<BN>::STAGE_BYTES;
+  static constexpr int RING_STAGE_BYTES = WS ? A_STAGE_BYTES : GemmCfg<BN>::STAGE_BYTES + (PAIR ? A_STAGE_BYTES : 0);
   static constexpr int BAR_BYTES = 384;
   static constexpr int EPI_BYTES = EW * WBUF;
   static constexpr int CS_SLOTS = (BN / 32 + EW / 4 - 1) / (EW / 4);            // 32-column chunks one warp handles per tile
@@ -146,14 +148,15 @@ template <int EPI> struct EpiWarps {
   static constexpr int N = (EPI == E_GELU_FWD || EPI == E_GELU_FWD_D || EPI == E_STORE || EPI == E_MUL_AUX || EPI == E_GELU_FWD_D_TMA) ? 16 : (EPI == E_GELU_BWD ? 12 : 8);
 };
 
-template <int BN, int EPI, bool DROP, int EW = EpiWarps<EPI>::N, bool WS = false>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
+template <int BN, int EPI, bool DROP, int EW = EpiWarps<EPI>::N, bool WS = false, bool PAIR = false>      // DROP: dropout mask in the epilogue (compile-time: the branch costs the fused epilogues 6-17 %)
 __global__ void __launch_bounds__((CTRL_WARPS + EW) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
                          const __grid_constant__ CUtensorMap tmE, const GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int EPI_WARPS = EW;
-  using Sm = GemmSmem<BN, EPI_WARPS, EpiTraits<EPI>::LEAN, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB>;
+  using Sm = GemmSmem<BN, EPI_WARPS, EpiTraits<EPI>::LEAN || PAIR, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB, PAIR>;
+  static_assert(!PAIR || EPI == E_ATOMIC, "paired tiles: split-K red.add epilogue only");
   constexpr int STAGES = Sm::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST
@@ -221,14 +224,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + Sm::OFF_RING + stage * Sm::RING_STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
+          uint8_t* sb = sa + (PAIR ? 2 : 1) * A_STAGE_BYTES;
           tc::mbar_expect_tx(&full_bar[stage], Sm::RING_STAGE_BYTES);
+          constexpr int AH = PAIR ? 2 : 1;                     // 128-row halves of A per stage
           if (!p.a_mn) {
-            tc::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+#pragma unroll
+            for (int h = 0; h < AH; ++h)
+              tc::tma_load_2d(sa + h * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, (m_blk * AH + h) * BM);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              tc::tma_load_2d(sa + i * 8192, &tmA, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+            for (int i = 0; i < AH * BM / 64; ++i)
+              tc::tma_load_2d(sa + i * 8192, &tmA, &full_bar[stage], m_blk * AH * BM + i * 64, kb * BK);
           }
           if constexpr (!WS) load_b(sb, &full_bar[stage], kb, n_blk);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -252,7 +258,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tc::mbar_wait(&full_bar[stage], phase);
           tc::fence_after_sync();
           const uint32_t sa = tc::smem_u32(smem + Sm::OFF_RING + stage * Sm::RING_STAGE_BYTES);
-          const uint32_t sb = WS ? tc::smem_u32(smem + kb * Cfg::B_STAGE_BYTES) : sa + A_STAGE_BYTES;
+          const uint32_t sb = WS ? tc::smem_u32(smem + kb * Cfg::B_STAGE_BYTES) : sa + (PAIR ? 2 : 1) * A_STAGE_BYTES;
           // K-major:  rows of 128 B, 8-row groups 1024 B apart (SBO); K advance = 32 B inside the swizzle atom.
           // MN-major: 64-element (128 B) MN chunks, 8 k-rows per 1024 B (SBO), MN blocks 8192 B apart (LBO);
           //           K advance = 16 k-rows = 2048 B.
@@ -261,15 +267,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint32_t a_step = p.a_mn ? (2048 >> 4) : (32 >> 4);
           const uint32_t b_step = p.b_mn ? (2048 >> 4) : (32 >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            tc::mma_bf16_ss(d_tmem, a_desc + (uint64_t)(k * a_step), b_desc + (uint64_t)(k * b_step), idesc,
-                            (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int h = 0; h < (PAIR ? 2 : 1); ++h) {   // PAIR: rows 0..127 -> accumulator 0, rows 128..255 -> accumulator 1
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              tc::mma_bf16_ss(d_tmem + h * BN, a_desc + (uint64_t)(h * (A_STAGE_BYTES >> 4)) + (uint64_t)(k * a_step),
+                              b_desc + (uint64_t)(k * b_step), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           tc::mma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(&acc_full[acc]);               // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        tc::mma_commit(&acc_full[acc]);               // accumulator(s) complete -> epilogue
+        if constexpr (PAIR) acc_phase ^= 1; else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if constexpr (EPI == E_STORE_TMA) {
@@ -739,7 +748,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int it = 0; it < 8; ++it) { ls1[it] = 0.f; ls2[it] = 0.f; }
       tc::mbar_wait(&acc_full[acc], acc_phase);
       tc::fence_after_sync();
-      const int row0 = m_blk * BM + q * 32;
+#pragma unroll 1
+      for (int half = 0; half < (PAIR ? 2 : 1); ++half) {
+      const int acc_c = PAIR ? half : acc;             // accumulator read below
+      const int row0 = (PAIR ? m_blk * 2 + half : m_blk) * BM + q * 32;
       const int nrows = min(32, p.M - row0);          // may be <= 0 for the M tail
 #pragma unroll 1
       for (int c = par; c < BN / 32; c += EPI_WARPS / 4) {
@@ -762,7 +774,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t r[16];
-          tc::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32 + hh * 16), r);
+          tc::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_c * BN + c * 32 + hh * 16), r);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4)
@@ -864,13 +876,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
       }
+      }   // half
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if constexpr (PAIR) acc_phase ^= 1; else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if constexpr (LNF) {
         // ---- row statistics: 8 lanes share a row inside the warp, the two warps of the quadrant share it between them
         const int cchunk = lane & 7, rsub = lane >> 3;
+        const int row0 = m_blk * BM + q * 32;
+        const int nrows = min(32, p.M - row0);
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
 #pragma unroll
@@ -1008,13 +1023,13 @@ static int make_tmap_f32_2d(CUtensorMap* tm, const void* base, uint64_t inner, u
   return EAVIT_OK;
 }
 
-template <int BN, int EPI, bool DROP = false, int EW = EpiWarps<EPI>::N, bool WS = false>
+template <int BN, int EPI, bool DROP = false, int EW = EpiWarps<EPI>::N, bool WS = false, bool PAIR = false>
 static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<BN, EW, EpiTraits<EPI>::LEAN, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB>::TOTAL));
+    EAVIT_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    GemmSmem<BN, EW, EpiTraits<EPI>::LEAN || PAIR, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB, PAIR>::TOTAL));
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
@@ -1052,7 +1067,7 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   GemmKernelParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_mn; p.b_mn = a->b_mn;
-  p.m_tiles = cdiv(a->M, BM);
+  p.m_tiles = PAIR ? cdiv(cdiv(a->M, BM), 2) : cdiv(a->M, BM);      // PAIR: work items are pairs of 128-row tiles
   p.n_tiles = cdiv(a->N, BN);
   p.kb_total = cdiv(a->K, BK);
   int splits = a->split_k > 0 ? a->split_k : 1;
@@ -1078,14 +1093,14 @@ static int launch_gemm(const eavit_gemm_args* a, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3((CTRL_WARPS + EW) * 32);
-  cfg.dynamicSmemBytes = GemmSmem<BN, EW, EpiTraits<EPI>::LEAN, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB>::TOTAL;
+  cfg.dynamicSmemBytes = GemmSmem<BN, EW, EpiTraits<EPI>::LEAN || PAIR, WS, EpiTraits<EPI>::WBUF, EpiTraits<EPI>::XB, PAIR>::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS>, tmA, tmB, tmC, tmD, tmE, p));
+  EAVIT_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, DROP, EW, WS, PAIR>, tmA, tmB, tmC, tmD, tmE, p));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }
@@ -1120,6 +1135,9 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
   if (a->N > 128) {
     const bool none = a->act == EAVIT_ACT_NONE;
     const bool plain = !a->residual && !a->aux_bf16 && !a->out_pre_bf16;
+    if (a->atomic_f32 && none && plain && !a->bias && !a->out_bf16 && !a->colsum && !drop && a->M > BM &&
+        cdiv(a->M, BM) * cdiv(a->N, 256) >= 4 && !getenv("EAVIT_NO_PAIR"))   // engine._split_k mirrors this rule; 2 tiles (256 x 256) are faster unpaired (62 vs 74 us)
+      return launch_gemm<256, E_ATOMIC, false, 8, false, true>(a, st);
     if (a->atomic_f32 && none && plain && !a->bias && !a->out_bf16) return launch_gemm<256, E_ATOMIC>(a, st);
     if (a->atomic_f32) return launch_gemm<256, E_GENERIC>(a, st);
     if (a->colsum != nullptr && a->act != EAVIT_ACT_GELU_BWD && a->act != EAVIT_ACT_MUL_AUX)   // only the GELU' / multiply and generic epilogues carry column sums

@@ -160,7 +160,10 @@ def _split_k(M: int, N: int, K: int) -> int:
     """K splits of a weight-gradient GEMM: the smallest count whose work items (tiles * splits) fill the persistent
     148-CTA grid to >= 90 % in whole waves (149 items would cost a second wave; 96 tiles alone leave a third of the SMs
     idle, 96 * 3 = 288 items fill two waves to 97 %), with at least 8 k-blocks per split."""
-    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+    mt = (M + 127) // 128
+    if N > 128 and mt >= 2 and mt * ((N + 255) // 256) >= 4 and not os.environ.get("EAVIT_NO_PAIR"):
+        mt = (mt + 1) // 2           # the 256-wide kernel takes 128-row tiles in pairs (both TMEM accumulators, B read once)
+    tiles = mt * ((N + 255) // 256 if N > 128 else 1)
     kb = (K + 63) // 64
     one_wave = max(1, min(148 // tiles, kb))
     if tiles * one_wave >= 0.85 * 148:

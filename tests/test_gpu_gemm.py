@@ -65,6 +65,25 @@ def test_gemm_split_k_atomic(ops):
     assert rel_err(out, 2 * ref) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K,mn,split", [(768, 256, 5000, True, 16), (1024, 256, 9000, True, 37), (256, 1024, 4100, True, 9),
+                                             (704, 512, 3000, True, 5), (384, 256, 2048, False, 4), (333, 264, 1000, False, 1)])
+def test_gemm_split_k_paired_tiles(ops, M, N, K, mn, split):
+    """Weight-gradient GEMMs take their 128-row tiles in pairs (both TMEM accumulators per work item): odd tile counts, M / N
+    tails, MN-major and K-major operands, accumulation on top of earlier content."""
+    torch.manual_seed(M + K)
+    At = torch.randn(K, M, device="cuda").bfloat16()
+    Bt = torch.randn(K, N, device="cuda").bfloat16()
+    ref = At.float().t() @ Bt.float()
+    out = torch.full((M + 2, N), 3.0, device="cuda", dtype=torch.float32)
+    if mn:
+        ops.gemm(At, Bt, a_mn=True, b_mn=True, out_f32=out[:M], atomic=True, split_k=split)
+    else:
+        ops.gemm(At.t().contiguous(), Bt.t().contiguous(), out_f32=out[:M], atomic=True, split_k=split)
+    torch.cuda.synchronize()
+    assert rel_err(out[:M], ref + 3.0) < 2e-5, rel_err(out[:M], ref + 3.0)
+    assert bool((out[M:] == 3.0).all())
+
+
 def test_gemm_epilogues(ops):
     torch.manual_seed(3)
     M, N, K = 500, 1024, 256

@@ -24,6 +24,8 @@ b2 = torch.randn(D, device="cuda")
 wo = (torch.randn(D, D, device="cuda") / 16).bfloat16()
 wq = (torch.randn(3 * D, D, device="cuda") / 16).bfloat16()
 qkv = torch.empty(T, 3 * D, device="cuda", dtype=torch.bfloat16)
+from eavit_b200.engine import _split_k
+dWq = torch.zeros(768, 256, device="cuda"); dW1 = torch.zeros(1024, 256, device="cuda"); dW2 = torch.zeros(256, 1024, device="cuda"); dWo = torch.zeros(256, 256, device="cuda")
 cases = {
     "mlp1_fwd_gelu_save_grad  <256,6>": lambda: ops.gemm(x, w1, bias=b1, act=ops.ACT_GELU_SAVE_GRAD, out_bf16=hact, out_pre=hpre),
     "mlp2_dx_mul_aux+colsum   <256,7>": lambda: ops.gemm(x, w2, b_mn=True, act=ops.ACT_MUL_AUX, aux=hpre, out_bf16=dh, colsum=cs),
@@ -31,6 +33,10 @@ cases = {
     "mlp2_fwd_resid_ln        <256,8>": lambda: ops.gemm(hact, w2, bias=b2, residual=res, out_f32=out, out_bf16=xn, ln=(g, be, mu, rs, 1e-5)),
     "outproj_fwd_resid_ln K=256 <256,8>": lambda: ops.gemm(x, wo, bias=b2, residual=res, out_f32=out, out_bf16=xn, ln=(g, be, mu, rs, 1e-5)),
     "qkv_fwd_store            <256,1>": lambda: ops.gemm(x, wq, out_bf16=qkv),
+    "dW_qkv  M=768 N=256 splitk": lambda: ops.gemm(qkv, x, a_mn=True, b_mn=True, out_f32=dWq, atomic=True, split_k=_split_k(768, 256, T)),
+    "dW_mlp1 M=1024 N=256 splitk": lambda: ops.gemm(hact, x, a_mn=True, b_mn=True, out_f32=dW1, atomic=True, split_k=_split_k(1024, 256, T)),
+    "dW_mlp2 M=256 N=1024 splitk": lambda: ops.gemm(x, hact, a_mn=True, b_mn=True, out_f32=dW2, atomic=True, split_k=_split_k(256, 1024, T)),
+    "dW_out  M=256 N=256 splitk": lambda: ops.gemm(x, xn, a_mn=True, b_mn=True, out_f32=dWo, atomic=True, split_k=_split_k(256, 256, T)),
     "qkv_dx  N=256 K=768 kmn bf16 out": lambda: ops.gemm(qkv, wq, b_mn=True, out_bf16=xn),
     "mlp1_dx N=256 K=1024 kmn bf16 out": lambda: ops.gemm(hact, w1, b_mn=True, out_bf16=xn),
     "outproj_dx N=256 K=256 kmn bf16 out": lambda: ops.gemm(x, wo, b_mn=True, out_bf16=xn),
