@@ -390,6 +390,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         tc::mbar_wait(&acc_full[acc], acc_phase);
         tc::fence_after_sync();
+        uint32_t rk = 0u;
+        if constexpr (DROP) rk = drop_row_key(p.drop, (uint32_t)(row0 + lane));
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
         for (int k = 0; k < BPW; ++k) {
@@ -412,8 +414,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const float4 rv = *slot;
             const float4 bv = *reinterpret_cast<const float4*>(my_bias + k * 32 + j * 4);
             float4 v;
-            v.x = __uint_as_float(r[4 * j + 0]) + bv.x + rv.x; v.y = __uint_as_float(r[4 * j + 1]) + bv.y + rv.y;
-            v.z = __uint_as_float(r[4 * j + 2]) + bv.z + rv.z; v.w = __uint_as_float(r[4 * j + 3]) + bv.w + rv.w;
+            if constexpr (DROP) {                              // nn.Dropout on the Linear output, before the residual add
+              float dm[4];
+              drop4(p.drop, rk, (uint32_t)(n_blk * BN + (par * BPW + k) * 32 + 4 * j), dm);
+              v.x = fmaf(__uint_as_float(r[4 * j + 0]) + bv.x, dm[0], rv.x); v.y = fmaf(__uint_as_float(r[4 * j + 1]) + bv.y, dm[1], rv.y);
+              v.z = fmaf(__uint_as_float(r[4 * j + 2]) + bv.z, dm[2], rv.z); v.w = fmaf(__uint_as_float(r[4 * j + 3]) + bv.w, dm[3], rv.w);
+            } else {
+              v.x = __uint_as_float(r[4 * j + 0]) + bv.x + rv.x; v.y = __uint_as_float(r[4 * j + 1]) + bv.y + rv.y;
+              v.z = __uint_as_float(r[4 * j + 2]) + bv.z + rv.z; v.w = __uint_as_float(r[4 * j + 3]) + bv.w + rv.w;
+            }
             *slot = v;
             if constexpr (LN) {
               s1 += (v.x + v.y) + (v.z + v.w);
@@ -525,6 +534,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         if (!waited) { tc::mbar_wait(&acc_full[acc], acc_phase); tc::fence_after_sync(); waited = true; }
         uint32_t gp[32];                               // gelu' of the box, packed bf16 pairs
+        uint32_t rk = 0u;
+        if constexpr (DROP) rk = drop_row_key(p.drop, (uint32_t)(row0 + lane));
         if (lane == 0) tc::tma_store_wait_read<0>();   // the previous box (g of the last item) has left the staging buffer
         __syncwarp();
 #pragma unroll
@@ -540,6 +551,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             float hv[8], gv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) hv[i] = gelu_erf_and_grad(__uint_as_float(r[8 * c4 + i]) + bb[i], gv[i]);
+            if constexpr (DROP) {                              // nn.Dropout after the activation (gelu' is stored unmasked)
+              float dm[8];
+              drop4(p.drop, rk, (uint32_t)(col0 + hh * 32 + c4 * 8), dm);
+              drop4(p.drop, rk, (uint32_t)(col0 + hh * 32 + c4 * 8 + 4), dm + 4);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) hv[i] *= dm[i];
+            }
             *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + c4) ^ (lane & 7)) << 4)) =
                 make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]), pack_bf16x2(hv[6], hv[7]));
 #pragma unroll
@@ -632,6 +650,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         tc::mbar_wait(&my_bar[b], ph[b]);
         ph[b] ^= 1u;
+        uint32_t rk = 0u;
+        if constexpr (DROP) rk = drop_row_key(p.drop, (uint32_t)(row0 + lane));
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t r[32];
@@ -641,6 +661,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int c4 = 0; c4 < 4; ++c4) {
             uint4* slot = reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + c4) ^ (lane & 7)) << 4));
             const uint4 a = *slot;
+            if constexpr (DROP) {                              // the forward's dropout mask on the MLP hidden, regenerated
+              float dm[8];
+              drop4(p.drop, rk, (uint32_t)(n_blk * BN + g * 64 + hh * 32 + c4 * 8), dm);
+              drop4(p.drop, rk, (uint32_t)(n_blk * BN + g * 64 + hh * 32 + c4 * 8 + 4), dm + 4);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[8 * c4 + i] = __float_as_uint(__uint_as_float(r[8 * c4 + i]) * dm[i]);
+            }
             uint4 v;
             v.x = pack_bf16x2(__uint_as_float(r[8 * c4 + 0]) * __uint_as_float(a.x << 16), __uint_as_float(r[8 * c4 + 1]) * __uint_as_float(a.x & 0xffff0000u));
             v.y = pack_bf16x2(__uint_as_float(r[8 * c4 + 2]) * __uint_as_float(a.y << 16), __uint_as_float(r[8 * c4 + 3]) * __uint_as_float(a.y & 0xffff0000u));
@@ -1146,27 +1173,24 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
       return drop ? launch_gemm<256, E_GELU_FWD, true>(a, st) : launch_gemm<256, E_GELU_FWD>(a, st);
     if (a->act == EAVIT_ACT_GELU_BWD && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
       return drop ? launch_gemm<256, E_GELU_BWD, true>(a, st) : launch_gemm<256, E_GELU_BWD>(a, st);
-    if (a->act == EAVIT_ACT_GELU_SAVE_GRAD && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32 && !drop &&
+    if (a->act == EAVIT_ACT_GELU_SAVE_GRAD && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32 &&
         (a->ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_pre_bf16) & 15) == 0 &&
         !getenv("EAVIT_NO_TMA_STORE"))
-      return launch_gemm<256, E_GELU_FWD_D_TMA>(a, st);
+      return drop ? launch_gemm<256, E_GELU_FWD_D_TMA, true>(a, st) : launch_gemm<256, E_GELU_FWD_D_TMA>(a, st);
     if (a->act == EAVIT_ACT_GELU_SAVE_GRAD && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32)
       return drop ? launch_gemm<256, E_GELU_FWD_D, true>(a, st) : launch_gemm<256, E_GELU_FWD_D>(a, st);
     const bool tma_ok = (a->ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && !getenv("EAVIT_NO_TMA_STORE");
-    if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16 && !drop && tma_ok &&
-        (reinterpret_cast<uintptr_t>(a->aux_bf16) & 15) == 0) {
-      const int kbt = cdiv(a->K, BK), nt = cdiv(a->N, 256), tiles = cdiv(a->M, BM) * nt;
-      if (kbt <= 4 && tiles >= kNumSMs && nt <= kNumSMs && getenv("EAVIT_MULAUX_WS")) return launch_gemm<256, E_MUL_AUX_TMA, false, 8, true>(a, st);
-      return launch_gemm<256, E_MUL_AUX_TMA, false, 8>(a, st);
-    }
+    if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16 && tma_ok &&
+        (reinterpret_cast<uintptr_t>(a->aux_bf16) & 15) == 0)     // (weight-stationary B leaves 2 A stages beside the aux buffers: 181 vs 155 us)
+      return drop ? launch_gemm<256, E_MUL_AUX_TMA, true, 8>(a, st) : launch_gemm<256, E_MUL_AUX_TMA, false, 8>(a, st);
     if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16)
       return drop ? launch_gemm<256, E_MUL_AUX, true>(a, st) : launch_gemm<256, E_MUL_AUX>(a, st);
-    const bool res_tma = !drop && a->ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 &&
+    const bool res_tma = a->ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 &&
                          !getenv("EAVIT_NO_TMA_STORE");
-    if (a->ln_gamma != nullptr && res_tma) return launch_gemm<256, E_RESID_LN_TMA, false, 8>(a, st);
+    if (a->ln_gamma != nullptr && res_tma) return drop ? launch_gemm<256, E_RESID_LN_TMA, true, 8>(a, st) : launch_gemm<256, E_RESID_LN_TMA, false, 8>(a, st);
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16 && !a->colsum && res_tma)
-      return launch_gemm<256, E_RESID_TMA, false, 8>(a, st);
+      return drop ? launch_gemm<256, E_RESID_TMA, true, 8>(a, st) : launch_gemm<256, E_RESID_TMA, false, 8>(a, st);
     if (a->ln_gamma != nullptr)            // checked above: N == 256, bias + residual + fp32 and bf16 outputs, no split-K
       return drop ? launch_gemm<256, E_RESID_LN, true>(a, st) : launch_gemm<256, E_RESID_LN>(a, st);
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)

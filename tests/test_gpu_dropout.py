@@ -77,6 +77,50 @@ def test_gemm_epilogue_dropout(ops):
     assert rel(cs, ref.sum(0)) < 2e-3
 
 
+@pytest.mark.parametrize("M", [700, 20000])
+def test_gemm_tma_epilogues_dropout(ops, M):
+    """The TMA epilogues regenerate the same (row, column) masks in the accumulator's native layout: GELU storing gelu'
+    (mask on the activation only), multiply-by-aux + column sums, residual and residual + LayerNorm."""
+    torch.manual_seed(M)
+    N, K, p = 1024, 256, 0.1
+    seed = ops.site_seed(91, 5)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") / 16).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    mask = ops.dropout_mask(M, N, p, seed)
+    pre = (A.float() @ B.float().t() + bias).requires_grad_(True)
+    hr = torch.nn.functional.gelu(pre)
+    hr.sum().backward()
+    h16, g16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, bias=bias, act=ops.ACT_GELU_SAVE_GRAD, out_bf16=h16, out_pre=g16, drop_p=p, drop_seed=seed)
+    assert rel(h16, hr.detach() * mask) < 5e-3
+    assert rel(g16, pre.grad) < 5e-3
+    assert ((h16 == 0) == (mask == 0)).float().mean().item() > 0.999
+    cs = torch.zeros(N, device="cuda")
+    d16 = torch.empty_like(h16)
+    ops.gemm(A, B, act=ops.ACT_MUL_AUX, aux=g16, out_bf16=d16, colsum=cs, drop_p=p, drop_seed=seed)
+    want = (A.float() @ B.float().t()) * g16.float() * mask
+    assert rel(d16, want) < 5e-3
+    assert rel(cs, want.sum(0)) < 3e-3
+    # N = 256: residual (+ LayerNorm) epilogues, K = 1024 operand
+    A2 = h16
+    W2 = (torch.randn(256, N, device="cuda") / 32).bfloat16()
+    b2 = torch.randn(256, device="cuda")
+    res = torch.randn(M, 256, device="cuda")
+    m2 = ops.dropout_mask(M, 256, p, seed)
+    y = (A2.float() @ W2.float().t() + b2) * m2 + res
+    out = torch.empty(M, 256, device="cuda")
+    ops.gemm(A2, W2, bias=b2, residual=res, out_f32=out, drop_p=p, drop_seed=seed)
+    assert rel(out, y) < 1e-5
+    gam, bet = torch.randn(256, device="cuda") * 0.2 + 1, torch.randn(256, device="cuda") * 0.1
+    xn = torch.empty(M, 256, device="cuda", dtype=torch.bfloat16)
+    mu, rs = torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    ops.gemm(A2, W2, bias=b2, residual=res, out_f32=out, out_bf16=xn, ln=(gam, bet, mu, rs, 1e-5), drop_p=p, drop_seed=seed)
+    assert rel(out, y) < 1e-5
+    assert rel(xn, torch.nn.functional.layer_norm(y, (256,), gam, bet, 1e-5)) < 5e-3
+    assert rel(mu, y.mean(1)) < 1e-5
+
+
 def test_layernorm_bwd_masks_linear_output_gradient(ops):
     torch.manual_seed(1)
     T, D, p = 999, 256, 0.1
