@@ -310,6 +310,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           uint32_t r[32];
           tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + g * 64 + hh * 32), r);
           tc::tmem_ld_wait();
+          if (p.bias != nullptr) {                     // warp-uniform; the same 16 bytes for every lane (L1 broadcast)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = col0 + hh * 32 + 4 * j;
+              const float4 b4 = c < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);   // N % 8 == 0
+              r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + b4.x); r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b4.y);
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b4.z); r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b4.w);
+            }
+          }
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             uint4 v;
@@ -1195,7 +1204,7 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
       return drop ? launch_gemm<256, E_RESID_LN, true>(a, st) : launch_gemm<256, E_RESID_LN>(a, st);
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)
       return drop ? launch_gemm<256, E_RESID, true>(a, st) : launch_gemm<256, E_RESID>(a, st);
-    if (none && plain && !drop && !a->bias && a->out_bf16 && !a->out_f32 && !a->colsum && (a->ldc * 2) % 16 == 0 &&
+    if (none && plain && !drop && a->out_bf16 && !a->out_f32 && !a->colsum && (a->ldc * 2) % 16 == 0 &&
         (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && !getenv("EAVIT_NO_TMA_STORE"))
     {
       const int kbt = cdiv(a->K, BK), nt = cdiv(a->N, 256), tiles = cdiv(a->M, BM) * nt;

@@ -173,6 +173,9 @@ def test_gemm_tma_epilogues(ops, M, N, K, b_mn):
     ops.gemm(A, Bop, b_mn=b_mn, out_bf16=out16[:M])
     assert rel_err(out16[:M], ref) < 5e-3
     assert bool((out16[M:] == 7.0).all())
+    bias0 = torch.randn(N, device="cuda")
+    ops.gemm(A, Bop, b_mn=b_mn, bias=bias0, out_bf16=out16[:M])                           # + bias (HF-style qkv)
+    assert rel_err(out16[:M], ref + bias0) < 5e-3
     aux = torch.randn(M, N, device="cuda").bfloat16()
     cs = torch.zeros(N, device="cuda")
     dh = torch.full((M + 3, N), 7.0, device="cuda", dtype=torch.bfloat16)
