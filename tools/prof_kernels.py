@@ -32,6 +32,9 @@ if which in ("all", "gemm"):
         ops.gemm(hact, w2, bias=b2, residual=res, out_f32=out)                             # MLP2 fwd + residual             <256, 4, 0>
     for _ in range(reps):
         ops.gemm(hact, w2, bias=b2, residual=res, out_f32=out, out_bf16=xn, ln=(g, be, mu, rs, 1e-5))   # + fused LayerNorm   <256, 8, 0>
+    wo = (torch.randn(D, D, device="cuda") / 16).bfloat16()
+    for _ in range(reps):
+        ops.gemm(x, wo, bias=b2, residual=res, out_f32=out, out_bf16=xn, ln=(g, be, mu, rs, 1e-5))      # out-proj + residual + LayerNorm, K = 256
     wq = (torch.randn(3 * D, D, device="cuda") / 16).bfloat16()
     qkv = torch.empty(T, 3 * D, device="cuda", dtype=torch.bfloat16)
     for _ in range(reps):

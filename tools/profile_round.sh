@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 180 -c 460 --csv --
     python bench.py --steps 2 --warmup 1 --no-side --no-cpu --no-e2e > gpurun_out/r2_ncu_launches.log 2>&1
 python tools/ncu_launch_shares.py gpurun_out/r2_ncu_launch_list.csv > gpurun_out/r2_ncu_launch_shares.md
 python tools/prof_kernels.py all > gpurun_out/r2_prof_plain.log 2>&1 &&
-ncu --set full --clock-control none -k regex:'attention|gemm_bf16|layernorm|rms_u8x16|obs_normalize|rms_partial|rms_reduce' -c 48 \
+ncu --set full --clock-control none -k regex:'attention|gemm_bf16|layernorm|rms_u8x16|obs_normalize|rms_partial|rms_reduce|embed_fused' -c 56 \
     -o /tmp/r2_prof python tools/prof_kernels.py all > gpurun_out/r2_ncu_full.log 2>&1
 python tools/ncu_summary.py /tmp/r2_prof.ncu-rep > gpurun_out/r2_ncu_full_top_kernels_table.md
 ncu -i /tmp/r2_prof.ncu-rep --page raw --csv 2>/dev/null | cut -c1-100000 | python -c "
