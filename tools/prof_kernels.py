@@ -41,7 +41,7 @@ if which in ("all", "gemm"):
         ops.gemm(x, wq, out_bf16=qkv)                                                       # QKV
     dW = torch.zeros(MLP, D, device="cuda")
     for _ in range(reps):
-        ops.gemm(dh, x, a_mn=True, b_mn=True, out_f32=dW, atomic=True, split_k=10)          # dW1 split-K
+        ops.gemm(dh, x, a_mn=True, b_mn=True, out_f32=dW, atomic=True, split_k=37)          # dW1 split-K (engine._split_k(1024, 256, T) = 37)          # dW1 split-K
 if which in ("all", "attn"):
     B = 512
     lens = [196] * B + [197] * B
