@@ -1167,12 +1167,15 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
   }
   EAVIT_CHECK_ARG(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
+  // switches for A/B measurements and for falling back to the transposing epilogues (read once)
+  static const bool no_tma = getenv("EAVIT_NO_TMA_STORE") != nullptr, no_ws = getenv("EAVIT_NO_WS") != nullptr,
+                    no_pair = getenv("EAVIT_NO_PAIR") != nullptr;
   const bool drop = make_drop(a->drop_p, a->drop_seed).thresh != 0;
   if (a->N > 128) {
     const bool none = a->act == EAVIT_ACT_NONE;
     const bool plain = !a->residual && !a->aux_bf16 && !a->out_pre_bf16;
     if (a->atomic_f32 && none && plain && !a->bias && !a->out_bf16 && !a->colsum && !drop && a->M > BM &&
-        cdiv(a->M, BM) * cdiv(a->N, 256) >= 4 && !getenv("EAVIT_NO_PAIR"))   // engine._split_k mirrors this rule; 2 tiles (256 x 256) are faster unpaired (62 vs 74 us)
+        cdiv(a->M, BM) * cdiv(a->N, 256) >= 4 && !no_pair)   // engine._split_k mirrors this rule; 2 tiles (256 x 256) are faster unpaired (62 vs 74 us)
       return launch_gemm<256, E_ATOMIC, false, 8, false, true>(a, st);
     if (a->atomic_f32 && none && plain && !a->bias && !a->out_bf16) return launch_gemm<256, E_ATOMIC>(a, st);
     if (a->atomic_f32) return launch_gemm<256, E_GENERIC>(a, st);
@@ -1184,11 +1187,11 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
       return drop ? launch_gemm<256, E_GELU_BWD, true>(a, st) : launch_gemm<256, E_GELU_BWD>(a, st);
     if (a->act == EAVIT_ACT_GELU_SAVE_GRAD && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32 &&
         (a->ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_pre_bf16) & 15) == 0 &&
-        !getenv("EAVIT_NO_TMA_STORE"))
+        !no_tma)
       return drop ? launch_gemm<256, E_GELU_FWD_D_TMA, true>(a, st) : launch_gemm<256, E_GELU_FWD_D_TMA>(a, st);
     if (a->act == EAVIT_ACT_GELU_SAVE_GRAD && a->bias && a->out_pre_bf16 && a->out_bf16 && !a->residual && !a->out_f32)
       return drop ? launch_gemm<256, E_GELU_FWD_D, true>(a, st) : launch_gemm<256, E_GELU_FWD_D>(a, st);
-    const bool tma_ok = (a->ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && !getenv("EAVIT_NO_TMA_STORE");
+    const bool tma_ok = (a->ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && !no_tma;
     if (a->act == EAVIT_ACT_MUL_AUX && a->out_bf16 && !a->bias && !a->residual && !a->out_f32 && !a->out_pre_bf16 && tma_ok &&
         (reinterpret_cast<uintptr_t>(a->aux_bf16) & 15) == 0)     // (weight-stationary B leaves 2 A stages beside the aux buffers: 181 vs 155 us)
       return drop ? launch_gemm<256, E_MUL_AUX_TMA, true, 8>(a, st) : launch_gemm<256, E_MUL_AUX_TMA, false, 8>(a, st);
@@ -1196,7 +1199,7 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
       return drop ? launch_gemm<256, E_MUL_AUX, true>(a, st) : launch_gemm<256, E_MUL_AUX>(a, st);
     const bool res_tma = a->ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 &&
-                         !getenv("EAVIT_NO_TMA_STORE");
+                         !no_tma;
     if (a->ln_gamma != nullptr && res_tma) return drop ? launch_gemm<256, E_RESID_LN_TMA, true, 8>(a, st) : launch_gemm<256, E_RESID_LN_TMA, false, 8>(a, st);
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16 && !a->colsum && res_tma)
       return drop ? launch_gemm<256, E_RESID_TMA, true, 8>(a, st) : launch_gemm<256, E_RESID_TMA, false, 8>(a, st);
@@ -1205,10 +1208,10 @@ extern "C" int eavit_gemm_bf16(const eavit_gemm_args* a, void* stream) {
     if (none && a->bias && a->residual && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && !a->aux_bf16)
       return drop ? launch_gemm<256, E_RESID, true>(a, st) : launch_gemm<256, E_RESID>(a, st);
     if (none && plain && !drop && a->out_bf16 && !a->out_f32 && !a->colsum && (a->ldc * 2) % 16 == 0 &&
-        (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && !getenv("EAVIT_NO_TMA_STORE"))
+        (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && !no_tma)
     {
       const int kbt = cdiv(a->K, BK), nt = cdiv(a->N, 256), tiles = cdiv(a->M, BM) * nt;
-      if (kbt <= 4 && tiles >= kNumSMs && nt <= kNumSMs && !getenv("EAVIT_NO_WS")) return launch_gemm<256, E_STORE_TMA, false, 8, true>(a, st);
+      if (kbt <= 4 && tiles >= kNumSMs && nt <= kNumSMs && !no_ws) return launch_gemm<256, E_STORE_TMA, false, 8, true>(a, st);
       return launch_gemm<256, E_STORE_TMA, false, 8>(a, st);
     }
     if (none && plain && !drop) return launch_gemm<256, E_STORE>(a, st);
