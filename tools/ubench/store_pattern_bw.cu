@@ -10,6 +10,7 @@
 // MODE 2: 16 B / lane, 8 lanes per row: 4 rows x 128 B per instruction (64-column chunks)
 // MODE 3: 16 B / lane, 16 lanes per row: 2 rows x 256 B per instruction (128-column chunks)
 // MODE 4: 16 B / lane, 32 lanes per row: 1 row x 512 B (whole 256-column tile row)
+// MODE 5: the accumulator's native layout without a transpose: lane = row, 4 x 16 B back to back per 32 columns (32 rows x 16 B per instruction)
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) k(uint16_t* out, int T, int N) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -17,7 +18,7 @@ __global__ void __launch_bounds__(512, 1) k(uint16_t* out, int T, int N) {
   for (int tile = blockIdx.x; tile < n_tiles * m_tiles; tile += gridDim.x) {
     const int nb = tile % n_tiles, mb = tile / n_tiles;
     // the tile is 128 x 256 bf16 = 64 KB; split into per-warp pieces of 32 rows x CW columns
-    constexpr int CW = MODE <= 1 ? 32 : MODE == 2 ? 64 : MODE == 3 ? 128 : 256;
+    constexpr int CW = (MODE <= 1 || MODE == 5) ? 32 : MODE == 2 ? 64 : MODE == 3 ? 128 : 256;
     constexpr int PIECES = 4 * (256 / CW);
     for (int pc = warp; pc < PIECES; pc += nw) {
       const int q = pc & 3, c = pc >> 2;
@@ -27,6 +28,10 @@ __global__ void __launch_bounds__(512, 1) k(uint16_t* out, int T, int N) {
 #pragma unroll
         for (int it = 0; it < 8; ++it)
           *reinterpret_cast<uint2*>(out + (size_t)(row0 + it * 4 + rs) * N + col0 + cch * 4) = make_uint2(tile, lane);
+      } else if (MODE == 5) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          *reinterpret_cast<uint4*>(out + (size_t)(row0 + lane) * N + col0 + it * 8) = make_uint4(tile, lane, it, 0);
       } else {
         constexpr int LPR = CW / 8;           // lanes per row
         constexpr int RPI = 32 / LPR;         // rows per instruction
@@ -61,6 +66,7 @@ int main() {
       run<2>(d, T, N, th, "16B/lane 4 rows x 128B");
       run<3>(d, T, N, th, "16B/lane 2 rows x 256B");
       run<4>(d, T, N, th, "16B/lane 1 row x 512B");
+      run<5>(d, T, N, th, "native: lane = row, 32 rows x 16B");
     }
   }
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
