@@ -453,6 +453,23 @@ def main():
                 "per_kernel": [{"kernel": gname, "launches_per_step": a[0] / nprof, "ms_per_step": a[1] / nprof, "share": a[1] / tot_ms,
                                 "tflops": (a[2] / (a[1] * 1e-3) / 1e12 if a[2] > 0 else None)}
                                for gname, a in sorted(groups.items(), key=lambda kv: -kv[1][1])[:14]]}
+    # Both ceilings of the classical roofline for that kernel.  `bound` / `frac` above stay the tensor-pipe view (the kernel is a
+    # dense contraction; same definition as round 1); at its arithmetic intensity the LOWER ceiling is the HBM one, so the
+    # fraction of the binding ceiling is reported beside it.  Algorithmic bytes of the attention kernels at [T, 3*inner] bf16:
+    # backward reads qkv, O, dO and writes dqkv (8 * T * inner * 2 B); forward reads qkv, writes O (4 * T * inner * 2 B).
+    T_tok, inner = B * (196 + 197), 256
+    alg_bytes = {"attention_bwd": 8 * T_tok * inner * 2, "attention_fwd": 4 * T_tok * inner * 2}
+    ab = next((v for k, v in alg_bytes.items() if dom_label.startswith(k)), None)
+    if ab is not None:
+        t_launch = dms / dn * 1e-3
+        ridge = pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+        ai = dfl / ab
+        roofline["ceilings"] = {
+            "algorithmic_bytes": ab, "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+            "binding": "hbm" if ai < ridge else "tensor",
+            "hbm": {"achieved": ab / t_launch / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ab / t_launch / 1e9 / pk["hbm_gbs"]},
+            "tensor": {"achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"]},
+            "frac_of_binding_ceiling": max(ab / t_launch / 1e9 / pk["hbm_gbs"], achieved / pk["bf16_tflops"])}
     if args.profile_out and rank == 0:
         rows = sorted(((l, n / nprof, tms / nprof, fl) for l, (n, tms, fl) in table.items()), key=lambda r: -r[2])
         json.dump({"per_step": [{"kernel": l, "launches": n, "ms": tms, "tflops": (fl * n / (tms * 1e-3) / 1e12 if fl else None)}
