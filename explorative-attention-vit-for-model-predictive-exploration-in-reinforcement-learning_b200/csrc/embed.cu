@@ -239,6 +239,143 @@ __global__ void __launch_bounds__(128) embed_assemble_bwd_pos_kernel(const float
   }
 }
 
+// Both of the above in ONE pass over dx (D = 128 * NV4 <= 1024): a CTA owns one sequence position j and a chunk of samples, its
+// 8 warps take the samples in turn.  For j >= 1 a warp forms the patch-token gradient g[b, j-1] (sum over the sequences) and keeps
+// the row it has just read as its share of dpos[j]; the j = 0 CTAs only sum the token rows (dpos[0], dtokA / dtokB).  The 8 warps'
+// partial sums meet in shared memory and leave as one atomicAdd per (j, column) and chunk -- the position / token gradients no
+// longer re-read the 103 MB the separate kernel streamed with one 512-step strided loop per thread.
+//   LN = true additionally runs the backward of the LayerNorm(D) that ends to_patch_embedding (vit.py:113) on the row the
+// warp holds: g never goes to memory, de = LN'(g) leaves as bf16 (the dY operand of the patch Linear's dW / dX GEMMs), and
+// dgamma / dbeta / the Linear's bias gradient (column sums of de) join the per-CTA partial sums.
+struct EmbedLnBwd {
+  const float* e0;      // LayerNorm input [B*np, D]
+  const float* mean;    // [B*np]
+  const float* rstd;
+  const float* gamma;   // [D]
+  float* dgamma;        // += sum g * xhat
+  float* dbeta;         // += sum g
+  float* dbias;         // += sum de   (may be NULL)
+};
+template <int NV4, bool LN>
+__global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const float* __restrict__ dx, int mode, int B, int np,
+                                                                       float* __restrict__ g, __nv_bfloat16* __restrict__ g_bf16,
+                                                                       float* __restrict__ dpos, float* __restrict__ dtokA,
+                                                                       float* __restrict__ dtokB, int bchunk, const EmbedLnBwd ln) {
+  constexpr int D = 128 * NV4;
+  __shared__ float4 red[8][32 * NV4];
+  const int j = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
+  const int S1 = np + 1;
+  // row of (sequence set q, sample b, position jj) in the flat token matrix; set 1 exists for modes 0 and 2
+  auto row = [&](int q, int b, int jj) -> const float4* {
+    size_t r;
+    if (mode == 0) r = q == 0 ? (size_t)b * np + (jj - 1) : (size_t)B * np + (size_t)b * S1 + jj;
+    else r = (size_t)q * B * S1 + (size_t)b * S1 + jj;
+    return reinterpret_cast<const float4*>(dx + r * D);
+  };
+  // flush the warps' partial sums `acc` to out0 (and out1) with one atomicAdd per column
+  auto flush = [&](const float4* acc, float* out0, float* out1) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) red[w][lane + 32 * i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += reinterpret_cast<const float*>(red[k])[c];
+      atomicAdd(out0 + c, t);
+      if (out1 != nullptr) atomicAdd(out1 + c, t);
+    }
+  };
+  float4 acc[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j == 0) {
+    // token rows: mode 0 -> set 1 (exploitative pass; exploration_token, bug kept), mode 1 -> set 0, mode 2 -> both sets
+    const int nset = mode == 2 ? 2 : 1;
+    for (int q = 0; q < nset; ++q) {
+      const int qs = mode == 0 ? 1 : q;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b = b0 + w; b < b1; b += 8) {
+        const float4* a = row(qs, b, 0);
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) { const float4 v = __ldg(a + lane + 32 * i); acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w; }
+      }
+      flush(acc, dpos, q == 0 ? dtokA : dtokB);
+    }
+    return;
+  }
+  const int n = j - 1;
+  float4 ag[LN ? NV4 : 1], ab[LN ? NV4 : 1], ax[LN ? NV4 : 1], gm[LN ? NV4 : 1];
+  if constexpr (LN) {
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      ag[i] = ab[i] = ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gm[i] = __ldg(reinterpret_cast<const float4*>(ln.gamma) + lane + 32 * i);
+    }
+  }
+  for (int b = b0 + w; b < b1; b += 8) {
+    const float4* a = row(0, b, j);
+    const float4* c2 = mode == 1 ? nullptr : row(1, b, j);
+    const size_t wid = (size_t)b * np + n;
+    float4 v[NV4], xv[LN ? NV4 : 1];
+    float mu = 0.f, rs = 0.f;
+    if constexpr (LN) {
+      mu = __ldg(ln.mean + wid); rs = __ldg(ln.rstd + wid);
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) xv[i] = __ldg(reinterpret_cast<const float4*>(ln.e0 + wid * D) + lane + 32 * i);
+    }
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = __ldg(a + c);
+      float4 pz = v[i];                                // what this position's dpos receives
+      if (c2 != nullptr) {
+        const float4 u = __ldg(c2 + c);
+        v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+        pz = mode == 0 ? u : v[i];                     // mode 0: only the exploitative pass adds the positional embedding
+      }
+      acc[i].x += pz.x; acc[i].y += pz.y; acc[i].z += pz.z; acc[i].w += pz.w;
+      if constexpr (!LN) {
+        if (g != nullptr) *(reinterpret_cast<float4*>(g + wid * D) + c) = v[i];
+        if (g_bf16 != nullptr)
+          *(reinterpret_cast<uint2*>(g_bf16 + wid * D) + c) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+      }
+    }
+    if constexpr (LN) {
+      // dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)), the same evaluation order as layernorm_bwd_kernel
+      float4 gg[NV4], xh[NV4];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const float4 d = v[i];
+        xh[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);
+        gg[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+        s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+        s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      }
+      s1 = warp_sum(s1) / (float)D;
+      s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const float4 o = make_float4(rs * (gg[i].x - s1 - xh[i].x * s2), rs * (gg[i].y - s1 - xh[i].y * s2),
+                                     rs * (gg[i].z - s1 - xh[i].z * s2), rs * (gg[i].w - s1 - xh[i].w * s2));
+        ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
+        *(reinterpret_cast<uint2*>(g_bf16 + wid * D) + lane + 32 * i) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
+  flush(acc, dpos + (size_t)j * D, nullptr);
+  if constexpr (LN) {
+    flush(ag, ln.dgamma, nullptr);
+    flush(ab, ln.dbeta, nullptr);
+    if (ln.dbias != nullptr) flush(ax, ln.dbias, nullptr);
+  }
+}
+
 }  // namespace eavit
 
 using namespace eavit;
@@ -301,10 +438,41 @@ int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, fl
   EAVIT_CHECK_ARG(dx && (g || g_bf16) && dpos && dtokA && B > 0 && np > 0 && D % 4 == 0 && mode >= 0 && mode <= 2);
   EAVIT_CHECK_ARG(mode != 2 || dtokB != nullptr);
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool fused = getenv("EAVIT_NO_EMBED_BWD_FUSED") == nullptr;
+  if (fused && D % 128 == 0 && D <= 1024) {
+    // enough CTAs for a few waves, at least 8 samples per warp-pass so that the partial sums amortise their flush
+    int bchunk = 64;
+    while (bchunk > 8 && (long long)(np + 1) * cdiv(B, bchunk) < 4LL * kNumSMs) bchunk >>= 1;
+    dim3 grid(np + 1, cdiv(B, bchunk));
+#define EAVIT_EAB(NV) embed_assemble_bwd_fused_kernel<NV, false><<<grid, 256, 0, st>>>(dx, mode, B, np, g, (__nv_bfloat16*)g_bf16, dpos, dtokA, dtokB, bchunk, EmbedLnBwd{})
+    switch (D / 128) {
+      case 1: EAVIT_EAB(1); break; case 2: EAVIT_EAB(2); break; case 3: EAVIT_EAB(3); break; case 4: EAVIT_EAB(4); break;
+      case 5: EAVIT_EAB(5); break; case 6: EAVIT_EAB(6); break; case 7: EAVIT_EAB(7); break; default: EAVIT_EAB(8); break;
+    }
+#undef EAVIT_EAB
+    EAVIT_LAUNCH_OK();
+    return EAVIT_OK;
+  }
   embed_assemble_bwd_rows_kernel<<<cdiv((long long)B * np, 8), 256, 0, st>>>(dx, mode, B, np, D, g, (__nv_bfloat16*)g_bf16);
   EAVIT_LAUNCH_OK();
   dim3 grid(np + 1, cdiv(D, 128));
   embed_assemble_bwd_pos_kernel<<<grid, 128, 0, st>>>(dx, mode, B, np, D, dpos, dtokA, dtokB);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_embed_assemble_ln_bwd(const float* dx, int mode, int B, int np, int D, const float* e0, const float* mean,
+                                const float* rstd, const float* gamma, void* de_bf16, float* dgamma, float* dbeta, float* dbias,
+                                float* dpos, float* dtokA, float* dtokB, void* stream) {
+  EAVIT_CHECK_ARG(dx && e0 && mean && rstd && gamma && de_bf16 && dgamma && dbeta && dpos && dtokA && B > 0 && np > 0);
+  EAVIT_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || dtokB != nullptr));
+  EAVIT_CHECK_ARG(D == 256);                         // the row a warp holds (2 x float4 per lane); other widths: the two separate calls
+  int bchunk = 64;
+  while (bchunk > 8 && (long long)(np + 1) * cdiv(B, bchunk) < 4LL * kNumSMs) bchunk >>= 1;
+  dim3 grid(np + 1, cdiv(B, bchunk));
+  const EmbedLnBwd ln{e0, mean, rstd, gamma, dgamma, dbeta, dbias};
+  embed_assemble_bwd_fused_kernel<2, true><<<grid, 256, 0, (cudaStream_t)stream>>>(dx, mode, B, np, nullptr, (__nv_bfloat16*)de_bf16, dpos,
+                                                                                  dtokA, dtokB, bchunk, ln);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }

@@ -220,6 +220,7 @@ class ViTEncoder:
         # LayerNorm and MLP run on the pooled rows only and its attention with one query row per (sequence, head) --
         # identical loss and gradients, a third of the ViT's token-wise work and one of three attention launches removed.
         self.prune_last = os.environ.get("EAVIT_PRUNE_LAST", "1") != "0"
+        self.fuse_embed_bwd = os.environ.get("EAVIT_FUSE_EMBED_BWD", "1") != "0"
         # layer parameter names
         p = prefix
         self.L = []
@@ -566,13 +567,20 @@ class ViTEncoder:
         img, sidx = bf.img, bf.sample_idx
         img_dt = ops._DT[img.dtype]
         if c.impl == "lucidrains":
-            g = bf.get("g_embed", (rows, D), torch.float32)
             tok = p + ("exploration_token" if c.use_explorative else "cls_token")
-            call("eavit_embed_assemble_bwd", dx, self.mode, B, np_, D, g, None, s.g(p + "pos_embedding"), s.g(tok), None)
             de16 = bf.get("de16", (rows, D), torch.bfloat16)
-            call("eavit_layernorm_bwd", g, F32, D, bf.t["e0"], D, bf.t["m3"], bf.t["r3"], s.w(p + "to_patch_embedding.3.weight"),
-                 None, D, None, D, de16, D, s.g(p + "to_patch_embedding.3.weight"), s.g(p + "to_patch_embedding.3.bias"),
-                 s.g(p + "to_patch_embedding.2.bias"), 0.0, 0, rows, D)
+            if D == 256 and self.fuse_embed_bwd:
+                # token / position gradients, the sum over the two passes and the LayerNorm(dim) backward in one pass over dx
+                call("eavit_embed_assemble_ln_bwd", dx, self.mode, B, np_, D, bf.t["e0"], bf.t["m3"], bf.t["r3"],
+                     s.w(p + "to_patch_embedding.3.weight"), de16, s.g(p + "to_patch_embedding.3.weight"),
+                     s.g(p + "to_patch_embedding.3.bias"), s.g(p + "to_patch_embedding.2.bias"), s.g(p + "pos_embedding"),
+                     s.g(tok), None)
+            else:
+                g = bf.get("g_embed", (rows, D), torch.float32)
+                call("eavit_embed_assemble_bwd", dx, self.mode, B, np_, D, g, None, s.g(p + "pos_embedding"), s.g(tok), None)
+                call("eavit_layernorm_bwd", g, F32, D, bf.t["e0"], D, bf.t["m3"], bf.t["r3"], s.w(p + "to_patch_embedding.3.weight"),
+                     None, D, None, D, de16, D, s.g(p + "to_patch_embedding.3.weight"), s.g(p + "to_patch_embedding.3.bias"),
+                     s.g(p + "to_patch_embedding.2.bias"), 0.0, 0, rows, D)
             dpln = bf.get("dpln", (rows, PD), torch.float32)
             linear_bwd(de16, bf.t["pln"], s.b16(p + "to_patch_embedding.2.weight"), dW=s.g(p + "to_patch_embedding.2.weight"),
                        db=None, dx_f32=dpln)

@@ -250,8 +250,18 @@ int eavit_embed_fused_fwd(const void* img, int img_dtype, const long long* sampl
                           int mode, const float* g1, const float* b1, float eps1, const void* w_bf16, const float* bias,
                           const float* g3, const float* b3, float eps3, const float* pos, const float* tok, void* pln_bf16,
                           float* pmean, float* prstd, float* e0, float* m3, float* r3, float* x0, void* stream);
+/* Backward of eavit_embed_assemble (vit.py:141-158; vit_hg.py:121-145): g[b*np+n] = patch-token gradient summed over the
+ * sequences (fp32 and / or bf16), dpos / dtokA / dtokB += the positional / token gradients summed over the samples.  One pass
+ * over dx: a CTA per sequence position and sample chunk (D % 128 == 0, D <= 1024; other widths take two kernels). */
 int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, float* g, void* g_bf16, float* dpos,
                              float* dtokA, float* dtokB, void* stream);
+/* The same pass continued through the LayerNorm(dim) that ends to_patch_embedding (vit.py:113; D == 256): the patch-token
+ * gradient stays in registers, de_bf16 [B*np, D] = LayerNorm'(g) (the dY operand of the patch Linear's dW / dX GEMMs),
+ * dgamma / dbeta += that LayerNorm's parameter gradients, dbias (may be NULL) += column sums of de = the Linear's bias gradient
+ * (vit.py:112).  e0 / mean / rstd: the LayerNorm's input and statistics as the forward stored them. */
+int eavit_embed_assemble_ln_bwd(const float* dx, int mode, int B, int np, int D, const float* e0, const float* mean,
+                                const float* rstd, const float* gamma, void* de_bf16, float* dgamma, float* dbeta, float* dbias,
+                                float* dpos, float* dtokA, float* dtokB, void* stream);
 
 /* ------------------------------------------------------------------ heads + losses (model.py, agents.py) */
 

@@ -66,3 +66,84 @@ def test_train_step_gradients_with_and_without_fused_embedding(monkeypatch):
         torch.cuda.synchronize()
         g[fused] = st.grad.detach().cpu().clone()
     assert rel(g["1"], g["0"]) < 3e-3
+
+
+@pytest.mark.parametrize("mode,B,np_,D", [(0, 5, 196, 256), (1, 7, 196, 256), (2, 9, 49, 1024), (0, 70, 16, 384), (2, 3, 4, 128),
+                                          (0, 512, 196, 256)])
+def test_embed_assemble_bwd_single_pass(mode, B, np_, D):
+    """vit.py:141-158 backward: patch-token gradient summed over the sequences, positional / token gradients summed over the
+    samples -- the one-pass kernel (a CTA per position and sample chunk) against a torch restatement; accumulation into
+    non-zero dpos / dtok buffers (the gradients are +=)."""
+    from eavit_b200.ops import call
+    g = torch.Generator(device="cuda").manual_seed(mode * 100 + B)
+    S1 = np_ + 1
+    T = B * np_ + B * S1 if mode == 0 else (B * S1 if mode == 1 else 2 * B * S1)
+    dx = torch.randn(T, D, device="cuda", generator=g)
+    out = torch.empty(B * np_, D, device="cuda")
+    out16 = torch.empty(B * np_, D, device="cuda", dtype=torch.bfloat16)
+    dpos0 = torch.randn(S1, D, device="cuda", generator=g)
+    dta0, dtb0 = torch.randn(D, device="cuda", generator=g), torch.randn(D, device="cuda", generator=g)
+    dpos, dta, dtb = dpos0.clone(), dta0.clone(), dtb0.clone()
+    call("eavit_embed_assemble_bwd", dx, mode, B, np_, D, out, out16, dpos, dta, dtb if mode == 2 else None)
+    torch.cuda.synchronize()
+    d = dx.double()
+    if mode == 0:
+        a, b = d[: B * np_].view(B, np_, D), d[B * np_:].view(B, S1, D)
+        ref_g, ref_pos, ref_ta, ref_tb = a + b[:, 1:], b.sum(0), b[:, 0].sum(0), None
+    elif mode == 1:
+        a = d.view(B, S1, D)
+        ref_g, ref_pos, ref_ta, ref_tb = a[:, 1:], a.sum(0), a[:, 0].sum(0), None
+    else:
+        a, b = d[: B * S1].view(B, S1, D), d[B * S1:].view(B, S1, D)
+        ref_g, ref_pos, ref_ta, ref_tb = a[:, 1:] + b[:, 1:], (a + b).sum(0), a[:, 0].sum(0), b[:, 0].sum(0)
+    assert torch.equal(out, ref_g.reshape(B * np_, D).float())                   # one fp32 add per element: exact
+    assert torch.equal(out16, ref_g.reshape(B * np_, D).float().bfloat16())
+    tol = 1e-6 * max(1.0, B ** 0.5) * 8
+    assert (dpos.double() - dpos0.double() - ref_pos).abs().max().item() < tol * 4
+    assert (dta.double() - dta0.double() - ref_ta).abs().max().item() < tol * 4
+    if mode == 2:
+        assert (dtb.double() - dtb0.double() - ref_tb).abs().max().item() < tol * 4
+    else:
+        assert torch.equal(dtb, dtb0)
+
+
+@pytest.mark.parametrize("mode,B,np_", [(0, 5, 196), (1, 7, 196), (0, 70, 16), (0, 512, 196)])
+def test_embed_assemble_ln_bwd_single_pass(mode, B, np_):
+    """The same pass continued through the LayerNorm(256) that ends to_patch_embedding (vit.py:113): de, dgamma, dbeta, the
+    Linear's bias gradient and the positional / token gradients against torch autograd in float64."""
+    from eavit_b200.ops import call
+    D = 256
+    g = torch.Generator(device="cuda").manual_seed(7 + mode * 100 + B)
+    S1 = np_ + 1
+    T = B * np_ + B * S1 if mode == 0 else B * S1
+    rows = B * np_
+    dx = torch.randn(T, D, device="cuda", generator=g)
+    e0 = torch.randn(rows, D, device="cuda", generator=g) * 1.7 + 0.3
+    gamma = torch.randn(D, device="cuda", generator=g)
+    mean = e0.double().mean(1)
+    rstd = (e0.double().var(1, unbiased=False) + 1e-5).rsqrt()
+    de16 = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    dgam, dbet, dbias = (torch.randn(D, device="cuda", generator=g) for _ in range(3))
+    dpos = torch.randn(S1, D, device="cuda", generator=g)
+    dtok = torch.randn(D, device="cuda", generator=g)
+    base = [t.double().clone() for t in (dgam, dbet, dbias, dpos, dtok)]
+    call("eavit_embed_assemble_ln_bwd", dx, mode, B, np_, D, e0, mean.float(), rstd.float(), gamma, de16, dgam, dbet, dbias,
+         dpos, dtok, None)
+    torch.cuda.synchronize()
+    d = dx.double()
+    if mode == 0:
+        a, b = d[: B * np_].view(B, np_, D), d[B * np_:].view(B, S1, D)
+        gg, ref_pos, ref_tok = (a + b[:, 1:]).reshape(rows, D), b.sum(0), b[:, 0].sum(0)
+    else:
+        a = d.view(B, S1, D)
+        gg, ref_pos, ref_tok = a[:, 1:].reshape(rows, D), a.sum(0), a[:, 0].sum(0)
+    x = e0.double().requires_grad_(True)
+    gm = gamma.double().requires_grad_(True)
+    bt = torch.zeros(D, dtype=torch.float64, device="cuda", requires_grad=True)
+    y = torch.nn.functional.layer_norm(x, (D,), gm, bt, 1e-5)
+    y.backward(gg)
+    assert rel(de16.double().cpu(), x.grad.cpu()) < 4e-3                                      # bf16 rounding of the output
+    for got, b0, ref in ((dgam, base[0], gm.grad), (dbet, base[1], bt.grad), (dbias, base[2], x.grad.sum(0)),
+                         (dpos, base[3], ref_pos), (dtok, base[4], ref_tok)):
+        err = (got.double() - b0 - ref).abs().max().item()
+        assert err < 2e-5 * max(1.0, ref.abs().max().item()) * max(1.0, rows ** 0.5 / 30), (err, ref.abs().max().item())
