@@ -260,20 +260,29 @@ template <int NV4, bool LN>
 __global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const float* __restrict__ dx, int mode, int B, int np,
                                                                        float* __restrict__ g, __nv_bfloat16* __restrict__ g_bf16,
                                                                        float* __restrict__ dpos, float* __restrict__ dtokA,
-                                                                       float* __restrict__ dtokB, int bchunk, const EmbedLnBwd ln) {
+                                                                       float* __restrict__ dtokB, int bchunk, int nchunk,
+                                                                       const EmbedLnBwd ln, const DropCfg drop) {
   constexpr int D = 128 * NV4;
   __shared__ float4 red[8][32 * NV4];
-  const int j = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S1 = np + 1;
   // row of (sequence set q, sample b, position jj) in the flat token matrix; set 1 exists for modes 0 and 2
-  auto row = [&](int q, int b, int jj) -> const float4* {
-    size_t r;
-    if (mode == 0) r = q == 0 ? (size_t)b * np + (jj - 1) : (size_t)B * np + (size_t)b * S1 + jj;
-    else r = (size_t)q * B * S1 + (size_t)b * S1 + jj;
-    return reinterpret_cast<const float4*>(dx + r * D);
+  auto row = [&](int q, int b, int jj) -> size_t {
+    if (mode == 0) return q == 0 ? (size_t)b * np + (jj - 1) : (size_t)B * np + (size_t)b * S1 + jj;
+    return (size_t)q * B * S1 + (size_t)b * S1 + jj;
   };
-  // flush the warps' partial sums `acc` to out0 (and out1) with one atomicAdd per column
+  // float4 c of token row r under the embedding-dropout mask of the forward (vit.py:158; drop.thresh == 0: none)
+  auto ldrow = [&](size_t r, uint32_t rk, int c) -> float4 {
+    float4 v = __ldg(reinterpret_cast<const float4*>(dx + r * D) + c);
+    if (drop.thresh != 0) {
+      float dm[4];
+      drop4(drop, rk, (uint32_t)(4 * c), dm);
+      v.x *= dm[0]; v.y *= dm[1]; v.z *= dm[2]; v.w *= dm[3];
+    }
+    return v;
+  };
+  auto rkey = [&](size_t r) -> uint32_t { return drop.thresh != 0 ? drop_row_key(drop, (uint32_t)r) : 0u; };
+  // the warps' partial sums `acc` -> out0 (and out1): one atomicAdd per column and call
   auto flush = [&](const float4* acc, float* out0, float* out1) {
     __syncthreads();
 #pragma unroll
@@ -287,94 +296,117 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const flo
       if (out1 != nullptr) atomicAdd(out1 + c, t);
     }
   };
-  float4 acc[NV4];
+  auto zero = [&](float4* acc) {
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (j == 0) {
-    // token rows: mode 0 -> set 1 (exploitative pass; exploration_token, bug kept), mode 1 -> set 0, mode 2 -> both sets
-    const int nset = mode == 2 ? 2 : 1;
-    for (int q = 0; q < nset; ++q) {
-      const int qs = mode == 0 ? 1 : q;
-#pragma unroll
-      for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int b = b0 + w; b < b1; b += 8) {
-        const float4* a = row(qs, b, 0);
-#pragma unroll
-        for (int i = 0; i < NV4; ++i) { const float4 v = __ldg(a + lane + 32 * i); acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w; }
-      }
-      flush(acc, dpos, q == 0 ? dtokA : dtokB);
-    }
-    return;
-  }
-  const int n = j - 1;
+    for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  // LayerNorm partial sums live across every item of this (persistent) CTA: one flush per CTA at the end
   float4 ag[LN ? NV4 : 1], ab[LN ? NV4 : 1], ax[LN ? NV4 : 1], gm[LN ? NV4 : 1];
   if constexpr (LN) {
+    zero(ag); zero(ab); zero(ax);
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) {
-      ag[i] = ab[i] = ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      gm[i] = __ldg(reinterpret_cast<const float4*>(ln.gamma) + lane + 32 * i);
-    }
+    for (int i = 0; i < NV4; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(ln.gamma) + lane + 32 * i);
   }
-  for (int b = b0 + w; b < b1; b += 8) {
-    const float4* a = row(0, b, j);
-    const float4* c2 = mode == 1 ? nullptr : row(1, b, j);
-    const size_t wid = (size_t)b * np + n;
-    float4 v[NV4], xv[LN ? NV4 : 1];
-    float mu = 0.f, rs = 0.f;
-    if constexpr (LN) {
-      mu = __ldg(ln.mean + wid); rs = __ldg(ln.rstd + wid);
+  struct Raw { float4 a[NV4], u[NV4], x[LN ? NV4 : 1]; float mu, rs; };
+  const int items = S1 * nchunk;
+#pragma unroll 1
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int j = item % S1, ch = item / S1;                 // neighbouring CTAs read neighbouring positions of the same samples
+    const int b0 = ch * bchunk, b1 = min(B, b0 + bchunk);
+    float4 acc[NV4];
+    if (j == 0) {
+      // token rows: mode 0 -> set 1 (exploitative pass; exploration_token, bug kept), mode 1 -> set 0, mode 2 -> both sets
+      const int nset = mode == 2 ? 2 : 1;
+      for (int q = 0; q < nset; ++q) {
+        const int qs = mode == 0 ? 1 : q;
+        zero(acc);
+        for (int b = b0 + w; b < b1; b += 8) {
+          const size_t a = row(qs, b, 0);
+          const uint32_t ka = rkey(a);
 #pragma unroll
-      for (int i = 0; i < NV4; ++i) xv[i] = __ldg(reinterpret_cast<const float4*>(ln.e0 + wid * D) + lane + 32 * i);
-    }
-#pragma unroll
-    for (int i = 0; i < NV4; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = __ldg(a + c);
-      float4 pz = v[i];                                // what this position's dpos receives
-      if (c2 != nullptr) {
-        const float4 u = __ldg(c2 + c);
-        v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
-        pz = mode == 0 ? u : v[i];                     // mode 0: only the exploitative pass adds the positional embedding
+          for (int i = 0; i < NV4; ++i) { const float4 v = ldrow(a, ka, lane + 32 * i); acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w; }
+        }
+        flush(acc, dpos, q == 0 ? dtokA : dtokB);
       }
-      acc[i].x += pz.x; acc[i].y += pz.y; acc[i].z += pz.z; acc[i].w += pz.w;
-      if constexpr (!LN) {
-        if (g != nullptr) *(reinterpret_cast<float4*>(g + wid * D) + c) = v[i];
-        if (g_bf16 != nullptr)
-          *(reinterpret_cast<uint2*>(g_bf16 + wid * D) + c) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
-      }
+      continue;
     }
-    if constexpr (LN) {
-      // dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)), the same evaluation order as layernorm_bwd_kernel
-      float4 gg[NV4], xh[NV4];
-      float s1 = 0.f, s2 = 0.f;
+    zero(acc);
+    auto load = [&](int b, Raw& R) {
+      const size_t a = row(0, b, j), c2 = mode == 1 ? 0 : row(1, b, j);
+      const uint32_t ka = rkey(a), k2 = mode == 1 ? 0u : rkey(c2);
+      const size_t wid = (size_t)b * np + (j - 1);
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
-        const float4 d = v[i];
-        xh[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);
-        gg[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
-        s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
-        s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
-        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
-        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        R.a[i] = ldrow(a, ka, lane + 32 * i);
+        if (mode != 1) R.u[i] = ldrow(c2, k2, lane + 32 * i);
+        if constexpr (LN) R.x[i] = __ldg(reinterpret_cast<const float4*>(ln.e0 + wid * D) + lane + 32 * i);
       }
-      s1 = warp_sum(s1) / (float)D;
-      s2 = warp_sum(s2) / (float)D;
+      if constexpr (LN) { R.mu = __ldg(ln.mean + wid); R.rs = __ldg(ln.rstd + wid); }
+    };
+    auto process = [&](int b, const Raw& R) {
+      const size_t wid = (size_t)b * np + (j - 1);
+      float4 v[NV4];
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
-        const float4 o = make_float4(rs * (gg[i].x - s1 - xh[i].x * s2), rs * (gg[i].y - s1 - xh[i].y * s2),
-                                     rs * (gg[i].z - s1 - xh[i].z * s2), rs * (gg[i].w - s1 - xh[i].w * s2));
-        ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
-        *(reinterpret_cast<uint2*>(g_bf16 + wid * D) + lane + 32 * i) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        const int c = lane + 32 * i;
+        v[i] = R.a[i];
+        float4 pz = v[i];                                  // what this position's dpos receives
+        if (mode != 1) {
+          const float4 u = R.u[i];
+          v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+          pz = mode == 0 ? u : v[i];                       // mode 0: only the exploitative pass adds the positional embedding
+        }
+        acc[i].x += pz.x; acc[i].y += pz.y; acc[i].z += pz.z; acc[i].w += pz.w;
+        if constexpr (!LN) {
+          if (g != nullptr) *(reinterpret_cast<float4*>(g + wid * D) + c) = v[i];
+          if (g_bf16 != nullptr)
+            *(reinterpret_cast<uint2*>(g_bf16 + wid * D) + c) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+        }
       }
+      if constexpr (LN) {
+        // dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)), the same evaluation order as layernorm_bwd_kernel
+        const float mu = R.mu, rs = R.rs;
+        float4 gg[NV4], xh[NV4];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) {
+          const float4 d = v[i], xv = R.x[i];
+          xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+          gg[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+          s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+          s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+          ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+          ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        }
+        s1 = warp_sum(s1) / (float)D;
+        s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) {
+          const float4 o = make_float4(rs * (gg[i].x - s1 - xh[i].x * s2), rs * (gg[i].y - s1 - xh[i].y * s2),
+                                       rs * (gg[i].z - s1 - xh[i].z * s2), rs * (gg[i].w - s1 - xh[i].w * s2));
+          ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
+          *(reinterpret_cast<uint2*>(g_bf16 + wid * D) + lane + 32 * i) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
+      }
+    };
+    // two samples per warp in flight: the second one's rows are requested before the first one is reduced
+    for (int b = b0 + w; b < b1; b += 16) {
+      Raw A, Bn;
+      load(b, A);
+      const bool two = b + 8 < b1;
+      if (two) load(b + 8, Bn);
+      process(b, A);
+      if (two) process(b + 8, Bn);
     }
+    flush(acc, dpos + (size_t)j * D, nullptr);
   }
-  flush(acc, dpos + (size_t)j * D, nullptr);
   if constexpr (LN) {
     flush(ag, ln.dgamma, nullptr);
     flush(ab, ln.dbeta, nullptr);
     if (ln.dbias != nullptr) flush(ax, ln.dbias, nullptr);
   }
 }
+
 
 }  // namespace eavit
 
@@ -433,6 +465,19 @@ int eavit_embed_assemble(const float* e, const float* pos, const float* tokA, co
   return EAVIT_OK;
 }
 
+// work items of the one-pass embedding backward: (position, chunk of samples); chunks of 64 samples (8 per warp) unless that
+// leaves fewer items than a few per co-resident CTA; a persistent grid of two CTAs per SM walks them
+struct EabGrid { int bchunk, nchunk, grid; };
+static EabGrid eab_grid(int B, int np) {
+  EabGrid e;
+  e.bchunk = 64;
+  while (e.bchunk > 16 && (long long)(np + 1) * cdiv(B, e.bchunk) < 8LL * kNumSMs) e.bchunk >>= 1;
+  e.nchunk = cdiv(B, e.bchunk);
+  const long long items = (long long)(np + 1) * e.nchunk;
+  e.grid = (int)(items < 2LL * kNumSMs ? items : 2LL * kNumSMs);
+  return e;
+}
+
 int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, float* g, void* g_bf16, float* dpos,
                              float* dtokA, float* dtokB, void* stream) {
   EAVIT_CHECK_ARG(dx && (g || g_bf16) && dpos && dtokA && B > 0 && np > 0 && D % 4 == 0 && mode >= 0 && mode <= 2);
@@ -441,10 +486,8 @@ int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, fl
   static const bool fused = getenv("EAVIT_NO_EMBED_BWD_FUSED") == nullptr;
   if (fused && D % 128 == 0 && D <= 1024) {
     // enough CTAs for a few waves, at least 8 samples per warp-pass so that the partial sums amortise their flush
-    int bchunk = 64;
-    while (bchunk > 8 && (long long)(np + 1) * cdiv(B, bchunk) < 4LL * kNumSMs) bchunk >>= 1;
-    dim3 grid(np + 1, cdiv(B, bchunk));
-#define EAVIT_EAB(NV) embed_assemble_bwd_fused_kernel<NV, false><<<grid, 256, 0, st>>>(dx, mode, B, np, g, (__nv_bfloat16*)g_bf16, dpos, dtokA, dtokB, bchunk, EmbedLnBwd{})
+    const EabGrid eg = eab_grid(B, np);
+#define EAVIT_EAB(NV) embed_assemble_bwd_fused_kernel<NV, false><<<eg.grid, 256, 0, st>>>(dx, mode, B, np, g, (__nv_bfloat16*)g_bf16, dpos, dtokA, dtokB, eg.bchunk, eg.nchunk, EmbedLnBwd{}, make_drop(0.f, 0))
     switch (D / 128) {
       case 1: EAVIT_EAB(1); break; case 2: EAVIT_EAB(2); break; case 3: EAVIT_EAB(3); break; case 4: EAVIT_EAB(4); break;
       case 5: EAVIT_EAB(5); break; case 6: EAVIT_EAB(6); break; case 7: EAVIT_EAB(7); break; default: EAVIT_EAB(8); break;
@@ -463,16 +506,16 @@ int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, fl
 
 int eavit_embed_assemble_ln_bwd(const float* dx, int mode, int B, int np, int D, const float* e0, const float* mean,
                                 const float* rstd, const float* gamma, void* de_bf16, float* dgamma, float* dbeta, float* dbias,
-                                float* dpos, float* dtokA, float* dtokB, void* stream) {
+                                float* dpos, float* dtokA, float* dtokB, float drop_p, unsigned long long drop_seed,
+                                void* stream) {
   EAVIT_CHECK_ARG(dx && e0 && mean && rstd && gamma && de_bf16 && dgamma && dbeta && dpos && dtokA && B > 0 && np > 0);
   EAVIT_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || dtokB != nullptr));
   EAVIT_CHECK_ARG(D == 256);                         // the row a warp holds (2 x float4 per lane); other widths: the two separate calls
-  int bchunk = 64;
-  while (bchunk > 8 && (long long)(np + 1) * cdiv(B, bchunk) < 4LL * kNumSMs) bchunk >>= 1;
-  dim3 grid(np + 1, cdiv(B, bchunk));
+  const EabGrid eg = eab_grid(B, np);
   const EmbedLnBwd ln{e0, mean, rstd, gamma, dgamma, dbeta, dbias};
-  embed_assemble_bwd_fused_kernel<2, true><<<grid, 256, 0, (cudaStream_t)stream>>>(dx, mode, B, np, nullptr, (__nv_bfloat16*)de_bf16, dpos,
-                                                                                  dtokA, dtokB, bchunk, ln);
+  embed_assemble_bwd_fused_kernel<2, true><<<eg.grid, 256, 0, (cudaStream_t)stream>>>(dx, mode, B, np, nullptr, (__nv_bfloat16*)de_bf16, dpos,
+                                                                                     dtokA, dtokB, eg.bchunk, eg.nchunk, ln,
+                                                                                     make_drop(drop_p, drop_seed));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }

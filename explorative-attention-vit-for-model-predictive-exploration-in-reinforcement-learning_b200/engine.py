@@ -561,7 +561,8 @@ class ViTEncoder:
                 on_layer_done(li)
         # embedding (dropout after the positional add, vit.py:158)
         pe, se = self._site(bf, 0, self.SITE_EMB)
-        if pe > 0:
+        fused_bwd = c.impl == "lucidrains" and D == 256 and self.fuse_embed_bwd
+        if pe > 0 and not fused_bwd:                       # the fused backward reads dx under the mask itself
             call("eavit_dropout_apply", dx, D, None, 0, dx, D, T, D, pe, se)
         rows = B * np_
         img, sidx = bf.img, bf.sample_idx
@@ -569,12 +570,12 @@ class ViTEncoder:
         if c.impl == "lucidrains":
             tok = p + ("exploration_token" if c.use_explorative else "cls_token")
             de16 = bf.get("de16", (rows, D), torch.bfloat16)
-            if D == 256 and self.fuse_embed_bwd:
+            if fused_bwd:
                 # token / position gradients, the sum over the two passes and the LayerNorm(dim) backward in one pass over dx
                 call("eavit_embed_assemble_ln_bwd", dx, self.mode, B, np_, D, bf.t["e0"], bf.t["m3"], bf.t["r3"],
                      s.w(p + "to_patch_embedding.3.weight"), de16, s.g(p + "to_patch_embedding.3.weight"),
                      s.g(p + "to_patch_embedding.3.bias"), s.g(p + "to_patch_embedding.2.bias"), s.g(p + "pos_embedding"),
-                     s.g(tok), None)
+                     s.g(tok), None, pe, se)
             else:
                 g = bf.get("g_embed", (rows, D), torch.float32)
                 call("eavit_embed_assemble_bwd", dx, self.mode, B, np_, D, g, None, s.g(p + "pos_embedding"), s.g(tok), None)

@@ -259,7 +259,7 @@ _SPECS = {
     "eavit_embed_assemble": "ppppiiiip",
     "eavit_embed_fused_fwd": "pipiiiii" "ppf" "pp" "ppf" "pp" "ppp" "ppp" "p",
     "eavit_embed_assemble_bwd": "piiiippppp",
-    "eavit_embed_assemble_ln_bwd": "piiii" "pppp" "pppp" "ppp",
+    "eavit_embed_assemble_ln_bwd": "piiii" "pppp" "pppp" "ppp" "fu",
     "eavit_sgemm_small": "pliplippplliiii".replace("ll", "l", 0),
     "eavit_heads_value_fwd": "ppppppiiip",
     "eavit_heads_value_bwd": "pppppiiipppppp",

@@ -258,10 +258,12 @@ int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, fl
 /* The same pass continued through the LayerNorm(dim) that ends to_patch_embedding (vit.py:113; D == 256): the patch-token
  * gradient stays in registers, de_bf16 [B*np, D] = LayerNorm'(g) (the dY operand of the patch Linear's dW / dX GEMMs),
  * dgamma / dbeta += that LayerNorm's parameter gradients, dbias (may be NULL) += column sums of de = the Linear's bias gradient
- * (vit.py:112).  e0 / mean / rstd: the LayerNorm's input and statistics as the forward stored them. */
+ * (vit.py:112).  e0 / mean / rstd: the LayerNorm's input and statistics as the forward stored them.  drop_p > 0: dx is read
+ * under the embedding-dropout mask of the forward (vit.py:158; rows = flat token rows) instead of being masked in place first. */
 int eavit_embed_assemble_ln_bwd(const float* dx, int mode, int B, int np, int D, const float* e0, const float* mean,
                                 const float* rstd, const float* gamma, void* de_bf16, float* dgamma, float* dbeta, float* dbias,
-                                float* dpos, float* dtokA, float* dtokB, void* stream);
+                                float* dpos, float* dtokA, float* dtokB, float drop_p, unsigned long long drop_seed,
+                                void* stream);
 
 /* ------------------------------------------------------------------ heads + losses (model.py, agents.py) */
 

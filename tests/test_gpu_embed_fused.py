@@ -107,11 +107,15 @@ def test_embed_assemble_bwd_single_pass(mode, B, np_, D):
         assert torch.equal(dtb, dtb0)
 
 
-@pytest.mark.parametrize("mode,B,np_", [(0, 5, 196), (1, 7, 196), (0, 70, 16), (0, 512, 196)])
-def test_embed_assemble_ln_bwd_single_pass(mode, B, np_):
+@pytest.mark.parametrize("mode,B,np_,p", [(0, 5, 196, 0.0), (1, 7, 196, 0.0), (0, 70, 16, 0.1), (1, 9, 49, 0.25), (0, 512, 196, 0.0),
+                                          (0, 512, 196, 0.1)])
+def test_embed_assemble_ln_bwd_single_pass(mode, B, np_, p):
     """The same pass continued through the LayerNorm(256) that ends to_patch_embedding (vit.py:113): de, dgamma, dbeta, the
-    Linear's bias gradient and the positional / token gradients against torch autograd in float64."""
+    Linear's bias gradient and the positional / token gradients against torch autograd in float64.  p > 0: dx is read under the
+    embedding-dropout mask (vit.py:158) -- the reference multiplies dx by the materialised mask first."""
+    from eavit_b200 import ops
     from eavit_b200.ops import call
+    seed = 0x1234_5678_9ABC_DEF0 + B
     D = 256
     g = torch.Generator(device="cuda").manual_seed(7 + mode * 100 + B)
     S1 = np_ + 1
@@ -128,9 +132,13 @@ def test_embed_assemble_ln_bwd_single_pass(mode, B, np_):
     dtok = torch.randn(D, device="cuda", generator=g)
     base = [t.double().clone() for t in (dgam, dbet, dbias, dpos, dtok)]
     call("eavit_embed_assemble_ln_bwd", dx, mode, B, np_, D, e0, mean.float(), rstd.float(), gamma, de16, dgam, dbet, dbias,
-         dpos, dtok, None)
+         dpos, dtok, None, float(p), seed)
     torch.cuda.synchronize()
     d = dx.double()
+    if p > 0:
+        m = ops.dropout_mask(T, D, p, seed)
+        assert 0.5 * p < float((m == 0).float().mean()) < 1.5 * p
+        d = (dx * m).double()                                                     # one fp32 multiply, as in the kernel
     if mode == 0:
         a, b = d[: B * np_].view(B, np_, D), d[B * np_:].view(B, S1, D)
         gg, ref_pos, ref_tok = (a + b[:, 1:]).reshape(rows, D), b.sum(0), b[:, 0].sum(0)
