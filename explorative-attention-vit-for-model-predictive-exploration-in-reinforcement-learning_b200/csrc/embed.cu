@@ -465,6 +465,32 @@ int eavit_embed_assemble(const float* e, const float* pos, const float* tokA, co
   return EAVIT_OK;
 }
 
+// see include/eavit_b200.h: eavit_patch_ln_fold_bwd.  One CTA per input column k, thread j per output row (N <= 1024).
+__global__ void __launch_bounds__(1024) patch_ln_fold_bwd_kernel(const float* __restrict__ G, const float* __restrict__ sv,
+                                                                 const float* __restrict__ W, const float* __restrict__ g1,
+                                                                 const float* __restrict__ b1, float* __restrict__ dW,
+                                                                 float* __restrict__ dbias, float* __restrict__ dg1,
+                                                                 float* __restrict__ db1, int N, int K) {
+  __shared__ float ra[32], rb[32];
+  const int k = blockIdx.x, j = threadIdx.x;
+  float a = 0.f, b = 0.f;
+  if (j < N) {
+    const float gjk = G[(size_t)j * K + k], sj = sv[j], w = W[(size_t)j * K + k];
+    dW[(size_t)j * K + k] += fmaf(g1[k], gjk, b1[k] * sj);
+    if (k == 0) dbias[j] += sj;
+    a = w * gjk; b = w * sj;
+  }
+  a = eavit::warp_sum(a); b = eavit::warp_sum(b);
+  if ((j & 31) == 0) { ra[j >> 5] = a; rb[j >> 5] = b; }
+  __syncthreads();
+  if (j < 32) {
+    const int nw = (blockDim.x + 31) >> 5;
+    a = j < nw ? ra[j] : 0.f; b = j < nw ? rb[j] : 0.f;
+    a = eavit::warp_sum(a); b = eavit::warp_sum(b);
+    if (j == 0) { dg1[k] += a; db1[k] += b; }
+  }
+}
+
 // work items of the one-pass embedding backward: (position, chunk of samples); chunks of 64 samples (8 per warp) unless that
 // leaves fewer items than a few per co-resident CTA; a persistent grid of two CTAs per SM walks them
 struct EabGrid { int bchunk, nchunk, grid; };
@@ -500,6 +526,14 @@ int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, fl
   EAVIT_LAUNCH_OK();
   dim3 grid(np + 1, cdiv(D, 128));
   embed_assemble_bwd_pos_kernel<<<grid, 128, 0, st>>>(dx, mode, B, np, D, dpos, dtokA, dtokB);
+  EAVIT_LAUNCH_OK();
+  return EAVIT_OK;
+}
+
+int eavit_patch_ln_fold_bwd(const float* G, const float* s, const float* W, const float* g1, const float* b1, float* dW,
+                            float* dbias, float* dg1, float* db1, int N, int K, void* stream) {
+  EAVIT_CHECK_ARG(G && s && W && g1 && b1 && dW && dbias && dg1 && db1 && N > 0 && N <= 1024 && K > 0);
+  patch_ln_fold_bwd_kernel<<<K, ((N + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(G, s, W, g1, b1, dW, dbias, dg1, db1, N, K);
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }

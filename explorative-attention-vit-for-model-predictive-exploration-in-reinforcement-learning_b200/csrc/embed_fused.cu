@@ -64,6 +64,7 @@ struct Params {
   float* e0; float *m3, *r3;
   float* x0;                                   // flat residual stream
   int rows, tiles;
+  int pln_xhat;                                // pln receives the normalised patch WITHOUT the LayerNorm's affine (see the ABI comment)
 };
 
 template <typename ImgT>
@@ -218,7 +219,8 @@ __global__ void __launch_bounds__(THREADS, 1) embed_fused_kernel(const __grid_co
             const uint32_t pk = pack_bf16x2((v[i][0] - mu) * rs * g1v[i][0] + b1v[i][0], (v[i][1] - mu) * rs * g1v[i][1] + b1v[i][1]);
             // element k of k-block i: byte 4 lane of the 128-byte row = chunk lane / 4, offset (lane & 3) * 4
             *reinterpret_cast<uint32_t*>(A + i * (TILE_M * 128) + sw_off(tr, lane >> 2) + (lane & 3) * 4) = pk;
-            *reinterpret_cast<uint32_t*>(p.pln + (size_t)row * p.PD + 2 * lane + 64 * i) = pk;
+            *reinterpret_cast<uint32_t*>(p.pln + (size_t)row * p.PD + 2 * lane + 64 * i) =
+                p.pln_xhat ? pack_bf16x2((v[i][0] - mu) * rs, (v[i][1] - mu) * rs) : pk;
           }
         }
       };
@@ -404,7 +406,7 @@ extern "C" int eavit_embed_fused_fwd(const void* img, int img_dtype, const long 
                                      const float* g1, const float* b1, float eps1, const void* w_bf16, const float* bias,
                                      const float* g3, const float* b3, float eps3, const float* pos, const float* tok,
                                      void* pln_bf16, float* pmean, float* prstd, float* e0, float* m3, float* r3, float* x0,
-                                     void* stream) {
+                                     int pln_xhat, void* stream) {
   EAVIT_CHECK_ARG(img && g1 && b1 && w_bf16 && bias && g3 && b3 && pos && tok && pln_bf16 && pmean && prstd && e0 && m3 && r3 && x0);
   EAVIT_CHECK_ARG(B > 0 && C > 0 && P > 0 && HW % P == 0 && (mode == 0 || mode == 1));
   EAVIT_CHECK_ARG(img_dtype == EAVIT_U8 || img_dtype == EAVIT_F32);
@@ -422,6 +424,7 @@ extern "C" int eavit_embed_fused_fwd(const void* img, int img_dtype, const long 
   p.g1 = g1; p.b1 = b1; p.eps1 = eps1; p.bias = bias; p.g3 = g3; p.b3 = b3; p.eps3 = eps3; p.pos = pos; p.tok = tok;
   p.pln = reinterpret_cast<__nv_bfloat16*>(pln_bf16); p.pmean = pmean; p.prstd = prstd; p.e0 = e0; p.m3 = m3; p.r3 = r3; p.x0 = x0;
   p.rows = B * np;
+  p.pln_xhat = pln_xhat;
   p.tiles = cdiv(p.rows, ef::TILE_M);
   const int grid = p.tiles < kNumSMs ? p.tiles : kNumSMs;
   static bool attr_done = false;

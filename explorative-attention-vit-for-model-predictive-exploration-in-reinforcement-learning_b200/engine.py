@@ -318,6 +318,7 @@ class ViTEncoder:
         x0 = bf.get("x0", (T, D), torch.float32)
         fused_embed = (c.impl == "lucidrains" and D == 256 and PD % 16 == 0 and PD <= 192 and c.channels * c.patch * c.image <= 2080
                        and os.environ.get("EAVIT_FUSE_EMBED", "1") == "1")
+        bf.pln_is_xhat = bool(fused_embed and self.fuse_embed_bwd)      # which backward of the patch Linear matches `pln`
         if fused_embed:
             # patchify + LayerNorm(PD) + Linear + LayerNorm(D) + token / position assembly: one kernel (csrc/embed_fused.cu)
             pm, pr = bf.get("pmean", (rows,), torch.float32), bf.get("prstd", (rows,), torch.float32)
@@ -327,7 +328,7 @@ class ViTEncoder:
                  s.w(p + "to_patch_embedding.1.weight"), s.w(p + "to_patch_embedding.1.bias"), 1e-5,
                  s.b16(p + "to_patch_embedding.2.weight"), s.w(p + "to_patch_embedding.2.bias"),
                  s.w(p + "to_patch_embedding.3.weight"), s.w(p + "to_patch_embedding.3.bias"), 1e-5,
-                 s.w(p + "pos_embedding"), tokA, pln, pm, pr, e0, m3, r3, x0)
+                 s.w(p + "pos_embedding"), tokA, pln, pm, pr, e0, m3, r3, x0, int(self.fuse_embed_bwd))
         elif c.impl == "lucidrains":
             pm, pr = bf.get("pmean", (rows,), torch.float32), bf.get("prstd", (rows,), torch.float32)
             call("eavit_patchify", img, img_dt, sample_idx, B, c.channels, c.image, c.patch, 0,
@@ -570,24 +571,39 @@ class ViTEncoder:
         if c.impl == "lucidrains":
             tok = p + ("exploration_token" if c.use_explorative else "cls_token")
             de16 = bf.get("de16", (rows, D), torch.bfloat16)
+            fold = fused_bwd and getattr(bf, "pln_is_xhat", False)
+            if fold:
+                # `pln` holds xhat (no affine) and the frames need no gradient: G = de^T xhat and s = colsum(de) give the Linear's
+                # weight / bias gradient AND LayerNorm(patch_dim)'s dgamma / dbeta (eavit_patch_ln_fold_bwd) -- no dX GEMM, no
+                # second pass over the frames
+                gs = bf.get("embed_G_s", (D * PD + D,), torch.float32)
+                call("eavit_zero", gs, gs.numel() * 4)
+                G, sv = gs[: D * PD].view(D, PD), gs[D * PD:]
             if fused_bwd:
                 # token / position gradients, the sum over the two passes and the LayerNorm(dim) backward in one pass over dx
                 call("eavit_embed_assemble_ln_bwd", dx, self.mode, B, np_, D, bf.t["e0"], bf.t["m3"], bf.t["r3"],
                      s.w(p + "to_patch_embedding.3.weight"), de16, s.g(p + "to_patch_embedding.3.weight"),
-                     s.g(p + "to_patch_embedding.3.bias"), s.g(p + "to_patch_embedding.2.bias"), s.g(p + "pos_embedding"),
-                     s.g(tok), None, pe, se)
+                     s.g(p + "to_patch_embedding.3.bias"), sv if fold else s.g(p + "to_patch_embedding.2.bias"),
+                     s.g(p + "pos_embedding"), s.g(tok), None, pe, se)
             else:
                 g = bf.get("g_embed", (rows, D), torch.float32)
                 call("eavit_embed_assemble_bwd", dx, self.mode, B, np_, D, g, None, s.g(p + "pos_embedding"), s.g(tok), None)
                 call("eavit_layernorm_bwd", g, F32, D, bf.t["e0"], D, bf.t["m3"], bf.t["r3"], s.w(p + "to_patch_embedding.3.weight"),
                      None, D, None, D, de16, D, s.g(p + "to_patch_embedding.3.weight"), s.g(p + "to_patch_embedding.3.bias"),
                      s.g(p + "to_patch_embedding.2.bias"), 0.0, 0, rows, D)
-            dpln = bf.get("dpln", (rows, PD), torch.float32)
-            linear_bwd(de16, bf.t["pln"], s.b16(p + "to_patch_embedding.2.weight"), dW=s.g(p + "to_patch_embedding.2.weight"),
-                       db=None, dx_f32=dpln)
-            call("eavit_patchify_ln_bwd", img, img_dt, sidx, B, c.channels, c.image, c.patch, 0,
-                 s.w(p + "to_patch_embedding.1.weight"), bf.t["pmean"], bf.t["prstd"], dpln,
-                 s.g(p + "to_patch_embedding.1.weight"), s.g(p + "to_patch_embedding.1.bias"))
+            if fold:
+                ops.gemm(de16, bf.t["pln"], a_mn=True, b_mn=True, out_f32=G, atomic=True, split_k=_split_k(D, PD, rows))
+                call("eavit_patch_ln_fold_bwd", G, sv, s.w(p + "to_patch_embedding.2.weight"), s.w(p + "to_patch_embedding.1.weight"),
+                     s.w(p + "to_patch_embedding.1.bias"), s.g(p + "to_patch_embedding.2.weight"),
+                     s.g(p + "to_patch_embedding.2.bias"), s.g(p + "to_patch_embedding.1.weight"),
+                     s.g(p + "to_patch_embedding.1.bias"), D, PD)
+            else:
+                dpln = bf.get("dpln", (rows, PD), torch.float32)
+                linear_bwd(de16, bf.t["pln"], s.b16(p + "to_patch_embedding.2.weight"), dW=s.g(p + "to_patch_embedding.2.weight"),
+                           db=None, dx_f32=dpln)
+                call("eavit_patchify_ln_bwd", img, img_dt, sidx, B, c.channels, c.image, c.patch, 0,
+                     s.w(p + "to_patch_embedding.1.weight"), bf.t["pmean"], bf.t["prstd"], dpln,
+                     s.g(p + "to_patch_embedding.1.weight"), s.g(p + "to_patch_embedding.1.bias"))
         else:
             e = p + "embeddings."
             g16 = bf.get("de16", (rows, D), torch.bfloat16)

@@ -257,7 +257,8 @@ _SPECS = {
     "eavit_patchify": "pipiiiiippfppp",
     "eavit_patchify_ln_bwd": "pipiiiiipppppp",
     "eavit_embed_assemble": "ppppiiiip",
-    "eavit_embed_fused_fwd": "pipiiiii" "ppf" "pp" "ppf" "pp" "ppp" "ppp" "p",
+    "eavit_embed_fused_fwd": "pipiiiii" "ppf" "pp" "ppf" "pp" "ppp" "ppp" "p" "i",
+    "eavit_patch_ln_fold_bwd": "ppppp" "pppp" "ii",
     "eavit_embed_assemble_bwd": "piiiippppp",
     "eavit_embed_assemble_ln_bwd": "piiii" "pppp" "pppp" "ppp" "fu",
     "eavit_sgemm_small": "pliplippplliiii".replace("ll", "l", 0),

@@ -245,11 +245,19 @@ int eavit_embed_assemble(const float* e, const float* pos, const float* tokA, co
  * patch_dim <= 192, dim == 256): vit.py:109-114 to_patch_embedding (Rearrange, LayerNorm(patch_dim), Linear, LayerNorm(dim)) +
  * vit.py:141-158 token prepend / positional add.  Image rows staged in shared memory, LayerNorm'ed patches written straight into
  * the swizzled A tile of a tcgen05 GEMM whose weight is TMA-loaded once per CTA, LayerNorm(dim) + assembly in the epilogue.
- * Also writes what the backward needs: pln bf16 [B*np, PD] (+ pmean, prstd), e0 fp32 [B*np, 256] (+ m3, r3). */
+ * Also writes what the backward needs: pln bf16 [B*np, PD] (+ pmean, prstd), e0 fp32 [B*np, 256] (+ m3, r3).
+ * pln_xhat != 0: pln receives the normalised patch xhat WITHOUT LayerNorm(patch_dim)'s affine (the GEMM still multiplies
+ * g1 * xhat + b1): with G = dE^T xhat the Linear's weight gradient and that LayerNorm's dgamma / dbeta all follow from one
+ * weight-gradient GEMM (eavit_patch_ln_fold_bwd) -- no dX GEMM and no second pass over the frames. */
 int eavit_embed_fused_fwd(const void* img, int img_dtype, const long long* sample_idx /* may be NULL */, int B, int C, int HW, int P,
                           int mode, const float* g1, const float* b1, float eps1, const void* w_bf16, const float* bias,
                           const float* g3, const float* b3, float eps3, const float* pos, const float* tok, void* pln_bf16,
-                          float* pmean, float* prstd, float* e0, float* m3, float* r3, float* x0, void* stream);
+                          float* pmean, float* prstd, float* e0, float* m3, float* r3, float* x0, int pln_xhat, void* stream);
+/* Backward of y = W (g1 * xhat + b1) + bias (vit.py:111-112: LayerNorm(patch_dim) then Linear) when the INPUT needs no gradient
+ * (the frames): with G [N, K] = dY^T xhat (one split-K GEMM) and s [N] = column sums of dY,
+ *   dW[j,k] += g1[k] G[j,k] + b1[k] s[j],   dbias[j] += s[j],   dg1[k] += sum_j W[j,k] G[j,k],   db1[k] += sum_j W[j,k] s[j]. */
+int eavit_patch_ln_fold_bwd(const float* G, const float* s, const float* W, const float* g1, const float* b1, float* dW,
+                            float* dbias, float* dg1, float* db1, int N, int K, void* stream);
 /* Backward of eavit_embed_assemble (vit.py:141-158; vit_hg.py:121-145): g[b*np+n] = patch-token gradient summed over the
  * sequences (fp32 and / or bf16), dpos / dtokA / dtokB += the positional / token gradients summed over the samples.  One pass
  * over dx: a CTA per sequence position and sample chunk (D % 128 == 0, D <= 1024; other widths take two kernels). */
