@@ -256,12 +256,25 @@ struct EmbedLnBwd {
   float* dbeta;         // += sum g
   float* dbias;         // += sum de   (may be NULL)
 };
-template <int NV4, bool LN>
-__global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const float* __restrict__ dx, int mode, int B, int np,
+//   L1 = true puts one more LayerNorm backward IN FRONT of the pass: the first transformer layer's pre-attention LayerNorm
+// (vit.py:47 of layer 0).  `dx` then is the residual gradient arriving at that LayerNorm's input (dres), and the gradient of
+// the embedding output is formed per row as dres + LN1'(dy) from dy (bf16, the QKV dX GEMM's output), the LayerNorm's input x
+// (the embedding output itself) and its statistics -- the [T, D] fp32 gradient never makes the round trip through memory.
+struct EmbedLn1Bwd {
+  const __nv_bfloat16* dy;   // [T, D]
+  const float* x;            // [T, D]
+  const float* mean;         // [T]
+  const float* rstd;
+  const float* gamma;        // [D]
+  float* dgamma;
+  float* dbeta;
+};
+template <int NV4, bool LN, bool L1>
+__global__ void __launch_bounds__(256, (LN && NV4 <= 2) ? 2 : 1) embed_assemble_bwd_fused_kernel(const float* __restrict__ dx, int mode, int B, int np,
                                                                        float* __restrict__ g, __nv_bfloat16* __restrict__ g_bf16,
                                                                        float* __restrict__ dpos, float* __restrict__ dtokA,
                                                                        float* __restrict__ dtokB, int bchunk, int nchunk,
-                                                                       const EmbedLnBwd ln, const DropCfg drop) {
+                                                                       const EmbedLnBwd ln, const EmbedLn1Bwd l1, const DropCfg drop) {
   constexpr int D = 128 * NV4;
   __shared__ float4 red[8][32 * NV4];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -271,17 +284,70 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const flo
     if (mode == 0) return q == 0 ? (size_t)b * np + (jj - 1) : (size_t)B * np + (size_t)b * S1 + jj;
     return (size_t)q * B * S1 + (size_t)b * S1 + jj;
   };
-  // float4 c of token row r under the embedding-dropout mask of the forward (vit.py:158; drop.thresh == 0: none)
-  auto ldrow = [&](size_t r, uint32_t rk, int c) -> float4 {
-    float4 v = __ldg(reinterpret_cast<const float4*>(dx + r * D) + c);
-    if (drop.thresh != 0) {
-      float dm[4];
-      drop4(drop, rk, (uint32_t)(4 * c), dm);
-      v.x *= dm[0]; v.y *= dm[1]; v.z *= dm[2]; v.w *= dm[3];
-    }
-    return v;
+  auto zero = [&](float4* acc) {
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  auto rkey = [&](size_t r) -> uint32_t { return drop.thresh != 0 ? drop_row_key(drop, (uint32_t)r) : 0u; };
+  // partial sums that live across every item of this (persistent) CTA: one flush per CTA at the end
+  float4 ag[LN ? NV4 : 1], ab[LN ? NV4 : 1], ax[LN ? NV4 : 1], gm[LN ? NV4 : 1];
+  float4 ag1[L1 ? NV4 : 1], ab1[L1 ? NV4 : 1], gm1[L1 ? NV4 : 1];
+  if constexpr (LN) {
+    zero(ag); zero(ab); zero(ax);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(ln.gamma) + lane + 32 * i);
+  }
+  if constexpr (L1) {
+    zero(ag1); zero(ab1);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) gm1[i] = __ldg(reinterpret_cast<const float4*>(l1.gamma) + lane + 32 * i);
+  }
+  // one token row of the embedding-output gradient: requested by `load_row`, completed (LayerNorm-1 backward, dropout mask of
+  // the forward's embedding dropout, vit.py:158) by `finish_row` -- warp-collective
+  struct Row { float4 a[NV4]; uint2 dy[L1 ? NV4 : 1]; float4 x[L1 ? NV4 : 1]; float mu, rs; };
+  auto load_row = [&](size_t r, Row& R) {
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      R.a[i] = __ldg(reinterpret_cast<const float4*>(dx + r * D) + lane + 32 * i);
+      if constexpr (L1) {
+        R.dy[i] = __ldg(reinterpret_cast<const uint2*>(l1.dy + r * D) + lane + 32 * i);
+        R.x[i] = __ldg(reinterpret_cast<const float4*>(l1.x + r * D) + lane + 32 * i);
+      }
+    }
+    if constexpr (L1) { R.mu = __ldg(l1.mean + r); R.rs = __ldg(l1.rstd + r); }
+  };
+  auto finish_row = [&](size_t r, Row& R) {
+    if constexpr (L1) {
+      float4 gg[NV4], xh[NV4];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const float2 lo = unpack_bf16x2(R.dy[i].x), hi = unpack_bf16x2(R.dy[i].y);
+        const float4 d = make_float4(lo.x, lo.y, hi.x, hi.y), xv = R.x[i];
+        xh[i] = make_float4((xv.x - R.mu) * R.rs, (xv.y - R.mu) * R.rs, (xv.z - R.mu) * R.rs, (xv.w - R.mu) * R.rs);
+        gg[i] = make_float4(d.x * gm1[i].x, d.y * gm1[i].y, d.z * gm1[i].z, d.w * gm1[i].w);
+        s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+        s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+        ag1[i].x += d.x * xh[i].x; ag1[i].y += d.y * xh[i].y; ag1[i].z += d.z * xh[i].z; ag1[i].w += d.w * xh[i].w;
+        ab1[i].x += d.x; ab1[i].y += d.y; ab1[i].z += d.z; ab1[i].w += d.w;
+      }
+      s1 = warp_sum(s1) / (float)D;
+      s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        R.a[i].x += R.rs * (gg[i].x - s1 - xh[i].x * s2); R.a[i].y += R.rs * (gg[i].y - s1 - xh[i].y * s2);
+        R.a[i].z += R.rs * (gg[i].z - s1 - xh[i].z * s2); R.a[i].w += R.rs * (gg[i].w - s1 - xh[i].w * s2);
+      }
+    }
+    if (drop.thresh != 0) {
+      const uint32_t rk = drop_row_key(drop, (uint32_t)r);
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        float dm[4];
+        drop4(drop, rk, (uint32_t)(4 * (lane + 32 * i)), dm);
+        R.a[i].x *= dm[0]; R.a[i].y *= dm[1]; R.a[i].z *= dm[2]; R.a[i].w *= dm[3];
+      }
+    }
+  };
   // the warps' partial sums `acc` -> out0 (and out1): one atomicAdd per column and call
   auto flush = [&](const float4* acc, float* out0, float* out1) {
     __syncthreads();
@@ -296,18 +362,7 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const flo
       if (out1 != nullptr) atomicAdd(out1 + c, t);
     }
   };
-  auto zero = [&](float4* acc) {
-#pragma unroll
-    for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  // LayerNorm partial sums live across every item of this (persistent) CTA: one flush per CTA at the end
-  float4 ag[LN ? NV4 : 1], ab[LN ? NV4 : 1], ax[LN ? NV4 : 1], gm[LN ? NV4 : 1];
-  if constexpr (LN) {
-    zero(ag); zero(ab); zero(ax);
-#pragma unroll
-    for (int i = 0; i < NV4; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(ln.gamma) + lane + 32 * i);
-  }
-  struct Raw { float4 a[NV4], u[NV4], x[LN ? NV4 : 1]; float mu, rs; };
+  struct Raw { Row a, u; float4 x[LN ? NV4 : 1]; float mu, rs; };
   const int items = S1 * nchunk;
 #pragma unroll 1
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -321,10 +376,12 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const flo
         const int qs = mode == 0 ? 1 : q;
         zero(acc);
         for (int b = b0 + w; b < b1; b += 8) {
-          const size_t a = row(qs, b, 0);
-          const uint32_t ka = rkey(a);
+          const size_t r = row(qs, b, 0);
+          Row R;
+          load_row(r, R);
+          finish_row(r, R);
 #pragma unroll
-          for (int i = 0; i < NV4; ++i) { const float4 v = ldrow(a, ka, lane + 32 * i); acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w; }
+          for (int i = 0; i < NV4; ++i) { acc[i].x += R.a[i].x; acc[i].y += R.a[i].y; acc[i].z += R.a[i].z; acc[i].w += R.a[i].w; }
         }
         flush(acc, dpos, q == 0 ? dtokA : dtokB);
       }
@@ -332,27 +389,27 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const flo
     }
     zero(acc);
     auto load = [&](int b, Raw& R) {
-      const size_t a = row(0, b, j), c2 = mode == 1 ? 0 : row(1, b, j);
-      const uint32_t ka = rkey(a), k2 = mode == 1 ? 0u : rkey(c2);
-      const size_t wid = (size_t)b * np + (j - 1);
+      load_row(row(0, b, j), R.a);
+      if (mode != 1) load_row(row(1, b, j), R.u);
+      if constexpr (LN) {
+        const size_t wid = (size_t)b * np + (j - 1);
 #pragma unroll
-      for (int i = 0; i < NV4; ++i) {
-        R.a[i] = ldrow(a, ka, lane + 32 * i);
-        if (mode != 1) R.u[i] = ldrow(c2, k2, lane + 32 * i);
-        if constexpr (LN) R.x[i] = __ldg(reinterpret_cast<const float4*>(ln.e0 + wid * D) + lane + 32 * i);
+        for (int i = 0; i < NV4; ++i) R.x[i] = __ldg(reinterpret_cast<const float4*>(ln.e0 + wid * D) + lane + 32 * i);
+        R.mu = __ldg(ln.mean + wid); R.rs = __ldg(ln.rstd + wid);
       }
-      if constexpr (LN) { R.mu = __ldg(ln.mean + wid); R.rs = __ldg(ln.rstd + wid); }
     };
-    auto process = [&](int b, const Raw& R) {
+    auto process = [&](int b, Raw& R) {
       const size_t wid = (size_t)b * np + (j - 1);
+      finish_row(row(0, b, j), R.a);
+      if (mode != 1) finish_row(row(1, b, j), R.u);
       float4 v[NV4];
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
         const int c = lane + 32 * i;
-        v[i] = R.a[i];
+        v[i] = R.a.a[i];
         float4 pz = v[i];                                  // what this position's dpos receives
         if (mode != 1) {
-          const float4 u = R.u[i];
+          const float4 u = R.u.a[i];
           v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
           pz = mode == 0 ? u : v[i];                       // mode 0: only the exploitative pass adds the positional embedding
         }
@@ -389,14 +446,23 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const flo
         }
       }
     };
-    // two samples per warp in flight: the second one's rows are requested before the first one is reduced
-    for (int b = b0 + w; b < b1; b += 16) {
-      Raw A, Bn;
-      load(b, A);
-      const bool two = b + 8 < b1;
-      if (two) load(b + 8, Bn);
-      process(b, A);
-      if (two) process(b + 8, Bn);
+    if constexpr (L1) {
+      // one sample per warp in flight: a sample is 6 KB of operands here (two token rows with their LayerNorm-1 operands)
+      for (int b = b0 + w; b < b1; b += 8) {
+        Raw A;
+        load(b, A);
+        process(b, A);
+      }
+    } else {
+      // two samples per warp in flight: the second one's rows are requested before the first one is reduced
+      for (int b = b0 + w; b < b1; b += 16) {
+        Raw A, Bn;
+        load(b, A);
+        const bool two = b + 8 < b1;
+        if (two) load(b + 8, Bn);
+        process(b, A);
+        if (two) process(b + 8, Bn);
+      }
     }
     flush(acc, dpos + (size_t)j * D, nullptr);
   }
@@ -404,6 +470,10 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_fused_kernel(const flo
     flush(ag, ln.dgamma, nullptr);
     flush(ab, ln.dbeta, nullptr);
     if (ln.dbias != nullptr) flush(ax, ln.dbias, nullptr);
+  }
+  if constexpr (L1) {
+    flush(ag1, l1.dgamma, nullptr);
+    flush(ab1, l1.dbeta, nullptr);
   }
 }
 
@@ -513,7 +583,7 @@ int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, fl
   if (fused && D % 128 == 0 && D <= 1024) {
     // enough CTAs for a few waves, at least 8 samples per warp-pass so that the partial sums amortise their flush
     const EabGrid eg = eab_grid(B, np);
-#define EAVIT_EAB(NV) embed_assemble_bwd_fused_kernel<NV, false><<<eg.grid, 256, 0, st>>>(dx, mode, B, np, g, (__nv_bfloat16*)g_bf16, dpos, dtokA, dtokB, eg.bchunk, eg.nchunk, EmbedLnBwd{}, make_drop(0.f, 0))
+#define EAVIT_EAB(NV) embed_assemble_bwd_fused_kernel<NV, false, false><<<eg.grid, 256, 0, st>>>(dx, mode, B, np, g, (__nv_bfloat16*)g_bf16, dpos, dtokA, dtokB, eg.bchunk, eg.nchunk, EmbedLnBwd{}, EmbedLn1Bwd{}, make_drop(0.f, 0))
     switch (D / 128) {
       case 1: EAVIT_EAB(1); break; case 2: EAVIT_EAB(2); break; case 3: EAVIT_EAB(3); break; case 4: EAVIT_EAB(4); break;
       case 5: EAVIT_EAB(5); break; case 6: EAVIT_EAB(6); break; case 7: EAVIT_EAB(7); break; default: EAVIT_EAB(8); break;
@@ -541,15 +611,23 @@ int eavit_patch_ln_fold_bwd(const float* G, const float* s, const float* W, cons
 int eavit_embed_assemble_ln_bwd(const float* dx, int mode, int B, int np, int D, const float* e0, const float* mean,
                                 const float* rstd, const float* gamma, void* de_bf16, float* dgamma, float* dbeta, float* dbias,
                                 float* dpos, float* dtokA, float* dtokB, float drop_p, unsigned long long drop_seed,
-                                void* stream) {
+                                const void* l1_dy_bf16, const float* l1_x, const float* l1_mean, const float* l1_rstd,
+                                const float* l1_gamma, float* l1_dgamma, float* l1_dbeta, void* stream) {
   EAVIT_CHECK_ARG(dx && e0 && mean && rstd && gamma && de_bf16 && dgamma && dbeta && dpos && dtokA && B > 0 && np > 0);
+  EAVIT_CHECK_ARG(l1_dy_bf16 == nullptr || (l1_x && l1_mean && l1_rstd && l1_gamma && l1_dgamma && l1_dbeta));
   EAVIT_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || dtokB != nullptr));
   EAVIT_CHECK_ARG(D == 256);                         // the row a warp holds (2 x float4 per lane); other widths: the two separate calls
   const EabGrid eg = eab_grid(B, np);
   const EmbedLnBwd ln{e0, mean, rstd, gamma, dgamma, dbeta, dbias};
-  embed_assemble_bwd_fused_kernel<2, true><<<eg.grid, 256, 0, (cudaStream_t)stream>>>(dx, mode, B, np, nullptr, (__nv_bfloat16*)de_bf16, dpos,
-                                                                                     dtokA, dtokB, eg.bchunk, eg.nchunk, ln,
-                                                                                     make_drop(drop_p, drop_seed));
+  const EmbedLn1Bwd l1{(const __nv_bfloat16*)l1_dy_bf16, l1_x, l1_mean, l1_rstd, l1_gamma, l1_dgamma, l1_dbeta};
+  if (l1_dy_bf16 != nullptr)
+    embed_assemble_bwd_fused_kernel<2, true, true><<<eg.grid, 256, 0, (cudaStream_t)stream>>>(dx, mode, B, np, nullptr, (__nv_bfloat16*)de_bf16,
+                                                                                             dpos, dtokA, dtokB, eg.bchunk, eg.nchunk, ln, l1,
+                                                                                             make_drop(drop_p, drop_seed));
+  else
+    embed_assemble_bwd_fused_kernel<2, true, false><<<eg.grid, 256, 0, (cudaStream_t)stream>>>(dx, mode, B, np, nullptr, (__nv_bfloat16*)de_bf16,
+                                                                                              dpos, dtokA, dtokB, eg.bchunk, eg.nchunk, ln, l1,
+                                                                                              make_drop(drop_p, drop_seed));
   EAVIT_LAUNCH_OK();
   return EAVIT_OK;
 }

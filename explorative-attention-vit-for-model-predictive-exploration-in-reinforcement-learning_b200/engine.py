@@ -221,6 +221,7 @@ class ViTEncoder:
         # identical loss and gradients, a third of the ViT's token-wise work and one of three attention launches removed.
         self.prune_last = os.environ.get("EAVIT_PRUNE_LAST", "1") != "0"
         self.fuse_embed_bwd = os.environ.get("EAVIT_FUSE_EMBED_BWD", "1") != "0"
+        self.fuse_embed_ln1 = os.environ.get("EAVIT_FUSE_EMBED_LN1", "1") != "0"
         # layer parameter names
         p = prefix
         self.L = []
@@ -518,6 +519,11 @@ class ViTEncoder:
         dxn = bf.get("dxn", (T, D), torch.bfloat16)     # LN-backward input (a GEMM output): bf16 halves its traffic
         do = bf.get("do", (T, I), torch.bfloat16)
         dqkv = bf.get("dqkv", (T, 3 * I), torch.bfloat16)
+        # lucidrains, dim 256: the embedding backward is one pass that can also run layer 0's pre-attention LayerNorm backward on
+        # the rows it reads (eavit_embed_assemble_ln_bwd, l1_* arguments) -- that LayerNorm's launch and the fp32 [T, D] gradient
+        # between the two kernels disappear
+        fuse_l1 = c.impl == "lucidrains" and D == 256 and self.fuse_embed_bwd and self.fuse_embed_ln1
+        l1_args = None
         for li in reversed(range(c.depth)):
             L = self.L[li]
             x_in = bf.t["x0"] if li == 0 else bf.t[f"x_{li}"]
@@ -555,8 +561,13 @@ class ViTEncoder:
             linear_bwd(dqkv, bf.t[f"xn1_{li}"], self._qkv(L, "w16"), dW=self._qkv(L, "gw"), db=self._qkv(L, "gb"), dx_bf16=dxn)
             db2_prev = s.g(self.L[li - 1]["b2"]) if li > 0 else None      # dx of this LN is the output gradient of layer li-1's MLP2
             pf, sf = self._site(bf, li - 1, self.SITE_FF_OUT) if li > 0 else (0.0, 0)   # dx16 / db2: layer li-1's MLP2 output
+            if li == 0 and fuse_l1:
+                # deferred into the embedding backward; `dx` stays the residual gradient at this LayerNorm's input
+                l1_args = (dxn, x_in, bf.t["m1_0"], bf.t["r1_0"], s.w(L["ln1"][0]), s.g(L["ln1"][0]), s.g(L["ln1"][1]))
+                continue
+            # (layer 0 has no MLP2 below it: nobody reads the bf16 copy)
             call("eavit_layernorm_bwd", dxn, BF16, D, x_in, D, bf.t[f"m1_{li}"], bf.t[f"r1_{li}"], s.w(L["ln1"][0]),
-                 dx, D, dx_other, D, dx16, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, pf, sf, T, D)
+                 dx, D, dx_other, D, dx16 if li > 0 else None, D, s.g(L["ln1"][0]), s.g(L["ln1"][1]), db2_prev, pf, sf, T, D)
             dx, dx_other = dx_other, dx
             if on_layer_done is not None:
                 on_layer_done(li)
@@ -584,7 +595,9 @@ class ViTEncoder:
                 call("eavit_embed_assemble_ln_bwd", dx, self.mode, B, np_, D, bf.t["e0"], bf.t["m3"], bf.t["r3"],
                      s.w(p + "to_patch_embedding.3.weight"), de16, s.g(p + "to_patch_embedding.3.weight"),
                      s.g(p + "to_patch_embedding.3.bias"), sv if fold else s.g(p + "to_patch_embedding.2.bias"),
-                     s.g(p + "pos_embedding"), s.g(tok), None, pe, se)
+                     s.g(p + "pos_embedding"), s.g(tok), None, pe, se, *(l1_args or (None,) * 7))
+                if l1_args is not None and on_layer_done is not None:
+                    on_layer_done(0)
             else:
                 g = bf.get("g_embed", (rows, D), torch.float32)
                 call("eavit_embed_assemble_bwd", dx, self.mode, B, np_, D, g, None, s.g(p + "pos_embedding"), s.g(tok), None)

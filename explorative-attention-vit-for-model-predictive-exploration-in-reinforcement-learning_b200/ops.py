@@ -260,7 +260,7 @@ _SPECS = {
     "eavit_embed_fused_fwd": "pipiiiii" "ppf" "pp" "ppf" "pp" "ppp" "ppp" "p" "i",
     "eavit_patch_ln_fold_bwd": "ppppp" "pppp" "ii",
     "eavit_embed_assemble_bwd": "piiiippppp",
-    "eavit_embed_assemble_ln_bwd": "piiii" "pppp" "pppp" "ppp" "fu",
+    "eavit_embed_assemble_ln_bwd": "piiii" "pppp" "pppp" "ppp" "fu" "ppppppp",
     "eavit_sgemm_small": "pliplippplliiii".replace("ll", "l", 0),
     "eavit_heads_value_fwd": "ppppppiiip",
     "eavit_heads_value_bwd": "pppppiiipppppp",

@@ -267,11 +267,17 @@ int eavit_embed_assemble_bwd(const float* dx, int mode, int B, int np, int D, fl
  * gradient stays in registers, de_bf16 [B*np, D] = LayerNorm'(g) (the dY operand of the patch Linear's dW / dX GEMMs),
  * dgamma / dbeta += that LayerNorm's parameter gradients, dbias (may be NULL) += column sums of de = the Linear's bias gradient
  * (vit.py:112).  e0 / mean / rstd: the LayerNorm's input and statistics as the forward stored them.  drop_p > 0: dx is read
- * under the embedding-dropout mask of the forward (vit.py:158; rows = flat token rows) instead of being masked in place first. */
+ * under the embedding-dropout mask of the forward (vit.py:158; rows = flat token rows) instead of being masked in place first.
+ * l1_dy_bf16 != NULL: the backward of the FIRST transformer layer's pre-attention LayerNorm (vit.py:47, layer 0) runs in front of
+ * the pass: dx then is the residual gradient at that LayerNorm's input and the embedding-output gradient is formed per row as
+ * dx + LN1'(l1_dy) (l1_dy = the QKV dX GEMM's bf16 output [T, D], l1_x = the embedding output, l1_mean / l1_rstd its
+ * statistics); l1_dgamma / l1_dbeta += that LayerNorm's parameter gradients.  Replaces one eavit_layernorm_bwd over [T, D] and the
+ * fp32 [T, D] round trip between the two kernels. */
 int eavit_embed_assemble_ln_bwd(const float* dx, int mode, int B, int np, int D, const float* e0, const float* mean,
                                 const float* rstd, const float* gamma, void* de_bf16, float* dgamma, float* dbeta, float* dbias,
                                 float* dpos, float* dtokA, float* dtokB, float drop_p, unsigned long long drop_seed,
-                                void* stream);
+                                const void* l1_dy_bf16, const float* l1_x, const float* l1_mean, const float* l1_rstd,
+                                const float* l1_gamma, float* l1_dgamma, float* l1_dbeta, void* stream);
 
 /* ------------------------------------------------------------------ heads + losses (model.py, agents.py) */
 

@@ -146,12 +146,15 @@ def test_embed_assemble_bwd_single_pass(mode, B, np_, D):
         assert torch.equal(dtb, dtb0)
 
 
+@pytest.mark.parametrize("l1", [False, True])
 @pytest.mark.parametrize("mode,B,np_,p", [(0, 5, 196, 0.0), (1, 7, 196, 0.0), (0, 70, 16, 0.1), (1, 9, 49, 0.25), (0, 512, 196, 0.0),
                                           (0, 512, 196, 0.1)])
-def test_embed_assemble_ln_bwd_single_pass(mode, B, np_, p):
+def test_embed_assemble_ln_bwd_single_pass(mode, B, np_, p, l1):
     """The same pass continued through the LayerNorm(256) that ends to_patch_embedding (vit.py:113): de, dgamma, dbeta, the
     Linear's bias gradient and the positional / token gradients against torch autograd in float64.  p > 0: dx is read under the
-    embedding-dropout mask (vit.py:158) -- the reference multiplies dx by the materialised mask first."""
+    embedding-dropout mask (vit.py:158) -- the reference multiplies dx by the materialised mask first.  l1: layer 0's
+    pre-attention LayerNorm backward (vit.py:47) runs in front of the pass -- the gradient of the embedding output is
+    dres + LN1'(dy), formed per row inside the kernel; its dgamma / dbeta are checked too."""
     from eavit_b200 import ops
     from eavit_b200.ops import call
     seed = 0x1234_5678_9ABC_DEF0 + B
@@ -170,14 +173,33 @@ def test_embed_assemble_ln_bwd_single_pass(mode, B, np_, p):
     dpos = torch.randn(S1, D, device="cuda", generator=g)
     dtok = torch.randn(D, device="cuda", generator=g)
     base = [t.double().clone() for t in (dgam, dbet, dbias, dpos, dtok)]
+    l1_args = (None,) * 7
+    if l1:
+        dy1 = torch.randn(T, D, device="cuda", generator=g).bfloat16()
+        x1 = torch.randn(T, D, device="cuda", generator=g) * 0.8 - 0.2
+        gam1 = torch.randn(D, device="cuda", generator=g)
+        m1 = x1.double().mean(1)
+        r1 = (x1.double().var(1, unbiased=False) + 1e-5).rsqrt()
+        dg1, db1 = torch.randn(D, device="cuda", generator=g), torch.randn(D, device="cuda", generator=g)
+        base1 = [dg1.double().clone(), db1.double().clone()]
+        l1_args = (dy1, x1, m1.float(), r1.float(), gam1, dg1, db1)
     call("eavit_embed_assemble_ln_bwd", dx, mode, B, np_, D, e0, mean.float(), rstd.float(), gamma, de16, dgam, dbet, dbias,
-         dpos, dtok, None, float(p), seed)
+         dpos, dtok, None, float(p), seed, *l1_args)
     torch.cuda.synchronize()
     d = dx.double()
+    if l1:
+        x1d = x1.double().requires_grad_(True)
+        g1d = gam1.double().requires_grad_(True)
+        b1d = torch.zeros(D, dtype=torch.float64, device="cuda", requires_grad=True)
+        torch.nn.functional.layer_norm(x1d, (D,), g1d, b1d, 1e-5).backward(dy1.double())
+        d = d + x1d.grad                                                         # dres + LN1'(dy)
+        for got, b0, ref in ((dg1, base1[0], g1d.grad), (db1, base1[1], b1d.grad)):
+            err = (got.double() - b0 - ref).abs().max().item()
+            assert err < 2e-5 * max(1.0, ref.abs().max().item()) * max(1.0, T ** 0.5 / 30), (err, ref.abs().max().item())
     if p > 0:
         m = ops.dropout_mask(T, D, p, seed)
         assert 0.5 * p < float((m == 0).float().mean()) < 1.5 * p
-        d = (dx * m).double()                                                     # one fp32 multiply, as in the kernel
+        d = d * m.double()
     if mode == 0:
         a, b = d[: B * np_].view(B, np_, D), d[B * np_:].view(B, S1, D)
         gg, ref_pos, ref_tok = (a + b[:, 1:]).reshape(rows, D), b.sum(0), b[:, 0].sum(0)
