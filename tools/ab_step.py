@@ -18,7 +18,7 @@ import bench  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("configs", nargs="+", help="attr=value[,attr=value] per configuration (encoder attributes; ints)")
+    ap.add_argument("configs", nargs="+", help="attr=value[,attr=value] per configuration (encoder attributes, ints; env:NAME=value for environment switches)")
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--rounds", type=int, default=3)
     a = ap.parse_args()
@@ -42,6 +42,9 @@ def main():
         for c in a.configs:
             for kv in c.split(","):
                 k, v = kv.split("=")
+                if k.startswith("env:"):                      # an environment switch read when the step is captured
+                    os.environ[k[4:]] = v
+                    continue
                 assert hasattr(rt.encoder, k), k
                 setattr(rt.encoder, k, type(getattr(rt.encoder, k))(int(v)))
             agent.__dict__.pop("_step_graphs", None)
