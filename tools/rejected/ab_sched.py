@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""A/B of the step's stream scheduling switches on one GPU (cfg3 shapes, rollout resident, captured step graph).
+"""REJECTED EXPERIMENT -- needs tools/rejected/r2_stream_scheduling_switches.patch applied (the switches it toggles are not
+in the shipped code; result: profiles/r2_ab_stream_scheduling.json).
+
+A/B of the step's stream scheduling switches on one GPU (cfg3 shapes, rollout resident, captured step graph).
 
     python tools/ab_sched.py [--steps 100] [--rounds 2]
 
