@@ -239,11 +239,11 @@ __global__ void __launch_bounds__(128) embed_assemble_bwd_pos_kernel(const float
   }
 }
 
-// Both of the above in ONE pass over dx (D = 128 * NV4 <= 1024): a CTA owns one sequence position j and a chunk of samples, its
-// 8 warps take the samples in turn.  For j >= 1 a warp forms the patch-token gradient g[b, j-1] (sum over the sequences) and keeps
-// the row it has just read as its share of dpos[j]; the j = 0 CTAs only sum the token rows (dpos[0], dtokA / dtokB).  The 8 warps'
-// partial sums meet in shared memory and leave as one atomicAdd per (j, column) and chunk -- the position / token gradients no
-// longer re-read the 103 MB the separate kernel streamed with one 512-step strided loop per thread.
+// Both of the above in ONE pass over dx (D = 128 * NV4 <= 1024): a persistent grid walks (sequence position j, chunk of samples)
+// items, a CTA's 8 warps take the samples in turn.  For j >= 1 a warp forms the patch-token gradient g[b, j-1] (sum over the
+// sequences) and keeps the row it has just read as its share of dpos[j]; the j = 0 items only sum the token rows (dpos[0], dtokA /
+// dtokB).  The 8 warps' partial sums meet in shared memory and leave as one atomicAdd per (j, column) and item -- the position /
+// token gradients no longer re-read the 103 MB the separate kernel streamed with one 512-step strided loop per thread.
 //   LN = true additionally runs the backward of the LayerNorm(D) that ends to_patch_embedding (vit.py:113) on the row the
 // warp holds: g never goes to memory, de = LN'(g) leaves as bf16 (the dY operand of the patch Linear's dW / dX GEMMs), and
 // dgamma / dbeta / the Linear's bias gradient (column sums of de) join the per-CTA partial sums.
